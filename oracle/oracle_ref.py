@@ -1,0 +1,302 @@
+"""ORACLE — test infrastructure only (imported by tests/, __graft_entry__.smoke and bench.py's
+cpu_baseline / --impl reference legs; never by the product package).
+
+ctypes wrapper around ``oracle/_ref/liboracle_ref.so``: the UNMODIFIED reference sources of
+cumberworth/LatticeDNAOrigami compiled by ``oracle/Makefile`` plus the C-ABI driver
+``oracle/src/ref_driver.cpp``. See that file for the reference file:line each call follows.
+"""
+import ctypes as C
+import os
+import tempfile
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "_ref", "liboracle_ref.so")
+CLI_PATH = os.path.join(HERE, "_ref", "latticeDNAOrigami")
+
+DRAW_DTYPE = np.dtype(
+    [("kind", "<i4"), ("lo", "<i4"), ("hi", "<i4"), ("ival", "<i4"), ("real", "<f8")]
+)
+
+_lib = None
+
+
+def available():
+    return os.path.exists(LIB_PATH)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        # RTLD_DEEPBIND: the reference objects must bind to their own libstdc++ symbols even when
+        # numpy/torch preloaded other C++ runtimes into the process.
+        L = C.CDLL(LIB_PATH, mode=os.RTLD_NOW | os.RTLD_DEEPBIND)
+        L.oref_create.restype = C.c_void_p
+        L.oref_create.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_int]
+        L.oref_destroy.argtypes = [C.c_void_p]
+        L.oref_last_error.restype = C.c_char_p
+        L.oref_last_error.argtypes = [C.c_void_p]
+        L.oref_simulate.argtypes = [C.c_void_p, C.c_longlong]
+        L.oref_step.restype = C.c_longlong
+        L.oref_step.argtypes = [C.c_void_p]
+        L.oref_seed.argtypes = [C.c_void_p, C.c_int]
+        L.oref_tape_len.restype = C.c_longlong
+        L.oref_tape_len.argtypes = [C.c_void_p]
+        L.oref_tape_copy.argtypes = [C.c_void_p, C.c_void_p]
+        L.oref_tape_clear.argtypes = [C.c_void_p]
+        L.oref_tape_set_replay.argtypes = [C.c_void_p, C.c_void_p, C.c_longlong]
+        L.oref_num_movetypes.argtypes = [C.c_void_p]
+        L.oref_move_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.oref_num_chains.argtypes = [C.c_void_p]
+        L.oref_num_domains.argtypes = [C.c_void_p]
+        L.oref_get_state.argtypes = [C.c_void_p] + [C.c_void_p] * 7
+        L.oref_set_state.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 5
+        L.oref_energy.restype = C.c_double
+        L.oref_energy.argtypes = [C.c_void_p]
+        L.oref_counters.argtypes = [C.c_void_p, C.c_void_p]
+        L.oref_energy_split.argtypes = [C.c_void_p, C.c_void_p]
+        L.oref_check_all_constraints.argtypes = [C.c_void_p]
+        L.oref_center.argtypes = [C.c_void_p, C.c_int]
+        L.oref_update_temp.argtypes = [C.c_void_p, C.c_double, C.c_double]
+        L.oref_update_staple_us.argtypes = [C.c_void_p, C.c_double, C.c_double]
+        L.oref_num_staple_types.argtypes = [C.c_void_p]
+        L.oref_staple_us.argtypes = [C.c_void_p, C.c_void_p]
+        L.oref_pair_energies.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        L.oref_init_energies.argtypes = [C.c_void_p, C.c_void_p]
+        L.oref_order_param.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p]
+        L.oref_total_bias.restype = C.c_double
+        L.oref_total_bias.argtypes = [C.c_void_p]
+        L.oref_check_domain.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.oref_set_domain.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.oref_unassign_domain.restype = C.c_double
+        L.oref_unassign_domain.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.oref_nn_unitless_thermo.argtypes = [C.c_char_p, C.c_double, C.c_double, C.c_void_p]
+        L.oref_nn_unitless_energy.restype = C.c_double
+        L.oref_nn_unitless_energy.argtypes = [C.c_char_p, C.c_double, C.c_double]
+        L.oref_nn_longest_contig_complement.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_int]
+        L.oref_num_walks.restype = C.c_double
+        L.oref_num_walks.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        _lib = L
+    return _lib
+
+
+def write_inp(path, options):
+    """Write a reference-format key=value parameter file (parser.cpp:477-479)."""
+    with open(path, "w") as f:
+        for k, v in options.items():
+            if isinstance(v, bool):
+                v = "true" if v else "false"
+            elif isinstance(v, (list, tuple)):
+                v = " ".join(str(x) for x in v)
+            f.write(f"{k}={v}\n")
+
+
+# Defaults of examples/constant-temp.inp with all outputs off
+SNODIN_OPTIONS = {
+    "domain_type": "HalfTurn",
+    "binding_pot": "FourBody",
+    "misbinding_pot": "Opposing",
+    "stacking_pot": "Constant",
+    "hybridization_pot": "NearestNeighbour",
+    "apply_mean_field_cor": False,
+    "temp": 330,
+    "staple_M": 1e-7,
+    "cation_M": 0.5,
+    "staple_u_mult": 1,
+    "stacking_ene": -1000,
+    "max_total_staples": 24,
+    "max_type_staples": 12,
+    "max_staple_size": 2,
+    "domain_update_biases_present": False,
+    "simulation_type": "constant_temp",
+    "centering_freq": 0,
+    "constraint_check_freq": 0,
+    "max_duration": 1e9,
+    "ct_steps": 0,
+    "logging_freq": 0,
+    "configs_output_freq": 0,
+    "vtf_output_freq": 0,
+    "vcf_per_domain": False,
+    "counts_output_freq": 0,
+    "order_params_output_freq": 0,
+    "times_output_freq": 0,
+    "energies_output_freq": 0,
+}
+
+
+class RefSystem:
+    """One reference OrigamiSystem (+ ConstantTGCMCSimulation when with_sim)."""
+
+    def __init__(self, options, with_sim=True, workdir=None):
+        self._tmp = None
+        if workdir is None:
+            self._tmp = tempfile.TemporaryDirectory(prefix="oref_")
+            workdir = self._tmp.name
+        opts = dict(options)
+        opts.setdefault("output_filebase", os.path.join(workdir, "out"))
+        inp = os.path.join(workdir, "oracle.inp")
+        write_inp(inp, opts)
+        err = C.create_string_buffer(1024)
+        self.L = lib()
+        self.h = self.L.oref_create(inp.encode(), 1 if with_sim else 0, err, 1024)
+        if not self.h:
+            raise RuntimeError("oracle: " + err.value.decode())
+
+    def close(self):
+        if self.h:
+            self.L.oref_destroy(self.h)
+            self.h = None
+        if self._tmp is not None:
+            self._tmp.cleanup()
+            self._tmp = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc):
+        if rc != 0:
+            raise RuntimeError("oracle: " + self.L.oref_last_error(self.h).decode())
+
+    # stepping
+    def seed(self, seed):
+        self.L.oref_seed(self.h, int(seed))
+
+    def simulate(self, steps):
+        self._check(self.L.oref_simulate(self.h, int(steps)))
+
+    @property
+    def step(self):
+        return self.L.oref_step(self.h)
+
+    def tape(self, clear=False):
+        n = self.L.oref_tape_len(self.h)
+        out = np.zeros(n, dtype=DRAW_DTYPE)
+        if n:
+            self.L.oref_tape_copy(self.h, out.ctypes.data)
+        if clear:
+            self.L.oref_tape_clear(self.h)
+        return out
+
+    def set_replay(self, tape):
+        tape = np.ascontiguousarray(tape, dtype=DRAW_DTYPE)
+        self.L.oref_tape_set_replay(self.h, tape.ctypes.data, len(tape))
+
+    def move_stats(self):
+        n = self.L.oref_num_movetypes(self.h)
+        a = np.zeros(n, dtype=np.int64)
+        b = np.zeros(n, dtype=np.int64)
+        self.L.oref_move_stats(self.h, a.ctypes.data, b.ctypes.data)
+        return a, b
+
+    # state
+    def state(self):
+        nc = self.L.oref_num_chains(self.h)
+        nd = self.L.oref_num_domains(self.h)
+        ci = np.zeros(nc, dtype=np.int32)
+        cid = np.zeros(nc, dtype=np.int32)
+        cl = np.zeros(nc, dtype=np.int32)
+        pos = np.zeros((nd, 3), dtype=np.int32)
+        ore = np.zeros((nd, 3), dtype=np.int32)
+        st = np.zeros(nd, dtype=np.int32)
+        bd = np.zeros((nd, 2), dtype=np.int32)
+        self.L.oref_get_state(
+            self.h, ci.ctypes.data, cid.ctypes.data, cl.ctypes.data, pos.ctypes.data,
+            ore.ctypes.data, st.ctypes.data, bd.ctypes.data)
+        return {"chain_index": ci, "chain_ident": cid, "chain_len": cl, "pos": pos,
+                "ore": ore, "state": st, "bound": bd}
+
+    def set_state(self, chain_index, chain_ident, chain_len, pos, ore):
+        ci = np.ascontiguousarray(chain_index, dtype=np.int32)
+        cid = np.ascontiguousarray(chain_ident, dtype=np.int32)
+        cl = np.ascontiguousarray(chain_len, dtype=np.int32)
+        p = np.ascontiguousarray(pos, dtype=np.int32)
+        o = np.ascontiguousarray(ore, dtype=np.int32)
+        self._check(self.L.oref_set_state(
+            self.h, len(ci), ci.ctypes.data, cid.ctypes.data, cl.ctypes.data,
+            p.ctypes.data, o.ctypes.data))
+
+    def energy(self):
+        return self.L.oref_energy(self.h)
+
+    def counters(self):
+        out = np.zeros(9, dtype=np.int32)
+        self.L.oref_counters(self.h, out.ctypes.data)
+        keys = ["staples", "domains", "bound_pairs", "fully_bound_pairs", "self_bound_pairs",
+                "misbound_pairs", "stacked_pairs", "unassigned", "current_c_i"]
+        return dict(zip(keys, (int(x) for x in out)))
+
+    def energy_split(self):
+        out = np.zeros(3)
+        self.L.oref_energy_split(self.h, out.ctypes.data)
+        return {"enthalpy": out[0], "entropy": out[1], "stacking": out[2]}
+
+    def check_all_constraints(self):
+        self._check(self.L.oref_check_all_constraints(self.h))
+
+    def center(self, d=0):
+        self.L.oref_center(self.h, d)
+
+    def update_temp(self, temp, stacking_mult=1.0):
+        self._check(self.L.oref_update_temp(self.h, temp, stacking_mult))
+
+    def pair_energies(self, a, b):
+        out = np.zeros(4)
+        if self.L.oref_pair_energies(self.h, a, b, out.ctypes.data) != 0:
+            return None
+        return out
+
+    def init_energies(self):
+        out = np.zeros(3)
+        self.L.oref_init_energies(self.h, out.ctypes.data)
+        return out
+
+    def order_param(self, tag):
+        v = C.c_int(0)
+        self._check(self.L.oref_order_param(self.h, tag.encode(), C.byref(v)))
+        return v.value
+
+    def total_bias(self):
+        return self.L.oref_total_bias(self.h)
+
+    def check_domain(self, c, d, pos, ore):
+        p = np.asarray(pos, dtype=np.int32)
+        o = np.asarray(ore, dtype=np.int32)
+        out = np.zeros(1)
+        v = self.L.oref_check_domain(self.h, c, d, p.ctypes.data, o.ctypes.data, out.ctypes.data)
+        return bool(v), out[0]
+
+    def set_domain(self, c, d, pos, ore):
+        p = np.asarray(pos, dtype=np.int32)
+        o = np.asarray(ore, dtype=np.int32)
+        out = np.zeros(1)
+        v = self.L.oref_set_domain(self.h, c, d, p.ctypes.data, o.ctypes.data, out.ctypes.data)
+        return bool(v), out[0]
+
+    def unassign_domain(self, c, d):
+        return self.L.oref_unassign_domain(self.h, c, d)
+
+
+def nn_unitless_thermo(seq, temp, cation_M):
+    out = np.zeros(2)
+    lib().oref_nn_unitless_thermo(seq.encode(), temp, cation_M, out.ctypes.data)
+    return out[0], out[1]
+
+
+def nn_unitless_energy(seq, temp, cation_M):
+    return lib().oref_nn_unitless_energy(seq.encode(), temp, cation_M)
+
+
+def nn_longest_contig_complement(a, b):
+    buf = C.create_string_buffer(4096)
+    lib().oref_nn_longest_contig_complement(a.encode(), b.encode(), buf, 4096)
+    return [s for s in buf.value.decode().split("\n") if s]
+
+
+def num_walks(start, end, steps):
+    s = np.asarray(start, dtype=np.int32)
+    e = np.asarray(end, dtype=np.int32)
+    return lib().oref_num_walks(s.ctypes.data, e.ctypes.data, steps)

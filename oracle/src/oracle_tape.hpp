@@ -1,0 +1,20 @@
+// ORACLE — test infrastructure only. Value-level RNG tape shared by
+// tape_random_gens.cpp and ref_driver.cpp.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <vector>
+namespace oracle_tape {
+struct Draw {
+    int32_t kind; // 0 = uniform_real, 1 = uniform_int
+    int32_t lo;
+    int32_t hi;
+    int32_t ival;
+    double real;
+};
+using Tape = std::vector<Draw>;
+extern thread_local Tape* g_record;
+extern thread_local Tape* g_replay;
+extern thread_local size_t g_replay_pos;
+extern thread_local bool g_quiet_seed;
+} // namespace oracle_tape

@@ -1,0 +1,418 @@
+// ORACLE — test infrastructure only; never linked into the product library.
+//
+// C-ABI driver around the UNMODIFIED reference sources (compiled in place from
+// /root/reference by oracle/Makefile into oracle/_ref/liboracle_ref.so). It drives the
+// reference exactly as apps/main.cpp:19-99 does (InputParameters(argc, argv) ->
+// origami::setup_origami -> ConstantTGCMCSimulation) and exposes
+//   * configuration, counters, energy and its enthalpy/entropy/stacking split,
+//   * GCMCSimulation::simulate() (simulation.cpp:568-653) in caller-sized chunks,
+//   * the value-level RNG tape recorded by tape_random_gens.cpp (record / replay),
+//   * per-movetype attempt / accept counters (movetypes.hpp:49-52),
+//   * leaf functions pinned by the reference's own tests (nearest_neighbour.cpp, ideal_random_walk.cpp),
+//   * the temperature-replica-exchange acceptance rule (ptmc_simulation.cpp:275-313).
+// Built with -fno-access-control so protected members can be read; nothing is modified.
+
+#include <cstring>
+#include <fstream>
+#include <iostream>
+#include <sstream>
+#include <string>
+#include <vector>
+
+#include "LatticeDNAOrigami/bias_functions.hpp"
+#include "LatticeDNAOrigami/constant_temp_simulation.hpp"
+#include "LatticeDNAOrigami/domain.hpp"
+#include "LatticeDNAOrigami/files.hpp"
+#include "LatticeDNAOrigami/ideal_random_walk.hpp"
+#include "LatticeDNAOrigami/movetypes.hpp"
+#include "LatticeDNAOrigami/nearest_neighbour.hpp"
+#include "LatticeDNAOrigami/order_params.hpp"
+#include "LatticeDNAOrigami/origami_system.hpp"
+#include "LatticeDNAOrigami/parser.hpp"
+#include "LatticeDNAOrigami/simulation.hpp"
+#include "oracle_tape.hpp"
+
+using domainContainer::Domain;
+using utility::Occupancy;
+using utility::VectorThree;
+
+namespace {
+
+struct Handle {
+    parser::InputParameters* params {nullptr};
+    origami::OrigamiSystem* origami {nullptr};
+    constantTemp::ConstantTGCMCSimulation* sim {nullptr};
+    oracle_tape::Tape tape {};
+    oracle_tape::Tape replay {};
+    long long step {0};
+    std::string err {};
+};
+
+void set_err(char* err, int errlen, std::string const& msg) {
+    if (err != nullptr and errlen > 0) {
+        std::strncpy(err, msg.c_str(), errlen - 1);
+        err[errlen - 1] = 0;
+    }
+}
+
+// Silence the reference's std::cout chatter while inside the driver
+struct CoutSilencer {
+    std::streambuf* old;
+    std::ostringstream sink;
+    CoutSilencer(): old {std::cout.rdbuf(sink.rdbuf())} {}
+    ~CoutSilencer() { std::cout.rdbuf(old); }
+};
+
+int state_code(Occupancy s) {
+    switch (s) {
+    case Occupancy::unassigned: return 0;
+    case Occupancy::unbound: return 1;
+    case Occupancy::bound: return 2;
+    case Occupancy::misbound: return 3;
+    }
+    return -1;
+}
+
+} // namespace
+
+extern "C" {
+
+void* oref_create(const char* inp_path, int with_sim, char* err, int errlen) {
+    auto h = new Handle {};
+    try {
+        CoutSilencer quiet {};
+        std::string a0 {"oracle"}, a1 {"-i"}, a2 {inp_path};
+        char* argv[] {&a0[0], &a1[0], &a2[0]};
+        h->params = new parser::InputParameters {3, argv};
+        h->origami = origami::setup_origami(*h->params);
+        if (with_sim) {
+            oracle_tape::g_record = nullptr;
+            oracle_tape::g_replay = nullptr;
+            h->sim = new constantTemp::ConstantTGCMCSimulation {
+                    *h->origami,
+                    h->origami->get_system_order_params(),
+                    h->origami->get_system_biases(),
+                    *h->params};
+            h->sim->m_logging_stream = new std::ostringstream {};
+        }
+    } catch (std::exception const& e) {
+        set_err(err, errlen, e.what());
+        delete h;
+        return nullptr;
+    }
+    return h;
+}
+
+void oref_destroy(void* vh) {
+    auto h = static_cast<Handle*>(vh);
+    CoutSilencer quiet {};
+    delete h->sim;
+    delete h->origami;
+    delete h->params;
+    delete h;
+}
+
+const char* oref_last_error(void* vh) { return static_cast<Handle*>(vh)->err.c_str(); }
+
+// ---- stepping -----------------------------------------------------------------------
+
+// Runs `steps` MC steps (simulation.cpp:568). Draws are appended to the handle's tape;
+// when a replay tape is installed they are served from it. Returns 0 or -1 (see last_error).
+int oref_simulate(void* vh, long long steps) {
+    auto h = static_cast<Handle*>(vh);
+    try {
+        CoutSilencer quiet {};
+        oracle_tape::g_record = &h->tape;
+        long long next {h->sim->simulate(steps, h->step, false)};
+        h->step = next - 1;
+        oracle_tape::g_record = nullptr;
+    } catch (std::exception const& e) {
+        oracle_tape::g_record = nullptr;
+        h->err = e.what();
+        return -1;
+    }
+    return 0;
+}
+
+long long oref_step(void* vh) { return static_cast<Handle*>(vh)->step; }
+
+void oref_seed(void* vh, int seed) {
+    static_cast<Handle*>(vh)->sim->m_random_gens.set_seed(seed);
+}
+
+long long oref_tape_len(void* vh) { return static_cast<Handle*>(vh)->tape.size(); }
+
+void oref_tape_copy(void* vh, oracle_tape::Draw* out) {
+    auto h = static_cast<Handle*>(vh);
+    std::memcpy(out, h->tape.data(), h->tape.size() * sizeof(oracle_tape::Draw));
+}
+
+void oref_tape_clear(void* vh) { static_cast<Handle*>(vh)->tape.clear(); }
+
+void oref_tape_set_replay(void* vh, oracle_tape::Draw const* draws, long long n) {
+    auto h = static_cast<Handle*>(vh);
+    h->replay.assign(draws, draws + n);
+    oracle_tape::g_replay = n > 0 ? &h->replay : nullptr;
+    oracle_tape::g_replay_pos = 0;
+}
+
+int oref_num_movetypes(void* vh) { return static_cast<Handle*>(vh)->sim->m_movetypes.size(); }
+
+void oref_move_stats(void* vh, long long* attempts, long long* accepts) {
+    auto h = static_cast<Handle*>(vh);
+    for (size_t i {0}; i != h->sim->m_movetypes.size(); i++) {
+        attempts[i] = h->sim->m_movetypes[i]->get_attempts();
+        accepts[i] = h->sim->m_movetypes[i]->get_accepts();
+    }
+}
+
+// ---- state ----------------------------------------------------------------------------
+
+int oref_num_chains(void* vh) { return static_cast<Handle*>(vh)->origami->m_domains.size(); }
+
+int oref_num_domains(void* vh) { return static_cast<Handle*>(vh)->origami->num_domains(); }
+
+// Working-order chains (origami_system.cpp:173-191). pos/ore are 3 ints per domain,
+// state per domain (0 unassigned, 1 unbound, 2 bound, 3 misbound), bound = (chain index, domain) or -1,-1.
+void oref_get_state(
+        void* vh,
+        int* chain_index,
+        int* chain_ident,
+        int* chain_len,
+        int* pos,
+        int* ore,
+        int* state,
+        int* bound) {
+    auto h = static_cast<Handle*>(vh);
+    auto& o {*h->origami};
+    size_t k {0};
+    for (size_t i {0}; i != o.m_domains.size(); i++) {
+        chain_index[i] = o.m_chain_indices[i];
+        chain_ident[i] = o.m_chain_identities[i];
+        chain_len[i] = o.m_domains[i].size();
+        for (auto d: o.m_domains[i]) {
+            for (int a {0}; a != 3; a++) {
+                pos[3 * k + a] = d->m_pos.at(a);
+                ore[3 * k + a] = d->m_ore.at(a);
+            }
+            state[k] = state_code(d->m_state);
+            if (d->m_bound_domain != nullptr) {
+                bound[2 * k] = d->m_bound_domain->m_c;
+                bound[2 * k + 1] = d->m_bound_domain->m_d;
+            }
+            else {
+                bound[2 * k] = -1;
+                bound[2 * k + 1] = -1;
+            }
+            k++;
+        }
+    }
+}
+
+// origami_system.cpp:327-341 (set_config)
+int oref_set_state(
+        void* vh,
+        int nchains,
+        int const* chain_index,
+        int const* chain_ident,
+        int const* chain_len,
+        int const* pos,
+        int const* ore) {
+    auto h = static_cast<Handle*>(vh);
+    try {
+        origami::Chains chains {};
+        size_t k {0};
+        for (int i {0}; i != nchains; i++) {
+            origami::Chain c {};
+            c.index = chain_index[i];
+            c.identity = chain_ident[i];
+            for (int d {0}; d != chain_len[i]; d++) {
+                c.positions.push_back({pos[3 * k], pos[3 * k + 1], pos[3 * k + 2]});
+                c.orientations.push_back({ore[3 * k], ore[3 * k + 1], ore[3 * k + 2]});
+                k++;
+            }
+            chains.push_back(c);
+        }
+        h->origami->set_config(chains);
+    } catch (std::exception const& e) {
+        h->err = e.what();
+        return -1;
+    }
+    return 0;
+}
+
+double oref_energy(void* vh) { return static_cast<Handle*>(vh)->origami->energy(); }
+
+// counters: staples, domains, bound pairs, fully bound pairs, self-bound pairs, misbound pairs,
+// stacked pairs, unassigned domains, current unique chain index
+void oref_counters(void* vh, int* out) {
+    auto& o {*static_cast<Handle*>(vh)->origami};
+    out[0] = o.num_staples();
+    out[1] = o.num_domains();
+    out[2] = o.num_bound_domain_pairs();
+    out[3] = o.num_fully_bound_domain_pairs();
+    out[4] = o.num_self_bound_domain_pairs();
+    out[5] = o.num_misbound_domain_pairs();
+    out[6] = o.num_stacked_domain_pairs();
+    out[7] = o.num_unassigned_domains();
+    out[8] = o.m_current_c_i;
+}
+
+// origami_system.cpp:204-246: out = enthalpy, entropy, stacking
+void oref_energy_split(void* vh, double* out) {
+    auto& o {*static_cast<Handle*>(vh)->origami};
+    o.update_enthalpy_and_entropy();
+    out[0] = o.hybridization_enthalpy();
+    out[1] = o.hybridization_entropy();
+    out[2] = o.stacking_energy();
+}
+
+int oref_check_all_constraints(void* vh) {
+    auto h = static_cast<Handle*>(vh);
+    try {
+        h->origami->check_all_constraints();
+    } catch (std::exception const& e) {
+        h->err = e.what();
+        return -1;
+    }
+    return 0;
+}
+
+void oref_center(void* vh, int centering_domain) {
+    static_cast<Handle*>(vh)->origami->center(centering_domain);
+}
+
+// origami_system.cpp:618-628
+int oref_update_temp(void* vh, double temp, double stacking_mult) {
+    auto h = static_cast<Handle*>(vh);
+    try {
+        h->origami->update_temp(temp, stacking_mult);
+    } catch (std::exception const& e) {
+        h->err = e.what();
+        return -1;
+    }
+    return 0;
+}
+
+void oref_update_staple_us(void* vh, double temp, double mult) {
+    static_cast<Handle*>(vh)->origami->update_staple_us(temp, mult);
+}
+
+int oref_num_staple_types(void* vh) {
+    return static_cast<Handle*>(vh)->origami->m_identities.size() - 1;
+}
+
+void oref_staple_us(void* vh, double* out) {
+    auto& o {*static_cast<Handle*>(vh)->origami};
+    for (size_t i {0}; i != o.m_staple_us.size(); i++) out[i] = o.m_staple_us[i];
+}
+
+// ---- potential tables (origami_potential.cpp:1057-1221, 1319-1350) ---------------------
+
+// Returns 0 and fills out[4] = {hyb energy, hyb enthalpy, hyb entropy, stacking energy}
+// for identity pair (a, b); -1 if the pair is not tabulated.
+int oref_pair_energies(void* vh, int ident_a, int ident_b, double* out) {
+    auto& p {static_cast<Handle*>(vh)->origami->m_pot};
+    std::pair<int, int> key {ident_a, ident_b};
+    if (p.m_hybridization_energies.count(key) == 0) return -1;
+    out[0] = p.m_hybridization_energies.at(key);
+    out[1] = p.m_hybridization_enthalpies.at(key);
+    out[2] = p.m_hybridization_entropies.at(key);
+    out[3] = p.m_stacking_energies.at(key);
+    return 0;
+}
+
+void oref_init_energies(void* vh, double* out) {
+    auto& p {static_cast<Handle*>(vh)->origami->m_pot};
+    out[0] = p.init_energy();
+    out[1] = p.init_enthalpy();
+    out[2] = p.init_entropy();
+}
+
+// ---- order parameters and biases ------------------------------------------------------
+
+int oref_order_param(void* vh, const char* tag, int* value) {
+    auto h = static_cast<Handle*>(vh);
+    try {
+        auto& op {h->origami->get_system_order_params().get_order_param(tag)};
+        op.calc_param();
+        *value = op.get_param();
+    } catch (std::exception const& e) {
+        h->err = e.what();
+        return -1;
+    }
+    return 0;
+}
+
+double oref_total_bias(void* vh) {
+    auto h = static_cast<Handle*>(vh);
+    h->origami->get_system_order_params().update_move_params();
+    h->origami->get_system_biases().calc_move();
+    return h->origami->get_system_biases().get_total_bias();
+}
+
+// ---- single-domain operations (origami_system.cpp:343-385, 478-541) -------------------
+
+// Finds the domain (unique chain index c, domain index d)
+static Domain* find_domain(Handle* h, int c, int d) { return h->origami->get_domain(c, d); }
+
+// out[0] = delta energy, returns 1 if constraints violated (and clears the flag), 0 otherwise
+int oref_check_domain(void* vh, int c, int d, int const* pos, int const* ore, double* out) {
+    auto h = static_cast<Handle*>(vh);
+    Domain* dom {find_domain(h, c, d)};
+    out[0] = h->origami->check_domain_constraints(
+            *dom, {pos[0], pos[1], pos[2]}, {ore[0], ore[1], ore[2]});
+    int violated {h->origami->m_constraints_violated ? 1 : 0};
+    h->origami->m_constraints_violated = false;
+    return violated;
+}
+
+int oref_set_domain(void* vh, int c, int d, int const* pos, int const* ore, double* out) {
+    auto h = static_cast<Handle*>(vh);
+    Domain* dom {find_domain(h, c, d)};
+    out[0] = h->origami->set_domain_config(
+            *dom, {pos[0], pos[1], pos[2]}, {ore[0], ore[1], ore[2]});
+    int violated {h->origami->m_constraints_violated ? 1 : 0};
+    h->origami->m_constraints_violated = false;
+    return violated;
+}
+
+double oref_unassign_domain(void* vh, int c, int d) {
+    auto h = static_cast<Handle*>(vh);
+    return h->origami->unassign_domain(*find_domain(h, c, d));
+}
+
+// ---- leaf functions pinned by the reference's own tests --------------------------------
+
+// nearest_neighbour.cpp:34-56 via calc_unitless_hybridization_thermo (:162-176)
+void oref_nn_unitless_thermo(const char* seq, double temp, double cation_M, double* out) {
+    auto t {nearestNeighbour::calc_unitless_hybridization_thermo(seq, temp, cation_M)};
+    out[0] = t.enthalpy;
+    out[1] = t.entropy;
+}
+
+double oref_nn_unitless_energy(const char* seq, double temp, double cation_M) {
+    return nearestNeighbour::calc_unitless_hybridization_energy(seq, temp, cation_M);
+}
+
+// nearest_neighbour.cpp:117-160; writes complements separated by '\n'
+int oref_nn_longest_contig_complement(const char* a, const char* b, char* out, int outlen) {
+    auto v {nearestNeighbour::find_longest_contig_complement(a, b)};
+    std::string s {};
+    for (auto const& x: v) {
+        s += x;
+        s += "\n";
+    }
+    std::strncpy(out, s.c_str(), outlen - 1);
+    out[outlen - 1] = 0;
+    return v.size();
+}
+
+// ideal_random_walk.cpp:14-73
+double oref_num_walks(int const* start, int const* end, int steps) {
+    idealRandomWalk::IdealRandomWalks w {};
+    return static_cast<double>(w.num_walks(
+            {start[0], start[1], start[2]}, {end[0], end[1], end[2]}, steps));
+}
+
+} // extern "C"
