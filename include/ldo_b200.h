@@ -1,0 +1,243 @@
+/* ldo_b200.h — C-ABI of the B200-native replica-batched Monte Carlo engine for the
+ * LatticeDNAOrigami model (drop-in for the MC hot path of cumberworth/LatticeDNAOrigami).
+ *
+ * The reference has no plugin/FFI seam for this path: it is one statically linked C++ binary whose
+ * internal seam is GCMCSimulation::simulate() (include/LatticeDNAOrigami/simulation.hpp:75-81,
+ * src/simulation.cpp:568-653), MCMovetype::attempt_move()/reset_origami()
+ * (include/LatticeDNAOrigami/movetypes.hpp:75-78) and the OrigamiSystem public methods
+ * (include/LatticeDNAOrigami/origami_system.hpp:99-165). Each entry point below names the reference
+ * interface it replaces. Conventions: plain C structs, caller-owned host buffers, int return codes
+ * (0 = ok, negative = error; see ldo_last_error), no exceptions cross the ABI, a handle is not
+ * thread-safe (one host thread per handle / GPU).
+ *
+ * One engine handle owns the replicas resident on one GPU; every replica is advanced by one warp.
+ */
+#ifndef LDO_B200_H
+#define LDO_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ldo_engine ldo_engine;
+
+/* ---- enumerations (values are part of the ABI) ------------------------------------------- */
+enum { LDO_DOMAIN_HALFTURN = 0, LDO_DOMAIN_THREEQUARTERTURN = 1 }; /* origami_system.cpp:415-422 */
+enum { LDO_MISBIND_OPPOSING = 0, LDO_MISBIND_DISALLOWED = 1 };     /* origami_potential.cpp:978-987 */
+
+enum { /* movetype "type" strings of the moveset JSON (simulation.cpp:283-318) */
+    LDO_MT_ORIENTATION_ROTATION = 0,
+    LDO_MT_MET_STAPLE_EXCHANGE = 1,
+    LDO_MT_MET_STAPLE_REGROWTH = 2,
+    LDO_MT_CB_STAPLE_REGROWTH = 3,
+    LDO_MT_CTCB_SCAFFOLD_REGROWTH = 4,
+    LDO_MT_CTCB_JUMP_SCAFFOLD_REGROWTH = 5,
+    LDO_MT_CTRG_SCAFFOLD_REGROWTH = 6,
+    LDO_MT_CTRG_JUMP_SCAFFOLD_REGROWTH = 7
+};
+
+enum { /* order parameter "type" strings (order_params.cpp:471-545) */
+    LDO_OP_NUM_STAPLES = 0,
+    LDO_OP_NUM_STAPLES_TYPE = 1,
+    LDO_OP_STAPLE_TYPE_FULLY_BOUND = 2,
+    LDO_OP_NUM_BOUND_DOMAIN_PAIRS = 3,
+    LDO_OP_NUM_MISBOUND_DOMAIN_PAIRS = 4,
+    LDO_OP_NUM_STACKED_PAIRS = 5,
+    LDO_OP_NUM_LINEAR_HELICES = 6,
+    LDO_OP_NUM_STACKED_JUNCTS = 7,
+    LDO_OP_SUM = 8
+};
+
+enum { /* bias function "type" strings (bias_functions.cpp:366-413) */
+    LDO_BIAS_LINEAR_STEP_WELL = 0,
+    LDO_BIAS_SQUARE_WELL = 1,
+    LDO_BIAS_GRID = 2
+};
+
+enum { /* replica exchange variants (ptmc_simulation.cpp:595-680) */
+    LDO_PT_T = 0,   /* t_parallel_tempering   : temperature                        */
+    LDO_PT_UT = 1,  /* ut_parallel_tempering  : temperature + staple chem. pot.    */
+    LDO_PT_HUT = 2, /* hut_parallel_tempering : + bias multiplier                  */
+    LDO_PT_ST = 3   /* st_parallel_tempering  : stacking multiplier                */
+};
+
+/* ---- descriptors -------------------------------------------------------------------------- */
+
+/* System topology and potential selectors: what origami::setup_origami (origami_system.cpp:991-1031)
+ * hands to the OrigamiSystem / OrigamiPotential constructors (origami_system.cpp:41-71,
+ * origami_potential.cpp:952-1013), minus sequences (those only feed the host-side table builder). */
+typedef struct {
+    int n_types;           /* chain identities, scaffold (identity 0) included */
+    const int* type_len;   /* [n_types] domains per chain identity */
+    const int* idents;     /* flattened domain identities, type-major (m_identities) */
+    int cyclic;
+    int domain_type;       /* LDO_DOMAIN_* */
+    int misbinding_pot;    /* LDO_MISBIND_* */
+    int apply_mean_field_cor;
+    int max_total_staples; /* parser.cpp: max_total_staples */
+    int max_type_staples;
+    int max_staple_size;
+    double staple_M;       /* reduced fugacity (origami_system.cpp:58) */
+    double stacking_ene;   /* Constant stacking potential, kb K (origami_potential.cpp:1219-1221) */
+} ldo_system_desc;
+
+typedef struct {
+    int type;            /* LDO_MT_* */
+    double freq;         /* "freq" of the moveset JSON; cumulated as simulation.cpp:233-237 */
+    int max_regrowth;    /* simulation.cpp:411,530 */
+    int max_seg_regrowth;
+    int max_num_recoils; /* simulation.cpp:528 */
+    int max_c_attempts;  /* simulation.cpp:529 */
+    int adaptive_exchange;
+    int n_exchange_mults;
+    const double* exchange_mults; /* simulation.cpp:349-352 */
+} ldo_movetype_desc;
+
+typedef struct {
+    int type;    /* LDO_OP_* */
+    int staple;  /* "staple" option of NumStaplesType / StapleTypeFullyBound */
+    int n_sum;   /* Sum: indices of earlier order parameters */
+    const int* sum_ops;
+} ldo_order_param_desc;
+
+typedef struct {
+    int type;   /* LDO_BIAS_* */
+    int n_ops;  /* 1 for the wells, 1..3 for Grid */
+    const int* ops; /* indices into the order-parameter list */
+    int min_op, max_op;
+    double well_bias, min_bias, slope, outside_bias;
+} ldo_bias_desc;
+
+/* One draw of the value-level replay tape; layout shared with the oracle. */
+typedef struct {
+    int kind; /* 0 = uniform_real, 1 = uniform_int */
+    int lo, hi, ival;
+    double real;
+} ldo_tape_draw;
+
+/* ---- lifetime ----------------------------------------------------------------------------- */
+
+/* Replaces: OrigamiSystem construction for n_replicas independent systems on CUDA device `device`. */
+int ldo_engine_create(const ldo_system_desc* desc, int n_replicas, int device, ldo_engine** out);
+void ldo_engine_destroy(ldo_engine* e);
+const char* ldo_last_error(const ldo_engine* e); /* pass NULL for errors of ldo_engine_create */
+int ldo_num_replicas(const ldo_engine* e);
+
+/* ---- potential tables ---------------------------------------------------------------------- */
+
+/* Replaces: OrigamiPotential::calc_energies / update_temp table cache (origami_potential.cpp:1019-1100).
+ * n_temps tables; each hyb_* array is [n_temps][(2 n_ident + 1)^2] indexed (a + n_ident)*(2 n_ident + 1) + (b + n_ident);
+ * init is [n_temps][3] = init energy, enthalpy, entropy (origami_potential.cpp:1060-1063). */
+int ldo_set_temperature_tables(ldo_engine* e, int n_temps, int n_ident, const double* temps,
+                               const double* hyb_energy, const double* hyb_enthalpy,
+                               const double* hyb_entropy, const double* init);
+
+/* ---- moveset, order parameters, biases ----------------------------------------------------- */
+
+/* Replaces: GCMCSimulation::construct_movetypes (simulation.cpp:267-320). */
+int ldo_set_moveset(ldo_engine* e, int n, const ldo_movetype_desc* movetypes, int allow_nonsensical_ps);
+/* Replaces: SystemOrderParams::setup_ops (order_params.cpp:471-577), move-update kind. */
+int ldo_set_order_params(ldo_engine* e, int n, const ldo_order_param_desc* ops);
+/* Replaces: SystemBiases::setup_biases (bias_functions.cpp:334-430), move-update kind. */
+int ldo_set_biases(ldo_engine* e, int n, const ldo_bias_desc* biases);
+/* Replaces: MWUSGCMCSimulation window override of a well bias (us_simulation.cpp:503-516). */
+int ldo_set_window(ldo_engine* e, int replica, int bias, int min_op, int max_op);
+/* Replaces: GridBiasFunction::replace_biases (bias_functions.cpp:238-241). Dense box of
+ * prod(n[k]) values, row-major; NaN marks a point that is not on the grid. */
+int ldo_set_grid_bias(ldo_engine* e, int replica, int bias, const int* lo, const int* n, const double* values);
+/* Per-step visit histogram over a grid bias' box (USGCMCSimulation::update_internal,
+ * us_simulation.cpp:262-266). Counts accumulate until read with clear != 0. */
+int ldo_get_grid_visits(ldo_engine* e, int replica, int bias, long long* counts, int clear);
+
+/* ---- control variables, seeds, tapes -------------------------------------------------------- */
+
+/* Replaces: OrigamiSystem::update_temp / update_staple_us / SystemBiases::update_bias_mult
+ * (origami_system.cpp:618-628, ptmc_simulation.cpp:651-680). The running energy of every touched
+ * replica is rebuilt (update_energy, origami_system.cpp:808-826). */
+int ldo_set_control(ldo_engine* e, int first, int count, const int* temp_idx,
+                    const double* staple_u_mult, const double* bias_mult, const double* stacking_mult);
+int ldo_get_control(ldo_engine* e, int first, int count, int* temp_idx,
+                    double* staple_u_mult, double* bias_mult, double* stacking_mult);
+/* Replaces: RandomGens seeding (simulation.cpp:200-203): Philox4x32-10 key = seed, subsequence =
+ * first_subsequence + replica. */
+int ldo_seed(ldo_engine* e, unsigned long long seed, unsigned int first_subsequence);
+/* Replay mode: serve the replica's draws from a tape (n = 0 detaches). */
+int ldo_attach_tape(ldo_engine* e, int replica, const ldo_tape_draw* draws, long long n);
+int ldo_tape_position(ldo_engine* e, int replica, long long* pos);
+
+/* ---- configuration -------------------------------------------------------------------------- */
+
+/* Replaces: OrigamiSystem::set_config / set_all_domains(Chains) (origami_system.cpp:327-341, 588-616).
+ * Chains in the reference's wire format (struct Chain, origami_system.hpp:46-62): working order,
+ * scaffold first; pos / ore are 3 ints per domain. replica = -1 sets every replica. */
+int ldo_set_state(ldo_engine* e, int replica, int n_chains, const int* chain_index,
+                  const int* chain_ident, const int* chain_len, const int* pos, const int* ore);
+/* Replaces: OrigamiSystem::chains() (origami_system.cpp:173-191). Buffers sized by ldo_state_capacity. */
+int ldo_state_capacity(const ldo_engine* e, int* max_chains, int* max_domains);
+int ldo_get_state(ldo_engine* e, int replica, int* n_chains, int* chain_index, int* chain_ident,
+                  int* chain_len, int* pos, int* ore, int* state, int* bound);
+
+/* ---- stepping -------------------------------------------------------------------------------- */
+
+/* Replaces: GCMCSimulation::simulate (simulation.cpp:568-653) for every replica: n_steps attempted
+ * moves each, centring every centering_freq steps and check_all_constraints every
+ * constraint_check_freq steps (0 = never), step counter continuing from the previous call. */
+int ldo_run(ldo_engine* e, long long n_steps, int centering_freq, int centering_domain,
+            int constraint_check_freq);
+/* Per-replica status: 0 ok, else the LDO_ERR_* code mirroring the reference's exception sites. */
+int ldo_get_status(ldo_engine* e, int* status, int* detail);
+/* Same as ldo_run but neither synchronises nor reads status back (for timing loops). */
+int ldo_run_async(ldo_engine* e, long long n_steps, int centering_freq, int centering_domain,
+                  int constraint_check_freq);
+int ldo_synchronize(ldo_engine* e);
+/* The CUDA stream every kernel of this engine is launched on (cudaStream_t as void*). */
+void* ldo_stream(ldo_engine* e);
+
+/* ---- observables ------------------------------------------------------------------------------ */
+
+/* [n_replicas][5]: total energy, hybridization enthalpy, entropy, stacking energy, external bias
+ * (.ene columns, files.cpp:707-720; update_enthalpy_and_entropy origami_system.cpp:204-246). */
+int ldo_get_energies(ldo_engine* e, double* out);
+/* [n_replicas][9]: staples, domains, bound pairs, fully bound pairs, self-bound pairs, misbound
+ * pairs, stacked pairs, unassigned domains, current unique chain index. */
+int ldo_get_counters(ldo_engine* e, int* out);
+/* [n_replicas][n_types-1] staples per identity (OrigamiSystem::get_staple_counts). */
+int ldo_get_staple_counts(ldo_engine* e, int* out);
+/* [n_replicas][n_ops] (SystemOrderParams, order_params.cpp:587-593). */
+int ldo_get_order_params(ldo_engine* e, int* out);
+/* [n_replicas][n_movetypes] attempts / accepts (MovetypeTracking, movetypes.hpp:49-52; .moves). */
+int ldo_get_move_stats(ldo_engine* e, long long* attempts, long long* accepts);
+/* Full energy of every replica recomputed from scratch on device without touching the state
+ * (the same pass check_all_constraints relies on): [n_replicas] energies, [n_replicas] stacked pairs. */
+int ldo_recompute_energies(ldo_engine* e, double* energy, int* stacked_pairs);
+/* Whole-state passes (origami_system.cpp:267-325, 553-571). */
+int ldo_check_all_constraints(ldo_engine* e);
+int ldo_center(ldo_engine* e, int centering_domain);
+
+/* ---- replica exchange ------------------------------------------------------------------------- */
+
+/* Replaces: PTGCMCSimulation::attempt_exchange for the 1-D variants (ptmc_simulation.cpp:360-412)
+ * over `n_ladders` independent ladders of `ladder_len` control-variable slots. Replica of slot k of
+ * ladder l is global replica index l * ladder_len + k (all GPUs concatenated, this engine holding
+ * [global_first, global_first + n_replicas)). Decisions are taken on device from a Philox stream
+ * shared by all ranks; accepted swaps relabel control variables (temperature table index and
+ * multipliers), configurations never move. `dependent` is the all-gathered [n_global][3 + n_staple_types]
+ * array of (enthalpy, bias, stacking, staple counts...) in units of kb T as produced by
+ * ldo_exchange_collect; pass NULL when this engine holds every replica. slot_to_replica is the
+ * reference's m_q_to_repi, per ladder (the .swp row). attempts/accepts: [n_ladders*(ladder_len-1)]. */
+/* Control-variable ladder (m_control_qs, ptmc_simulation.cpp:341-346): temperature table index and
+ * multipliers of every slot; NULL multipliers mean 1. */
+int ldo_set_exchange_ladder(ldo_engine* e, int ladder_len, const int* temp_idx, const double* staple_u_mult,
+                            const double* bias_mult, const double* stacking_mult);
+int ldo_exchange_collect(ldo_engine* e, double* dependent_local);
+int ldo_exchange_pt(ldo_engine* e, int variant, long long swap_i, int n_ladders, int ladder_len,
+                    int global_first, int n_global, const double* dependent,
+                    int* slot_to_replica, long long* attempts, long long* accepts);
+/* Device pointers for the NCCL path: local send buffer / full receive buffer of the dependent
+ * quantities ([n][3 + n_staple_types] doubles), so the all-gather runs device-to-device. */
+int ldo_exchange_buffers(ldo_engine* e, int n_global, void** send_dev, void** recv_dev, int* doubles_per_replica);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LDO_B200_H */

@@ -1,0 +1,71 @@
+/* ldo_host.h — C-ABI of the C++ host that keeps the reference's input/output surface for the MC
+ * hot path: it reads the reference's .inp parameter file and JSON side files, builds the fp64 energy
+ * tables, configures one ldo_engine (include/ldo_b200.h) and runs the reference's simulation drivers
+ * on it. Replaces, at the driver level:
+ *   main()                                    apps/main.cpp:19-117
+ *   origami::setup_origami                    src/origami_system.cpp:991-1031
+ *   GCMCSimulation constructor                src/simulation.cpp:182-265
+ *   ConstantTGCMCSimulation::run              include/LatticeDNAOrigami/constant_temp_simulation.hpp:31
+ *   AnnealingGCMCSimulation::run              src/annealing_simulation.cpp:38-49
+ *   PTGCMCSimulation::run (1-D variants)      src/ptmc_simulation.cpp:106-150
+ *   output files                              src/files.cpp:519-793, src/simulation.cpp:47-147
+ */
+#ifndef LDO_HOST_H
+#define LDO_HOST_H
+
+#include "ldo_b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ldo_sim ldo_sim;
+
+/* Error text of the last failed ldo_sim_* / ldo_host_* call on this thread. */
+const char* ldo_host_last_error(void);
+
+/* Reads `inp_path` (parser.cpp:477-479 format) and builds an engine with `n_replicas` replicas on CUDA
+ * device `device`. For the replica-exchange simulation types the replicas form n_replicas / num_reps
+ * independent ladders; `global_first` / `n_global` place this engine's replicas inside a multi-GPU
+ * ensemble (pass 0 / n_replicas for a single GPU). Every replica starts from the configuration of the
+ * system file (or restart_traj_file / restart_step). Returns NULL on error. */
+ldo_sim* ldo_sim_create(const char* inp_path, int n_replicas, int device, int global_first, int n_global);
+void ldo_sim_destroy(ldo_sim* s);
+ldo_engine* ldo_sim_engine(ldo_sim* s);
+
+/* Runs the driver selected by simulation_type (constant_temp, annealing, t_/ut_/hut_/st_parallel_tempering)
+ * to completion, writing the reference's output files for every replica (`<filebase>-<replica>.*` when
+ * there is more than one). Single-GPU only for the exchange types (the multi-GPU exchange is driven by the
+ * caller through ldo_sim_exchange_round with its own all-gather). Returns 0 or -1. */
+int ldo_sim_run(ldo_sim* s);
+
+/* One replica-exchange round (ptmc_simulation.cpp:113-141): `exchange_interval` MC steps on every local
+ * replica, then collection of the dependent quantities. After the caller has all-gathered them (or when
+ * this engine holds every replica) ldo_sim_exchange_apply takes the swap decisions. */
+int ldo_sim_exchange_advance(ldo_sim* s);
+int ldo_sim_exchange_apply(ldo_sim* s, long long swap_i, const double* dependent_all);
+/* m_q_to_repi of every ladder ([n_ladders][num_reps]) and the per-pair counters. */
+int ldo_sim_exchange_state(ldo_sim* s, int* slot_to_replica, long long* attempts, long long* accepts);
+
+/* Introspection used by tests and tools */
+int ldo_sim_num_temps(ldo_sim* s);
+int ldo_sim_num_order_params(ldo_sim* s);
+const char* ldo_sim_order_param_tag(ldo_sim* s, int i);
+int ldo_sim_num_movetypes(ldo_sim* s);
+const char* ldo_sim_movetype_label(ldo_sim* s, int i);
+int ldo_sim_num_staple_types(ldo_sim* s);
+long long ldo_sim_step(ldo_sim* s);
+
+/* Host-side energy-table builder exposed for parity tests (nearest_neighbour.cpp, origami_potential.cpp:1057-1221).
+ * out = {hyb energy, hyb enthalpy, hyb entropy} of identity pair (a, b) at table `temp_idx`; returns -1 if absent. */
+int ldo_sim_pair_energies(ldo_sim* s, int temp_idx, int a, int b, double* out);
+int ldo_sim_init_energies(ldo_sim* s, int temp_idx, double* out);
+int ldo_host_nn_unitless_thermo(const char* seq, double temp, double cation_M, double* out);
+int ldo_host_longest_contig_complement(const char* a, const char* b, char* out, int outlen);
+/* ideal_random_walk.cpp:14-73 reduced to the only property the path consumes (num_walks == 0). */
+int ldo_host_no_walks(const int* start, const int* end, int steps);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LDO_HOST_H */

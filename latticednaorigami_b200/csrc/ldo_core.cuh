@@ -1,0 +1,1424 @@
+// ldo_core.cuh — per-replica system state and the FourBody / misbinding / stacking / hybridization
+// delta-energy evaluation of the LatticeDNAOrigami model, written for one warp per replica.
+//
+// Execution model. Every replica is owned by one warp. All 32 lanes execute the serial Monte Carlo
+// logic redundantly on identical data (warp-uniform control flow: loads broadcast, stores write the
+// same value); the places where a move evaluates several candidate lattice sites are distributed
+// over lanes (`for (k = LDO_LANE; k < n; k += LDO_NLANES)`), through a READ-ONLY evaluator: a
+// candidate placement is examined through an overlay `View` instead of the reference's
+// set-then-roll-back (origami_system.cpp:343-355), so lanes never race on the replica state.
+//
+// What this restates (reference file:line):
+//   * Domain records, chain walk, twist/kink/junction constraints     domain.hpp:14-92, domain.cpp:9-118
+//   * occupancy maps pos->state / pos->unbound domain                  origami_system.hpp:184-187, hash.hpp:16-24
+//     (rebuilt as one open-addressing table: packed position -> occupant domain id)
+//   * set/check/unassign one domain, add/delete chain, centre,
+//     full constraint check, energy rebuild, enthalpy/entropy split   origami_system.cpp:193-871
+//   * FourBody binding potential, Opposing/Disallowed misbinding       origami_potential.cpp:25-950, 1282-1350
+//
+// The same source compiles for the device (nvcc, sm_100a) and — for the host-emulation debugging
+// harness under tests/hostsim only — as plain C++ with one emulated lane.
+#pragma once
+
+#include <stdint.h>
+#include <math.h>
+
+#if defined(__CUDACC__)
+#define LDO_HD __host__ __device__
+// Out-of-line device functions: keeps the per-replica kernel's code size (instruction cache) and
+// ptxas time under control; the call overhead is negligible next to the shared-memory latency chains.
+#define LDO_HDN __host__ __device__ __noinline__
+#else
+#define LDO_HD
+#define LDO_HDN
+#endif
+
+#if defined(__CUDA_ARCH__)
+#define LDO_LANE ((int)(threadIdx.x & 31))
+#define LDO_NLANES 32
+#define LDO_SYNCWARP() __syncwarp()
+#else
+#define LDO_LANE 0
+#define LDO_NLANES 1
+#define LDO_SYNCWARP() ((void)0)
+#endif
+
+namespace ldo {
+
+// ---------------------------------------------------------------------------------------------
+// Lattice vectors (utility.hpp:66-95, utility.cpp:26-161)
+// ---------------------------------------------------------------------------------------------
+
+struct V3 {
+    int x, y, z;
+};
+
+LDO_HD inline V3 v3(int x, int y, int z) {
+    V3 v;
+    v.x = x;
+    v.y = y;
+    v.z = z;
+    return v;
+}
+LDO_HD inline V3 operator+(V3 a, V3 b) { return v3(a.x + b.x, a.y + b.y, a.z + b.z); }
+LDO_HD inline V3 operator-(V3 a, V3 b) { return v3(a.x - b.x, a.y - b.y, a.z - b.z); }
+LDO_HD inline V3 operator-(V3 a) { return v3(-a.x, -a.y, -a.z); }
+LDO_HD inline bool operator==(V3 a, V3 b) { return a.x == b.x && a.y == b.y && a.z == b.z; }
+LDO_HD inline bool operator!=(V3 a, V3 b) { return !(a == b); }
+LDO_HD inline int abssum(V3 a) { return abs(a.x) + abs(a.y) + abs(a.z); }
+
+// Orientation codes index utility::vectors (utility.hpp:156-162): +x,-x,+y,-y,+z,-z; 6 = zero vector
+enum { ORE_ZERO = 6 };
+
+LDO_HD inline V3 ore_vec(int code) {
+    int s = 1 - 2 * (code & 1);
+    int a = code >> 1;
+    return v3(a == 0 ? s : 0, a == 1 ? s : 0, a == 2 ? s : 0);
+}
+
+// Returns 0..5 for unit vectors, ORE_ZERO for (0,0,0), 7 for anything else
+LDO_HD inline int ore_code(V3 v) {
+    if (abssum(v) == 0) return ORE_ZERO;
+    if (abssum(v) != 1) return 7;
+    if (v.x != 0) return v.x > 0 ? 0 : 1;
+    if (v.y != 0) return v.y > 0 ? 2 : 3;
+    return v.z > 0 ? 4 : 5;
+}
+
+// VectorThree::rotate_half (utility.cpp:68-86): only acts when |axis| is a basis vector
+LDO_HD inline V3 rotate_half(V3 v, V3 axis) {
+    int ax = abs(axis.x), ay = abs(axis.y), az = abs(axis.z);
+    if (ax == 1 && ay == 0 && az == 0) return v3(v.x, -v.y, -v.z);
+    if (ax == 0 && ay == 1 && az == 0) return v3(-v.x, v.y, -v.z);
+    if (ax == 0 && ay == 0 && az == 1) return v3(-v.x, -v.y, v.z);
+    return v;
+}
+
+// VectorThree::rotate(axis, turns) (utility.cpp:103-142)
+LDO_HD inline V3 rotate_turns(V3 v, V3 axis, int turns) {
+    if (turns % 2 == 0) return rotate_half(v, axis);
+    bool odd_turns_even = ((turns - 1) / 2 % 2 == 0);
+    bool turns_neg = turns < 0;
+    int dir = (!turns_neg && odd_turns_even) ? 1 : -1;
+    V3 aa = v3(abs(axis.x), abs(axis.y), abs(axis.z));
+    if (axis != aa) dir *= -1;
+    if (aa == v3(1, 0, 0)) return v3(v.x, -dir * v.z, dir * v.y);
+    if (aa == v3(0, 1, 0)) return v3(-dir * v.z, v.y, dir * v.x);
+    if (aa == v3(0, 0, 1)) return v3(-dir * v.y, dir * v.x, v.z);
+    return v;
+}
+
+// VectorThree::rotate(origin, axis, turns) (utility.cpp:88-101)
+LDO_HD inline V3 rotate_about(V3 v, V3 origin, V3 axis, int turns) {
+    if (turns == 0) return v;
+    return rotate_turns(v - origin, axis, turns) + origin;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Constants, capacities
+// ---------------------------------------------------------------------------------------------
+
+// utility::Occupancy (utility.hpp:63)
+enum : uint8_t { ST_UNASSIGNED = 0, ST_UNBOUND = 1, ST_BOUND = 2, ST_MISBOUND = 3 };
+
+enum { DOMAIN_HALFTURN = 0, DOMAIN_THREEQUARTERTURN = 1 };
+enum { MISBIND_OPPOSING = 0, MISBIND_DISALLOWED = 1 };
+
+// Replica status codes (mirror the reference's exception sites)
+enum {
+    LDO_OK = 0,
+    LDO_ERR_TAPE_EXHAUSTED = 1, // replay tape ran out
+    LDO_ERR_TAPE_MISMATCH = 2, // replayed request differs from the taped one (kind or bounds)
+    LDO_ERR_COORD_RANGE = 3, // |coordinate| exceeded the packed-key range
+    LDO_ERR_TABLE_FULL = 4, // occupancy table full
+    LDO_ERR_CAPACITY = 5, // fixed-size move scratch exceeded
+    LDO_ERR_UNASSIGNED_AT_CHECK = 6, // origami_system.cpp:272-279
+    LDO_ERR_STACK_COUNT = 7, // origami_system.cpp:296-300
+    LDO_ERR_ENERGY_DRIFT = 8, // origami_system.cpp:305-309
+    LDO_ERR_CONSTRAINTS = 9, // origami_system.cpp:579-583
+    LDO_ERR_DISTANCE = 10, // origami_system.cpp:367-369
+    LDO_ERR_BIND_BOUND = 11, // origami_system.cpp:804
+    LDO_ERR_SET_ASSIGNED = 12, // origami_system.cpp:526
+    LDO_ERR_NONSENSICAL_P = 13, // met_movetypes.cpp:240,291
+    LDO_ERR_UNBOUND_STAPLE = 14, // movetypes.cpp:273
+    LDO_ERR_INTERNAL = 15
+};
+
+#define LDO_COORD_MAX 511
+
+// One domain: position, orientation code, occupancy state. 8 bytes = one LDS.64.
+struct __attribute__((aligned(8))) DomRec {
+    short x, y, z;
+    int8_t ore;
+    uint8_t state;
+};
+
+// System description shared by every replica (read-only on the device)
+#define LDO_MAX_TYPES 192
+#define LDO_MAX_IDENTS 1024
+struct SysConst {
+    int n_types; // chain identities including the scaffold (identity 0)
+    int n_scaffold; // scaffold length
+    int lmax; // staple slot stride (max_staple_size)
+    int cyclic;
+    int domain_type;
+    int misbinding_pot;
+    int apply_mean_field_cor;
+    int max_total_staples;
+    int max_type_staples;
+    int n_ident; // identities run over [-n_ident, n_ident]; tables are (2 n_ident + 1)^2
+    double staple_M; // reduced fugacity (origami_system.cpp:58)
+    double stacking_ene; // Constant stacking potential, kb K (origami_potential.cpp:1219-1221)
+    int type_len[LDO_MAX_TYPES];
+    int type_off[LDO_MAX_TYPES];
+    short idents[LDO_MAX_IDENTS]; // flattened m_identities
+};
+
+// Per-temperature energy tables (origami_potential.cpp:1057-1221); shared by replicas at that T
+struct TempTables {
+    double temp;
+    double init_energy, init_enthalpy, init_entropy;
+    const double* hyb_energy; // [(2n+1)^2], index (a+n)*(2n+1) + (b+n)
+    const double* hyb_enthalpy;
+    const double* hyb_entropy;
+};
+
+// Control variables of one replica (what replica exchange permutes, ptmc_simulation.hpp:73-81)
+struct Control {
+    int temp_idx;
+    double temp;
+    double staple_u_mult;
+    double bias_mult;
+    double stacking_mult;
+};
+
+template <int D_, int C_, int HBITS_, int T_>
+struct Caps {
+    static const int D = D_; // domain slots
+    static const int C = C_; // chain slots (scaffold + staples)
+    static const int T = T_; // chain identities (scaffold + staple types)
+    static const int HBITS = HBITS_;
+    static const int H = 1 << HBITS_; // occupancy table slots
+};
+
+#define LDO_HEMPTY 0xFFFFFFFFu
+
+// Persistent configuration of one replica
+template <class K>
+struct SysState {
+    DomRec dom[K::D];
+    short bound[K::D]; // partner domain id or -1
+    short ident[K::D]; // domain identity (m_d_ident)
+    uint16_t dchain[K::D]; // chain slot
+    uint16_t dindex[K::D]; // index in chain (m_d)
+    uint32_t hkey[K::H];
+    short hval[K::H];
+    int chain_uid[K::C]; // unique chain index (m_c)
+    uint16_t chain_type[K::C]; // chain identity (m_c_ident)
+    uint16_t chain_len[K::C];
+    uint8_t chain_used[K::C];
+    uint16_t order[K::C]; // working order -> chain slot (m_domains order, App. B)
+    int n_chains; // scaffold included
+    int current_c_i; // m_current_c_i
+    int num_staples, num_domains;
+    int num_bound_pairs, num_fully_bound_pairs, num_self_bound_pairs;
+    int num_stacked_pairs, num_unassigned;
+    int constraints_violated;
+    int status;
+    int status_detail;
+    double energy;
+    double stack_e; // stacking_ene * stacking_mult / T for this replica
+    int type_count[K::T]; // staples per identity (|m_identity_to_index[i]|)
+};
+
+struct DeltaConfig {
+    double e;
+    int stacked;
+    bool violated;
+};
+
+LDO_HD inline uint32_t pack_pos(V3 p) {
+    return ((uint32_t)(p.x & 0x3FF) << 20) | ((uint32_t)(p.y & 0x3FF) << 10) | (uint32_t)(p.z & 0x3FF);
+}
+
+template <class K>
+LDO_HD inline uint32_t hash_slot(uint32_t key) {
+    return (key * 0x9E3779B1u) >> (32 - K::HBITS);
+}
+
+// ---------------------------------------------------------------------------------------------
+// System: state + constants + tables, with an optional overlay of one hypothetical placement
+// ---------------------------------------------------------------------------------------------
+
+template <class K>
+struct System {
+    SysState<K>* s;
+    const SysConst* sc;
+    TempTables tt;
+
+    // Overlay (read-only candidate evaluation): domain od placed at orec, bound to oj (or -1)
+    int od, oj;
+    DomRec orec;
+
+    LDO_HD void init(SysState<K>* s_, const SysConst* sc_, const TempTables& tt_) {
+        s = s_;
+        sc = sc_;
+        tt = tt_;
+        od = -1;
+        oj = -1;
+    }
+
+    LDO_HD void fail(int code, int detail = 0) {
+        if (s->status == LDO_OK) {
+            s->status = code;
+            s->status_detail = detail;
+        }
+    }
+
+    // ---- accessors (overlay aware) ----
+    LDO_HD V3 pos(int d) const {
+        if (d == od) return v3(orec.x, orec.y, orec.z);
+        const DomRec& r = s->dom[d];
+        return v3(r.x, r.y, r.z);
+    }
+    LDO_HD V3 ore(int d) const {
+        if (d == od) return ore_vec(orec.ore);
+        return ore_vec(s->dom[d].ore);
+    }
+    LDO_HD int state(int d) const {
+        if (d == od || d == oj) return orec.state;
+        return s->dom[d].state;
+    }
+    LDO_HD int bound(int d) const {
+        if (d == od) return oj;
+        if (d == oj) return od;
+        return s->bound[d];
+    }
+    LDO_HD int chain(int d) const { return s->dchain[d]; }
+    LDO_HD int dindex(int d) const { return s->dindex[d]; }
+    LDO_HD int ident(int d) const { return s->ident[d]; }
+    LDO_HD int chain_base(int c) const { return c == 0 ? 0 : sc->n_scaffold + (c - 1) * sc->lmax; }
+    LDO_HD int dom_id(int c, int i) const { return chain_base(c) + i; }
+
+    // Domain::m_forward_domain / m_backward_domain (domain.hpp:30-31; cyclic scaffold origami_system.cpp:687-692)
+    LDO_HD int fwd(int d) const {
+        int c = s->dchain[d], i = s->dindex[d], L = s->chain_len[c];
+        if (i + 1 < L) return d + 1;
+        if (c == 0 && sc->cyclic) return chain_base(0);
+        return -1;
+    }
+    LDO_HD int bac(int d) const {
+        int c = s->dchain[d], i = s->dindex[d];
+        if (i > 0) return d - 1;
+        if (c == 0 && sc->cyclic) return chain_base(0) + s->chain_len[0] - 1;
+        return -1;
+    }
+    // Domain::operator+ (domain.cpp:9-31)
+    LDO_HDN int step(int d, int incr) const {
+        while (incr > 0 && d >= 0) {
+            d = fwd(d);
+            incr--;
+        }
+        while (incr < 0 && d >= 0) {
+            d = bac(d);
+            incr++;
+        }
+        return d;
+    }
+
+    // ---- energy tables ----
+    LDO_HD int pair_index(int a, int b) const {
+        int n = sc->n_ident;
+        return (a + n) * (2 * n + 1) + (b + n);
+    }
+    LDO_HD double hyb_energy(int di, int dj) const { return tt.hyb_energy[pair_index(ident(di), ident(dj))]; }
+    LDO_HD double hyb_enthalpy(int di, int dj) const { return tt.hyb_enthalpy[pair_index(ident(di), ident(dj))]; }
+    LDO_HD double hyb_entropy(int di, int dj) const { return tt.hyb_entropy[pair_index(ident(di), ident(dj))]; }
+    LDO_HD double stack_energy() const { return s->stack_e; }
+
+    // ---- occupancy table ----
+    // Returns the occupant domain id at p, or -1 (origami_system.cpp:193-202, 130-132)
+    LDO_HDN int occupant(V3 p) const {
+        uint32_t key = pack_pos(p);
+        uint32_t i = hash_slot<K>(key);
+        for (int n = 0; n < K::H; n++) {
+            uint32_t k = s->hkey[i];
+            if (k == key) return s->hval[i];
+            if (k == LDO_HEMPTY) return -1;
+            i = (i + 1) & (K::H - 1);
+        }
+        return -1;
+    }
+    LDO_HDN void table_put(V3 p, int d) {
+        if (abs(p.x) > LDO_COORD_MAX || abs(p.y) > LDO_COORD_MAX || abs(p.z) > LDO_COORD_MAX) {
+            fail(LDO_ERR_COORD_RANGE, d);
+        }
+        uint32_t key = pack_pos(p);
+        uint32_t i = hash_slot<K>(key);
+        for (int n = 0; n < K::H; n++) {
+            uint32_t k = s->hkey[i];
+            if (k == key || k == LDO_HEMPTY) {
+                s->hkey[i] = key;
+                s->hval[i] = (short)d;
+                return;
+            }
+            i = (i + 1) & (K::H - 1);
+        }
+        fail(LDO_ERR_TABLE_FULL, d);
+    }
+    // Linear-probing erase with backward shift (no tombstones: erases are as frequent as inserts)
+    LDO_HDN void table_erase(V3 p) {
+        uint32_t key = pack_pos(p);
+        uint32_t i = hash_slot<K>(key);
+        int n = 0;
+        while (s->hkey[i] != key) {
+            if (s->hkey[i] == LDO_HEMPTY || ++n == K::H) return;
+            i = (i + 1) & (K::H - 1);
+        }
+        uint32_t j = i;
+        for (;;) {
+            j = (j + 1) & (K::H - 1);
+            uint32_t kj = s->hkey[j];
+            if (kj == LDO_HEMPTY) break;
+            uint32_t h = hash_slot<K>(kj);
+            // move kj into the hole i unless its home slot lies cyclically in (i, j]
+            bool home_between = (i <= j) ? (i < h && h <= j) : (i < h || h <= j);
+            if (!home_between) {
+                s->hkey[i] = kj;
+                s->hval[i] = s->hval[j];
+                i = j;
+            }
+        }
+        s->hkey[i] = LDO_HEMPTY;
+    }
+    LDO_HD void table_clear() {
+        for (int i = 0; i < K::H; i++) s->hkey[i] = LDO_HEMPTY;
+    }
+
+    // ---- domain constraint checkers (domain.cpp:33-118) ----
+    LDO_HD bool check_twist(int d1, V3 ndr, int d2) const {
+        V3 o1 = ore(d1);
+        V3 rot = sc->domain_type == DOMAIN_HALFTURN ? rotate_half(o1, ndr) : rotate_turns(o1, ndr, -1);
+        return rot == ore(d2);
+    }
+    LDO_HD bool check_kink(int d1, V3 ndr, int d2) const {
+        V3 o1 = ore(d1), o2 = ore(d2);
+        if (ndr == -o1) return false;
+        if (ndr == o1) {
+            if (sc->domain_type == DOMAIN_HALFTURN) {
+                if (o2 == -o1) return false;
+            }
+            else {
+                if (o1 == o2 || o1 == -o2) return false;
+            }
+            return true;
+        }
+        if (ndr == o2 || ndr == -o2) return false;
+        return true;
+    }
+    LDO_HD bool check_junction_constraint(int j1, int j2, int k1, int k2) const {
+        if (sc->domain_type == DOMAIN_HALFTURN) return true;
+        V3 ndr_k1 = pos(k2) - pos(k1);
+        if (ndr_k1 == ore(k1)) {
+            V3 ndr_1 = pos(j2) - pos(j1);
+            if (dindex(j1) > dindex(j2)) ndr_1 = -ndr_1;
+            if (!check_twist(k1, ndr_1, k2)) return false;
+        }
+        return true;
+    }
+
+    // ---- free helpers (origami_potential.cpp:25-127) ----
+    LDO_HD bool exists_bound(int d) const { return d >= 0 && state(d) == ST_BOUND; }
+    LDO_HD bool doubly_contiguous(int d1, int d2) const {
+        if (chain(d1) != chain(d2) || dindex(d2) != dindex(d1) + 1) return false;
+        int b1 = bound(d1), b2 = bound(d2);
+        if (chain(b1) != chain(b2)) return false;
+        return abs(dindex(b2) - dindex(b1)) == 1;
+    }
+    LDO_HDN bool pair_stacked(int d1, int d2) const {
+        if (dindex(d1) > dindex(d2)) {
+            int t = d1;
+            d1 = d2;
+            d2 = t;
+        }
+        V3 ndr = pos(d2) - pos(d1);
+        V3 o1 = ore(d1);
+        if (ndr != o1 && ndr != -o1) return check_twist(d1, ndr, d2);
+        return false;
+    }
+    LDO_HD int junction_stacking_penalty(int j1, int j2, int j3, int j4, int k1, int k2) const {
+        int penalty = 0;
+        V3 ndr_k1 = pos(k2) - pos(k1);
+        if (ndr_k1 == ore(k1)) {
+            V3 ndr_1 = pos(j2) - pos(j1);
+            if (dindex(j1) > dindex(j2)) ndr_1 = -ndr_1;
+            V3 ndr_3 = pos(j4) - pos(j3);
+            if (dindex(j3) > dindex(j4)) ndr_3 = -ndr_3;
+            if (ndr_1 == ndr_3) penalty = 2;
+            else if (ndr_1 == -ndr_3) penalty = 0;
+            else penalty = 1;
+        }
+        return penalty;
+    }
+
+    // ---- triplet terms (origami_potential.cpp:158-210) ----
+    LDO_HD void triplet_single_stacking(DeltaConfig& dc, int h1, int h2, int h3) const {
+        V3 ndr_1 = pos(h2) - pos(h1);
+        if (ndr_1 == ore(h1)) return;
+        V3 ndr_2 = pos(h3) - pos(h2);
+        if (ndr_1 != ndr_2) {
+            dc.e -= stack_energy();
+            dc.stacked -= 1;
+        }
+    }
+    LDO_HD void triplet_double_stacking(DeltaConfig& dc, int h1, int h2, int h3) const {
+        V3 ndr_1 = pos(h2) - pos(h1);
+        V3 ndr_2 = pos(h3) - pos(h2);
+        if (ndr_1 != ndr_2) {
+            dc.e -= stack_energy() / 2;
+            dc.e -= stack_energy() / 2;
+            dc.stacked -= 1;
+        }
+    }
+    LDO_HD void triply_contig_helix(DeltaConfig& dc, int h1, int h2, int h3) const {
+        V3 ndr_1 = pos(h2) - pos(h1);
+        V3 ndr_2 = pos(h3) - pos(h2);
+        if (ndr_1 != ndr_2) dc.violated = true;
+    }
+
+    // origami_potential.cpp:419-462
+    LDO_HDN void check_junction(DeltaConfig& dc, int j1, int j2, int j3, int j4, int k1, int k2) const {
+        if (dindex(k1) > dindex(k2)) {
+            int t = k1;
+            k1 = k2;
+            k2 = t;
+            t = j1;
+            j1 = j4;
+            j4 = t;
+            t = j2;
+            j2 = j3;
+            j3 = t;
+        }
+        if (!(pair_stacked(j1, j2) && pair_stacked(j3, j4))) return;
+        if (!check_junction_constraint(j1, j2, k1, k2)) {
+            dc.violated = true;
+            return;
+        }
+        int penalty = junction_stacking_penalty(j1, j2, j3, j4, k1, k2);
+        if (penalty == 1) {
+            dc.e -= stack_energy() / 2;
+            dc.e -= stack_energy() / 2;
+            dc.stacked -= 1;
+        }
+        else if (penalty == 2) {
+            dc.e -= stack_energy();
+            dc.e -= stack_energy();
+            dc.stacked -= 2;
+        }
+    }
+
+    // Second-junction-pair scan shared by the three single-junction routines
+    // (origami_potential.cpp:713-745, 809-841, 905-933): pairs (a, a_next) on the kink chain and on
+    // the chain bound to a. `forward_role`: true when the pair found is (j3, j4), false for (j2, j1).
+    LDO_HDN void scan_second_pairs(
+            DeltaConfig& dc,
+            int a,
+            int a_next,
+            bool found_is_j34,
+            int fj1,
+            int fj2,
+            int k1,
+            int k2) const {
+        int sel_a[3], sel_b[3];
+        int n = 0;
+        sel_a[n] = a;
+        sel_b[n] = a_next;
+        n++;
+        int ab = bound(a);
+        int ab_for = fwd(ab), ab_bac = bac(ab);
+        if (exists_bound(a_next)) {
+            int anb = bound(a_next);
+            if (ab_for != anb) {
+                sel_a[n] = ab;
+                sel_b[n] = ab_for;
+                n++;
+            }
+            if (ab_bac != anb) {
+                sel_a[n] = ab;
+                sel_b[n] = ab_bac;
+                n++;
+            }
+        }
+        else {
+            sel_a[n] = ab;
+            sel_b[n] = ab_for;
+            n++;
+            sel_a[n] = ab;
+            sel_b[n] = ab_bac;
+            n++;
+        }
+        for (int q = 0; q < n; q++) {
+            if (!exists_bound(sel_b[q])) continue;
+            if (found_is_j34) check_junction(dc, fj1, fj2, sel_a[q], sel_b[q], k1, k2);
+            else check_junction(dc, sel_b[q], sel_a[q], fj1, fj2, k1, k2);
+        }
+    }
+
+    // origami_potential.cpp:654-748 (passed domains are the second junction pair j3, j4)
+    LDO_HDN void backward_single_junction(DeltaConfig& dc, int d1, int d2) const {
+        int j3 = d1, j4 = d2;
+        int sel_k2[3], sel_k1[3];
+        int n = 0;
+        int j3_bac = bac(j3);
+        sel_k2[n] = j3;
+        sel_k1[n] = j3_bac;
+        n++;
+        int j3b = bound(j3);
+        int j4b = bound(j4);
+        int j3b_for = fwd(j3b), j3b_bac = bac(j3b);
+        if (j3b_for == j4b) {
+            sel_k2[n] = j3b;
+            sel_k1[n] = j3b_bac;
+            n++;
+        }
+        else if (exists_bound(j3_bac) && exists_bound(j3b_bac) && bound(j3_bac) == j3b_bac) {
+            sel_k2[n] = j3b;
+            sel_k1[n] = j3b_for;
+            n++;
+        }
+        else if (exists_bound(j3_bac) && exists_bound(j3b_for) && bound(j3_bac) == j3b_for) {
+            sel_k2[n] = j3b;
+            sel_k1[n] = j3b_bac;
+            n++;
+        }
+        else {
+            sel_k2[n] = j3b;
+            sel_k1[n] = j3b_for;
+            n++;
+            sel_k2[n] = j3b;
+            sel_k1[n] = j3b_bac;
+            n++;
+        }
+        for (int q = 0; q < n; q++) {
+            int k2 = sel_k2[q], k1 = sel_k1[q];
+            if (!exists_bound(k1)) continue;
+            if (pair_stacked(k1, k2)) continue;
+            int dir = dindex(k1) - dindex(k2);
+            int k1_next = step(k1, dir);
+            scan_second_pairs(dc, k1, k1_next, false, j3, j4, k1, k2);
+        }
+    }
+
+    // origami_potential.cpp:750-844 (passed domains are the first junction pair j1, j2)
+    LDO_HDN void forward_single_junction(DeltaConfig& dc, int d1, int d2) const {
+        int j1 = d1, j2 = d2;
+        int sel_k1[3], sel_k2[3];
+        int n = 0;
+        int j2_for = fwd(j2);
+        sel_k1[n] = j2;
+        sel_k2[n] = j2_for;
+        n++;
+        int j1b = bound(j1);
+        int j2b = bound(j2);
+        int j2b_for = fwd(j2b), j2b_bac = bac(j2b);
+        if (fwd(j1b) == j2b) {
+            sel_k1[n] = j2b;
+            sel_k2[n] = j2b_for;
+            n++;
+        }
+        else if (exists_bound(j2_for) && exists_bound(j2b_bac) && bound(j2_for) == j2b_bac) {
+            sel_k1[n] = j2b;
+            sel_k2[n] = j2b_for;
+            n++;
+        }
+        else if (exists_bound(j2_for) && exists_bound(j2b_for) && bound(j2_for) == j2b_for) {
+            sel_k1[n] = j2b;
+            sel_k2[n] = j2b_bac;
+            n++;
+        }
+        else {
+            sel_k1[n] = j2b;
+            sel_k2[n] = j2b_for;
+            n++;
+            sel_k1[n] = j2b;
+            sel_k2[n] = j2b_bac;
+            n++;
+        }
+        for (int q = 0; q < n; q++) {
+            int k1 = sel_k1[q], k2 = sel_k2[q];
+            if (!exists_bound(k2)) continue;
+            if (pair_stacked(k1, k2)) continue;
+            int dir = dindex(k2) - dindex(k1);
+            int k2_next = step(k2, dir);
+            scan_second_pairs(dc, k2, k2_next, true, j1, j2, k1, k2);
+        }
+    }
+
+    // origami_potential.cpp:846-934 (passed domains are the kink pair)
+    LDO_HDN void central_single_junction(DeltaConfig& dc, int d1, int d2) const {
+        int k1 = d1, k2 = d2;
+        int k1b = bound(k1), k2b = bound(k2);
+        if (chain(k1b) == chain(k2b) && abs(dindex(k1b) - dindex(k2b)) == 1) return;
+
+        int sel_j2[3], sel_j1[3];
+        int n = 0;
+        int k1_bac = bac(k1);
+        sel_j2[n] = k1;
+        sel_j1[n] = k1_bac;
+        n++;
+        int k1b_for = fwd(k1b), k1b_bac = bac(k1b);
+        if (exists_bound(k1_bac)) {
+            int kbb = bound(k1_bac);
+            if (k1b_for != kbb) {
+                sel_j2[n] = k1b;
+                sel_j1[n] = k1b_for;
+                n++;
+            }
+            if (k1b_bac != kbb) {
+                sel_j2[n] = k1b;
+                sel_j1[n] = k1b_bac;
+                n++;
+            }
+        }
+        else {
+            sel_j2[n] = k1b;
+            sel_j1[n] = k1b_for;
+            n++;
+            sel_j2[n] = k1b;
+            sel_j1[n] = k1b_bac;
+            n++;
+        }
+        for (int q = 0; q < n; q++) {
+            int j2 = sel_j2[q], j1 = sel_j1[q];
+            if (!exists_bound(j1)) continue;
+            int k2_for = fwd(k2);
+            scan_second_pairs(dc, k2, k2_for, true, j1, j2, k1, k2);
+        }
+    }
+
+    // origami_potential.cpp:464-519
+    LDO_HDN void backward_triplet_combos(DeltaConfig& dc, int d1, int d2) const {
+        int h2 = d1, h3 = d2;
+        if (!pair_stacked(h2, h3)) return;
+        int h1 = step(d1, -1);
+        bool h2_h3_dc = doubly_contiguous(h2, h3);
+        if (exists_bound(h1)) {
+            bool h1_h2_dc = doubly_contiguous(h1, h2);
+            if (pair_stacked(h1, h2)) {
+                if (h1_h2_dc && h2_h3_dc) {
+                    triply_contig_helix(dc, h1, h2, h3);
+                    if (dc.violated) return;
+                }
+                triplet_double_stacking(dc, h1, h2, h3);
+            }
+            else {
+                triplet_single_stacking(dc, h1, h2, h3);
+            }
+        }
+        int h2_prev = h1;
+        int d1b = bound(d1);
+        h1 = step(d1b, 1);
+        if (exists_bound(h1) && bound(h1) != h2_prev && bound(h1) != h3) {
+            if (pair_stacked(d1b, h1)) triplet_double_stacking(dc, h1, h2, h3);
+        }
+        h1 = step(d1b, -1);
+        if (exists_bound(h1) && bound(h1) != h2_prev && bound(h1) != h3) {
+            if (pair_stacked(h1, d1b)) triplet_double_stacking(dc, h1, h2, h3);
+            else triplet_single_stacking(dc, h1, d1b, h3);
+        }
+    }
+
+    // origami_potential.cpp:521-585
+    LDO_HDN void forward_triplet_combos(DeltaConfig& dc, int d1, int d2) const {
+        int h2 = d2, h1 = d1;
+        bool first_pair_stacked = pair_stacked(h1, h2);
+        int h3 = step(d2, 1);
+        bool h1_h2_dc = doubly_contiguous(h1, h2);
+        if (exists_bound(h3)) {
+            bool second_pair_stacked = pair_stacked(h2, h3);
+            if (first_pair_stacked && second_pair_stacked) {
+                bool h2_h3_dc = doubly_contiguous(h2, h3);
+                if (h1_h2_dc && h2_h3_dc) {
+                    triply_contig_helix(dc, h1, h2, h3);
+                    if (dc.violated) return;
+                }
+                triplet_double_stacking(dc, h1, h2, h3);
+            }
+            else if (second_pair_stacked) {
+                triplet_single_stacking(dc, h1, h2, h3);
+            }
+        }
+        int h2_next = h3;
+        int d2b = bound(d2);
+        h3 = step(d2b, 1);
+        if (exists_bound(h3) && bound(h3) != h2_next && bound(h3) != h1) {
+            if (pair_stacked(d2b, h3)) {
+                if (first_pair_stacked) triplet_double_stacking(dc, h1, h2, h3);
+                else triplet_single_stacking(dc, h1, h2, h3);
+            }
+        }
+        h3 = step(d2b, -1);
+        if (exists_bound(h3) && bound(h3) != h2_next && bound(h3) != h1) {
+            if (pair_stacked(h3, d2b)) {
+                if (first_pair_stacked) triplet_double_stacking(dc, h1, h2, h3);
+                else triplet_single_stacking(dc, h1, h2, h3);
+            }
+            else if (first_pair_stacked) {
+                triplet_single_stacking(dc, h3, d2b, h1);
+            }
+        }
+    }
+
+    // origami_potential.cpp:587-652
+    LDO_HDN void central_triplet_combos(DeltaConfig& dc, int di, int dj) const {
+        int h1 = step(di, -1);
+        int h2 = di;
+        int h3 = step(dj, 1);
+        int h2_next = step(di, 1);
+        if (exists_bound(h1) && exists_bound(h3) && bound(h3) != h2_next && !doubly_contiguous(h1, h2)) {
+            if (pair_stacked(dj, h3)) {
+                if (pair_stacked(h1, h2)) triplet_double_stacking(dc, h1, h2, h3);
+                else triplet_single_stacking(dc, h1, h2, h3);
+            }
+        }
+        h3 = step(dj, -1);
+        if (exists_bound(h1) && exists_bound(h3) && bound(h3) != h1 && !doubly_contiguous(h1, h2)) {
+            if (pair_stacked(h1, h2)) {
+                if (pair_stacked(h3, dj)) triplet_double_stacking(dc, h1, h2, h3);
+                else triplet_single_stacking(dc, h3, dj, h1);
+            }
+            else if (pair_stacked(h3, dj)) {
+                triplet_single_stacking(dc, h1, h2, h3);
+            }
+        }
+        h2 = di;
+        h3 = step(di, 1);
+        h1 = step(dj, 1);
+        int h2_prev = step(di, -1);
+        if (exists_bound(h1) && exists_bound(h3) && bound(h1) != h3 && !doubly_contiguous(h2, h3)) {
+            if (pair_stacked(dj, h1) && pair_stacked(h2, h3)) triplet_double_stacking(dc, h1, h2, h3);
+        }
+        h1 = step(dj, -1);
+        if (exists_bound(h1) && exists_bound(h3) && bound(h1) != h2_prev && !doubly_contiguous(h2, h3)) {
+            if (pair_stacked(h2, h3)) {
+                if (pair_stacked(h1, dj)) triplet_double_stacking(dc, h1, h2, h3);
+                else triplet_single_stacking(dc, h1, dj, h3);
+            }
+        }
+    }
+
+    // origami_potential.cpp:288-320
+    LDO_HDN void regular_pair_constraints(DeltaConfig& dc, int d1, int d2, int i) const {
+        V3 ndr = pos(d2) - pos(d1);
+        if (!check_kink(d1, ndr, d2)) {
+            dc.violated = true;
+            return;
+        }
+        if (pair_stacked(d1, d2)) {
+            dc.e += stack_energy();
+            dc.stacked += 1;
+            if (i == -1) backward_single_junction(dc, d1, d2);
+            else forward_single_junction(dc, d1, d2);
+        }
+        else {
+            central_single_junction(dc, d1, d2);
+        }
+        if (i == -1) backward_triplet_combos(dc, d1, d2);
+        else forward_triplet_combos(dc, d1, d2);
+    }
+
+    // origami_potential.cpp:322-357
+    LDO_HDN void doubly_contig_helix_pair(DeltaConfig& dc, int d1, int d2, int i, int j) const {
+        if (j == 1) return;
+        V3 ndr = pos(d2) - pos(d1);
+        V3 o1 = ore(d1);
+        if (ndr == o1 || ndr == -o1) {
+            dc.violated = true;
+            return;
+        }
+        if (check_twist(d1, ndr, d2)) {
+            dc.e += stack_energy();
+            dc.stacked += 1;
+        }
+        else {
+            dc.violated = true;
+            return;
+        }
+        if (i == -1) {
+            backward_triplet_combos(dc, d1, d2);
+            backward_single_junction(dc, d1, d2);
+        }
+        else {
+            forward_triplet_combos(dc, d1, d2);
+            forward_single_junction(dc, d1, d2);
+        }
+    }
+
+    // origami_potential.cpp:359-417
+    LDO_HDN void doubly_contig_junction_pair(DeltaConfig& dc, int d1, int d2, int j) const {
+        int k1 = d1, k2 = d2;
+        V3 ndr = pos(k2) - pos(k1);
+        if (ore(k1) != ndr) {
+            dc.violated = true;
+            return;
+        }
+        if (j == 1) return;
+        int d1b = bound(d1);
+        int sel_j1[2], sel_j2[2];
+        sel_j1[0] = step(d1, -1);
+        sel_j2[0] = d1;
+        sel_j1[1] = step(d1b, 1);
+        sel_j2[1] = d1b;
+        for (int q = 0; q < 2; q++) {
+            int j1 = sel_j1[q], j2 = sel_j2[q];
+            int j3 = k2;
+            int j4 = step(k2, 1);
+            if (exists_bound(j4)) {
+                if (exists_bound(j1)) check_junction(dc, j1, j2, j3, j4, k1, k2);
+            }
+            j3 = bound(k2);
+            j4 = step(j3, -1);
+            if (exists_bound(j4)) {
+                if (exists_bound(j1)) check_junction(dc, j1, j2, j3, j4, k1, k2);
+            }
+        }
+    }
+
+    // origami_potential.cpp:231-286
+    LDO_HDN void check_constraints(DeltaConfig& dc, int cd, int j) const {
+        for (int i = -1; i <= 0; i++) {
+            int d1 = step(cd, i);
+            int d2 = step(cd, i + 1);
+            if (!(exists_bound(d1) && exists_bound(d2))) continue;
+            int b1 = bound(d1), b2 = bound(d2);
+            if (chain(b1) == chain(b2)) {
+                if (dindex(b1) == dindex(b2) - 1) doubly_contig_helix_pair(dc, d1, d2, i, j);
+                else if (dindex(b1) == dindex(b2) + 1) doubly_contig_junction_pair(dc, d1, d2, j);
+                else regular_pair_constraints(dc, d1, d2, i);
+            }
+            else {
+                regular_pair_constraints(dc, d1, d2, i);
+            }
+            if (dc.violated) return;
+        }
+        int prev = step(cd, -1);
+        int forw = step(cd, 1);
+        if (exists_bound(prev) && exists_bound(forw)) {
+            if (pair_stacked(cd, forw)) {
+                if (pair_stacked(prev, cd)) {
+                    if (doubly_contiguous(prev, cd) && doubly_contiguous(cd, forw)) {
+                        triply_contig_helix(dc, prev, cd, forw);
+                        if (dc.violated) return;
+                    }
+                    triplet_double_stacking(dc, prev, cd, forw);
+                }
+                else {
+                    triplet_single_stacking(dc, prev, cd, forw);
+                }
+            }
+        }
+    }
+
+    // JunctionBindingPotential::calc_stacking_and_steric_terms (origami_potential.cpp:212-229)
+    LDO_HDN void stacking_and_steric_terms(DeltaConfig& dc, int di, int dj) const {
+        check_constraints(dc, di, 0);
+        if (dc.violated) return;
+        check_constraints(dc, dj, 1);
+        if (dc.violated) return;
+        central_triplet_combos(dc, di, dj);
+    }
+
+    // BindingPotential::check_stacking (origami_potential.cpp:149-156)
+    LDO_HD DeltaConfig check_stacking(int di, int dj) const {
+        DeltaConfig dc;
+        dc.e = 0;
+        dc.stacked = 0;
+        dc.violated = false;
+        stacking_and_steric_terms(dc, di, dj);
+        return dc;
+    }
+
+    // OrigamiPotential::bind_domain (origami_potential.cpp:1282-1293) on the (possibly overlaid) pair
+    LDO_HD DeltaConfig bind_domain(int di) const {
+        int dj = bound(di);
+        DeltaConfig dc;
+        dc.e = 0;
+        dc.stacked = 0;
+        dc.violated = false;
+        bool opposing = ore(di) == -ore(dj);
+        if (ident(di) == -ident(dj)) {
+            // BindingPotential::bind_domains (origami_potential.cpp:131-147)
+            if (!opposing) {
+                dc.violated = true;
+                return dc;
+            }
+            stacking_and_steric_terms(dc, di, dj);
+            if (dc.violated) {
+                dc.e = 0;
+                dc.stacked = 0;
+                return dc;
+            }
+            dc.e += hyb_energy(di, dj);
+        }
+        else {
+            // origami_potential.cpp:938-950
+            if (sc->misbinding_pot == MISBIND_DISALLOWED || !opposing) {
+                dc.violated = true;
+                return dc;
+            }
+            dc.e += hyb_energy(di, dj);
+        }
+        return dc;
+    }
+
+    // -----------------------------------------------------------------------------------------
+    // Read-only evaluation of placing unassigned domain d at (p, o): what
+    // OrigamiSystem::check_domain_constraints (origami_system.cpp:343-355, 828-871) returns, without
+    // touching the state. `new_state` receives the state d would take.
+    // -----------------------------------------------------------------------------------------
+    LDO_HDN DeltaConfig eval_place(int d, V3 p, int o, int* new_state, int* partner) {
+        DeltaConfig dc;
+        dc.e = 0;
+        dc.stacked = 0;
+        dc.violated = false;
+        int j = occupant(p);
+        *partner = -1;
+        if (j < 0) {
+            *new_state = ST_UNBOUND;
+            return dc;
+        }
+        int sj = s->dom[j].state;
+        if (sj != ST_UNBOUND) {
+            dc.violated = true;
+            *new_state = ST_UNASSIGNED;
+            return dc;
+        }
+        *partner = j;
+        bool comp = s->ident[d] == -s->ident[j];
+        od = d;
+        oj = j;
+        orec.x = (short)p.x;
+        orec.y = (short)p.y;
+        orec.z = (short)p.z;
+        orec.ore = (int8_t)o;
+        orec.state = comp ? ST_BOUND : ST_MISBOUND;
+        *new_state = orec.state;
+        dc = bind_domain(d);
+        od = -1;
+        oj = -1;
+        if (sc->apply_mean_field_cor && !dc.violated && comp) {
+            // origami_system.cpp:858-868 (counter already incremented in the reference at this point)
+            int nfb = s->num_fully_bound_pairs + 1;
+            if (nfb == 1) dc.e += 2 * log(6.0);
+            else if (nfb == 2) dc.e += log(3.0);
+        }
+        return dc;
+    }
+
+    // ---- mutation ----
+    LDO_HD void write_dom(int d, V3 p, int o) {
+        DomRec& r = s->dom[d];
+        r.x = (short)p.x;
+        r.y = (short)p.y;
+        r.z = (short)p.z;
+        r.ore = (int8_t)o;
+    }
+
+    // update_domain + update_occupancies (origami_system.cpp:762-806)
+    LDO_HDN void commit_place(int d, V3 p, int o) {
+        write_dom(d, p, o);
+        int j = occupant(p);
+        if (j < 0) {
+            s->dom[d].state = ST_UNBOUND;
+            s->bound[d] = -1;
+            table_put(p, d);
+            return;
+        }
+        if (s->dom[j].state != ST_UNBOUND) {
+            fail(LDO_ERR_BIND_BOUND, d);
+            return;
+        }
+        s->num_bound_pairs += 1;
+        uint8_t ns;
+        if (s->ident[d] == -s->ident[j]) {
+            ns = ST_BOUND;
+            s->num_fully_bound_pairs += 1;
+        }
+        else {
+            if (s->dchain[d] == s->dchain[j]) s->num_self_bound_pairs += 1;
+            ns = ST_MISBOUND;
+        }
+        s->dom[d].state = ns;
+        s->dom[j].state = ns;
+        s->bound[d] = (short)j;
+        s->bound[j] = (short)d;
+    }
+
+    // OrigamiSystem::set_domain_config (origami_system.cpp:517-541). Sets constraints_violated.
+    LDO_HDN double set_domain_config(int d, V3 p, int o) {
+        if (s->dom[d].state != ST_UNASSIGNED) {
+            fail(LDO_ERR_SET_ASSIGNED, d);
+            return 0;
+        }
+        int ns, partner;
+        DeltaConfig dc = eval_place(d, p, o, &ns, &partner);
+        if (ns == ST_UNASSIGNED) {
+            // site already bound/misbound: position and orientation are left untouched (:838-845)
+            s->constraints_violated = 1;
+            return dc.e;
+        }
+        if (partner < 0) {
+            // unassigned site: the sticky violation flag is NOT cleared (App. A8, :852-855)
+            if (s->constraints_violated) {
+                write_dom(d, p, o); // reverted by internal_unassign_domain, pos/ore stay
+                return dc.e;
+            }
+            commit_place(d, p, o);
+            s->num_unassigned--;
+            return dc.e;
+        }
+        s->constraints_violated = dc.violated ? 1 : 0;
+        if (dc.violated) {
+            write_dom(d, p, o);
+            return dc.e;
+        }
+        commit_place(d, p, o);
+        s->energy += dc.e;
+        s->num_stacked_pairs += dc.stacked;
+        s->num_unassigned--;
+        return dc.e;
+    }
+
+    // OrigamiSystem::check_domain_constraints (origami_system.cpp:343-355): side-effect free apart
+    // from the violation flag and (as in the reference) the stored position/orientation of d.
+    LDO_HDN double check_domain_constraints(int d, V3 p, int o) {
+        int ns, partner;
+        DeltaConfig dc = eval_place(d, p, o, &ns, &partner);
+        if (ns == ST_UNASSIGNED) {
+            s->constraints_violated = 1;
+            return dc.e;
+        }
+        write_dom(d, p, o);
+        if (partner >= 0) s->constraints_violated = dc.violated ? 1 : 0;
+        return dc.e;
+    }
+
+    // OrigamiSystem::set_checked_domain_config (origami_system.cpp:478-515)
+    LDO_HDN double set_checked_domain_config(int d, V3 p, int o) {
+        commit_place(d, p, o);
+        double delta_e = 0;
+        int st = s->dom[d].state;
+        if (st == ST_MISBOUND) {
+            delta_e += hyb_energy(d, s->bound[d]);
+        }
+        else if (st == ST_BOUND) {
+            delta_e += hyb_energy(d, s->bound[d]);
+            DeltaConfig dc = check_stacking(d, s->bound[d]);
+            delta_e += dc.e;
+            s->num_stacked_pairs += dc.stacked;
+        }
+        if (sc->apply_mean_field_cor && st == ST_BOUND) {
+            if (s->num_fully_bound_pairs == 1) delta_e += 2 * log(6.0);
+            else if (s->num_fully_bound_pairs == 2) delta_e += log(3.0);
+        }
+        s->energy += delta_e;
+        s->num_unassigned--;
+        return delta_e;
+    }
+
+    // internal_unassign_domain + unassign_domain (origami_system.cpp:375-385, 695-760)
+    LDO_HDN double unassign_domain(int d) {
+        int st = s->dom[d].state;
+        double e = 0;
+        int stacked = 0;
+        if (st == ST_BOUND || st == ST_MISBOUND) {
+            int j = s->bound[d];
+            s->num_bound_pairs -= 1;
+            if (st == ST_BOUND) {
+                s->num_fully_bound_pairs -= 1;
+                DeltaConfig dc = check_stacking(d, j);
+                e = -dc.e;
+                stacked = -dc.stacked;
+            }
+            else if (s->dchain[j] == s->dchain[d]) {
+                s->num_self_bound_pairs -= 1;
+            }
+            e += -hyb_energy(d, j);
+            s->bound[d] = -1;
+            s->bound[j] = -1;
+            s->dom[d].state = ST_UNASSIGNED;
+            s->dom[j].state = ST_UNBOUND;
+            const DomRec& r = s->dom[d];
+            table_put(v3(r.x, r.y, r.z), j);
+            if (sc->apply_mean_field_cor && st == ST_BOUND) {
+                if (s->num_fully_bound_pairs == 0) e -= 2 * log(6.0);
+                else if (s->num_fully_bound_pairs == 1) e -= log(3.0);
+            }
+        }
+        else if (st == ST_UNBOUND) {
+            const DomRec& r = s->dom[d];
+            table_erase(v3(r.x, r.y, r.z));
+            s->dom[d].state = ST_UNASSIGNED;
+        }
+        else {
+            // double unassignment is allowed (:720-724): the two counter updates cancel
+            s->num_unassigned--;
+        }
+        s->energy += e;
+        s->num_stacked_pairs += stacked;
+        s->num_unassigned++;
+        return e;
+    }
+
+    // ---- chains ----
+    // add_chain(c_i_ident, c_i) (origami_system.cpp:402-443). Returns the chain slot.
+    LDO_HDN int add_chain_with_uid(int type, int uid) {
+        int c = -1;
+        for (int k = 1; k < K::C; k++) {
+            if (!s->chain_used[k]) {
+                c = k;
+                break;
+            }
+        }
+        int len = sc->type_len[type];
+        if (c < 0 || len > sc->lmax || chain_base(c) + len > K::D) {
+            fail(LDO_ERR_CAPACITY, type);
+            return -1;
+        }
+        s->chain_used[c] = 1;
+        s->chain_uid[c] = uid;
+        s->chain_type[c] = (uint16_t)type;
+        s->chain_len[c] = (uint16_t)len;
+        s->order[s->n_chains] = (uint16_t)c;
+        s->n_chains++;
+        s->type_count[type]++;
+        s->num_staples++;
+        int base = chain_base(c);
+        for (int i = 0; i < len; i++) {
+            int d = base + i;
+            s->dom[d].x = 0;
+            s->dom[d].y = 0;
+            s->dom[d].z = 0;
+            s->dom[d].ore = ORE_ZERO;
+            s->dom[d].state = ST_UNASSIGNED;
+            s->bound[d] = -1;
+            s->ident[d] = sc->idents[sc->type_off[type] + i];
+            s->dchain[d] = (uint16_t)c;
+            s->dindex[d] = (uint16_t)i;
+            s->num_domains++;
+            s->num_unassigned++;
+        }
+        return c;
+    }
+    // add_chain(c_i_ident) (origami_system.cpp:387-400)
+    LDO_HD int add_chain(int type) {
+        s->current_c_i += 1;
+        if (sc->apply_mean_field_cor) s->energy += log(6.0);
+        s->energy += tt.init_energy;
+        return add_chain_with_uid(type, s->current_c_i);
+    }
+    // delete_chain (origami_system.cpp:445-472); the chain's domains must be unassigned
+    LDO_HDN void delete_chain(int c) {
+        int w = -1;
+        for (int k = 0; k < s->n_chains; k++) {
+            if (s->order[k] == c) {
+                w = k;
+                break;
+            }
+        }
+        if (w < 0) {
+            fail(LDO_ERR_INTERNAL, c);
+            return;
+        }
+        for (int k = w; k + 1 < s->n_chains; k++) s->order[k] = s->order[k + 1];
+        s->n_chains--;
+        int len = s->chain_len[c];
+        s->type_count[s->chain_type[c]]--;
+        s->num_domains -= len;
+        s->num_staples--;
+        s->num_unassigned -= len;
+        s->chain_used[c] = 0;
+        if (sc->apply_mean_field_cor) s->energy -= log(6.0);
+        s->energy -= tt.init_energy;
+    }
+
+    // k-th staple of a given identity in insertion order (m_identity_to_index[type][k]; App. B)
+    LDO_HD int staple_of_type(int type, int k) const {
+        for (int w = 1; w < s->n_chains; w++) {
+            int c = s->order[w];
+            if (s->chain_type[c] == type) {
+                if (k == 0) return c;
+                k--;
+            }
+        }
+        return -1;
+    }
+
+    // Domain at position `index` of the concatenation of chains in working order (movetypes.cpp:98-113)
+    LDO_HD int domain_by_flat_index(int index) const {
+        for (int w = 0; w < s->n_chains; w++) {
+            int c = s->order[w];
+            int len = s->chain_len[c];
+            if (index < len) return chain_base(c) + index;
+            index -= len;
+        }
+        return -1;
+    }
+
+    // ---- whole-system passes ----
+    // OrigamiSystem::center (origami_system.cpp:553-571)
+    LDO_HDN void center(int centering_domain) {
+        const DomRec& c0 = s->dom[chain_base(0) + centering_domain];
+        V3 ref = v3(c0.x, c0.y, c0.z);
+        table_clear();
+        for (int w = 0; w < s->n_chains; w++) {
+            int c = s->order[w];
+            int base = chain_base(c);
+            for (int i = 0; i < s->chain_len[c]; i++) {
+                DomRec& r = s->dom[base + i];
+                r.x = (short)(r.x - ref.x);
+                r.y = (short)(r.y - ref.y);
+                r.z = (short)(r.z - ref.z);
+                if (r.state != ST_UNASSIGNED) table_put(v3(r.x, r.y, r.z), base + i);
+            }
+        }
+        // a site shared by a bound pair must resolve to a valid occupant: either is fine
+    }
+
+    // set_all_domains() + check_distance_constraints (origami_system.cpp:357-373, 573-586)
+    LDO_HDN bool set_all_domains() {
+        for (int w = 0; w < s->n_chains; w++) {
+            int c = s->order[w];
+            int base = chain_base(c);
+            for (int i = 0; i < s->chain_len[c]; i++) {
+                int d = base + i;
+                const DomRec r = s->dom[d];
+                set_domain_config(d, v3(r.x, r.y, r.z), r.ore);
+                if (s->constraints_violated) {
+                    fail(LDO_ERR_CONSTRAINTS, d);
+                    return false;
+                }
+            }
+        }
+        for (int w = 0; w < s->n_chains; w++) {
+            int c = s->order[w];
+            int base = chain_base(c);
+            for (int i = 0; i < s->chain_len[c]; i++) {
+                int d = base + i;
+                int n = step(d, 1);
+                if (n < 0) continue;
+                const DomRec& a = s->dom[d];
+                const DomRec& b = s->dom[n];
+                if (abs(b.x - a.x) + abs(b.y - a.y) + abs(b.z - a.z) != 1) {
+                    fail(LDO_ERR_DISTANCE, d);
+                    return false;
+                }
+            }
+        }
+        return true;
+    }
+
+    LDO_HD void unassign_all() {
+        for (int w = 0; w < s->n_chains; w++) {
+            int c = s->order[w];
+            int base = chain_base(c);
+            for (int i = 0; i < s->chain_len[c]; i++) unassign_domain(base + i);
+        }
+    }
+
+    // OrigamiSystem::check_all_constraints (origami_system.cpp:267-325)
+    LDO_HDN bool check_all_constraints() {
+        if (s->num_unassigned != 0) {
+            fail(LDO_ERR_UNASSIGNED_AT_CHECK);
+            return false;
+        }
+        for (int w = 0; w < s->n_chains; w++) {
+            int c = s->order[w];
+            int base = chain_base(c);
+            for (int i = 0; i < s->chain_len[c]; i++) {
+                if (s->dom[base + i].state == ST_UNASSIGNED) {
+                    fail(LDO_ERR_UNASSIGNED_AT_CHECK, base + i);
+                    return false;
+                }
+                unassign_domain(base + i);
+            }
+        }
+        int ns = s->n_chains - 1;
+        if (sc->apply_mean_field_cor) s->energy -= ns * log(6.0);
+        s->energy -= ns * tt.init_energy;
+        if (s->num_stacked_pairs != 0) {
+            int sp = s->num_stacked_pairs;
+            set_all_domains();
+            fail(LDO_ERR_STACK_COUNT, sp);
+            return false;
+        }
+        double eps = 0.000001;
+        if (s->energy < -eps || s->energy > eps) {
+            set_all_domains();
+            fail(LDO_ERR_ENERGY_DRIFT);
+            return false;
+        }
+        s->energy = 0;
+        if (!set_all_domains()) return false;
+        if (sc->apply_mean_field_cor) s->energy += ns * log(6.0);
+        s->energy += ns * tt.init_energy;
+        return true;
+    }
+
+    // OrigamiSystem::update_energy (origami_system.cpp:808-826), after new tables were installed
+    LDO_HDN bool update_energy() {
+        unassign_all();
+        s->energy = 0;
+        int ns = s->n_chains - 1;
+        if (sc->apply_mean_field_cor) s->energy += ns * log(6.0);
+        s->energy += ns * tt.init_energy;
+        return set_all_domains();
+    }
+
+    // OrigamiSystem::update_enthalpy_and_entropy (origami_system.cpp:204-246)
+    LDO_HDN void enthalpy_and_entropy(double* enthalpy, double* entropy, double* stacking) const {
+        double H = 0, S = 0;
+        for (int w = 0; w < s->n_chains; w++) {
+            int c = s->order[w];
+            int base = chain_base(c);
+            for (int i = 0; i < s->chain_len[c]; i++) {
+                int d = base + i;
+                int st = s->dom[d].state;
+                if (st == ST_BOUND || st == ST_MISBOUND) {
+                    int j = s->bound[d];
+                    // the pair is counted when its first member (in working order) is visited
+                    bool j_first = false;
+                    int cj = s->dchain[j];
+                    if (cj == c) {
+                        j_first = s->dindex[j] < i;
+                    }
+                    else {
+                        for (int w2 = 0; w2 < w; w2++) {
+                            if (s->order[w2] == cj) {
+                                j_first = true;
+                                break;
+                            }
+                        }
+                    }
+                    if (!j_first) {
+                        H += hyb_enthalpy(d, j);
+                        S += hyb_entropy(d, j);
+                    }
+                }
+            }
+        }
+        int ns = s->n_chains - 1;
+        if (sc->apply_mean_field_cor) {
+            S -= ns * log(6.0);
+            if (s->num_fully_bound_pairs >= 1) S -= 2 * log(6.0);
+            if (s->num_fully_bound_pairs >= 2) S -= log(3.0);
+        }
+        H += ns * tt.init_enthalpy;
+        S += ns * tt.init_entropy;
+        *enthalpy = H;
+        *entropy = S;
+        *stacking = s->energy - (H - S);
+    }
+};
+
+} // namespace ldo

@@ -1,0 +1,1574 @@
+// ldo_engine.cu — kernels and C-ABI (include/ldo_b200.h) of the replica-batched Monte Carlo engine.
+//
+// Data layout in HBM (per engine = per GPU):
+//   states[R]   SysState<K>   persistent configuration of every replica (array of structs; one
+//                             replica is a contiguous, 16-byte aligned blob so that a warp stages it
+//                             to / from shared memory with coalesced 128-bit loads and stores)
+//   aux[R]      RepAux        RNG state, control variables, bias state, move statistics, step counter
+//   tables      TempTables[n_temps] + fp64 hybridization tables (shared by all replicas at a temperature)
+// One warp owns one replica for the whole launch: the state lives in shared memory while the warp
+// runs its `n_steps` moves (small systems), or stays in HBM/L2 and is accessed in place (large
+// systems whose state + move scratch exceed the per-warp shared-memory budget).
+//
+// With LDO_HOSTSIM defined (tests/hostsim only) the same per-replica functions are driven by a plain
+// host loop with one emulated lane, for sanitizer/debug runs of the device logic on a machine without
+// a GPU. That build is never part of the shipped library: the product path is CUDA only.
+
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+#include "ldo_moves.cuh"
+#include "../../include/ldo_b200.h"
+
+using namespace ldo;
+
+// ---------------------------------------------------------------------------------------------
+// Backend
+// ---------------------------------------------------------------------------------------------
+#ifdef LDO_HOSTSIM
+#define LDO_GLOBAL
+typedef int dev_stream_t;
+static int dev_malloc(void** p, size_t n) {
+    *p = calloc(1, n ? n : 1);
+    return *p ? 0 : -1;
+}
+static void dev_free(void* p) { free(p); }
+static int dev_h2d(void* d, const void* h, size_t n, dev_stream_t) {
+    memcpy(d, h, n);
+    return 0;
+}
+static int dev_d2h(void* h, const void* d, size_t n, dev_stream_t) {
+    memcpy(h, d, n);
+    return 0;
+}
+static int dev_memset(void* d, int v, size_t n, dev_stream_t) {
+    memset(d, v, n);
+    return 0;
+}
+static int dev_sync(dev_stream_t) { return 0; }
+static const char* dev_err() { return "hostsim"; }
+#else
+#include <cuda_runtime.h>
+#define LDO_GLOBAL __global__
+typedef cudaStream_t dev_stream_t;
+static cudaError_t g_last_cuda = cudaSuccess;
+static int chk(cudaError_t e) {
+    if (e != cudaSuccess) {
+        g_last_cuda = e;
+        return -1;
+    }
+    return 0;
+}
+static int dev_malloc(void** p, size_t n) {
+    if (chk(cudaMalloc(p, n ? n : 1))) return -1;
+    return chk(cudaMemset(*p, 0, n ? n : 1));
+}
+static void dev_free(void* p) { cudaFree(p); }
+static int dev_h2d(void* d, const void* h, size_t n, dev_stream_t s) {
+    if (chk(cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, s))) return -1;
+    return chk(cudaStreamSynchronize(s));
+}
+static int dev_d2h(void* h, const void* d, size_t n, dev_stream_t s) {
+    if (chk(cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, s))) return -1;
+    return chk(cudaStreamSynchronize(s));
+}
+static int dev_memset(void* d, int v, size_t n, dev_stream_t s) { return chk(cudaMemsetAsync(d, v, n, s)); }
+static int dev_sync(dev_stream_t s) { return chk(cudaStreamSynchronize(s)); }
+static const char* dev_err() { return cudaGetErrorString(g_last_cuda); }
+#endif
+
+// ---------------------------------------------------------------------------------------------
+// Per-replica auxiliary state and shared (read-only) engine constants
+// ---------------------------------------------------------------------------------------------
+
+#define LDO_GRID_CAP 512 // grid-bias points per replica (sum over grid biases)
+
+struct RepAux {
+    Rng rng;
+    Control ctl;
+    BiasState bs;
+    MoveStats stats;
+    long long step;
+};
+
+struct Shared {
+    SysConst sc;
+    MoveSet ms;
+    OpsBiasConst ob;
+    int n_temps;
+    int has_grid;
+};
+
+enum {
+    OP_RUN = 0,
+    OP_LOAD_CONFIG = 1,
+    OP_UPDATE_ENERGY = 2,
+    OP_CHECK_CONSTRAINTS = 3,
+    OP_CENTER = 4,
+    OP_OBSERVE = 5,
+    OP_RECOMPUTE = 6
+};
+
+struct OpArgs {
+    int op;
+    int n_replicas;
+    int only_replica; // -1 = all
+    long long n_steps;
+    int centering_freq, centering_domain, constraint_check_freq;
+    // LOAD_CONFIG staging: one configuration applied to the selected replicas
+    int cfg_n_chains;
+    const int* cfg_chain_index;
+    const int* cfg_chain_ident;
+    const int* cfg_chain_len;
+    const int* cfg_pos;
+    const int* cfg_ore;
+    // OBSERVE / RECOMPUTE outputs
+    double* out_energies; // [R][5]
+    int* out_counters; // [R][9]
+    int* out_ops; // [R][n_ops]
+    int* out_staples; // [R][n_types - 1]
+    double* out_dependent; // [R][3 + n_types - 1] (exchange quantities)
+    int* out_status; // [R][2]
+    double* out_recomputed; // [R]
+    int* out_recomputed_stacked; // [R]
+};
+
+template <class K>
+struct DevPtrs {
+    SysState<K>* states;
+    MoveScratch<K>* scratch; // only for the in-place (non-staged) path
+    RepAux* aux;
+    const Shared* shared;
+    const TempTables* tables;
+    double* grid_vals; // [R][LDO_GRID_CAP]
+    long long* grid_visits; // [R][LDO_GRID_CAP]
+};
+
+// ---------------------------------------------------------------------------------------------
+// Per-replica operations (host+device; executed warp-uniformly)
+// ---------------------------------------------------------------------------------------------
+
+template <class K>
+LDO_HD void rep_init_engine(Engine<K>& eng, SysState<K>* st, MoveScratch<K>* ms, RepAux* aux, const DevPtrs<K>& P, int r) {
+    const Shared* sh = P.shared;
+    eng.sys.init(st, &sh->sc, P.tables[aux->ctl.temp_idx]);
+    eng.m = ms;
+    eng.rng = &aux->rng;
+    eng.ms = &sh->ms;
+    eng.ob = &sh->ob;
+    eng.bs = &aux->bs;
+    eng.grid_vals = P.grid_vals ? P.grid_vals + (size_t)r * LDO_GRID_CAP : nullptr;
+    eng.ctl = aux->ctl;
+    eng.stats = &aux->stats;
+}
+
+template <class K>
+LDO_HD void rep_refresh_stack_energy(SysState<K>* st, const Shared* sh, const Control& ctl) {
+    // OrigamiPotential::update_temp scales the Constant stacking energy (origami_potential.cpp:1026-1029,1219)
+    st->stack_e = sh->sc.stacking_ene * ctl.stacking_mult / ctl.temp;
+}
+
+// Bias bookkeeping restart (SystemBiases constructor: every m_bias evaluated once, bias_functions.cpp:60-66,423-426)
+template <class K>
+LDO_HD void rep_init_biases(Engine<K>& eng) {
+    eng.update_move_params();
+    eng.bs->move_update_bias = 0;
+    for (int b = 0; b < eng.ob->n_biases; b++) {
+        eng.bs->bias_val[b] = eng.calc_bias_fn(b);
+        eng.bs->move_update_bias += eng.bs->bias_val[b];
+    }
+}
+
+// set_config (origami_system.cpp:327-341) + the constructor's initialisation (:41-71, 659-693)
+template <class K>
+LDO_HD void rep_load_config(Engine<K>& eng, const OpArgs& a) {
+    System<K>& sys = eng.sys;
+    SysState<K>* s = sys.s;
+    const SysConst* sc = sys.sc;
+    s->status = LDO_OK;
+    s->status_detail = 0;
+    s->constraints_violated = 0;
+    sys.table_clear();
+    for (int c = 0; c < K::C; c++) s->chain_used[c] = 0;
+    for (int t = 0; t < K::T; t++) s->type_count[t] = 0;
+    s->n_chains = 0;
+    s->num_staples = 0;
+    s->num_domains = 0;
+    s->num_bound_pairs = 0;
+    s->num_fully_bound_pairs = 0;
+    s->num_self_bound_pairs = 0;
+    s->num_stacked_pairs = 0;
+    s->num_unassigned = 0;
+    s->energy = 0;
+    // scaffold (initialize_scaffold, :680-693)
+    {
+        int len = sc->type_len[0];
+        s->chain_used[0] = 1;
+        s->chain_uid[0] = a.cfg_chain_index[0];
+        s->chain_type[0] = 0;
+        s->chain_len[0] = (uint16_t)len;
+        s->order[0] = 0;
+        s->n_chains = 1;
+        s->type_count[0] = 1;
+        for (int i = 0; i < len; i++) {
+            s->dom[i].state = ST_UNASSIGNED;
+            s->bound[i] = -1;
+            s->ident[i] = sc->idents[sc->type_off[0] + i];
+            s->dchain[i] = 0;
+            s->dindex[i] = (uint16_t)i;
+            s->num_domains++;
+            s->num_unassigned++;
+        }
+    }
+    // staples (initialize_staples, :659-678)
+    int max_uid = a.cfg_chain_index[0];
+    for (int i = 1; i < a.cfg_n_chains; i++) {
+        sys.add_chain_with_uid(a.cfg_chain_ident[i], a.cfg_chain_index[i]);
+        if (a.cfg_chain_index[i] > max_uid) max_uid = a.cfg_chain_index[i];
+    }
+    int ns = a.cfg_n_chains - 1;
+    if (sc->apply_mean_field_cor) s->energy += ns * log(6.0);
+    s->energy += ns * sys.tt.init_energy;
+    s->current_c_i = max_uid;
+    if (s->status != LDO_OK) return;
+    // positions and orientations, then set_all_domains (:588-616)
+    int k = 0;
+    for (int w = 0; w < s->n_chains; w++) {
+        int c = s->order[w];
+        int base = sys.chain_base(c);
+        for (int i = 0; i < s->chain_len[c]; i++) {
+            V3 p = v3(a.cfg_pos[3 * k], a.cfg_pos[3 * k + 1], a.cfg_pos[3 * k + 2]);
+            V3 o = v3(a.cfg_ore[3 * k], a.cfg_ore[3 * k + 1], a.cfg_ore[3 * k + 2]);
+            int oc = ore_code(o);
+            if (oc == 7) oc = ORE_ZERO;
+            sys.write_dom(base + i, p, oc);
+            k++;
+        }
+    }
+    sys.set_all_domains();
+    rep_init_biases(eng);
+}
+
+template <class K>
+LDO_HD void rep_observe(Engine<K>& eng, const OpArgs& a, int r) {
+    System<K>& sys = eng.sys;
+    const SysState<K>* s = sys.s;
+    int nst = sys.sc->n_types - 1;
+    if (a.out_energies) {
+        double H, S, stk;
+        sys.enthalpy_and_entropy(&H, &S, &stk);
+        double* o = a.out_energies + (size_t)r * 5;
+        o[0] = s->energy;
+        o[1] = H;
+        o[2] = S;
+        o[3] = stk;
+        o[4] = eng.total_bias();
+    }
+    if (a.out_dependent) {
+        // PTGCMCSimulation::update_dependent_qs (ptmc_simulation.cpp:152-161) + staple counts
+        double H, S, stk;
+        sys.enthalpy_and_entropy(&H, &S, &stk);
+        double* o = a.out_dependent + (size_t)r * (3 + nst);
+        o[0] = H;
+        o[1] = eng.total_bias();
+        o[2] = stk;
+        for (int t = 0; t < nst; t++) o[3 + t] = (double)s->type_count[t + 1];
+    }
+    if (a.out_counters) {
+        int* o = a.out_counters + (size_t)r * 9;
+        o[0] = s->num_staples;
+        o[1] = s->num_domains;
+        o[2] = s->num_bound_pairs;
+        o[3] = s->num_fully_bound_pairs;
+        o[4] = s->num_self_bound_pairs;
+        o[5] = s->num_bound_pairs - s->num_fully_bound_pairs;
+        o[6] = s->num_stacked_pairs;
+        o[7] = s->num_unassigned;
+        o[8] = s->current_c_i;
+    }
+    if (a.out_ops) {
+        eng.update_move_params();
+        for (int i = 0; i < eng.ob->n_ops; i++) a.out_ops[(size_t)r * eng.ob->n_ops + i] = eng.bs->op_val[i];
+    }
+    if (a.out_staples) {
+        for (int t = 0; t < nst; t++) a.out_staples[(size_t)r * nst + t] = s->type_count[t + 1];
+    }
+    if (a.out_status) {
+        a.out_status[2 * (size_t)r] = s->status;
+        a.out_status[2 * (size_t)r + 1] = s->status_detail;
+    }
+}
+
+// USGCMCSimulation::update_internal (us_simulation.cpp:262-266): visit count of the current grid point
+template <class K>
+LDO_HD void rep_count_grid_visit(Engine<K>& eng, long long* visits) {
+    for (int b = 0; b < eng.ob->n_biases; b++) {
+        if (eng.ob->biases[b].type != BIAS_GRID) continue;
+        int off = eng.bs->grid_off[b];
+        if (off < 0) continue;
+        const BiasDef& bd = eng.ob->biases[b];
+        int idx = 0;
+        bool inside = true;
+        for (int k = 0; k < bd.n_ops; k++) {
+            int v = eng.bs->op_val[bd.op_idx[k]] - eng.bs->grid_lo[b][k];
+            if (v < 0 || v >= eng.bs->grid_n[b][k]) {
+                inside = false;
+                break;
+            }
+            idx = idx * eng.bs->grid_n[b][k] + v;
+        }
+        if (inside) visits[off + idx] += 1;
+    }
+}
+
+template <class K>
+LDO_HD void rep_execute(SysState<K>* st, MoveScratch<K>* ms, RepAux* aux, const DevPtrs<K>& P, const OpArgs& a, int r) {
+    Engine<K> eng;
+    rep_init_engine(eng, st, ms, aux, P, r);
+    switch (a.op) {
+    case OP_RUN: {
+        if (st->status != LDO_OK) break;
+        long long step = aux->step;
+        long long* visits = (P.shared->has_grid && P.grid_visits) ? P.grid_visits + (size_t)r * LDO_GRID_CAP : nullptr;
+        for (long long n = 0; n < a.n_steps; n++) {
+            step++;
+            eng.mc_step();
+            if (st->status != LDO_OK) break;
+            if (a.centering_freq != 0 && step % a.centering_freq == 0) eng.sys.center(a.centering_domain);
+            if (a.constraint_check_freq != 0 && step % a.constraint_check_freq == 0) {
+                if (!eng.sys.check_all_constraints()) break;
+            }
+            if (visits) {
+                eng.update_move_params();
+                rep_count_grid_visit(eng, visits);
+            }
+        }
+        aux->step = step;
+        break;
+    }
+    case OP_LOAD_CONFIG: {
+        rep_refresh_stack_energy(st, P.shared, aux->ctl);
+        rep_load_config(eng, a);
+        break;
+    }
+    case OP_UPDATE_ENERGY: {
+        // OrigamiSystem::update_temp -> update_energy (origami_system.cpp:618-622, 808-826)
+        rep_refresh_stack_energy(st, P.shared, aux->ctl);
+        if (st->status == LDO_OK) eng.sys.update_energy();
+        eng.update_move_params();
+        break;
+    }
+    case OP_CHECK_CONSTRAINTS: {
+        if (st->status == LDO_OK) eng.sys.check_all_constraints();
+        break;
+    }
+    case OP_CENTER: {
+        if (st->status == LDO_OK) eng.sys.center(a.centering_domain);
+        break;
+    }
+    case OP_OBSERVE: {
+        rep_observe(eng, a, r);
+        break;
+    }
+    case OP_RECOMPUTE: {
+        // tear down and rebuild the running energy on the staged copy (never written back)
+        eng.sys.update_energy();
+        a.out_recomputed[r] = st->energy;
+        a.out_recomputed_stacked[r] = st->num_stacked_pairs;
+        break;
+    }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Kernels: one warp per replica
+// ---------------------------------------------------------------------------------------------
+#ifndef LDO_HOSTSIM
+
+template <class T>
+__device__ inline void warp_copy16(T* dst, const T* src) {
+    static_assert(sizeof(T) % 16 == 0, "struct must be a multiple of 16 bytes");
+    const uint4* s = reinterpret_cast<const uint4*>(src);
+    uint4* d = reinterpret_cast<uint4*>(dst);
+    const int n = sizeof(T) / 16;
+    for (int i = threadIdx.x & 31; i < n; i += 32) d[i] = s[i];
+    __syncwarp();
+}
+
+template <class K>
+struct __align__(16) WarpSmem {
+    SysState<K> st;
+    MoveScratch<K> ms;
+};
+
+// Staged: the replica state is copied HBM -> shared memory (coalesced 128-bit), all moves run on
+// shared memory, and the state is copied back once at the end.
+template <class K>
+__global__ void __launch_bounds__(128) k_exec_staged(DevPtrs<K> P, OpArgs a, int warps_per_block) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    WarpSmem<K>* ws = reinterpret_cast<WarpSmem<K>*>(smem_raw);
+    int warp = threadIdx.x >> 5;
+    int r = blockIdx.x * warps_per_block + warp;
+    if (r >= a.n_replicas) return;
+    if (a.only_replica >= 0 && r != a.only_replica) return;
+    WarpSmem<K>& w = ws[warp];
+    warp_copy16(&w.st, &P.states[r]);
+    rep_execute<K>(&w.st, &w.ms, &P.aux[r], P, a, r);
+    __syncwarp();
+    if (a.op != OP_OBSERVE && a.op != OP_RECOMPUTE) warp_copy16(&P.states[r], &w.st);
+}
+
+// In place: state and scratch stay in HBM / L2 (large systems)
+template <class K>
+__global__ void __launch_bounds__(128) k_exec_inplace(DevPtrs<K> P, OpArgs a, int warps_per_block, SysState<K>* recompute_tmp) {
+    int warp = threadIdx.x >> 5;
+    int r = blockIdx.x * warps_per_block + warp;
+    if (r >= a.n_replicas) return;
+    if (a.only_replica >= 0 && r != a.only_replica) return;
+    SysState<K>* st = &P.states[r];
+    if (a.op == OP_RECOMPUTE) {
+        warp_copy16(&recompute_tmp[r], &P.states[r]);
+        st = &recompute_tmp[r];
+    }
+    rep_execute<K>(st, &P.scratch[r], &P.aux[r], P, a, r);
+}
+
+#endif // !LDO_HOSTSIM
+
+// ---------------------------------------------------------------------------------------------
+// Replica exchange (ptmc_simulation.cpp:255-412), decided on device
+// ---------------------------------------------------------------------------------------------
+
+struct ExchangeArgs {
+    int variant;
+    long long swap_i;
+    int n_ladders, ladder_len;
+    int global_first, n_local, n_global;
+    int n_staple_types;
+    unsigned long long seed;
+    const double* dependent; // [n_global][3 + nst]
+    int* slot_to_replica; // [n_ladders][ladder_len], updated in place (m_q_to_repi)
+    // control variables per slot of a ladder [ladder_len] (m_control_qs), fixed for the whole run
+    const int* slot_temp_idx;
+    const double* slot_temp;
+    const double* slot_staple_u_mult;
+    const double* slot_bias_mult;
+    const double* slot_stacking_mult;
+    long long* attempts; // [n_ladders][ladder_len - 1]
+    long long* accepts;
+    const double* reduced_staple_u; // [nst]: ln M - (2L-1) ln 6 (origami_system.cpp:965-990)
+    RepAux* aux; // local replicas
+};
+
+// One thread per ladder: the neighbour tests of one ladder are sequential in the reference only
+// through the shared RNG; here every (swap, ladder, pair) owns a Philox counter, so all ranks
+// reproduce the same decisions without communication.
+LDO_HD inline void exchange_ladder(const ExchangeArgs& x, int l) {
+    int nq = 3 + x.n_staple_types;
+    int* q2r = x.slot_to_replica + (size_t)l * x.ladder_len;
+    int swap_set = (int)(x.swap_i % 2);
+    for (int i = swap_set; i < x.ladder_len - 1; i += 2) {
+        size_t si = (size_t)i;
+        x.attempts[(size_t)l * (x.ladder_len - 1) + i]++;
+        int rep1 = q2r[i], rep2 = q2r[i + 1];
+        const double* d1 = x.dependent + (size_t)(l * x.ladder_len + rep1) * nq;
+        const double* d2 = x.dependent + (size_t)(l * x.ladder_len + rep2) * nq;
+        double temp1 = x.slot_temp[si], temp2 = x.slot_temp[si + 1];
+        double sm1 = x.slot_stacking_mult[si], sm2 = x.slot_stacking_mult[si + 1];
+        double um1 = x.slot_staple_u_mult[si], um2 = x.slot_staple_u_mult[si + 1];
+        // calc_acceptance_p (ptmc_simulation.cpp:275-313); the staple sum runs over the n_types - 1
+        // staple identities (the reference's loop bound reads one past the end, App. A1)
+        double DBU_DN = 0;
+        for (int t = 0; t < x.n_staple_types; t++) {
+            double N1 = d1[3 + t], N2 = d2[3 + t];
+            double u1 = x.reduced_staple_u[t] * temp1 * um1;
+            double u2 = x.reduced_staple_u[t] * temp2 * um2;
+            DBU_DN += (u2 / temp2 - u1 / temp1) * (N2 - N1);
+        }
+        double DB = 1 / temp2 - 1 / temp1;
+        double DH = d2[0] * temp2 - d1[0] * temp1;
+        double Dstacking = d2[2] * temp2 - d1[2] * temp1;
+        double DBM = sm2 / temp2 - sm1 / temp1;
+        double DBias = d2[1] * temp2 - d1[1] * temp1;
+        double p_accept = fmin(1.0, exp(DB * (DH + DBias) + DBM * Dstacking - DBU_DN));
+        bool accept;
+        if (p_accept == 1) {
+            accept = true;
+        }
+        else {
+            Rng g;
+            g.tape = nullptr;
+            g.key0 = (uint32_t)x.seed;
+            g.key1 = (uint32_t)(x.seed >> 32);
+            g.subseq = (uint32_t)(l * x.ladder_len + i);
+            g.stream = 0x45584348u; // "EXCH"
+            uint32_t o[4];
+            philox4x32_10(g, (unsigned long long)x.swap_i, o);
+            unsigned long long u = ((unsigned long long)o[0] << 32) | o[1];
+            double prob = (double)(u >> 11) * (1.0 / 9007199254740992.0);
+            accept = p_accept > prob;
+        }
+        if (accept) {
+            x.accepts[(size_t)l * (x.ladder_len - 1) + i]++;
+            q2r[i] = rep2;
+            q2r[i + 1] = rep1;
+        }
+    }
+    // master_send (ptmc_simulation.cpp:212-226): every replica receives the control variables of its slot
+    for (int i = 0; i < x.ladder_len; i++) {
+        int g = l * x.ladder_len + q2r[i];
+        int loc = g - x.global_first;
+        if (loc < 0 || loc >= x.n_local) continue;
+        size_t si = (size_t)i;
+        Control& c = x.aux[loc].ctl;
+        if (x.variant == LDO_PT_ST) {
+            c.temp_idx = x.slot_temp_idx[si];
+            c.temp = x.slot_temp[si];
+            c.stacking_mult = x.slot_stacking_mult[si];
+        }
+        else {
+            c.temp_idx = x.slot_temp_idx[si];
+            c.temp = x.slot_temp[si];
+            if (x.variant == LDO_PT_UT || x.variant == LDO_PT_HUT) c.staple_u_mult = x.slot_staple_u_mult[si];
+            if (x.variant == LDO_PT_HUT) c.bias_mult = x.slot_bias_mult[si];
+        }
+    }
+}
+
+#ifndef LDO_HOSTSIM
+__global__ void k_exchange(ExchangeArgs x) {
+    int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l < x.n_ladders) exchange_ladder(x, l);
+}
+#endif
+
+// ---------------------------------------------------------------------------------------------
+// Engine object
+// ---------------------------------------------------------------------------------------------
+
+typedef Caps<80, 26, 8, 16> CapsSmall; // snodin-class systems: staged in shared memory
+typedef Caps<512, 176, 11, 96> CapsLarge; // large scaffolds: in place in HBM/L2
+
+static std::string g_create_error;
+
+struct EngineBase {
+    virtual ~EngineBase() {}
+    std::string err;
+    int R = 0;
+    int device = 0;
+    Shared shared;
+    int n_ident = 0;
+    std::vector<double> temps;
+    std::vector<double> reduced_staple_u;
+    dev_stream_t stream;
+    int fail(const std::string& m) {
+        err = m;
+        return -1;
+    }
+    virtual int set_tables(int n_temps, int n_ident, const double* temps, const double* e, const double* h, const double* s, const double* init) = 0;
+    virtual int push_shared() = 0;
+    virtual int exec(OpArgs& a, bool sync) = 0;
+    virtual int get_aux(int first, int count, RepAux* out) = 0;
+    virtual int put_aux(int first, int count, const RepAux* in) = 0;
+    virtual int get_state_raw(int replica, std::vector<unsigned char>& blob) = 0;
+    virtual int decode_state(int replica, int* n_chains, int* ci, int* cid, int* cl, int* pos, int* ore, int* st, int* bd) = 0;
+    virtual void capacity(int* c, int* d) = 0;
+    virtual int set_grid(int replica, int bias, const int* lo, const int* n, const double* vals) = 0;
+    virtual int get_visits(int replica, int bias, long long* counts, int clear) = 0;
+    virtual int attach_tape(int replica, const ldo_tape_draw* draws, long long n) = 0;
+    virtual int exchange(ExchangeArgs& x, const double* dependent_host, int* slot_to_replica, long long* attempts, long long* accepts) = 0;
+    virtual int exchange_buffers(int n_global, void** send, void** recv, int* nq) = 0;
+    virtual int alloc_outputs() = 0;
+    // device output buffers
+    double* d_energies = nullptr;
+    int* d_counters = nullptr;
+    int* d_ops = nullptr;
+    int* d_staples = nullptr;
+    double* d_dependent = nullptr;
+    double* d_recomputed = nullptr;
+    int* d_recomputed_stacked = nullptr;
+    int* d_status = nullptr;
+    // control-variable ladder for replica exchange (m_control_qs, ptmc_simulation.cpp:341-346)
+    std::vector<int> ladder_temp_idx;
+    std::vector<double> ladder_staple_u_mult, ladder_bias_mult, ladder_stacking_mult;
+};
+
+template <class K, bool STAGED>
+struct EngineImpl: EngineBase {
+    DevPtrs<K> P;
+    Shared* d_shared = nullptr;
+    TempTables* d_tables = nullptr;
+    double* d_table_data = nullptr;
+    std::vector<void*> tape_bufs;
+    SysState<K>* d_recompute_tmp = nullptr;
+    int* d_cfg = nullptr;
+    size_t cfg_cap = 0;
+    // exchange
+    double* d_dep_all = nullptr;
+    int dep_all_n = 0;
+    int* d_q2r = nullptr;
+    long long* d_att = nullptr;
+    long long* d_acc = nullptr;
+    int* d_slot_tidx = nullptr;
+    double* d_slot_vals = nullptr;
+    double* d_red_u = nullptr;
+    int exch_cap = 0;
+    int warps_per_block = 4;
+
+    EngineImpl() {
+        memset(&P, 0, sizeof(P));
+        memset(&shared, 0, sizeof(shared));
+    }
+    ~EngineImpl() override {
+        dev_free(P.states);
+        dev_free(P.scratch);
+        dev_free(P.aux);
+        dev_free(d_shared);
+        dev_free(d_tables);
+        dev_free(d_table_data);
+        dev_free(P.grid_vals);
+        dev_free(P.grid_visits);
+        dev_free(d_recompute_tmp);
+        dev_free(d_cfg);
+        dev_free(d_energies);
+        dev_free(d_counters);
+        dev_free(d_ops);
+        dev_free(d_staples);
+        dev_free(d_dependent);
+        dev_free(d_recomputed);
+        dev_free(d_recomputed_stacked);
+        dev_free(d_status);
+        dev_free(d_dep_all);
+        dev_free(d_q2r);
+        dev_free(d_att);
+        dev_free(d_acc);
+        dev_free(d_slot_tidx);
+        dev_free(d_slot_vals);
+        dev_free(d_red_u);
+        for (void* p: tape_bufs) dev_free(p);
+#ifndef LDO_HOSTSIM
+        cudaStreamDestroy(stream);
+#endif
+    }
+
+    int init(int n_replicas) {
+        R = n_replicas;
+#ifndef LDO_HOSTSIM
+        if (chk(cudaSetDevice(device))) return fail(dev_err());
+        if (chk(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking))) return fail(dev_err());
+#else
+        stream = 0;
+#endif
+        if (dev_malloc((void**)&P.states, sizeof(SysState<K>) * R)) return fail(dev_err());
+        if (!STAGED) {
+            if (dev_malloc((void**)&P.scratch, sizeof(MoveScratch<K>) * R)) return fail(dev_err());
+            if (dev_malloc((void**)&d_recompute_tmp, sizeof(SysState<K>) * R)) return fail(dev_err());
+        }
+#ifdef LDO_HOSTSIM
+        if (STAGED && dev_malloc((void**)&P.scratch, sizeof(MoveScratch<K>))) return fail(dev_err());
+        if (STAGED && dev_malloc((void**)&d_recompute_tmp, sizeof(SysState<K>))) return fail(dev_err());
+#endif
+        if (dev_malloc((void**)&P.aux, sizeof(RepAux) * R)) return fail(dev_err());
+        if (dev_malloc((void**)&d_shared, sizeof(Shared))) return fail(dev_err());
+        P.shared = d_shared;
+        tape_bufs.assign(R, nullptr);
+        // default per-replica aux
+        std::vector<RepAux> aux(R);
+        memset(aux.data(), 0, sizeof(RepAux) * R);
+        for (int r = 0; r < R; r++) {
+            aux[r].ctl.temp_idx = 0;
+            aux[r].ctl.temp = 0;
+            aux[r].ctl.staple_u_mult = 1;
+            aux[r].ctl.bias_mult = 1;
+            aux[r].ctl.stacking_mult = 1;
+            aux[r].rng.subseq = (uint32_t)r;
+            for (int b = 0; b < LDO_MAX_BIASES; b++) aux[r].bs.grid_off[b] = -1;
+        }
+        if (dev_h2d(P.aux, aux.data(), sizeof(RepAux) * R, stream)) return fail(dev_err());
+        return alloc_outputs();
+    }
+
+    int alloc_outputs() override {
+        int nst = shared.sc.n_types - 1;
+        if (dev_malloc((void**)&d_energies, sizeof(double) * 5 * R)) return fail(dev_err());
+        if (dev_malloc((void**)&d_counters, sizeof(int) * 9 * R)) return fail(dev_err());
+        if (dev_malloc((void**)&d_ops, sizeof(int) * LDO_MAX_OPS * R)) return fail(dev_err());
+        if (dev_malloc((void**)&d_staples, sizeof(int) * (nst > 0 ? nst : 1) * R)) return fail(dev_err());
+        if (dev_malloc((void**)&d_dependent, sizeof(double) * (3 + nst) * R)) return fail(dev_err());
+        if (dev_malloc((void**)&d_recomputed, sizeof(double) * R)) return fail(dev_err());
+        if (dev_malloc((void**)&d_recomputed_stacked, sizeof(int) * R)) return fail(dev_err());
+        if (dev_malloc((void**)&d_status, sizeof(int) * 2 * R)) return fail(dev_err());
+        return 0;
+    }
+
+    int push_shared() override {
+        if (dev_h2d(d_shared, &shared, sizeof(Shared), stream)) return fail(dev_err());
+        if (shared.has_grid && !P.grid_vals) {
+            if (dev_malloc((void**)&P.grid_vals, sizeof(double) * LDO_GRID_CAP * R)) return fail(dev_err());
+            if (dev_malloc((void**)&P.grid_visits, sizeof(long long) * LDO_GRID_CAP * R)) return fail(dev_err());
+        }
+        return 0;
+    }
+
+    int set_tables(int n_temps, int nid, const double* tv, const double* e, const double* h, const double* s, const double* init) override {
+        n_ident = nid;
+        shared.sc.n_ident = nid;
+        shared.n_temps = n_temps;
+        size_t tsz = (size_t)(2 * nid + 1) * (2 * nid + 1);
+        dev_free(d_table_data);
+        dev_free(d_tables);
+        d_table_data = nullptr;
+        d_tables = nullptr;
+        if (dev_malloc((void**)&d_table_data, sizeof(double) * tsz * 3 * n_temps)) return fail(dev_err());
+        if (dev_malloc((void**)&d_tables, sizeof(TempTables) * n_temps)) return fail(dev_err());
+        std::vector<TempTables> tt(n_temps);
+        temps.assign(tv, tv + n_temps);
+        for (int t = 0; t < n_temps; t++) {
+            tt[t].temp = tv[t];
+            tt[t].init_energy = init[3 * t];
+            tt[t].init_enthalpy = init[3 * t + 1];
+            tt[t].init_entropy = init[3 * t + 2];
+            tt[t].hyb_energy = d_table_data + (size_t)(3 * t) * tsz;
+            tt[t].hyb_enthalpy = d_table_data + (size_t)(3 * t + 1) * tsz;
+            tt[t].hyb_entropy = d_table_data + (size_t)(3 * t + 2) * tsz;
+            if (dev_h2d((void*)tt[t].hyb_energy, e + t * tsz, sizeof(double) * tsz, stream)) return fail(dev_err());
+            if (dev_h2d((void*)tt[t].hyb_enthalpy, h + t * tsz, sizeof(double) * tsz, stream)) return fail(dev_err());
+            if (dev_h2d((void*)tt[t].hyb_entropy, s + t * tsz, sizeof(double) * tsz, stream)) return fail(dev_err());
+        }
+        if (dev_h2d(d_tables, tt.data(), sizeof(TempTables) * n_temps, stream)) return fail(dev_err());
+        P.tables = d_tables;
+        // default control: temperature slot 0
+        std::vector<RepAux> aux(R);
+        if (get_aux(0, R, aux.data())) return -1;
+        for (int r = 0; r < R; r++) {
+            if (aux[r].ctl.temp_idx >= n_temps) aux[r].ctl.temp_idx = 0;
+            aux[r].ctl.temp = tv[aux[r].ctl.temp_idx];
+        }
+        if (put_aux(0, R, aux.data())) return -1;
+        return push_shared();
+    }
+
+    int exec(OpArgs& a, bool sync) override {
+        a.n_replicas = R;
+        if (!P.tables) return fail("temperature tables not set");
+#ifdef LDO_HOSTSIM
+        for (int r = 0; r < R; r++) {
+            if (a.only_replica >= 0 && r != a.only_replica) continue;
+            SysState<K>* st = &P.states[r];
+            MoveScratch<K>* ms = STAGED ? P.scratch : &P.scratch[r];
+            if (a.op == OP_RECOMPUTE) {
+                SysState<K>* tmp = STAGED ? d_recompute_tmp : &d_recompute_tmp[r];
+                memcpy(tmp, st, sizeof(SysState<K>));
+                st = tmp;
+            }
+            rep_execute<K>(st, ms, &P.aux[r], P, a, r);
+        }
+        (void)sync;
+        return 0;
+#else
+        int wpb = warps_per_block;
+        int blocks = (R + wpb - 1) / wpb;
+        if (STAGED) {
+            size_t smem = sizeof(WarpSmem<K>) * wpb;
+            k_exec_staged<K><<<blocks, wpb * 32, smem, stream>>>(P, a, wpb);
+        }
+        else {
+            k_exec_inplace<K><<<blocks, wpb * 32, 0, stream>>>(P, a, wpb, d_recompute_tmp);
+        }
+        if (chk(cudaGetLastError())) return fail(dev_err());
+        if (sync && dev_sync(stream)) return fail(dev_err());
+        return 0;
+#endif
+    }
+
+    int configure_launch() {
+#ifndef LDO_HOSTSIM
+        if (STAGED) {
+            // as many warps per block as fit the opt-in shared memory limit, capped at 4 (128 threads)
+            int max_smem = 0;
+            cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+            size_t per_warp = sizeof(WarpSmem<K>);
+            int wpb = (int)(max_smem / per_warp);
+            if (wpb < 1) return fail("replica state does not fit shared memory");
+            if (wpb > 4) wpb = 4;
+            warps_per_block = wpb;
+            if (chk(cudaFuncSetAttribute(k_exec_staged<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(per_warp * wpb)))) {
+                return fail(dev_err());
+            }
+        }
+#endif
+        return 0;
+    }
+
+    int get_aux(int first, int count, RepAux* out) override {
+        if (dev_d2h(out, P.aux + first, sizeof(RepAux) * count, stream)) return fail(dev_err());
+        return 0;
+    }
+    int put_aux(int first, int count, const RepAux* in) override {
+        if (dev_h2d(P.aux + first, in, sizeof(RepAux) * count, stream)) return fail(dev_err());
+        return 0;
+    }
+    int get_state_raw(int replica, std::vector<unsigned char>& blob) override {
+        blob.resize(sizeof(SysState<K>));
+        if (dev_d2h(blob.data(), &P.states[replica], sizeof(SysState<K>), stream)) return fail(dev_err());
+        return 0;
+    }
+    void capacity(int* c, int* d) override {
+        *c = K::C;
+        *d = K::D;
+    }
+    int decode_state(int replica, int* n_chains, int* ci, int* cid, int* cl, int* pos, int* ore, int* st, int* bd) override {
+        std::vector<unsigned char> blob;
+        if (get_state_raw(replica, blob)) return -1;
+        const SysState<K>* s = reinterpret_cast<const SysState<K>*>(blob.data());
+        const SysConst& sc = shared.sc;
+        *n_chains = s->n_chains;
+        int k = 0;
+        for (int w = 0; w < s->n_chains; w++) {
+            int c = s->order[w];
+            ci[w] = s->chain_uid[c];
+            cid[w] = s->chain_type[c];
+            cl[w] = s->chain_len[c];
+            int base = c == 0 ? 0 : sc.n_scaffold + (c - 1) * sc.lmax;
+            for (int i = 0; i < s->chain_len[c]; i++) {
+                const DomRec& r = s->dom[base + i];
+                pos[3 * k] = r.x;
+                pos[3 * k + 1] = r.y;
+                pos[3 * k + 2] = r.z;
+                V3 o = r.ore == ORE_ZERO ? v3(0, 0, 0) : ore_vec(r.ore);
+                ore[3 * k] = o.x;
+                ore[3 * k + 1] = o.y;
+                ore[3 * k + 2] = o.z;
+                st[k] = r.state;
+                int b = s->bound[base + i];
+                if (b >= 0 && r.state != ST_UNASSIGNED && r.state != ST_UNBOUND) {
+                    bd[2 * k] = s->chain_uid[s->dchain[b]];
+                    bd[2 * k + 1] = s->dindex[b];
+                }
+                else {
+                    bd[2 * k] = -1;
+                    bd[2 * k + 1] = -1;
+                }
+                k++;
+            }
+        }
+        return 0;
+    }
+
+    int load_config(int replica, int n_chains, const int* ci, const int* cid, const int* cl, const int* pos, const int* ore) {
+        int nd = 0;
+        for (int i = 0; i < n_chains; i++) nd += cl[i];
+        const SysConst& sc = shared.sc;
+        if (n_chains < 1 || n_chains > K::C) return fail("too many chains for this engine's capacity");
+        if (cid[0] != 0 || cl[0] != sc.n_scaffold) return fail("first chain must be the scaffold");
+        for (int i = 1; i < n_chains; i++) {
+            if (cid[i] < 1 || cid[i] >= sc.n_types) return fail("chain identity out of range");
+            if (cl[i] != sc.type_len[cid[i]]) return fail("chain length does not match its identity");
+        }
+        size_t ints = (size_t)3 * n_chains + (size_t)6 * nd;
+        if (ints > cfg_cap) {
+            dev_free(d_cfg);
+            d_cfg = nullptr;
+            if (dev_malloc((void**)&d_cfg, sizeof(int) * ints)) return fail(dev_err());
+            cfg_cap = ints;
+        }
+        std::vector<int> h(ints);
+        memcpy(&h[0], ci, sizeof(int) * n_chains);
+        memcpy(&h[n_chains], cid, sizeof(int) * n_chains);
+        memcpy(&h[2 * n_chains], cl, sizeof(int) * n_chains);
+        memcpy(&h[3 * n_chains], pos, sizeof(int) * 3 * nd);
+        memcpy(&h[3 * n_chains + 3 * nd], ore, sizeof(int) * 3 * nd);
+        if (dev_h2d(d_cfg, h.data(), sizeof(int) * ints, stream)) return fail(dev_err());
+        OpArgs a;
+        memset(&a, 0, sizeof(a));
+        a.op = OP_LOAD_CONFIG;
+        a.only_replica = replica;
+        a.cfg_n_chains = n_chains;
+        a.cfg_chain_index = d_cfg;
+        a.cfg_chain_ident = d_cfg + n_chains;
+        a.cfg_chain_len = d_cfg + 2 * n_chains;
+        a.cfg_pos = d_cfg + 3 * n_chains;
+        a.cfg_ore = d_cfg + 3 * n_chains + 3 * nd;
+        return exec(a, true);
+    }
+
+    int set_grid(int replica, int bias, const int* lo, const int* n, const double* vals) override {
+        if (!shared.has_grid || !P.grid_vals) return fail("no Grid bias configured");
+        if (bias < 0 || bias >= shared.ob.n_biases || shared.ob.biases[bias].type != BIAS_GRID) return fail("not a Grid bias");
+        RepAux aux;
+        if (get_aux(replica, 1, &aux)) return -1;
+        // offsets: grid biases are packed in bias order
+        int off = 0;
+        for (int b = 0; b < bias; b++) {
+            if (shared.ob.biases[b].type != BIAS_GRID || aux.bs.grid_off[b] < 0) continue;
+            int sz = 1;
+            for (int k = 0; k < shared.ob.biases[b].n_ops; k++) sz *= aux.bs.grid_n[b][k];
+            off = aux.bs.grid_off[b] + sz;
+        }
+        int sz = 1;
+        for (int k = 0; k < shared.ob.biases[bias].n_ops; k++) {
+            aux.bs.grid_lo[bias][k] = lo[k];
+            aux.bs.grid_n[bias][k] = n[k];
+            sz *= n[k];
+        }
+        if (off + sz > LDO_GRID_CAP) return fail("grid bias exceeds LDO_GRID_CAP points");
+        aux.bs.grid_off[bias] = off;
+        if (put_aux(replica, 1, &aux)) return -1;
+        if (dev_h2d(P.grid_vals + (size_t)replica * LDO_GRID_CAP + off, vals, sizeof(double) * sz, stream)) return fail(dev_err());
+        return 0;
+    }
+    int get_visits(int replica, int bias, long long* counts, int clear) override {
+        if (!shared.has_grid || !P.grid_visits) return fail("no Grid bias configured");
+        RepAux aux;
+        if (get_aux(replica, 1, &aux)) return -1;
+        int off = aux.bs.grid_off[bias];
+        if (off < 0) return fail("grid not set for this replica");
+        int sz = 1;
+        for (int k = 0; k < shared.ob.biases[bias].n_ops; k++) sz *= aux.bs.grid_n[bias][k];
+        long long* p = P.grid_visits + (size_t)replica * LDO_GRID_CAP + off;
+        if (dev_d2h(counts, p, sizeof(long long) * sz, stream)) return fail(dev_err());
+        if (clear) {
+            if (dev_memset(p, 0, sizeof(long long) * sz, stream)) return fail(dev_err());
+            if (dev_sync(stream)) return fail(dev_err());
+        }
+        return 0;
+    }
+
+    int attach_tape(int replica, const ldo_tape_draw* draws, long long n) override {
+        static_assert(sizeof(ldo_tape_draw) == sizeof(TapeDraw), "tape layout");
+        RepAux aux;
+        if (get_aux(replica, 1, &aux)) return -1;
+        dev_free(tape_bufs[replica]);
+        tape_bufs[replica] = nullptr;
+        aux.rng.tape = nullptr;
+        aux.rng.tape_len = 0;
+        aux.rng.tape_pos = 0;
+        if (n > 0) {
+            void* p = nullptr;
+            if (dev_malloc(&p, sizeof(TapeDraw) * n)) return fail(dev_err());
+            if (dev_h2d(p, draws, sizeof(TapeDraw) * n, stream)) return fail(dev_err());
+            tape_bufs[replica] = p;
+            aux.rng.tape = (const TapeDraw*)p;
+            aux.rng.tape_len = n;
+        }
+        return put_aux(replica, 1, &aux);
+    }
+
+    int ensure_exchange(int n_global, int n_slots) {
+        int nq = 3 + (shared.sc.n_types - 1);
+        if (n_global > dep_all_n) {
+            dev_free(d_dep_all);
+            d_dep_all = nullptr;
+            if (dev_malloc((void**)&d_dep_all, sizeof(double) * nq * n_global)) return fail(dev_err());
+            dep_all_n = n_global;
+        }
+        if (n_slots > exch_cap) {
+            dev_free(d_q2r);
+            dev_free(d_att);
+            dev_free(d_acc);
+            dev_free(d_slot_tidx);
+            dev_free(d_slot_vals);
+            d_q2r = nullptr;
+            d_att = d_acc = nullptr;
+            d_slot_tidx = nullptr;
+            d_slot_vals = nullptr;
+            if (dev_malloc((void**)&d_q2r, sizeof(int) * n_slots)) return fail(dev_err());
+            if (dev_malloc((void**)&d_att, sizeof(long long) * n_slots)) return fail(dev_err());
+            if (dev_malloc((void**)&d_acc, sizeof(long long) * n_slots)) return fail(dev_err());
+            if (dev_malloc((void**)&d_slot_tidx, sizeof(int) * n_slots)) return fail(dev_err());
+            if (dev_malloc((void**)&d_slot_vals, sizeof(double) * 4 * n_slots)) return fail(dev_err());
+            exch_cap = n_slots;
+        }
+        if (!d_red_u) {
+            int nst = shared.sc.n_types - 1;
+            if (dev_malloc((void**)&d_red_u, sizeof(double) * (nst > 0 ? nst : 1))) return fail(dev_err());
+            if (nst > 0 && dev_h2d(d_red_u, reduced_staple_u.data(), sizeof(double) * nst, stream)) return fail(dev_err());
+        }
+        return 0;
+    }
+    int exchange_buffers(int n_global, void** send, void** recv, int* nq) override {
+        if (ensure_exchange(n_global, 1)) return -1;
+        *send = d_dependent;
+        *recv = d_dep_all;
+        *nq = 3 + (shared.sc.n_types - 1);
+        return 0;
+    }
+
+    // slot control variables are passed through x.slot_* as HOST arrays by the caller
+    int exchange(ExchangeArgs& x, const double* dependent_host, int* slot_to_replica, long long* attempts, long long* accepts) override {
+        int n_slots = x.n_ladders * x.ladder_len;
+        int n_pairs = x.n_ladders * (x.ladder_len - 1);
+        int nq = 3 + x.n_staple_types;
+        if (ensure_exchange(x.n_global, n_slots)) return -1;
+        if (dependent_host) {
+            if (dev_h2d(d_dep_all, dependent_host, sizeof(double) * nq * x.n_global, stream)) return fail(dev_err());
+        }
+        else if (x.n_global == R) {
+            // single-GPU: the local dependent quantities are the global ones
+#ifdef LDO_HOSTSIM
+            memcpy(d_dep_all, d_dependent, sizeof(double) * nq * R);
+#else
+            if (chk(cudaMemcpyAsync(d_dep_all, d_dependent, sizeof(double) * nq * R, cudaMemcpyDeviceToDevice, stream))) return fail(dev_err());
+#endif
+        }
+        if (dev_h2d(d_q2r, slot_to_replica, sizeof(int) * n_slots, stream)) return fail(dev_err());
+        if (dev_h2d(d_att, attempts, sizeof(long long) * n_pairs, stream)) return fail(dev_err());
+        if (dev_h2d(d_acc, accepts, sizeof(long long) * n_pairs, stream)) return fail(dev_err());
+        int L = x.ladder_len;
+        if (dev_h2d(d_slot_tidx, x.slot_temp_idx, sizeof(int) * L, stream)) return fail(dev_err());
+        std::vector<double> sv(4 * (size_t)L);
+        memcpy(&sv[0], x.slot_temp, sizeof(double) * L);
+        memcpy(&sv[L], x.slot_staple_u_mult, sizeof(double) * L);
+        memcpy(&sv[2 * L], x.slot_bias_mult, sizeof(double) * L);
+        memcpy(&sv[3 * L], x.slot_stacking_mult, sizeof(double) * L);
+        if (dev_h2d(d_slot_vals, sv.data(), sizeof(double) * 4 * L, stream)) return fail(dev_err());
+        ExchangeArgs dx = x;
+        dx.dependent = d_dep_all;
+        dx.slot_to_replica = d_q2r;
+        dx.attempts = d_att;
+        dx.accepts = d_acc;
+        dx.slot_temp_idx = d_slot_tidx;
+        dx.slot_temp = d_slot_vals;
+        dx.slot_staple_u_mult = d_slot_vals + L;
+        dx.slot_bias_mult = d_slot_vals + 2 * L;
+        dx.slot_stacking_mult = d_slot_vals + 3 * L;
+        dx.reduced_staple_u = d_red_u;
+        dx.aux = P.aux;
+#ifdef LDO_HOSTSIM
+        for (int l = 0; l < x.n_ladders; l++) exchange_ladder(dx, l);
+#else
+        int threads = 128;
+        k_exchange<<<(x.n_ladders + threads - 1) / threads, threads, 0, stream>>>(dx);
+        if (chk(cudaGetLastError())) return fail(dev_err());
+#endif
+        if (dev_d2h(slot_to_replica, d_q2r, sizeof(int) * n_slots, stream)) return fail(dev_err());
+        if (dev_d2h(attempts, d_att, sizeof(long long) * n_pairs, stream)) return fail(dev_err());
+        if (dev_d2h(accepts, d_acc, sizeof(long long) * n_pairs, stream)) return fail(dev_err());
+        return 0;
+    }
+};
+
+struct ldo_engine {
+    EngineBase* b;
+    int (*load_config)(ldo_engine*, int, int, const int*, const int*, const int*, const int*, const int*);
+    unsigned long long seed;
+};
+
+template <class K, bool STAGED>
+static int load_config_thunk(ldo_engine* e, int replica, int n, const int* ci, const int* cid, const int* cl, const int* pos, const int* ore) {
+    return static_cast<EngineImpl<K, STAGED>*>(e->b)->load_config(replica, n, ci, cid, cl, pos, ore);
+}
+
+template <class K, bool STAGED>
+static int make_engine(const ldo_system_desc* d, const SysConst& sc, int n_replicas, int device, ldo_engine** out) {
+    auto* impl = new EngineImpl<K, STAGED>();
+    impl->device = device;
+    impl->shared.sc = sc;
+    // staple chemical potentials / T (origami_system.cpp:965-990)
+    for (int t = 1; t < sc.n_types; t++) {
+        impl->reduced_staple_u.push_back(log(d->staple_M) - (2.0 * sc.type_len[t] - 1) * log(6.0));
+    }
+    if (impl->init(n_replicas) || impl->configure_launch()) {
+        g_create_error = impl->err;
+        delete impl;
+        return -1;
+    }
+    ldo_engine* e = new ldo_engine();
+    e->b = impl;
+    e->load_config = &load_config_thunk<K, STAGED>;
+    e->seed = 0;
+    *out = e;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// C-ABI
+// ---------------------------------------------------------------------------------------------
+
+extern "C" {
+
+int ldo_engine_create(const ldo_system_desc* d, int n_replicas, int device, ldo_engine** out) {
+    if (!d || !out || n_replicas < 1) {
+        g_create_error = "bad arguments";
+        return -1;
+    }
+    if (d->n_types < 1 || d->n_types > LDO_MAX_TYPES) {
+        g_create_error = "too many chain identities";
+        return -1;
+    }
+    SysConst sc;
+    memset(&sc, 0, sizeof(sc));
+    sc.n_types = d->n_types;
+    int off = 0, n_ident = 0, max_staple_len = 0;
+    for (int t = 0; t < d->n_types; t++) {
+        sc.type_len[t] = d->type_len[t];
+        sc.type_off[t] = off;
+        for (int i = 0; i < d->type_len[t]; i++) {
+            if (off + i >= LDO_MAX_IDENTS) {
+                g_create_error = "too many domain identities";
+                return -1;
+            }
+            int id = d->idents[off + i];
+            sc.idents[off + i] = (short)id;
+            if (abs(id) > n_ident) n_ident = abs(id);
+        }
+        off += d->type_len[t];
+        if (t > 0 && d->type_len[t] > max_staple_len) max_staple_len = d->type_len[t];
+    }
+    sc.n_scaffold = d->type_len[0];
+    sc.lmax = d->max_staple_size > max_staple_len ? d->max_staple_size : max_staple_len;
+    if (sc.lmax < 1) sc.lmax = 1;
+    sc.cyclic = d->cyclic;
+    sc.domain_type = d->domain_type;
+    sc.misbinding_pot = d->misbinding_pot;
+    sc.apply_mean_field_cor = d->apply_mean_field_cor;
+    sc.max_total_staples = d->max_total_staples;
+    sc.max_type_staples = d->max_type_staples;
+    sc.n_ident = n_ident;
+    sc.staple_M = d->staple_M;
+    sc.stacking_ene = d->stacking_ene;
+    int need_d = sc.n_scaffold + d->max_total_staples * sc.lmax;
+    int need_c = 1 + d->max_total_staples;
+    if (need_d <= CapsSmall::D && need_c <= CapsSmall::C && d->n_types <= CapsSmall::T) {
+        return make_engine<CapsSmall, true>(d, sc, n_replicas, device, out);
+    }
+    if (need_d <= CapsLarge::D && need_c <= CapsLarge::C && d->n_types <= CapsLarge::T) {
+        return make_engine<CapsLarge, false>(d, sc, n_replicas, device, out);
+    }
+    g_create_error = "system exceeds the compiled capacities (domains/chains/types)";
+    return -1;
+}
+
+void ldo_engine_destroy(ldo_engine* e) {
+    if (!e) return;
+    delete e->b;
+    delete e;
+}
+
+const char* ldo_last_error(const ldo_engine* e) { return e ? e->b->err.c_str() : g_create_error.c_str(); }
+int ldo_num_replicas(const ldo_engine* e) { return e->b->R; }
+
+int ldo_set_temperature_tables(ldo_engine* e, int n_temps, int n_ident, const double* temps, const double* hyb_energy,
+                               const double* hyb_enthalpy, const double* hyb_entropy, const double* init) {
+    if (n_ident < e->b->shared.sc.n_ident) return e->b->fail("n_ident smaller than the largest domain identity");
+    return e->b->set_tables(n_temps, n_ident, temps, hyb_energy, hyb_enthalpy, hyb_entropy, init);
+}
+
+int ldo_set_moveset(ldo_engine* e, int n, const ldo_movetype_desc* mts, int allow_nonsensical_ps) {
+    EngineBase* b = e->b;
+    if (n < 1 || n > LDO_MAX_MOVETYPES) return b->fail("bad movetype count");
+    MoveSet& ms = b->shared.ms;
+    memset(&ms, 0, sizeof(ms));
+    ms.n = n;
+    ms.allow_nonsensical_ps = allow_nonsensical_ps;
+    double cum = 0;
+    int nst = b->shared.sc.n_types - 1;
+    int em_off = 0;
+    for (int i = 0; i < n; i++) {
+        MoveDef& md = ms.mt[i];
+        md.type = mts[i].type;
+        if (md.type == MT_CTCB_SCAFFOLD_REGROWTH || md.type == MT_CTCB_JUMP_SCAFFOLD_REGROWTH || md.type < 0 ||
+            md.type > MT_CTRG_JUMP_SCAFFOLD_REGROWTH) {
+            return b->fail("movetype not available on device");
+        }
+        cum += mts[i].freq;
+        md.cum_prob = cum;
+        md.max_regrowth = mts[i].max_regrowth;
+        md.max_seg_regrowth = mts[i].max_seg_regrowth;
+        md.max_num_recoils = mts[i].max_num_recoils;
+        md.max_c_attempts = mts[i].max_c_attempts;
+        md.adaptive_exchange = mts[i].adaptive_exchange;
+        md.exchange_mults_off = 0;
+        if (md.type == MT_MET_STAPLE_EXCHANGE) {
+            if (em_off + nst > LDO_MAX_TYPES) return b->fail("too many exchange multipliers");
+            md.exchange_mults_off = em_off;
+            for (int t = 0; t < nst; t++) {
+                ms.exchange_mults[em_off + t] = t < mts[i].n_exchange_mults ? mts[i].exchange_mults[t] : 1.0;
+            }
+            em_off += nst;
+        }
+        if ((md.type == MT_CTRG_SCAFFOLD_REGROWTH || md.type == MT_CTRG_JUMP_SCAFFOLD_REGROWTH) &&
+            (md.max_c_attempts < 1 || md.max_c_attempts > 36 || md.max_regrowth < 2)) {
+            return b->fail("CTRG options out of range (max_c_attempts 1..36, max_regrowth >= 2)");
+        }
+    }
+    return b->push_shared();
+}
+
+int ldo_set_order_params(ldo_engine* e, int n, const ldo_order_param_desc* ops) {
+    EngineBase* b = e->b;
+    if (n < 0 || n > LDO_MAX_OPS) return b->fail("too many order parameters");
+    OpsBiasConst& ob = b->shared.ob;
+    ob.n_ops = n;
+    for (int i = 0; i < n; i++) {
+        ob.ops[i].type = ops[i].type;
+        ob.ops[i].arg = ops[i].staple;
+        ob.ops[i].n_sum = 0;
+        if (ops[i].type == OP_SUM) {
+            if (ops[i].n_sum > LDO_MAX_SUM) return b->fail("Sum order parameter has too many terms");
+            ob.ops[i].n_sum = ops[i].n_sum;
+            for (int k = 0; k < ops[i].n_sum; k++) {
+                if (ops[i].sum_ops[k] < 0 || ops[i].sum_ops[k] >= i) return b->fail("Sum refers to a later order parameter");
+                ob.ops[i].sum_idx[k] = ops[i].sum_ops[k];
+            }
+        }
+        if ((ops[i].type == OP_NUM_STAPLES_TYPE || ops[i].type == OP_STAPLE_TYPE_FULLY_BOUND) &&
+            (ops[i].staple < 1 || ops[i].staple >= b->shared.sc.n_types)) {
+            return b->fail("order parameter staple identity out of range");
+        }
+    }
+    return b->push_shared();
+}
+
+int ldo_set_biases(ldo_engine* e, int n, const ldo_bias_desc* biases) {
+    EngineBase* b = e->b;
+    if (n < 0 || n > LDO_MAX_BIASES) return b->fail("too many bias functions");
+    OpsBiasConst& ob = b->shared.ob;
+    ob.n_biases = n;
+    b->shared.has_grid = 0;
+    std::vector<RepAux> aux(b->R);
+    if (b->get_aux(0, b->R, aux.data())) return -1;
+    for (int i = 0; i < n; i++) {
+        BiasDef& bd = ob.biases[i];
+        bd.type = biases[i].type;
+        bd.n_ops = biases[i].n_ops;
+        if (bd.n_ops < 1 || bd.n_ops > LDO_MAX_GRID_DIM) return b->fail("bias function has a bad number of order parameters");
+        for (int k = 0; k < bd.n_ops; k++) {
+            if (biases[i].ops[k] < 0 || biases[i].ops[k] >= ob.n_ops) return b->fail("bias refers to an unknown order parameter");
+            bd.op_idx[k] = biases[i].ops[k];
+        }
+        bd.min_op = biases[i].min_op;
+        bd.max_op = biases[i].max_op;
+        bd.well_bias = biases[i].well_bias;
+        bd.min_bias = biases[i].min_bias;
+        bd.slope = biases[i].slope;
+        bd.outside_bias = biases[i].outside_bias;
+        if (bd.type == BIAS_GRID) b->shared.has_grid = 1;
+        for (int r = 0; r < b->R; r++) {
+            aux[r].bs.win_min[i] = bd.min_op;
+            aux[r].bs.win_max[i] = bd.max_op;
+            aux[r].bs.grid_off[i] = -1;
+        }
+    }
+    if (b->put_aux(0, b->R, aux.data())) return -1;
+    return b->push_shared();
+}
+
+int ldo_set_window(ldo_engine* e, int replica, int bias, int min_op, int max_op) {
+    EngineBase* b = e->b;
+    if (replica < 0 || replica >= b->R || bias < 0 || bias >= b->shared.ob.n_biases) return b->fail("bad replica or bias index");
+    RepAux aux;
+    if (b->get_aux(replica, 1, &aux)) return -1;
+    aux.bs.win_min[bias] = min_op;
+    aux.bs.win_max[bias] = max_op;
+    return b->put_aux(replica, 1, &aux);
+}
+
+int ldo_set_grid_bias(ldo_engine* e, int replica, int bias, const int* lo, const int* n, const double* values) {
+    if (replica < 0 || replica >= e->b->R) return e->b->fail("bad replica index");
+    return e->b->set_grid(replica, bias, lo, n, values);
+}
+
+int ldo_get_grid_visits(ldo_engine* e, int replica, int bias, long long* counts, int clear) {
+    if (replica < 0 || replica >= e->b->R) return e->b->fail("bad replica index");
+    return e->b->get_visits(replica, bias, counts, clear);
+}
+
+static int refresh_energy(ldo_engine* e) {
+    OpArgs a;
+    memset(&a, 0, sizeof(a));
+    a.op = OP_UPDATE_ENERGY;
+    a.only_replica = -1;
+    return e->b->exec(a, true);
+}
+
+int ldo_set_control(ldo_engine* e, int first, int count, const int* temp_idx, const double* staple_u_mult,
+                    const double* bias_mult, const double* stacking_mult) {
+    EngineBase* b = e->b;
+    if (first < 0 || count < 0 || first + count > b->R) return b->fail("bad replica range");
+    std::vector<RepAux> aux(count);
+    if (b->get_aux(first, count, aux.data())) return -1;
+    for (int i = 0; i < count; i++) {
+        if (temp_idx) {
+            if (temp_idx[i] < 0 || temp_idx[i] >= b->shared.n_temps) return b->fail("temperature index out of range");
+            aux[i].ctl.temp_idx = temp_idx[i];
+            aux[i].ctl.temp = b->temps[temp_idx[i]];
+        }
+        if (staple_u_mult) aux[i].ctl.staple_u_mult = staple_u_mult[i];
+        if (bias_mult) aux[i].ctl.bias_mult = bias_mult[i];
+        if (stacking_mult) aux[i].ctl.stacking_mult = stacking_mult[i];
+    }
+    if (b->put_aux(first, count, aux.data())) return -1;
+    return refresh_energy(e);
+}
+
+int ldo_get_control(ldo_engine* e, int first, int count, int* temp_idx, double* staple_u_mult, double* bias_mult,
+                    double* stacking_mult) {
+    EngineBase* b = e->b;
+    if (first < 0 || count < 0 || first + count > b->R) return b->fail("bad replica range");
+    std::vector<RepAux> aux(count);
+    if (b->get_aux(first, count, aux.data())) return -1;
+    for (int i = 0; i < count; i++) {
+        if (temp_idx) temp_idx[i] = aux[i].ctl.temp_idx;
+        if (staple_u_mult) staple_u_mult[i] = aux[i].ctl.staple_u_mult;
+        if (bias_mult) bias_mult[i] = aux[i].ctl.bias_mult;
+        if (stacking_mult) stacking_mult[i] = aux[i].ctl.stacking_mult;
+    }
+    return 0;
+}
+
+int ldo_seed(ldo_engine* e, unsigned long long seed, unsigned int first_subsequence) {
+    EngineBase* b = e->b;
+    e->seed = seed;
+    std::vector<RepAux> aux(b->R);
+    if (b->get_aux(0, b->R, aux.data())) return -1;
+    for (int r = 0; r < b->R; r++) {
+        aux[r].rng.key0 = (uint32_t)seed;
+        aux[r].rng.key1 = (uint32_t)(seed >> 32);
+        aux[r].rng.subseq = first_subsequence + (uint32_t)r;
+        aux[r].rng.stream = 0;
+        aux[r].rng.counter = 0;
+    }
+    return b->put_aux(0, b->R, aux.data());
+}
+
+int ldo_attach_tape(ldo_engine* e, int replica, const ldo_tape_draw* draws, long long n) {
+    if (replica < 0 || replica >= e->b->R) return e->b->fail("bad replica index");
+    return e->b->attach_tape(replica, draws, n);
+}
+
+int ldo_tape_position(ldo_engine* e, int replica, long long* pos) {
+    if (replica < 0 || replica >= e->b->R) return e->b->fail("bad replica index");
+    RepAux aux;
+    if (e->b->get_aux(replica, 1, &aux)) return -1;
+    *pos = aux.rng.tape_pos;
+    return 0;
+}
+
+int ldo_set_state(ldo_engine* e, int replica, int n_chains, const int* chain_index, const int* chain_ident,
+                  const int* chain_len, const int* pos, const int* ore) {
+    if (replica < -1 || replica >= e->b->R) return e->b->fail("bad replica index");
+    return e->load_config(e, replica, n_chains, chain_index, chain_ident, chain_len, pos, ore);
+}
+
+int ldo_state_capacity(const ldo_engine* e, int* max_chains, int* max_domains) {
+    e->b->capacity(max_chains, max_domains);
+    return 0;
+}
+
+int ldo_get_state(ldo_engine* e, int replica, int* n_chains, int* chain_index, int* chain_ident, int* chain_len,
+                  int* pos, int* ore, int* state, int* bound) {
+    if (replica < 0 || replica >= e->b->R) return e->b->fail("bad replica index");
+    return e->b->decode_state(replica, n_chains, chain_index, chain_ident, chain_len, pos, ore, state, bound);
+}
+
+static int run_impl(ldo_engine* e, long long n_steps, int cf, int cd, int ccf, bool sync) {
+    OpArgs a;
+    memset(&a, 0, sizeof(a));
+    a.op = OP_RUN;
+    a.only_replica = -1;
+    a.n_steps = n_steps;
+    a.centering_freq = cf;
+    a.centering_domain = cd;
+    a.constraint_check_freq = ccf;
+    if (e->b->shared.ms.n < 1) return e->b->fail("moveset not set");
+    return e->b->exec(a, sync);
+}
+
+int ldo_run(ldo_engine* e, long long n_steps, int centering_freq, int centering_domain, int constraint_check_freq) {
+    return run_impl(e, n_steps, centering_freq, centering_domain, constraint_check_freq, true);
+}
+int ldo_run_async(ldo_engine* e, long long n_steps, int centering_freq, int centering_domain, int constraint_check_freq) {
+    return run_impl(e, n_steps, centering_freq, centering_domain, constraint_check_freq, false);
+}
+int ldo_synchronize(ldo_engine* e) {
+    if (dev_sync(e->b->stream)) return e->b->fail(dev_err());
+    return 0;
+}
+void* ldo_stream(ldo_engine* e) {
+#ifdef LDO_HOSTSIM
+    return nullptr;
+#else
+    return (void*)e->b->stream;
+#endif
+}
+
+static int observe(ldo_engine* e, OpArgs& a) {
+    a.op = OP_OBSERVE;
+    a.only_replica = -1;
+    return e->b->exec(a, true);
+}
+
+int ldo_get_status(ldo_engine* e, int* status, int* detail) {
+    EngineBase* b = e->b;
+    OpArgs a;
+    memset(&a, 0, sizeof(a));
+    a.out_status = b->d_status;
+    if (observe(e, a)) return -1;
+    std::vector<int> h(2 * (size_t)b->R);
+    if (dev_d2h(h.data(), b->d_status, sizeof(int) * 2 * b->R, b->stream)) return b->fail(dev_err());
+    for (int r = 0; r < b->R; r++) {
+        if (status) status[r] = h[2 * r];
+        if (detail) detail[r] = h[2 * r + 1];
+    }
+    return 0;
+}
+
+int ldo_get_energies(ldo_engine* e, double* out) {
+    EngineBase* b = e->b;
+    OpArgs a;
+    memset(&a, 0, sizeof(a));
+    a.out_energies = b->d_energies;
+    if (observe(e, a)) return -1;
+    if (dev_d2h(out, b->d_energies, sizeof(double) * 5 * b->R, b->stream)) return b->fail(dev_err());
+    return 0;
+}
+
+int ldo_get_counters(ldo_engine* e, int* out) {
+    EngineBase* b = e->b;
+    OpArgs a;
+    memset(&a, 0, sizeof(a));
+    a.out_counters = b->d_counters;
+    if (observe(e, a)) return -1;
+    if (dev_d2h(out, b->d_counters, sizeof(int) * 9 * b->R, b->stream)) return b->fail(dev_err());
+    return 0;
+}
+
+int ldo_get_staple_counts(ldo_engine* e, int* out) {
+    EngineBase* b = e->b;
+    int nst = b->shared.sc.n_types - 1;
+    if (nst < 1) return 0;
+    OpArgs a;
+    memset(&a, 0, sizeof(a));
+    a.out_staples = b->d_staples;
+    if (observe(e, a)) return -1;
+    if (dev_d2h(out, b->d_staples, sizeof(int) * nst * b->R, b->stream)) return b->fail(dev_err());
+    return 0;
+}
+
+int ldo_get_order_params(ldo_engine* e, int* out) {
+    EngineBase* b = e->b;
+    int n = b->shared.ob.n_ops;
+    if (n < 1) return 0;
+    OpArgs a;
+    memset(&a, 0, sizeof(a));
+    a.out_ops = b->d_ops;
+    if (observe(e, a)) return -1;
+    if (dev_d2h(out, b->d_ops, sizeof(int) * n * b->R, b->stream)) return b->fail(dev_err());
+    return 0;
+}
+
+int ldo_get_move_stats(ldo_engine* e, long long* attempts, long long* accepts) {
+    EngineBase* b = e->b;
+    std::vector<RepAux> aux(b->R);
+    if (b->get_aux(0, b->R, aux.data())) return -1;
+    int n = b->shared.ms.n;
+    for (int r = 0; r < b->R; r++) {
+        for (int i = 0; i < n; i++) {
+            attempts[(size_t)r * n + i] = aux[r].stats.attempts[i];
+            accepts[(size_t)r * n + i] = aux[r].stats.accepts[i];
+        }
+    }
+    return 0;
+}
+
+int ldo_recompute_energies(ldo_engine* e, double* energy, int* stacked_pairs) {
+    EngineBase* b = e->b;
+    OpArgs a;
+    memset(&a, 0, sizeof(a));
+    a.op = OP_RECOMPUTE;
+    a.only_replica = -1;
+    a.out_recomputed = b->d_recomputed;
+    a.out_recomputed_stacked = b->d_recomputed_stacked;
+    if (b->exec(a, true)) return -1;
+    if (dev_d2h(energy, b->d_recomputed, sizeof(double) * b->R, b->stream)) return b->fail(dev_err());
+    if (dev_d2h(stacked_pairs, b->d_recomputed_stacked, sizeof(int) * b->R, b->stream)) return b->fail(dev_err());
+    return 0;
+}
+
+int ldo_check_all_constraints(ldo_engine* e) {
+    OpArgs a;
+    memset(&a, 0, sizeof(a));
+    a.op = OP_CHECK_CONSTRAINTS;
+    a.only_replica = -1;
+    return e->b->exec(a, true);
+}
+
+int ldo_center(ldo_engine* e, int centering_domain) {
+    OpArgs a;
+    memset(&a, 0, sizeof(a));
+    a.op = OP_CENTER;
+    a.only_replica = -1;
+    a.centering_domain = centering_domain;
+    return e->b->exec(a, true);
+}
+
+int ldo_exchange_collect(ldo_engine* e, double* dependent_local) {
+    EngineBase* b = e->b;
+    int nq = 3 + (b->shared.sc.n_types - 1);
+    OpArgs a;
+    memset(&a, 0, sizeof(a));
+    a.out_dependent = b->d_dependent;
+    if (observe(e, a)) return -1;
+    if (dependent_local) {
+        if (dev_d2h(dependent_local, b->d_dependent, sizeof(double) * nq * b->R, b->stream)) return b->fail(dev_err());
+    }
+    return 0;
+}
+
+int ldo_set_exchange_ladder(ldo_engine* e, int ladder_len, const int* temp_idx, const double* staple_u_mult,
+                            const double* bias_mult, const double* stacking_mult) {
+    EngineBase* b = e->b;
+    if (ladder_len < 1) return b->fail("bad ladder length");
+    b->ladder_temp_idx.assign(temp_idx, temp_idx + ladder_len);
+    for (int i = 0; i < ladder_len; i++) {
+        if (temp_idx[i] < 0 || temp_idx[i] >= b->shared.n_temps) return b->fail("ladder temperature index out of range");
+    }
+    b->ladder_staple_u_mult.assign(ladder_len, 1.0);
+    b->ladder_bias_mult.assign(ladder_len, 1.0);
+    b->ladder_stacking_mult.assign(ladder_len, 1.0);
+    if (staple_u_mult) b->ladder_staple_u_mult.assign(staple_u_mult, staple_u_mult + ladder_len);
+    if (bias_mult) b->ladder_bias_mult.assign(bias_mult, bias_mult + ladder_len);
+    if (stacking_mult) b->ladder_stacking_mult.assign(stacking_mult, stacking_mult + ladder_len);
+    return 0;
+}
+
+int ldo_exchange_pt(ldo_engine* e, int variant, long long swap_i, int n_ladders, int ladder_len, int global_first,
+                    int n_global, const double* dependent, int* slot_to_replica, long long* attempts,
+                    long long* accepts) {
+    EngineBase* b = e->b;
+    if ((int)b->ladder_temp_idx.size() != ladder_len) return b->fail("ldo_set_exchange_ladder not called for this ladder length");
+    if (n_ladders * ladder_len != n_global) return b->fail("n_ladders * ladder_len must equal n_global");
+    if (global_first < 0 || global_first + b->R > n_global) return b->fail("bad global replica range");
+    std::vector<double> slot_temp(ladder_len);
+    for (int i = 0; i < ladder_len; i++) slot_temp[i] = b->temps[b->ladder_temp_idx[i]];
+    ExchangeArgs x;
+    memset(&x, 0, sizeof(x));
+    x.variant = variant;
+    x.swap_i = swap_i;
+    x.n_ladders = n_ladders;
+    x.ladder_len = ladder_len;
+    x.global_first = global_first;
+    x.n_local = b->R;
+    x.n_global = n_global;
+    x.n_staple_types = b->shared.sc.n_types - 1;
+    x.seed = e->seed;
+    x.slot_temp_idx = b->ladder_temp_idx.data();
+    x.slot_temp = slot_temp.data();
+    x.slot_staple_u_mult = b->ladder_staple_u_mult.data();
+    x.slot_bias_mult = b->ladder_bias_mult.data();
+    x.slot_stacking_mult = b->ladder_stacking_mult.data();
+    if (b->exchange(x, dependent, slot_to_replica, attempts, accepts)) return -1;
+    // PTGCMCSimulation::run calls update_control_qs() at the top of every round, which always ends
+    // in update_energy() (App. A19): rebuild the running energy with the (possibly new) tables
+    return refresh_energy(e);
+}
+
+int ldo_exchange_buffers(ldo_engine* e, int n_global, void** send_dev, void** recv_dev, int* doubles_per_replica) {
+    return e->b->exchange_buffers(n_global, send_dev, recv_dev, doubles_per_replica);
+}
+
+} // extern "C"

@@ -1,0 +1,1815 @@
+// ldo_moves.cuh — random numbers, order parameters / biases, topology constraint points and the
+// Monte Carlo movetypes of the LatticeDNAOrigami model, one warp per replica (see ldo_core.cuh for
+// the execution model).
+//
+// What this restates (reference file:line):
+//   * RandomGens::uniform_real / uniform_int                      random_gens.cpp:29-49
+//     -> counter-based Philox4x32-10, or a value-level replay tape for parity
+//   * SystemOrderParams::update_move_params, move-update biases   order_params.cpp:143-445,595-601
+//                                                                 bias_functions.cpp:139-283,447-487
+//   * MCMovetype skeleton: attempt / reset_origami / acceptance   movetypes.cpp:41-277
+//   * OrientationRotation                                         orientation_movetype.cpp:30-65
+//   * MetStapleExchange, MetStapleRegrowth, growth helpers        met_movetypes.cpp:50-513, movetypes.cpp:322-395
+//   * CBStapleRegrowth (6-site Rosenbluth weights over lanes)     cb_movetypes.cpp:44-404
+//   * StapleNetwork + Constraintpoints                            top_constraint_points.cpp:36-601
+//   * IdealRandomWalks::num_walks == 0 predicate                  ideal_random_walk.cpp:14-73 (App. A7)
+//   * CT segment selection (contiguous, non-contiguous)           movetypes.cpp:449-719
+//   * CTRG recoil growth: scaffold + jump variants                rg_movetypes.cpp:14-856
+//   * GCMCSimulation::simulate step                               simulation.cpp:568-665
+#pragma once
+
+#include "ldo_core.cuh"
+
+namespace ldo {
+
+// ---------------------------------------------------------------------------------------------
+// Random numbers
+// ---------------------------------------------------------------------------------------------
+
+struct TapeDraw {
+    int32_t kind; // 0 = uniform_real, 1 = uniform_int
+    int32_t lo, hi, ival;
+    double real;
+};
+
+struct Rng {
+    // replay tape (parity mode) when tape != nullptr
+    const TapeDraw* tape;
+    long long tape_len;
+    long long tape_pos;
+    // Philox4x32-10: key = seed, counter = (draw index lo, draw index hi, replica id, stream)
+    uint32_t key0, key1;
+    uint32_t subseq;
+    uint32_t stream;
+    unsigned long long counter;
+};
+
+LDO_HD inline void philox_round(uint32_t& c0, uint32_t& c1, uint32_t& c2, uint32_t& c3, uint32_t k0, uint32_t k1) {
+    unsigned long long p0 = (unsigned long long)0xD2511F53u * c0;
+    unsigned long long p1 = (unsigned long long)0xCD9E8D57u * c2;
+    uint32_t hi0 = (uint32_t)(p0 >> 32), lo0 = (uint32_t)p0;
+    uint32_t hi1 = (uint32_t)(p1 >> 32), lo1 = (uint32_t)p1;
+    uint32_t n0 = hi1 ^ c1 ^ k0;
+    uint32_t n2 = hi0 ^ c3 ^ k1;
+    c0 = n0;
+    c1 = lo1;
+    c2 = n2;
+    c3 = lo0;
+}
+
+LDO_HD inline void philox4x32_10(const Rng& r, unsigned long long ctr, uint32_t out[4]) {
+    uint32_t c0 = (uint32_t)ctr, c1 = (uint32_t)(ctr >> 32), c2 = r.subseq, c3 = r.stream;
+    uint32_t k0 = r.key0, k1 = r.key1;
+    for (int i = 0; i < 10; i++) {
+        philox_round(c0, c1, c2, c3, k0, k1);
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    out[0] = c0;
+    out[1] = c1;
+    out[2] = c2;
+    out[3] = c3;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Order parameters and biases evaluated per move (the `update_per_domain: false` kind)
+// ---------------------------------------------------------------------------------------------
+
+enum {
+    OP_NUM_STAPLES = 0,
+    OP_NUM_STAPLES_TYPE = 1,
+    OP_STAPLE_TYPE_FULLY_BOUND = 2,
+    OP_NUM_BOUND_DOMAIN_PAIRS = 3,
+    OP_NUM_MISBOUND_DOMAIN_PAIRS = 4,
+    OP_NUM_STACKED_PAIRS = 5,
+    OP_NUM_LINEAR_HELICES = 6,
+    OP_NUM_STACKED_JUNCTS = 7,
+    OP_SUM = 8
+};
+enum { BIAS_LINEAR_STEP_WELL = 0, BIAS_SQUARE_WELL = 1, BIAS_GRID = 2 };
+
+#define LDO_MAX_OPS 16
+#define LDO_MAX_BIASES 8
+#define LDO_MAX_SUM 8
+#define LDO_MAX_GRID_DIM 3
+
+struct OpDef {
+    int type;
+    int arg; // staple identity for the *Type ops
+    int n_sum;
+    int sum_idx[LDO_MAX_SUM];
+};
+
+struct BiasDef {
+    int type;
+    int n_ops;
+    int op_idx[LDO_MAX_GRID_DIM];
+    int min_op, max_op; // LinearStepWell / SquareWell
+    double well_bias, min_bias, slope, outside_bias;
+};
+
+struct OpsBiasConst {
+    int n_ops;
+    int n_biases;
+    OpDef ops[LDO_MAX_OPS];
+    BiasDef biases[LDO_MAX_BIASES];
+};
+
+// Per-replica bias state: window limits (MWUS overrides min_op/max_op per window,
+// us_simulation.cpp:503-516) and dense grid-bias boxes (GridBiasFunction, bias_functions.cpp:242-283)
+struct BiasState {
+    int op_val[LDO_MAX_OPS]; // m_param of every order parameter
+    double bias_val[LDO_MAX_BIASES]; // BiasFunction::m_bias
+    double move_update_bias; // SystemBiases::m_move_update_bias
+    int win_min[LDO_MAX_BIASES], win_max[LDO_MAX_BIASES];
+    int grid_lo[LDO_MAX_BIASES][LDO_MAX_GRID_DIM];
+    int grid_n[LDO_MAX_BIASES][LDO_MAX_GRID_DIM];
+    int grid_off[LDO_MAX_BIASES]; // offset into the replica's grid value / visit arrays, -1 = none
+};
+
+// ---------------------------------------------------------------------------------------------
+// Moveset
+// ---------------------------------------------------------------------------------------------
+
+enum {
+    MT_ORIENTATION_ROTATION = 0,
+    MT_MET_STAPLE_EXCHANGE = 1,
+    MT_MET_STAPLE_REGROWTH = 2,
+    MT_CB_STAPLE_REGROWTH = 3,
+    MT_CTCB_SCAFFOLD_REGROWTH = 4,
+    MT_CTCB_JUMP_SCAFFOLD_REGROWTH = 5,
+    MT_CTRG_SCAFFOLD_REGROWTH = 6,
+    MT_CTRG_JUMP_SCAFFOLD_REGROWTH = 7
+};
+
+#define LDO_MAX_MOVETYPES 12
+struct MoveDef {
+    int type;
+    double cum_prob; // m_cumulative_probs (simulation.cpp:233-237)
+    int max_regrowth, max_seg_regrowth, max_num_recoils, max_c_attempts;
+    int adaptive_exchange;
+    int exchange_mults_off; // offset into MoveSet::exchange_mults
+};
+struct MoveSet {
+    int n;
+    int allow_nonsensical_ps;
+    MoveDef mt[LDO_MAX_MOVETYPES];
+    double exchange_mults[LDO_MAX_TYPES];
+};
+
+// ---------------------------------------------------------------------------------------------
+// Per-move scratch (MCMovetype / RegrowthMCMovetype / CBMCMovetype / CTRGRegrowthMCMovetype members)
+// and Constraintpoints (top_constraint_points.hpp:112-288), fixed capacity
+// ---------------------------------------------------------------------------------------------
+
+template <class K>
+struct MoveScratch {
+    static const int A = 2 * K::D + 8; // assigned-domain list capacity
+    static const int E = K::D; // active endpoints capacity
+    static const int S = 2 * K::D + 2; // scaffold segments capacity
+
+    // MCMovetype (movetypes.hpp:146-166)
+    short modified[K::D + 1];
+    int n_modified;
+    short assigned[A];
+    int n_assigned;
+    int added_chain; // chain slot or -1 (at most one chain is added per move)
+    DomRec prev[K::D]; // m_prev_pos / m_prev_ore
+    DomRec oldc[K::D]; // m_old_pos / m_old_ore
+    DomRec newc[K::D]; // m_new_pos / m_new_ore
+    int rejected;
+    double modifier;
+
+    // CTRG (rg_movetypes.hpp:83-115)
+    short regrow[K::D + 1];
+    int n_regrow;
+    short sel_scaf[K::D + 1];
+    int n_sel;
+    uint8_t c_attempts_q[K::D + 1], c_attempts_wq[K::D + 1];
+    unsigned long long avail_q[K::D + 1], avail_wq[K::D + 1];
+    double c_opens[K::D + 1];
+    // m_erased_endpoints_q: stack of position lists
+    int eq_depth;
+    short eq_start[A + 1];
+    int eq_npos;
+    short eq_pos[E][3];
+
+    // Constraintpoints
+    int8_t seg_of[K::D]; // m_segs (-1 = absent)
+    int8_t scaf_dir[S]; // m_domain_to_dir for (scaffold, seg); staples: seg 0 -> +1, seg 1 -> -1
+    short stem_gp[K::D]; // m_stemdomains[d] (growthpoint of stem domain d) or -1
+    short gp_stem[K::D]; // m_growthpoints[d] (domain to grow from d) or -1
+    short inactive[K::D]; // m_inactive_endpoints[d] or -1
+    int8_t stem_seg0[K::D]; // m_stemd_to_segs[d] = {s, s+1}, -1 = none
+    uint8_t in_sel[K::D]; // membership in m_scaffold_domains
+    uint8_t checked_chain[K::C]; // m_checked_staples
+    int n_ep; // m_active_endpoints, flattened, per-key order preserved
+    short ep_chain[E];
+    int8_t ep_seg[E];
+    short ep_d[E];
+    short ep_pos[E][3];
+    int n_ep0; // m_initial_active_endpoints
+    short ep0_chain[E];
+    int8_t ep0_seg[E];
+    short ep0_d[E];
+    short ep0_pos[E][3];
+    int n_erased; // m_erased_endpoints
+    short erased_pos[8][3];
+
+    // StapleNetwork scratch (top_constraint_points.hpp:40-108)
+    uint8_t net_chain[K::C];
+    short net_growth_idx[K::C];
+    int n_pot_gps, n_pot_iaes, n_pot_ds;
+    short pot_gps[K::D + 1][2];
+    short pot_iaes[K::D + 1][2];
+    short pot_ds[K::D + 1];
+    short scan_stack[K::C][2];
+
+    // non-contiguous selection (movetypes.cpp:512-648)
+    short seg_start[S + 1]; // segment s occupies seg_dom[seg_start[s] .. seg_start[s+1])
+    short seg_dom[2 * K::D + 2];
+    short stems[K::D + 1];
+    short stem_queue[4 * K::D + 8];
+
+    // lane-parallel candidate evaluation results (6 neighbour sites)
+    double site_w[8];
+    int site_o[8];
+    int site_kind[8];
+};
+
+// Move statistics (MovetypeTracking, movetypes.hpp:49-52)
+struct MoveStats {
+    long long attempts[LDO_MAX_MOVETYPES];
+    long long accepts[LDO_MAX_MOVETYPES];
+};
+
+// ---------------------------------------------------------------------------------------------
+// The per-replica engine
+// ---------------------------------------------------------------------------------------------
+
+template <class K>
+struct Engine {
+    System<K> sys;
+    MoveScratch<K>* m;
+    Rng* rng;
+    const MoveSet* ms;
+    const OpsBiasConst* ob;
+    BiasState* bs;
+    const double* grid_vals; // replica's grid-bias values (NaN = off grid)
+    Control ctl;
+    MoveStats* stats;
+
+    // RG per-domain working state (rg_movetypes.hpp:118-126)
+    int di, d, ref_d, stemd, dir, c_attempts, d_max_c_attempts;
+    unsigned long long avail;
+    int max_recoils, max_c_attempts;
+    double delta_e, weight, weight_new;
+
+    // ---- RNG (random_gens.cpp:29-49) ----
+    LDO_HDN double uniform_real() {
+        if (rng->tape != nullptr) {
+            if (rng->tape_pos >= rng->tape_len) {
+                sys.fail(LDO_ERR_TAPE_EXHAUSTED);
+                return 0.5;
+            }
+            const TapeDraw& t = rng->tape[rng->tape_pos];
+            if (t.kind != 0) {
+                sys.fail(LDO_ERR_TAPE_MISMATCH, (int)rng->tape_pos);
+                return 0.5;
+            }
+            rng->tape_pos++;
+            return t.real;
+        }
+        uint32_t o[4];
+        philox4x32_10(*rng, rng->counter++, o);
+        unsigned long long u = ((unsigned long long)o[0] << 32) | o[1];
+        return (double)(u >> 11) * (1.0 / 9007199254740992.0);
+    }
+    LDO_HDN int uniform_int(int lo, int hi) {
+        if (rng->tape != nullptr) {
+            if (rng->tape_pos >= rng->tape_len) {
+                sys.fail(LDO_ERR_TAPE_EXHAUSTED);
+                return lo;
+            }
+            const TapeDraw& t = rng->tape[rng->tape_pos];
+            if (t.kind != 1 || t.lo != lo || t.hi != hi) {
+                sys.fail(LDO_ERR_TAPE_MISMATCH, (int)rng->tape_pos);
+                return lo;
+            }
+            rng->tape_pos++;
+            return t.ival;
+        }
+        uint32_t n = (uint32_t)(hi - lo) + 1u;
+        if (n == 0) return lo; // full 32-bit range never occurs on this path
+        // Lemire's nearly-divisionless unbiased bounded integer
+        uint32_t o[4];
+        philox4x32_10(*rng, rng->counter++, o);
+        unsigned long long mm = (unsigned long long)o[0] * n;
+        uint32_t l = (uint32_t)mm;
+        if (l < n) {
+            uint32_t t = (0u - n) % n;
+            int w = 1;
+            while (l < t) {
+                if (w == 4) {
+                    philox4x32_10(*rng, rng->counter++, o);
+                    w = 0;
+                }
+                mm = (unsigned long long)o[w++] * n;
+                l = (uint32_t)mm;
+            }
+        }
+        return lo + (int)(mm >> 32);
+    }
+
+    // ---- order parameters and biases ----
+    LDO_HDN int calc_op(int i) const {
+        const OpDef& o = ob->ops[i];
+        const SysState<K>* s = sys.s;
+        switch (o.type) {
+        case OP_NUM_STAPLES: return s->num_staples;
+        case OP_NUM_STAPLES_TYPE: return s->type_count[o.arg];
+        case OP_STAPLE_TYPE_FULLY_BOUND: {
+            // order_params.cpp:250-266
+            for (int w = 1; w < s->n_chains; w++) {
+                int c = s->order[w];
+                if (s->chain_type[c] != o.arg) continue;
+                bool full = true;
+                int base = sys.chain_base(c);
+                for (int k = 0; k < s->chain_len[c]; k++) {
+                    if (s->dom[base + k].state != ST_BOUND) {
+                        full = false;
+                        break;
+                    }
+                }
+                if (full) return 1;
+            }
+            return 0;
+        }
+        case OP_NUM_BOUND_DOMAIN_PAIRS: return s->num_fully_bound_pairs;
+        case OP_NUM_MISBOUND_DOMAIN_PAIRS: return s->num_bound_pairs - s->num_fully_bound_pairs;
+        case OP_NUM_STACKED_PAIRS: return s->num_stacked_pairs;
+        case OP_NUM_LINEAR_HELICES: return 0; // never modified in the reference (App. A5)
+        case OP_NUM_STACKED_JUNCTS: return 0;
+        case OP_SUM: {
+            int sum = 0;
+            for (int k = 0; k < o.n_sum; k++) sum += bs->op_val[o.sum_idx[k]];
+            return sum;
+        }
+        }
+        return 0;
+    }
+    // SystemOrderParams::update_move_params (order_params.cpp:595-601)
+    LDO_HD void update_move_params() {
+        for (int i = 0; i < ob->n_ops; i++) bs->op_val[i] = calc_op(i);
+    }
+    LDO_HD double grid_lookup(int b) const {
+        int off = bs->grid_off[b];
+        if (off < 0) return 0;
+        const BiasDef& bd = ob->biases[b];
+        int idx = 0;
+        for (int k = 0; k < bd.n_ops; k++) {
+            int v = bs->op_val[bd.op_idx[k]] - bs->grid_lo[b][k];
+            if (v < 0 || v >= bs->grid_n[b][k]) return 0;
+            idx = idx * bs->grid_n[b][k] + v;
+        }
+        double g = grid_vals[off + idx];
+        return g == g ? g : 0; // NaN marks a point absent from the grid (m_off_grid_bias = 0)
+    }
+    LDO_HD double calc_bias_fn(int b) const {
+        const BiasDef& bd = ob->biases[b];
+        if (bd.type == BIAS_GRID) return grid_lookup(b);
+        int param = bs->op_val[bd.op_idx[0]];
+        int lo = bs->win_min[b], hi = bs->win_max[b];
+        if (bd.type == BIAS_LINEAR_STEP_WELL) {
+            // bias_functions.cpp:139-151
+            if (param < lo) return bd.slope * (lo - param - 1) + bd.min_bias;
+            if (param > hi) return bd.slope * (param - hi - 1) + bd.min_bias;
+            return bd.well_bias;
+        }
+        // bias_functions.cpp:194-204
+        if (param < lo || param > hi) return bd.outside_bias;
+        return bd.well_bias;
+    }
+    // SystemBiases::calc_move (bias_functions.cpp:475-487)
+    LDO_HDN double calc_move_bias() {
+        double diff = 0;
+        for (int b = 0; b < ob->n_biases; b++) {
+            double prev = bs->bias_val[b];
+            double nb = calc_bias_fn(b);
+            bs->bias_val[b] = nb;
+            diff += nb - prev;
+        }
+        bs->move_update_bias += diff;
+        return diff * ctl.bias_mult;
+    }
+    LDO_HD double total_bias() const { return bs->move_update_bias * ctl.bias_mult; }
+
+    // ---- MCMovetype shared helpers (movetypes.cpp:98-158) ----
+    LDO_HD int select_random_domain() {
+        int idx = uniform_int(0, sys.s->num_domains - 1);
+        return sys.domain_by_flat_index(idx);
+    }
+    LDO_HD bool test_acceptance(double p_ratio) {
+        double p_accept = fmin(1.0, p_ratio) * m->modifier;
+        if (p_accept == 1) return true;
+        return p_accept > uniform_real();
+    }
+    LDO_HD void reset_internal() {
+        m->n_modified = 0;
+        m->n_assigned = 0;
+        m->added_chain = -1;
+        m->rejected = 0;
+        m->modifier = 1;
+    }
+    LDO_HD void push_assigned(int dd) {
+        if (m->n_assigned >= MoveScratch<K>::A) {
+            sys.fail(LDO_ERR_CAPACITY, 1);
+            return;
+        }
+        m->assigned[m->n_assigned++] = (short)dd;
+    }
+    LDO_HD void push_modified(int dd) {
+        if (m->n_modified >= K::D) {
+            sys.fail(LDO_ERR_CAPACITY, 2);
+            return;
+        }
+        m->modified[m->n_modified++] = (short)dd;
+    }
+    LDO_HD V3 rec_pos(const DomRec& r) const { return v3(r.x, r.y, r.z); }
+
+    // MCMovetype::reset_origami (movetypes.cpp:53-85)
+    LDO_HDN void reset_origami() {
+        for (int k = 0; k < m->n_assigned; k++) sys.unassign_domain(m->assigned[k]);
+        if (m->added_chain >= 0) {
+            sys.delete_chain(m->added_chain);
+            sys.s->current_c_i -= 1;
+        }
+        for (int k = 0; k < m->n_modified; k++) {
+            int dd = m->modified[k];
+            const DomRec& r = m->prev[dd];
+            sys.set_checked_domain_config(dd, rec_pos(r), r.ore);
+        }
+        sys.s->constraints_violated = 0;
+    }
+
+    // staple_is_connector / scan_for_scaffold_domain (movetypes.cpp:160-232); chains tracked by slot
+    LDO_HDN bool scan_for_scaffold_domain(int start, uint8_t* participating) {
+        // iterative depth-first walk; frame = (entry domain, next index in its chain)
+        short (*st)[2] = m->scan_stack;
+        int sp = 0;
+        st[0][0] = (short)start;
+        st[0][1] = 0;
+        participating[sys.chain(start)] = 1;
+        while (sp >= 0) {
+            int dom = st[sp][0];
+            int c = sys.chain(dom);
+            int base = sys.chain_base(c);
+            int len = sys.s->chain_len[c];
+            bool descended = false;
+            while (st[sp][1] < len) {
+                int cur = base + st[sp][1];
+                st[sp][1]++;
+                if (cur == dom) continue;
+                int b = sys.s->bound[cur];
+                if (b < 0) continue;
+                if (sys.chain(b) == c) continue;
+                if (sys.chain(b) == 0) return true;
+                if (participating[sys.chain(b)]) continue;
+                if (sp + 1 >= K::C) {
+                    sys.fail(LDO_ERR_CAPACITY, 3);
+                    return true;
+                }
+                participating[sys.chain(b)] = 1;
+                sp++;
+                st[sp][0] = (short)b;
+                st[sp][1] = 0;
+                descended = true;
+                break;
+            }
+            if (!descended) sp--;
+        }
+        return false;
+    }
+    LDO_HDN bool staple_is_connector(int c) {
+        int base = sys.chain_base(c);
+        for (int k = 0; k < sys.s->chain_len[c]; k++) {
+            int dd = base + k;
+            if (sys.s->dom[dd].state != ST_UNBOUND) {
+                int b = sys.s->bound[dd];
+                if (sys.chain(b) == 0) continue;
+                for (int q = 0; q < K::C; q++) m->net_chain[q] = 0;
+                m->net_chain[c] = 1;
+                if (!scan_for_scaffold_domain(b, m->net_chain)) return true;
+            }
+        }
+        return false;
+    }
+    LDO_HD int num_bound_staple_domains(int c) const {
+        int n = 0;
+        int base = sys.chain_base(c);
+        for (int k = 0; k < sys.s->chain_len[c]; k++) {
+            int st = sys.s->dom[base + k].state;
+            if (st == ST_BOUND || st == ST_MISBOUND) n++;
+        }
+        return n;
+    }
+    LDO_HD bool staple_has_bound_domain(int c) const {
+        int base = sys.chain_base(c);
+        for (int k = 0; k < sys.s->chain_len[c]; k++) {
+            if (sys.s->dom[base + k].state == ST_BOUND) return true;
+        }
+        return false;
+    }
+    // find_bound_domains (movetypes.cpp:258-277): count, and k-th pair (new domain, old domain)
+    LDO_HD int count_bound_to_other_chains(int c) const {
+        int n = 0;
+        int base = sys.chain_base(c);
+        for (int k = 0; k < sys.s->chain_len[c]; k++) {
+            int b = sys.s->bound[base + k];
+            if (b >= 0 && sys.chain(b) != c) n++;
+        }
+        return n;
+    }
+    LDO_HD int kth_bound_to_other_chains(int c, int kth) const {
+        int base = sys.chain_base(c);
+        for (int k = 0; k < sys.s->chain_len[c]; k++) {
+            int b = sys.s->bound[base + k];
+            if (b >= 0 && sys.chain(b) != c) {
+                if (kth == 0) return base + k;
+                kth--;
+            }
+        }
+        return -1;
+    }
+
+    // ---- OrientationRotation (orientation_movetype.cpp:30-65) ----
+    LDO_HDN bool move_orientation_rotation() {
+        bool accepted = false;
+        int dd = select_random_domain();
+        int o_new = uniform_int(0, 5);
+        int st = sys.s->dom[dd].state;
+        if (st == ST_BOUND || st == ST_MISBOUND) {
+            double de = 0;
+            int o_old = sys.s->dom[dd].ore;
+            int b = sys.s->bound[dd];
+            de += sys.unassign_domain(b);
+            // set_domain_orientation: domain is now unbound (origami_system.cpp:543-551)
+            sys.s->dom[dd].ore = (int8_t)o_new;
+            V3 p = rec_pos(sys.s->dom[dd]);
+            de += sys.set_domain_config(b, p, o_new ^ 1);
+            if (!sys.s->constraints_violated) accepted = test_acceptance(exp(-de));
+            if (!accepted) {
+                sys.unassign_domain(b);
+                sys.s->dom[dd].ore = (int8_t)o_old;
+                sys.set_checked_domain_config(b, p, o_old < 6 ? (o_old ^ 1) : o_old);
+            }
+        }
+        else {
+            sys.s->dom[dd].ore = (int8_t)o_new;
+            accepted = true;
+        }
+        return accepted;
+    }
+
+    // ---- growth helpers (movetypes.cpp:322-383, met_movetypes.cpp:50-95) ----
+    LDO_HD double set_growth_point(int d_new, int d_old) {
+        const DomRec& ro = sys.s->dom[d_old];
+        int o_new = ro.ore < 6 ? (ro.ore ^ 1) : ro.ore;
+        double de = sys.set_domain_config(d_new, rec_pos(ro), o_new);
+        if (sys.s->constraints_violated) m->rejected = 1;
+        else push_assigned(d_new);
+        return de;
+    }
+    // MetMCMovetype::grow_chain over domains base+from, base+from+step, ... (count domains incl. the first)
+    LDO_HDN void met_grow_chain(int first, int stepdir, int count) {
+        for (int i = 1; i < count; i++) {
+            int dd = first + stepdir * i;
+            int prev = first + stepdir * (i - 1);
+            V3 p = rec_pos(sys.s->dom[prev]) + ore_vec(uniform_int(0, 5));
+            int o = uniform_int(0, 5);
+            delta_e += sys.set_domain_config(dd, p, o);
+            if (sys.s->constraints_violated) {
+                m->rejected = 1;
+                break;
+            }
+            push_assigned(dd);
+        }
+    }
+    // RegrowthMCMovetype::grow_staple (movetypes.cpp:343-370)
+    LDO_HD void met_grow_staple(int c, int d_i) {
+        int base = sys.chain_base(c);
+        int len = sys.s->chain_len[c];
+        if (len - d_i > 1) met_grow_chain(base + d_i, +1, len - d_i);
+        if (m->rejected) return;
+        if (d_i + 1 > 1) met_grow_chain(base + d_i, -1, d_i + 1);
+    }
+    LDO_HD void met_unassign_domains(int c) {
+        int base = sys.chain_base(c);
+        for (int k = 0; k < sys.s->chain_len[c]; k++) {
+            int dd = base + k;
+            m->prev[dd] = sys.s->dom[dd];
+            push_modified(dd);
+            delta_e += sys.unassign_domain(dd);
+        }
+    }
+    LDO_HD void met_add_external_bias() {
+        update_move_params();
+        delta_e += calc_move_bias();
+    }
+
+    // ---- MetStapleExchange (met_movetypes.cpp:192-403) ----
+    LDO_HD bool exchange_accept(double pratio, int type, bool staple_bound, const MoveDef& md) {
+        if (staple_bound) {
+            m->modifier *= ms->exchange_mults[md.exchange_mults_off + type - 1];
+            if (m->modifier * fmin(1.0, pratio) > 1) {
+                if (md.adaptive_exchange) return false; // adaptive multipliers are host-side state: not adapted on device
+                if (ms->allow_nonsensical_ps) return true;
+                sys.fail(LDO_ERR_NONSENSICAL_P, type);
+                return false;
+            }
+        }
+        return test_acceptance(pratio);
+    }
+    LDO_HDN bool move_staple_exchange(const MoveDef& md) {
+        SysState<K>* s = sys.s;
+        delta_e = 0;
+        int insertion_sites = s->num_domains;
+        if (uniform_real() < 0.5) {
+            // insert_staple (:303-359)
+            int type = uniform_int(1, sys.sc->n_types - 1);
+            if (s->num_staples == sys.sc->max_total_staples) return false;
+            if (s->type_count[type] == sys.sc->max_type_staples) return false;
+            int c = sys.add_chain(type);
+            if (c < 0) return false;
+            if (sys.sc->apply_mean_field_cor) delta_e += log(6.0);
+            delta_e += sys.tt.init_energy;
+            m->added_chain = c;
+            // select_new_growthpoint (movetypes.cpp:372-383)
+            int len = s->chain_len[c];
+            int g_new = sys.chain_base(c) + uniform_int(0, len - 1);
+            int g_old = select_random_domain();
+            while (sys.chain(g_old) == c && s->status == LDO_OK) g_old = select_random_domain();
+            delta_e += set_growth_point(g_new, g_old);
+            if (m->rejected) return false;
+            met_grow_staple(c, s->dindex[g_new]);
+            if (m->rejected) return false;
+            bool staple_bound = staple_has_bound_domain(c);
+            int num_bd = num_bound_staple_domains(c);
+            // staple_insertion_accepted (:212-253)
+            met_add_external_bias();
+            double boltz = exp(-delta_e);
+            int Ni_new = s->type_count[type];
+            double pratio = (double)len / 6.0 / Ni_new * boltz;
+            pratio *= insertion_sites * sys.sc->staple_M;
+            pratio /= num_bd;
+            return exchange_accept(pratio, type, staple_bound, md);
+        }
+        // delete_staple (:361-403)
+        int type = uniform_int(1, sys.sc->n_types - 1);
+        int n_of_type = s->type_count[type];
+        if (n_of_type == 0) {
+            m->rejected = 1;
+            return false;
+        }
+        int c = sys.staple_of_type(type, uniform_int(0, n_of_type - 1));
+        if (staple_is_connector(c)) return false;
+        bool staple_bound = staple_has_bound_domain(c);
+        int num_bd = num_bound_staple_domains(c);
+        int len = s->chain_len[c];
+        met_unassign_domains(c);
+        if (sys.sc->apply_mean_field_cor) delta_e -= log(6.0);
+        delta_e -= sys.tt.init_energy;
+        // staple_deletion_accepted (:255-301)
+        s->num_staples--;
+        met_add_external_bias();
+        s->num_staples++;
+        double boltz = exp(-delta_e);
+        int Ni = s->type_count[type];
+        double pratio = Ni * 6.0 / (double)len * boltz;
+        pratio /= sys.sc->staple_M * (insertion_sites - len);
+        pratio *= num_bd;
+        bool accepted = exchange_accept(pratio, type, staple_bound, md);
+        if (accepted) sys.delete_chain(c);
+        return accepted;
+    }
+
+    // ---- MetStapleRegrowth (met_movetypes.cpp:470-513) ----
+    LDO_HDN bool move_met_staple_regrowth() {
+        SysState<K>* s = sys.s;
+        delta_e = 0;
+        if (s->num_staples == 0) return false;
+        int c = s->order[uniform_int(1, s->num_staples)];
+        if (staple_is_connector(c)) return false;
+        int n_bd = count_bound_to_other_chains(c);
+        if (n_bd == 0) {
+            sys.fail(LDO_ERR_UNBOUND_STAPLE, c);
+            return false;
+        }
+        int g_new = kth_bound_to_other_chains(c, uniform_int(0, n_bd - 1));
+        int g_old = s->bound[g_new];
+        met_unassign_domains(c);
+        delta_e += set_growth_point(g_new, g_old);
+        if (m->rejected) return false;
+        met_grow_staple(c, s->dindex[g_new]);
+        if (m->rejected) return false;
+        met_add_external_bias();
+        int new_num_bd = num_bound_staple_domains(c);
+        double pratio = exp(-delta_e) * n_bd / new_num_bd;
+        return test_acceptance(pratio);
+    }
+
+    // ---- CB staple regrowth (cb_movetypes.cpp:44-404) ----
+    // Weights of the six neighbour sites of p_prev for `dom`, evaluated one site per lane
+    // (CBMCMovetype::calc_biases, cb_movetypes.cpp:58-102). Results: site_kind 0 = skipped,
+    // 1 = empty site (orientation drawn later), 2 = binds the unbound occupant with orientation site_o.
+    LDO_HDN void cb_site_weights(V3 p_prev, int dom) {
+        for (int k = LDO_LANE; k < 6; k += LDO_NLANES) {
+            V3 p = p_prev + ore_vec(k);
+            int j = sys.occupant(p);
+            int kind = 0, o = ORE_ZERO;
+            double w = 0;
+            if (j < 0) {
+                kind = 1;
+                w = 6 * exp(-0.0);
+            }
+            else if (sys.s->dom[j].state == ST_UNBOUND) {
+                int oj = sys.s->dom[j].ore;
+                o = oj < 6 ? (oj ^ 1) : oj;
+                int ns, partner;
+                System<K> view = sys; // private overlay per lane
+                DeltaConfig dc = view.eval_place(dom, p, o, &ns, &partner);
+                if (!dc.violated) {
+                    kind = 2;
+                    w = exp(-dc.e);
+                }
+            }
+            m->site_kind[k] = kind;
+            m->site_o[k] = o;
+            m->site_w[k] = w;
+        }
+        LDO_SYNCWARP();
+    }
+    // select_and_set_config for CBStapleRegrowth (cb_movetypes.cpp:104-160, 363-387)
+    LDO_HDN void cb_select_and_set_config(int dom, int prev_dom, bool regrow_old, double& bias) {
+        V3 p_prev = rec_pos(sys.s->dom[prev_dom]);
+        cb_site_weights(p_prev, dom);
+        sys.s->constraints_violated = 0;
+        double ros = 0;
+        for (int k = 0; k < 6; k++) {
+            if (m->site_kind[k] != 0) ros += m->site_w[k];
+        }
+        if (ros == 0) {
+            m->rejected = 1;
+            return;
+        }
+        bias *= ros;
+        if (!regrow_old) {
+            double cum = 0;
+            double r = uniform_real();
+            V3 p_new = v3(0, 0, 0);
+            int o_new = ORE_ZERO;
+            for (int k = 0; k < 6; k++) {
+                if (m->site_kind[k] == 0) continue;
+                cum += m->site_w[k] / ros;
+                if (r < cum) {
+                    p_new = p_prev + ore_vec(k);
+                    o_new = m->site_kind[k] == 2 ? m->site_o[k] : ORE_ZERO;
+                    break;
+                }
+            }
+            if (o_new == ORE_ZERO) o_new = uniform_int(0, 5);
+            sys.set_checked_domain_config(dom, p_new, o_new);
+        }
+        else {
+            const DomRec& r = m->oldc[dom];
+            sys.set_checked_domain_config(dom, rec_pos(r), r.ore);
+        }
+        push_assigned(dom);
+    }
+    LDO_HD void cb_grow_chain(int first, int stepdir, int count, bool regrow_old, double& bias) {
+        for (int i = 1; i < count; i++) {
+            cb_select_and_set_config(first + stepdir * i, first + stepdir * (i - 1), regrow_old, bias);
+            if (m->rejected) break;
+        }
+    }
+    LDO_HD void cb_set_growthpoint_and_grow_staple(int g_new, int g_old, int c, bool regrow_old, double& bias) {
+        if (regrow_old) {
+            // set_old_growth_point (cb_movetypes.cpp:168-180)
+            double de = sys.set_checked_domain_config(g_new, rec_pos(sys.s->dom[g_old]), m->oldc[g_new].ore);
+            bias *= exp(-de);
+            push_assigned(g_new);
+        }
+        else {
+            double de = set_growth_point(g_new, g_old);
+            bias *= exp(-de);
+        }
+        if (!m->rejected) {
+            int base = sys.chain_base(c);
+            int len = sys.s->chain_len[c];
+            int d_i = sys.s->dindex[g_new];
+            if (len - d_i > 1) cb_grow_chain(base + d_i, +1, len - d_i, regrow_old, bias);
+            if (m->rejected) return;
+            if (d_i + 1 > 1) cb_grow_chain(base + d_i, -1, d_i + 1, regrow_old, bias);
+        }
+    }
+    LDO_HD void cb_unassign_domains(int c) {
+        int base = sys.chain_base(c);
+        for (int k = 0; k < sys.s->chain_len[c]; k++) {
+            int dd = base + k;
+            m->prev[dd] = sys.s->dom[dd];
+            push_modified(dd);
+            sys.unassign_domain(dd);
+        }
+    }
+    LDO_HDN bool move_cb_staple_regrowth() {
+        SysState<K>* s = sys.s;
+        if (s->num_staples == 0) return false;
+        int c = s->order[uniform_int(1, s->num_staples)];
+        if (staple_is_connector(c)) return false;
+        double bias = 1;
+        int n_bd = count_bound_to_other_chains(c);
+        if (n_bd == 0) {
+            sys.fail(LDO_ERR_UNBOUND_STAPLE, c);
+            return false;
+        }
+        // bound (new, old) pairs are fixed before anything is unassigned
+        short bd_new[8], bd_old[8];
+        bool small = n_bd <= 8;
+        if (small) {
+            for (int k = 0; k < n_bd; k++) {
+                bd_new[k] = (short)kth_bound_to_other_chains(c, k);
+                bd_old[k] = s->bound[bd_new[k]];
+            }
+        }
+        else {
+            sys.fail(LDO_ERR_CAPACITY, 4);
+            return false;
+        }
+        bias *= n_bd;
+        int gi = uniform_int(0, n_bd - 1);
+        cb_unassign_domains(c);
+        cb_set_growthpoint_and_grow_staple(bd_new[gi], bd_old[gi], c, false, bias);
+        if (m->rejected) return false;
+        bias /= num_bound_staple_domains(c);
+        // add_external_bias (cb_movetypes.cpp:52-56)
+        update_move_params();
+        bias *= exp(-calc_move_bias());
+        // setup_for_regrow_old (cb_movetypes.cpp:237-247)
+        double new_bias = bias;
+        double new_modifier = m->modifier;
+        bias = 1;
+        m->n_modified = 0;
+        m->n_assigned = 0;
+        {
+            int base = sys.chain_base(c);
+            for (int k = 0; k < s->chain_len[c]; k++) m->oldc[base + k] = m->prev[base + k];
+        }
+        gi = uniform_int(0, n_bd - 1);
+        cb_unassign_domains(c);
+        cb_set_growthpoint_and_grow_staple(bd_new[gi], bd_old[gi], c, true, bias);
+        m->modifier = new_modifier;
+        // test_cb_acceptance (cb_movetypes.cpp:182-198)
+        double ratio = new_bias / bias;
+        if (test_acceptance(ratio)) {
+            reset_origami();
+            update_move_params();
+            calc_move_bias();
+            return true;
+        }
+        m->n_modified = 0;
+        m->n_assigned = 0;
+        return false;
+    }
+
+    // ---- Constraintpoints (top_constraint_points.cpp:163-601) ----
+    LDO_HDN void cp_reset() {
+        for (int k = 0; k < K::D; k++) {
+            m->seg_of[k] = -1;
+            m->stem_gp[k] = -1;
+            m->gp_stem[k] = -1;
+            m->inactive[k] = -1;
+            m->stem_seg0[k] = -1;
+            m->in_sel[k] = 0;
+        }
+        for (int k = 0; k < K::C; k++) m->checked_chain[k] = 0;
+        for (int k = 0; k < MoveScratch<K>::S; k++) m->scaf_dir[k] = 0;
+        m->n_ep = 0;
+        m->n_ep0 = 0;
+        m->n_erased = 0;
+        m->n_regrow = 0;
+        m->n_sel = 0;
+    }
+    LDO_HD int cp_dir_of(int chain, int seg) const {
+        if (chain == 0) return m->scaf_dir[seg];
+        return seg == 0 ? 1 : -1;
+    }
+    LDO_HD int cp_get_dir(int dd) const {
+        int seg = m->seg_of[dd] < 0 ? 0 : m->seg_of[dd];
+        return cp_dir_of(sys.chain(dd), seg);
+    }
+    LDO_HDN void cp_add_active_endpoint_seg(int dd, V3 p, int seg) {
+        if (m->n_ep >= MoveScratch<K>::E) {
+            sys.fail(LDO_ERR_CAPACITY, 5);
+            return;
+        }
+        int e = m->n_ep++;
+        m->ep_chain[e] = (short)sys.chain(dd);
+        m->ep_seg[e] = (int8_t)seg;
+        m->ep_d[e] = (short)sys.dindex(dd);
+        m->ep_pos[e][0] = (short)p.x;
+        m->ep_pos[e][1] = (short)p.y;
+        m->ep_pos[e][2] = (short)p.z;
+    }
+    LDO_HD void cp_add_active_endpoint(int dd, V3 p) { cp_add_active_endpoint_seg(dd, p, m->seg_of[dd]); }
+    LDO_HD void cp_erase_ep(int e) {
+        for (int k = e; k + 1 < m->n_ep; k++) {
+            m->ep_chain[k] = m->ep_chain[k + 1];
+            m->ep_seg[k] = m->ep_seg[k + 1];
+            m->ep_d[k] = m->ep_d[k + 1];
+            m->ep_pos[k][0] = m->ep_pos[k + 1][0];
+            m->ep_pos[k][1] = m->ep_pos[k + 1][1];
+            m->ep_pos[k][2] = m->ep_pos[k + 1][2];
+        }
+        m->n_ep--;
+    }
+    LDO_HDN void cp_save_initial() {
+        m->n_ep0 = m->n_ep;
+        for (int k = 0; k < m->n_ep; k++) {
+            m->ep0_chain[k] = m->ep_chain[k];
+            m->ep0_seg[k] = m->ep_seg[k];
+            m->ep0_d[k] = m->ep_d[k];
+            m->ep0_pos[k][0] = m->ep_pos[k][0];
+            m->ep0_pos[k][1] = m->ep_pos[k][1];
+            m->ep0_pos[k][2] = m->ep_pos[k][2];
+        }
+    }
+    LDO_HDN void cp_reset_active_endpoints() {
+        m->n_ep = m->n_ep0;
+        for (int k = 0; k < m->n_ep0; k++) {
+            m->ep_chain[k] = m->ep0_chain[k];
+            m->ep_seg[k] = m->ep0_seg[k];
+            m->ep_d[k] = m->ep0_d[k];
+            m->ep_pos[k][0] = m->ep0_pos[k][0];
+            m->ep_pos[k][1] = m->ep0_pos[k][1];
+            m->ep_pos[k][2] = m->ep0_pos[k][2];
+        }
+    }
+    // remove_active_endpoint (:299-320): erased positions are kept in m_erased_endpoints
+    LDO_HDN void cp_remove_active_endpoint(int dd) {
+        m->n_erased = 0;
+        int c = sys.chain(dd), seg = m->seg_of[dd], di_ = sys.dindex(dd);
+        int k = 0;
+        while (k < m->n_ep) {
+            if (m->ep_chain[k] == c && m->ep_seg[k] == seg && m->ep_d[k] == di_) {
+                if (m->n_erased < 8) {
+                    m->erased_pos[m->n_erased][0] = m->ep_pos[k][0];
+                    m->erased_pos[m->n_erased][1] = m->ep_pos[k][1];
+                    m->erased_pos[m->n_erased][2] = m->ep_pos[k][2];
+                    m->n_erased++;
+                }
+                else {
+                    sys.fail(LDO_ERR_CAPACITY, 6);
+                }
+                cp_erase_ep(k);
+            }
+            else {
+                k++;
+            }
+        }
+    }
+    // remove_activated_endpoint (:322-338)
+    LDO_HDN void cp_remove_activated_endpoint(int dd) {
+        int ed = m->inactive[dd];
+        if (ed < 0) return;
+        int c = sys.chain(ed), seg = m->seg_of[ed], di_ = sys.dindex(ed);
+        for (int k = 0; k < m->n_ep; k++) {
+            if (m->ep_chain[k] == c && m->ep_seg[k] == seg && m->ep_d[k] == di_) {
+                cp_erase_ep(k);
+                break;
+            }
+        }
+    }
+    // update_endpoints (:340-349)
+    LDO_HDN void cp_update_endpoints(int dd) {
+        cp_remove_active_endpoint(dd);
+        int ed = m->inactive[dd];
+        if (ed >= 0) cp_add_active_endpoint(ed, rec_pos(sys.s->dom[dd]));
+    }
+    // endpoint_reached (:359-372)
+    LDO_HDN bool cp_endpoint_reached(int dd, V3 p) const {
+        int c = sys.chain(dd), seg = m->seg_of[dd], di_ = sys.dindex(dd);
+        for (int k = 0; k < m->n_ep; k++) {
+            if (m->ep_chain[k] == c && m->ep_seg[k] == seg && m->ep_d[k] == di_ && m->ep_pos[k][0] == p.x &&
+                m->ep_pos[k][1] == p.y && m->ep_pos[k][2] == p.z) {
+                return true;
+            }
+        }
+        return false;
+    }
+    // calc_remaining_steps (:571-601)
+    LDO_HD int cp_remaining_steps(int end_d_i, int dd, int dir_) const {
+        int dm = sys.dindex(dd);
+        if (sys.sc->cyclic && sys.chain(dd) == 0) {
+            int n = sys.s->chain_len[0];
+            if (dir_ > 0 && end_d_i < dm) return n + end_d_i - dm;
+            if (dir_ < 0 && end_d_i > dm) return dm + n - end_d_i;
+            if (dir_ == 0 || end_d_i == dm) return 0;
+            return abs(end_d_i - dm);
+        }
+        return abs(end_d_i - dm);
+    }
+    // num_walks(...) == 0 (ideal_random_walk.cpp:35-40)
+    LDO_HD static bool no_walks(V3 a, V3 b, int steps) {
+        int dr = abssum(b - a);
+        return dr > steps || (steps - dr) % 2 != 0;
+    }
+    // walks_remain (:397-445)
+    LDO_HD bool cp_walks_remain_seg(int c, int seg, int dd, V3 p) const {
+        int dir_ = cp_dir_of(c, seg);
+        for (int k = 0; k < m->n_ep; k++) {
+            if (m->ep_chain[k] != c || m->ep_seg[k] != seg) continue;
+            int steps = cp_remaining_steps(m->ep_d[k], dd, dir_);
+            V3 ep = v3(m->ep_pos[k][0], m->ep_pos[k][1], m->ep_pos[k][2]);
+            if (no_walks(p, ep, steps)) return false;
+        }
+        return true;
+    }
+    LDO_HDN bool cp_walks_remain(int dd, V3 p) const {
+        int c = sys.chain(dd);
+        if (m->stem_gp[dd] >= 0) {
+            int s0 = m->stem_seg0[dd];
+            if (s0 < 0) return true; // m_stemd_to_segs[domain] default-constructs to an empty list
+            if (!cp_walks_remain_seg(c, s0, dd, p)) return false;
+            return cp_walks_remain_seg(c, s0 + 1, dd, p);
+        }
+        return cp_walks_remain_seg(c, m->seg_of[dd], dd, p);
+    }
+
+    // StapleNetwork::scan_network (top_constraint_points.cpp:36-161), iterative.
+    // Returns whether the network is externally bound.
+    LDO_HDN bool net_scan(int start) {
+        SysState<K>* s = sys.s;
+        for (int k = 0; k < K::C; k++) m->net_chain[k] = 0;
+        m->net_chain[0] = 1;
+        m->n_pot_gps = 0;
+        m->n_pot_iaes = 0;
+        m->n_pot_ds = 0;
+        bool external = false;
+        short (*st)[2] = m->scan_stack;
+        int sp = 0;
+        // enter frame
+        st[0][0] = (short)start;
+        st[0][1] = 0;
+        m->net_chain[sys.chain(start)] = 1;
+        m->net_growth_idx[sys.chain(start)] = (short)sys.dindex(start);
+        m->pot_ds[m->n_pot_ds++] = (short)start;
+        while (sp >= 0) {
+            int g = st[sp][0];
+            int ci = sys.chain(g);
+            int base = sys.chain_base(ci);
+            int len = s->chain_len[ci];
+            int gi = sys.dindex(g);
+            bool descended = false;
+            while (st[sp][1] < len - 1) {
+                int k = st[sp][1]++;
+                // make_staple_stack order: 3' of the growth domain, then 5' (:135-161)
+                int idx = (k < len - 1 - gi) ? (gi + 1 + k) : (gi - 1 - (k - (len - 1 - gi)));
+                int dd = base + idx;
+                m->pot_ds[m->n_pot_ds++] = (short)dd;
+                int bd = s->bound[dd];
+                if (bd < 0 || sys.chain(bd) == ci) continue;
+                int bd_ci = sys.chain(bd);
+                if (m->net_chain[bd_ci]) {
+                    bool ext = false;
+                    if (bd_ci == 0) ext = !m->in_sel[bd];
+                    if (!ext) {
+                        // add_potential_inactive_endpoint (:155-161)
+                        bool bd_in_ds = false;
+                        for (int q = 0; q < m->n_pot_ds; q++) {
+                            if (m->pot_ds[q] == bd) {
+                                bd_in_ds = true;
+                                break;
+                            }
+                        }
+                        int e = m->n_pot_iaes++;
+                        if (bd_in_ds) {
+                            m->pot_iaes[e][0] = (short)bd;
+                            m->pot_iaes[e][1] = (short)dd;
+                        }
+                        else {
+                            m->pot_iaes[e][0] = (short)dd;
+                            m->pot_iaes[e][1] = (short)bd;
+                        }
+                    }
+                    if (!external && ext) external = true;
+                }
+                else {
+                    int e = m->n_pot_gps++;
+                    m->pot_gps[e][0] = (short)dd;
+                    m->pot_gps[e][1] = (short)bd;
+                    if (sp + 1 >= K::C) {
+                        sys.fail(LDO_ERR_CAPACITY, 7);
+                        return true;
+                    }
+                    sp++;
+                    st[sp][0] = (short)bd;
+                    st[sp][1] = 0;
+                    m->net_chain[bd_ci] = 1;
+                    m->net_growth_idx[bd_ci] = (short)sys.dindex(bd);
+                    m->pot_ds[m->n_pot_ds++] = (short)bd;
+                    descended = true;
+                    break;
+                }
+            }
+            if (!descended) sp--;
+        }
+        return external;
+    }
+
+    // find_growthpoints_endpoints (:454-494)
+    LDO_HDN void cp_find_growthpoints_endpoints(const short* doms, int n, int seg) {
+        SysState<K>* s = sys.s;
+        for (int q = 0; q < n; q++) {
+            int dd = doms[q];
+            m->regrow[m->n_regrow++] = (short)dd;
+            m->seg_of[dd] = (int8_t)seg;
+            int bd = s->bound[dd];
+            if (bd < 0 || sys.chain(bd) == sys.chain(dd) || m->checked_chain[sys.chain(bd)]) continue;
+            bool external = net_scan(bd);
+            int e = m->n_pot_gps++;
+            m->pot_gps[e][0] = (short)dd;
+            m->pot_gps[e][1] = (short)bd;
+            if (external) {
+                // add_active_endpoints_on_scaffold (:540-559)
+                for (int k = 0; k < m->n_pot_gps; k++) {
+                    int gd = m->pot_gps[k][0];
+                    if (sys.chain(gd) == 0) cp_add_active_endpoint_seg(gd, rec_pos(s->dom[gd]), seg);
+                }
+                for (int k = 0; k < m->n_pot_iaes; k++) {
+                    int second = m->pot_iaes[k][1];
+                    if (sys.chain(second) == 0) {
+                        cp_add_active_endpoint_seg(m->pot_iaes[k][0], rec_pos(s->dom[second]), seg);
+                    }
+                }
+            }
+            else {
+                for (int k = 0; k < m->n_pot_gps; k++) {
+                    m->gp_stem[m->pot_gps[k][0]] = m->pot_gps[k][1];
+                    m->stem_gp[m->pot_gps[k][1]] = m->pot_gps[k][0];
+                }
+                for (int k = 0; k < m->n_pot_iaes; k++) m->inactive[m->pot_iaes[k][0]] = m->pot_iaes[k][1];
+                for (int k = 0; k < m->n_pot_ds; k++) {
+                    int pd = m->pot_ds[k];
+                    if (m->n_regrow >= K::D) {
+                        sys.fail(LDO_ERR_CAPACITY, 8);
+                        return;
+                    }
+                    m->regrow[m->n_regrow++] = (short)pd;
+                    // add_staple_to_segs_maps: unordered_map::insert keeps existing entries (:561-564)
+                    if (m->seg_of[pd] < 0) {
+                        m->seg_of[pd] = (sys.dindex(pd) >= m->net_growth_idx[sys.chain(pd)]) ? 0 : 1;
+                    }
+                }
+            }
+            for (int k = 0; k < K::C; k++) {
+                if (m->net_chain[k]) m->checked_chain[k] = 1;
+            }
+        }
+    }
+
+    // ---- CT selection (movetypes.cpp:469-719) ----
+    // select_indices on the whole scaffold, min_length 2, seg 0
+    LDO_HDN void ct_select_indices(const MoveDef& md) {
+        SysState<K>* s = sys.s;
+        int n = s->chain_len[0];
+        for (;;) {
+            if (s->status != LDO_OK) return;
+            int max_length = n < md.max_regrowth ? n : md.max_regrowth;
+            int sel_length = uniform_int(2, max_length);
+            int start_i = uniform_int(0, n - 1);
+            dir = uniform_int(0, 1);
+            if (dir == 0) dir = -1;
+            // forward part
+            short* buf = m->seg_dom; // scratch: forward list then backward list
+            int nf = 0, nb = 0;
+            int cur = sys.chain_base(0) + start_i;
+            while (cur >= 0 && nf != sel_length) {
+                buf[nf++] = (short)cur;
+                cur = sys.step(cur, dir);
+            }
+            int back = sys.step(sys.chain_base(0) + start_i, -dir);
+            while (back >= 0 && nf + nb != sel_length) {
+                buf[K::D + 1 + nb] = (short)back;
+                nb++;
+                back = sys.step(back, -dir);
+            }
+            if (nf + nb < 2) continue;
+            m->n_sel = 0;
+            for (int k = nb - 1; k >= 0; k--) m->sel_scaf[m->n_sel++] = buf[K::D + 1 + k];
+            for (int k = 0; k < nf; k++) m->sel_scaf[m->n_sel++] = buf[k];
+            if (cur >= 0) cp_add_active_endpoint_seg(cur, rec_pos(s->dom[cur]), 0);
+            return;
+        }
+    }
+
+    // check_for_stemds (movetypes.cpp:702-719); stems are queued in m->stem_queue[qh..qt)
+    LDO_HDN void ct_check_for_stemds(int cur, int& qt) {
+        SysState<K>* s = sys.s;
+        if (s->dom[cur].state != ST_BOUND) return;
+        int bd = s->bound[cur];
+        for (int sd = -1; sd <= 1; sd += 2) {
+            int nd = sys.step(bd, sd);
+            if (nd >= 0 && s->dom[nd].state == ST_BOUND) {
+                int bn = s->bound[nd];
+                if (sys.chain(bn) == 0) {
+                    if (qt >= 4 * K::D + 8) {
+                        sys.fail(LDO_ERR_CAPACITY, 9);
+                        return;
+                    }
+                    m->stem_queue[qt++] = (short)bn;
+                }
+            }
+        }
+    }
+    // fill_seg (movetypes.cpp:666-700). seg contents are appended at m->seg_dom[seg_n...]; returns
+    // whether max_length was reached. `seg_size` counts elements already in the segment.
+    LDO_HDN bool ct_fill_seg(int start_d, int max_length, int seg_max, int dir_, int& n_domains, int& qt, int& seg_n, int seg_size) {
+        int cur = start_d;
+        ct_check_for_stemds(cur, qt);
+        int next = start_d;
+        while (seg_size != seg_max && next >= 0) {
+            next = sys.step(cur, dir_);
+            if (next < 0) break;
+            int next_next = sys.step(next, dir_);
+            if (next_next >= 0 && m->in_sel[next_next]) break;
+            m->seg_dom[seg_n++] = (short)next;
+            seg_size++;
+            m->in_sel[next] = 1;
+            n_domains++;
+            if (n_domains == max_length) return true;
+            cur = next;
+            ct_check_for_stemds(cur, qt);
+        }
+        return false;
+    }
+
+    // select_noncontig_segs (movetypes.cpp:512-648). Segments are laid out in m->seg_dom with
+    // m->seg_start; dirs in m->scaf_dir; stems in m->stems. Returns the number of segments.
+    LDO_HDN int ct_select_noncontig_segs(const MoveDef& md, int& n_stems) {
+        SysState<K>* s = sys.s;
+        const int SMAX = MoveScratch<K>::S;
+        int n = s->chain_len[0];
+        int max_length = uniform_int(2, md.max_regrowth);
+        int seg_max = uniform_int(2, md.max_seg_regrowth + 1);
+        int start_d = sys.chain_base(0) + uniform_int(0, n - 1);
+        int dir_ = uniform_int(0, 1);
+        if (dir_ == 0) dir_ = -1;
+        if (sys.step(start_d, dir_) < 0) dir_ *= -1;
+        int n_domains = 0, qh = 0, qt = 0, seg_n = 0, n_segs = 0;
+        n_stems = 0;
+        // paired_empty[k] marks stems whose pair of segments was pushed as {[stem], []} (:556-563)
+        // first segment
+        m->seg_start[0] = 0;
+        m->seg_dom[seg_n++] = (short)start_d;
+        m->in_sel[start_d] = 1;
+        n_domains++;
+        m->scaf_dir[0] = (int8_t)dir_;
+        bool max_reached = ct_fill_seg(start_d, max_length, seg_max, dir_, n_domains, qt, seg_n, 1);
+        n_segs = 1;
+        m->seg_start[1] = (short)seg_n;
+        // paired segment bookkeeping: for stem k, its two segments are 1+2k and 2+2k; pair_first[k]
+        // records where the *paired_segs* (without the stem prefix) begin/end for endpoint search.
+        while (!max_reached && qh != qt) {
+            if (s->status != LDO_OK) return n_segs;
+            int stemd_ = m->stem_queue[qh++];
+            if (m->in_sel[stemd_]) continue;
+            bool adjacent = false;
+            for (int td = -1; td <= 1; td += 2) {
+                int nd = sys.step(stemd_, td);
+                if (nd >= 0 && m->in_sel[nd]) {
+                    adjacent = true;
+                    break;
+                }
+            }
+            if (adjacent) continue;
+            if (n_segs + 2 >= SMAX) {
+                sys.fail(LDO_ERR_CAPACITY, 10);
+                return n_segs;
+            }
+            m->in_sel[stemd_] = 1;
+            n_domains++;
+            m->stems[n_stems++] = (short)stemd_;
+            if (n_domains == max_length) {
+                max_reached = true;
+                // segs += [[stem], []], dirs += [1, -1]
+                m->seg_dom[seg_n++] = (short)stemd_;
+                m->seg_start[n_segs + 1] = (short)seg_n;
+                m->seg_start[n_segs + 2] = (short)seg_n;
+                m->scaf_dir[n_segs] = 1;
+                m->scaf_dir[n_segs + 1] = -1;
+                n_segs += 2;
+                break;
+            }
+            int dir1 = uniform_int(0, 1);
+            if (dir1 == 0) dir1 = -1;
+            m->scaf_dir[n_segs] = (int8_t)dir1;
+            m->scaf_dir[n_segs + 1] = (int8_t)(-dir1);
+            bool cur_seg_nonempty = true; // cur_seg = [stem]
+            for (int i = 0; i < 2; i++) {
+                int dsel = i == 0 ? dir1 : -dir1;
+                int smax = uniform_int(0, md.max_seg_regrowth);
+                if (i == 0) max_length++; // sic (movetypes.cpp:592-594)
+                // segment i: optional stem prefix, then the filled domains
+                if (cur_seg_nonempty) m->seg_dom[seg_n++] = (short)stemd_;
+                max_reached = ct_fill_seg(stemd_, max_length, smax, dsel, n_domains, qt, seg_n, 0);
+                m->seg_start[n_segs + i + 1] = (short)seg_n;
+                if (max_reached) {
+                    if (i == 0) m->seg_start[n_segs + 2] = (short)seg_n; // second segment stays empty
+                    break;
+                }
+                cur_seg_nonempty = false;
+            }
+            n_segs += 2;
+        }
+        return n_segs;
+    }
+
+    // ---- CTRG (rg_movetypes.cpp) ----
+    LDO_HDN void eq_push_erased() {
+        // m_erased_endpoints_q.push_back(get_erased_endpoints())
+        if (m->eq_depth >= MoveScratch<K>::A || m->eq_npos + m->n_erased > MoveScratch<K>::E) {
+            sys.fail(LDO_ERR_CAPACITY, 11);
+            return;
+        }
+        m->eq_start[m->eq_depth++] = (short)m->eq_npos;
+        for (int k = 0; k < m->n_erased; k++) {
+            m->eq_pos[m->eq_npos][0] = m->erased_pos[k][0];
+            m->eq_pos[m->eq_npos][1] = m->erased_pos[k][1];
+            m->eq_pos[m->eq_npos][2] = m->erased_pos[k][2];
+            m->eq_npos++;
+        }
+    }
+    // restore_endpoints (rg:288-295)
+    LDO_HDN void rg_restore_endpoints() {
+        cp_remove_activated_endpoint(d);
+        if (m->eq_depth <= 0) {
+            sys.fail(LDO_ERR_INTERNAL, 1);
+            return;
+        }
+        int start = m->eq_start[--m->eq_depth];
+        for (int k = start; k < m->eq_npos; k++) {
+            cp_add_active_endpoint(d, v3(m->eq_pos[k][0], m->eq_pos[k][1], m->eq_pos[k][2]));
+        }
+        m->eq_npos = start;
+    }
+    // unassign_and_save_domains() (rg:67-87)
+    LDO_HDN double rg_unassign_and_save_domains() {
+        double de = 0;
+        m->prev[m->regrow[0]] = sys.s->dom[m->regrow[0]];
+        for (int k = 1; k < m->n_regrow; k++) {
+            int dd = m->regrow[k];
+            m->prev[dd] = sys.s->dom[dd];
+            push_modified(dd);
+            de += sys.unassign_domain(dd);
+        }
+        m->eq_depth = 0;
+        m->eq_npos = 0;
+        return de;
+    }
+    LDO_HD void rg_unassign_domains() {
+        for (int k = 1; k < m->n_regrow; k++) sys.unassign_domain(m->regrow[k]);
+        m->eq_depth = 0;
+        m->eq_npos = 0;
+    }
+    // set_config (rg:233-244)
+    LDO_HDN double rg_set_config(int dd, V3 p, int o) {
+        double de = sys.set_checked_domain_config(dd, p, o);
+        push_assigned(dd);
+        cp_update_endpoints(d);
+        eq_push_erased();
+        return de;
+    }
+    LDO_HD static unsigned long long all_cis() { return (1ull << 36) - 1; }
+    // prepare_for_growth (rg:246-262)
+    LDO_HDN void rg_prepare_for_growth() {
+        di++;
+        d = m->regrow[di];
+        stemd = m->stem_gp[d] >= 0;
+        dir = cp_get_dir(d);
+        c_attempts = 0;
+        if (stemd) {
+            d_max_c_attempts = 1;
+            avail = 0;
+            ref_d = m->stem_gp[d];
+        }
+        else {
+            d_max_c_attempts = max_c_attempts;
+            avail = all_cis();
+            ref_d = sys.step(d, -dir);
+        }
+    }
+    // prepare_for_regrowth (rg:264-286)
+    LDO_HDN double rg_prepare_for_regrowth() {
+        di--;
+        d = m->regrow[di];
+        dir = cp_get_dir(d);
+        double de = sys.unassign_domain(d);
+        if (m->n_assigned > 0) m->n_assigned--;
+        rg_restore_endpoints();
+        stemd = m->stem_gp[d] >= 0;
+        if (stemd) {
+            d_max_c_attempts = 1;
+            c_attempts = 1;
+            avail = 0;
+            ref_d = m->stem_gp[d];
+        }
+        else {
+            d_max_c_attempts = max_c_attempts;
+            c_attempts = m->c_attempts_q[di];
+            avail = m->avail_q[di];
+            ref_d = sys.step(d, -dir);
+        }
+        return de;
+    }
+    // select_trial_config (rg:297-313): k-th remaining entry of the ordered list
+    LDO_HDN void rg_select_trial_config(V3& p, int& o) {
+        if (stemd) {
+            const DomRec& r = sys.s->dom[ref_d];
+            p = rec_pos(r);
+            o = r.ore < 6 ? (r.ore ^ 1) : r.ore;
+            return;
+        }
+        int n_avail = 0;
+        for (unsigned long long t = avail; t; t &= t - 1) n_avail++;
+        int ci = uniform_int(0, n_avail - 1);
+        unsigned long long t = avail;
+        for (int k = 0; k < ci; k++) t &= t - 1;
+        int i = 0;
+        while (!((t >> i) & 1ull) && i < 36) i++;
+        avail &= ~(1ull << i);
+        // m_all_configs = all_pairs(vectors): position-major, orientation-minor (utility.hpp:167-177)
+        p = ore_vec(i / 6) + rec_pos(sys.s->dom[ref_d]);
+        o = i % 6;
+    }
+    // calc_p_config_open (rg:315-343)
+    LDO_HDN double rg_calc_p_config_open(V3 p, int o) {
+        double de = sys.check_domain_constraints(d, p, o);
+        if (sys.s->constraints_violated) {
+            sys.s->constraints_violated = 0;
+            return 0;
+        }
+        if (!cp_walks_remain(d, p)) return 0;
+        int j = sys.occupant(p);
+        if (j >= 0 && sys.s->dom[j].state == ST_UNBOUND) {
+            bool same_chain = sys.chain(j) == sys.chain(d);
+            bool endpoint = cp_endpoint_reached(d, p);
+            if (!(same_chain || endpoint || stemd)) return 0;
+        }
+        return fmin(1.0, exp(-de));
+    }
+    // test_config_open (rg:345-361)
+    LDO_HD bool rg_test_config_open(double p) {
+        p = fmin(1.0, p);
+        if (p == 1) return true;
+        return p > uniform_real();
+    }
+    // recoil_regrow (rg:177-231)
+    LDO_HDN double rg_recoil_regrow() {
+        double de = 0;
+        di = 0;
+        d = m->regrow[0];
+        dir = cp_get_dir(d);
+        m->c_opens[0] = 1;
+        rg_prepare_for_growth();
+        int recoils = 0;
+        for (;;) {
+            if (sys.s->status != LDO_OK) {
+                m->rejected = 1;
+                break;
+            }
+            V3 p = v3(0, 0, 0);
+            int o = 0;
+            double p_c_open = 0;
+            bool c_open = false;
+            while (!c_open && c_attempts != d_max_c_attempts) {
+                c_attempts++;
+                rg_select_trial_config(p, o);
+                p_c_open = rg_calc_p_config_open(p, o);
+                c_open = rg_test_config_open(p_c_open);
+            }
+            if (c_open) {
+                if (recoils != 0) recoils--;
+                de += rg_set_config(d, p, o);
+                m->c_attempts_q[di] = (uint8_t)c_attempts;
+                m->avail_q[di] = avail;
+                m->c_opens[di] = p_c_open;
+                if (di == m->n_regrow - 1) break;
+                rg_prepare_for_growth();
+            }
+            else {
+                if (recoils == max_recoils || di == 1) {
+                    m->rejected = 1;
+                    break;
+                }
+                recoils++;
+                de += rg_prepare_for_regrowth();
+            }
+        }
+        return de;
+    }
+    // test_config_avail (rg:422-480)
+    LDO_HDN bool rg_test_config_avail() {
+        int feels = 0;
+        if (feels == max_recoils || di == m->n_regrow - 1) return true;
+        rg_prepare_for_growth();
+        bool c_avail = false;
+        for (;;) {
+            if (sys.s->status != LDO_OK) break;
+            V3 p = v3(0, 0, 0);
+            int o = 0;
+            bool c_open = false;
+            double p_c_open;
+            while (!c_open && c_attempts != d_max_c_attempts) {
+                c_attempts++;
+                rg_select_trial_config(p, o);
+                p_c_open = rg_calc_p_config_open(p, o);
+                c_open = rg_test_config_open(p_c_open);
+            }
+            if (c_open) {
+                feels++;
+                if (feels == max_recoils || di == m->n_regrow - 1) {
+                    feels--;
+                    c_avail = true;
+                    break;
+                }
+                rg_set_config(d, p, o);
+                m->c_attempts_q[di] = (uint8_t)c_attempts;
+                m->avail_q[di] = avail;
+                rg_prepare_for_growth();
+            }
+            else {
+                if (feels == 0) {
+                    c_avail = false;
+                    break;
+                }
+                feels--;
+                rg_prepare_for_regrowth();
+            }
+        }
+        while (feels != 0) {
+            di--;
+            feels--;
+            d = m->regrow[di];
+            sys.unassign_domain(d);
+            rg_restore_endpoints();
+        }
+        di--;
+        d = m->regrow[di];
+        return c_avail;
+    }
+    // calc_weights (rg:363-417)
+    LDO_HDN void rg_calc_weights() {
+        di = 0;
+        d = m->regrow[0];
+        while (di != m->n_regrow - 1) {
+            if (sys.s->status != LDO_OK) return;
+            di++;
+            d = m->regrow[di];
+            stemd = m->stem_gp[d] >= 0;
+            dir = cp_get_dir(d);
+            int avail_cs = 1;
+            if (!stemd) {
+                ref_d = sys.step(d, -dir);
+                int catt = m->c_attempts_wq[di];
+                avail = m->avail_wq[di];
+                while (catt != max_c_attempts) {
+                    catt++;
+                    V3 p;
+                    int o;
+                    rg_select_trial_config(p, o);
+                    double p_c_open = rg_calc_p_config_open(p, o);
+                    if (rg_test_config_open(p_c_open)) {
+                        sys.set_checked_domain_config(d, p, o);
+                        cp_update_endpoints(d);
+                        eq_push_erased();
+                        int dir_s = dir, ref_s = ref_d, stem_s = stemd;
+                        unsigned long long avail_s = avail;
+                        avail_cs += rg_test_config_avail() ? 1 : 0;
+                        avail = avail_s;
+                        stemd = stem_s;
+                        ref_d = ref_s;
+                        dir = dir_s;
+                        sys.unassign_domain(d);
+                        rg_restore_endpoints();
+                    }
+                }
+            }
+            weight *= avail_cs / m->c_opens[di - 1];
+            const DomRec& r = m->prev[d];
+            sys.set_checked_domain_config(d, rec_pos(r), r.ore);
+            cp_update_endpoints(d);
+            eq_push_erased();
+        }
+        weight /= m->c_opens[di];
+    }
+    // calc_old_c_opens (rg:482-513)
+    LDO_HDN void rg_calc_old_c_opens() {
+        di = 0;
+        m->c_opens[0] = 1;
+        while (di != m->n_regrow - 1) {
+            di++;
+            d = m->regrow[di];
+            m->c_attempts_q[di] = 1;
+            const DomRec r = m->oldc[d];
+            V3 p = rec_pos(r);
+            stemd = m->stem_gp[d] >= 0;
+            m->c_opens[di] = rg_calc_p_config_open(p, r.ore);
+            rg_set_config(d, p, r.ore);
+            if (stemd) {
+                m->avail_q[di] = 0;
+            }
+            else {
+                dir = cp_get_dir(d);
+                ref_d = sys.step(d, -dir);
+                V3 rel = p - rec_pos(m->oldc[ref_d]);
+                int pc = ore_code(rel);
+                int ci = pc * 6 + r.ore;
+                unsigned long long a = all_cis();
+                if (pc < 6 && r.ore >= 0 && r.ore < 6) a &= ~(1ull << ci);
+                else sys.fail(LDO_ERR_INTERNAL, 2); // m_config_to_i.at(c) would throw
+                m->avail_q[di] = a;
+            }
+        }
+    }
+    LDO_HD void rg_copy_queues_to_wq() {
+        for (int k = 0; k < m->n_regrow; k++) {
+            m->c_attempts_wq[k] = m->c_attempts_q[k];
+            m->avail_wq[k] = m->avail_q[k];
+        }
+    }
+
+    // Shared tail of the two CTRG scaffold moves (rg:636-689, 810-851). `whole_cyclic`: the
+    // endpoint-removal guards evaluated by the caller (App. A2 keeps the contiguous variant's quirk).
+    LDO_HDN bool rg_regrow_and_test(bool remove_first_a, bool remove_first_b, int first_dom) {
+        delta_e += rg_unassign_and_save_domains();
+        delta_e += rg_recoil_regrow();
+        if (m->rejected) return false;
+        // excluded staples: the reference hard-codes zero of them (simulation.cpp:410,527)
+        update_move_params();
+        delta_e += calc_move_bias();
+
+        // new-configuration weights (setup_for_calc_new_weights, rg:147-153)
+        rg_copy_queues_to_wq();
+        for (int k = 0; k < m->n_regrow; k++) m->oldc[m->regrow[k]] = m->prev[m->regrow[k]];
+        m->n_modified = 0;
+        rg_unassign_and_save_domains();
+        cp_reset_active_endpoints();
+        if (remove_first_a) cp_remove_active_endpoint(first_dom);
+        rg_calc_weights();
+
+        // old-configuration weights
+        rg_unassign_domains();
+        cp_reset_active_endpoints();
+        if (remove_first_b) cp_remove_active_endpoint(first_dom);
+        rg_calc_old_c_opens();
+        // setup_for_calc_old_weights (rg:155-163)
+        weight_new = weight;
+        weight = 1;
+        rg_copy_queues_to_wq();
+        for (int k = 0; k < m->n_regrow; k++) m->newc[m->regrow[k]] = m->prev[m->regrow[k]];
+        m->n_modified = 0;
+        rg_unassign_and_save_domains();
+        cp_reset_active_endpoints();
+        if (remove_first_a) cp_remove_active_endpoint(first_dom);
+        rg_calc_weights();
+
+        // test_rg_acceptance (rg:515-533)
+        double ratio = weight_new / weight * exp(-delta_e);
+        if (test_acceptance(ratio)) {
+            for (int k = 0; k < m->n_regrow; k++) m->prev[m->regrow[k]] = m->newc[m->regrow[k]];
+            reset_origami();
+            return true;
+        }
+        m->n_modified = 0;
+        m->n_assigned = 0;
+        return false;
+    }
+
+    LDO_HD void rg_reset(const MoveDef& md) {
+        cp_reset();
+        delta_e = 0;
+        weight = 1;
+        weight_new = 1;
+        max_recoils = md.max_num_recoils;
+        max_c_attempts = md.max_c_attempts;
+        m->eq_depth = 0;
+        m->eq_npos = 0;
+    }
+
+    // CTRGScaffoldRegrowthMCMovetype::internal_attempt_move (rg:629-689)
+    LDO_HDN bool move_ctrg_scaffold(const MoveDef& md) {
+        rg_reset(md);
+        ct_select_indices(md);
+        if (sys.s->status != LDO_OK) return false;
+        // setup_constraints (rg:134-145)
+        for (int k = 0; k < m->n_sel; k++) m->in_sel[m->sel_scaf[k]] = 1;
+        m->scaf_dir[0] = (int8_t)dir;
+        cp_find_growthpoints_endpoints(m->sel_scaf, m->n_sel, 0);
+        cp_save_initial();
+        int n_scaf = sys.s->chain_len[0];
+        bool cyc = sys.sc->cyclic != 0;
+        if (!(cyc && m->n_sel == n_scaf)) cp_remove_active_endpoint(m->sel_scaf[0]);
+        bool guard_a = !(cyc && m->n_regrow == n_scaf);
+        bool guard_b = !cyc && m->n_regrow == n_scaf; // sic (rg:671, App. A2)
+        return rg_regrow_and_test(guard_a, guard_b, m->regrow[0]);
+    }
+
+    // CTRGJumpScaffoldRegrowthMCMovetype::internal_attempt_move (rg:791-851)
+    LDO_HDN bool move_ctrg_jump_scaffold(const MoveDef& md) {
+        SysState<K>* s = sys.s;
+        rg_reset(md);
+        int n_stems = 0;
+        int n_segs = ct_select_noncontig_segs(md, n_stems);
+        if (s->status != LDO_OK) return false;
+        // endpoints registered by select_noncontig_segs (movetypes.cpp:618-647)
+        {
+            int last = m->seg_dom[m->seg_start[1] - 1];
+            int nd = sys.step(last, m->scaf_dir[0]);
+            if (nd >= 0) cp_add_active_endpoint_seg(nd, rec_pos(s->dom[nd]), 0);
+        }
+        for (int k = 0; k < n_stems; k++) {
+            int stem = m->stems[k];
+            int gp = s->bound[stem];
+            m->gp_stem[gp] = (short)stem;
+            m->stem_gp[stem] = (short)gp;
+            int seg_i = 1 + 2 * k;
+            m->stem_seg0[stem] = (int8_t)seg_i;
+            for (int q = 0; q < 2; q++) {
+                int sg = seg_i + q;
+                int a = m->seg_start[sg], b = m->seg_start[sg + 1];
+                // paired_segs hold the filled domains only (no stem prefix)
+                int last = stem;
+                if (b > a && !(b - a == 1 && m->seg_dom[a] == stem)) last = m->seg_dom[b - 1];
+                int nd = sys.step(last, m->scaf_dir[sg]);
+                if (nd >= 0) cp_add_active_endpoint_seg(nd, rec_pos(s->dom[nd]), sg);
+            }
+        }
+        // calculate_constraintpoints(segs, dirs, excluded) (top_constraint_points.cpp:223-248)
+        for (int sg = 0; sg < n_segs; sg++) {
+            int a = m->seg_start[sg], b = m->seg_start[sg + 1];
+            if (b > a) cp_find_growthpoints_endpoints(m->seg_dom + a, b - a, sg);
+        }
+        cp_save_initial();
+        int first = m->seg_dom[0];
+        cp_remove_active_endpoint(first);
+        for (int k = 0; k < n_stems; k++) {
+            int stem = m->stems[k];
+            int gp = s->bound[stem];
+            m->gp_stem[gp] = (short)stem;
+            m->stem_gp[stem] = (short)gp;
+        }
+        return rg_regrow_and_test(true, true, first);
+    }
+
+    // ---- one Monte Carlo step (simulation.cpp:568-596, 655-665) ----
+    LDO_HD int select_movetype() {
+        double prob = uniform_real();
+        int i;
+        for (i = 0; i < ms->n; i++) {
+            if (prob < ms->mt[i].cum_prob) break;
+        }
+        if (i >= ms->n) i = ms->n - 1; // reference reads out of bounds here; freqs sum to 1
+        return i;
+    }
+    LDO_HD bool attempt(int i) {
+        const MoveDef& md = ms->mt[i];
+        reset_internal();
+        stats->attempts[i]++;
+        bool accepted = false;
+        switch (md.type) {
+        case MT_ORIENTATION_ROTATION: accepted = move_orientation_rotation(); break;
+        case MT_MET_STAPLE_EXCHANGE: accepted = move_staple_exchange(md); break;
+        case MT_MET_STAPLE_REGROWTH: accepted = move_met_staple_regrowth(); break;
+        case MT_CB_STAPLE_REGROWTH: accepted = move_cb_staple_regrowth(); break;
+        case MT_CTRG_SCAFFOLD_REGROWTH: accepted = move_ctrg_scaffold(md); break;
+        case MT_CTRG_JUMP_SCAFFOLD_REGROWTH: accepted = move_ctrg_jump_scaffold(md); break;
+        default: sys.fail(LDO_ERR_INTERNAL, 100 + md.type); break;
+        }
+        if (sys.s->status != LDO_OK) return false;
+        stats->accepts[i] += accepted ? 1 : 0;
+        return accepted;
+    }
+    LDO_HD bool mc_step() {
+        int i = select_movetype();
+        bool accepted = attempt(i);
+        if (sys.s->status != LDO_OK) return false;
+        if (!accepted) {
+            reset_origami();
+            update_move_params();
+            calc_move_bias();
+        }
+        return accepted;
+    }
+};
+
+} // namespace ldo

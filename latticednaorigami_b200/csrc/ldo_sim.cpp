@@ -1,0 +1,674 @@
+// ldo_sim.cpp — simulation drivers on top of one ldo_engine: the host-side equivalents of
+// ConstantTGCMCSimulation::run, AnnealingGCMCSimulation::run and PTGCMCSimulation::run, with the
+// reference's text output files. See include/ldo_host.h for the reference file:line of each piece.
+
+#include <chrono>
+#include <cmath>
+#include <cstring>
+#include <fstream>
+#include <iomanip>
+#include <iostream>
+#include <memory>
+#include <random>
+#include <sstream>
+
+#include "../../include/ldo_host.h"
+#include "ldo_host.hpp"
+
+using namespace ldohost;
+
+namespace {
+thread_local std::string g_host_error;
+
+struct ReplicaFiles {
+    std::unique_ptr<std::ofstream> trj, counts, staples, staplestates, times, ene, ops;
+};
+} // namespace
+
+struct ldo_sim {
+    InputParameters params;
+    std::unique_ptr<OrigamiInputFile> sysfile;
+    std::vector<EnergyTables> tables;
+    std::vector<double> temps;
+    std::vector<MovetypeSpec> movetypes;
+    std::vector<OrderParamSpec> ops;
+    std::vector<BiasSpec> biases;
+    ldo_engine* eng {nullptr};
+    int R {0};
+    int global_first {0};
+    int n_global {0};
+    long long step {0};
+    bool is_pt {false};
+    int pt_variant {LDO_PT_T};
+    int num_reps {1};
+    int n_ladders {1};
+    std::vector<int> q2r;
+    std::vector<long long> attempts, accepts;
+    std::vector<ReplicaFiles> files;
+    std::vector<int> ops_out_idx;
+    std::chrono::steady_clock::time_point start;
+
+    ~ldo_sim() {
+        if (eng) ldo_engine_destroy(eng);
+    }
+    void check(int rc) {
+        if (rc != 0) throw std::runtime_error(std::string("engine: ") + ldo_last_error(eng));
+    }
+};
+
+namespace {
+
+int domain_type_code(std::string const& t) {
+    if (t == "HalfTurn") return LDO_DOMAIN_HALFTURN;
+    if (t == "ThreeQuarterTurn") return LDO_DOMAIN_THREEQUARTERTURN;
+    throw NotImplemented {t + ": No such domain type"}; // origami_system.cpp:423-425
+}
+
+int op_type_code(std::string const& t) {
+    if (t == "NumStaples") return LDO_OP_NUM_STAPLES;
+    if (t == "NumStaplesType") return LDO_OP_NUM_STAPLES_TYPE;
+    if (t == "StapleTypeFullyBound") return LDO_OP_STAPLE_TYPE_FULLY_BOUND;
+    if (t == "NumBoundDomainPairs") return LDO_OP_NUM_BOUND_DOMAIN_PAIRS;
+    if (t == "NumMisboundDomainPairs") return LDO_OP_NUM_MISBOUND_DOMAIN_PAIRS;
+    if (t == "NumStackedPairs") return LDO_OP_NUM_STACKED_PAIRS;
+    if (t == "NumLinearHelices") return LDO_OP_NUM_LINEAR_HELICES;
+    if (t == "NumStackedJuncts") return LDO_OP_NUM_STACKED_JUNCTS;
+    if (t == "Sum") return LDO_OP_SUM;
+    throw SimulationMisuse {t + ": order parameter type does not exist"}; // order_params.cpp:546-549
+}
+
+int bias_type_code(std::string const& t) {
+    if (t == "LinearStepWell") return LDO_BIAS_LINEAR_STEP_WELL;
+    if (t == "SquareWell") return LDO_BIAS_SQUARE_WELL;
+    return LDO_BIAS_GRID;
+}
+
+std::string replica_filebase(ldo_sim& s, int r) {
+    // PTGCMCSimulation appends "-<rank>" (ptmc_simulation.cpp:48); batches of independent replicas do the same
+    if (s.n_global == 1) return s.params.m_output_filebase;
+    return s.params.m_output_filebase + "-" + std::to_string(s.global_first + r);
+}
+
+void open_output_files(ldo_sim& s) {
+    InputParameters const& p = s.params;
+    if (p.m_output_filebase.empty()) return;
+    s.files.resize(s.R);
+    int n_scaf = static_cast<int>(s.sysfile->identities[0].size());
+    int max_domains = n_scaf + p.m_max_total_staples * p.m_max_staple_size;
+    for (int r {0}; r != s.R; r++) {
+        std::string base {replica_filebase(s, r)};
+        {
+            // OrigamiVSFOutputFile (files.cpp:519-527), always written (simulation.cpp:56-62)
+            std::ofstream vsf {base + ".vsf"};
+            if (!vsf) throw FileError {"Cannot open output file " + base + ".vsf"};
+            vsf << "atom 0:" << n_scaf << " radius 0.25 type scaffold\n";
+            vsf << "atom " << n_scaf << ":" << max_domains - 1 << " radius 0.25 type staple";
+        }
+        ReplicaFiles& f = s.files[r];
+        if (p.m_configs_output_freq != 0) f.trj.reset(new std::ofstream {base + ".trj"});
+        if (p.m_counts_output_freq != 0) {
+            f.counts.reset(new std::ofstream {base + ".counts"});
+            f.staples.reset(new std::ofstream {base + ".staples"});
+            f.staplestates.reset(new std::ofstream {base + ".staplestates"});
+        }
+        if (p.m_times_output_freq != 0) {
+            f.times.reset(new std::ofstream {base + ".times"});
+            *f.times << "step time\n";
+        }
+        if (p.m_energies_output_freq != 0) {
+            f.ene.reset(new std::ofstream {base + ".ene"});
+            *f.ene << "step tenergy henthalpy hentropy stacking bias\n";
+            f.ene->precision(10);
+        }
+        if (p.m_order_params_output_freq != 0) {
+            f.ops.reset(new std::ofstream {base + ".ops"});
+            for (auto const& tag: p.m_ops_to_output) *f.ops << tag << ", "; // header quirk (App. A14)
+            *f.ops << "\n";
+        }
+    }
+    s.ops_out_idx.clear();
+    for (auto const& tag: p.m_ops_to_output) {
+        int found {-1};
+        for (size_t i {0}; i != s.ops.size(); i++)
+            if (s.ops[i].tag == tag) found = static_cast<int>(i);
+        if (found < 0) throw SimulationMisuse {"ops_to_output: unknown order parameter " + tag};
+        s.ops_out_idx.push_back(found);
+    }
+}
+
+bool due(int freq, long long step) { return freq != 0 && step % freq == 0; }
+
+// Output at `step` for every replica (simulation.cpp:641-646 and the writers of files.cpp:529-778)
+void write_outputs(ldo_sim& s, long long step) {
+    InputParameters const& p = s.params;
+    if (s.files.empty()) return;
+    bool w_trj {due(p.m_configs_output_freq, step)}, w_counts {due(p.m_counts_output_freq, step)};
+    bool w_times {due(p.m_times_output_freq, step)}, w_ene {due(p.m_energies_output_freq, step)};
+    bool w_ops {due(p.m_order_params_output_freq, step)};
+    if (!(w_trj || w_counts || w_times || w_ene || w_ops)) return;
+    int nst {static_cast<int>(s.sysfile->identities.size()) - 1};
+    std::vector<double> ene;
+    std::vector<int> counters, staple_counts, opv;
+    if (w_ene) {
+        ene.resize(5 * static_cast<size_t>(s.R));
+        s.check(ldo_get_energies(s.eng, ene.data()));
+    }
+    if (w_counts) {
+        counters.resize(9 * static_cast<size_t>(s.R));
+        staple_counts.resize(static_cast<size_t>(std::max(nst, 1)) * s.R);
+        s.check(ldo_get_counters(s.eng, counters.data()));
+        s.check(ldo_get_staple_counts(s.eng, staple_counts.data()));
+    }
+    if (w_ops && !s.ops.empty()) {
+        opv.resize(s.ops.size() * s.R);
+        s.check(ldo_get_order_params(s.eng, opv.data()));
+    }
+    double dt {std::chrono::duration<double>(std::chrono::steady_clock::now() - s.start).count()};
+    int max_c, max_d;
+    ldo_state_capacity(s.eng, &max_c, &max_d);
+    std::vector<int> ci(max_c), cid(max_c), cl(max_c), pos(3 * max_d), ore(3 * max_d), st(max_d), bd(2 * max_d);
+    for (int r {0}; r != s.R; r++) {
+        ReplicaFiles& f = s.files[r];
+        bool need_state {(w_trj && f.trj) || (w_counts && f.staplestates)};
+        int nc {0};
+        if (need_state) s.check(ldo_get_state(s.eng, r, &nc, ci.data(), cid.data(), cl.data(), pos.data(), ore.data(), st.data(), bd.data()));
+        if (w_trj && f.trj) {
+            // OrigamiTrajOutputFile::write (files.cpp:529-548)
+            std::ofstream& o = *f.trj;
+            o << step << "\n";
+            int k {0};
+            for (int c {0}; c != nc; c++) {
+                o << ci[c] << " " << cid[c] << "\n";
+                for (int d {0}; d != cl[c]; d++)
+                    for (int a {0}; a != 3; a++) o << pos[3 * (k + d) + a] << " ";
+                o << "\n";
+                for (int d {0}; d != cl[c]; d++)
+                    for (int a {0}; a != 3; a++) o << ore[3 * (k + d) + a] << " ";
+                o << "\n";
+                k += cl[c];
+            }
+            o << "\n";
+            o.flush();
+        }
+        if (w_counts && f.counts) {
+            int const* c = &counters[9 * static_cast<size_t>(r)];
+            int unique {0};
+            for (int t {0}; t != nst; t++)
+                if (staple_counts[static_cast<size_t>(r) * nst + t] > 0) unique++;
+            *f.counts << step << " " << c[0] << " " << unique << " " << c[2] << " " << c[3] << " " << c[5] << " \n";
+            f.counts->flush();
+            *f.staples << step << " ";
+            for (int t {0}; t != nst; t++) *f.staples << staple_counts[static_cast<size_t>(r) * nst + t] << " ";
+            *f.staples << "\n";
+            f.staples->flush();
+            // OrigamiStaplesFullyBoundOutputFile::write (files.cpp:667-690)
+            std::vector<int> full(nst, 0);
+            int k {0};
+            for (int c {0}; c != nc; c++) {
+                if (c > 0) {
+                    bool all_bound {true};
+                    for (int d {0}; d != cl[c]; d++)
+                        if (st[k + d] != 2) all_bound = false;
+                    if (all_bound) full[cid[c] - 1] = 1;
+                }
+                k += cl[c];
+            }
+            *f.staplestates << step << " ";
+            for (int t {0}; t != nst; t++) *f.staplestates << full[t] << " ";
+            *f.staplestates << "\n";
+            f.staplestates->flush();
+        }
+        if (w_times && f.times) {
+            *f.times << step << " " << dt << "\n";
+            f.times->flush();
+        }
+        if (w_ene && f.ene) {
+            double const* e = &ene[5 * static_cast<size_t>(r)];
+            *f.ene << step << " " << e[0] << " " << e[1] << " " << e[2] << " " << e[3] << " " << e[4] << " \n";
+            f.ene->flush();
+        }
+        if (w_ops && f.ops) {
+            *f.ops << step;
+            for (int idx: s.ops_out_idx) *f.ops << " " << opv[static_cast<size_t>(r) * s.ops.size() + idx];
+            *f.ops << "\n";
+            f.ops->flush();
+        }
+    }
+}
+
+long long next_output_step(ldo_sim& s, long long cur, long long end) {
+    InputParameters const& p = s.params;
+    if (s.files.empty()) return end;
+    long long next {end};
+    int freqs[] {p.m_configs_output_freq, p.m_counts_output_freq, p.m_times_output_freq, p.m_energies_output_freq, p.m_order_params_output_freq};
+    for (int f: freqs) {
+        if (f == 0) continue;
+        long long n {(cur / f + 1) * f};
+        if (n < next) next = n;
+    }
+    return next;
+}
+
+// GCMCSimulation::simulate (simulation.cpp:568-653) for every replica; returns false when max_duration hit
+bool simulate(ldo_sim& s, long long steps) {
+    InputParameters const& p = s.params;
+    long long end {s.step + steps};
+    while (s.step < end) {
+        long long stop {next_output_step(s, s.step, end)};
+        // chunks are bounded so that the wall-clock limit is honoured with useful granularity
+        long long chunk {std::min<long long>(stop - s.step, 100000)};
+        s.check(ldo_run(s.eng, chunk, p.m_centering_freq, p.m_centering_domain, p.m_constraint_check_freq));
+        s.step += chunk;
+        std::vector<int> status(s.R), detail(s.R);
+        s.check(ldo_get_status(s.eng, status.data(), detail.data()));
+        for (int r {0}; r != s.R; r++) {
+            if (status[r] != 0) {
+                throw OrigamiMisuse {
+                        "replica " + std::to_string(s.global_first + r) + " stopped with status " +
+                        std::to_string(status[r]) + " (detail " + std::to_string(detail[r]) + ")"};
+            }
+        }
+        write_outputs(s, s.step);
+        double dt {std::chrono::duration<double>(std::chrono::steady_clock::now() - s.start).count()};
+        if (dt > p.m_max_duration) {
+            std::cout << "Maximum time allowed reached" << std::endl;
+            return false;
+        }
+    }
+    return true;
+}
+
+// write_log_summary (simulation.cpp:706-718, movetypes.cpp:87-96)
+void write_move_summary(ldo_sim& s) {
+    if (s.params.m_output_filebase.empty()) return;
+    size_t n {s.movetypes.size()};
+    std::vector<long long> att(n * s.R), acc(n * s.R);
+    s.check(ldo_get_move_stats(s.eng, att.data(), acc.data()));
+    for (int r {0}; r != s.R; r++) {
+        std::ofstream o {replica_filebase(s, r) + ".moves"};
+        for (size_t i {0}; i != n; i++) {
+            long long a {att[static_cast<size_t>(r) * n + i]}, c {acc[static_cast<size_t>(r) * n + i]};
+            o << "Movetype: " << s.movetypes[i].label << "\n";
+            o << "    Attempts: " << a << "\n";
+            o << "    Accepts: " << c << "\n";
+            o << "    Frequency: " << static_cast<double>(c) / a << "\n";
+        }
+    }
+}
+
+void set_all_control(ldo_sim& s, int temp_idx) {
+    std::vector<int> ti(s.R, temp_idx);
+    s.check(ldo_set_control(s.eng, 0, s.R, ti.data(), nullptr, nullptr, nullptr));
+}
+
+} // namespace
+
+extern "C" {
+
+const char* ldo_host_last_error(void) { return g_host_error.c_str(); }
+
+ldo_sim* ldo_sim_create(const char* inp_path, int n_replicas, int device, int global_first, int n_global) {
+    std::unique_ptr<ldo_sim> s {new ldo_sim {}};
+    try {
+        s->params = InputParameters {inp_path};
+        InputParameters& p = s->params;
+        s->sysfile.reset(new OrigamiInputFile {p.m_origami_input_filename});
+        OrigamiInputFile& sf = *s->sysfile;
+        s->R = n_replicas;
+        s->global_first = global_first;
+        s->n_global = n_global > 0 ? n_global : n_replicas;
+
+        // potentials (origami_potential.cpp:952-1013)
+        if (p.m_binding_pot != "FourBody") throw NotImplemented {p.m_binding_pot + ": No such binding potential"};
+        int misbind;
+        if (p.m_misbinding_pot == "Opposing") misbind = LDO_MISBIND_OPPOSING;
+        else if (p.m_misbinding_pot == "Disallowed") misbind = LDO_MISBIND_DISALLOWED;
+        else throw NotImplemented {p.m_misbinding_pot + ": No such misbinding potential"};
+        if (p.m_stacking_pot == "SequenceSpecific") {
+            throw NotImplemented {"SequenceSpecific stacking is not available on the device path (unfinished in the reference)"};
+        }
+        if (p.m_stacking_pot != "Constant") throw NotImplemented {p.m_stacking_pot + ": No such stacking potential"};
+        if (p.m_domain_update_biases_present) {
+            throw NotImplemented {"domain_update_biases_present: per-domain biases are not available on the device path yet"};
+        }
+        int domain_type {domain_type_code(p.m_domain_type)};
+
+        // temperatures
+        std::string const& st = p.m_simulation_type;
+        if (st == "constant_temp" || st == "umbrella_sampling" || st == "mw_umbrella_sampling") {
+            s->temps = {p.m_temp};
+        }
+        else if (st == "annealing") {
+            for (double t {p.m_max_temp}; t >= p.m_min_temp; t -= p.m_temp_interval) s->temps.push_back(t);
+            if (s->temps.empty()) throw SimulationMisuse {"annealing: empty temperature range"};
+        }
+        else if (st == "t_parallel_tempering" || st == "ut_parallel_tempering" || st == "hut_parallel_tempering" || st == "st_parallel_tempering") {
+            s->is_pt = true;
+            s->pt_variant = st == "t_parallel_tempering" ? LDO_PT_T : st == "ut_parallel_tempering" ? LDO_PT_UT : st == "hut_parallel_tempering" ? LDO_PT_HUT : LDO_PT_ST;
+            s->num_reps = p.m_num_reps;
+            if (static_cast<int>(p.m_temps.size()) != s->num_reps) throw SimulationMisuse {"temps must list num_reps values"};
+            if (s->n_global % s->num_reps != 0) throw SimulationMisuse {"replica count must be a multiple of num_reps"};
+            if (global_first % s->num_reps != 0 || n_replicas % s->num_reps != 0) {
+                // ladders may also be split across GPUs, but then global_first must still address whole slots
+            }
+            s->n_ladders = s->n_global / s->num_reps;
+            s->temps = p.m_temps;
+        }
+        else {
+            throw NotImplemented {st + ": simulation type not available on the device path"};
+        }
+        for (double t: s->temps) s->tables.push_back(calc_energy_tables(sf, p, t));
+
+        // engine
+        std::vector<int> type_len, idents;
+        for (auto const& chain: sf.identities) {
+            type_len.push_back(static_cast<int>(chain.size()));
+            for (int id: chain) idents.push_back(id);
+        }
+        ldo_system_desc d {};
+        d.n_types = static_cast<int>(sf.identities.size());
+        d.type_len = type_len.data();
+        d.idents = idents.data();
+        d.cyclic = sf.cyclic ? 1 : 0;
+        d.domain_type = domain_type;
+        d.misbinding_pot = misbind;
+        d.apply_mean_field_cor = p.m_apply_mean_field_cor ? 1 : 0;
+        d.max_total_staples = std::max(p.m_max_total_staples, static_cast<int>(sf.chains.size()) - 1);
+        // capacity follows the limits the moves can reach, clamped by what a scaffold can ever hold
+        int hard_cap {0};
+        for (size_t t {1}; t < sf.identities.size(); t++) hard_cap += p.m_max_type_staples;
+        if (d.max_total_staples > hard_cap && hard_cap >= static_cast<int>(sf.chains.size()) - 1) d.max_total_staples = hard_cap;
+        d.max_type_staples = p.m_max_type_staples;
+        d.max_staple_size = p.m_max_staple_size;
+        d.staple_M = p.m_staple_M;
+        d.stacking_ene = p.m_stacking_ene;
+        if (ldo_engine_create(&d, n_replicas, device, &s->eng) != 0) {
+            throw std::runtime_error(std::string("engine: ") + ldo_last_error(nullptr));
+        }
+        // the move rules use the reference's limits, not the capacity clamp
+        // (insertion refuses at num_staples == max_total_staples, met_movetypes.cpp:311-318)
+
+        // tables
+        int n_ident {s->tables[0].n_ident};
+        size_t tsz {s->tables[0].hyb_energy.size()};
+        std::vector<double> e, h, en, init;
+        for (auto const& t: s->tables) {
+            e.insert(e.end(), t.hyb_energy.begin(), t.hyb_energy.end());
+            h.insert(h.end(), t.hyb_enthalpy.begin(), t.hyb_enthalpy.end());
+            en.insert(en.end(), t.hyb_entropy.begin(), t.hyb_entropy.end());
+            init.push_back(t.init_energy);
+            init.push_back(t.init_enthalpy);
+            init.push_back(t.init_entropy);
+        }
+        (void)tsz;
+        s->check(ldo_set_temperature_tables(s->eng, static_cast<int>(s->temps.size()), n_ident, s->temps.data(), e.data(), h.data(), en.data(), init.data()));
+
+        // moveset
+        if (!p.m_movetype_filename.empty()) {
+            s->movetypes = read_movetype_file(p.m_movetype_filename);
+            std::vector<ldo_movetype_desc> md;
+            for (auto const& m: s->movetypes) md.push_back(m.desc);
+            s->check(ldo_set_moveset(s->eng, static_cast<int>(md.size()), md.data(), p.m_allow_nonsensical_ps ? 1 : 0));
+        }
+
+        // order parameters and biases
+        if (!p.m_ops_filename.empty()) {
+            s->ops = read_order_params_file(p.m_ops_filename);
+            std::vector<ldo_order_param_desc> od(s->ops.size());
+            for (size_t i {0}; i != s->ops.size(); i++) {
+                od[i].type = op_type_code(s->ops[i].type);
+                od[i].staple = s->ops[i].staple;
+                od[i].n_sum = static_cast<int>(s->ops[i].sum_ops.size());
+                od[i].sum_ops = s->ops[i].sum_ops.data();
+            }
+            s->check(ldo_set_order_params(s->eng, static_cast<int>(od.size()), od.data()));
+        }
+        if (!p.m_bias_funcs_filename.empty()) {
+            s->biases = read_bias_functions_file(p.m_bias_funcs_filename, s->ops);
+            std::vector<ldo_bias_desc> bd(s->biases.size());
+            for (size_t i {0}; i != s->biases.size(); i++) {
+                BiasSpec const& b = s->biases[i];
+                bd[i].type = bias_type_code(b.type);
+                bd[i].n_ops = static_cast<int>(b.ops.size());
+                bd[i].ops = b.ops.data();
+                bd[i].min_op = b.min_op;
+                bd[i].max_op = b.max_op;
+                bd[i].well_bias = b.well_bias;
+                bd[i].min_bias = b.min_bias;
+                bd[i].slope = b.slope;
+                bd[i].outside_bias = b.outside_bias;
+            }
+            s->check(ldo_set_biases(s->eng, static_cast<int>(bd.size()), bd.data()));
+        }
+
+        // control variables
+        std::vector<int> ti(n_replicas, 0);
+        std::vector<double> um(n_replicas, p.m_staple_u_mult), bm(n_replicas, p.m_bias_funcs_mult), sm(n_replicas, 1.0);
+        if (s->is_pt) {
+            std::vector<double> cm {p.m_chem_pot_mults}, bmm {p.m_bias_mults}, smm {p.m_stacking_mults};
+            cm.resize(s->num_reps, 1.0);
+            bmm.resize(s->num_reps, 1.0);
+            smm.resize(s->num_reps, 1.0);
+            std::vector<int> ladder_ti(s->num_reps);
+            for (int k {0}; k != s->num_reps; k++) ladder_ti[k] = k;
+            s->check(ldo_set_exchange_ladder(s->eng, s->num_reps, ladder_ti.data(), cm.data(), bmm.data(), smm.data()));
+            for (int r {0}; r != n_replicas; r++) {
+                int k {(global_first + r) % s->num_reps};
+                ti[r] = k;
+                um[r] = cm[k];
+                // OneDPTGCMCSimulation::initialize_control_qs stores the bias multiplier in the wrong
+                // slot (App. A17); with the shipped all-ones multipliers both readings coincide
+                bm[r] = bmm[k] * p.m_bias_funcs_mult;
+                sm[r] = smm[k];
+            }
+            s->q2r.resize(static_cast<size_t>(s->n_ladders) * s->num_reps);
+            for (int l {0}; l != s->n_ladders; l++)
+                for (int k {0}; k != s->num_reps; k++) s->q2r[static_cast<size_t>(l) * s->num_reps + k] = k;
+            s->attempts.assign(static_cast<size_t>(s->n_ladders) * (s->num_reps - 1), 0);
+            s->accepts.assign(static_cast<size_t>(s->n_ladders) * (s->num_reps - 1), 0);
+        }
+        s->check(ldo_set_control(s->eng, 0, n_replicas, ti.data(), um.data(), bm.data(), sm.data()));
+
+        // starting configuration
+        Chains chains {sf.chains};
+        if (!p.m_restart_traj_file.empty()) chains = read_trj_config(p.m_restart_traj_file, p.m_restart_step);
+        std::vector<int> ci, cid, cl, pos, ore;
+        for (auto const& c: chains) {
+            ci.push_back(c.index);
+            cid.push_back(c.identity);
+            cl.push_back(static_cast<int>(c.positions.size() / 3));
+            pos.insert(pos.end(), c.positions.begin(), c.positions.end());
+            ore.insert(ore.end(), c.orientations.begin(), c.orientations.end());
+        }
+        s->check(ldo_set_state(s->eng, -1, static_cast<int>(chains.size()), ci.data(), cid.data(), cl.data(), pos.data(), ore.data()));
+        std::vector<int> status(n_replicas), detail(n_replicas);
+        s->check(ldo_get_status(s->eng, status.data(), detail.data()));
+        if (status[0] != 0) {
+            throw OrigamiMisuse {"Constaints in violation after move complete (status " + std::to_string(status[0]) + ")"};
+        }
+
+        // seed (simulation.cpp:199-203; random_gens.cpp:12-19 when unspecified)
+        unsigned long long seed;
+        if (p.m_random_seed != -1) {
+            seed = static_cast<unsigned long long>(p.m_random_seed);
+            std::cout << "Using specified seed: " << p.m_random_seed << "\n";
+        }
+        else {
+            std::random_device rd {};
+            seed = (static_cast<unsigned long long>(rd()) << 32) ^ rd();
+            std::cout << "Truly random seed: " << seed << "\n";
+        }
+        s->check(ldo_seed(s->eng, seed, static_cast<unsigned int>(global_first)));
+        s->start = std::chrono::steady_clock::now();
+    } catch (std::exception const& e) {
+        g_host_error = e.what();
+        return nullptr;
+    }
+    return s.release();
+}
+
+void ldo_sim_destroy(ldo_sim* s) { delete s; }
+ldo_engine* ldo_sim_engine(ldo_sim* s) { return s->eng; }
+
+int ldo_sim_exchange_advance(ldo_sim* s) {
+    try {
+        if (!s->is_pt) throw SimulationMisuse {"not a replica-exchange simulation"};
+        if (!simulate(*s, s->params.m_exchange_interval)) return 1;
+        s->check(ldo_exchange_collect(s->eng, nullptr));
+    } catch (std::exception const& e) {
+        g_host_error = e.what();
+        return -1;
+    }
+    return 0;
+}
+
+int ldo_sim_exchange_apply(ldo_sim* s, long long swap_i, const double* dependent_all) {
+    try {
+        s->check(ldo_exchange_pt(
+                s->eng, s->pt_variant, swap_i, s->n_ladders, s->num_reps, s->global_first, s->n_global,
+                dependent_all, s->q2r.data(), s->attempts.data(), s->accepts.data()));
+    } catch (std::exception const& e) {
+        g_host_error = e.what();
+        return -1;
+    }
+    return 0;
+}
+
+int ldo_sim_exchange_state(ldo_sim* s, int* slot_to_replica, long long* attempts, long long* accepts) {
+    if (slot_to_replica) std::memcpy(slot_to_replica, s->q2r.data(), sizeof(int) * s->q2r.size());
+    if (attempts) std::memcpy(attempts, s->attempts.data(), sizeof(long long) * s->attempts.size());
+    if (accepts) std::memcpy(accepts, s->accepts.data(), sizeof(long long) * s->accepts.size());
+    return 0;
+}
+
+int ldo_sim_run(ldo_sim* s) {
+    try {
+        InputParameters const& p = s->params;
+        open_output_files(*s);
+        s->start = std::chrono::steady_clock::now();
+        std::string const& st = p.m_simulation_type;
+        if (st == "constant_temp") {
+            simulate(*s, p.m_ct_steps);
+        }
+        else if (st == "annealing") {
+            // AnnealingGCMCSimulation::run (annealing_simulation.cpp:38-49)
+            for (size_t i {0}; i != s->temps.size(); i++) {
+                set_all_control(*s, static_cast<int>(i));
+                if (!simulate(*s, p.m_steps_per_temp)) break;
+            }
+        }
+        else if (s->is_pt) {
+            if (s->n_global != s->R) throw SimulationMisuse {"ldo_sim_run drives single-GPU exchange only"};
+            // PTGCMCSimulation::run (ptmc_simulation.cpp:106-150); .swp as :92-104, :315-322
+            std::ofstream swp;
+            if (!p.m_output_filebase.empty()) {
+                swp.open(p.m_output_filebase + ".swp");
+                std::vector<double> cm {p.m_chem_pot_mults}, bmm {p.m_bias_mults}, smm {p.m_stacking_mults};
+                cm.resize(s->num_reps, 1.0);
+                bmm.resize(s->num_reps, 1.0);
+                smm.resize(s->num_reps, 1.0);
+                for (int k {0}; k != s->num_reps; k++) {
+                    swp << p.m_temps[k] << "/";
+                    if (s->pt_variant == LDO_PT_UT || s->pt_variant == LDO_PT_HUT) swp << cm[k] << "/";
+                    if (s->pt_variant == LDO_PT_HUT) swp << bmm[k] << "/";
+                    if (s->pt_variant == LDO_PT_ST) swp << smm[k] << "/";
+                    swp << " ";
+                }
+                swp << "\n";
+            }
+            auto write_swap_entry = [&](long long step) {
+                if (!swp.is_open() || p.m_configs_output_freq == 0) return;
+                if (step % p.m_configs_output_freq == 0) {
+                    for (int k {0}; k != s->num_reps; k++) swp << s->q2r[k] << " ";
+                    swp << "\n";
+                }
+            };
+            for (long long swap_i {1}; swap_i != p.m_swaps + 1; swap_i++) {
+                int rc {ldo_sim_exchange_advance(s)};
+                if (rc < 0) throw std::runtime_error(g_host_error);
+                double dt {std::chrono::duration<double>(std::chrono::steady_clock::now() - s->start).count()};
+                if (rc == 1 || dt > p.m_max_pt_dur) {
+                    std::cout << "Maximum time allowed reached\n";
+                    break;
+                }
+                write_swap_entry(s->step);
+                if (ldo_sim_exchange_apply(s, swap_i, nullptr) != 0) throw std::runtime_error(g_host_error);
+            }
+            write_swap_entry(s->step);
+            // write_acceptance_freqs (ptmc_simulation.cpp:414-426), first ladder
+            for (int i {0}; i + 1 < s->num_reps; i++) {
+                std::cout << p.m_temps[i] << " " << p.m_temps[i + 1] << " " << s->accepts[i] << " " << s->attempts[i] << " "
+                          << static_cast<double>(s->accepts[i]) / s->attempts[i] << " \n";
+            }
+            std::cout << "\n";
+        }
+        else {
+            throw NotImplemented {st + ": simulation type not available on the device path"};
+        }
+        write_move_summary(*s);
+    } catch (std::exception const& e) {
+        g_host_error = e.what();
+        return -1;
+    }
+    return 0;
+}
+
+int ldo_sim_num_temps(ldo_sim* s) { return static_cast<int>(s->temps.size()); }
+int ldo_sim_num_order_params(ldo_sim* s) { return static_cast<int>(s->ops.size()); }
+const char* ldo_sim_order_param_tag(ldo_sim* s, int i) { return s->ops[i].tag.c_str(); }
+int ldo_sim_num_movetypes(ldo_sim* s) { return static_cast<int>(s->movetypes.size()); }
+const char* ldo_sim_movetype_label(ldo_sim* s, int i) { return s->movetypes[i].label.c_str(); }
+int ldo_sim_num_staple_types(ldo_sim* s) { return static_cast<int>(s->sysfile->identities.size()) - 1; }
+long long ldo_sim_step(ldo_sim* s) { return s->step; }
+
+int ldo_sim_pair_energies(ldo_sim* s, int temp_idx, int a, int b, double* out) {
+    EnergyTables const& t = s->tables[temp_idx];
+    if (std::abs(a) > t.n_ident || std::abs(b) > t.n_ident) return -1;
+    size_t k {t.index(a, b)};
+    if (!t.present[k]) return -1;
+    out[0] = t.hyb_energy[k];
+    out[1] = t.hyb_enthalpy[k];
+    out[2] = t.hyb_entropy[k];
+    return 0;
+}
+
+int ldo_sim_init_energies(ldo_sim* s, int temp_idx, double* out) {
+    EnergyTables const& t = s->tables[temp_idx];
+    out[0] = t.init_energy;
+    out[1] = t.init_enthalpy;
+    out[2] = t.init_entropy;
+    return 0;
+}
+
+int ldo_host_nn_unitless_thermo(const char* seq, double temp, double cation_M, double* out) {
+    try {
+        ThermoOfHybrid t {calc_unitless_hybridization_thermo(seq, temp, cation_M)};
+        out[0] = t.enthalpy;
+        out[1] = t.entropy;
+    } catch (std::exception const& e) {
+        g_host_error = e.what();
+        return -1;
+    }
+    return 0;
+}
+
+int ldo_host_longest_contig_complement(const char* a, const char* b, char* out, int outlen) {
+    try {
+        auto v = find_longest_contig_complement(a, b);
+        std::string s;
+        for (auto const& x: v) s += x + "\n";
+        std::strncpy(out, s.c_str(), outlen - 1);
+        out[outlen - 1] = 0;
+        return static_cast<int>(v.size());
+    } catch (std::exception const& e) {
+        g_host_error = e.what();
+        return -1;
+    }
+}
+
+int ldo_host_no_walks(const int* start, const int* end, int steps) {
+    int dr {std::abs(end[0] - start[0]) + std::abs(end[1] - start[1]) + std::abs(end[2] - start[2])};
+    return (dr > steps || (steps - dr) % 2 != 0) ? 1 : 0;
+}
+
+} // extern "C"
