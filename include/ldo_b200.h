@@ -193,6 +193,20 @@ int ldo_synchronize(ldo_engine* e);
 /* The CUDA stream every kernel of this engine is launched on (cudaStream_t as void*). */
 void* ldo_stream(ldo_engine* e);
 
+/* Number of CUDA kernels this engine has launched so far. */
+long long ldo_launch_count(const ldo_engine* e);
+
+/* ---- checkpoint / resume ------------------------------------------------------------------------ */
+
+/* Device-side get_state / set_state for restart: `count` replicas starting at `first`
+ * as opaque blobs of ldo_checkpoint_size() bytes each (configuration, occupancy table, counters,
+ * running energy, RNG counter, control variables, bias state, move statistics). Blobs are only valid
+ * for an engine created with the same system descriptor; tapes are not part of a checkpoint. The host
+ * buffer may be pinned; ldo_checkpoint_load is asynchronous on the engine's stream. */
+unsigned long ldo_checkpoint_size(const ldo_engine* e);
+int ldo_checkpoint_save(ldo_engine* e, int first, int count, void* host);
+int ldo_checkpoint_load(ldo_engine* e, int first, int count, const void* host);
+
 /* ---- observables ------------------------------------------------------------------------------ */
 
 /* [n_replicas][5]: total energy, hybridization enthalpy, entropy, stacking energy, external bias

@@ -60,6 +60,12 @@ long long ldo_sim_step(ldo_sim* s);
  * out = {hyb energy, hyb enthalpy, hyb entropy} of identity pair (a, b) at table `temp_idx`; returns -1 if absent. */
 int ldo_sim_pair_energies(ldo_sim* s, int temp_idx, int a, int b, double* out);
 int ldo_sim_init_energies(ldo_sim* s, int temp_idx, double* out);
+/* GPU-free table build for the system named by a parameter file: sizes follow *n_ident ((2n+1)^2 per
+ * array; call with NULL arrays first to query it). `present` flags the tabulated identity pairs. */
+int ldo_host_energy_tables(const char* inp_path, double temp, int* n_ident, double* hyb_energy, double* hyb_enthalpy,
+                           double* hyb_entropy, char* present, double* init);
+/* Value the parameter-file reader assigns to `key` (defaults included), as text; for parser parity tests. */
+int ldo_host_inp_value(const char* inp_path, const char* key, char* out, int outlen);
 int ldo_host_nn_unitless_thermo(const char* seq, double temp, double cation_M, double* out);
 int ldo_host_longest_contig_complement(const char* a, const char* b, char* out, int outlen);
 /* ideal_random_walk.cpp:14-73 reduced to the only property the path consumes (num_walks == 0). */

@@ -19,6 +19,7 @@ ENGINE_SYMBOLS = [
     "ldo_get_energies", "ldo_get_counters", "ldo_get_staple_counts", "ldo_get_order_params",
     "ldo_get_move_stats", "ldo_recompute_energies", "ldo_check_all_constraints", "ldo_center",
     "ldo_set_exchange_ladder", "ldo_exchange_collect", "ldo_exchange_pt", "ldo_exchange_buffers",
+    "ldo_launch_count", "ldo_checkpoint_size", "ldo_checkpoint_save", "ldo_checkpoint_load",
 ]
 HOST_SYMBOLS = [
     "ldo_host_last_error", "ldo_sim_create", "ldo_sim_destroy", "ldo_sim_engine", "ldo_sim_run",
@@ -26,7 +27,7 @@ HOST_SYMBOLS = [
     "ldo_sim_num_order_params", "ldo_sim_order_param_tag", "ldo_sim_num_movetypes",
     "ldo_sim_movetype_label", "ldo_sim_num_staple_types", "ldo_sim_step", "ldo_sim_pair_energies",
     "ldo_sim_init_energies", "ldo_host_nn_unitless_thermo", "ldo_host_longest_contig_complement",
-    "ldo_host_no_walks",
+    "ldo_host_no_walks", "ldo_host_energy_tables", "ldo_host_inp_value",
 ]
 
 STATUS_NAMES = {
@@ -93,6 +94,10 @@ def load(path=None):
         "ldo_exchange_collect": (i, [vp, vp]),
         "ldo_exchange_pt": (i, [vp, i, ll, i, i, i, i, vp, vp, vp, vp]),
         "ldo_exchange_buffers": (i, [vp, i, vp, vp, vp]),
+        "ldo_launch_count": (ll, [vp]),
+        "ldo_checkpoint_size": (C.c_ulong, [vp]),
+        "ldo_checkpoint_save": (i, [vp, i, i, vp]),
+        "ldo_checkpoint_load": (i, [vp, i, i, vp]),
         "ldo_host_last_error": (C.c_char_p, []),
         "ldo_sim_create": (vp, [C.c_char_p, i, i, i, i]),
         "ldo_sim_destroy": (None, [vp]),
@@ -113,6 +118,8 @@ def load(path=None):
         "ldo_host_nn_unitless_thermo": (i, [C.c_char_p, d, d, vp]),
         "ldo_host_longest_contig_complement": (i, [C.c_char_p, C.c_char_p, C.c_char_p, i]),
         "ldo_host_no_walks": (i, [vp, vp, i]),
+        "ldo_host_energy_tables": (i, [C.c_char_p, d, vp, vp, vp, vp, vp, vp]),
+        "ldo_host_inp_value": (i, [C.c_char_p, C.c_char_p, C.c_char_p, i]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -274,6 +281,26 @@ class Engine:
         self._check(self.L.ldo_get_grid_visits(self.h, replica, bias, _ptr(out), 1 if clear else 0))
         return out
 
+    # checkpoint
+    def launch_count(self):
+        return self.L.ldo_launch_count(self.h)
+
+    def checkpoint_size(self):
+        return self.L.ldo_checkpoint_size(self.h)
+
+    def checkpoint_save(self, out=None, first=0, count=None):
+        count = self.R - first if count is None else count
+        if out is None:
+            out = np.zeros(count * self.checkpoint_size(), dtype=np.uint8)
+        ptr = out.data_ptr() if hasattr(out, "data_ptr") else out.ctypes.data
+        self._check(self.L.ldo_checkpoint_save(self.h, first, count, ptr))
+        return out
+
+    def checkpoint_load(self, blob, first=0, count=None):
+        count = self.R - first if count is None else count
+        ptr = blob.data_ptr() if hasattr(blob, "data_ptr") else blob.ctypes.data
+        self._check(self.L.ldo_checkpoint_load(self.h, first, count, ptr))
+
     # exchange
     def exchange_collect(self):
         out = np.zeros((self.R, 3 + self.n_staple_types))
@@ -344,3 +371,49 @@ class Simulation:
         out = np.zeros(3)
         self.L.ldo_sim_init_energies(self.h, temp_idx, _ptr(out))
         return out
+
+
+# ---- GPU-free host helpers (table builder, parameter-file reader) ---------------------------------
+
+def host_energy_tables(inp_path, temp, lib_path=None):
+    L = load(lib_path)
+    n = C.c_int(0)
+    if L.ldo_host_energy_tables(os.fsencode(inp_path), temp, C.byref(n), None, None, None, None, None) != 0:
+        raise LdoError(L.ldo_host_last_error().decode())
+    sz = (2 * n.value + 1) ** 2
+    e, h, s = np.zeros(sz), np.zeros(sz), np.zeros(sz)
+    present = np.zeros(sz, dtype=np.int8)
+    init = np.zeros(3)
+    if L.ldo_host_energy_tables(os.fsencode(inp_path), temp, C.byref(n), _ptr(e), _ptr(h), _ptr(s), _ptr(present), _ptr(init)) != 0:
+        raise LdoError(L.ldo_host_last_error().decode())
+    return {"n_ident": n.value, "energy": e, "enthalpy": h, "entropy": s, "present": present, "init": init}
+
+
+def host_inp_value(inp_path, key, lib_path=None):
+    L = load(lib_path)
+    buf = C.create_string_buffer(4096)
+    if L.ldo_host_inp_value(os.fsencode(inp_path), key.encode(), buf, 4096) != 0:
+        raise LdoError(L.ldo_host_last_error().decode())
+    return buf.value.decode()
+
+
+def host_nn_unitless_thermo(seq, temp, cation_M, lib_path=None):
+    L = load(lib_path)
+    out = np.zeros(2)
+    if L.ldo_host_nn_unitless_thermo(seq.encode(), temp, cation_M, _ptr(out)) != 0:
+        raise LdoError(L.ldo_host_last_error().decode())
+    return out[0], out[1]
+
+
+def host_longest_contig_complement(a, b, lib_path=None):
+    L = load(lib_path)
+    buf = C.create_string_buffer(4096)
+    L.ldo_host_longest_contig_complement(a.encode(), b.encode(), buf, 4096)
+    return [x for x in buf.value.decode().split("\n") if x]
+
+
+def host_no_walks(start, end, steps, lib_path=None):
+    L = load(lib_path)
+    s = np.asarray(start, dtype=np.int32)
+    e = np.asarray(end, dtype=np.int32)
+    return bool(L.ldo_host_no_walks(_ptr(s), _ptr(e), steps))

@@ -582,6 +582,10 @@ struct EngineBase {
     virtual int exchange(ExchangeArgs& x, const double* dependent_host, int* slot_to_replica, long long* attempts, long long* accepts) = 0;
     virtual int exchange_buffers(int n_global, void** send, void** recv, int* nq) = 0;
     virtual int alloc_outputs() = 0;
+    virtual size_t blob_size() = 0;
+    virtual int get_blobs(int first, int count, void* host) = 0;
+    virtual int put_blobs(int first, int count, const void* host) = 0;
+    long long launches = 0; // kernels launched so far (ldo_launch_count)
     // device output buffers
     double* d_energies = nullptr;
     int* d_counters = nullptr;
@@ -779,6 +783,7 @@ struct EngineImpl: EngineBase {
             k_exec_inplace<K><<<blocks, wpb * 32, 0, stream>>>(P, a, wpb, d_recompute_tmp);
         }
         if (chk(cudaGetLastError())) return fail(dev_err());
+        launches++;
         if (sync && dev_sync(stream)) return fail(dev_err());
         return 0;
 #endif
@@ -799,6 +804,32 @@ struct EngineImpl: EngineBase {
                 return fail(dev_err());
             }
         }
+#endif
+        return 0;
+    }
+
+    // Opaque checkpoint blobs: state + per-replica auxiliary data (RNG, control, biases, statistics)
+    size_t blob_size() override { return sizeof(SysState<K>) + sizeof(RepAux); }
+    int get_blobs(int first, int count, void* host) override {
+        unsigned char* h = static_cast<unsigned char*>(host);
+#ifdef LDO_HOSTSIM
+        memcpy(h, P.states + first, sizeof(SysState<K>) * count);
+        memcpy(h + sizeof(SysState<K>) * count, P.aux + first, sizeof(RepAux) * count);
+#else
+        if (chk(cudaMemcpyAsync(h, P.states + first, sizeof(SysState<K>) * count, cudaMemcpyDeviceToHost, stream))) return fail(dev_err());
+        if (chk(cudaMemcpyAsync(h + sizeof(SysState<K>) * count, P.aux + first, sizeof(RepAux) * count, cudaMemcpyDeviceToHost, stream))) return fail(dev_err());
+        if (dev_sync(stream)) return fail(dev_err());
+#endif
+        return 0;
+    }
+    int put_blobs(int first, int count, const void* host) override {
+        const unsigned char* h = static_cast<const unsigned char*>(host);
+#ifdef LDO_HOSTSIM
+        memcpy(P.states + first, h, sizeof(SysState<K>) * count);
+        memcpy(P.aux + first, h + sizeof(SysState<K>) * count, sizeof(RepAux) * count);
+#else
+        if (chk(cudaMemcpyAsync(P.states + first, h, sizeof(SysState<K>) * count, cudaMemcpyHostToDevice, stream))) return fail(dev_err());
+        if (chk(cudaMemcpyAsync(P.aux + first, h + sizeof(SysState<K>) * count, sizeof(RepAux) * count, cudaMemcpyHostToDevice, stream))) return fail(dev_err());
 #endif
         return 0;
     }
@@ -1043,6 +1074,7 @@ struct EngineImpl: EngineBase {
         int threads = 128;
         k_exchange<<<(x.n_ladders + threads - 1) / threads, threads, 0, stream>>>(dx);
         if (chk(cudaGetLastError())) return fail(dev_err());
+        launches++;
 #endif
         if (dev_d2h(slot_to_replica, d_q2r, sizeof(int) * n_slots, stream)) return fail(dev_err());
         if (dev_d2h(attempts, d_att, sizeof(long long) * n_pairs, stream)) return fail(dev_err());
@@ -1565,6 +1597,18 @@ int ldo_exchange_pt(ldo_engine* e, int variant, long long swap_i, int n_ladders,
     // PTGCMCSimulation::run calls update_control_qs() at the top of every round, which always ends
     // in update_energy() (App. A19): rebuild the running energy with the (possibly new) tables
     return refresh_energy(e);
+}
+
+long long ldo_launch_count(const ldo_engine* e) { return e->b->launches; }
+
+unsigned long ldo_checkpoint_size(const ldo_engine* e) { return e->b->blob_size(); }
+int ldo_checkpoint_save(ldo_engine* e, int first, int count, void* host) {
+    if (first < 0 || count < 0 || first + count > e->b->R) return e->b->fail("bad replica range");
+    return e->b->get_blobs(first, count, host);
+}
+int ldo_checkpoint_load(ldo_engine* e, int first, int count, const void* host) {
+    if (first < 0 || count < 0 || first + count > e->b->R) return e->b->fail("bad replica range");
+    return e->b->put_blobs(first, count, host);
 }
 
 int ldo_exchange_buffers(ldo_engine* e, int n_global, void** send_dev, void** recv_dev, int* doubles_per_replica) {

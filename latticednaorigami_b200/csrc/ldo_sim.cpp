@@ -640,6 +640,77 @@ int ldo_sim_init_energies(ldo_sim* s, int temp_idx, double* out) {
     return 0;
 }
 
+int ldo_host_energy_tables(const char* inp_path, double temp, int* n_ident, double* hyb_energy, double* hyb_enthalpy,
+                           double* hyb_entropy, char* present, double* init) {
+    try {
+        InputParameters p {inp_path};
+        OrigamiInputFile sf {p.m_origami_input_filename};
+        EnergyTables t {calc_energy_tables(sf, p, temp)};
+        *n_ident = t.n_ident;
+        size_t n {t.hyb_energy.size()};
+        if (hyb_energy) std::memcpy(hyb_energy, t.hyb_energy.data(), sizeof(double) * n);
+        if (hyb_enthalpy) std::memcpy(hyb_enthalpy, t.hyb_enthalpy.data(), sizeof(double) * n);
+        if (hyb_entropy) std::memcpy(hyb_entropy, t.hyb_entropy.data(), sizeof(double) * n);
+        if (present) std::memcpy(present, t.present.data(), n);
+        if (init) {
+            init[0] = t.init_energy;
+            init[1] = t.init_enthalpy;
+            init[2] = t.init_entropy;
+        }
+    } catch (std::exception const& e) {
+        g_host_error = e.what();
+        return -1;
+    }
+    return 0;
+}
+
+int ldo_host_inp_value(const char* inp_path, const char* key, char* out, int outlen) {
+    try {
+        InputParameters p {inp_path};
+        std::ostringstream os;
+        os.precision(17);
+        std::string k {key};
+        auto join = [&](auto const& v) {
+            for (size_t i {0}; i != v.size(); i++) os << (i ? " " : "") << v[i];
+        };
+        if (k == "origami_input_filename") os << p.m_origami_input_filename;
+        else if (k == "domain_type") os << p.m_domain_type;
+        else if (k == "temp") os << p.m_temp;
+        else if (k == "staple_M") os << p.m_staple_M;
+        else if (k == "cation_M") os << p.m_cation_M;
+        else if (k == "stacking_ene") os << p.m_stacking_ene;
+        else if (k == "max_total_staples") os << p.m_max_total_staples;
+        else if (k == "max_type_staples") os << p.m_max_type_staples;
+        else if (k == "max_staple_size") os << p.m_max_staple_size;
+        else if (k == "simulation_type") os << p.m_simulation_type;
+        else if (k == "random_seed") os << p.m_random_seed;
+        else if (k == "centering_freq") os << p.m_centering_freq;
+        else if (k == "constraint_check_freq") os << p.m_constraint_check_freq;
+        else if (k == "max_duration") os << p.m_max_duration;
+        else if (k == "ct_steps") os << p.m_ct_steps;
+        else if (k == "temps") join(p.m_temps);
+        else if (k == "chem_pot_mults") join(p.m_chem_pot_mults);
+        else if (k == "bias_mults") join(p.m_bias_mults);
+        else if (k == "stacking_mults") join(p.m_stacking_mults);
+        else if (k == "num_reps") os << p.m_num_reps;
+        else if (k == "exchange_interval") os << p.m_exchange_interval;
+        else if (k == "swaps") os << p.m_swaps;
+        else if (k == "ops_to_output") join(p.m_ops_to_output);
+        else if (k == "apply_mean_field_cor") os << (p.m_apply_mean_field_cor ? "true" : "false");
+        else if (k == "vcf_per_domain") os << (p.m_vcf_per_domain ? "true" : "false");
+        else if (k == "restart_traj_postfix") os << p.m_restart_traj_postfix;
+        else if (k == "max_rel_P_diff") os << p.m_max_rel_P_diff;
+        else if (k == "output_filebase") os << p.m_output_filebase;
+        else throw FileError {"ldo_host_inp_value: key not exposed: " + k};
+        std::strncpy(out, os.str().c_str(), outlen - 1);
+        out[outlen - 1] = 0;
+    } catch (std::exception const& e) {
+        g_host_error = e.what();
+        return -1;
+    }
+    return 0;
+}
+
 int ldo_host_nn_unitless_thermo(const char* seq, double temp, double cation_M, double* out) {
     try {
         ThermoOfHybrid t {calc_unitless_hybridization_thermo(seq, temp, cation_M)};

@@ -1,0 +1,154 @@
+"""Parity tests proper: the CUDA library (through the C-ABI) against tapes recorded from the unmodified
+reference, against the live oracle where oracle/_ref travelled, and — at BASELINE sizes — through
+size-independent properties (running energy == from-scratch recomputation, full constraint check,
+determinism, checkpoint round trip, exact-enumeration statistics)."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import (GOLDEN, assert_state_equal, make_options, options_from_fixture, replay_fixture_through, write_inp)
+from latticednaorigami_b200.binding import Simulation
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name", ["four_unbound_340K", "snodin_assembled_330K", "snodin_unbound_335K"])
+def test_replay_fixture_bit_exact(tmp_path, name):
+    fx = np.load(os.path.join(GOLDEN, f"replay_{name}.npz"))
+    sim = Simulation(write_inp(str(tmp_path / "r.inp"), options_from_fixture(fx)), 5, 0)
+    replay_fixture_through(sim, fx, replicas=[0, 2, 4])
+
+
+@pytest.mark.parametrize("key", ["snodin_assembled.json@330", "snodin_assembled.json@345", "snodin_unbound.json@330", "four_unbound.json@330"])
+def test_energy_of_reference_configurations(tmp_path, key):
+    golden = json.load(open(os.path.join(GOLDEN, "energies.json")))[key]
+    system, temp = key.split("@")
+    sim = Simulation(write_inp(str(tmp_path / "e.inp"), make_options(system, temp=float(temp))), 3, 0)
+    e = sim.engine.energies()
+    for r in range(3):
+        assert abs(e[r, 0] - golden["energy"]) <= 1e-12 * max(1.0, abs(golden["energy"]))
+        assert abs(e[r, 1] - golden["split"]["enthalpy"]) <= 1e-12 * max(1.0, abs(golden["split"]["enthalpy"]))
+        assert abs(e[r, 2] - golden["split"]["entropy"]) <= 1e-12 * max(1.0, abs(golden["split"]["entropy"]))
+        assert abs(e[r, 3] - golden["split"]["stacking"]) <= 1e-9 * max(1.0, abs(golden["split"]["stacking"]))
+    assert list(sim.engine.counters()[0]) == list(golden["counters"].values())
+
+
+def test_live_replay_against_oracle(oracle, tmp_path):
+    cases = [("snodin_assembled.json", 330, 201, 120, {}), ("snodin_unbound.json", 335, 202, 600, {}),
+             ("snodin_unbound.json", 345, 203, 600, {}),
+             ("four_unbound.json", 330, 204, 2000, {"movetype_file": None, "max_total_staples": 2, "max_type_staples": 2})]
+    for system, temp, seed, steps, extra in cases:
+        opts = make_options(system, temp=temp)
+        if "movetype_file" in extra:
+            opts = make_options(system, "moveset_four.json", temp=temp, max_total_staples=2, max_type_staples=2)
+        r = oracle.RefSystem(opts)
+        r.seed(seed)
+        sim = Simulation(write_inp(str(tmp_path / f"{seed}.inp"), opts), 2, 0)
+        for _ in range(4):
+            r.tape(clear=True)
+            r.simulate(steps // 4)
+            tape = r.tape(clear=True)
+            for rep in (0, 1):
+                sim.engine.attach_tape(rep, tape)
+            sim.engine.run(steps // 4)
+            sim.engine.assert_ok()
+            for rep in (0, 1):
+                assert sim.engine.tape_position(rep) == len(tape)
+                assert_state_equal(sim.engine.state(rep), r.state(), f"{system} seed {seed}")
+            e = r.energy()
+            assert abs(sim.engine.energies()[0, 0] - e) <= 1e-12 * max(1.0, abs(e))
+        att, acc = sim.engine.move_stats()
+        ra, rb = r.move_stats()
+        assert list(att[0]) == list(ra) and list(acc[0]) == list(rb)
+
+
+def test_centering_and_constraint_check_replay(oracle, tmp_path):
+    opts = make_options("snodin_assembled.json", temp=330, centering_freq=7, constraint_check_freq=5)
+    r = oracle.RefSystem(opts)
+    r.seed(9)
+    r.simulate(60)
+    sim = Simulation(write_inp(str(tmp_path / "c.inp"), opts), 1, 0)
+    sim.engine.attach_tape(0, r.tape())
+    sim.engine.run(60, 7, 0, 5)
+    sim.engine.assert_ok()
+    assert_state_equal(sim.engine.state(0), r.state())
+    assert abs(sim.engine.energies()[0, 0] - r.energy()) <= 1e-12 * abs(r.energy())
+
+
+def test_philox_ensemble_invariants_at_scale(tmp_path):
+    """4096 snodin replicas (BASELINE size): every replica keeps a consistent state."""
+    R = 4096
+    sim = Simulation(write_inp(str(tmp_path / "p.inp"), make_options("snodin_unbound.json", temp=336, random_seed=1234)), R, 0)
+    eng = sim.engine
+    eng.run(300, 100, 0, 150)
+    eng.assert_ok()
+    running = eng.energies()[:, 0]
+    recomputed, stacked = eng.recompute_energies()
+    assert np.all(np.abs(running - recomputed) <= 1e-9 * np.maximum(1.0, np.abs(recomputed)))
+    c = eng.counters()
+    assert np.array_equal(stacked, c[:, 6])
+    assert np.all(c[:, 7] == 0) and np.all(c[:, 0] >= 0) and np.all(c[:, 0] <= 24)
+    assert np.all(c[:, 1] == 24 + 2 * c[:, 0])
+    eng.check_all_constraints()
+    eng.assert_ok()
+    att, acc = eng.move_stats()
+    assert np.all(att.sum(axis=1) == 300) and np.all(acc <= att)
+    # replicas are independent streams: they must not all have done the same thing
+    assert len(np.unique(running)) > R // 4
+
+
+def test_determinism_and_checkpoint_roundtrip(tmp_path):
+    opts = make_options("snodin_assembled.json", temp=332, random_seed=77)
+    inp = write_inp(str(tmp_path / "d.inp"), opts)
+    a = Simulation(inp, 64, 0)
+    b = Simulation(inp, 64, 0)
+    a.engine.run(200)
+    b.engine.run(80)
+    blob = b.engine.checkpoint_save()
+    c = Simulation(inp, 64, 0)
+    c.engine.checkpoint_load(blob)
+    c.engine.run(120)
+    b.engine.run(120)
+    for eng in (b.engine, c.engine):
+        eng.assert_ok()
+        assert np.array_equal(eng.energies(), a.engine.energies())
+        assert np.array_equal(eng.counters(), a.engine.counters())
+    for r in (0, 17, 63):
+        assert_state_equal(c.engine.state(r), a.engine.state(r))
+
+
+def test_exact_enumeration_statistics(tmp_path):
+    """four_unbound at 345 K: ensemble histogram over (numfulldomains, nummisdomains, numstackedpairs,
+    numstaples) against the reference's exact enumeration (tests/golden/enum_four_unbound.json)."""
+    weights = json.load(open(os.path.join(GOLDEN, "enum_four_unbound.json")))["345"]["weights"]
+    R, burn, sweeps, stride = 2048, 20000, 40, 500
+    opts = make_options("four_unbound.json", "moveset_four.json", temp=345, max_total_staples=2, max_type_staples=2, random_seed=4242)
+    sim = Simulation(write_inp(str(tmp_path / "s.inp"), opts), R, 0)
+    eng = sim.engine
+    tags = sim.op_tags
+    idx = [tags.index(t) for t in ("numfulldomains", "nummisdomains", "numstackedpairs", "numstaples")]
+    eng.run(burn, 1000, 0, 0)
+    eng.assert_ok()
+    counts = {}
+    per_rep = {}
+    for _ in range(sweeps):
+        eng.run(stride, 1000, 0, 0)
+        ops = eng.order_params()[:, idx]
+        for r, row in enumerate(ops):
+            key = "(%d %d %d %d)" % tuple(row)
+            counts[key] = counts.get(key, 0) + 1
+            per_rep.setdefault(key, np.zeros(R))[r] += 1
+    eng.assert_ok()
+    total = R * sweeps
+    checked = 0
+    for key, w in weights.items():
+        if w < 2e-3:
+            continue
+        p = counts.get(key, 0) / total
+        rep_p = per_rep.get(key, np.zeros(R)) / sweeps
+        sem = rep_p.std(ddof=1) / np.sqrt(R) + 1e-4
+        assert abs(p - w) < 6 * sem + 0.02 * w, (key, p, w, sem)
+        checked += 1
+    assert checked >= 4
