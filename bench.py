@@ -1,0 +1,352 @@
+#!/usr/bin/env python
+"""bench.py — attempted MC moves / second (whole job) of snodin temperature replica exchange.
+
+Workload (BASELINE.json configs[2]): examples/ptmc.inp generalised to a batch:
+`ut_parallel_tempering`, exchange_interval 100, 32-temperature ladder 330..361 K (1 K steps), 4096
+replicas per GPU = 128*N ladders, GPU g holding ladder slots [g*32/N, (g+1)*32/N) of every ladder, start
+from snodin_unbound, moveset_standard. One "step" = one exchange round: 100 attempted moves on every
+replica, collection of the exchange quantities, (N > 1: NCCL all-gather), on-device swap decisions and
+the energy rebuild that follows a control-variable update.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA engine
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's own CPU code, host cores
+"""
+import argparse
+import json
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+INPUTS = os.path.join(ROOT, "tests", "golden", "inputs")
+
+LADDER = [330.0 + i for i in range(32)]
+EXCHANGE_INTERVAL = 100
+SMEM_BYTES_PER_MOVE = 41.7e3  # 2215 table ops * 8 B + 1500 record touches * 16 B
+HBM_FALLBACK_GBS = 6650.0  # B200_PROFILING.md fallback
+
+
+def base_options():
+    return {
+        "origami_input_filename": os.path.join(INPUTS, "snodin_unbound.json"),
+        "domain_type": "HalfTurn", "binding_pot": "FourBody", "misbinding_pot": "Opposing",
+        "stacking_pot": "Constant", "hybridization_pot": "NearestNeighbour", "apply_mean_field_cor": "false",
+        "staple_M": 1e-7, "cation_M": 0.5, "staple_u_mult": 1, "stacking_ene": -1000,
+        "max_total_staples": 24, "max_type_staples": 12, "max_staple_size": 2,
+        "domain_update_biases_present": "false",
+        "order_parameter_file": os.path.join(INPUTS, "ops_standard.json"),
+        "movetype_file": os.path.join(INPUTS, "moveset_standard.json"),
+        "centering_freq": 100000, "constraint_check_freq": 1000000,
+    }
+
+
+def write_inp(path, options):
+    with open(path, "w") as f:
+        for k, v in options.items():
+            if isinstance(v, (list, tuple)):
+                v = " ".join(str(x) for x in v)
+            f.write(f"{k}={v}\n")
+    return path
+
+
+# ---------------------------------------------------------------------------------------------
+# Reference arm / CPU baseline: the unmodified reference CLI (oracle/_ref), one process per host core
+# ---------------------------------------------------------------------------------------------
+
+def reference_sample(cores, moves_per_proc, workdir, seed0):
+    """One bounded sample: `cores` independent reference processes, each `moves_per_proc` attempted moves of
+    constant-T MC at a ladder temperature (the reference's exchange traffic is 28 doubles per 100 moves,
+    so real MPI would not change throughput; none is installed). Returns wall seconds."""
+    cli = os.path.join(ROOT, "oracle", "_ref", "latticeDNAOrigami")
+    procs = []
+    for c in range(cores):
+        d = os.path.join(workdir, f"p{seed0}_{c}")
+        os.makedirs(d, exist_ok=True)
+        opts = base_options()
+        opts.update({"simulation_type": "constant_temp", "temp": LADDER[c % len(LADDER)], "ct_steps": moves_per_proc,
+                     "random_seed": seed0 * 1000 + c, "max_duration": 1e9, "output_filebase": os.path.join(d, "out"),
+                     "logging_freq": 0})
+        write_inp(os.path.join(d, "ref.inp"), opts)
+        procs.append((cli, os.path.join(d, "ref.inp")))
+    t0 = time.perf_counter()
+    running = [subprocess.Popen([cli, "-i", inp], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL) for cli, inp in procs]
+    for p in running:
+        if p.wait() != 0:
+            raise RuntimeError("reference process failed")
+    return time.perf_counter() - t0
+
+
+def reference_available():
+    return os.path.exists(os.path.join(ROOT, "oracle", "_ref", "latticeDNAOrigami"))
+
+
+def cpu_baseline(moves_per_proc=12000):
+    cores = os.cpu_count() or 1
+    with tempfile.TemporaryDirectory(prefix="ldo_ref_") as tmp:
+        wall = reference_sample(cores, moves_per_proc, tmp, 1)
+    return {"value": cores * moves_per_proc / wall, "unit": "attempted MC moves/s", "cores": cores, "kind": "reference",
+            "sample": f"{cores} processes of the unmodified reference CLI (oracle/_ref), one per core, "
+                      f"{moves_per_proc} constant-T moves each at ladder temperatures {LADDER[0]:.0f}..{LADDER[min(cores, 32) - 1]:.0f} K "
+                      f"from snodin_unbound, {wall:.1f} s wall"}
+
+
+def run_reference_arm(args, rank):
+    if rank != 0:
+        return
+    if not reference_available():
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/latticeDNAOrigami not built (needs /root/reference at build time)"}))
+        return
+    cores = os.cpu_count() or 1
+    moves = 6000
+    with tempfile.TemporaryDirectory(prefix="ldo_ref_") as tmp:
+        for w in range(args.warmup):
+            reference_sample(cores, 500, tmp, 100 + w)
+        t0 = time.perf_counter()
+        for k in range(args.steps):
+            reference_sample(cores, moves, tmp, 200 + k)
+        wall = time.perf_counter() - t0
+    value = cores * moves * args.steps / wall
+    sample = (f"per step: {cores} processes of the unmodified reference CLI, one per host core, {moves} constant-T moves each "
+              f"at ladder temperatures from snodin_unbound")
+    print(json.dumps({
+        "impl": "reference", "metric": "attempted MC moves/sec (whole box), snodin PTMC", "value": value,
+        "unit": "attempted MC moves/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * wall / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic", "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": value, "unit": "attempted MC moves/s", "cores": cores, "kind": "reference", "sample": sample},
+        "e2e": {"value": value, "unit": "attempted MC moves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def workload_config(n_gpus):
+    return {"workload": "snodin ut_parallel_tempering (examples/ptmc.inp batched): 32-temperature ladder 330..361 K, "
+                        "exchange_interval 100, moveset_standard, start snodin_unbound",
+            "replicas_per_gpu": 4096, "ladders": 128 * n_gpus, "ladder_len": 32, "moves_per_step": 4096 * n_gpus * EXCHANGE_INTERVAL,
+            "l2_policy": "state (13 MB/GPU) is re-staged from HBM every launch; per-step working set is shared memory"}
+
+
+# ---------------------------------------------------------------------------------------------
+# This repo's arm
+# ---------------------------------------------------------------------------------------------
+
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device = device
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        if shutil.which("nvidia-smi") is None:
+            return
+        fd, self.path = tempfile.mkstemp(suffix=".csv")
+        os.close(fd)
+        self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.device}", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                                      "-lms", "200"], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        self.proc.terminate()
+        self.proc.wait()
+        sm, smax, reasons = [], [], set()
+        for line in open(self.path):
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v == "Active":
+                    reasons.add(name)
+        os.unlink(self.path)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(smax) if smax else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+class DevArray:
+    """__cuda_array_interface__ view of an engine-owned device buffer (for torch.as_tensor)."""
+
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False), "version": 2}
+
+
+def run_ours(args, rank, world, local_rank):
+    import numpy as np
+    import torch
+
+    from latticednaorigami_b200.binding import Simulation
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the engine has no CPU path)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    R = args.replicas_per_gpu
+    L = len(LADDER)
+    slots = L // world
+    n_ladders = R // slots
+    tmp = tempfile.mkdtemp(prefix="ldo_bench_")
+    opts = base_options()
+    opts.update({"simulation_type": "ut_parallel_tempering", "num_reps": L, "temps": LADDER, "chem_pot_mults": [1] * L,
+                 "bias_mults": [1] * L, "stacking_mults": [1] * L, "exchange_interval": EXCHANGE_INTERVAL, "swaps": 0,
+                 "random_seed": 20261017})
+    sim = Simulation(write_inp(os.path.join(tmp, f"bench{rank}.inp"), opts), R, local_rank, rank=rank, n_ranks=world)
+    eng = sim.engine
+    stream = torch.cuda.ExternalStream(eng.stream(), device=local_rank)
+    send = recv = None
+    if world > 1:
+        send_ptr, recv_ptr, nq = eng.exchange_buffers(R * world)
+        send = torch.as_tensor(DevArray(send_ptr, R * nq), device=f"cuda:{local_rank}")
+        recv = torch.as_tensor(DevArray(recv_ptr, R * world * nq), device=f"cuda:{local_rank}")
+
+    cf, ccf = int(opts["centering_freq"]), int(opts["constraint_check_freq"])
+    swap = [0]
+    kernel_events = []
+
+    def exchange_round(record=False):
+        swap[0] += 1
+        if record:
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+        eng.run_async(EXCHANGE_INTERVAL, cf, 0, ccf)
+        if record:
+            b.record(stream)
+            kernel_events.append((a, b))
+        eng.exchange_collect(to_host=False)
+        if world > 1:
+            eng.synchronize()
+            dist.all_gather_into_tensor(recv, send)
+            torch.cuda.current_stream().synchronize()
+        sim.exchange_apply(swap[0], None)
+
+    def barrier():
+        eng.synchronize()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    for _ in range(args.warmup):
+        exchange_round()
+    barrier()
+    eng.assert_ok()
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = eng.launch_count()
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    start.record(stream)
+    for _ in range(args.steps):
+        exchange_round(record=True)
+    end.record(stream)
+    barrier()
+    elapsed_ms = start.elapsed_time(end)
+    launches = eng.launch_count() - launches0
+    clocks = sampler.stop()
+    eng.assert_ok()
+    kernel_ms = sum(a.elapsed_time(b) for a, b in kernel_events) / len(kernel_events)
+
+    if world > 1:
+        t = torch.tensor([elapsed_ms], device=f"cuda:{local_rank}", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        elapsed_ms = float(t.item())
+    moves_per_step = R * world * EXCHANGE_INTERVAL
+    value = moves_per_step * args.steps / (elapsed_ms * 1e-3)
+    att, acc = eng.move_stats()
+    accepted_frac = float(acc.sum()) / float(att.sum())
+
+    # end to end through the C-ABI with host buffers: every round uploads the replicas' checkpoint blobs
+    # from pinned host memory, runs the round, and reads blobs + energies back
+    blob_bytes = eng.checkpoint_size() * R
+    host_blob = torch.empty(blob_bytes, dtype=torch.uint8, pin_memory=True)
+    eng.checkpoint_save(host_blob)
+    e2e_steps = max(3, min(args.steps, 10))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        eng.checkpoint_load(host_blob)
+        exchange_round()
+        eng.checkpoint_save(host_blob)
+        energies = eng.energies()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device=f"cuda:{local_rank}", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = moves_per_step * e2e_steps / e2e_s
+    eng.assert_ok()
+
+    if rank == 0:
+        peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        if os.path.exists(peaks_path):
+            peak, peak_src = json.load(open(peaks_path))["hbm_gbs"], "measured (MEASURED_PEAKS.json hbm_gbs)"
+        else:
+            peak, peak_src = HBM_FALLBACK_GBS, "fallback (B200_PROFILING.md)"
+        state_bytes = eng.state_bytes()
+        hbm_bytes = 2.0 * state_bytes * R  # algorithmic: every replica's state is loaded and stored once per launch
+        achieved = hbm_bytes / (kernel_ms * 1e-3) / 1e9
+        moves_per_launch = R * EXCHANGE_INTERVAL
+        smem_gbs = SMEM_BYTES_PER_MOVE * moves_per_launch / (kernel_ms * 1e-3) / 1e9
+        smem_peak = 148 * 128 * (clocks.get("sm_max_mhz") or 1965.0) * 1e6 / 1e9
+        line = {
+            "metric": "attempted MC moves/sec (whole box), snodin PTMC", "value": value, "unit": "attempted MC moves/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(world), "clocks": clocks, "gpu_launches": int(launches),
+            "accepted_moves_per_s": value * accepted_frac,
+            "e2e": {"value": e2e_value, "unit": "attempted MC moves/s", "h2d_bytes_per_step": int(blob_bytes),
+                    "d2h_bytes_per_step": int(blob_bytes + energies.nbytes), "steps": e2e_steps},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                         "kernel": "k_exec_staged<CapsSmall> (run, 100 moves/replica)", "kernel_ms": kernel_ms,
+                         "algorithmic_bytes_per_launch": hbm_bytes, "peak_source": peak_src,
+                         "note": "the path is latency/issue bound on shared memory, not HBM bound (SURVEY.md 8d): see smem",
+                         "smem": {"achieved": smem_gbs, "peak": smem_peak, "unit": "GB/s", "frac": smem_gbs / smem_peak,
+                                  "bytes_per_move": SMEM_BYTES_PER_MOVE, "peak_source": "nominal 148 SM * 128 B/clk * sm_max_mhz"}},
+        }
+        if world == 1 and reference_available() and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline()
+        else:
+            line["cpu_baseline"] = None
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    shutil.rmtree(tmp, ignore_errors=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--replicas-per-gpu", type=int, default=4096)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference_arm(args, rank)
+        return
+    if world != args.gpus:
+        if args.gpus != 1:
+            raise SystemExit(f"--gpus {args.gpus} needs torchrun with {args.gpus} ranks (WORLD_SIZE={world})")
+    run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

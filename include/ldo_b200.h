@@ -161,6 +161,9 @@ int ldo_get_control(ldo_engine* e, int first, int count, int* temp_idx,
 /* Replaces: RandomGens seeding (simulation.cpp:200-203): Philox4x32-10 key = seed, subsequence =
  * first_subsequence + replica. */
 int ldo_seed(ldo_engine* e, unsigned long long seed, unsigned int first_subsequence);
+/* Same with an explicit Philox subsequence per replica ([n_replicas]); used to give a replica the same
+ * stream whichever GPU it lives on. */
+int ldo_seed_subsequences(ldo_engine* e, unsigned long long seed, const unsigned int* subsequences);
 /* Replay mode: serve the replica's draws from a tape (n = 0 detaches). */
 int ldo_attach_tape(ldo_engine* e, int replica, const ldo_tape_draw* draws, long long n);
 int ldo_tape_position(ldo_engine* e, int replica, long long* pos);
@@ -195,6 +198,8 @@ void* ldo_stream(ldo_engine* e);
 
 /* Number of CUDA kernels this engine has launched so far. */
 long long ldo_launch_count(const ldo_engine* e);
+/* Bytes of one replica's persistent state in HBM (what a run launch loads and stores once). */
+unsigned long ldo_state_bytes(const ldo_engine* e);
 
 /* ---- checkpoint / resume ------------------------------------------------------------------------ */
 
@@ -231,21 +236,23 @@ int ldo_center(ldo_engine* e, int centering_domain);
 /* ---- replica exchange ------------------------------------------------------------------------- */
 
 /* Replaces: PTGCMCSimulation::attempt_exchange for the 1-D variants (ptmc_simulation.cpp:360-412)
- * over `n_ladders` independent ladders of `ladder_len` control-variable slots. Replica of slot k of
- * ladder l is global replica index l * ladder_len + k (all GPUs concatenated, this engine holding
- * [global_first, global_first + n_replicas)). Decisions are taken on device from a Philox stream
- * shared by all ranks; accepted swaps relabel control variables (temperature table index and
- * multipliers), configurations never move. `dependent` is the all-gathered [n_global][3 + n_staple_types]
- * array of (enthalpy, bias, stacking, staple counts...) in units of kb T as produced by
- * ldo_exchange_collect; pass NULL when this engine holds every replica. slot_to_replica is the
- * reference's m_q_to_repi, per ladder (the .swp row). attempts/accepts: [n_ladders*(ladder_len-1)]. */
+ * over `n_ladders` independent ladders of `ladder_len` control-variable slots, sharded over `n_ranks`
+ * GPUs: rank g holds replicas [g*S, (g+1)*S) of EVERY ladder (S = ladder_len / n_ranks), replica k of
+ * ladder l at local index l*S + k%S, so every exchange round has pairs that straddle GPUs. Decisions
+ * are taken on device from a Philox stream shared by all ranks (identical on every rank, no
+ * communication); accepted swaps relabel control variables (temperature table index and multipliers),
+ * configurations never move. `dependent` is the all-gathered, rank-major [n_ranks][R][3 + n_staple_types]
+ * array of (enthalpy, bias, stacking, staple counts...) as produced by ldo_exchange_collect on every
+ * rank; pass NULL when n_ranks == 1, or after an NCCL all-gather wrote the engine's own receive buffer
+ * (ldo_exchange_buffers). slot_to_replica is the reference's m_q_to_repi per ladder (the .swp row);
+ * attempts / accepts are [n_ladders][ladder_len - 1]. */
 /* Control-variable ladder (m_control_qs, ptmc_simulation.cpp:341-346): temperature table index and
  * multipliers of every slot; NULL multipliers mean 1. */
 int ldo_set_exchange_ladder(ldo_engine* e, int ladder_len, const int* temp_idx, const double* staple_u_mult,
                             const double* bias_mult, const double* stacking_mult);
 int ldo_exchange_collect(ldo_engine* e, double* dependent_local);
 int ldo_exchange_pt(ldo_engine* e, int variant, long long swap_i, int n_ladders, int ladder_len,
-                    int global_first, int n_global, const double* dependent,
+                    int rank, int n_ranks, const double* dependent,
                     int* slot_to_replica, long long* attempts, long long* accepts);
 /* Device pointers for the NCCL path: local send buffer / full receive buffer of the dependent
  * quantities ([n][3 + n_staple_types] doubles), so the all-gather runs device-to-device. */

@@ -25,11 +25,13 @@ typedef struct ldo_sim ldo_sim;
 const char* ldo_host_last_error(void);
 
 /* Reads `inp_path` (parser.cpp:477-479 format) and builds an engine with `n_replicas` replicas on CUDA
- * device `device`. For the replica-exchange simulation types the replicas form n_replicas / num_reps
- * independent ladders; `global_first` / `n_global` place this engine's replicas inside a multi-GPU
- * ensemble (pass 0 / n_replicas for a single GPU). Every replica starts from the configuration of the
- * system file (or restart_traj_file / restart_step). Returns NULL on error. */
-ldo_sim* ldo_sim_create(const char* inp_path, int n_replicas, int device, int global_first, int n_global);
+ * device `device`. `rank` / `n_ranks` place the engine inside a multi-GPU ensemble (0 / 1 for a single
+ * GPU): independent replicas are simply numbered rank * n_replicas + r; for the replica-exchange types
+ * every rank holds num_reps / n_ranks consecutive slots of every ladder (see ldo_exchange_pt), i.e.
+ * n_replicas / (num_reps / n_ranks) ladders. Every replica starts from the configuration of the system
+ * file (or restart_traj_file / restart_step). With n_ranks > 1 random_seed must be set (all ranks must
+ * share the exchange stream). Returns NULL on error. */
+ldo_sim* ldo_sim_create(const char* inp_path, int n_replicas, int device, int rank, int n_ranks);
 void ldo_sim_destroy(ldo_sim* s);
 ldo_engine* ldo_sim_engine(ldo_sim* s);
 

@@ -14,12 +14,12 @@ ENGINE_SYMBOLS = [
     "ldo_engine_create", "ldo_engine_destroy", "ldo_last_error", "ldo_num_replicas",
     "ldo_set_temperature_tables", "ldo_set_moveset", "ldo_set_order_params", "ldo_set_biases",
     "ldo_set_window", "ldo_set_grid_bias", "ldo_get_grid_visits", "ldo_set_control", "ldo_get_control",
-    "ldo_seed", "ldo_attach_tape", "ldo_tape_position", "ldo_set_state", "ldo_state_capacity",
+    "ldo_seed", "ldo_seed_subsequences", "ldo_attach_tape", "ldo_tape_position", "ldo_set_state", "ldo_state_capacity",
     "ldo_get_state", "ldo_run", "ldo_get_status", "ldo_run_async", "ldo_synchronize", "ldo_stream",
     "ldo_get_energies", "ldo_get_counters", "ldo_get_staple_counts", "ldo_get_order_params",
     "ldo_get_move_stats", "ldo_recompute_energies", "ldo_check_all_constraints", "ldo_center",
     "ldo_set_exchange_ladder", "ldo_exchange_collect", "ldo_exchange_pt", "ldo_exchange_buffers",
-    "ldo_launch_count", "ldo_checkpoint_size", "ldo_checkpoint_save", "ldo_checkpoint_load",
+    "ldo_launch_count", "ldo_state_bytes", "ldo_checkpoint_size", "ldo_checkpoint_save", "ldo_checkpoint_load",
 ]
 HOST_SYMBOLS = [
     "ldo_host_last_error", "ldo_sim_create", "ldo_sim_destroy", "ldo_sim_engine", "ldo_sim_run",
@@ -72,6 +72,7 @@ def load(path=None):
         "ldo_set_control": (i, [vp, i, i, vp, vp, vp, vp]),
         "ldo_get_control": (i, [vp, i, i, vp, vp, vp, vp]),
         "ldo_seed": (i, [vp, C.c_ulonglong, C.c_uint]),
+        "ldo_seed_subsequences": (i, [vp, C.c_ulonglong, vp]),
         "ldo_attach_tape": (i, [vp, i, vp, ll]),
         "ldo_tape_position": (i, [vp, i, vp]),
         "ldo_set_state": (i, [vp, i, i, vp, vp, vp, vp, vp]),
@@ -95,6 +96,7 @@ def load(path=None):
         "ldo_exchange_pt": (i, [vp, i, ll, i, i, i, i, vp, vp, vp, vp]),
         "ldo_exchange_buffers": (i, [vp, i, vp, vp, vp]),
         "ldo_launch_count": (ll, [vp]),
+        "ldo_state_bytes": (C.c_ulong, [vp]),
         "ldo_checkpoint_size": (C.c_ulong, [vp]),
         "ldo_checkpoint_save": (i, [vp, i, i, vp]),
         "ldo_checkpoint_load": (i, [vp, i, i, vp]),
@@ -302,19 +304,29 @@ class Engine:
         self._check(self.L.ldo_checkpoint_load(self.h, first, count, ptr))
 
     # exchange
-    def exchange_collect(self):
+    def exchange_collect(self, to_host=True):
+        if not to_host:
+            self._check(self.L.ldo_exchange_collect(self.h, None))
+            return None
         out = np.zeros((self.R, 3 + self.n_staple_types))
         self._check(self.L.ldo_exchange_collect(self.h, _ptr(out)))
         return out
+
+    def exchange_buffers(self, n_global):
+        send, recv, nq = C.c_void_p(0), C.c_void_p(0), C.c_int(0)
+        self._check(self.L.ldo_exchange_buffers(self.h, n_global, C.byref(send), C.byref(recv), C.byref(nq)))
+        return send.value, recv.value, nq.value
+
+    def state_bytes(self):
+        return self.L.ldo_state_bytes(self.h)
 
 
 class Simulation:
     """A simulation described by a reference-format ``.inp`` file (ldo_sim_create)."""
 
-    def __init__(self, inp_path, n_replicas=1, device=0, global_first=0, n_global=None, lib_path=None):
+    def __init__(self, inp_path, n_replicas=1, device=0, rank=0, n_ranks=1, lib_path=None):
         self.L = load(lib_path)
-        n_global = n_replicas if n_global is None else n_global
-        self.h = self.L.ldo_sim_create(os.fsencode(inp_path), n_replicas, device, global_first, n_global)
+        self.h = self.L.ldo_sim_create(os.fsencode(inp_path), n_replicas, device, rank, n_ranks)
         if not self.h:
             raise LdoError(self.L.ldo_host_last_error().decode())
         self.n_ops = self.L.ldo_sim_num_order_params(self.h)

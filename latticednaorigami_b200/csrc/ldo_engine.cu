@@ -446,7 +446,7 @@ struct ExchangeArgs {
     int variant;
     long long swap_i;
     int n_ladders, ladder_len;
-    int global_first, n_local, n_global;
+    int rank, n_ranks, n_local, n_global;
     int n_staple_types;
     unsigned long long seed;
     const double* dependent; // [n_global][3 + nst]
@@ -466,6 +466,17 @@ struct ExchangeArgs {
 // One thread per ladder: the neighbour tests of one ladder are sequential in the reference only
 // through the shared RNG; here every (swap, ladder, pair) owns a Philox counter, so all ranks
 // reproduce the same decisions without communication.
+// Replica k of ladder l lives on rank k / S (S = ladder_len / n_ranks slots of every ladder per rank) at
+// local index l * S + k % S; the all-gathered buffer is rank-major.
+LDO_HD inline int exchange_rank_of(const ExchangeArgs& x, int k) { return k / (x.ladder_len / x.n_ranks); }
+LDO_HD inline int exchange_local_index(const ExchangeArgs& x, int l, int k) {
+    int S = x.ladder_len / x.n_ranks;
+    return l * S + k % S;
+}
+LDO_HD inline size_t exchange_gathered_index(const ExchangeArgs& x, int l, int k) {
+    return (size_t)exchange_rank_of(x, k) * x.n_local + exchange_local_index(x, l, k);
+}
+
 LDO_HD inline void exchange_ladder(const ExchangeArgs& x, int l) {
     int nq = 3 + x.n_staple_types;
     int* q2r = x.slot_to_replica + (size_t)l * x.ladder_len;
@@ -474,8 +485,8 @@ LDO_HD inline void exchange_ladder(const ExchangeArgs& x, int l) {
         size_t si = (size_t)i;
         x.attempts[(size_t)l * (x.ladder_len - 1) + i]++;
         int rep1 = q2r[i], rep2 = q2r[i + 1];
-        const double* d1 = x.dependent + (size_t)(l * x.ladder_len + rep1) * nq;
-        const double* d2 = x.dependent + (size_t)(l * x.ladder_len + rep2) * nq;
+        const double* d1 = x.dependent + exchange_gathered_index(x, l, rep1) * nq;
+        const double* d2 = x.dependent + exchange_gathered_index(x, l, rep2) * nq;
         double temp1 = x.slot_temp[si], temp2 = x.slot_temp[si + 1];
         double sm1 = x.slot_stacking_mult[si], sm2 = x.slot_stacking_mult[si + 1];
         double um1 = x.slot_staple_u_mult[si], um2 = x.slot_staple_u_mult[si + 1];
@@ -519,9 +530,8 @@ LDO_HD inline void exchange_ladder(const ExchangeArgs& x, int l) {
     }
     // master_send (ptmc_simulation.cpp:212-226): every replica receives the control variables of its slot
     for (int i = 0; i < x.ladder_len; i++) {
-        int g = l * x.ladder_len + q2r[i];
-        int loc = g - x.global_first;
-        if (loc < 0 || loc >= x.n_local) continue;
+        if (exchange_rank_of(x, q2r[i]) != x.rank) continue;
+        int loc = exchange_local_index(x, l, q2r[i]);
         size_t si = (size_t)i;
         Control& c = x.aux[loc].ctl;
         if (x.variant == LDO_PT_ST) {
@@ -583,6 +593,7 @@ struct EngineBase {
     virtual int exchange_buffers(int n_global, void** send, void** recv, int* nq) = 0;
     virtual int alloc_outputs() = 0;
     virtual size_t blob_size() = 0;
+    virtual size_t state_bytes() = 0;
     virtual int get_blobs(int first, int count, void* host) = 0;
     virtual int put_blobs(int first, int count, const void* host) = 0;
     long long launches = 0; // kernels launched so far (ldo_launch_count)
@@ -810,6 +821,7 @@ struct EngineImpl: EngineBase {
 
     // Opaque checkpoint blobs: state + per-replica auxiliary data (RNG, control, biases, statistics)
     size_t blob_size() override { return sizeof(SysState<K>) + sizeof(RepAux); }
+    size_t state_bytes() override { return sizeof(SysState<K>); }
     int get_blobs(int first, int count, void* host) override {
         unsigned char* h = static_cast<unsigned char*>(host);
 #ifdef LDO_HOSTSIM
@@ -1367,6 +1379,21 @@ int ldo_seed(ldo_engine* e, unsigned long long seed, unsigned int first_subseque
     return b->put_aux(0, b->R, aux.data());
 }
 
+int ldo_seed_subsequences(ldo_engine* e, unsigned long long seed, const unsigned int* subsequences) {
+    EngineBase* b = e->b;
+    e->seed = seed;
+    std::vector<RepAux> aux(b->R);
+    if (b->get_aux(0, b->R, aux.data())) return -1;
+    for (int r = 0; r < b->R; r++) {
+        aux[r].rng.key0 = (uint32_t)seed;
+        aux[r].rng.key1 = (uint32_t)(seed >> 32);
+        aux[r].rng.subseq = subsequences[r];
+        aux[r].rng.stream = 0;
+        aux[r].rng.counter = 0;
+    }
+    return b->put_aux(0, b->R, aux.data());
+}
+
 int ldo_attach_tape(ldo_engine* e, int replica, const ldo_tape_draw* draws, long long n) {
     if (replica < 0 || replica >= e->b->R) return e->b->fail("bad replica index");
     return e->b->attach_tape(replica, draws, n);
@@ -1568,13 +1595,14 @@ int ldo_set_exchange_ladder(ldo_engine* e, int ladder_len, const int* temp_idx, 
     return 0;
 }
 
-int ldo_exchange_pt(ldo_engine* e, int variant, long long swap_i, int n_ladders, int ladder_len, int global_first,
-                    int n_global, const double* dependent, int* slot_to_replica, long long* attempts,
+int ldo_exchange_pt(ldo_engine* e, int variant, long long swap_i, int n_ladders, int ladder_len, int rank,
+                    int n_ranks, const double* dependent, int* slot_to_replica, long long* attempts,
                     long long* accepts) {
     EngineBase* b = e->b;
     if ((int)b->ladder_temp_idx.size() != ladder_len) return b->fail("ldo_set_exchange_ladder not called for this ladder length");
-    if (n_ladders * ladder_len != n_global) return b->fail("n_ladders * ladder_len must equal n_global");
-    if (global_first < 0 || global_first + b->R > n_global) return b->fail("bad global replica range");
+    if (n_ranks < 1 || rank < 0 || rank >= n_ranks || ladder_len % n_ranks != 0) return b->fail("ladder_len must be a multiple of n_ranks");
+    if (n_ladders * (ladder_len / n_ranks) != b->R) return b->fail("this rank must hold ladder_len / n_ranks slots of every ladder");
+    int n_global = n_ladders * ladder_len;
     std::vector<double> slot_temp(ladder_len);
     for (int i = 0; i < ladder_len; i++) slot_temp[i] = b->temps[b->ladder_temp_idx[i]];
     ExchangeArgs x;
@@ -1583,7 +1611,8 @@ int ldo_exchange_pt(ldo_engine* e, int variant, long long swap_i, int n_ladders,
     x.swap_i = swap_i;
     x.n_ladders = n_ladders;
     x.ladder_len = ladder_len;
-    x.global_first = global_first;
+    x.rank = rank;
+    x.n_ranks = n_ranks;
     x.n_local = b->R;
     x.n_global = n_global;
     x.n_staple_types = b->shared.sc.n_types - 1;
@@ -1600,6 +1629,7 @@ int ldo_exchange_pt(ldo_engine* e, int variant, long long swap_i, int n_ladders,
 }
 
 long long ldo_launch_count(const ldo_engine* e) { return e->b->launches; }
+unsigned long ldo_state_bytes(const ldo_engine* e) { return e->b->state_bytes(); }
 
 unsigned long ldo_checkpoint_size(const ldo_engine* e) { return e->b->blob_size(); }
 int ldo_checkpoint_save(ldo_engine* e, int first, int count, void* host) {

@@ -35,8 +35,8 @@ struct ldo_sim {
     std::vector<BiasSpec> biases;
     ldo_engine* eng {nullptr};
     int R {0};
-    int global_first {0};
-    int n_global {0};
+    int rank {0};
+    int n_ranks {1};
     long long step {0};
     bool is_pt {false};
     int pt_variant {LDO_PT_T};
@@ -85,8 +85,8 @@ int bias_type_code(std::string const& t) {
 
 std::string replica_filebase(ldo_sim& s, int r) {
     // PTGCMCSimulation appends "-<rank>" (ptmc_simulation.cpp:48); batches of independent replicas do the same
-    if (s.n_global == 1) return s.params.m_output_filebase;
-    return s.params.m_output_filebase + "-" + std::to_string(s.global_first + r);
+    if (s.R * s.n_ranks == 1) return s.params.m_output_filebase;
+    return s.params.m_output_filebase + "-" + std::to_string(s.rank * s.R + r);
 }
 
 void open_output_files(ldo_sim& s) {
@@ -264,7 +264,7 @@ bool simulate(ldo_sim& s, long long steps) {
         for (int r {0}; r != s.R; r++) {
             if (status[r] != 0) {
                 throw OrigamiMisuse {
-                        "replica " + std::to_string(s.global_first + r) + " stopped with status " +
+                        "replica " + std::to_string(s.rank * s.R + r) + " stopped with status " +
                         std::to_string(status[r]) + " (detail " + std::to_string(detail[r]) + ")"};
             }
         }
@@ -307,7 +307,7 @@ extern "C" {
 
 const char* ldo_host_last_error(void) { return g_host_error.c_str(); }
 
-ldo_sim* ldo_sim_create(const char* inp_path, int n_replicas, int device, int global_first, int n_global) {
+ldo_sim* ldo_sim_create(const char* inp_path, int n_replicas, int device, int rank, int n_ranks) {
     std::unique_ptr<ldo_sim> s {new ldo_sim {}};
     try {
         s->params = InputParameters {inp_path};
@@ -315,8 +315,8 @@ ldo_sim* ldo_sim_create(const char* inp_path, int n_replicas, int device, int gl
         s->sysfile.reset(new OrigamiInputFile {p.m_origami_input_filename});
         OrigamiInputFile& sf = *s->sysfile;
         s->R = n_replicas;
-        s->global_first = global_first;
-        s->n_global = n_global > 0 ? n_global : n_replicas;
+        s->rank = rank;
+        s->n_ranks = n_ranks > 0 ? n_ranks : 1;
 
         // potentials (origami_potential.cpp:952-1013)
         if (p.m_binding_pot != "FourBody") throw NotImplemented {p.m_binding_pot + ": No such binding potential"};
@@ -347,11 +347,11 @@ ldo_sim* ldo_sim_create(const char* inp_path, int n_replicas, int device, int gl
             s->pt_variant = st == "t_parallel_tempering" ? LDO_PT_T : st == "ut_parallel_tempering" ? LDO_PT_UT : st == "hut_parallel_tempering" ? LDO_PT_HUT : LDO_PT_ST;
             s->num_reps = p.m_num_reps;
             if (static_cast<int>(p.m_temps.size()) != s->num_reps) throw SimulationMisuse {"temps must list num_reps values"};
-            if (s->n_global % s->num_reps != 0) throw SimulationMisuse {"replica count must be a multiple of num_reps"};
-            if (global_first % s->num_reps != 0 || n_replicas % s->num_reps != 0) {
-                // ladders may also be split across GPUs, but then global_first must still address whole slots
+            if (s->num_reps % s->n_ranks != 0) throw SimulationMisuse {"num_reps must be a multiple of the number of ranks"};
+            if (n_replicas % (s->num_reps / s->n_ranks) != 0) {
+                throw SimulationMisuse {"replicas per rank must be a multiple of num_reps / ranks"};
             }
-            s->n_ladders = s->n_global / s->num_reps;
+            s->n_ladders = n_replicas / (s->num_reps / s->n_ranks);
             s->temps = p.m_temps;
         }
         else {
@@ -452,8 +452,9 @@ ldo_sim* ldo_sim_create(const char* inp_path, int n_replicas, int device, int gl
             std::vector<int> ladder_ti(s->num_reps);
             for (int k {0}; k != s->num_reps; k++) ladder_ti[k] = k;
             s->check(ldo_set_exchange_ladder(s->eng, s->num_reps, ladder_ti.data(), cm.data(), bmm.data(), smm.data()));
+            int slots_per_rank {s->num_reps / s->n_ranks};
             for (int r {0}; r != n_replicas; r++) {
-                int k {(global_first + r) % s->num_reps};
+                int k {s->rank * slots_per_rank + r % slots_per_rank};
                 ti[r] = k;
                 um[r] = cm[k];
                 // OneDPTGCMCSimulation::initialize_control_qs stores the bias multiplier in the wrong
@@ -498,7 +499,19 @@ ldo_sim* ldo_sim_create(const char* inp_path, int n_replicas, int device, int gl
             seed = (static_cast<unsigned long long>(rd()) << 32) ^ rd();
             std::cout << "Truly random seed: " << seed << "\n";
         }
-        s->check(ldo_seed(s->eng, seed, static_cast<unsigned int>(global_first)));
+        if (s->is_pt) {
+            // replica k of ladder l keeps stream l * num_reps + k whichever rank holds it
+            int slots_per_rank {s->num_reps / s->n_ranks};
+            std::vector<unsigned int> sub(n_replicas);
+            for (int r {0}; r != n_replicas; r++) {
+                int l {r / slots_per_rank}, k {s->rank * slots_per_rank + r % slots_per_rank};
+                sub[r] = static_cast<unsigned int>(l * s->num_reps + k);
+            }
+            s->check(ldo_seed_subsequences(s->eng, seed, sub.data()));
+        }
+        else {
+            s->check(ldo_seed(s->eng, seed, static_cast<unsigned int>(s->rank * n_replicas)));
+        }
         s->start = std::chrono::steady_clock::now();
     } catch (std::exception const& e) {
         g_host_error = e.what();
@@ -525,7 +538,7 @@ int ldo_sim_exchange_advance(ldo_sim* s) {
 int ldo_sim_exchange_apply(ldo_sim* s, long long swap_i, const double* dependent_all) {
     try {
         s->check(ldo_exchange_pt(
-                s->eng, s->pt_variant, swap_i, s->n_ladders, s->num_reps, s->global_first, s->n_global,
+                s->eng, s->pt_variant, swap_i, s->n_ladders, s->num_reps, s->rank, s->n_ranks,
                 dependent_all, s->q2r.data(), s->attempts.data(), s->accepts.data()));
     } catch (std::exception const& e) {
         g_host_error = e.what();
@@ -558,7 +571,7 @@ int ldo_sim_run(ldo_sim* s) {
             }
         }
         else if (s->is_pt) {
-            if (s->n_global != s->R) throw SimulationMisuse {"ldo_sim_run drives single-GPU exchange only"};
+            if (s->n_ranks != 1) throw SimulationMisuse {"ldo_sim_run drives single-GPU exchange only"};
             // PTGCMCSimulation::run (ptmc_simulation.cpp:106-150); .swp as :92-104, :315-322
             std::ofstream swp;
             if (!p.m_output_filebase.empty()) {

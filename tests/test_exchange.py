@@ -1,0 +1,116 @@
+"""Replica exchange: the on-device swap rule against a numpy restatement of
+PTGCMCSimulation::calc_acceptance_p (ptmc_simulation.cpp:275-313), and the multi-rank path (split
+ladders + all-gather of the dependent quantities) under the gloo backend with world_size 2, run on the
+host emulation of the device sources (no GPU needed)."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, make_options, write_inp
+from latticednaorigami_b200.binding import Simulation
+
+TEMPS = [330.0, 332.0, 334.0, 336.0]
+
+
+def pt_options(**kw):
+    return make_options("snodin_unbound.json", simulation_type="ut_parallel_tempering", num_reps=len(TEMPS),
+                        temps=TEMPS, chem_pot_mults=[1] * len(TEMPS), bias_mults=[1] * len(TEMPS),
+                        stacking_mults=[1] * len(TEMPS), exchange_interval=20, swaps=4, random_seed=99, **kw)
+
+
+def acceptance_p(t1, t2, d1, d2):
+    """calc_acceptance_p with equal multipliers: only the enthalpy / bias / stacking terms remain."""
+    DB = 1 / t2 - 1 / t1
+    DH = d2[0] * t2 - d1[0] * t1
+    Dst = d2[2] * t2 - d1[2] * t1
+    DBM = 1 / t2 - 1 / t1
+    DBias = d2[1] * t2 - d1[1] * t1
+    return min(1.0, np.exp(DB * (DH + DBias) + DBM * Dst))
+
+
+def test_single_rank_exchange_rule(hostsim_lib, tmp_path):
+    n_ladders = 6
+    sim = Simulation(write_inp(str(tmp_path / "pt.inp"), pt_options()), n_ladders * len(TEMPS), 0, lib_path=hostsim_lib)
+    L = len(TEMPS)
+    q2r_prev = np.tile(np.arange(L, dtype=np.int32), (n_ladders, 1))
+    for swap_i in range(1, 7):
+        assert sim.exchange_advance() == 0
+        dep = sim.engine.exchange_collect().reshape(n_ladders, L, -1)
+        sim.exchange_apply(swap_i)
+        q2r, att, acc = sim.exchange_state(n_ladders, L)
+        ctl = sim.engine.control()["temp_idx"].reshape(n_ladders, L)
+        for l in range(n_ladders):
+            for i in range(swap_i % 2, L - 1, 2):
+                r1, r2 = q2r_prev[l, i], q2r_prev[l, i + 1]
+                p = acceptance_p(TEMPS[i], TEMPS[i + 1], dep[l, r1], dep[l, r2])
+                swapped = q2r[l, i] == r2 and q2r[l, i + 1] == r1
+                if p == 1.0:
+                    assert swapped  # p == 1 accepts without a draw (App. A9)
+                if p < 1e-12:
+                    assert not swapped
+            # control variables follow the permutation: replica q2r[i] now runs at slot i
+            for i in range(L):
+                assert ctl[l, q2r[l, i]] == i
+            assert sorted(q2r[l]) == list(range(L))
+        q2r_prev = q2r.copy()
+        assert att.sum() == sum(len(range(s % 2, L - 1, 2)) for s in range(1, swap_i + 1)) * n_ladders
+    sim.engine.assert_ok()
+    e = sim.engine.energies()[:, 0]
+    re, _ = sim.engine.recompute_energies()
+    assert np.allclose(e, re, rtol=1e-10, atol=1e-9)
+
+
+WORKER = r"""
+import os, sys
+import numpy as np
+import torch
+import torch.distributed as dist
+sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, "tests"))
+from latticednaorigami_b200.binding import Simulation
+rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo", rank=rank, world_size=world)
+n_ladders, L = 5, 4
+S = L // world
+sim = Simulation({inp!r}, n_ladders * S, 0, rank=rank, n_ranks=world, lib_path={lib!r})
+for swap_i in range(1, 6):
+    assert sim.exchange_advance() == 0
+    dep = torch.from_numpy(sim.engine.exchange_collect().copy())
+    gathered = [torch.zeros_like(dep) for _ in range(world)]
+    dist.all_gather(gathered, dep)
+    sim.exchange_apply(swap_i, torch.stack(gathered).numpy())
+q2r, att, acc = sim.exchange_state(n_ladders, L)
+np.savez({out!r} + str(rank), q2r=q2r, att=att, acc=acc, energy=sim.engine.energies(), ctl=sim.engine.control()["temp_idx"])
+dist.destroy_process_group()
+"""
+
+
+def test_two_rank_exchange_matches_single_rank(hostsim_lib, tmp_path):
+    """world_size 2 over gloo: ranks hold half of every ladder, all-gather the dependent quantities and
+    must take exactly the decisions of a single rank holding everything."""
+    inp = write_inp(str(tmp_path / "pt.inp"), pt_options())
+    n_ladders, L = 5, len(TEMPS)
+    one = Simulation(inp, n_ladders * L, 0, lib_path=hostsim_lib)
+    for swap_i in range(1, 6):
+        assert one.exchange_advance() == 0
+        one.exchange_apply(swap_i)
+    q2r1, att1, acc1 = one.exchange_state(n_ladders, L)
+    e1 = one.engine.energies().reshape(n_ladders, L, 5)
+
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER.format(root=ROOT, inp=inp, lib=hostsim_lib, out=str(tmp_path / "out")))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29631", WORLD_SIZE="2")
+    procs = [subprocess.Popen([sys.executable, str(script)], env=dict(env, RANK=str(r))) for r in range(2)]
+    for p in procs:
+        assert p.wait(timeout=600) == 0
+    outs = [np.load(str(tmp_path / f"out{r}.npz")) for r in range(2)]
+    for o in outs:
+        assert np.array_equal(o["q2r"], q2r1) and np.array_equal(o["att"], att1) and np.array_equal(o["acc"], acc1)
+    # same trajectories: replica k of ladder l lives on rank k // 2 at local index l * 2 + k % 2
+    S = L // 2
+    for l in range(n_ladders):
+        for k in range(L):
+            got = outs[k // S]["energy"][l * S + k % S]
+            assert np.array_equal(got, e1[l, k]), (l, k)

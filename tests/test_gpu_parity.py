@@ -32,7 +32,9 @@ def test_energy_of_reference_configurations(tmp_path, key):
         assert abs(e[r, 1] - golden["split"]["enthalpy"]) <= 1e-12 * max(1.0, abs(golden["split"]["enthalpy"]))
         assert abs(e[r, 2] - golden["split"]["entropy"]) <= 1e-12 * max(1.0, abs(golden["split"]["entropy"]))
         assert abs(e[r, 3] - golden["split"]["stacking"]) <= 1e-9 * max(1.0, abs(golden["split"]["stacking"]))
-    assert list(sim.engine.counters()[0]) == list(golden["counters"].values())
+    keys = ["staples", "domains", "bound_pairs", "fully_bound_pairs", "self_bound_pairs", "misbound_pairs",
+            "stacked_pairs", "unassigned", "current_c_i"]
+    assert [int(x) for x in sim.engine.counters()[0]] == [golden["counters"][k] for k in keys]
 
 
 def test_live_replay_against_oracle(oracle, tmp_path):
