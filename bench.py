@@ -84,7 +84,7 @@ def reference_available():
     return os.path.exists(os.path.join(ROOT, "oracle", "_ref", "latticeDNAOrigami"))
 
 
-def cpu_baseline(moves_per_proc=12000):
+def cpu_baseline(moves_per_proc=100000):
     cores = os.cpu_count() or 1
     with tempfile.TemporaryDirectory(prefix="ldo_ref_") as tmp:
         wall = reference_sample(cores, moves_per_proc, tmp, 1)
@@ -101,7 +101,7 @@ def run_reference_arm(args, rank):
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/latticeDNAOrigami not built (needs /root/reference at build time)"}))
         return
     cores = os.cpu_count() or 1
-    moves = 6000
+    moves = 30000
     with tempfile.TemporaryDirectory(prefix="ldo_ref_") as tmp:
         for w in range(args.warmup):
             reference_sample(cores, 500, tmp, 100 + w)

@@ -64,7 +64,10 @@ static int chk(cudaError_t e) {
 }
 static int dev_malloc(void** p, size_t n) {
     if (chk(cudaMalloc(p, n ? n : 1))) return -1;
-    return chk(cudaMemset(*p, 0, n ? n : 1));
+    // the engine's stream is non-blocking with respect to the legacy stream this memset runs on:
+    // wait for it, or a later copy on the engine stream could be overwritten by the zero fill
+    if (chk(cudaMemset(*p, 0, n ? n : 1))) return -1;
+    return chk(cudaDeviceSynchronize());
 }
 static void dev_free(void* p) { cudaFree(p); }
 static int dev_h2d(void* d, const void* h, size_t n, dev_stream_t s) {
@@ -1235,8 +1238,9 @@ int ldo_set_moveset(ldo_engine* e, int n, const ldo_movetype_desc* mts, int allo
             em_off += nst;
         }
         if ((md.type == MT_CTRG_SCAFFOLD_REGROWTH || md.type == MT_CTRG_JUMP_SCAFFOLD_REGROWTH) &&
-            (md.max_c_attempts < 1 || md.max_c_attempts > 36 || md.max_regrowth < 2)) {
-            return b->fail("CTRG options out of range (max_c_attempts 1..36, max_regrowth >= 2)");
+            (md.max_c_attempts < 1 || md.max_c_attempts > 36 || md.max_regrowth < 2 || md.max_num_recoils < 0 ||
+             md.max_num_recoils >= LDO_RG_OWN_SLOTS)) {
+            return b->fail("CTRG options out of range (max_c_attempts 1..36, max_regrowth >= 2, max_num_recoils 0..3)");
         }
     }
     return b->push_shared();
@@ -1375,6 +1379,7 @@ int ldo_seed(ldo_engine* e, unsigned long long seed, unsigned int first_subseque
         aux[r].rng.subseq = first_subsequence + (uint32_t)r;
         aux[r].rng.stream = 0;
         aux[r].rng.counter = 0;
+        aux[r].rng.buf_n = 0;
     }
     return b->put_aux(0, b->R, aux.data());
 }
@@ -1390,6 +1395,7 @@ int ldo_seed_subsequences(ldo_engine* e, unsigned long long seed, const unsigned
         aux[r].rng.subseq = subsequences[r];
         aux[r].rng.stream = 0;
         aux[r].rng.counter = 0;
+        aux[r].rng.buf_n = 0;
     }
     return b->put_aux(0, b->R, aux.data());
 }

@@ -42,6 +42,9 @@ struct Rng {
     uint32_t subseq;
     uint32_t stream;
     unsigned long long counter;
+    // unconsumed words of the last Philox block (one block = 4 words: a real takes 2, an int 1)
+    uint32_t buf[4];
+    int buf_n;
 };
 
 LDO_HD inline void philox_round(uint32_t& c0, uint32_t& c1, uint32_t& c2, uint32_t& c3, uint32_t k0, uint32_t k1) {
@@ -157,6 +160,43 @@ struct MoveSet {
     double exchange_mults[LDO_MAX_TYPES];
 };
 
+// 36-bit configuration masks: population count and position of the n-th (0-based) set bit
+LDO_HD inline int popc36(unsigned long long m) {
+#if defined(__CUDA_ARCH__)
+    return __popcll(m);
+#else
+    int n = 0;
+    for (; m; m &= m - 1) n++;
+    return n;
+#endif
+}
+LDO_HD inline int nth_set_bit36(unsigned long long m, int n) {
+#if defined(__CUDA_ARCH__)
+    unsigned lo = (unsigned)m, hi = (unsigned)(m >> 32);
+    int nlo = __popc(lo);
+    if (n < nlo) return (int)__fns(lo, 0, n + 1);
+    return 32 + (int)__fns(hi, 0, n - nlo + 1);
+#else
+    for (int k = 0; k < n; k++) m &= m - 1;
+    int i = 0;
+    while (i < 36 && !((m >> i) & 1ull)) i++;
+    return i;
+#endif
+}
+
+// Open probabilities of the 36 trial configurations of one regrown domain, stored per neighbour
+// site of the reference domain (the 6 orientations of a site share the lattice lookup):
+//   kind 0: site blocked or binding violates a constraint -> p = 0 for all orientations
+//   kind 1: empty site -> p (1, or 0 when no ideal walk remains) for every orientation
+//   kind 2: site holds an unbound domain -> p for the single opposing orientation `ore`, else 0
+struct RgSlot {
+    double p[6];
+    uint8_t kind[6];
+    int8_t ore[6];
+};
+#define LDO_RG_OWN_SLOTS 4
+#define LDO_RG_SLOTS (LDO_RG_OWN_SLOTS + 6)
+
 // ---------------------------------------------------------------------------------------------
 // Per-move scratch (MCMovetype / RegrowthMCMovetype / CBMCMovetype / CTRGRegrowthMCMovetype members)
 // and Constraintpoints (top_constraint_points.hpp:112-288), fixed capacity
@@ -231,6 +271,9 @@ struct MoveScratch {
     short stems[K::D + 1];
     short stem_queue[4 * K::D + 8];
 
+    // CTRG trial-configuration caches: own[level % 4] and feeler memo keyed by the parent's site
+    RgSlot slots[LDO_RG_SLOTS];
+
     // lane-parallel candidate evaluation results (6 neighbour sites)
     double site_w[8];
     int site_o[8];
@@ -264,8 +307,17 @@ struct Engine {
     unsigned long long avail;
     int max_recoils, max_c_attempts;
     double delta_e, weight, weight_new;
+    // slot holding the current domain's trial probabilities; feeler memo bookkeeping
+    int cur_slot, memo_level, memo_key, memo_mask, last_pc, last_kind;
 
     // ---- RNG (random_gens.cpp:29-49) ----
+    LDO_HD uint32_t next_word() {
+        if (rng->buf_n == 0) {
+            philox4x32_10(*rng, rng->counter++, rng->buf);
+            rng->buf_n = 4;
+        }
+        return rng->buf[--rng->buf_n];
+    }
     LDO_HDN double uniform_real() {
         if (rng->tape != nullptr) {
             if (rng->tape_pos >= rng->tape_len) {
@@ -280,9 +332,9 @@ struct Engine {
             rng->tape_pos++;
             return t.real;
         }
-        uint32_t o[4];
-        philox4x32_10(*rng, rng->counter++, o);
-        unsigned long long u = ((unsigned long long)o[0] << 32) | o[1];
+        uint32_t hi = next_word();
+        uint32_t lo = next_word();
+        unsigned long long u = ((unsigned long long)hi << 32) | lo;
         return (double)(u >> 11) * (1.0 / 9007199254740992.0);
     }
     LDO_HDN int uniform_int(int lo, int hi) {
@@ -302,19 +354,12 @@ struct Engine {
         uint32_t n = (uint32_t)(hi - lo) + 1u;
         if (n == 0) return lo; // full 32-bit range never occurs on this path
         // Lemire's nearly-divisionless unbiased bounded integer
-        uint32_t o[4];
-        philox4x32_10(*rng, rng->counter++, o);
-        unsigned long long mm = (unsigned long long)o[0] * n;
+        unsigned long long mm = (unsigned long long)next_word() * n;
         uint32_t l = (uint32_t)mm;
         if (l < n) {
             uint32_t t = (0u - n) % n;
-            int w = 1;
             while (l < t) {
-                if (w == 4) {
-                    philox4x32_10(*rng, rng->counter++, o);
-                    w = 0;
-                }
-                mm = (unsigned long long)o[w++] * n;
+                mm = (unsigned long long)next_word() * n;
                 l = (uint32_t)mm;
             }
         }
@@ -1406,7 +1451,66 @@ struct Engine {
             d_max_c_attempts = max_c_attempts;
             avail = all_cis();
             ref_d = sys.step(d, -dir);
+            rg_acquire_slot();
         }
+    }
+    // Chooses and fills the trial-probability cache of the current domain: the feeler memo when this is
+    // the first feeler level of calc_weights and the parent sits on an empty site (the feeler's results
+    // do not depend on the parent's orientation then), else the level's own slot.
+    LDO_HD void rg_acquire_slot() {
+        bool use_memo = di == memo_level && memo_key >= 0;
+        if (use_memo) {
+            // the memo is keyed by the parent's site only: unusable when the current domain could bind
+            // to the (unbound) parent itself, because that depends on the parent's orientation
+            V3 dq = rec_pos(sys.s->dom[m->regrow[di - 1]]) - rec_pos(sys.s->dom[ref_d]);
+            if (abssum(dq) == 1) use_memo = false;
+        }
+        if (use_memo) {
+            cur_slot = LDO_RG_OWN_SLOTS + memo_key;
+            if (!((memo_mask >> memo_key) & 1)) {
+                rg_compute_slot(cur_slot);
+                memo_mask |= 1 << memo_key;
+            }
+        }
+        else {
+            cur_slot = di & (LDO_RG_OWN_SLOTS - 1);
+            rg_compute_slot(cur_slot);
+        }
+    }
+    // Evaluates the six neighbour sites of the reference domain for the current domain, one site per
+    // lane, read-only (calc_p_config_open, rg:315-343, for all 36 configurations at once).
+    LDO_HDN void rg_compute_slot(int slot) {
+        RgSlot& sl = m->slots[slot];
+        V3 refp = rec_pos(sys.s->dom[ref_d]);
+        for (int k = LDO_LANE; k < 6; k += LDO_NLANES) {
+            V3 r = refp + ore_vec(k);
+            int j = sys.occupant(r);
+            int kind = 0, o = ORE_ZERO;
+            double pv = 0;
+            if (j < 0) {
+                kind = 1;
+                pv = cp_walks_remain(d, r) ? 1.0 : 0.0;
+            }
+            else if (sys.s->dom[j].state == ST_UNBOUND && sys.s->dom[j].ore < 6) {
+                o = sys.s->dom[j].ore ^ 1;
+                int ns, partner;
+                DeltaConfig dc = sys.eval_place(d, r, o, &ns, &partner);
+                if (!dc.violated && cp_walks_remain(d, r)) {
+                    bool same_chain = sys.chain(j) == sys.chain(d);
+                    if (same_chain || stemd || cp_endpoint_reached(d, r)) {
+                        kind = 2;
+                        pv = fmin(1.0, exp(-dc.e));
+                    }
+                }
+            }
+            sl.kind[k] = (uint8_t)kind;
+            sl.ore[k] = (int8_t)o;
+            sl.p[k] = pv;
+#if defined(LDO_DEBUG_SLOTS) && !defined(__CUDA_ARCH__)
+            printf("  compute slot=%d di=%d d=%d ref_d=%d k=%d r=(%d %d %d) j=%d kind=%d o=%d p=%g n_ep=%d\n", slot, di, d, ref_d, k, r.x, r.y, r.z, j, kind, o, pv, m->n_ep);
+#endif
+        }
+        LDO_SYNCWARP();
     }
     // prepare_for_regrowth (rg:264-286)
     LDO_HDN double rg_prepare_for_regrowth() {
@@ -1428,28 +1532,49 @@ struct Engine {
             c_attempts = m->c_attempts_q[di];
             avail = m->avail_q[di];
             ref_d = sys.step(d, -dir);
+            cur_slot = di & (LDO_RG_OWN_SLOTS - 1);
+            rg_compute_slot(cur_slot);
         }
         return de;
     }
-    // select_trial_config (rg:297-313): k-th remaining entry of the ordered list
-    LDO_HDN void rg_select_trial_config(V3& p, int& o) {
+    // select_trial_config + calc_p_config_open (rg:297-343): draws the k-th remaining entry of the
+    // ordered configuration list and returns its open probability from the current slot
+    LDO_HDN double rg_trial(V3& p, int& o) {
         if (stemd) {
             const DomRec& r = sys.s->dom[ref_d];
             p = rec_pos(r);
             o = r.ore < 6 ? (r.ore ^ 1) : r.ore;
-            return;
+            last_pc = -1;
+            last_kind = 0;
+            return rg_calc_p_config_open(p, o);
         }
-        int n_avail = 0;
-        for (unsigned long long t = avail; t; t &= t - 1) n_avail++;
+        int n_avail = popc36(avail);
         int ci = uniform_int(0, n_avail - 1);
-        unsigned long long t = avail;
-        for (int k = 0; k < ci; k++) t &= t - 1;
-        int i = 0;
-        while (!((t >> i) & 1ull) && i < 36) i++;
+        int i = nth_set_bit36(avail, ci);
         avail &= ~(1ull << i);
         // m_all_configs = all_pairs(vectors): position-major, orientation-minor (utility.hpp:167-177)
-        p = ore_vec(i / 6) + rec_pos(sys.s->dom[ref_d]);
-        o = i % 6;
+        int pc = i / 6;
+        o = i - 6 * pc;
+        p = ore_vec(pc) + rec_pos(sys.s->dom[ref_d]);
+        const RgSlot& sl = m->slots[cur_slot];
+        int kind = sl.kind[pc];
+        last_pc = pc;
+        last_kind = kind;
+        double pv = 0;
+        if (kind == 1) pv = sl.p[pc];
+        else if (kind == 2 && o == sl.ore[pc]) pv = sl.p[pc];
+#if defined(LDO_DEBUG_SLOTS) && !defined(__CUDA_ARCH__)
+        {
+            DomRec saved = sys.s->dom[d];
+            double pref = rg_calc_p_config_open(p, o);
+            sys.s->dom[d] = saved;
+            if (pref != pv) {
+                for (int q = 0; q < m->n_ep; q++) printf("   ep chain=%d seg=%d d=%d pos=(%d %d %d)\n", m->ep_chain[q], m->ep_seg[q], m->ep_d[q], m->ep_pos[q][0], m->ep_pos[q][1], m->ep_pos[q][2]);
+                printf("SLOT MISMATCH p=(%d %d %d) di=%d d=%d ci=%d pc=%d o=%d kind=%d slot=%d pv=%g ref=%g stemd=%d memo_level=%d memo_key=%d\n", p.x, p.y, p.z, di, d, i, pc, o, kind, cur_slot, pv, pref, stemd, memo_level, memo_key);
+            }
+        }
+#endif
+        return pv;
     }
     // calc_p_config_open (rg:315-343)
     LDO_HDN double rg_calc_p_config_open(V3 p, int o) {
@@ -1493,8 +1618,7 @@ struct Engine {
             bool c_open = false;
             while (!c_open && c_attempts != d_max_c_attempts) {
                 c_attempts++;
-                rg_select_trial_config(p, o);
-                p_c_open = rg_calc_p_config_open(p, o);
+                p_c_open = rg_trial(p, o);
                 c_open = rg_test_config_open(p_c_open);
             }
             if (c_open) {
@@ -1531,8 +1655,7 @@ struct Engine {
             double p_c_open;
             while (!c_open && c_attempts != d_max_c_attempts) {
                 c_attempts++;
-                rg_select_trial_config(p, o);
-                p_c_open = rg_calc_p_config_open(p, o);
+                p_c_open = rg_trial(p, o);
                 c_open = rg_test_config_open(p_c_open);
             }
             if (c_open) {
@@ -1582,23 +1705,30 @@ struct Engine {
                 ref_d = sys.step(d, -dir);
                 int catt = m->c_attempts_wq[di];
                 avail = m->avail_wq[di];
+                memo_level = -1;
+                memo_mask = 0;
+                cur_slot = di & (LDO_RG_OWN_SLOTS - 1);
+                if (catt != max_c_attempts) rg_compute_slot(cur_slot);
                 while (catt != max_c_attempts) {
                     catt++;
                     V3 p;
                     int o;
-                    rg_select_trial_config(p, o);
-                    double p_c_open = rg_calc_p_config_open(p, o);
+                    double p_c_open = rg_trial(p, o);
                     if (rg_test_config_open(p_c_open)) {
                         sys.set_checked_domain_config(d, p, o);
                         cp_update_endpoints(d);
                         eq_push_erased();
-                        int dir_s = dir, ref_s = ref_d, stem_s = stemd;
+                        int dir_s = dir, ref_s = ref_d, stem_s = stemd, slot_s = cur_slot;
                         unsigned long long avail_s = avail;
+                        memo_level = di + 1;
+                        memo_key = last_kind == 1 ? last_pc : -1;
                         avail_cs += rg_test_config_avail() ? 1 : 0;
+                        memo_key = -1;
                         avail = avail_s;
                         stemd = stem_s;
                         ref_d = ref_s;
                         dir = dir_s;
+                        cur_slot = slot_s;
                         sys.unassign_domain(d);
                         rg_restore_endpoints();
                     }
@@ -1702,6 +1832,10 @@ struct Engine {
         weight_new = 1;
         max_recoils = md.max_num_recoils;
         max_c_attempts = md.max_c_attempts;
+        memo_level = -1;
+        memo_key = -1;
+        memo_mask = 0;
+        cur_slot = 0;
         m->eq_depth = 0;
         m->eq_npos = 0;
     }
