@@ -48,7 +48,7 @@ _libs = {}
 
 def load(path=None):
     """Load the CUDA library. Fails loudly when it is missing: there is no CPU path."""
-    path = path or LIB_PATH
+    path = path or os.environ.get("LDO_B200_LIB") or LIB_PATH
     if path in _libs:
         return _libs[path]
     if not os.path.exists(path):

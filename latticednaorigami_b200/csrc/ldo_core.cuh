@@ -174,6 +174,23 @@ struct SysConst {
     short idents[LDO_MAX_IDENTS]; // flattened m_identities
 };
 
+#if defined(__CUDACC__)
+// Device copy of the system description: constant memory, read with uniform addresses by every lane
+__constant__ SysConst ldo_c_sc;
+#endif
+
+// Generic pointers that are known to address shared memory (staged replicas) let the compiler emit
+// LDS/STS instead of generic loads and stores
+#if defined(__CUDA_ARCH__)
+#if defined(LDO_ENABLE_ASSUME_SHARED)
+#define LDO_ASSUME_SHARED(K, ptr) do { if (K::STAGED) __builtin_assume(__isShared(ptr)); } while (0)
+#else
+#define LDO_ASSUME_SHARED(K, ptr) ((void)0)
+#endif
+#else
+#define LDO_ASSUME_SHARED(K, ptr) ((void)0)
+#endif
+
 // Per-temperature energy tables (origami_potential.cpp:1057-1221); shared by replicas at that T
 struct TempTables {
     double temp;
@@ -192,8 +209,12 @@ struct Control {
     double stacking_mult;
 };
 
-template <int D_, int C_, int HBITS_, int T_>
+template <int D_, int C_, int HBITS_, int T_, bool STAGED_, int LV_, int E_, int SEG_>
 struct Caps {
+    static const bool STAGED = STAGED_; // replica state lives in shared memory during a launch
+    static const int LV = LV_; // domains regrown by one move (regrowth levels)
+    static const int E = E_; // active endpoints of one move
+    static const int SEG = SEG_; // scaffold segments of one move
     static const int D = D_; // domain slots
     static const int C = C_; // chain slots (scaffold + staples)
     static const int T = T_; // chain identities (scaffold + staple types)
@@ -260,6 +281,19 @@ struct System {
     int od, oj;
     DomRec orec;
 
+    LDO_HD SysState<K>* S() const {
+        SysState<K>* p = s;
+        LDO_ASSUME_SHARED(K, p);
+        return p;
+    }
+    LDO_HD const SysConst& SC() const {
+#if defined(__CUDA_ARCH__)
+        return ldo_c_sc;
+#else
+        return *sc;
+#endif
+    }
+
     LDO_HD void init(SysState<K>* s_, const SysConst* sc_, const TempTables& tt_) {
         s = s_;
         sc = sc_;
@@ -268,49 +302,49 @@ struct System {
         oj = -1;
     }
 
-    LDO_HD void fail(int code, int detail = 0) {
-        if (s->status == LDO_OK) {
-            s->status = code;
-            s->status_detail = detail;
+    LDO_HDN void fail(int code, int detail = 0) {
+        if (S()->status == LDO_OK) {
+            S()->status = code;
+            S()->status_detail = detail;
         }
     }
 
     // ---- accessors (overlay aware) ----
     LDO_HD V3 pos(int d) const {
         if (d == od) return v3(orec.x, orec.y, orec.z);
-        const DomRec& r = s->dom[d];
+        const DomRec& r = S()->dom[d];
         return v3(r.x, r.y, r.z);
     }
     LDO_HD V3 ore(int d) const {
         if (d == od) return ore_vec(orec.ore);
-        return ore_vec(s->dom[d].ore);
+        return ore_vec(S()->dom[d].ore);
     }
     LDO_HD int state(int d) const {
         if (d == od || d == oj) return orec.state;
-        return s->dom[d].state;
+        return S()->dom[d].state;
     }
     LDO_HD int bound(int d) const {
         if (d == od) return oj;
         if (d == oj) return od;
-        return s->bound[d];
+        return S()->bound[d];
     }
-    LDO_HD int chain(int d) const { return s->dchain[d]; }
-    LDO_HD int dindex(int d) const { return s->dindex[d]; }
-    LDO_HD int ident(int d) const { return s->ident[d]; }
-    LDO_HD int chain_base(int c) const { return c == 0 ? 0 : sc->n_scaffold + (c - 1) * sc->lmax; }
+    LDO_HD int chain(int d) const { return S()->dchain[d]; }
+    LDO_HD int dindex(int d) const { return S()->dindex[d]; }
+    LDO_HD int ident(int d) const { return S()->ident[d]; }
+    LDO_HD int chain_base(int c) const { return c == 0 ? 0 : SC().n_scaffold + (c - 1) * SC().lmax; }
     LDO_HD int dom_id(int c, int i) const { return chain_base(c) + i; }
 
     // Domain::m_forward_domain / m_backward_domain (domain.hpp:30-31; cyclic scaffold origami_system.cpp:687-692)
     LDO_HD int fwd(int d) const {
-        int c = s->dchain[d], i = s->dindex[d], L = s->chain_len[c];
+        int c = S()->dchain[d], i = S()->dindex[d], L = S()->chain_len[c];
         if (i + 1 < L) return d + 1;
-        if (c == 0 && sc->cyclic) return chain_base(0);
+        if (c == 0 && SC().cyclic) return chain_base(0);
         return -1;
     }
     LDO_HD int bac(int d) const {
-        int c = s->dchain[d], i = s->dindex[d];
+        int c = S()->dchain[d], i = S()->dindex[d];
         if (i > 0) return d - 1;
-        if (c == 0 && sc->cyclic) return chain_base(0) + s->chain_len[0] - 1;
+        if (c == 0 && SC().cyclic) return chain_base(0) + S()->chain_len[0] - 1;
         return -1;
     }
     // Domain::operator+ (domain.cpp:9-31)
@@ -328,13 +362,13 @@ struct System {
 
     // ---- energy tables ----
     LDO_HD int pair_index(int a, int b) const {
-        int n = sc->n_ident;
+        int n = SC().n_ident;
         return (a + n) * (2 * n + 1) + (b + n);
     }
     LDO_HD double hyb_energy(int di, int dj) const { return tt.hyb_energy[pair_index(ident(di), ident(dj))]; }
     LDO_HD double hyb_enthalpy(int di, int dj) const { return tt.hyb_enthalpy[pair_index(ident(di), ident(dj))]; }
     LDO_HD double hyb_entropy(int di, int dj) const { return tt.hyb_entropy[pair_index(ident(di), ident(dj))]; }
-    LDO_HD double stack_energy() const { return s->stack_e; }
+    LDO_HD double stack_energy() const { return S()->stack_e; }
 
     // ---- occupancy table ----
     // Returns the occupant domain id at p, or -1 (origami_system.cpp:193-202, 130-132)
@@ -342,8 +376,8 @@ struct System {
         uint32_t key = pack_pos(p);
         uint32_t i = hash_slot<K>(key);
         for (int n = 0; n < K::H; n++) {
-            uint32_t k = s->hkey[i];
-            if (k == key) return s->hval[i];
+            uint32_t k = S()->hkey[i];
+            if (k == key) return S()->hval[i];
             if (k == LDO_HEMPTY) return -1;
             i = (i + 1) & (K::H - 1);
         }
@@ -356,10 +390,10 @@ struct System {
         uint32_t key = pack_pos(p);
         uint32_t i = hash_slot<K>(key);
         for (int n = 0; n < K::H; n++) {
-            uint32_t k = s->hkey[i];
+            uint32_t k = S()->hkey[i];
             if (k == key || k == LDO_HEMPTY) {
-                s->hkey[i] = key;
-                s->hval[i] = (short)d;
+                S()->hkey[i] = key;
+                S()->hval[i] = (short)d;
                 return;
             }
             i = (i + 1) & (K::H - 1);
@@ -371,41 +405,41 @@ struct System {
         uint32_t key = pack_pos(p);
         uint32_t i = hash_slot<K>(key);
         int n = 0;
-        while (s->hkey[i] != key) {
-            if (s->hkey[i] == LDO_HEMPTY || ++n == K::H) return;
+        while (S()->hkey[i] != key) {
+            if (S()->hkey[i] == LDO_HEMPTY || ++n == K::H) return;
             i = (i + 1) & (K::H - 1);
         }
         uint32_t j = i;
         for (;;) {
             j = (j + 1) & (K::H - 1);
-            uint32_t kj = s->hkey[j];
+            uint32_t kj = S()->hkey[j];
             if (kj == LDO_HEMPTY) break;
             uint32_t h = hash_slot<K>(kj);
             // move kj into the hole i unless its home slot lies cyclically in (i, j]
             bool home_between = (i <= j) ? (i < h && h <= j) : (i < h || h <= j);
             if (!home_between) {
-                s->hkey[i] = kj;
-                s->hval[i] = s->hval[j];
+                S()->hkey[i] = kj;
+                S()->hval[i] = S()->hval[j];
                 i = j;
             }
         }
-        s->hkey[i] = LDO_HEMPTY;
+        S()->hkey[i] = LDO_HEMPTY;
     }
     LDO_HD void table_clear() {
-        for (int i = 0; i < K::H; i++) s->hkey[i] = LDO_HEMPTY;
+        for (int i = 0; i < K::H; i++) S()->hkey[i] = LDO_HEMPTY;
     }
 
     // ---- domain constraint checkers (domain.cpp:33-118) ----
     LDO_HD bool check_twist(int d1, V3 ndr, int d2) const {
         V3 o1 = ore(d1);
-        V3 rot = sc->domain_type == DOMAIN_HALFTURN ? rotate_half(o1, ndr) : rotate_turns(o1, ndr, -1);
+        V3 rot = SC().domain_type == DOMAIN_HALFTURN ? rotate_half(o1, ndr) : rotate_turns(o1, ndr, -1);
         return rot == ore(d2);
     }
     LDO_HD bool check_kink(int d1, V3 ndr, int d2) const {
         V3 o1 = ore(d1), o2 = ore(d2);
         if (ndr == -o1) return false;
         if (ndr == o1) {
-            if (sc->domain_type == DOMAIN_HALFTURN) {
+            if (SC().domain_type == DOMAIN_HALFTURN) {
                 if (o2 == -o1) return false;
             }
             else {
@@ -417,7 +451,7 @@ struct System {
         return true;
     }
     LDO_HD bool check_junction_constraint(int j1, int j2, int k1, int k2) const {
-        if (sc->domain_type == DOMAIN_HALFTURN) return true;
+        if (SC().domain_type == DOMAIN_HALFTURN) return true;
         V3 ndr_k1 = pos(k2) - pos(k1);
         if (ndr_k1 == ore(k1)) {
             V3 ndr_1 = pos(j2) - pos(j1);
@@ -962,7 +996,7 @@ struct System {
         }
         else {
             // origami_potential.cpp:938-950
-            if (sc->misbinding_pot == MISBIND_DISALLOWED || !opposing) {
+            if (SC().misbinding_pot == MISBIND_DISALLOWED || !opposing) {
                 dc.violated = true;
                 return dc;
             }
@@ -987,14 +1021,14 @@ struct System {
             *new_state = ST_UNBOUND;
             return dc;
         }
-        int sj = s->dom[j].state;
+        int sj = S()->dom[j].state;
         if (sj != ST_UNBOUND) {
             dc.violated = true;
             *new_state = ST_UNASSIGNED;
             return dc;
         }
         *partner = j;
-        bool comp = s->ident[d] == -s->ident[j];
+        bool comp = S()->ident[d] == -S()->ident[j];
         od = d;
         oj = j;
         orec.x = (short)p.x;
@@ -1006,9 +1040,9 @@ struct System {
         dc = bind_domain(d);
         od = -1;
         oj = -1;
-        if (sc->apply_mean_field_cor && !dc.violated && comp) {
+        if (SC().apply_mean_field_cor && !dc.violated && comp) {
             // origami_system.cpp:858-868 (counter already incremented in the reference at this point)
-            int nfb = s->num_fully_bound_pairs + 1;
+            int nfb = S()->num_fully_bound_pairs + 1;
             if (nfb == 1) dc.e += 2 * log(6.0);
             else if (nfb == 2) dc.e += log(3.0);
         }
@@ -1017,7 +1051,7 @@ struct System {
 
     // ---- mutation ----
     LDO_HD void write_dom(int d, V3 p, int o) {
-        DomRec& r = s->dom[d];
+        DomRec& r = S()->dom[d];
         r.x = (short)p.x;
         r.y = (short)p.y;
         r.z = (short)p.z;
@@ -1029,34 +1063,34 @@ struct System {
         write_dom(d, p, o);
         int j = occupant(p);
         if (j < 0) {
-            s->dom[d].state = ST_UNBOUND;
-            s->bound[d] = -1;
+            S()->dom[d].state = ST_UNBOUND;
+            S()->bound[d] = -1;
             table_put(p, d);
             return;
         }
-        if (s->dom[j].state != ST_UNBOUND) {
+        if (S()->dom[j].state != ST_UNBOUND) {
             fail(LDO_ERR_BIND_BOUND, d);
             return;
         }
-        s->num_bound_pairs += 1;
+        S()->num_bound_pairs += 1;
         uint8_t ns;
-        if (s->ident[d] == -s->ident[j]) {
+        if (S()->ident[d] == -S()->ident[j]) {
             ns = ST_BOUND;
-            s->num_fully_bound_pairs += 1;
+            S()->num_fully_bound_pairs += 1;
         }
         else {
-            if (s->dchain[d] == s->dchain[j]) s->num_self_bound_pairs += 1;
+            if (S()->dchain[d] == S()->dchain[j]) S()->num_self_bound_pairs += 1;
             ns = ST_MISBOUND;
         }
-        s->dom[d].state = ns;
-        s->dom[j].state = ns;
-        s->bound[d] = (short)j;
-        s->bound[j] = (short)d;
+        S()->dom[d].state = ns;
+        S()->dom[j].state = ns;
+        S()->bound[d] = (short)j;
+        S()->bound[j] = (short)d;
     }
 
     // OrigamiSystem::set_domain_config (origami_system.cpp:517-541). Sets constraints_violated.
     LDO_HDN double set_domain_config(int d, V3 p, int o) {
-        if (s->dom[d].state != ST_UNASSIGNED) {
+        if (S()->dom[d].state != ST_UNASSIGNED) {
             fail(LDO_ERR_SET_ASSIGNED, d);
             return 0;
         }
@@ -1064,28 +1098,28 @@ struct System {
         DeltaConfig dc = eval_place(d, p, o, &ns, &partner);
         if (ns == ST_UNASSIGNED) {
             // site already bound/misbound: position and orientation are left untouched (:838-845)
-            s->constraints_violated = 1;
+            S()->constraints_violated = 1;
             return dc.e;
         }
         if (partner < 0) {
             // unassigned site: the sticky violation flag is NOT cleared (App. A8, :852-855)
-            if (s->constraints_violated) {
+            if (S()->constraints_violated) {
                 write_dom(d, p, o); // reverted by internal_unassign_domain, pos/ore stay
                 return dc.e;
             }
             commit_place(d, p, o);
-            s->num_unassigned--;
+            S()->num_unassigned--;
             return dc.e;
         }
-        s->constraints_violated = dc.violated ? 1 : 0;
+        S()->constraints_violated = dc.violated ? 1 : 0;
         if (dc.violated) {
             write_dom(d, p, o);
             return dc.e;
         }
         commit_place(d, p, o);
-        s->energy += dc.e;
-        s->num_stacked_pairs += dc.stacked;
-        s->num_unassigned--;
+        S()->energy += dc.e;
+        S()->num_stacked_pairs += dc.stacked;
+        S()->num_unassigned--;
         return dc.e;
     }
 
@@ -1095,11 +1129,11 @@ struct System {
         int ns, partner;
         DeltaConfig dc = eval_place(d, p, o, &ns, &partner);
         if (ns == ST_UNASSIGNED) {
-            s->constraints_violated = 1;
+            S()->constraints_violated = 1;
             return dc.e;
         }
         write_dom(d, p, o);
-        if (partner >= 0) s->constraints_violated = dc.violated ? 1 : 0;
+        if (partner >= 0) S()->constraints_violated = dc.violated ? 1 : 0;
         return dc.e;
     }
 
@@ -1107,66 +1141,66 @@ struct System {
     LDO_HDN double set_checked_domain_config(int d, V3 p, int o) {
         commit_place(d, p, o);
         double delta_e = 0;
-        int st = s->dom[d].state;
+        int st = S()->dom[d].state;
         if (st == ST_MISBOUND) {
-            delta_e += hyb_energy(d, s->bound[d]);
+            delta_e += hyb_energy(d, S()->bound[d]);
         }
         else if (st == ST_BOUND) {
-            delta_e += hyb_energy(d, s->bound[d]);
-            DeltaConfig dc = check_stacking(d, s->bound[d]);
+            delta_e += hyb_energy(d, S()->bound[d]);
+            DeltaConfig dc = check_stacking(d, S()->bound[d]);
             delta_e += dc.e;
-            s->num_stacked_pairs += dc.stacked;
+            S()->num_stacked_pairs += dc.stacked;
         }
-        if (sc->apply_mean_field_cor && st == ST_BOUND) {
-            if (s->num_fully_bound_pairs == 1) delta_e += 2 * log(6.0);
-            else if (s->num_fully_bound_pairs == 2) delta_e += log(3.0);
+        if (SC().apply_mean_field_cor && st == ST_BOUND) {
+            if (S()->num_fully_bound_pairs == 1) delta_e += 2 * log(6.0);
+            else if (S()->num_fully_bound_pairs == 2) delta_e += log(3.0);
         }
-        s->energy += delta_e;
-        s->num_unassigned--;
+        S()->energy += delta_e;
+        S()->num_unassigned--;
         return delta_e;
     }
 
     // internal_unassign_domain + unassign_domain (origami_system.cpp:375-385, 695-760)
     LDO_HDN double unassign_domain(int d) {
-        int st = s->dom[d].state;
+        int st = S()->dom[d].state;
         double e = 0;
         int stacked = 0;
         if (st == ST_BOUND || st == ST_MISBOUND) {
-            int j = s->bound[d];
-            s->num_bound_pairs -= 1;
+            int j = S()->bound[d];
+            S()->num_bound_pairs -= 1;
             if (st == ST_BOUND) {
-                s->num_fully_bound_pairs -= 1;
+                S()->num_fully_bound_pairs -= 1;
                 DeltaConfig dc = check_stacking(d, j);
                 e = -dc.e;
                 stacked = -dc.stacked;
             }
-            else if (s->dchain[j] == s->dchain[d]) {
-                s->num_self_bound_pairs -= 1;
+            else if (S()->dchain[j] == S()->dchain[d]) {
+                S()->num_self_bound_pairs -= 1;
             }
             e += -hyb_energy(d, j);
-            s->bound[d] = -1;
-            s->bound[j] = -1;
-            s->dom[d].state = ST_UNASSIGNED;
-            s->dom[j].state = ST_UNBOUND;
-            const DomRec& r = s->dom[d];
+            S()->bound[d] = -1;
+            S()->bound[j] = -1;
+            S()->dom[d].state = ST_UNASSIGNED;
+            S()->dom[j].state = ST_UNBOUND;
+            const DomRec& r = S()->dom[d];
             table_put(v3(r.x, r.y, r.z), j);
-            if (sc->apply_mean_field_cor && st == ST_BOUND) {
-                if (s->num_fully_bound_pairs == 0) e -= 2 * log(6.0);
-                else if (s->num_fully_bound_pairs == 1) e -= log(3.0);
+            if (SC().apply_mean_field_cor && st == ST_BOUND) {
+                if (S()->num_fully_bound_pairs == 0) e -= 2 * log(6.0);
+                else if (S()->num_fully_bound_pairs == 1) e -= log(3.0);
             }
         }
         else if (st == ST_UNBOUND) {
-            const DomRec& r = s->dom[d];
+            const DomRec& r = S()->dom[d];
             table_erase(v3(r.x, r.y, r.z));
-            s->dom[d].state = ST_UNASSIGNED;
+            S()->dom[d].state = ST_UNASSIGNED;
         }
         else {
             // double unassignment is allowed (:720-724): the two counter updates cancel
-            s->num_unassigned--;
+            S()->num_unassigned--;
         }
-        s->energy += e;
-        s->num_stacked_pairs += stacked;
-        s->num_unassigned++;
+        S()->energy += e;
+        S()->num_stacked_pairs += stacked;
+        S()->num_unassigned++;
         return e;
     }
 
@@ -1175,53 +1209,53 @@ struct System {
     LDO_HDN int add_chain_with_uid(int type, int uid) {
         int c = -1;
         for (int k = 1; k < K::C; k++) {
-            if (!s->chain_used[k]) {
+            if (!S()->chain_used[k]) {
                 c = k;
                 break;
             }
         }
-        int len = sc->type_len[type];
-        if (c < 0 || len > sc->lmax || chain_base(c) + len > K::D) {
+        int len = SC().type_len[type];
+        if (c < 0 || len > SC().lmax || chain_base(c) + len > K::D) {
             fail(LDO_ERR_CAPACITY, type);
             return -1;
         }
-        s->chain_used[c] = 1;
-        s->chain_uid[c] = uid;
-        s->chain_type[c] = (uint16_t)type;
-        s->chain_len[c] = (uint16_t)len;
-        s->order[s->n_chains] = (uint16_t)c;
-        s->n_chains++;
-        s->type_count[type]++;
-        s->num_staples++;
+        S()->chain_used[c] = 1;
+        S()->chain_uid[c] = uid;
+        S()->chain_type[c] = (uint16_t)type;
+        S()->chain_len[c] = (uint16_t)len;
+        S()->order[S()->n_chains] = (uint16_t)c;
+        S()->n_chains++;
+        S()->type_count[type]++;
+        S()->num_staples++;
         int base = chain_base(c);
         for (int i = 0; i < len; i++) {
             int d = base + i;
-            s->dom[d].x = 0;
-            s->dom[d].y = 0;
-            s->dom[d].z = 0;
-            s->dom[d].ore = ORE_ZERO;
-            s->dom[d].state = ST_UNASSIGNED;
-            s->bound[d] = -1;
-            s->ident[d] = sc->idents[sc->type_off[type] + i];
-            s->dchain[d] = (uint16_t)c;
-            s->dindex[d] = (uint16_t)i;
-            s->num_domains++;
-            s->num_unassigned++;
+            S()->dom[d].x = 0;
+            S()->dom[d].y = 0;
+            S()->dom[d].z = 0;
+            S()->dom[d].ore = ORE_ZERO;
+            S()->dom[d].state = ST_UNASSIGNED;
+            S()->bound[d] = -1;
+            S()->ident[d] = SC().idents[SC().type_off[type] + i];
+            S()->dchain[d] = (uint16_t)c;
+            S()->dindex[d] = (uint16_t)i;
+            S()->num_domains++;
+            S()->num_unassigned++;
         }
         return c;
     }
     // add_chain(c_i_ident) (origami_system.cpp:387-400)
     LDO_HD int add_chain(int type) {
-        s->current_c_i += 1;
-        if (sc->apply_mean_field_cor) s->energy += log(6.0);
-        s->energy += tt.init_energy;
-        return add_chain_with_uid(type, s->current_c_i);
+        S()->current_c_i += 1;
+        if (SC().apply_mean_field_cor) S()->energy += log(6.0);
+        S()->energy += tt.init_energy;
+        return add_chain_with_uid(type, S()->current_c_i);
     }
     // delete_chain (origami_system.cpp:445-472); the chain's domains must be unassigned
     LDO_HDN void delete_chain(int c) {
         int w = -1;
-        for (int k = 0; k < s->n_chains; k++) {
-            if (s->order[k] == c) {
+        for (int k = 0; k < S()->n_chains; k++) {
+            if (S()->order[k] == c) {
                 w = k;
                 break;
             }
@@ -1230,23 +1264,23 @@ struct System {
             fail(LDO_ERR_INTERNAL, c);
             return;
         }
-        for (int k = w; k + 1 < s->n_chains; k++) s->order[k] = s->order[k + 1];
-        s->n_chains--;
-        int len = s->chain_len[c];
-        s->type_count[s->chain_type[c]]--;
-        s->num_domains -= len;
-        s->num_staples--;
-        s->num_unassigned -= len;
-        s->chain_used[c] = 0;
-        if (sc->apply_mean_field_cor) s->energy -= log(6.0);
-        s->energy -= tt.init_energy;
+        for (int k = w; k + 1 < S()->n_chains; k++) S()->order[k] = S()->order[k + 1];
+        S()->n_chains--;
+        int len = S()->chain_len[c];
+        S()->type_count[S()->chain_type[c]]--;
+        S()->num_domains -= len;
+        S()->num_staples--;
+        S()->num_unassigned -= len;
+        S()->chain_used[c] = 0;
+        if (SC().apply_mean_field_cor) S()->energy -= log(6.0);
+        S()->energy -= tt.init_energy;
     }
 
     // k-th staple of a given identity in insertion order (m_identity_to_index[type][k]; App. B)
     LDO_HD int staple_of_type(int type, int k) const {
-        for (int w = 1; w < s->n_chains; w++) {
-            int c = s->order[w];
-            if (s->chain_type[c] == type) {
+        for (int w = 1; w < S()->n_chains; w++) {
+            int c = S()->order[w];
+            if (S()->chain_type[c] == type) {
                 if (k == 0) return c;
                 k--;
             }
@@ -1256,9 +1290,9 @@ struct System {
 
     // Domain at position `index` of the concatenation of chains in working order (movetypes.cpp:98-113)
     LDO_HD int domain_by_flat_index(int index) const {
-        for (int w = 0; w < s->n_chains; w++) {
-            int c = s->order[w];
-            int len = s->chain_len[c];
+        for (int w = 0; w < S()->n_chains; w++) {
+            int c = S()->order[w];
+            int len = S()->chain_len[c];
             if (index < len) return chain_base(c) + index;
             index -= len;
         }
@@ -1268,14 +1302,14 @@ struct System {
     // ---- whole-system passes ----
     // OrigamiSystem::center (origami_system.cpp:553-571)
     LDO_HDN void center(int centering_domain) {
-        const DomRec& c0 = s->dom[chain_base(0) + centering_domain];
+        const DomRec& c0 = S()->dom[chain_base(0) + centering_domain];
         V3 ref = v3(c0.x, c0.y, c0.z);
         table_clear();
-        for (int w = 0; w < s->n_chains; w++) {
-            int c = s->order[w];
+        for (int w = 0; w < S()->n_chains; w++) {
+            int c = S()->order[w];
             int base = chain_base(c);
-            for (int i = 0; i < s->chain_len[c]; i++) {
-                DomRec& r = s->dom[base + i];
+            for (int i = 0; i < S()->chain_len[c]; i++) {
+                DomRec& r = S()->dom[base + i];
                 r.x = (short)(r.x - ref.x);
                 r.y = (short)(r.y - ref.y);
                 r.z = (short)(r.z - ref.z);
@@ -1287,28 +1321,28 @@ struct System {
 
     // set_all_domains() + check_distance_constraints (origami_system.cpp:357-373, 573-586)
     LDO_HDN bool set_all_domains() {
-        for (int w = 0; w < s->n_chains; w++) {
-            int c = s->order[w];
+        for (int w = 0; w < S()->n_chains; w++) {
+            int c = S()->order[w];
             int base = chain_base(c);
-            for (int i = 0; i < s->chain_len[c]; i++) {
+            for (int i = 0; i < S()->chain_len[c]; i++) {
                 int d = base + i;
-                const DomRec r = s->dom[d];
+                const DomRec r = S()->dom[d];
                 set_domain_config(d, v3(r.x, r.y, r.z), r.ore);
-                if (s->constraints_violated) {
+                if (S()->constraints_violated) {
                     fail(LDO_ERR_CONSTRAINTS, d);
                     return false;
                 }
             }
         }
-        for (int w = 0; w < s->n_chains; w++) {
-            int c = s->order[w];
+        for (int w = 0; w < S()->n_chains; w++) {
+            int c = S()->order[w];
             int base = chain_base(c);
-            for (int i = 0; i < s->chain_len[c]; i++) {
+            for (int i = 0; i < S()->chain_len[c]; i++) {
                 int d = base + i;
                 int n = step(d, 1);
                 if (n < 0) continue;
-                const DomRec& a = s->dom[d];
-                const DomRec& b = s->dom[n];
+                const DomRec& a = S()->dom[d];
+                const DomRec& b = S()->dom[n];
                 if (abs(b.x - a.x) + abs(b.y - a.y) + abs(b.z - a.z) != 1) {
                     fail(LDO_ERR_DISTANCE, d);
                     return false;
@@ -1319,82 +1353,82 @@ struct System {
     }
 
     LDO_HD void unassign_all() {
-        for (int w = 0; w < s->n_chains; w++) {
-            int c = s->order[w];
+        for (int w = 0; w < S()->n_chains; w++) {
+            int c = S()->order[w];
             int base = chain_base(c);
-            for (int i = 0; i < s->chain_len[c]; i++) unassign_domain(base + i);
+            for (int i = 0; i < S()->chain_len[c]; i++) unassign_domain(base + i);
         }
     }
 
     // OrigamiSystem::check_all_constraints (origami_system.cpp:267-325)
     LDO_HDN bool check_all_constraints() {
-        if (s->num_unassigned != 0) {
+        if (S()->num_unassigned != 0) {
             fail(LDO_ERR_UNASSIGNED_AT_CHECK);
             return false;
         }
-        for (int w = 0; w < s->n_chains; w++) {
-            int c = s->order[w];
+        for (int w = 0; w < S()->n_chains; w++) {
+            int c = S()->order[w];
             int base = chain_base(c);
-            for (int i = 0; i < s->chain_len[c]; i++) {
-                if (s->dom[base + i].state == ST_UNASSIGNED) {
+            for (int i = 0; i < S()->chain_len[c]; i++) {
+                if (S()->dom[base + i].state == ST_UNASSIGNED) {
                     fail(LDO_ERR_UNASSIGNED_AT_CHECK, base + i);
                     return false;
                 }
                 unassign_domain(base + i);
             }
         }
-        int ns = s->n_chains - 1;
-        if (sc->apply_mean_field_cor) s->energy -= ns * log(6.0);
-        s->energy -= ns * tt.init_energy;
-        if (s->num_stacked_pairs != 0) {
-            int sp = s->num_stacked_pairs;
+        int ns = S()->n_chains - 1;
+        if (SC().apply_mean_field_cor) S()->energy -= ns * log(6.0);
+        S()->energy -= ns * tt.init_energy;
+        if (S()->num_stacked_pairs != 0) {
+            int sp = S()->num_stacked_pairs;
             set_all_domains();
             fail(LDO_ERR_STACK_COUNT, sp);
             return false;
         }
         double eps = 0.000001;
-        if (s->energy < -eps || s->energy > eps) {
+        if (S()->energy < -eps || S()->energy > eps) {
             set_all_domains();
             fail(LDO_ERR_ENERGY_DRIFT);
             return false;
         }
-        s->energy = 0;
+        S()->energy = 0;
         if (!set_all_domains()) return false;
-        if (sc->apply_mean_field_cor) s->energy += ns * log(6.0);
-        s->energy += ns * tt.init_energy;
+        if (SC().apply_mean_field_cor) S()->energy += ns * log(6.0);
+        S()->energy += ns * tt.init_energy;
         return true;
     }
 
     // OrigamiSystem::update_energy (origami_system.cpp:808-826), after new tables were installed
     LDO_HDN bool update_energy() {
         unassign_all();
-        s->energy = 0;
-        int ns = s->n_chains - 1;
-        if (sc->apply_mean_field_cor) s->energy += ns * log(6.0);
-        s->energy += ns * tt.init_energy;
+        S()->energy = 0;
+        int ns = S()->n_chains - 1;
+        if (SC().apply_mean_field_cor) S()->energy += ns * log(6.0);
+        S()->energy += ns * tt.init_energy;
         return set_all_domains();
     }
 
     // OrigamiSystem::update_enthalpy_and_entropy (origami_system.cpp:204-246)
     LDO_HDN void enthalpy_and_entropy(double* enthalpy, double* entropy, double* stacking) const {
-        double H = 0, S = 0;
-        for (int w = 0; w < s->n_chains; w++) {
-            int c = s->order[w];
+        double H = 0, Sent = 0;
+        for (int w = 0; w < S()->n_chains; w++) {
+            int c = S()->order[w];
             int base = chain_base(c);
-            for (int i = 0; i < s->chain_len[c]; i++) {
+            for (int i = 0; i < S()->chain_len[c]; i++) {
                 int d = base + i;
-                int st = s->dom[d].state;
+                int st = S()->dom[d].state;
                 if (st == ST_BOUND || st == ST_MISBOUND) {
-                    int j = s->bound[d];
+                    int j = S()->bound[d];
                     // the pair is counted when its first member (in working order) is visited
                     bool j_first = false;
-                    int cj = s->dchain[j];
+                    int cj = S()->dchain[j];
                     if (cj == c) {
-                        j_first = s->dindex[j] < i;
+                        j_first = S()->dindex[j] < i;
                     }
                     else {
                         for (int w2 = 0; w2 < w; w2++) {
-                            if (s->order[w2] == cj) {
+                            if (S()->order[w2] == cj) {
                                 j_first = true;
                                 break;
                             }
@@ -1402,22 +1436,22 @@ struct System {
                     }
                     if (!j_first) {
                         H += hyb_enthalpy(d, j);
-                        S += hyb_entropy(d, j);
+                        Sent += hyb_entropy(d, j);
                     }
                 }
             }
         }
-        int ns = s->n_chains - 1;
-        if (sc->apply_mean_field_cor) {
-            S -= ns * log(6.0);
-            if (s->num_fully_bound_pairs >= 1) S -= 2 * log(6.0);
-            if (s->num_fully_bound_pairs >= 2) S -= log(3.0);
+        int ns = S()->n_chains - 1;
+        if (SC().apply_mean_field_cor) {
+            Sent -= ns * log(6.0);
+            if (S()->num_fully_bound_pairs >= 1) Sent -= 2 * log(6.0);
+            if (S()->num_fully_bound_pairs >= 2) Sent -= log(3.0);
         }
         H += ns * tt.init_enthalpy;
-        S += ns * tt.init_entropy;
+        Sent += ns * tt.init_entropy;
         *enthalpy = H;
-        *entropy = S;
-        *stacking = s->energy - (H - S);
+        *entropy = Sent;
+        *stacking = S()->energy - (H - Sent);
     }
 };
 

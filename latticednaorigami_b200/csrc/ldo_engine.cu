@@ -89,7 +89,7 @@ static const char* dev_err() { return cudaGetErrorString(g_last_cuda); }
 
 #define LDO_GRID_CAP 512 // grid-bias points per replica (sum over grid biases)
 
-struct RepAux {
+struct __attribute__((aligned(16))) RepAux {
     Rng rng;
     Control ctl;
     BiasState bs;
@@ -142,7 +142,9 @@ struct OpArgs {
 template <class K>
 struct DevPtrs {
     SysState<K>* states;
-    MoveScratch<K>* scratch; // only for the in-place (non-staged) path
+    MoveScratch<K>* scratch; // hot move scratch, only for the in-place (non-staged) path
+    ColdScratch<K>* cold; // [R] selection / topology scratch, always in global memory
+    Engine<K>* engines; // per-replica engine objects, only for the in-place path
     RepAux* aux;
     const Shared* shared;
     const TempTables* tables;
@@ -159,6 +161,7 @@ LDO_HD void rep_init_engine(Engine<K>& eng, SysState<K>* st, MoveScratch<K>* ms,
     const Shared* sh = P.shared;
     eng.sys.init(st, &sh->sc, P.tables[aux->ctl.temp_idx]);
     eng.m = ms;
+    eng.mc = &P.cold[r];
     eng.rng = &aux->rng;
     eng.ms = &sh->ms;
     eng.ob = &sh->ob;
@@ -171,17 +174,22 @@ LDO_HD void rep_init_engine(Engine<K>& eng, SysState<K>* st, MoveScratch<K>* ms,
 template <class K>
 LDO_HD void rep_refresh_stack_energy(SysState<K>* st, const Shared* sh, const Control& ctl) {
     // OrigamiPotential::update_temp scales the Constant stacking energy (origami_potential.cpp:1026-1029,1219)
+    (void)sh;
+#if defined(__CUDA_ARCH__)
+    st->stack_e = ldo_c_sc.stacking_ene * ctl.stacking_mult / ctl.temp;
+#else
     st->stack_e = sh->sc.stacking_ene * ctl.stacking_mult / ctl.temp;
+#endif
 }
 
 // Bias bookkeeping restart (SystemBiases constructor: every m_bias evaluated once, bias_functions.cpp:60-66,423-426)
 template <class K>
 LDO_HD void rep_init_biases(Engine<K>& eng) {
     eng.update_move_params();
-    eng.bs->move_update_bias = 0;
-    for (int b = 0; b < eng.ob->n_biases; b++) {
-        eng.bs->bias_val[b] = eng.calc_bias_fn(b);
-        eng.bs->move_update_bias += eng.bs->bias_val[b];
+    eng.BS()->move_update_bias = 0;
+    for (int b = 0; b < eng.OB().n_biases; b++) {
+        eng.BS()->bias_val[b] = eng.calc_bias_fn(b);
+        eng.BS()->move_update_bias += eng.BS()->bias_val[b];
     }
 }
 
@@ -189,8 +197,8 @@ LDO_HD void rep_init_biases(Engine<K>& eng) {
 template <class K>
 LDO_HD void rep_load_config(Engine<K>& eng, const OpArgs& a) {
     System<K>& sys = eng.sys;
-    SysState<K>* s = sys.s;
-    const SysConst* sc = sys.sc;
+    SysState<K>* s = sys.S();
+    const SysConst* sc = &sys.SC();
     s->status = LDO_OK;
     s->status_detail = 0;
     s->constraints_violated = 0;
@@ -258,8 +266,8 @@ LDO_HD void rep_load_config(Engine<K>& eng, const OpArgs& a) {
 template <class K>
 LDO_HD void rep_observe(Engine<K>& eng, const OpArgs& a, int r) {
     System<K>& sys = eng.sys;
-    const SysState<K>* s = sys.s;
-    int nst = sys.sc->n_types - 1;
+    const SysState<K>* s = sys.S();
+    int nst = sys.SC().n_types - 1;
     if (a.out_energies) {
         double H, S, stk;
         sys.enthalpy_and_entropy(&H, &S, &stk);
@@ -294,7 +302,7 @@ LDO_HD void rep_observe(Engine<K>& eng, const OpArgs& a, int r) {
     }
     if (a.out_ops) {
         eng.update_move_params();
-        for (int i = 0; i < eng.ob->n_ops; i++) a.out_ops[(size_t)r * eng.ob->n_ops + i] = eng.bs->op_val[i];
+        for (int i = 0; i < eng.OB().n_ops; i++) a.out_ops[(size_t)r * eng.OB().n_ops + i] = eng.BS()->op_val[i];
     }
     if (a.out_staples) {
         for (int t = 0; t < nst; t++) a.out_staples[(size_t)r * nst + t] = s->type_count[t + 1];
@@ -308,29 +316,32 @@ LDO_HD void rep_observe(Engine<K>& eng, const OpArgs& a, int r) {
 // USGCMCSimulation::update_internal (us_simulation.cpp:262-266): visit count of the current grid point
 template <class K>
 LDO_HD void rep_count_grid_visit(Engine<K>& eng, long long* visits) {
-    for (int b = 0; b < eng.ob->n_biases; b++) {
-        if (eng.ob->biases[b].type != BIAS_GRID) continue;
-        int off = eng.bs->grid_off[b];
+    for (int b = 0; b < eng.OB().n_biases; b++) {
+        if (eng.OB().biases[b].type != BIAS_GRID) continue;
+        int off = eng.BS()->grid_off[b];
         if (off < 0) continue;
-        const BiasDef& bd = eng.ob->biases[b];
+        const BiasDef& bd = eng.OB().biases[b];
         int idx = 0;
         bool inside = true;
         for (int k = 0; k < bd.n_ops; k++) {
-            int v = eng.bs->op_val[bd.op_idx[k]] - eng.bs->grid_lo[b][k];
-            if (v < 0 || v >= eng.bs->grid_n[b][k]) {
+            int v = eng.BS()->op_val[bd.op_idx[k]] - eng.BS()->grid_lo[b][k];
+            if (v < 0 || v >= eng.BS()->grid_n[b][k]) {
                 inside = false;
                 break;
             }
-            idx = idx * eng.bs->grid_n[b][k] + v;
+            idx = idx * eng.BS()->grid_n[b][k] + v;
         }
         if (inside) visits[off + idx] += 1;
     }
 }
 
+// `engp` is one engine object per replica (shared by the warp's lanes: shared memory when staged), so
+// that the move state is not replicated 32 times in per-lane local memory.
 template <class K>
-LDO_HD void rep_execute(SysState<K>* st, MoveScratch<K>* ms, RepAux* aux, const DevPtrs<K>& P, const OpArgs& a, int r) {
-    Engine<K> eng;
+LDO_HD void rep_execute(Engine<K>* engp, SysState<K>* st, MoveScratch<K>* ms, RepAux* aux, const DevPtrs<K>& P, const OpArgs& a, int r) {
+    Engine<K>& eng = *engp;
     rep_init_engine(eng, st, ms, aux, P, r);
+    LDO_SYNCWARP();
     switch (a.op) {
     case OP_RUN: {
         if (st->status != LDO_OK) break;
@@ -404,13 +415,23 @@ __device__ inline void warp_copy16(T* dst, const T* src) {
 template <class K>
 struct __align__(16) WarpSmem {
     SysState<K> st;
+    RepAux aux;
     MoveScratch<K> ms;
+    Engine<K> eng;
 };
 
 // Staged: the replica state is copied HBM -> shared memory (coalesced 128-bit), all moves run on
 // shared memory, and the state is copied back once at the end.
+// Launch shape of the staged kernel: LDO_BLOCK_WARPS warps per block, at least LDO_MIN_BLOCKS blocks per
+// SM (this caps the registers per thread; see DESIGN.md for the measured occupancy trade-off)
+#ifndef LDO_BLOCK_WARPS
+#define LDO_BLOCK_WARPS 2
+#endif
+#ifndef LDO_MIN_BLOCKS
+#define LDO_MIN_BLOCKS 12
+#endif
 template <class K>
-__global__ void __launch_bounds__(128) k_exec_staged(DevPtrs<K> P, OpArgs a, int warps_per_block) {
+__global__ void __launch_bounds__(32 * LDO_BLOCK_WARPS, LDO_MIN_BLOCKS) k_exec_staged(DevPtrs<K> P, OpArgs a, int warps_per_block) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     WarpSmem<K>* ws = reinterpret_cast<WarpSmem<K>*>(smem_raw);
     int warp = threadIdx.x >> 5;
@@ -419,9 +440,13 @@ __global__ void __launch_bounds__(128) k_exec_staged(DevPtrs<K> P, OpArgs a, int
     if (a.only_replica >= 0 && r != a.only_replica) return;
     WarpSmem<K>& w = ws[warp];
     warp_copy16(&w.st, &P.states[r]);
-    rep_execute<K>(&w.st, &w.ms, &P.aux[r], P, a, r);
+    warp_copy16(&w.aux, &P.aux[r]);
+    rep_execute<K>(&w.eng, &w.st, &w.ms, &w.aux, P, a, r);
     __syncwarp();
-    if (a.op != OP_OBSERVE && a.op != OP_RECOMPUTE) warp_copy16(&P.states[r], &w.st);
+    if (a.op != OP_OBSERVE && a.op != OP_RECOMPUTE) {
+        warp_copy16(&P.states[r], &w.st);
+        warp_copy16(&P.aux[r], &w.aux);
+    }
 }
 
 // In place: state and scratch stay in HBM / L2 (large systems)
@@ -436,7 +461,7 @@ __global__ void __launch_bounds__(128) k_exec_inplace(DevPtrs<K> P, OpArgs a, in
         warp_copy16(&recompute_tmp[r], &P.states[r]);
         st = &recompute_tmp[r];
     }
-    rep_execute<K>(st, &P.scratch[r], &P.aux[r], P, a, r);
+    rep_execute<K>(&P.engines[r], st, &P.scratch[r], &P.aux[r], P, a, r);
 }
 
 #endif // !LDO_HOSTSIM
@@ -562,10 +587,13 @@ __global__ void k_exchange(ExchangeArgs x) {
 // Engine object
 // ---------------------------------------------------------------------------------------------
 
-typedef Caps<80, 26, 8, 16> CapsSmall; // snodin-class systems: staged in shared memory
-typedef Caps<512, 176, 11, 96> CapsLarge; // large scaffolds: in place in HBM/L2
+typedef Caps<80, 26, 7, 16, true, 48, 40, 40> CapsSmall; // snodin-class systems: staged in shared memory
+typedef Caps<512, 176, 11, 96, false, 511, 512, 1026> CapsLarge; // large scaffolds: in place in HBM/L2
 
 static std::string g_create_error;
+static const void* g_const_owner = nullptr; // engine whose descriptions are in constant memory
+static long long g_const_version = -1;
+static long long g_const_counter = 0;
 
 struct EngineBase {
     virtual ~EngineBase() {}
@@ -600,6 +628,7 @@ struct EngineBase {
     virtual int get_blobs(int first, int count, void* host) = 0;
     virtual int put_blobs(int first, int count, const void* host) = 0;
     long long launches = 0; // kernels launched so far (ldo_launch_count)
+    long long const_version = 0;
     // device output buffers
     double* d_energies = nullptr;
     int* d_counters = nullptr;
@@ -643,6 +672,8 @@ struct EngineImpl: EngineBase {
     ~EngineImpl() override {
         dev_free(P.states);
         dev_free(P.scratch);
+        dev_free(P.cold);
+        dev_free(P.engines);
         dev_free(P.aux);
         dev_free(d_shared);
         dev_free(d_tables);
@@ -667,6 +698,7 @@ struct EngineImpl: EngineBase {
         dev_free(d_slot_vals);
         dev_free(d_red_u);
         for (void* p: tape_bufs) dev_free(p);
+        if (g_const_owner == this) g_const_owner = nullptr;
 #ifndef LDO_HOSTSIM
         cudaStreamDestroy(stream);
 #endif
@@ -681,7 +713,9 @@ struct EngineImpl: EngineBase {
         stream = 0;
 #endif
         if (dev_malloc((void**)&P.states, sizeof(SysState<K>) * R)) return fail(dev_err());
+        if (dev_malloc((void**)&P.cold, sizeof(ColdScratch<K>) * R)) return fail(dev_err());
         if (!STAGED) {
+            if (dev_malloc((void**)&P.engines, sizeof(Engine<K>) * R)) return fail(dev_err());
             if (dev_malloc((void**)&P.scratch, sizeof(MoveScratch<K>) * R)) return fail(dev_err());
             if (dev_malloc((void**)&d_recompute_tmp, sizeof(SysState<K>) * R)) return fail(dev_err());
         }
@@ -723,6 +757,7 @@ struct EngineImpl: EngineBase {
     }
 
     int push_shared() override {
+        const_version = ++g_const_counter;
         if (dev_h2d(d_shared, &shared, sizeof(Shared), stream)) return fail(dev_err());
         if (shared.has_grid && !P.grid_vals) {
             if (dev_malloc((void**)&P.grid_vals, sizeof(double) * LDO_GRID_CAP * R)) return fail(dev_err());
@@ -782,14 +817,16 @@ struct EngineImpl: EngineBase {
                 memcpy(tmp, st, sizeof(SysState<K>));
                 st = tmp;
             }
-            rep_execute<K>(st, ms, &P.aux[r], P, a, r);
+            Engine<K> eng;
+            rep_execute<K>(&eng, st, ms, &P.aux[r], P, a, r);
         }
         (void)sync;
         return 0;
 #else
         int wpb = warps_per_block;
         int blocks = (R + wpb - 1) / wpb;
-        if (STAGED) {
+        if (upload_constants()) return -1;
+        if constexpr (STAGED) {
             size_t smem = sizeof(WarpSmem<K>) * wpb;
             k_exec_staged<K><<<blocks, wpb * 32, smem, stream>>>(P, a, wpb);
         }
@@ -803,16 +840,32 @@ struct EngineImpl: EngineBase {
 #endif
     }
 
+    // The system / moveset / order-parameter descriptions live in constant memory, which is shared by
+    // every engine of the process: re-upload when another engine (or a new description) owns it.
+    int upload_constants() {
+#ifndef LDO_HOSTSIM
+        if (g_const_owner == this && g_const_version == const_version) return 0;
+        if (chk(cudaDeviceSynchronize())) return fail(dev_err());
+        if (chk(cudaMemcpyToSymbol(ldo_c_sc, &shared.sc, sizeof(SysConst)))) return fail(dev_err());
+        if (chk(cudaMemcpyToSymbol(ldo_c_ms, &shared.ms, sizeof(MoveSet)))) return fail(dev_err());
+        if (chk(cudaMemcpyToSymbol(ldo_c_ob, &shared.ob, sizeof(OpsBiasConst)))) return fail(dev_err());
+        if (chk(cudaDeviceSynchronize())) return fail(dev_err());
+        g_const_owner = this;
+        g_const_version = const_version;
+#endif
+        return 0;
+    }
+
     int configure_launch() {
 #ifndef LDO_HOSTSIM
-        if (STAGED) {
+        if constexpr (STAGED) {
             // as many warps per block as fit the opt-in shared memory limit, capped at 4 (128 threads)
             int max_smem = 0;
             cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
             size_t per_warp = sizeof(WarpSmem<K>);
             int wpb = (int)(max_smem / per_warp);
             if (wpb < 1) return fail("replica state does not fit shared memory");
-            if (wpb > 4) wpb = 4;
+            if (wpb > LDO_BLOCK_WARPS) wpb = LDO_BLOCK_WARPS;
             warps_per_block = wpb;
             if (chk(cudaFuncSetAttribute(k_exec_staged<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(per_warp * wpb)))) {
                 return fail(dev_err());

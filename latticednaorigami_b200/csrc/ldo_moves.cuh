@@ -63,6 +63,7 @@ LDO_HD inline void philox_round(uint32_t& c0, uint32_t& c1, uint32_t& c2, uint32
 LDO_HD inline void philox4x32_10(const Rng& r, unsigned long long ctr, uint32_t out[4]) {
     uint32_t c0 = (uint32_t)ctr, c1 = (uint32_t)(ctr >> 32), c2 = r.subseq, c3 = r.stream;
     uint32_t k0 = r.key0, k1 = r.key1;
+#pragma unroll 1
     for (int i = 0; i < 10; i++) {
         philox_round(c0, c1, c2, c3, k0, k1);
         k0 += 0x9E3779B9u;
@@ -172,10 +173,29 @@ LDO_HD inline int popc36(unsigned long long m) {
 }
 LDO_HD inline int nth_set_bit36(unsigned long long m, int n) {
 #if defined(__CUDA_ARCH__)
-    unsigned lo = (unsigned)m, hi = (unsigned)(m >> 32);
-    int nlo = __popc(lo);
-    if (n < nlo) return (int)__fns(lo, 0, n + 1);
-    return 32 + (int)__fns(hi, 0, n - nlo + 1);
+    // rank-select by halving with popc (the __fns intrinsic expands to a long software routine)
+    unsigned x = (unsigned)m;
+    int pos = 0;
+    int nlo = __popc(x);
+    if (n >= nlo) {
+        n -= nlo;
+        x = (unsigned)(m >> 32);
+        pos = 32;
+    }
+#pragma unroll
+    for (int w = 16; w >= 1; w >>= 1) {
+        unsigned low = x & ((1u << w) - 1u);
+        int c = __popc(low);
+        if (n >= c) {
+            n -= c;
+            x >>= w;
+            pos += w;
+        }
+        else {
+            x = low;
+        }
+    }
+    return pos;
 #else
     for (int k = 0; k < n; k++) m &= m - 1;
     int i = 0;
@@ -197,37 +217,49 @@ struct RgSlot {
 #define LDO_RG_OWN_SLOTS 4
 #define LDO_RG_SLOTS (LDO_RG_OWN_SLOTS + 6)
 
+#if defined(__CUDACC__)
+__constant__ MoveSet ldo_c_ms;
+__constant__ OpsBiasConst ldo_c_ob;
+#endif
+
 // ---------------------------------------------------------------------------------------------
 // Per-move scratch (MCMovetype / RegrowthMCMovetype / CBMCMovetype / CTRGRegrowthMCMovetype members)
 // and Constraintpoints (top_constraint_points.hpp:112-288), fixed capacity
 // ---------------------------------------------------------------------------------------------
 
+// Effect of placing a parent domain on an EMPTY site q on the active endpoints (update_endpoints,
+// top_constraint_points.cpp:340-349), applied on the fly by the read-only walk / endpoint predicates:
+// endpoints of (rm_chain, rm_seg) with domain index rm_d are removed; one endpoint is added when the
+// parent has an inactive endpoint.
+struct EpOverlay {
+    int rm_chain, rm_seg, rm_d; // rm_chain < 0: no overlay
+    int add_chain, add_seg, add_d; // add_chain < 0: nothing added
+    V3 add_pos;
+};
+
+// Hot part: touched inside the trial loops; lives in shared memory for staged replicas
 template <class K>
 struct MoveScratch {
-    static const int A = 2 * K::D + 8; // assigned-domain list capacity
-    static const int E = K::D; // active endpoints capacity
-    static const int S = 2 * K::D + 2; // scaffold segments capacity
+    static const int A = 2 * K::LV + 8; // assigned-domain list capacity
+    static const int E = K::E; // active endpoints capacity
+    static const int S = K::SEG; // scaffold segments capacity
 
     // MCMovetype (movetypes.hpp:146-166)
-    short modified[K::D + 1];
+    short modified[K::LV + 1];
     int n_modified;
     short assigned[A];
     int n_assigned;
     int added_chain; // chain slot or -1 (at most one chain is added per move)
     DomRec prev[K::D]; // m_prev_pos / m_prev_ore
-    DomRec oldc[K::D]; // m_old_pos / m_old_ore
-    DomRec newc[K::D]; // m_new_pos / m_new_ore
     int rejected;
     double modifier;
 
     // CTRG (rg_movetypes.hpp:83-115)
-    short regrow[K::D + 1];
+    short regrow[K::LV + 1];
     int n_regrow;
-    short sel_scaf[K::D + 1];
-    int n_sel;
-    uint8_t c_attempts_q[K::D + 1], c_attempts_wq[K::D + 1];
-    unsigned long long avail_q[K::D + 1], avail_wq[K::D + 1];
-    double c_opens[K::D + 1];
+    uint8_t c_attempts_q[K::LV + 1], c_attempts_wq[K::LV + 1];
+    unsigned long long avail_q[K::LV + 1], avail_wq[K::LV + 1];
+    double c_opens[K::LV + 1];
     // m_erased_endpoints_q: stack of position lists
     int eq_depth;
     short eq_start[A + 1];
@@ -241,20 +273,40 @@ struct MoveScratch {
     short gp_stem[K::D]; // m_growthpoints[d] (domain to grow from d) or -1
     short inactive[K::D]; // m_inactive_endpoints[d] or -1
     int8_t stem_seg0[K::D]; // m_stemd_to_segs[d] = {s, s+1}, -1 = none
-    uint8_t in_sel[K::D]; // membership in m_scaffold_domains
-    uint8_t checked_chain[K::C]; // m_checked_staples
     int n_ep; // m_active_endpoints, flattened, per-key order preserved
     short ep_chain[E];
     int8_t ep_seg[E];
     short ep_d[E];
     short ep_pos[E][3];
+    int n_erased; // m_erased_endpoints
+    short erased_pos[8][3];
+
+    // CTRG trial-configuration caches: own[level % 4] and feeler memo keyed by the parent's site
+    RgSlot slots[LDO_RG_SLOTS];
+
+    // lane-parallel candidate evaluation results (6 neighbour sites)
+    double site_w[8];
+    int site_o[8];
+    int site_kind[8];
+};
+
+// Cold part: selection / topology set-up and the saved configurations, touched a few times per move;
+// always in global memory (L2 resident)
+template <class K>
+struct ColdScratch {
+    static const int E = K::E;
+    static const int S = K::SEG;
+    DomRec oldc[K::D]; // m_old_pos / m_old_ore
+    DomRec newc[K::D]; // m_new_pos / m_new_ore
+    short sel_scaf[K::D + 1];
+    int n_sel;
+    uint8_t in_sel[K::D]; // membership in m_scaffold_domains
+    uint8_t checked_chain[K::C]; // m_checked_staples
     int n_ep0; // m_initial_active_endpoints
     short ep0_chain[E];
     int8_t ep0_seg[E];
     short ep0_d[E];
     short ep0_pos[E][3];
-    int n_erased; // m_erased_endpoints
-    short erased_pos[8][3];
 
     // StapleNetwork scratch (top_constraint_points.hpp:40-108)
     uint8_t net_chain[K::C];
@@ -270,14 +322,6 @@ struct MoveScratch {
     short seg_dom[2 * K::D + 2];
     short stems[K::D + 1];
     short stem_queue[4 * K::D + 8];
-
-    // CTRG trial-configuration caches: own[level % 4] and feeler memo keyed by the parent's site
-    RgSlot slots[LDO_RG_SLOTS];
-
-    // lane-parallel candidate evaluation results (6 neighbour sites)
-    double site_w[8];
-    int site_o[8];
-    int site_kind[8];
 };
 
 // Move statistics (MovetypeTracking, movetypes.hpp:49-52)
@@ -294,6 +338,7 @@ template <class K>
 struct Engine {
     System<K> sys;
     MoveScratch<K>* m;
+    ColdScratch<K>* mc;
     Rng* rng;
     const MoveSet* ms;
     const OpsBiasConst* ob;
@@ -310,66 +355,110 @@ struct Engine {
     // slot holding the current domain's trial probabilities; feeler memo bookkeeping
     int cur_slot, memo_level, memo_key, memo_mask, last_pc, last_kind;
 
-    // ---- RNG (random_gens.cpp:29-49) ----
-    LDO_HD uint32_t next_word() {
-        if (rng->buf_n == 0) {
-            philox4x32_10(*rng, rng->counter++, rng->buf);
-            rng->buf_n = 4;
-        }
-        return rng->buf[--rng->buf_n];
+    // ---- accessors: shared-memory hints and constant-memory copies on the device ----
+    LDO_HD MoveScratch<K>* M() const {
+        MoveScratch<K>* p = m;
+        LDO_ASSUME_SHARED(K, p);
+        return p;
     }
-    LDO_HDN double uniform_real() {
-        if (rng->tape != nullptr) {
-            if (rng->tape_pos >= rng->tape_len) {
-                sys.fail(LDO_ERR_TAPE_EXHAUSTED);
-                return 0.5;
-            }
-            const TapeDraw& t = rng->tape[rng->tape_pos];
-            if (t.kind != 0) {
-                sys.fail(LDO_ERR_TAPE_MISMATCH, (int)rng->tape_pos);
-                return 0.5;
-            }
-            rng->tape_pos++;
-            return t.real;
+    LDO_HD ColdScratch<K>* C() const { return mc; }
+    LDO_HD Rng* RNG() const {
+        Rng* p = rng;
+        LDO_ASSUME_SHARED(K, p);
+        return p;
+    }
+    LDO_HD BiasState* BS() const {
+        BiasState* p = bs;
+        LDO_ASSUME_SHARED(K, p);
+        return p;
+    }
+    LDO_HD MoveStats* STATS() const {
+        MoveStats* p = stats;
+        LDO_ASSUME_SHARED(K, p);
+        return p;
+    }
+    LDO_HD const MoveSet& MS() const {
+#if defined(__CUDA_ARCH__)
+        return ldo_c_ms;
+#else
+        return *ms;
+#endif
+    }
+    LDO_HD const OpsBiasConst& OB() const {
+#if defined(__CUDA_ARCH__)
+        return ldo_c_ob;
+#else
+        return *ob;
+#endif
+    }
+
+    // ---- RNG (random_gens.cpp:29-49) ----
+    // Refill of the 4-word buffer is the only out-of-line part of the Philox path, so that the draw
+    // functions stay a few instructions long inside the trial loops (instruction-cache footprint)
+    LDO_HDN void philox_refill() {
+        Rng* g = RNG();
+        philox4x32_10(*g, g->counter++, g->buf);
+        g->buf_n = 4;
+    }
+    LDO_HD uint32_t next_word() {
+        Rng* g = RNG();
+        if (g->buf_n == 0) philox_refill();
+        return g->buf[--g->buf_n];
+    }
+    // replay tape (parity mode)
+    LDO_HDN double tape_real() {
+        Rng* g = RNG();
+        if (g->tape_pos >= g->tape_len) {
+            sys.fail(LDO_ERR_TAPE_EXHAUSTED);
+            return 0.5;
         }
+        const TapeDraw& t = g->tape[g->tape_pos];
+        if (t.kind != 0) {
+            sys.fail(LDO_ERR_TAPE_MISMATCH, (int)g->tape_pos);
+            return 0.5;
+        }
+        g->tape_pos++;
+        return t.real;
+    }
+    LDO_HDN int tape_int(int lo, int hi) {
+        Rng* g = RNG();
+        if (g->tape_pos >= g->tape_len) {
+            sys.fail(LDO_ERR_TAPE_EXHAUSTED);
+            return lo;
+        }
+        const TapeDraw& t = g->tape[g->tape_pos];
+        if (t.kind != 1 || t.lo != lo || t.hi != hi) {
+            sys.fail(LDO_ERR_TAPE_MISMATCH, (int)g->tape_pos);
+            return lo;
+        }
+        g->tape_pos++;
+        return t.ival;
+    }
+    LDO_HD double uniform_real() {
+        if (RNG()->tape != nullptr) return tape_real();
         uint32_t hi = next_word();
         uint32_t lo = next_word();
         unsigned long long u = ((unsigned long long)hi << 32) | lo;
         return (double)(u >> 11) * (1.0 / 9007199254740992.0);
     }
-    LDO_HDN int uniform_int(int lo, int hi) {
-        if (rng->tape != nullptr) {
-            if (rng->tape_pos >= rng->tape_len) {
-                sys.fail(LDO_ERR_TAPE_EXHAUSTED);
-                return lo;
-            }
-            const TapeDraw& t = rng->tape[rng->tape_pos];
-            if (t.kind != 1 || t.lo != lo || t.hi != hi) {
-                sys.fail(LDO_ERR_TAPE_MISMATCH, (int)rng->tape_pos);
-                return lo;
-            }
-            rng->tape_pos++;
-            return t.ival;
-        }
+    // Lemire's nearly-divisionless unbiased bounded integer: rejection part
+    LDO_HDN unsigned long long uniform_int_reject(unsigned long long mm, uint32_t n) {
+        uint32_t t = (0u - n) % n;
+        while ((uint32_t)mm < t) mm = (unsigned long long)next_word() * n;
+        return mm;
+    }
+    LDO_HD int uniform_int(int lo, int hi) {
+        if (RNG()->tape != nullptr) return tape_int(lo, hi);
         uint32_t n = (uint32_t)(hi - lo) + 1u;
-        if (n == 0) return lo; // full 32-bit range never occurs on this path
-        // Lemire's nearly-divisionless unbiased bounded integer
         unsigned long long mm = (unsigned long long)next_word() * n;
-        uint32_t l = (uint32_t)mm;
-        if (l < n) {
-            uint32_t t = (0u - n) % n;
-            while (l < t) {
-                mm = (unsigned long long)next_word() * n;
-                l = (uint32_t)mm;
-            }
-        }
+        if ((uint32_t)mm < n) mm = uniform_int_reject(mm, n);
         return lo + (int)(mm >> 32);
     }
 
     // ---- order parameters and biases ----
     LDO_HDN int calc_op(int i) const {
-        const OpDef& o = ob->ops[i];
-        const SysState<K>* s = sys.s;
+        const OpDef& o = OB().ops[i];
+        const SysState<K>* s = sys.S();
         switch (o.type) {
         case OP_NUM_STAPLES: return s->num_staples;
         case OP_NUM_STAPLES_TYPE: return s->type_count[o.arg];
@@ -397,7 +486,7 @@ struct Engine {
         case OP_NUM_STACKED_JUNCTS: return 0;
         case OP_SUM: {
             int sum = 0;
-            for (int k = 0; k < o.n_sum; k++) sum += bs->op_val[o.sum_idx[k]];
+            for (int k = 0; k < o.n_sum; k++) sum += BS()->op_val[o.sum_idx[k]];
             return sum;
         }
         }
@@ -405,26 +494,26 @@ struct Engine {
     }
     // SystemOrderParams::update_move_params (order_params.cpp:595-601)
     LDO_HD void update_move_params() {
-        for (int i = 0; i < ob->n_ops; i++) bs->op_val[i] = calc_op(i);
+        for (int i = 0; i < OB().n_ops; i++) BS()->op_val[i] = calc_op(i);
     }
     LDO_HD double grid_lookup(int b) const {
-        int off = bs->grid_off[b];
+        int off = BS()->grid_off[b];
         if (off < 0) return 0;
-        const BiasDef& bd = ob->biases[b];
+        const BiasDef& bd = OB().biases[b];
         int idx = 0;
         for (int k = 0; k < bd.n_ops; k++) {
-            int v = bs->op_val[bd.op_idx[k]] - bs->grid_lo[b][k];
-            if (v < 0 || v >= bs->grid_n[b][k]) return 0;
-            idx = idx * bs->grid_n[b][k] + v;
+            int v = BS()->op_val[bd.op_idx[k]] - BS()->grid_lo[b][k];
+            if (v < 0 || v >= BS()->grid_n[b][k]) return 0;
+            idx = idx * BS()->grid_n[b][k] + v;
         }
         double g = grid_vals[off + idx];
         return g == g ? g : 0; // NaN marks a point absent from the grid (m_off_grid_bias = 0)
     }
     LDO_HD double calc_bias_fn(int b) const {
-        const BiasDef& bd = ob->biases[b];
+        const BiasDef& bd = OB().biases[b];
         if (bd.type == BIAS_GRID) return grid_lookup(b);
-        int param = bs->op_val[bd.op_idx[0]];
-        int lo = bs->win_min[b], hi = bs->win_max[b];
+        int param = BS()->op_val[bd.op_idx[0]];
+        int lo = BS()->win_min[b], hi = BS()->win_max[b];
         if (bd.type == BIAS_LINEAR_STEP_WELL) {
             // bias_functions.cpp:139-151
             if (param < lo) return bd.slope * (lo - param - 1) + bd.min_bias;
@@ -438,69 +527,69 @@ struct Engine {
     // SystemBiases::calc_move (bias_functions.cpp:475-487)
     LDO_HDN double calc_move_bias() {
         double diff = 0;
-        for (int b = 0; b < ob->n_biases; b++) {
-            double prev = bs->bias_val[b];
+        for (int b = 0; b < OB().n_biases; b++) {
+            double prev = BS()->bias_val[b];
             double nb = calc_bias_fn(b);
-            bs->bias_val[b] = nb;
+            BS()->bias_val[b] = nb;
             diff += nb - prev;
         }
-        bs->move_update_bias += diff;
+        BS()->move_update_bias += diff;
         return diff * ctl.bias_mult;
     }
-    LDO_HD double total_bias() const { return bs->move_update_bias * ctl.bias_mult; }
+    LDO_HD double total_bias() const { return BS()->move_update_bias * ctl.bias_mult; }
 
     // ---- MCMovetype shared helpers (movetypes.cpp:98-158) ----
     LDO_HD int select_random_domain() {
-        int idx = uniform_int(0, sys.s->num_domains - 1);
+        int idx = uniform_int(0, sys.S()->num_domains - 1);
         return sys.domain_by_flat_index(idx);
     }
     LDO_HD bool test_acceptance(double p_ratio) {
-        double p_accept = fmin(1.0, p_ratio) * m->modifier;
+        double p_accept = fmin(1.0, p_ratio) * M()->modifier;
         if (p_accept == 1) return true;
         return p_accept > uniform_real();
     }
     LDO_HD void reset_internal() {
-        m->n_modified = 0;
-        m->n_assigned = 0;
-        m->added_chain = -1;
-        m->rejected = 0;
-        m->modifier = 1;
+        M()->n_modified = 0;
+        M()->n_assigned = 0;
+        M()->added_chain = -1;
+        M()->rejected = 0;
+        M()->modifier = 1;
     }
     LDO_HD void push_assigned(int dd) {
-        if (m->n_assigned >= MoveScratch<K>::A) {
+        if (M()->n_assigned >= MoveScratch<K>::A) {
             sys.fail(LDO_ERR_CAPACITY, 1);
             return;
         }
-        m->assigned[m->n_assigned++] = (short)dd;
+        M()->assigned[M()->n_assigned++] = (short)dd;
     }
     LDO_HD void push_modified(int dd) {
-        if (m->n_modified >= K::D) {
+        if (M()->n_modified >= K::LV) {
             sys.fail(LDO_ERR_CAPACITY, 2);
             return;
         }
-        m->modified[m->n_modified++] = (short)dd;
+        M()->modified[M()->n_modified++] = (short)dd;
     }
     LDO_HD V3 rec_pos(const DomRec& r) const { return v3(r.x, r.y, r.z); }
 
     // MCMovetype::reset_origami (movetypes.cpp:53-85)
     LDO_HDN void reset_origami() {
-        for (int k = 0; k < m->n_assigned; k++) sys.unassign_domain(m->assigned[k]);
-        if (m->added_chain >= 0) {
-            sys.delete_chain(m->added_chain);
-            sys.s->current_c_i -= 1;
+        for (int k = 0; k < M()->n_assigned; k++) sys.unassign_domain(M()->assigned[k]);
+        if (M()->added_chain >= 0) {
+            sys.delete_chain(M()->added_chain);
+            sys.S()->current_c_i -= 1;
         }
-        for (int k = 0; k < m->n_modified; k++) {
-            int dd = m->modified[k];
-            const DomRec& r = m->prev[dd];
+        for (int k = 0; k < M()->n_modified; k++) {
+            int dd = M()->modified[k];
+            const DomRec& r = M()->prev[dd];
             sys.set_checked_domain_config(dd, rec_pos(r), r.ore);
         }
-        sys.s->constraints_violated = 0;
+        sys.S()->constraints_violated = 0;
     }
 
     // staple_is_connector / scan_for_scaffold_domain (movetypes.cpp:160-232); chains tracked by slot
     LDO_HDN bool scan_for_scaffold_domain(int start, uint8_t* participating) {
         // iterative depth-first walk; frame = (entry domain, next index in its chain)
-        short (*st)[2] = m->scan_stack;
+        short (*st)[2] = C()->scan_stack;
         int sp = 0;
         st[0][0] = (short)start;
         st[0][1] = 0;
@@ -509,13 +598,13 @@ struct Engine {
             int dom = st[sp][0];
             int c = sys.chain(dom);
             int base = sys.chain_base(c);
-            int len = sys.s->chain_len[c];
+            int len = sys.S()->chain_len[c];
             bool descended = false;
             while (st[sp][1] < len) {
                 int cur = base + st[sp][1];
                 st[sp][1]++;
                 if (cur == dom) continue;
-                int b = sys.s->bound[cur];
+                int b = sys.S()->bound[cur];
                 if (b < 0) continue;
                 if (sys.chain(b) == c) continue;
                 if (sys.chain(b) == 0) return true;
@@ -537,14 +626,14 @@ struct Engine {
     }
     LDO_HDN bool staple_is_connector(int c) {
         int base = sys.chain_base(c);
-        for (int k = 0; k < sys.s->chain_len[c]; k++) {
+        for (int k = 0; k < sys.S()->chain_len[c]; k++) {
             int dd = base + k;
-            if (sys.s->dom[dd].state != ST_UNBOUND) {
-                int b = sys.s->bound[dd];
+            if (sys.S()->dom[dd].state != ST_UNBOUND) {
+                int b = sys.S()->bound[dd];
                 if (sys.chain(b) == 0) continue;
-                for (int q = 0; q < K::C; q++) m->net_chain[q] = 0;
-                m->net_chain[c] = 1;
-                if (!scan_for_scaffold_domain(b, m->net_chain)) return true;
+                for (int q = 0; q < K::C; q++) C()->net_chain[q] = 0;
+                C()->net_chain[c] = 1;
+                if (!scan_for_scaffold_domain(b, C()->net_chain)) return true;
             }
         }
         return false;
@@ -552,16 +641,16 @@ struct Engine {
     LDO_HD int num_bound_staple_domains(int c) const {
         int n = 0;
         int base = sys.chain_base(c);
-        for (int k = 0; k < sys.s->chain_len[c]; k++) {
-            int st = sys.s->dom[base + k].state;
+        for (int k = 0; k < sys.S()->chain_len[c]; k++) {
+            int st = sys.S()->dom[base + k].state;
             if (st == ST_BOUND || st == ST_MISBOUND) n++;
         }
         return n;
     }
     LDO_HD bool staple_has_bound_domain(int c) const {
         int base = sys.chain_base(c);
-        for (int k = 0; k < sys.s->chain_len[c]; k++) {
-            if (sys.s->dom[base + k].state == ST_BOUND) return true;
+        for (int k = 0; k < sys.S()->chain_len[c]; k++) {
+            if (sys.S()->dom[base + k].state == ST_BOUND) return true;
         }
         return false;
     }
@@ -569,16 +658,16 @@ struct Engine {
     LDO_HD int count_bound_to_other_chains(int c) const {
         int n = 0;
         int base = sys.chain_base(c);
-        for (int k = 0; k < sys.s->chain_len[c]; k++) {
-            int b = sys.s->bound[base + k];
+        for (int k = 0; k < sys.S()->chain_len[c]; k++) {
+            int b = sys.S()->bound[base + k];
             if (b >= 0 && sys.chain(b) != c) n++;
         }
         return n;
     }
     LDO_HD int kth_bound_to_other_chains(int c, int kth) const {
         int base = sys.chain_base(c);
-        for (int k = 0; k < sys.s->chain_len[c]; k++) {
-            int b = sys.s->bound[base + k];
+        for (int k = 0; k < sys.S()->chain_len[c]; k++) {
+            int b = sys.S()->bound[base + k];
             if (b >= 0 && sys.chain(b) != c) {
                 if (kth == 0) return base + k;
                 kth--;
@@ -592,25 +681,25 @@ struct Engine {
         bool accepted = false;
         int dd = select_random_domain();
         int o_new = uniform_int(0, 5);
-        int st = sys.s->dom[dd].state;
+        int st = sys.S()->dom[dd].state;
         if (st == ST_BOUND || st == ST_MISBOUND) {
             double de = 0;
-            int o_old = sys.s->dom[dd].ore;
-            int b = sys.s->bound[dd];
+            int o_old = sys.S()->dom[dd].ore;
+            int b = sys.S()->bound[dd];
             de += sys.unassign_domain(b);
             // set_domain_orientation: domain is now unbound (origami_system.cpp:543-551)
-            sys.s->dom[dd].ore = (int8_t)o_new;
-            V3 p = rec_pos(sys.s->dom[dd]);
+            sys.S()->dom[dd].ore = (int8_t)o_new;
+            V3 p = rec_pos(sys.S()->dom[dd]);
             de += sys.set_domain_config(b, p, o_new ^ 1);
-            if (!sys.s->constraints_violated) accepted = test_acceptance(exp(-de));
+            if (!sys.S()->constraints_violated) accepted = test_acceptance(exp(-de));
             if (!accepted) {
                 sys.unassign_domain(b);
-                sys.s->dom[dd].ore = (int8_t)o_old;
+                sys.S()->dom[dd].ore = (int8_t)o_old;
                 sys.set_checked_domain_config(b, p, o_old < 6 ? (o_old ^ 1) : o_old);
             }
         }
         else {
-            sys.s->dom[dd].ore = (int8_t)o_new;
+            sys.S()->dom[dd].ore = (int8_t)o_new;
             accepted = true;
         }
         return accepted;
@@ -618,10 +707,10 @@ struct Engine {
 
     // ---- growth helpers (movetypes.cpp:322-383, met_movetypes.cpp:50-95) ----
     LDO_HD double set_growth_point(int d_new, int d_old) {
-        const DomRec& ro = sys.s->dom[d_old];
+        const DomRec& ro = sys.S()->dom[d_old];
         int o_new = ro.ore < 6 ? (ro.ore ^ 1) : ro.ore;
         double de = sys.set_domain_config(d_new, rec_pos(ro), o_new);
-        if (sys.s->constraints_violated) m->rejected = 1;
+        if (sys.S()->constraints_violated) M()->rejected = 1;
         else push_assigned(d_new);
         return de;
     }
@@ -630,11 +719,11 @@ struct Engine {
         for (int i = 1; i < count; i++) {
             int dd = first + stepdir * i;
             int prev = first + stepdir * (i - 1);
-            V3 p = rec_pos(sys.s->dom[prev]) + ore_vec(uniform_int(0, 5));
+            V3 p = rec_pos(sys.S()->dom[prev]) + ore_vec(uniform_int(0, 5));
             int o = uniform_int(0, 5);
             delta_e += sys.set_domain_config(dd, p, o);
-            if (sys.s->constraints_violated) {
-                m->rejected = 1;
+            if (sys.S()->constraints_violated) {
+                M()->rejected = 1;
                 break;
             }
             push_assigned(dd);
@@ -643,16 +732,16 @@ struct Engine {
     // RegrowthMCMovetype::grow_staple (movetypes.cpp:343-370)
     LDO_HD void met_grow_staple(int c, int d_i) {
         int base = sys.chain_base(c);
-        int len = sys.s->chain_len[c];
+        int len = sys.S()->chain_len[c];
         if (len - d_i > 1) met_grow_chain(base + d_i, +1, len - d_i);
-        if (m->rejected) return;
+        if (M()->rejected) return;
         if (d_i + 1 > 1) met_grow_chain(base + d_i, -1, d_i + 1);
     }
     LDO_HD void met_unassign_domains(int c) {
         int base = sys.chain_base(c);
-        for (int k = 0; k < sys.s->chain_len[c]; k++) {
+        for (int k = 0; k < sys.S()->chain_len[c]; k++) {
             int dd = base + k;
-            m->prev[dd] = sys.s->dom[dd];
+            M()->prev[dd] = sys.S()->dom[dd];
             push_modified(dd);
             delta_e += sys.unassign_domain(dd);
         }
@@ -665,10 +754,10 @@ struct Engine {
     // ---- MetStapleExchange (met_movetypes.cpp:192-403) ----
     LDO_HD bool exchange_accept(double pratio, int type, bool staple_bound, const MoveDef& md) {
         if (staple_bound) {
-            m->modifier *= ms->exchange_mults[md.exchange_mults_off + type - 1];
-            if (m->modifier * fmin(1.0, pratio) > 1) {
+            M()->modifier *= MS().exchange_mults[md.exchange_mults_off + type - 1];
+            if (M()->modifier * fmin(1.0, pratio) > 1) {
                 if (md.adaptive_exchange) return false; // adaptive multipliers are host-side state: not adapted on device
-                if (ms->allow_nonsensical_ps) return true;
+                if (MS().allow_nonsensical_ps) return true;
                 sys.fail(LDO_ERR_NONSENSICAL_P, type);
                 return false;
             }
@@ -676,28 +765,28 @@ struct Engine {
         return test_acceptance(pratio);
     }
     LDO_HDN bool move_staple_exchange(const MoveDef& md) {
-        SysState<K>* s = sys.s;
+        SysState<K>* s = sys.S();
         delta_e = 0;
         int insertion_sites = s->num_domains;
         if (uniform_real() < 0.5) {
             // insert_staple (:303-359)
-            int type = uniform_int(1, sys.sc->n_types - 1);
-            if (s->num_staples == sys.sc->max_total_staples) return false;
-            if (s->type_count[type] == sys.sc->max_type_staples) return false;
+            int type = uniform_int(1, sys.SC().n_types - 1);
+            if (s->num_staples == sys.SC().max_total_staples) return false;
+            if (s->type_count[type] == sys.SC().max_type_staples) return false;
             int c = sys.add_chain(type);
             if (c < 0) return false;
-            if (sys.sc->apply_mean_field_cor) delta_e += log(6.0);
+            if (sys.SC().apply_mean_field_cor) delta_e += log(6.0);
             delta_e += sys.tt.init_energy;
-            m->added_chain = c;
+            M()->added_chain = c;
             // select_new_growthpoint (movetypes.cpp:372-383)
             int len = s->chain_len[c];
             int g_new = sys.chain_base(c) + uniform_int(0, len - 1);
             int g_old = select_random_domain();
             while (sys.chain(g_old) == c && s->status == LDO_OK) g_old = select_random_domain();
             delta_e += set_growth_point(g_new, g_old);
-            if (m->rejected) return false;
+            if (M()->rejected) return false;
             met_grow_staple(c, s->dindex[g_new]);
-            if (m->rejected) return false;
+            if (M()->rejected) return false;
             bool staple_bound = staple_has_bound_domain(c);
             int num_bd = num_bound_staple_domains(c);
             // staple_insertion_accepted (:212-253)
@@ -705,15 +794,15 @@ struct Engine {
             double boltz = exp(-delta_e);
             int Ni_new = s->type_count[type];
             double pratio = (double)len / 6.0 / Ni_new * boltz;
-            pratio *= insertion_sites * sys.sc->staple_M;
+            pratio *= insertion_sites * sys.SC().staple_M;
             pratio /= num_bd;
             return exchange_accept(pratio, type, staple_bound, md);
         }
         // delete_staple (:361-403)
-        int type = uniform_int(1, sys.sc->n_types - 1);
+        int type = uniform_int(1, sys.SC().n_types - 1);
         int n_of_type = s->type_count[type];
         if (n_of_type == 0) {
-            m->rejected = 1;
+            M()->rejected = 1;
             return false;
         }
         int c = sys.staple_of_type(type, uniform_int(0, n_of_type - 1));
@@ -722,7 +811,7 @@ struct Engine {
         int num_bd = num_bound_staple_domains(c);
         int len = s->chain_len[c];
         met_unassign_domains(c);
-        if (sys.sc->apply_mean_field_cor) delta_e -= log(6.0);
+        if (sys.SC().apply_mean_field_cor) delta_e -= log(6.0);
         delta_e -= sys.tt.init_energy;
         // staple_deletion_accepted (:255-301)
         s->num_staples--;
@@ -731,7 +820,7 @@ struct Engine {
         double boltz = exp(-delta_e);
         int Ni = s->type_count[type];
         double pratio = Ni * 6.0 / (double)len * boltz;
-        pratio /= sys.sc->staple_M * (insertion_sites - len);
+        pratio /= sys.SC().staple_M * (insertion_sites - len);
         pratio *= num_bd;
         bool accepted = exchange_accept(pratio, type, staple_bound, md);
         if (accepted) sys.delete_chain(c);
@@ -740,7 +829,7 @@ struct Engine {
 
     // ---- MetStapleRegrowth (met_movetypes.cpp:470-513) ----
     LDO_HDN bool move_met_staple_regrowth() {
-        SysState<K>* s = sys.s;
+        SysState<K>* s = sys.S();
         delta_e = 0;
         if (s->num_staples == 0) return false;
         int c = s->order[uniform_int(1, s->num_staples)];
@@ -754,9 +843,9 @@ struct Engine {
         int g_old = s->bound[g_new];
         met_unassign_domains(c);
         delta_e += set_growth_point(g_new, g_old);
-        if (m->rejected) return false;
+        if (M()->rejected) return false;
         met_grow_staple(c, s->dindex[g_new]);
-        if (m->rejected) return false;
+        if (M()->rejected) return false;
         met_add_external_bias();
         int new_num_bd = num_bound_staple_domains(c);
         double pratio = exp(-delta_e) * n_bd / new_num_bd;
@@ -777,8 +866,8 @@ struct Engine {
                 kind = 1;
                 w = 6 * exp(-0.0);
             }
-            else if (sys.s->dom[j].state == ST_UNBOUND) {
-                int oj = sys.s->dom[j].ore;
+            else if (sys.S()->dom[j].state == ST_UNBOUND) {
+                int oj = sys.S()->dom[j].ore;
                 o = oj < 6 ? (oj ^ 1) : oj;
                 int ns, partner;
                 System<K> view = sys; // private overlay per lane
@@ -788,23 +877,23 @@ struct Engine {
                     w = exp(-dc.e);
                 }
             }
-            m->site_kind[k] = kind;
-            m->site_o[k] = o;
-            m->site_w[k] = w;
+            M()->site_kind[k] = kind;
+            M()->site_o[k] = o;
+            M()->site_w[k] = w;
         }
         LDO_SYNCWARP();
     }
     // select_and_set_config for CBStapleRegrowth (cb_movetypes.cpp:104-160, 363-387)
     LDO_HDN void cb_select_and_set_config(int dom, int prev_dom, bool regrow_old, double& bias) {
-        V3 p_prev = rec_pos(sys.s->dom[prev_dom]);
+        V3 p_prev = rec_pos(sys.S()->dom[prev_dom]);
         cb_site_weights(p_prev, dom);
-        sys.s->constraints_violated = 0;
+        sys.S()->constraints_violated = 0;
         double ros = 0;
         for (int k = 0; k < 6; k++) {
-            if (m->site_kind[k] != 0) ros += m->site_w[k];
+            if (M()->site_kind[k] != 0) ros += M()->site_w[k];
         }
         if (ros == 0) {
-            m->rejected = 1;
+            M()->rejected = 1;
             return;
         }
         bias *= ros;
@@ -814,11 +903,11 @@ struct Engine {
             V3 p_new = v3(0, 0, 0);
             int o_new = ORE_ZERO;
             for (int k = 0; k < 6; k++) {
-                if (m->site_kind[k] == 0) continue;
-                cum += m->site_w[k] / ros;
+                if (M()->site_kind[k] == 0) continue;
+                cum += M()->site_w[k] / ros;
                 if (r < cum) {
                     p_new = p_prev + ore_vec(k);
-                    o_new = m->site_kind[k] == 2 ? m->site_o[k] : ORE_ZERO;
+                    o_new = M()->site_kind[k] == 2 ? M()->site_o[k] : ORE_ZERO;
                     break;
                 }
             }
@@ -826,7 +915,7 @@ struct Engine {
             sys.set_checked_domain_config(dom, p_new, o_new);
         }
         else {
-            const DomRec& r = m->oldc[dom];
+            const DomRec& r = C()->oldc[dom];
             sys.set_checked_domain_config(dom, rec_pos(r), r.ore);
         }
         push_assigned(dom);
@@ -834,13 +923,13 @@ struct Engine {
     LDO_HD void cb_grow_chain(int first, int stepdir, int count, bool regrow_old, double& bias) {
         for (int i = 1; i < count; i++) {
             cb_select_and_set_config(first + stepdir * i, first + stepdir * (i - 1), regrow_old, bias);
-            if (m->rejected) break;
+            if (M()->rejected) break;
         }
     }
     LDO_HD void cb_set_growthpoint_and_grow_staple(int g_new, int g_old, int c, bool regrow_old, double& bias) {
         if (regrow_old) {
             // set_old_growth_point (cb_movetypes.cpp:168-180)
-            double de = sys.set_checked_domain_config(g_new, rec_pos(sys.s->dom[g_old]), m->oldc[g_new].ore);
+            double de = sys.set_checked_domain_config(g_new, rec_pos(sys.S()->dom[g_old]), C()->oldc[g_new].ore);
             bias *= exp(-de);
             push_assigned(g_new);
         }
@@ -848,26 +937,26 @@ struct Engine {
             double de = set_growth_point(g_new, g_old);
             bias *= exp(-de);
         }
-        if (!m->rejected) {
+        if (!M()->rejected) {
             int base = sys.chain_base(c);
-            int len = sys.s->chain_len[c];
-            int d_i = sys.s->dindex[g_new];
+            int len = sys.S()->chain_len[c];
+            int d_i = sys.S()->dindex[g_new];
             if (len - d_i > 1) cb_grow_chain(base + d_i, +1, len - d_i, regrow_old, bias);
-            if (m->rejected) return;
+            if (M()->rejected) return;
             if (d_i + 1 > 1) cb_grow_chain(base + d_i, -1, d_i + 1, regrow_old, bias);
         }
     }
     LDO_HD void cb_unassign_domains(int c) {
         int base = sys.chain_base(c);
-        for (int k = 0; k < sys.s->chain_len[c]; k++) {
+        for (int k = 0; k < sys.S()->chain_len[c]; k++) {
             int dd = base + k;
-            m->prev[dd] = sys.s->dom[dd];
+            M()->prev[dd] = sys.S()->dom[dd];
             push_modified(dd);
             sys.unassign_domain(dd);
         }
     }
     LDO_HDN bool move_cb_staple_regrowth() {
-        SysState<K>* s = sys.s;
+        SysState<K>* s = sys.S();
         if (s->num_staples == 0) return false;
         int c = s->order[uniform_int(1, s->num_staples)];
         if (staple_is_connector(c)) return false;
@@ -894,25 +983,25 @@ struct Engine {
         int gi = uniform_int(0, n_bd - 1);
         cb_unassign_domains(c);
         cb_set_growthpoint_and_grow_staple(bd_new[gi], bd_old[gi], c, false, bias);
-        if (m->rejected) return false;
+        if (M()->rejected) return false;
         bias /= num_bound_staple_domains(c);
         // add_external_bias (cb_movetypes.cpp:52-56)
         update_move_params();
         bias *= exp(-calc_move_bias());
         // setup_for_regrow_old (cb_movetypes.cpp:237-247)
         double new_bias = bias;
-        double new_modifier = m->modifier;
+        double new_modifier = M()->modifier;
         bias = 1;
-        m->n_modified = 0;
-        m->n_assigned = 0;
+        M()->n_modified = 0;
+        M()->n_assigned = 0;
         {
             int base = sys.chain_base(c);
-            for (int k = 0; k < s->chain_len[c]; k++) m->oldc[base + k] = m->prev[base + k];
+            for (int k = 0; k < s->chain_len[c]; k++) C()->oldc[base + k] = M()->prev[base + k];
         }
         gi = uniform_int(0, n_bd - 1);
         cb_unassign_domains(c);
         cb_set_growthpoint_and_grow_staple(bd_new[gi], bd_old[gi], c, true, bias);
-        m->modifier = new_modifier;
+        M()->modifier = new_modifier;
         // test_cb_acceptance (cb_movetypes.cpp:182-198)
         double ratio = new_bias / bias;
         if (test_acceptance(ratio)) {
@@ -921,96 +1010,96 @@ struct Engine {
             calc_move_bias();
             return true;
         }
-        m->n_modified = 0;
-        m->n_assigned = 0;
+        M()->n_modified = 0;
+        M()->n_assigned = 0;
         return false;
     }
 
     // ---- Constraintpoints (top_constraint_points.cpp:163-601) ----
     LDO_HDN void cp_reset() {
         for (int k = 0; k < K::D; k++) {
-            m->seg_of[k] = -1;
-            m->stem_gp[k] = -1;
-            m->gp_stem[k] = -1;
-            m->inactive[k] = -1;
-            m->stem_seg0[k] = -1;
-            m->in_sel[k] = 0;
+            M()->seg_of[k] = -1;
+            M()->stem_gp[k] = -1;
+            M()->gp_stem[k] = -1;
+            M()->inactive[k] = -1;
+            M()->stem_seg0[k] = -1;
+            C()->in_sel[k] = 0;
         }
-        for (int k = 0; k < K::C; k++) m->checked_chain[k] = 0;
-        for (int k = 0; k < MoveScratch<K>::S; k++) m->scaf_dir[k] = 0;
-        m->n_ep = 0;
-        m->n_ep0 = 0;
-        m->n_erased = 0;
-        m->n_regrow = 0;
-        m->n_sel = 0;
+        for (int k = 0; k < K::C; k++) C()->checked_chain[k] = 0;
+        for (int k = 0; k < MoveScratch<K>::S; k++) M()->scaf_dir[k] = 0;
+        M()->n_ep = 0;
+        C()->n_ep0 = 0;
+        M()->n_erased = 0;
+        M()->n_regrow = 0;
+        C()->n_sel = 0;
     }
     LDO_HD int cp_dir_of(int chain, int seg) const {
-        if (chain == 0) return m->scaf_dir[seg];
+        if (chain == 0) return M()->scaf_dir[seg];
         return seg == 0 ? 1 : -1;
     }
     LDO_HD int cp_get_dir(int dd) const {
-        int seg = m->seg_of[dd] < 0 ? 0 : m->seg_of[dd];
+        int seg = M()->seg_of[dd] < 0 ? 0 : M()->seg_of[dd];
         return cp_dir_of(sys.chain(dd), seg);
     }
     LDO_HDN void cp_add_active_endpoint_seg(int dd, V3 p, int seg) {
-        if (m->n_ep >= MoveScratch<K>::E) {
+        if (M()->n_ep >= MoveScratch<K>::E) {
             sys.fail(LDO_ERR_CAPACITY, 5);
             return;
         }
-        int e = m->n_ep++;
-        m->ep_chain[e] = (short)sys.chain(dd);
-        m->ep_seg[e] = (int8_t)seg;
-        m->ep_d[e] = (short)sys.dindex(dd);
-        m->ep_pos[e][0] = (short)p.x;
-        m->ep_pos[e][1] = (short)p.y;
-        m->ep_pos[e][2] = (short)p.z;
+        int e = M()->n_ep++;
+        M()->ep_chain[e] = (short)sys.chain(dd);
+        M()->ep_seg[e] = (int8_t)seg;
+        M()->ep_d[e] = (short)sys.dindex(dd);
+        M()->ep_pos[e][0] = (short)p.x;
+        M()->ep_pos[e][1] = (short)p.y;
+        M()->ep_pos[e][2] = (short)p.z;
     }
-    LDO_HD void cp_add_active_endpoint(int dd, V3 p) { cp_add_active_endpoint_seg(dd, p, m->seg_of[dd]); }
+    LDO_HD void cp_add_active_endpoint(int dd, V3 p) { cp_add_active_endpoint_seg(dd, p, M()->seg_of[dd]); }
     LDO_HD void cp_erase_ep(int e) {
-        for (int k = e; k + 1 < m->n_ep; k++) {
-            m->ep_chain[k] = m->ep_chain[k + 1];
-            m->ep_seg[k] = m->ep_seg[k + 1];
-            m->ep_d[k] = m->ep_d[k + 1];
-            m->ep_pos[k][0] = m->ep_pos[k + 1][0];
-            m->ep_pos[k][1] = m->ep_pos[k + 1][1];
-            m->ep_pos[k][2] = m->ep_pos[k + 1][2];
+        for (int k = e; k + 1 < M()->n_ep; k++) {
+            M()->ep_chain[k] = M()->ep_chain[k + 1];
+            M()->ep_seg[k] = M()->ep_seg[k + 1];
+            M()->ep_d[k] = M()->ep_d[k + 1];
+            M()->ep_pos[k][0] = M()->ep_pos[k + 1][0];
+            M()->ep_pos[k][1] = M()->ep_pos[k + 1][1];
+            M()->ep_pos[k][2] = M()->ep_pos[k + 1][2];
         }
-        m->n_ep--;
+        M()->n_ep--;
     }
     LDO_HDN void cp_save_initial() {
-        m->n_ep0 = m->n_ep;
-        for (int k = 0; k < m->n_ep; k++) {
-            m->ep0_chain[k] = m->ep_chain[k];
-            m->ep0_seg[k] = m->ep_seg[k];
-            m->ep0_d[k] = m->ep_d[k];
-            m->ep0_pos[k][0] = m->ep_pos[k][0];
-            m->ep0_pos[k][1] = m->ep_pos[k][1];
-            m->ep0_pos[k][2] = m->ep_pos[k][2];
+        C()->n_ep0 = M()->n_ep;
+        for (int k = 0; k < M()->n_ep; k++) {
+            C()->ep0_chain[k] = M()->ep_chain[k];
+            C()->ep0_seg[k] = M()->ep_seg[k];
+            C()->ep0_d[k] = M()->ep_d[k];
+            C()->ep0_pos[k][0] = M()->ep_pos[k][0];
+            C()->ep0_pos[k][1] = M()->ep_pos[k][1];
+            C()->ep0_pos[k][2] = M()->ep_pos[k][2];
         }
     }
     LDO_HDN void cp_reset_active_endpoints() {
-        m->n_ep = m->n_ep0;
-        for (int k = 0; k < m->n_ep0; k++) {
-            m->ep_chain[k] = m->ep0_chain[k];
-            m->ep_seg[k] = m->ep0_seg[k];
-            m->ep_d[k] = m->ep0_d[k];
-            m->ep_pos[k][0] = m->ep0_pos[k][0];
-            m->ep_pos[k][1] = m->ep0_pos[k][1];
-            m->ep_pos[k][2] = m->ep0_pos[k][2];
+        M()->n_ep = C()->n_ep0;
+        for (int k = 0; k < C()->n_ep0; k++) {
+            M()->ep_chain[k] = C()->ep0_chain[k];
+            M()->ep_seg[k] = C()->ep0_seg[k];
+            M()->ep_d[k] = C()->ep0_d[k];
+            M()->ep_pos[k][0] = C()->ep0_pos[k][0];
+            M()->ep_pos[k][1] = C()->ep0_pos[k][1];
+            M()->ep_pos[k][2] = C()->ep0_pos[k][2];
         }
     }
     // remove_active_endpoint (:299-320): erased positions are kept in m_erased_endpoints
     LDO_HDN void cp_remove_active_endpoint(int dd) {
-        m->n_erased = 0;
-        int c = sys.chain(dd), seg = m->seg_of[dd], di_ = sys.dindex(dd);
+        M()->n_erased = 0;
+        int c = sys.chain(dd), seg = M()->seg_of[dd], di_ = sys.dindex(dd);
         int k = 0;
-        while (k < m->n_ep) {
-            if (m->ep_chain[k] == c && m->ep_seg[k] == seg && m->ep_d[k] == di_) {
-                if (m->n_erased < 8) {
-                    m->erased_pos[m->n_erased][0] = m->ep_pos[k][0];
-                    m->erased_pos[m->n_erased][1] = m->ep_pos[k][1];
-                    m->erased_pos[m->n_erased][2] = m->ep_pos[k][2];
-                    m->n_erased++;
+        while (k < M()->n_ep) {
+            if (M()->ep_chain[k] == c && M()->ep_seg[k] == seg && M()->ep_d[k] == di_) {
+                if (M()->n_erased < 8) {
+                    M()->erased_pos[M()->n_erased][0] = M()->ep_pos[k][0];
+                    M()->erased_pos[M()->n_erased][1] = M()->ep_pos[k][1];
+                    M()->erased_pos[M()->n_erased][2] = M()->ep_pos[k][2];
+                    M()->n_erased++;
                 }
                 else {
                     sys.fail(LDO_ERR_CAPACITY, 6);
@@ -1024,11 +1113,11 @@ struct Engine {
     }
     // remove_activated_endpoint (:322-338)
     LDO_HDN void cp_remove_activated_endpoint(int dd) {
-        int ed = m->inactive[dd];
+        int ed = M()->inactive[dd];
         if (ed < 0) return;
-        int c = sys.chain(ed), seg = m->seg_of[ed], di_ = sys.dindex(ed);
-        for (int k = 0; k < m->n_ep; k++) {
-            if (m->ep_chain[k] == c && m->ep_seg[k] == seg && m->ep_d[k] == di_) {
+        int c = sys.chain(ed), seg = M()->seg_of[ed], di_ = sys.dindex(ed);
+        for (int k = 0; k < M()->n_ep; k++) {
+            if (M()->ep_chain[k] == c && M()->ep_seg[k] == seg && M()->ep_d[k] == di_) {
                 cp_erase_ep(k);
                 break;
             }
@@ -1037,15 +1126,18 @@ struct Engine {
     // update_endpoints (:340-349)
     LDO_HDN void cp_update_endpoints(int dd) {
         cp_remove_active_endpoint(dd);
-        int ed = m->inactive[dd];
-        if (ed >= 0) cp_add_active_endpoint(ed, rec_pos(sys.s->dom[dd]));
+        int ed = M()->inactive[dd];
+        if (ed >= 0) cp_add_active_endpoint(ed, rec_pos(sys.S()->dom[dd]));
     }
     // endpoint_reached (:359-372)
-    LDO_HDN bool cp_endpoint_reached(int dd, V3 p) const {
-        int c = sys.chain(dd), seg = m->seg_of[dd], di_ = sys.dindex(dd);
-        for (int k = 0; k < m->n_ep; k++) {
-            if (m->ep_chain[k] == c && m->ep_seg[k] == seg && m->ep_d[k] == di_ && m->ep_pos[k][0] == p.x &&
-                m->ep_pos[k][1] == p.y && m->ep_pos[k][2] == p.z) {
+    LDO_HDN bool cp_endpoint_reached(int dd, V3 p, const EpOverlay* ov = nullptr) const {
+        int c = sys.chain(dd), seg = M()->seg_of[dd], di_ = sys.dindex(dd);
+        if (ov && ov->add_chain == c && ov->add_seg == seg && ov->add_d == di_ && ov->add_pos == p) return true;
+        if (ov && ov->rm_chain == c && ov->rm_seg == seg && ov->rm_d == di_) return false;
+#pragma unroll 1
+        for (int k = 0; k < M()->n_ep; k++) {
+            if (M()->ep_chain[k] == c && M()->ep_seg[k] == seg && M()->ep_d[k] == di_ && M()->ep_pos[k][0] == p.x &&
+                M()->ep_pos[k][1] == p.y && M()->ep_pos[k][2] == p.z) {
                 return true;
             }
         }
@@ -1054,8 +1146,8 @@ struct Engine {
     // calc_remaining_steps (:571-601)
     LDO_HD int cp_remaining_steps(int end_d_i, int dd, int dir_) const {
         int dm = sys.dindex(dd);
-        if (sys.sc->cyclic && sys.chain(dd) == 0) {
-            int n = sys.s->chain_len[0];
+        if (sys.SC().cyclic && sys.chain(dd) == 0) {
+            int n = sys.S()->chain_len[0];
             if (dir_ > 0 && end_d_i < dm) return n + end_d_i - dm;
             if (dir_ < 0 && end_d_i > dm) return dm + n - end_d_i;
             if (dir_ == 0 || end_d_i == dm) return 0;
@@ -1069,45 +1161,52 @@ struct Engine {
         return dr > steps || (steps - dr) % 2 != 0;
     }
     // walks_remain (:397-445)
-    LDO_HD bool cp_walks_remain_seg(int c, int seg, int dd, V3 p) const {
+    LDO_HDN bool cp_walks_remain_seg(int c, int seg, int dd, V3 p, const EpOverlay* ov) const {
         int dir_ = cp_dir_of(c, seg);
-        for (int k = 0; k < m->n_ep; k++) {
-            if (m->ep_chain[k] != c || m->ep_seg[k] != seg) continue;
-            int steps = cp_remaining_steps(m->ep_d[k], dd, dir_);
-            V3 ep = v3(m->ep_pos[k][0], m->ep_pos[k][1], m->ep_pos[k][2]);
+        bool rm = ov && ov->rm_chain == c && ov->rm_seg == seg;
+#pragma unroll 1
+        for (int k = 0; k < M()->n_ep; k++) {
+            if (M()->ep_chain[k] != c || M()->ep_seg[k] != seg) continue;
+            if (rm && M()->ep_d[k] == ov->rm_d) continue;
+            int steps = cp_remaining_steps(M()->ep_d[k], dd, dir_);
+            V3 ep = v3(M()->ep_pos[k][0], M()->ep_pos[k][1], M()->ep_pos[k][2]);
             if (no_walks(p, ep, steps)) return false;
+        }
+        if (ov && ov->add_chain == c && ov->add_seg == seg) {
+            int steps = cp_remaining_steps(ov->add_d, dd, dir_);
+            if (no_walks(p, ov->add_pos, steps)) return false;
         }
         return true;
     }
-    LDO_HDN bool cp_walks_remain(int dd, V3 p) const {
+    LDO_HDN bool cp_walks_remain(int dd, V3 p, const EpOverlay* ov = nullptr) const {
         int c = sys.chain(dd);
-        if (m->stem_gp[dd] >= 0) {
-            int s0 = m->stem_seg0[dd];
+        if (M()->stem_gp[dd] >= 0) {
+            int s0 = M()->stem_seg0[dd];
             if (s0 < 0) return true; // m_stemd_to_segs[domain] default-constructs to an empty list
-            if (!cp_walks_remain_seg(c, s0, dd, p)) return false;
-            return cp_walks_remain_seg(c, s0 + 1, dd, p);
+            if (!cp_walks_remain_seg(c, s0, dd, p, ov)) return false;
+            return cp_walks_remain_seg(c, s0 + 1, dd, p, ov);
         }
-        return cp_walks_remain_seg(c, m->seg_of[dd], dd, p);
+        return cp_walks_remain_seg(c, M()->seg_of[dd], dd, p, ov);
     }
 
     // StapleNetwork::scan_network (top_constraint_points.cpp:36-161), iterative.
     // Returns whether the network is externally bound.
     LDO_HDN bool net_scan(int start) {
-        SysState<K>* s = sys.s;
-        for (int k = 0; k < K::C; k++) m->net_chain[k] = 0;
-        m->net_chain[0] = 1;
-        m->n_pot_gps = 0;
-        m->n_pot_iaes = 0;
-        m->n_pot_ds = 0;
+        SysState<K>* s = sys.S();
+        for (int k = 0; k < K::C; k++) C()->net_chain[k] = 0;
+        C()->net_chain[0] = 1;
+        C()->n_pot_gps = 0;
+        C()->n_pot_iaes = 0;
+        C()->n_pot_ds = 0;
         bool external = false;
-        short (*st)[2] = m->scan_stack;
+        short (*st)[2] = C()->scan_stack;
         int sp = 0;
         // enter frame
         st[0][0] = (short)start;
         st[0][1] = 0;
-        m->net_chain[sys.chain(start)] = 1;
-        m->net_growth_idx[sys.chain(start)] = (short)sys.dindex(start);
-        m->pot_ds[m->n_pot_ds++] = (short)start;
+        C()->net_chain[sys.chain(start)] = 1;
+        C()->net_growth_idx[sys.chain(start)] = (short)sys.dindex(start);
+        C()->pot_ds[C()->n_pot_ds++] = (short)start;
         while (sp >= 0) {
             int g = st[sp][0];
             int ci = sys.chain(g);
@@ -1120,38 +1219,38 @@ struct Engine {
                 // make_staple_stack order: 3' of the growth domain, then 5' (:135-161)
                 int idx = (k < len - 1 - gi) ? (gi + 1 + k) : (gi - 1 - (k - (len - 1 - gi)));
                 int dd = base + idx;
-                m->pot_ds[m->n_pot_ds++] = (short)dd;
+                C()->pot_ds[C()->n_pot_ds++] = (short)dd;
                 int bd = s->bound[dd];
                 if (bd < 0 || sys.chain(bd) == ci) continue;
                 int bd_ci = sys.chain(bd);
-                if (m->net_chain[bd_ci]) {
+                if (C()->net_chain[bd_ci]) {
                     bool ext = false;
-                    if (bd_ci == 0) ext = !m->in_sel[bd];
+                    if (bd_ci == 0) ext = !C()->in_sel[bd];
                     if (!ext) {
                         // add_potential_inactive_endpoint (:155-161)
                         bool bd_in_ds = false;
-                        for (int q = 0; q < m->n_pot_ds; q++) {
-                            if (m->pot_ds[q] == bd) {
+                        for (int q = 0; q < C()->n_pot_ds; q++) {
+                            if (C()->pot_ds[q] == bd) {
                                 bd_in_ds = true;
                                 break;
                             }
                         }
-                        int e = m->n_pot_iaes++;
+                        int e = C()->n_pot_iaes++;
                         if (bd_in_ds) {
-                            m->pot_iaes[e][0] = (short)bd;
-                            m->pot_iaes[e][1] = (short)dd;
+                            C()->pot_iaes[e][0] = (short)bd;
+                            C()->pot_iaes[e][1] = (short)dd;
                         }
                         else {
-                            m->pot_iaes[e][0] = (short)dd;
-                            m->pot_iaes[e][1] = (short)bd;
+                            C()->pot_iaes[e][0] = (short)dd;
+                            C()->pot_iaes[e][1] = (short)bd;
                         }
                     }
                     if (!external && ext) external = true;
                 }
                 else {
-                    int e = m->n_pot_gps++;
-                    m->pot_gps[e][0] = (short)dd;
-                    m->pot_gps[e][1] = (short)bd;
+                    int e = C()->n_pot_gps++;
+                    C()->pot_gps[e][0] = (short)dd;
+                    C()->pot_gps[e][1] = (short)bd;
                     if (sp + 1 >= K::C) {
                         sys.fail(LDO_ERR_CAPACITY, 7);
                         return true;
@@ -1159,9 +1258,9 @@ struct Engine {
                     sp++;
                     st[sp][0] = (short)bd;
                     st[sp][1] = 0;
-                    m->net_chain[bd_ci] = 1;
-                    m->net_growth_idx[bd_ci] = (short)sys.dindex(bd);
-                    m->pot_ds[m->n_pot_ds++] = (short)bd;
+                    C()->net_chain[bd_ci] = 1;
+                    C()->net_growth_idx[bd_ci] = (short)sys.dindex(bd);
+                    C()->pot_ds[C()->n_pot_ds++] = (short)bd;
                     descended = true;
                     break;
                 }
@@ -1173,51 +1272,55 @@ struct Engine {
 
     // find_growthpoints_endpoints (:454-494)
     LDO_HDN void cp_find_growthpoints_endpoints(const short* doms, int n, int seg) {
-        SysState<K>* s = sys.s;
+        SysState<K>* s = sys.S();
         for (int q = 0; q < n; q++) {
             int dd = doms[q];
-            m->regrow[m->n_regrow++] = (short)dd;
-            m->seg_of[dd] = (int8_t)seg;
+            if (M()->n_regrow >= K::LV) {
+                sys.fail(LDO_ERR_CAPACITY, 8);
+                return;
+            }
+            M()->regrow[M()->n_regrow++] = (short)dd;
+            M()->seg_of[dd] = (int8_t)seg;
             int bd = s->bound[dd];
-            if (bd < 0 || sys.chain(bd) == sys.chain(dd) || m->checked_chain[sys.chain(bd)]) continue;
+            if (bd < 0 || sys.chain(bd) == sys.chain(dd) || C()->checked_chain[sys.chain(bd)]) continue;
             bool external = net_scan(bd);
-            int e = m->n_pot_gps++;
-            m->pot_gps[e][0] = (short)dd;
-            m->pot_gps[e][1] = (short)bd;
+            int e = C()->n_pot_gps++;
+            C()->pot_gps[e][0] = (short)dd;
+            C()->pot_gps[e][1] = (short)bd;
             if (external) {
                 // add_active_endpoints_on_scaffold (:540-559)
-                for (int k = 0; k < m->n_pot_gps; k++) {
-                    int gd = m->pot_gps[k][0];
+                for (int k = 0; k < C()->n_pot_gps; k++) {
+                    int gd = C()->pot_gps[k][0];
                     if (sys.chain(gd) == 0) cp_add_active_endpoint_seg(gd, rec_pos(s->dom[gd]), seg);
                 }
-                for (int k = 0; k < m->n_pot_iaes; k++) {
-                    int second = m->pot_iaes[k][1];
+                for (int k = 0; k < C()->n_pot_iaes; k++) {
+                    int second = C()->pot_iaes[k][1];
                     if (sys.chain(second) == 0) {
-                        cp_add_active_endpoint_seg(m->pot_iaes[k][0], rec_pos(s->dom[second]), seg);
+                        cp_add_active_endpoint_seg(C()->pot_iaes[k][0], rec_pos(s->dom[second]), seg);
                     }
                 }
             }
             else {
-                for (int k = 0; k < m->n_pot_gps; k++) {
-                    m->gp_stem[m->pot_gps[k][0]] = m->pot_gps[k][1];
-                    m->stem_gp[m->pot_gps[k][1]] = m->pot_gps[k][0];
+                for (int k = 0; k < C()->n_pot_gps; k++) {
+                    M()->gp_stem[C()->pot_gps[k][0]] = C()->pot_gps[k][1];
+                    M()->stem_gp[C()->pot_gps[k][1]] = C()->pot_gps[k][0];
                 }
-                for (int k = 0; k < m->n_pot_iaes; k++) m->inactive[m->pot_iaes[k][0]] = m->pot_iaes[k][1];
-                for (int k = 0; k < m->n_pot_ds; k++) {
-                    int pd = m->pot_ds[k];
-                    if (m->n_regrow >= K::D) {
+                for (int k = 0; k < C()->n_pot_iaes; k++) M()->inactive[C()->pot_iaes[k][0]] = C()->pot_iaes[k][1];
+                for (int k = 0; k < C()->n_pot_ds; k++) {
+                    int pd = C()->pot_ds[k];
+                    if (M()->n_regrow >= K::LV) {
                         sys.fail(LDO_ERR_CAPACITY, 8);
                         return;
                     }
-                    m->regrow[m->n_regrow++] = (short)pd;
+                    M()->regrow[M()->n_regrow++] = (short)pd;
                     // add_staple_to_segs_maps: unordered_map::insert keeps existing entries (:561-564)
-                    if (m->seg_of[pd] < 0) {
-                        m->seg_of[pd] = (sys.dindex(pd) >= m->net_growth_idx[sys.chain(pd)]) ? 0 : 1;
+                    if (M()->seg_of[pd] < 0) {
+                        M()->seg_of[pd] = (sys.dindex(pd) >= C()->net_growth_idx[sys.chain(pd)]) ? 0 : 1;
                     }
                 }
             }
             for (int k = 0; k < K::C; k++) {
-                if (m->net_chain[k]) m->checked_chain[k] = 1;
+                if (C()->net_chain[k]) C()->checked_chain[k] = 1;
             }
         }
     }
@@ -1225,7 +1328,7 @@ struct Engine {
     // ---- CT selection (movetypes.cpp:469-719) ----
     // select_indices on the whole scaffold, min_length 2, seg 0
     LDO_HDN void ct_select_indices(const MoveDef& md) {
-        SysState<K>* s = sys.s;
+        SysState<K>* s = sys.S();
         int n = s->chain_len[0];
         for (;;) {
             if (s->status != LDO_OK) return;
@@ -1235,7 +1338,7 @@ struct Engine {
             dir = uniform_int(0, 1);
             if (dir == 0) dir = -1;
             // forward part
-            short* buf = m->seg_dom; // scratch: forward list then backward list
+            short* buf = C()->seg_dom; // scratch: forward list then backward list
             int nf = 0, nb = 0;
             int cur = sys.chain_base(0) + start_i;
             while (cur >= 0 && nf != sel_length) {
@@ -1249,17 +1352,17 @@ struct Engine {
                 back = sys.step(back, -dir);
             }
             if (nf + nb < 2) continue;
-            m->n_sel = 0;
-            for (int k = nb - 1; k >= 0; k--) m->sel_scaf[m->n_sel++] = buf[K::D + 1 + k];
-            for (int k = 0; k < nf; k++) m->sel_scaf[m->n_sel++] = buf[k];
+            C()->n_sel = 0;
+            for (int k = nb - 1; k >= 0; k--) C()->sel_scaf[C()->n_sel++] = buf[K::D + 1 + k];
+            for (int k = 0; k < nf; k++) C()->sel_scaf[C()->n_sel++] = buf[k];
             if (cur >= 0) cp_add_active_endpoint_seg(cur, rec_pos(s->dom[cur]), 0);
             return;
         }
     }
 
-    // check_for_stemds (movetypes.cpp:702-719); stems are queued in m->stem_queue[qh..qt)
+    // check_for_stemds (movetypes.cpp:702-719); stems are queued in C()->stem_queue[qh..qt)
     LDO_HDN void ct_check_for_stemds(int cur, int& qt) {
-        SysState<K>* s = sys.s;
+        SysState<K>* s = sys.S();
         if (s->dom[cur].state != ST_BOUND) return;
         int bd = s->bound[cur];
         for (int sd = -1; sd <= 1; sd += 2) {
@@ -1271,12 +1374,12 @@ struct Engine {
                         sys.fail(LDO_ERR_CAPACITY, 9);
                         return;
                     }
-                    m->stem_queue[qt++] = (short)bn;
+                    C()->stem_queue[qt++] = (short)bn;
                 }
             }
         }
     }
-    // fill_seg (movetypes.cpp:666-700). seg contents are appended at m->seg_dom[seg_n...]; returns
+    // fill_seg (movetypes.cpp:666-700). seg contents are appended at C()->seg_dom[seg_n...]; returns
     // whether max_length was reached. `seg_size` counts elements already in the segment.
     LDO_HDN bool ct_fill_seg(int start_d, int max_length, int seg_max, int dir_, int& n_domains, int& qt, int& seg_n, int seg_size) {
         int cur = start_d;
@@ -1286,10 +1389,10 @@ struct Engine {
             next = sys.step(cur, dir_);
             if (next < 0) break;
             int next_next = sys.step(next, dir_);
-            if (next_next >= 0 && m->in_sel[next_next]) break;
-            m->seg_dom[seg_n++] = (short)next;
+            if (next_next >= 0 && C()->in_sel[next_next]) break;
+            C()->seg_dom[seg_n++] = (short)next;
             seg_size++;
-            m->in_sel[next] = 1;
+            C()->in_sel[next] = 1;
             n_domains++;
             if (n_domains == max_length) return true;
             cur = next;
@@ -1298,10 +1401,10 @@ struct Engine {
         return false;
     }
 
-    // select_noncontig_segs (movetypes.cpp:512-648). Segments are laid out in m->seg_dom with
-    // m->seg_start; dirs in m->scaf_dir; stems in m->stems. Returns the number of segments.
+    // select_noncontig_segs (movetypes.cpp:512-648). Segments are laid out in C()->seg_dom with
+    // C()->seg_start; dirs in M()->scaf_dir; stems in C()->stems. Returns the number of segments.
     LDO_HDN int ct_select_noncontig_segs(const MoveDef& md, int& n_stems) {
-        SysState<K>* s = sys.s;
+        SysState<K>* s = sys.S();
         const int SMAX = MoveScratch<K>::S;
         int n = s->chain_len[0];
         int max_length = uniform_int(2, md.max_regrowth);
@@ -1314,24 +1417,24 @@ struct Engine {
         n_stems = 0;
         // paired_empty[k] marks stems whose pair of segments was pushed as {[stem], []} (:556-563)
         // first segment
-        m->seg_start[0] = 0;
-        m->seg_dom[seg_n++] = (short)start_d;
-        m->in_sel[start_d] = 1;
+        C()->seg_start[0] = 0;
+        C()->seg_dom[seg_n++] = (short)start_d;
+        C()->in_sel[start_d] = 1;
         n_domains++;
-        m->scaf_dir[0] = (int8_t)dir_;
+        M()->scaf_dir[0] = (int8_t)dir_;
         bool max_reached = ct_fill_seg(start_d, max_length, seg_max, dir_, n_domains, qt, seg_n, 1);
         n_segs = 1;
-        m->seg_start[1] = (short)seg_n;
+        C()->seg_start[1] = (short)seg_n;
         // paired segment bookkeeping: for stem k, its two segments are 1+2k and 2+2k; pair_first[k]
         // records where the *paired_segs* (without the stem prefix) begin/end for endpoint search.
         while (!max_reached && qh != qt) {
             if (s->status != LDO_OK) return n_segs;
-            int stemd_ = m->stem_queue[qh++];
-            if (m->in_sel[stemd_]) continue;
+            int stemd_ = C()->stem_queue[qh++];
+            if (C()->in_sel[stemd_]) continue;
             bool adjacent = false;
             for (int td = -1; td <= 1; td += 2) {
                 int nd = sys.step(stemd_, td);
-                if (nd >= 0 && m->in_sel[nd]) {
+                if (nd >= 0 && C()->in_sel[nd]) {
                     adjacent = true;
                     break;
                 }
@@ -1341,35 +1444,35 @@ struct Engine {
                 sys.fail(LDO_ERR_CAPACITY, 10);
                 return n_segs;
             }
-            m->in_sel[stemd_] = 1;
+            C()->in_sel[stemd_] = 1;
             n_domains++;
-            m->stems[n_stems++] = (short)stemd_;
+            C()->stems[n_stems++] = (short)stemd_;
             if (n_domains == max_length) {
                 max_reached = true;
                 // segs += [[stem], []], dirs += [1, -1]
-                m->seg_dom[seg_n++] = (short)stemd_;
-                m->seg_start[n_segs + 1] = (short)seg_n;
-                m->seg_start[n_segs + 2] = (short)seg_n;
-                m->scaf_dir[n_segs] = 1;
-                m->scaf_dir[n_segs + 1] = -1;
+                C()->seg_dom[seg_n++] = (short)stemd_;
+                C()->seg_start[n_segs + 1] = (short)seg_n;
+                C()->seg_start[n_segs + 2] = (short)seg_n;
+                M()->scaf_dir[n_segs] = 1;
+                M()->scaf_dir[n_segs + 1] = -1;
                 n_segs += 2;
                 break;
             }
             int dir1 = uniform_int(0, 1);
             if (dir1 == 0) dir1 = -1;
-            m->scaf_dir[n_segs] = (int8_t)dir1;
-            m->scaf_dir[n_segs + 1] = (int8_t)(-dir1);
+            M()->scaf_dir[n_segs] = (int8_t)dir1;
+            M()->scaf_dir[n_segs + 1] = (int8_t)(-dir1);
             bool cur_seg_nonempty = true; // cur_seg = [stem]
             for (int i = 0; i < 2; i++) {
                 int dsel = i == 0 ? dir1 : -dir1;
                 int smax = uniform_int(0, md.max_seg_regrowth);
                 if (i == 0) max_length++; // sic (movetypes.cpp:592-594)
                 // segment i: optional stem prefix, then the filled domains
-                if (cur_seg_nonempty) m->seg_dom[seg_n++] = (short)stemd_;
+                if (cur_seg_nonempty) C()->seg_dom[seg_n++] = (short)stemd_;
                 max_reached = ct_fill_seg(stemd_, max_length, smax, dsel, n_domains, qt, seg_n, 0);
-                m->seg_start[n_segs + i + 1] = (short)seg_n;
+                C()->seg_start[n_segs + i + 1] = (short)seg_n;
                 if (max_reached) {
-                    if (i == 0) m->seg_start[n_segs + 2] = (short)seg_n; // second segment stays empty
+                    if (i == 0) C()->seg_start[n_segs + 2] = (short)seg_n; // second segment stays empty
                     break;
                 }
                 cur_seg_nonempty = false;
@@ -1382,49 +1485,49 @@ struct Engine {
     // ---- CTRG (rg_movetypes.cpp) ----
     LDO_HDN void eq_push_erased() {
         // m_erased_endpoints_q.push_back(get_erased_endpoints())
-        if (m->eq_depth >= MoveScratch<K>::A || m->eq_npos + m->n_erased > MoveScratch<K>::E) {
+        if (M()->eq_depth >= MoveScratch<K>::A || M()->eq_npos + M()->n_erased > MoveScratch<K>::E) {
             sys.fail(LDO_ERR_CAPACITY, 11);
             return;
         }
-        m->eq_start[m->eq_depth++] = (short)m->eq_npos;
-        for (int k = 0; k < m->n_erased; k++) {
-            m->eq_pos[m->eq_npos][0] = m->erased_pos[k][0];
-            m->eq_pos[m->eq_npos][1] = m->erased_pos[k][1];
-            m->eq_pos[m->eq_npos][2] = m->erased_pos[k][2];
-            m->eq_npos++;
+        M()->eq_start[M()->eq_depth++] = (short)M()->eq_npos;
+        for (int k = 0; k < M()->n_erased; k++) {
+            M()->eq_pos[M()->eq_npos][0] = M()->erased_pos[k][0];
+            M()->eq_pos[M()->eq_npos][1] = M()->erased_pos[k][1];
+            M()->eq_pos[M()->eq_npos][2] = M()->erased_pos[k][2];
+            M()->eq_npos++;
         }
     }
     // restore_endpoints (rg:288-295)
     LDO_HDN void rg_restore_endpoints() {
         cp_remove_activated_endpoint(d);
-        if (m->eq_depth <= 0) {
+        if (M()->eq_depth <= 0) {
             sys.fail(LDO_ERR_INTERNAL, 1);
             return;
         }
-        int start = m->eq_start[--m->eq_depth];
-        for (int k = start; k < m->eq_npos; k++) {
-            cp_add_active_endpoint(d, v3(m->eq_pos[k][0], m->eq_pos[k][1], m->eq_pos[k][2]));
+        int start = M()->eq_start[--M()->eq_depth];
+        for (int k = start; k < M()->eq_npos; k++) {
+            cp_add_active_endpoint(d, v3(M()->eq_pos[k][0], M()->eq_pos[k][1], M()->eq_pos[k][2]));
         }
-        m->eq_npos = start;
+        M()->eq_npos = start;
     }
     // unassign_and_save_domains() (rg:67-87)
     LDO_HDN double rg_unassign_and_save_domains() {
         double de = 0;
-        m->prev[m->regrow[0]] = sys.s->dom[m->regrow[0]];
-        for (int k = 1; k < m->n_regrow; k++) {
-            int dd = m->regrow[k];
-            m->prev[dd] = sys.s->dom[dd];
+        M()->prev[M()->regrow[0]] = sys.S()->dom[M()->regrow[0]];
+        for (int k = 1; k < M()->n_regrow; k++) {
+            int dd = M()->regrow[k];
+            M()->prev[dd] = sys.S()->dom[dd];
             push_modified(dd);
             de += sys.unassign_domain(dd);
         }
-        m->eq_depth = 0;
-        m->eq_npos = 0;
+        M()->eq_depth = 0;
+        M()->eq_npos = 0;
         return de;
     }
     LDO_HD void rg_unassign_domains() {
-        for (int k = 1; k < m->n_regrow; k++) sys.unassign_domain(m->regrow[k]);
-        m->eq_depth = 0;
-        m->eq_npos = 0;
+        for (int k = 1; k < M()->n_regrow; k++) sys.unassign_domain(M()->regrow[k]);
+        M()->eq_depth = 0;
+        M()->eq_npos = 0;
     }
     // set_config (rg:233-244)
     LDO_HDN double rg_set_config(int dd, V3 p, int o) {
@@ -1438,14 +1541,14 @@ struct Engine {
     // prepare_for_growth (rg:246-262)
     LDO_HDN void rg_prepare_for_growth() {
         di++;
-        d = m->regrow[di];
-        stemd = m->stem_gp[d] >= 0;
+        d = M()->regrow[di];
+        stemd = M()->stem_gp[d] >= 0;
         dir = cp_get_dir(d);
         c_attempts = 0;
         if (stemd) {
             d_max_c_attempts = 1;
             avail = 0;
-            ref_d = m->stem_gp[d];
+            ref_d = M()->stem_gp[d];
         }
         else {
             d_max_c_attempts = max_c_attempts;
@@ -1462,7 +1565,7 @@ struct Engine {
         if (use_memo) {
             // the memo is keyed by the parent's site only: unusable when the current domain could bind
             // to the (unbound) parent itself, because that depends on the parent's orientation
-            V3 dq = rec_pos(sys.s->dom[m->regrow[di - 1]]) - rec_pos(sys.s->dom[ref_d]);
+            V3 dq = rec_pos(sys.S()->dom[M()->regrow[di - 1]]) - rec_pos(sys.S()->dom[ref_d]);
             if (abssum(dq) == 1) use_memo = false;
         }
         if (use_memo) {
@@ -1477,60 +1580,112 @@ struct Engine {
             rg_compute_slot(cur_slot);
         }
     }
-    // Evaluates the six neighbour sites of the reference domain for the current domain, one site per
-    // lane, read-only (calc_p_config_open, rg:315-343, for all 36 configurations at once).
-    LDO_HDN void rg_compute_slot(int slot) {
-        RgSlot& sl = m->slots[slot];
-        V3 refp = rec_pos(sys.s->dom[ref_d]);
-        for (int k = LDO_LANE; k < 6; k += LDO_NLANES) {
-            V3 r = refp + ore_vec(k);
-            int j = sys.occupant(r);
-            int kind = 0, o = ORE_ZERO;
-            double pv = 0;
-            if (j < 0) {
-                kind = 1;
-                pv = cp_walks_remain(d, r) ? 1.0 : 0.0;
-            }
-            else if (sys.s->dom[j].state == ST_UNBOUND && sys.s->dom[j].ore < 6) {
-                o = sys.s->dom[j].ore ^ 1;
-                int ns, partner;
-                DeltaConfig dc = sys.eval_place(d, r, o, &ns, &partner);
-                if (!dc.violated && cp_walks_remain(d, r)) {
-                    bool same_chain = sys.chain(j) == sys.chain(d);
-                    if (same_chain || stemd || cp_endpoint_reached(d, r)) {
-                        kind = 2;
-                        pv = fmin(1.0, exp(-dc.e));
-                    }
+    // Open probability data of domain `dom` at site r (calc_p_config_open, rg:315-343, for the six
+    // orientations of the site at once); read-only, callable concurrently by different lanes.
+    LDO_HDN void rg_eval_site(int dom, bool dom_is_stem, V3 r, const EpOverlay* ov, int& kind, int& o, double& pv) {
+        kind = 0;
+        o = ORE_ZERO;
+        pv = 0;
+        int j = sys.occupant(r);
+        if (j < 0) {
+            kind = 1;
+            pv = cp_walks_remain(dom, r, ov) ? 1.0 : 0.0;
+        }
+        else if (sys.S()->dom[j].state == ST_UNBOUND && sys.S()->dom[j].ore < 6) {
+            o = sys.S()->dom[j].ore ^ 1;
+            int ns, partner;
+            System<K> view = sys; // lane-private overlay (the engine object is shared by the warp)
+            DeltaConfig dc = view.eval_place(dom, r, o, &ns, &partner);
+            if (!dc.violated && cp_walks_remain(dom, r, ov)) {
+                bool same_chain = sys.chain(j) == sys.chain(dom);
+                if (same_chain || dom_is_stem || cp_endpoint_reached(dom, r, ov)) {
+                    kind = 2;
+                    pv = fmin(1.0, exp(-dc.e));
                 }
             }
+        }
+    }
+    // Evaluates the six neighbour sites of the reference domain for the current domain, one site per
+    // lane, read-only.
+    LDO_HDN void rg_compute_slot(int slot) {
+        RgSlot& sl = M()->slots[slot];
+        V3 refp = rec_pos(sys.S()->dom[ref_d]);
+        for (int k = LDO_LANE; k < 6; k += LDO_NLANES) {
+            int kind, o;
+            double pv;
+            rg_eval_site(d, stemd != 0, refp + ore_vec(k), nullptr, kind, o, pv);
             sl.kind[k] = (uint8_t)kind;
             sl.ore[k] = (int8_t)o;
             sl.p[k] = pv;
-#if defined(LDO_DEBUG_SLOTS) && !defined(__CUDA_ARCH__)
-            printf("  compute slot=%d di=%d d=%d ref_d=%d k=%d r=(%d %d %d) j=%d kind=%d o=%d p=%g n_ep=%d\n", slot, di, d, ref_d, k, r.x, r.y, r.z, j, kind, o, pv, m->n_ep);
-#endif
         }
         LDO_SYNCWARP();
+    }
+    // Feeler slots of the NEXT domain for every empty parent site of the current domain, all 36
+    // (parent site, feeler site) pairs spread over the lanes and evaluated read-only: the parent is not
+    // placed; its only effects on the feeler (it is unbound on an empty site) are the endpoint updates
+    // carried by an EpOverlay. Fills the memo slots and memo_mask. `fd` / `fref`: feeler domain and its
+    // reference domain (the parent itself, or an already placed domain).
+    LDO_HDN void rg_fill_feeler_memo(int fd, int fref) {
+        const RgSlot& own = M()->slots[cur_slot];
+        V3 refp = rec_pos(sys.S()->dom[ref_d]);
+        bool fref_is_parent = fref == d;
+        V3 frefp = fref_is_parent ? v3(0, 0, 0) : rec_pos(sys.S()->dom[fref]);
+        int mask = 0;
+        for (int pc = 0; pc < 6; pc++) {
+            if (own.kind[pc] != 1) continue;
+            // a feeler that can reach the parent's own site would bind to the parent: orientation dependent
+            if (!fref_is_parent && abssum(refp + ore_vec(pc) - frefp) == 1) continue;
+            mask |= 1 << pc;
+        }
+        EpOverlay ov;
+        ov.rm_chain = sys.chain(d);
+        ov.rm_seg = M()->seg_of[d];
+        ov.rm_d = sys.dindex(d);
+        int ie = M()->inactive[d];
+        ov.add_chain = -1;
+        ov.add_seg = 0;
+        ov.add_d = 0;
+        if (ie >= 0) {
+            ov.add_chain = sys.chain(ie);
+            ov.add_seg = M()->seg_of[ie];
+            ov.add_d = sys.dindex(ie);
+        }
+        for (int t = LDO_LANE; t < 36; t += LDO_NLANES) {
+            int pc = t / 6, k = t - 6 * pc;
+            if (!((mask >> pc) & 1)) continue;
+            V3 q = refp + ore_vec(pc);
+            ov.add_pos = q;
+            V3 r = (fref_is_parent ? q : frefp) + ore_vec(k);
+            int kind, o;
+            double pv;
+            rg_eval_site(fd, false, r, &ov, kind, o, pv);
+            RgSlot& sl = M()->slots[LDO_RG_OWN_SLOTS + pc];
+            sl.kind[k] = (uint8_t)kind;
+            sl.ore[k] = (int8_t)o;
+            sl.p[k] = pv;
+        }
+        LDO_SYNCWARP();
+        memo_mask = mask;
     }
     // prepare_for_regrowth (rg:264-286)
     LDO_HDN double rg_prepare_for_regrowth() {
         di--;
-        d = m->regrow[di];
+        d = M()->regrow[di];
         dir = cp_get_dir(d);
         double de = sys.unassign_domain(d);
-        if (m->n_assigned > 0) m->n_assigned--;
+        if (M()->n_assigned > 0) M()->n_assigned--;
         rg_restore_endpoints();
-        stemd = m->stem_gp[d] >= 0;
+        stemd = M()->stem_gp[d] >= 0;
         if (stemd) {
             d_max_c_attempts = 1;
             c_attempts = 1;
             avail = 0;
-            ref_d = m->stem_gp[d];
+            ref_d = M()->stem_gp[d];
         }
         else {
             d_max_c_attempts = max_c_attempts;
-            c_attempts = m->c_attempts_q[di];
-            avail = m->avail_q[di];
+            c_attempts = M()->c_attempts_q[di];
+            avail = M()->avail_q[di];
             ref_d = sys.step(d, -dir);
             cur_slot = di & (LDO_RG_OWN_SLOTS - 1);
             rg_compute_slot(cur_slot);
@@ -1541,7 +1696,7 @@ struct Engine {
     // ordered configuration list and returns its open probability from the current slot
     LDO_HDN double rg_trial(V3& p, int& o) {
         if (stemd) {
-            const DomRec& r = sys.s->dom[ref_d];
+            const DomRec& r = sys.S()->dom[ref_d];
             p = rec_pos(r);
             o = r.ore < 6 ? (r.ore ^ 1) : r.ore;
             last_pc = -1;
@@ -1555,8 +1710,8 @@ struct Engine {
         // m_all_configs = all_pairs(vectors): position-major, orientation-minor (utility.hpp:167-177)
         int pc = i / 6;
         o = i - 6 * pc;
-        p = ore_vec(pc) + rec_pos(sys.s->dom[ref_d]);
-        const RgSlot& sl = m->slots[cur_slot];
+        p = ore_vec(pc) + rec_pos(sys.S()->dom[ref_d]);
+        const RgSlot& sl = M()->slots[cur_slot];
         int kind = sl.kind[pc];
         last_pc = pc;
         last_kind = kind;
@@ -1565,11 +1720,11 @@ struct Engine {
         else if (kind == 2 && o == sl.ore[pc]) pv = sl.p[pc];
 #if defined(LDO_DEBUG_SLOTS) && !defined(__CUDA_ARCH__)
         {
-            DomRec saved = sys.s->dom[d];
+            DomRec saved = sys.S()->dom[d];
             double pref = rg_calc_p_config_open(p, o);
-            sys.s->dom[d] = saved;
+            sys.S()->dom[d] = saved;
             if (pref != pv) {
-                for (int q = 0; q < m->n_ep; q++) printf("   ep chain=%d seg=%d d=%d pos=(%d %d %d)\n", m->ep_chain[q], m->ep_seg[q], m->ep_d[q], m->ep_pos[q][0], m->ep_pos[q][1], m->ep_pos[q][2]);
+                for (int q = 0; q < M()->n_ep; q++) printf("   ep chain=%d seg=%d d=%d pos=(%d %d %d)\n", M()->ep_chain[q], M()->ep_seg[q], M()->ep_d[q], M()->ep_pos[q][0], M()->ep_pos[q][1], M()->ep_pos[q][2]);
                 printf("SLOT MISMATCH p=(%d %d %d) di=%d d=%d ci=%d pc=%d o=%d kind=%d slot=%d pv=%g ref=%g stemd=%d memo_level=%d memo_key=%d\n", p.x, p.y, p.z, di, d, i, pc, o, kind, cur_slot, pv, pref, stemd, memo_level, memo_key);
             }
         }
@@ -1579,13 +1734,13 @@ struct Engine {
     // calc_p_config_open (rg:315-343)
     LDO_HDN double rg_calc_p_config_open(V3 p, int o) {
         double de = sys.check_domain_constraints(d, p, o);
-        if (sys.s->constraints_violated) {
-            sys.s->constraints_violated = 0;
+        if (sys.S()->constraints_violated) {
+            sys.S()->constraints_violated = 0;
             return 0;
         }
         if (!cp_walks_remain(d, p)) return 0;
         int j = sys.occupant(p);
-        if (j >= 0 && sys.s->dom[j].state == ST_UNBOUND) {
+        if (j >= 0 && sys.S()->dom[j].state == ST_UNBOUND) {
             bool same_chain = sys.chain(j) == sys.chain(d);
             bool endpoint = cp_endpoint_reached(d, p);
             if (!(same_chain || endpoint || stemd)) return 0;
@@ -1602,14 +1757,14 @@ struct Engine {
     LDO_HDN double rg_recoil_regrow() {
         double de = 0;
         di = 0;
-        d = m->regrow[0];
+        d = M()->regrow[0];
         dir = cp_get_dir(d);
-        m->c_opens[0] = 1;
+        M()->c_opens[0] = 1;
         rg_prepare_for_growth();
         int recoils = 0;
         for (;;) {
-            if (sys.s->status != LDO_OK) {
-                m->rejected = 1;
+            if (sys.S()->status != LDO_OK) {
+                M()->rejected = 1;
                 break;
             }
             V3 p = v3(0, 0, 0);
@@ -1624,15 +1779,15 @@ struct Engine {
             if (c_open) {
                 if (recoils != 0) recoils--;
                 de += rg_set_config(d, p, o);
-                m->c_attempts_q[di] = (uint8_t)c_attempts;
-                m->avail_q[di] = avail;
-                m->c_opens[di] = p_c_open;
-                if (di == m->n_regrow - 1) break;
+                M()->c_attempts_q[di] = (uint8_t)c_attempts;
+                M()->avail_q[di] = avail;
+                M()->c_opens[di] = p_c_open;
+                if (di == M()->n_regrow - 1) break;
                 rg_prepare_for_growth();
             }
             else {
                 if (recoils == max_recoils || di == 1) {
-                    m->rejected = 1;
+                    M()->rejected = 1;
                     break;
                 }
                 recoils++;
@@ -1644,11 +1799,11 @@ struct Engine {
     // test_config_avail (rg:422-480)
     LDO_HDN bool rg_test_config_avail() {
         int feels = 0;
-        if (feels == max_recoils || di == m->n_regrow - 1) return true;
+        if (feels == max_recoils || di == M()->n_regrow - 1) return true;
         rg_prepare_for_growth();
         bool c_avail = false;
         for (;;) {
-            if (sys.s->status != LDO_OK) break;
+            if (sys.S()->status != LDO_OK) break;
             V3 p = v3(0, 0, 0);
             int o = 0;
             bool c_open = false;
@@ -1660,14 +1815,14 @@ struct Engine {
             }
             if (c_open) {
                 feels++;
-                if (feels == max_recoils || di == m->n_regrow - 1) {
+                if (feels == max_recoils || di == M()->n_regrow - 1) {
                     feels--;
                     c_avail = true;
                     break;
                 }
                 rg_set_config(d, p, o);
-                m->c_attempts_q[di] = (uint8_t)c_attempts;
-                m->avail_q[di] = avail;
+                M()->c_attempts_q[di] = (uint8_t)c_attempts;
+                M()->avail_q[di] = avail;
                 rg_prepare_for_growth();
             }
             else {
@@ -1682,39 +1837,68 @@ struct Engine {
         while (feels != 0) {
             di--;
             feels--;
-            d = m->regrow[di];
+            d = M()->regrow[di];
             sys.unassign_domain(d);
             rg_restore_endpoints();
         }
         di--;
-        d = m->regrow[di];
+        d = M()->regrow[di];
         return c_avail;
     }
     // calc_weights (rg:363-417)
     LDO_HDN void rg_calc_weights() {
         di = 0;
-        d = m->regrow[0];
-        while (di != m->n_regrow - 1) {
-            if (sys.s->status != LDO_OK) return;
+        d = M()->regrow[0];
+        while (di != M()->n_regrow - 1) {
+            if (sys.S()->status != LDO_OK) return;
             di++;
-            d = m->regrow[di];
-            stemd = m->stem_gp[d] >= 0;
+            d = M()->regrow[di];
+            stemd = M()->stem_gp[d] >= 0;
             dir = cp_get_dir(d);
             int avail_cs = 1;
             if (!stemd) {
                 ref_d = sys.step(d, -dir);
-                int catt = m->c_attempts_wq[di];
-                avail = m->avail_wq[di];
+                int catt = M()->c_attempts_wq[di];
+                avail = M()->avail_wq[di];
                 memo_level = -1;
                 memo_mask = 0;
                 cur_slot = di & (LDO_RG_OWN_SLOTS - 1);
                 if (catt != max_c_attempts) rg_compute_slot(cur_slot);
+                // With one feeler level (max_num_recoils == 1) an open trial configuration on an EMPTY
+                // site only needs "does the next domain have an open configuration"; that depends on the
+                // site, not on the orientation, so after the first orientation of a site has been
+                // examined for real the remaining ones replay the feeler's draws on the memoised slot
+                // without touching the lattice. (The reference sets and unsets the domain each time,
+                // rg:378-402; the net state change is nil.)
+                bool last_level = di == M()->n_regrow - 1;
+                bool feeler_simple = false;
+                V3 feeler_refp = v3(0, 0, 0);
+                bool feeler_ref_is_parent = false;
+                if (!last_level && max_recoils == 1 && catt != max_c_attempts) {
+                    int fd = M()->regrow[di + 1];
+                    if (M()->stem_gp[fd] < 0) {
+                        int fref = sys.step(fd, -cp_get_dir(fd));
+                        feeler_simple = true;
+                        feeler_ref_is_parent = fref == d;
+                        if (!feeler_ref_is_parent) feeler_refp = rec_pos(sys.S()->dom[fref]);
+                        rg_fill_feeler_memo(fd, fref);
+                    }
+                }
                 while (catt != max_c_attempts) {
                     catt++;
                     V3 p;
                     int o;
                     double p_c_open = rg_trial(p, o);
                     if (rg_test_config_open(p_c_open)) {
+                        if (last_level && max_recoils >= 1) {
+                            avail_cs += 1;
+                            continue;
+                        }
+                        if (feeler_simple && last_kind == 1 && ((memo_mask >> last_pc) & 1) &&
+                            (feeler_ref_is_parent || abssum(p - feeler_refp) != 1)) {
+                            avail_cs += rg_feeler_from_slot(LDO_RG_OWN_SLOTS + last_pc) ? 1 : 0;
+                            continue;
+                        }
                         sys.set_checked_domain_config(d, p, o);
                         cp_update_endpoints(d);
                         eq_push_erased();
@@ -1734,47 +1918,66 @@ struct Engine {
                     }
                 }
             }
-            weight *= avail_cs / m->c_opens[di - 1];
-            const DomRec& r = m->prev[d];
+            weight *= avail_cs / M()->c_opens[di - 1];
+            const DomRec& r = M()->prev[d];
             sys.set_checked_domain_config(d, rec_pos(r), r.ore);
             cp_update_endpoints(d);
             eq_push_erased();
         }
-        weight /= m->c_opens[di];
+        weight /= M()->c_opens[di];
+    }
+    // test_config_avail (rg:422-480) for a single feeler level, replayed on an already computed slot:
+    // same draws as the general path, no lattice updates
+    LDO_HDN bool rg_feeler_from_slot(int slot) {
+        const RgSlot& sl = M()->slots[slot];
+        unsigned long long av = all_cis();
+        for (int catt = 0; catt != max_c_attempts; catt++) {
+            int ci = uniform_int(0, popc36(av) - 1);
+            int i = nth_set_bit36(av, ci);
+            av &= ~(1ull << i);
+            int pc = i / 6;
+            int o = i - 6 * pc;
+            int kind = sl.kind[pc];
+            double pv = 0;
+            if (kind == 1) pv = sl.p[pc];
+            else if (kind == 2 && o == sl.ore[pc]) pv = sl.p[pc];
+            if (rg_test_config_open(pv)) return true;
+        }
+        return false;
     }
     // calc_old_c_opens (rg:482-513)
     LDO_HDN void rg_calc_old_c_opens() {
         di = 0;
-        m->c_opens[0] = 1;
-        while (di != m->n_regrow - 1) {
+        M()->c_opens[0] = 1;
+        while (di != M()->n_regrow - 1) {
             di++;
-            d = m->regrow[di];
-            m->c_attempts_q[di] = 1;
-            const DomRec r = m->oldc[d];
+            d = M()->regrow[di];
+            M()->c_attempts_q[di] = 1;
+            const DomRec r = C()->oldc[d];
             V3 p = rec_pos(r);
-            stemd = m->stem_gp[d] >= 0;
-            m->c_opens[di] = rg_calc_p_config_open(p, r.ore);
+            stemd = M()->stem_gp[d] >= 0;
+            M()->c_opens[di] = rg_calc_p_config_open(p, r.ore);
             rg_set_config(d, p, r.ore);
             if (stemd) {
-                m->avail_q[di] = 0;
+                M()->avail_q[di] = 0;
             }
             else {
                 dir = cp_get_dir(d);
                 ref_d = sys.step(d, -dir);
-                V3 rel = p - rec_pos(m->oldc[ref_d]);
+                V3 rel = p - rec_pos(C()->oldc[ref_d]);
                 int pc = ore_code(rel);
                 int ci = pc * 6 + r.ore;
                 unsigned long long a = all_cis();
                 if (pc < 6 && r.ore >= 0 && r.ore < 6) a &= ~(1ull << ci);
                 else sys.fail(LDO_ERR_INTERNAL, 2); // m_config_to_i.at(c) would throw
-                m->avail_q[di] = a;
+                M()->avail_q[di] = a;
             }
         }
     }
     LDO_HD void rg_copy_queues_to_wq() {
-        for (int k = 0; k < m->n_regrow; k++) {
-            m->c_attempts_wq[k] = m->c_attempts_q[k];
-            m->avail_wq[k] = m->avail_q[k];
+        for (int k = 0; k < M()->n_regrow; k++) {
+            M()->c_attempts_wq[k] = M()->c_attempts_q[k];
+            M()->avail_wq[k] = M()->avail_q[k];
         }
     }
 
@@ -1783,15 +1986,15 @@ struct Engine {
     LDO_HDN bool rg_regrow_and_test(bool remove_first_a, bool remove_first_b, int first_dom) {
         delta_e += rg_unassign_and_save_domains();
         delta_e += rg_recoil_regrow();
-        if (m->rejected) return false;
+        if (M()->rejected) return false;
         // excluded staples: the reference hard-codes zero of them (simulation.cpp:410,527)
         update_move_params();
         delta_e += calc_move_bias();
 
         // new-configuration weights (setup_for_calc_new_weights, rg:147-153)
         rg_copy_queues_to_wq();
-        for (int k = 0; k < m->n_regrow; k++) m->oldc[m->regrow[k]] = m->prev[m->regrow[k]];
-        m->n_modified = 0;
+        for (int k = 0; k < M()->n_regrow; k++) C()->oldc[M()->regrow[k]] = M()->prev[M()->regrow[k]];
+        M()->n_modified = 0;
         rg_unassign_and_save_domains();
         cp_reset_active_endpoints();
         if (remove_first_a) cp_remove_active_endpoint(first_dom);
@@ -1806,8 +2009,8 @@ struct Engine {
         weight_new = weight;
         weight = 1;
         rg_copy_queues_to_wq();
-        for (int k = 0; k < m->n_regrow; k++) m->newc[m->regrow[k]] = m->prev[m->regrow[k]];
-        m->n_modified = 0;
+        for (int k = 0; k < M()->n_regrow; k++) C()->newc[M()->regrow[k]] = M()->prev[M()->regrow[k]];
+        M()->n_modified = 0;
         rg_unassign_and_save_domains();
         cp_reset_active_endpoints();
         if (remove_first_a) cp_remove_active_endpoint(first_dom);
@@ -1816,12 +2019,12 @@ struct Engine {
         // test_rg_acceptance (rg:515-533)
         double ratio = weight_new / weight * exp(-delta_e);
         if (test_acceptance(ratio)) {
-            for (int k = 0; k < m->n_regrow; k++) m->prev[m->regrow[k]] = m->newc[m->regrow[k]];
+            for (int k = 0; k < M()->n_regrow; k++) M()->prev[M()->regrow[k]] = C()->newc[M()->regrow[k]];
             reset_origami();
             return true;
         }
-        m->n_modified = 0;
-        m->n_assigned = 0;
+        M()->n_modified = 0;
+        M()->n_assigned = 0;
         return false;
     }
 
@@ -1836,71 +2039,71 @@ struct Engine {
         memo_key = -1;
         memo_mask = 0;
         cur_slot = 0;
-        m->eq_depth = 0;
-        m->eq_npos = 0;
+        M()->eq_depth = 0;
+        M()->eq_npos = 0;
     }
 
     // CTRGScaffoldRegrowthMCMovetype::internal_attempt_move (rg:629-689)
     LDO_HDN bool move_ctrg_scaffold(const MoveDef& md) {
         rg_reset(md);
         ct_select_indices(md);
-        if (sys.s->status != LDO_OK) return false;
+        if (sys.S()->status != LDO_OK) return false;
         // setup_constraints (rg:134-145)
-        for (int k = 0; k < m->n_sel; k++) m->in_sel[m->sel_scaf[k]] = 1;
-        m->scaf_dir[0] = (int8_t)dir;
-        cp_find_growthpoints_endpoints(m->sel_scaf, m->n_sel, 0);
+        for (int k = 0; k < C()->n_sel; k++) C()->in_sel[C()->sel_scaf[k]] = 1;
+        M()->scaf_dir[0] = (int8_t)dir;
+        cp_find_growthpoints_endpoints(C()->sel_scaf, C()->n_sel, 0);
         cp_save_initial();
-        int n_scaf = sys.s->chain_len[0];
-        bool cyc = sys.sc->cyclic != 0;
-        if (!(cyc && m->n_sel == n_scaf)) cp_remove_active_endpoint(m->sel_scaf[0]);
-        bool guard_a = !(cyc && m->n_regrow == n_scaf);
-        bool guard_b = !cyc && m->n_regrow == n_scaf; // sic (rg:671, App. A2)
-        return rg_regrow_and_test(guard_a, guard_b, m->regrow[0]);
+        int n_scaf = sys.S()->chain_len[0];
+        bool cyc = sys.SC().cyclic != 0;
+        if (!(cyc && C()->n_sel == n_scaf)) cp_remove_active_endpoint(C()->sel_scaf[0]);
+        bool guard_a = !(cyc && M()->n_regrow == n_scaf);
+        bool guard_b = !cyc && M()->n_regrow == n_scaf; // sic (rg:671, App. A2)
+        return rg_regrow_and_test(guard_a, guard_b, M()->regrow[0]);
     }
 
     // CTRGJumpScaffoldRegrowthMCMovetype::internal_attempt_move (rg:791-851)
     LDO_HDN bool move_ctrg_jump_scaffold(const MoveDef& md) {
-        SysState<K>* s = sys.s;
+        SysState<K>* s = sys.S();
         rg_reset(md);
         int n_stems = 0;
         int n_segs = ct_select_noncontig_segs(md, n_stems);
         if (s->status != LDO_OK) return false;
         // endpoints registered by select_noncontig_segs (movetypes.cpp:618-647)
         {
-            int last = m->seg_dom[m->seg_start[1] - 1];
-            int nd = sys.step(last, m->scaf_dir[0]);
+            int last = C()->seg_dom[C()->seg_start[1] - 1];
+            int nd = sys.step(last, M()->scaf_dir[0]);
             if (nd >= 0) cp_add_active_endpoint_seg(nd, rec_pos(s->dom[nd]), 0);
         }
         for (int k = 0; k < n_stems; k++) {
-            int stem = m->stems[k];
+            int stem = C()->stems[k];
             int gp = s->bound[stem];
-            m->gp_stem[gp] = (short)stem;
-            m->stem_gp[stem] = (short)gp;
+            M()->gp_stem[gp] = (short)stem;
+            M()->stem_gp[stem] = (short)gp;
             int seg_i = 1 + 2 * k;
-            m->stem_seg0[stem] = (int8_t)seg_i;
+            M()->stem_seg0[stem] = (int8_t)seg_i;
             for (int q = 0; q < 2; q++) {
                 int sg = seg_i + q;
-                int a = m->seg_start[sg], b = m->seg_start[sg + 1];
+                int a = C()->seg_start[sg], b = C()->seg_start[sg + 1];
                 // paired_segs hold the filled domains only (no stem prefix)
                 int last = stem;
-                if (b > a && !(b - a == 1 && m->seg_dom[a] == stem)) last = m->seg_dom[b - 1];
-                int nd = sys.step(last, m->scaf_dir[sg]);
+                if (b > a && !(b - a == 1 && C()->seg_dom[a] == stem)) last = C()->seg_dom[b - 1];
+                int nd = sys.step(last, M()->scaf_dir[sg]);
                 if (nd >= 0) cp_add_active_endpoint_seg(nd, rec_pos(s->dom[nd]), sg);
             }
         }
         // calculate_constraintpoints(segs, dirs, excluded) (top_constraint_points.cpp:223-248)
         for (int sg = 0; sg < n_segs; sg++) {
-            int a = m->seg_start[sg], b = m->seg_start[sg + 1];
-            if (b > a) cp_find_growthpoints_endpoints(m->seg_dom + a, b - a, sg);
+            int a = C()->seg_start[sg], b = C()->seg_start[sg + 1];
+            if (b > a) cp_find_growthpoints_endpoints(C()->seg_dom + a, b - a, sg);
         }
         cp_save_initial();
-        int first = m->seg_dom[0];
+        int first = C()->seg_dom[0];
         cp_remove_active_endpoint(first);
         for (int k = 0; k < n_stems; k++) {
-            int stem = m->stems[k];
+            int stem = C()->stems[k];
             int gp = s->bound[stem];
-            m->gp_stem[gp] = (short)stem;
-            m->stem_gp[stem] = (short)gp;
+            M()->gp_stem[gp] = (short)stem;
+            M()->stem_gp[stem] = (short)gp;
         }
         return rg_regrow_and_test(true, true, first);
     }
@@ -1909,16 +2112,16 @@ struct Engine {
     LDO_HD int select_movetype() {
         double prob = uniform_real();
         int i;
-        for (i = 0; i < ms->n; i++) {
-            if (prob < ms->mt[i].cum_prob) break;
+        for (i = 0; i < MS().n; i++) {
+            if (prob < MS().mt[i].cum_prob) break;
         }
-        if (i >= ms->n) i = ms->n - 1; // reference reads out of bounds here; freqs sum to 1
+        if (i >= MS().n) i = MS().n - 1; // reference reads out of bounds here; freqs sum to 1
         return i;
     }
     LDO_HD bool attempt(int i) {
-        const MoveDef& md = ms->mt[i];
+        const MoveDef& md = MS().mt[i];
         reset_internal();
-        stats->attempts[i]++;
+        STATS()->attempts[i]++;
         bool accepted = false;
         switch (md.type) {
         case MT_ORIENTATION_ROTATION: accepted = move_orientation_rotation(); break;
@@ -1929,14 +2132,14 @@ struct Engine {
         case MT_CTRG_JUMP_SCAFFOLD_REGROWTH: accepted = move_ctrg_jump_scaffold(md); break;
         default: sys.fail(LDO_ERR_INTERNAL, 100 + md.type); break;
         }
-        if (sys.s->status != LDO_OK) return false;
-        stats->accepts[i] += accepted ? 1 : 0;
+        if (sys.S()->status != LDO_OK) return false;
+        STATS()->accepts[i] += accepted ? 1 : 0;
         return accepted;
     }
     LDO_HD bool mc_step() {
         int i = select_movetype();
         bool accepted = attempt(i);
-        if (sys.s->status != LDO_OK) return false;
+        if (sys.S()->status != LDO_OK) return false;
         if (!accepted) {
             reset_origami();
             update_move_params();
