@@ -1884,6 +1884,15 @@ struct Engine {
                         rg_fill_feeler_memo(fd, fref);
                     }
                 }
+                // Production (Philox) mode with exhaustive trials: every remaining configuration is
+                // examined whatever the order, and its contribution is an independent Bernoulli variable,
+                // so the configurations are spread over the lanes, each with its own Philox block, and the
+                // count is reduced across the warp. Replay (tape) mode keeps the reference's serial order.
+                if (RNG()->tape == nullptr && max_c_attempts == 36 && max_recoils == 1 && catt != max_c_attempts &&
+                    (last_level || feeler_simple)) {
+                    avail_cs += rg_count_avail_parallel(last_level);
+                    catt = max_c_attempts;
+                }
                 while (catt != max_c_attempts) {
                     catt++;
                     V3 p;
@@ -1899,22 +1908,7 @@ struct Engine {
                             avail_cs += rg_feeler_from_slot(LDO_RG_OWN_SLOTS + last_pc) ? 1 : 0;
                             continue;
                         }
-                        sys.set_checked_domain_config(d, p, o);
-                        cp_update_endpoints(d);
-                        eq_push_erased();
-                        int dir_s = dir, ref_s = ref_d, stem_s = stemd, slot_s = cur_slot;
-                        unsigned long long avail_s = avail;
-                        memo_level = di + 1;
-                        memo_key = last_kind == 1 ? last_pc : -1;
-                        avail_cs += rg_test_config_avail() ? 1 : 0;
-                        memo_key = -1;
-                        avail = avail_s;
-                        stemd = stem_s;
-                        ref_d = ref_s;
-                        dir = dir_s;
-                        cur_slot = slot_s;
-                        sys.unassign_domain(d);
-                        rg_restore_endpoints();
+                        avail_cs += rg_feeler_general(p, o) ? 1 : 0;
                     }
                 }
             }
@@ -1925,6 +1919,102 @@ struct Engine {
             eq_push_erased();
         }
         weight /= M()->c_opens[di];
+    }
+    // One open trial configuration of calc_weights examined the reference's way: place the domain, grow
+    // feelers, take it back (rg:384-400)
+    LDO_HDN bool rg_feeler_general(V3 p, int o) {
+        sys.set_checked_domain_config(d, p, o);
+        cp_update_endpoints(d);
+        eq_push_erased();
+        int dir_s = dir, ref_s = ref_d, stem_s = stemd, slot_s = cur_slot;
+        unsigned long long avail_s = avail;
+        memo_level = di + 1;
+        memo_key = last_kind == 1 ? last_pc : -1;
+        bool c_avail = rg_test_config_avail();
+        memo_key = -1;
+        avail = avail_s;
+        stemd = stem_s;
+        ref_d = ref_s;
+        dir = dir_s;
+        cur_slot = slot_s;
+        sys.unassign_domain(d);
+        rg_restore_endpoints();
+        return c_avail;
+    }
+    // Lane-parallel count of the available configurations among the remaining ones (Philox mode,
+    // max_c_attempts == 36, one feeler level). A configuration is available when it is open
+    // (probability p) and, unless it is the last level, the next domain finds an open configuration
+    // among all 36 of its own: probability 1 - prod(1 - p') over the feeler slot, independent of the
+    // order in which the reference would have tried them.
+    LDO_HDN int rg_count_avail_parallel(bool last_level) {
+        const RgSlot& own = M()->slots[cur_slot];
+        // feeler availability probability per parent site (warp-uniform)
+        double pav[6];
+        for (int pc = 0; pc < 6; pc++) {
+            pav[pc] = -1; // not memoised: needs the general path
+            if (last_level || !((memo_mask >> pc) & 1)) continue;
+            const RgSlot& sl = M()->slots[LDO_RG_OWN_SLOTS + pc];
+            double none = 1.0;
+            for (int k = 0; k < 6; k++) {
+                if (sl.kind[k] != 0) none *= 1.0 - sl.p[k]; // kind 1: six orientations share p (0 or 1)
+            }
+            pav[pc] = 1.0 - none;
+        }
+        unsigned long long rem = avail;
+        unsigned long long ctr = RNG()->counter;
+        int count = 0;
+        unsigned lo_mask = 0, hi_mask = 0; // configurations left to the general path
+        for (int ci = LDO_LANE; ci < 36; ci += LDO_NLANES) {
+            if (!((rem >> ci) & 1ull)) continue;
+            int pc = ci / 6, o = ci - 6 * pc;
+            int kind = own.kind[pc];
+            double pv = 0;
+            if (kind == 1) pv = own.p[pc];
+            else if (kind == 2 && o == own.ore[pc]) pv = own.p[pc];
+            if (pv == 0) continue;
+            // private Philox block of this configuration: stream word tagged with the configuration index
+            Rng g = *RNG();
+            g.stream = 0x52470000u + (uint32_t)ci;
+            uint32_t w[4];
+            philox4x32_10(g, ctr, w);
+            double ua = (double)((((unsigned long long)w[0] << 32) | w[1]) >> 11) * (1.0 / 9007199254740992.0);
+            double ub = (double)((((unsigned long long)w[2] << 32) | w[3]) >> 11) * (1.0 / 9007199254740992.0);
+            if (!(pv == 1.0 || pv > ua)) continue;
+            if (last_level) {
+                count++;
+            }
+            else if (kind == 1 && pav[pc] >= 0) {
+                if (pav[pc] == 1.0 || pav[pc] > ub) count++;
+            }
+            else if (ci < 32) {
+                lo_mask |= 1u << ci;
+            }
+            else {
+                hi_mask |= 1u << (ci - 32);
+            }
+        }
+#if defined(__CUDA_ARCH__)
+        count = __reduce_add_sync(0xffffffffu, count);
+        lo_mask = __reduce_or_sync(0xffffffffu, lo_mask);
+        hi_mask = __reduce_or_sync(0xffffffffu, hi_mask);
+#endif
+        RNG()->counter = ctr + 1;
+        RNG()->buf_n = 0;
+        LDO_SYNCWARP();
+        // configurations that bind the parent (at most one orientation per site) go through the real
+        // place / feel / take-back path, serially
+        unsigned long long todo = ((unsigned long long)hi_mask << 32) | lo_mask;
+        while (todo) {
+            int ci = nth_set_bit36(todo, 0);
+            todo &= todo - 1;
+            int pc = ci / 6, o = ci - 6 * pc;
+            last_pc = pc;
+            last_kind = own.kind[pc];
+            V3 p = ore_vec(pc) + rec_pos(sys.S()->dom[ref_d]);
+            count += rg_feeler_general(p, o) ? 1 : 0;
+        }
+        avail = 0;
+        return count;
     }
     // test_config_avail (rg:422-480) for a single feeler level, replayed on an already computed slot:
     // same draws as the general path, no lattice updates
