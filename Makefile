@@ -5,7 +5,7 @@ HOSTCXX := /usr/bin/g++
 CSRC := latticednaorigami_b200/csrc
 OUT := latticednaorigami_b200
 NVFLAGS := -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -ccbin $(HOSTCXX) -Xcompiler -fPIC
-CXXFLAGS := -std=c++17 -O2 -fPIC -Wall -Wno-unused-function
+CXXFLAGS := -std=c++17 -O2 -fPIC -Wall -Wno-unused-function -Wno-unknown-pragmas
 HOST_SRCS := $(CSRC)/ldo_host.cpp $(CSRC)/ldo_sim.cpp
 HDRS := $(wildcard $(CSRC)/*.cuh $(CSRC)/*.hpp include/*.h)
 

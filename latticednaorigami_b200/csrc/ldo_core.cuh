@@ -349,10 +349,12 @@ struct System {
     }
     // Domain::operator+ (domain.cpp:9-31)
     LDO_HDN int step(int d, int incr) const {
+#pragma unroll 1
         while (incr > 0 && d >= 0) {
             d = fwd(d);
             incr--;
         }
+#pragma unroll 1
         while (incr < 0 && d >= 0) {
             d = bac(d);
             incr++;
@@ -375,6 +377,7 @@ struct System {
     LDO_HDN int occupant(V3 p) const {
         uint32_t key = pack_pos(p);
         uint32_t i = hash_slot<K>(key);
+#pragma unroll 1
         for (int n = 0; n < K::H; n++) {
             uint32_t k = S()->hkey[i];
             if (k == key) return S()->hval[i];
@@ -389,6 +392,7 @@ struct System {
         }
         uint32_t key = pack_pos(p);
         uint32_t i = hash_slot<K>(key);
+#pragma unroll 1
         for (int n = 0; n < K::H; n++) {
             uint32_t k = S()->hkey[i];
             if (k == key || k == LDO_HEMPTY) {
@@ -405,11 +409,13 @@ struct System {
         uint32_t key = pack_pos(p);
         uint32_t i = hash_slot<K>(key);
         int n = 0;
+#pragma unroll 1
         while (S()->hkey[i] != key) {
             if (S()->hkey[i] == LDO_HEMPTY || ++n == K::H) return;
             i = (i + 1) & (K::H - 1);
         }
         uint32_t j = i;
+#pragma unroll 1
         for (;;) {
             j = (j + 1) & (K::H - 1);
             uint32_t kj = S()->hkey[j];
@@ -426,16 +432,17 @@ struct System {
         S()->hkey[i] = LDO_HEMPTY;
     }
     LDO_HD void table_clear() {
+#pragma unroll 1
         for (int i = 0; i < K::H; i++) S()->hkey[i] = LDO_HEMPTY;
     }
 
     // ---- domain constraint checkers (domain.cpp:33-118) ----
-    LDO_HD bool check_twist(int d1, V3 ndr, int d2) const {
+    LDO_HDN bool check_twist(int d1, V3 ndr, int d2) const {
         V3 o1 = ore(d1);
         V3 rot = SC().domain_type == DOMAIN_HALFTURN ? rotate_half(o1, ndr) : rotate_turns(o1, ndr, -1);
         return rot == ore(d2);
     }
-    LDO_HD bool check_kink(int d1, V3 ndr, int d2) const {
+    LDO_HDN bool check_kink(int d1, V3 ndr, int d2) const {
         V3 o1 = ore(d1), o2 = ore(d2);
         if (ndr == -o1) return false;
         if (ndr == o1) {
@@ -450,7 +457,7 @@ struct System {
         if (ndr == o2 || ndr == -o2) return false;
         return true;
     }
-    LDO_HD bool check_junction_constraint(int j1, int j2, int k1, int k2) const {
+    LDO_HDN bool check_junction_constraint(int j1, int j2, int k1, int k2) const {
         if (SC().domain_type == DOMAIN_HALFTURN) return true;
         V3 ndr_k1 = pos(k2) - pos(k1);
         if (ndr_k1 == ore(k1)) {
@@ -463,7 +470,7 @@ struct System {
 
     // ---- free helpers (origami_potential.cpp:25-127) ----
     LDO_HD bool exists_bound(int d) const { return d >= 0 && state(d) == ST_BOUND; }
-    LDO_HD bool doubly_contiguous(int d1, int d2) const {
+    LDO_HDN bool doubly_contiguous(int d1, int d2) const {
         if (chain(d1) != chain(d2) || dindex(d2) != dindex(d1) + 1) return false;
         int b1 = bound(d1), b2 = bound(d2);
         if (chain(b1) != chain(b2)) return false;
@@ -480,7 +487,7 @@ struct System {
         if (ndr != o1 && ndr != -o1) return check_twist(d1, ndr, d2);
         return false;
     }
-    LDO_HD int junction_stacking_penalty(int j1, int j2, int j3, int j4, int k1, int k2) const {
+    LDO_HDN int junction_stacking_penalty(int j1, int j2, int j3, int j4, int k1, int k2) const {
         int penalty = 0;
         V3 ndr_k1 = pos(k2) - pos(k1);
         if (ndr_k1 == ore(k1)) {
@@ -496,7 +503,7 @@ struct System {
     }
 
     // ---- triplet terms (origami_potential.cpp:158-210) ----
-    LDO_HD void triplet_single_stacking(DeltaConfig& dc, int h1, int h2, int h3) const {
+    LDO_HDN void triplet_single_stacking(DeltaConfig& dc, int h1, int h2, int h3) const {
         V3 ndr_1 = pos(h2) - pos(h1);
         if (ndr_1 == ore(h1)) return;
         V3 ndr_2 = pos(h3) - pos(h2);
@@ -505,7 +512,7 @@ struct System {
             dc.stacked -= 1;
         }
     }
-    LDO_HD void triplet_double_stacking(DeltaConfig& dc, int h1, int h2, int h3) const {
+    LDO_HDN void triplet_double_stacking(DeltaConfig& dc, int h1, int h2, int h3) const {
         V3 ndr_1 = pos(h2) - pos(h1);
         V3 ndr_2 = pos(h3) - pos(h2);
         if (ndr_1 != ndr_2) {
@@ -514,7 +521,7 @@ struct System {
             dc.stacked -= 1;
         }
     }
-    LDO_HD void triply_contig_helix(DeltaConfig& dc, int h1, int h2, int h3) const {
+    LDO_HDN void triply_contig_helix(DeltaConfig& dc, int h1, int h2, int h3) const {
         V3 ndr_1 = pos(h2) - pos(h1);
         V3 ndr_2 = pos(h3) - pos(h2);
         if (ndr_1 != ndr_2) dc.violated = true;
@@ -591,6 +598,7 @@ struct System {
             sel_b[n] = ab_bac;
             n++;
         }
+#pragma unroll 1
         for (int q = 0; q < n; q++) {
             if (!exists_bound(sel_b[q])) continue;
             if (found_is_j34) check_junction(dc, fj1, fj2, sel_a[q], sel_b[q], k1, k2);
@@ -633,6 +641,7 @@ struct System {
             sel_k1[n] = j3b_bac;
             n++;
         }
+#pragma unroll 1
         for (int q = 0; q < n; q++) {
             int k2 = sel_k2[q], k1 = sel_k1[q];
             if (!exists_bound(k1)) continue;
@@ -678,6 +687,7 @@ struct System {
             sel_k2[n] = j2b_bac;
             n++;
         }
+#pragma unroll 1
         for (int q = 0; q < n; q++) {
             int k1 = sel_k1[q], k2 = sel_k2[q];
             if (!exists_bound(k2)) continue;
@@ -722,6 +732,7 @@ struct System {
             sel_j1[n] = k1b_bac;
             n++;
         }
+#pragma unroll 1
         for (int q = 0; q < n; q++) {
             int j2 = sel_j2[q], j1 = sel_j1[q];
             if (!exists_bound(j1)) continue;
@@ -903,6 +914,7 @@ struct System {
         sel_j2[0] = d1;
         sel_j1[1] = step(d1b, 1);
         sel_j2[1] = d1b;
+#pragma unroll 1
         for (int q = 0; q < 2; q++) {
             int j1 = sel_j1[q], j2 = sel_j2[q];
             int j3 = k2;
@@ -920,6 +932,7 @@ struct System {
 
     // origami_potential.cpp:231-286
     LDO_HDN void check_constraints(DeltaConfig& dc, int cd, int j) const {
+#pragma unroll 1
         for (int i = -1; i <= 0; i++) {
             int d1 = step(cd, i);
             int d2 = step(cd, i + 1);
@@ -963,7 +976,7 @@ struct System {
     }
 
     // BindingPotential::check_stacking (origami_potential.cpp:149-156)
-    LDO_HD DeltaConfig check_stacking(int di, int dj) const {
+    LDO_HDN DeltaConfig check_stacking(int di, int dj) const {
         DeltaConfig dc;
         dc.e = 0;
         dc.stacked = 0;
@@ -973,7 +986,7 @@ struct System {
     }
 
     // OrigamiPotential::bind_domain (origami_potential.cpp:1282-1293) on the (possibly overlaid) pair
-    LDO_HD DeltaConfig bind_domain(int di) const {
+    LDO_HDN DeltaConfig bind_domain(int di) const {
         int dj = bound(di);
         DeltaConfig dc;
         dc.e = 0;
@@ -1208,6 +1221,7 @@ struct System {
     // add_chain(c_i_ident, c_i) (origami_system.cpp:402-443). Returns the chain slot.
     LDO_HDN int add_chain_with_uid(int type, int uid) {
         int c = -1;
+#pragma unroll 1
         for (int k = 1; k < K::C; k++) {
             if (!S()->chain_used[k]) {
                 c = k;
@@ -1228,6 +1242,7 @@ struct System {
         S()->type_count[type]++;
         S()->num_staples++;
         int base = chain_base(c);
+#pragma unroll 1
         for (int i = 0; i < len; i++) {
             int d = base + i;
             S()->dom[d].x = 0;
@@ -1254,6 +1269,7 @@ struct System {
     // delete_chain (origami_system.cpp:445-472); the chain's domains must be unassigned
     LDO_HDN void delete_chain(int c) {
         int w = -1;
+#pragma unroll 1
         for (int k = 0; k < S()->n_chains; k++) {
             if (S()->order[k] == c) {
                 w = k;
@@ -1264,6 +1280,7 @@ struct System {
             fail(LDO_ERR_INTERNAL, c);
             return;
         }
+#pragma unroll 1
         for (int k = w; k + 1 < S()->n_chains; k++) S()->order[k] = S()->order[k + 1];
         S()->n_chains--;
         int len = S()->chain_len[c];
@@ -1278,6 +1295,7 @@ struct System {
 
     // k-th staple of a given identity in insertion order (m_identity_to_index[type][k]; App. B)
     LDO_HD int staple_of_type(int type, int k) const {
+#pragma unroll 1
         for (int w = 1; w < S()->n_chains; w++) {
             int c = S()->order[w];
             if (S()->chain_type[c] == type) {
@@ -1290,6 +1308,7 @@ struct System {
 
     // Domain at position `index` of the concatenation of chains in working order (movetypes.cpp:98-113)
     LDO_HD int domain_by_flat_index(int index) const {
+#pragma unroll 1
         for (int w = 0; w < S()->n_chains; w++) {
             int c = S()->order[w];
             int len = S()->chain_len[c];
@@ -1305,9 +1324,11 @@ struct System {
         const DomRec& c0 = S()->dom[chain_base(0) + centering_domain];
         V3 ref = v3(c0.x, c0.y, c0.z);
         table_clear();
+#pragma unroll 1
         for (int w = 0; w < S()->n_chains; w++) {
             int c = S()->order[w];
             int base = chain_base(c);
+#pragma unroll 1
             for (int i = 0; i < S()->chain_len[c]; i++) {
                 DomRec& r = S()->dom[base + i];
                 r.x = (short)(r.x - ref.x);
@@ -1321,9 +1342,11 @@ struct System {
 
     // set_all_domains() + check_distance_constraints (origami_system.cpp:357-373, 573-586)
     LDO_HDN bool set_all_domains() {
+#pragma unroll 1
         for (int w = 0; w < S()->n_chains; w++) {
             int c = S()->order[w];
             int base = chain_base(c);
+#pragma unroll 1
             for (int i = 0; i < S()->chain_len[c]; i++) {
                 int d = base + i;
                 const DomRec r = S()->dom[d];
@@ -1334,9 +1357,11 @@ struct System {
                 }
             }
         }
+#pragma unroll 1
         for (int w = 0; w < S()->n_chains; w++) {
             int c = S()->order[w];
             int base = chain_base(c);
+#pragma unroll 1
             for (int i = 0; i < S()->chain_len[c]; i++) {
                 int d = base + i;
                 int n = step(d, 1);
@@ -1353,9 +1378,11 @@ struct System {
     }
 
     LDO_HD void unassign_all() {
+#pragma unroll 1
         for (int w = 0; w < S()->n_chains; w++) {
             int c = S()->order[w];
             int base = chain_base(c);
+#pragma unroll 1
             for (int i = 0; i < S()->chain_len[c]; i++) unassign_domain(base + i);
         }
     }
@@ -1366,9 +1393,11 @@ struct System {
             fail(LDO_ERR_UNASSIGNED_AT_CHECK);
             return false;
         }
+#pragma unroll 1
         for (int w = 0; w < S()->n_chains; w++) {
             int c = S()->order[w];
             int base = chain_base(c);
+#pragma unroll 1
             for (int i = 0; i < S()->chain_len[c]; i++) {
                 if (S()->dom[base + i].state == ST_UNASSIGNED) {
                     fail(LDO_ERR_UNASSIGNED_AT_CHECK, base + i);
@@ -1412,9 +1441,11 @@ struct System {
     // OrigamiSystem::update_enthalpy_and_entropy (origami_system.cpp:204-246)
     LDO_HDN void enthalpy_and_entropy(double* enthalpy, double* entropy, double* stacking) const {
         double H = 0, Sent = 0;
+#pragma unroll 1
         for (int w = 0; w < S()->n_chains; w++) {
             int c = S()->order[w];
             int base = chain_base(c);
+#pragma unroll 1
             for (int i = 0; i < S()->chain_len[c]; i++) {
                 int d = base + i;
                 int st = S()->dom[d].state;
@@ -1427,6 +1458,7 @@ struct System {
                         j_first = S()->dindex[j] < i;
                     }
                     else {
+#pragma unroll 1
                         for (int w2 = 0; w2 < w; w2++) {
                             if (S()->order[w2] == cj) {
                                 j_first = true;

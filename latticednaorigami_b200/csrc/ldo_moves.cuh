@@ -167,6 +167,7 @@ LDO_HD inline int popc36(unsigned long long m) {
     return __popcll(m);
 #else
     int n = 0;
+#pragma unroll 1
     for (; m; m &= m - 1) n++;
     return n;
 #endif
@@ -197,8 +198,10 @@ LDO_HD inline int nth_set_bit36(unsigned long long m, int n) {
     }
     return pos;
 #else
+#pragma unroll 1
     for (int k = 0; k < n; k++) m &= m - 1;
     int i = 0;
+#pragma unroll 1
     while (i < 36 && !((m >> i) & 1ull)) i++;
     return i;
 #endif
@@ -444,6 +447,7 @@ struct Engine {
     // Lemire's nearly-divisionless unbiased bounded integer: rejection part
     LDO_HDN unsigned long long uniform_int_reject(unsigned long long mm, uint32_t n) {
         uint32_t t = (0u - n) % n;
+#pragma unroll 1
         while ((uint32_t)mm < t) mm = (unsigned long long)next_word() * n;
         return mm;
     }
@@ -464,11 +468,13 @@ struct Engine {
         case OP_NUM_STAPLES_TYPE: return s->type_count[o.arg];
         case OP_STAPLE_TYPE_FULLY_BOUND: {
             // order_params.cpp:250-266
+#pragma unroll 1
             for (int w = 1; w < s->n_chains; w++) {
                 int c = s->order[w];
                 if (s->chain_type[c] != o.arg) continue;
                 bool full = true;
                 int base = sys.chain_base(c);
+#pragma unroll 1
                 for (int k = 0; k < s->chain_len[c]; k++) {
                     if (s->dom[base + k].state != ST_BOUND) {
                         full = false;
@@ -486,6 +492,7 @@ struct Engine {
         case OP_NUM_STACKED_JUNCTS: return 0;
         case OP_SUM: {
             int sum = 0;
+#pragma unroll 1
             for (int k = 0; k < o.n_sum; k++) sum += BS()->op_val[o.sum_idx[k]];
             return sum;
         }
@@ -494,6 +501,7 @@ struct Engine {
     }
     // SystemOrderParams::update_move_params (order_params.cpp:595-601)
     LDO_HD void update_move_params() {
+#pragma unroll 1
         for (int i = 0; i < OB().n_ops; i++) BS()->op_val[i] = calc_op(i);
     }
     LDO_HD double grid_lookup(int b) const {
@@ -501,6 +509,7 @@ struct Engine {
         if (off < 0) return 0;
         const BiasDef& bd = OB().biases[b];
         int idx = 0;
+#pragma unroll 1
         for (int k = 0; k < bd.n_ops; k++) {
             int v = BS()->op_val[bd.op_idx[k]] - BS()->grid_lo[b][k];
             if (v < 0 || v >= BS()->grid_n[b][k]) return 0;
@@ -527,6 +536,7 @@ struct Engine {
     // SystemBiases::calc_move (bias_functions.cpp:475-487)
     LDO_HDN double calc_move_bias() {
         double diff = 0;
+#pragma unroll 1
         for (int b = 0; b < OB().n_biases; b++) {
             double prev = BS()->bias_val[b];
             double nb = calc_bias_fn(b);
@@ -573,11 +583,13 @@ struct Engine {
 
     // MCMovetype::reset_origami (movetypes.cpp:53-85)
     LDO_HDN void reset_origami() {
+#pragma unroll 1
         for (int k = 0; k < M()->n_assigned; k++) sys.unassign_domain(M()->assigned[k]);
         if (M()->added_chain >= 0) {
             sys.delete_chain(M()->added_chain);
             sys.S()->current_c_i -= 1;
         }
+#pragma unroll 1
         for (int k = 0; k < M()->n_modified; k++) {
             int dd = M()->modified[k];
             const DomRec& r = M()->prev[dd];
@@ -594,12 +606,14 @@ struct Engine {
         st[0][0] = (short)start;
         st[0][1] = 0;
         participating[sys.chain(start)] = 1;
+#pragma unroll 1
         while (sp >= 0) {
             int dom = st[sp][0];
             int c = sys.chain(dom);
             int base = sys.chain_base(c);
             int len = sys.S()->chain_len[c];
             bool descended = false;
+#pragma unroll 1
             while (st[sp][1] < len) {
                 int cur = base + st[sp][1];
                 st[sp][1]++;
@@ -626,11 +640,13 @@ struct Engine {
     }
     LDO_HDN bool staple_is_connector(int c) {
         int base = sys.chain_base(c);
+#pragma unroll 1
         for (int k = 0; k < sys.S()->chain_len[c]; k++) {
             int dd = base + k;
             if (sys.S()->dom[dd].state != ST_UNBOUND) {
                 int b = sys.S()->bound[dd];
                 if (sys.chain(b) == 0) continue;
+#pragma unroll 1
                 for (int q = 0; q < K::C; q++) C()->net_chain[q] = 0;
                 C()->net_chain[c] = 1;
                 if (!scan_for_scaffold_domain(b, C()->net_chain)) return true;
@@ -641,6 +657,7 @@ struct Engine {
     LDO_HD int num_bound_staple_domains(int c) const {
         int n = 0;
         int base = sys.chain_base(c);
+#pragma unroll 1
         for (int k = 0; k < sys.S()->chain_len[c]; k++) {
             int st = sys.S()->dom[base + k].state;
             if (st == ST_BOUND || st == ST_MISBOUND) n++;
@@ -649,6 +666,7 @@ struct Engine {
     }
     LDO_HD bool staple_has_bound_domain(int c) const {
         int base = sys.chain_base(c);
+#pragma unroll 1
         for (int k = 0; k < sys.S()->chain_len[c]; k++) {
             if (sys.S()->dom[base + k].state == ST_BOUND) return true;
         }
@@ -658,6 +676,7 @@ struct Engine {
     LDO_HD int count_bound_to_other_chains(int c) const {
         int n = 0;
         int base = sys.chain_base(c);
+#pragma unroll 1
         for (int k = 0; k < sys.S()->chain_len[c]; k++) {
             int b = sys.S()->bound[base + k];
             if (b >= 0 && sys.chain(b) != c) n++;
@@ -666,6 +685,7 @@ struct Engine {
     }
     LDO_HD int kth_bound_to_other_chains(int c, int kth) const {
         int base = sys.chain_base(c);
+#pragma unroll 1
         for (int k = 0; k < sys.S()->chain_len[c]; k++) {
             int b = sys.S()->bound[base + k];
             if (b >= 0 && sys.chain(b) != c) {
@@ -716,6 +736,7 @@ struct Engine {
     }
     // MetMCMovetype::grow_chain over domains base+from, base+from+step, ... (count domains incl. the first)
     LDO_HDN void met_grow_chain(int first, int stepdir, int count) {
+#pragma unroll 1
         for (int i = 1; i < count; i++) {
             int dd = first + stepdir * i;
             int prev = first + stepdir * (i - 1);
@@ -739,6 +760,7 @@ struct Engine {
     }
     LDO_HD void met_unassign_domains(int c) {
         int base = sys.chain_base(c);
+#pragma unroll 1
         for (int k = 0; k < sys.S()->chain_len[c]; k++) {
             int dd = base + k;
             M()->prev[dd] = sys.S()->dom[dd];
@@ -782,6 +804,7 @@ struct Engine {
             int len = s->chain_len[c];
             int g_new = sys.chain_base(c) + uniform_int(0, len - 1);
             int g_old = select_random_domain();
+#pragma unroll 1
             while (sys.chain(g_old) == c && s->status == LDO_OK) g_old = select_random_domain();
             delta_e += set_growth_point(g_new, g_old);
             if (M()->rejected) return false;
@@ -857,6 +880,7 @@ struct Engine {
     // (CBMCMovetype::calc_biases, cb_movetypes.cpp:58-102). Results: site_kind 0 = skipped,
     // 1 = empty site (orientation drawn later), 2 = binds the unbound occupant with orientation site_o.
     LDO_HDN void cb_site_weights(V3 p_prev, int dom) {
+#pragma unroll 1
         for (int k = LDO_LANE; k < 6; k += LDO_NLANES) {
             V3 p = p_prev + ore_vec(k);
             int j = sys.occupant(p);
@@ -889,6 +913,7 @@ struct Engine {
         cb_site_weights(p_prev, dom);
         sys.S()->constraints_violated = 0;
         double ros = 0;
+#pragma unroll 1
         for (int k = 0; k < 6; k++) {
             if (M()->site_kind[k] != 0) ros += M()->site_w[k];
         }
@@ -902,6 +927,7 @@ struct Engine {
             double r = uniform_real();
             V3 p_new = v3(0, 0, 0);
             int o_new = ORE_ZERO;
+#pragma unroll 1
             for (int k = 0; k < 6; k++) {
                 if (M()->site_kind[k] == 0) continue;
                 cum += M()->site_w[k] / ros;
@@ -921,6 +947,7 @@ struct Engine {
         push_assigned(dom);
     }
     LDO_HD void cb_grow_chain(int first, int stepdir, int count, bool regrow_old, double& bias) {
+#pragma unroll 1
         for (int i = 1; i < count; i++) {
             cb_select_and_set_config(first + stepdir * i, first + stepdir * (i - 1), regrow_old, bias);
             if (M()->rejected) break;
@@ -948,6 +975,7 @@ struct Engine {
     }
     LDO_HD void cb_unassign_domains(int c) {
         int base = sys.chain_base(c);
+#pragma unroll 1
         for (int k = 0; k < sys.S()->chain_len[c]; k++) {
             int dd = base + k;
             M()->prev[dd] = sys.S()->dom[dd];
@@ -970,6 +998,7 @@ struct Engine {
         short bd_new[8], bd_old[8];
         bool small = n_bd <= 8;
         if (small) {
+#pragma unroll 1
             for (int k = 0; k < n_bd; k++) {
                 bd_new[k] = (short)kth_bound_to_other_chains(c, k);
                 bd_old[k] = s->bound[bd_new[k]];
@@ -996,6 +1025,7 @@ struct Engine {
         M()->n_assigned = 0;
         {
             int base = sys.chain_base(c);
+#pragma unroll 1
             for (int k = 0; k < s->chain_len[c]; k++) C()->oldc[base + k] = M()->prev[base + k];
         }
         gi = uniform_int(0, n_bd - 1);
@@ -1017,6 +1047,7 @@ struct Engine {
 
     // ---- Constraintpoints (top_constraint_points.cpp:163-601) ----
     LDO_HDN void cp_reset() {
+#pragma unroll 1
         for (int k = 0; k < K::D; k++) {
             M()->seg_of[k] = -1;
             M()->stem_gp[k] = -1;
@@ -1025,7 +1056,9 @@ struct Engine {
             M()->stem_seg0[k] = -1;
             C()->in_sel[k] = 0;
         }
+#pragma unroll 1
         for (int k = 0; k < K::C; k++) C()->checked_chain[k] = 0;
+#pragma unroll 1
         for (int k = 0; k < MoveScratch<K>::S; k++) M()->scaf_dir[k] = 0;
         M()->n_ep = 0;
         C()->n_ep0 = 0;
@@ -1056,6 +1089,7 @@ struct Engine {
     }
     LDO_HD void cp_add_active_endpoint(int dd, V3 p) { cp_add_active_endpoint_seg(dd, p, M()->seg_of[dd]); }
     LDO_HD void cp_erase_ep(int e) {
+#pragma unroll 1
         for (int k = e; k + 1 < M()->n_ep; k++) {
             M()->ep_chain[k] = M()->ep_chain[k + 1];
             M()->ep_seg[k] = M()->ep_seg[k + 1];
@@ -1068,6 +1102,7 @@ struct Engine {
     }
     LDO_HDN void cp_save_initial() {
         C()->n_ep0 = M()->n_ep;
+#pragma unroll 1
         for (int k = 0; k < M()->n_ep; k++) {
             C()->ep0_chain[k] = M()->ep_chain[k];
             C()->ep0_seg[k] = M()->ep_seg[k];
@@ -1079,6 +1114,7 @@ struct Engine {
     }
     LDO_HDN void cp_reset_active_endpoints() {
         M()->n_ep = C()->n_ep0;
+#pragma unroll 1
         for (int k = 0; k < C()->n_ep0; k++) {
             M()->ep_chain[k] = C()->ep0_chain[k];
             M()->ep_seg[k] = C()->ep0_seg[k];
@@ -1093,6 +1129,7 @@ struct Engine {
         M()->n_erased = 0;
         int c = sys.chain(dd), seg = M()->seg_of[dd], di_ = sys.dindex(dd);
         int k = 0;
+#pragma unroll 1
         while (k < M()->n_ep) {
             if (M()->ep_chain[k] == c && M()->ep_seg[k] == seg && M()->ep_d[k] == di_) {
                 if (M()->n_erased < 8) {
@@ -1116,6 +1153,7 @@ struct Engine {
         int ed = M()->inactive[dd];
         if (ed < 0) return;
         int c = sys.chain(ed), seg = M()->seg_of[ed], di_ = sys.dindex(ed);
+#pragma unroll 1
         for (int k = 0; k < M()->n_ep; k++) {
             if (M()->ep_chain[k] == c && M()->ep_seg[k] == seg && M()->ep_d[k] == di_) {
                 cp_erase_ep(k);
@@ -1193,6 +1231,7 @@ struct Engine {
     // Returns whether the network is externally bound.
     LDO_HDN bool net_scan(int start) {
         SysState<K>* s = sys.S();
+#pragma unroll 1
         for (int k = 0; k < K::C; k++) C()->net_chain[k] = 0;
         C()->net_chain[0] = 1;
         C()->n_pot_gps = 0;
@@ -1207,6 +1246,7 @@ struct Engine {
         C()->net_chain[sys.chain(start)] = 1;
         C()->net_growth_idx[sys.chain(start)] = (short)sys.dindex(start);
         C()->pot_ds[C()->n_pot_ds++] = (short)start;
+#pragma unroll 1
         while (sp >= 0) {
             int g = st[sp][0];
             int ci = sys.chain(g);
@@ -1214,6 +1254,7 @@ struct Engine {
             int len = s->chain_len[ci];
             int gi = sys.dindex(g);
             bool descended = false;
+#pragma unroll 1
             while (st[sp][1] < len - 1) {
                 int k = st[sp][1]++;
                 // make_staple_stack order: 3' of the growth domain, then 5' (:135-161)
@@ -1229,6 +1270,7 @@ struct Engine {
                     if (!ext) {
                         // add_potential_inactive_endpoint (:155-161)
                         bool bd_in_ds = false;
+#pragma unroll 1
                         for (int q = 0; q < C()->n_pot_ds; q++) {
                             if (C()->pot_ds[q] == bd) {
                                 bd_in_ds = true;
@@ -1273,6 +1315,7 @@ struct Engine {
     // find_growthpoints_endpoints (:454-494)
     LDO_HDN void cp_find_growthpoints_endpoints(const short* doms, int n, int seg) {
         SysState<K>* s = sys.S();
+#pragma unroll 1
         for (int q = 0; q < n; q++) {
             int dd = doms[q];
             if (M()->n_regrow >= K::LV) {
@@ -1289,10 +1332,12 @@ struct Engine {
             C()->pot_gps[e][1] = (short)bd;
             if (external) {
                 // add_active_endpoints_on_scaffold (:540-559)
+#pragma unroll 1
                 for (int k = 0; k < C()->n_pot_gps; k++) {
                     int gd = C()->pot_gps[k][0];
                     if (sys.chain(gd) == 0) cp_add_active_endpoint_seg(gd, rec_pos(s->dom[gd]), seg);
                 }
+#pragma unroll 1
                 for (int k = 0; k < C()->n_pot_iaes; k++) {
                     int second = C()->pot_iaes[k][1];
                     if (sys.chain(second) == 0) {
@@ -1301,11 +1346,14 @@ struct Engine {
                 }
             }
             else {
+#pragma unroll 1
                 for (int k = 0; k < C()->n_pot_gps; k++) {
                     M()->gp_stem[C()->pot_gps[k][0]] = C()->pot_gps[k][1];
                     M()->stem_gp[C()->pot_gps[k][1]] = C()->pot_gps[k][0];
                 }
+#pragma unroll 1
                 for (int k = 0; k < C()->n_pot_iaes; k++) M()->inactive[C()->pot_iaes[k][0]] = C()->pot_iaes[k][1];
+#pragma unroll 1
                 for (int k = 0; k < C()->n_pot_ds; k++) {
                     int pd = C()->pot_ds[k];
                     if (M()->n_regrow >= K::LV) {
@@ -1319,6 +1367,7 @@ struct Engine {
                     }
                 }
             }
+#pragma unroll 1
             for (int k = 0; k < K::C; k++) {
                 if (C()->net_chain[k]) C()->checked_chain[k] = 1;
             }
@@ -1330,6 +1379,7 @@ struct Engine {
     LDO_HDN void ct_select_indices(const MoveDef& md) {
         SysState<K>* s = sys.S();
         int n = s->chain_len[0];
+#pragma unroll 1
         for (;;) {
             if (s->status != LDO_OK) return;
             int max_length = n < md.max_regrowth ? n : md.max_regrowth;
@@ -1341,11 +1391,13 @@ struct Engine {
             short* buf = C()->seg_dom; // scratch: forward list then backward list
             int nf = 0, nb = 0;
             int cur = sys.chain_base(0) + start_i;
+#pragma unroll 1
             while (cur >= 0 && nf != sel_length) {
                 buf[nf++] = (short)cur;
                 cur = sys.step(cur, dir);
             }
             int back = sys.step(sys.chain_base(0) + start_i, -dir);
+#pragma unroll 1
             while (back >= 0 && nf + nb != sel_length) {
                 buf[K::D + 1 + nb] = (short)back;
                 nb++;
@@ -1353,7 +1405,9 @@ struct Engine {
             }
             if (nf + nb < 2) continue;
             C()->n_sel = 0;
+#pragma unroll 1
             for (int k = nb - 1; k >= 0; k--) C()->sel_scaf[C()->n_sel++] = buf[K::D + 1 + k];
+#pragma unroll 1
             for (int k = 0; k < nf; k++) C()->sel_scaf[C()->n_sel++] = buf[k];
             if (cur >= 0) cp_add_active_endpoint_seg(cur, rec_pos(s->dom[cur]), 0);
             return;
@@ -1365,6 +1419,7 @@ struct Engine {
         SysState<K>* s = sys.S();
         if (s->dom[cur].state != ST_BOUND) return;
         int bd = s->bound[cur];
+#pragma unroll 1
         for (int sd = -1; sd <= 1; sd += 2) {
             int nd = sys.step(bd, sd);
             if (nd >= 0 && s->dom[nd].state == ST_BOUND) {
@@ -1385,6 +1440,7 @@ struct Engine {
         int cur = start_d;
         ct_check_for_stemds(cur, qt);
         int next = start_d;
+#pragma unroll 1
         while (seg_size != seg_max && next >= 0) {
             next = sys.step(cur, dir_);
             if (next < 0) break;
@@ -1427,11 +1483,13 @@ struct Engine {
         C()->seg_start[1] = (short)seg_n;
         // paired segment bookkeeping: for stem k, its two segments are 1+2k and 2+2k; pair_first[k]
         // records where the *paired_segs* (without the stem prefix) begin/end for endpoint search.
+#pragma unroll 1
         while (!max_reached && qh != qt) {
             if (s->status != LDO_OK) return n_segs;
             int stemd_ = C()->stem_queue[qh++];
             if (C()->in_sel[stemd_]) continue;
             bool adjacent = false;
+#pragma unroll 1
             for (int td = -1; td <= 1; td += 2) {
                 int nd = sys.step(stemd_, td);
                 if (nd >= 0 && C()->in_sel[nd]) {
@@ -1463,6 +1521,7 @@ struct Engine {
             M()->scaf_dir[n_segs] = (int8_t)dir1;
             M()->scaf_dir[n_segs + 1] = (int8_t)(-dir1);
             bool cur_seg_nonempty = true; // cur_seg = [stem]
+#pragma unroll 1
             for (int i = 0; i < 2; i++) {
                 int dsel = i == 0 ? dir1 : -dir1;
                 int smax = uniform_int(0, md.max_seg_regrowth);
@@ -1490,6 +1549,7 @@ struct Engine {
             return;
         }
         M()->eq_start[M()->eq_depth++] = (short)M()->eq_npos;
+#pragma unroll 1
         for (int k = 0; k < M()->n_erased; k++) {
             M()->eq_pos[M()->eq_npos][0] = M()->erased_pos[k][0];
             M()->eq_pos[M()->eq_npos][1] = M()->erased_pos[k][1];
@@ -1505,6 +1565,7 @@ struct Engine {
             return;
         }
         int start = M()->eq_start[--M()->eq_depth];
+#pragma unroll 1
         for (int k = start; k < M()->eq_npos; k++) {
             cp_add_active_endpoint(d, v3(M()->eq_pos[k][0], M()->eq_pos[k][1], M()->eq_pos[k][2]));
         }
@@ -1514,6 +1575,7 @@ struct Engine {
     LDO_HDN double rg_unassign_and_save_domains() {
         double de = 0;
         M()->prev[M()->regrow[0]] = sys.S()->dom[M()->regrow[0]];
+#pragma unroll 1
         for (int k = 1; k < M()->n_regrow; k++) {
             int dd = M()->regrow[k];
             M()->prev[dd] = sys.S()->dom[dd];
@@ -1525,6 +1587,7 @@ struct Engine {
         return de;
     }
     LDO_HD void rg_unassign_domains() {
+#pragma unroll 1
         for (int k = 1; k < M()->n_regrow; k++) sys.unassign_domain(M()->regrow[k]);
         M()->eq_depth = 0;
         M()->eq_npos = 0;
@@ -1610,6 +1673,7 @@ struct Engine {
     LDO_HDN void rg_compute_slot(int slot) {
         RgSlot& sl = M()->slots[slot];
         V3 refp = rec_pos(sys.S()->dom[ref_d]);
+#pragma unroll 1
         for (int k = LDO_LANE; k < 6; k += LDO_NLANES) {
             int kind, o;
             double pv;
@@ -1631,6 +1695,7 @@ struct Engine {
         bool fref_is_parent = fref == d;
         V3 frefp = fref_is_parent ? v3(0, 0, 0) : rec_pos(sys.S()->dom[fref]);
         int mask = 0;
+#pragma unroll 1
         for (int pc = 0; pc < 6; pc++) {
             if (own.kind[pc] != 1) continue;
             // a feeler that can reach the parent's own site would bind to the parent: orientation dependent
@@ -1650,6 +1715,7 @@ struct Engine {
             ov.add_seg = M()->seg_of[ie];
             ov.add_d = sys.dindex(ie);
         }
+#pragma unroll 1
         for (int t = LDO_LANE; t < 36; t += LDO_NLANES) {
             int pc = t / 6, k = t - 6 * pc;
             if (!((mask >> pc) & 1)) continue;
@@ -1724,6 +1790,7 @@ struct Engine {
             double pref = rg_calc_p_config_open(p, o);
             sys.S()->dom[d] = saved;
             if (pref != pv) {
+#pragma unroll 1
                 for (int q = 0; q < M()->n_ep; q++) printf("   ep chain=%d seg=%d d=%d pos=(%d %d %d)\n", M()->ep_chain[q], M()->ep_seg[q], M()->ep_d[q], M()->ep_pos[q][0], M()->ep_pos[q][1], M()->ep_pos[q][2]);
                 printf("SLOT MISMATCH p=(%d %d %d) di=%d d=%d ci=%d pc=%d o=%d kind=%d slot=%d pv=%g ref=%g stemd=%d memo_level=%d memo_key=%d\n", p.x, p.y, p.z, di, d, i, pc, o, kind, cur_slot, pv, pref, stemd, memo_level, memo_key);
             }
@@ -1762,6 +1829,7 @@ struct Engine {
         M()->c_opens[0] = 1;
         rg_prepare_for_growth();
         int recoils = 0;
+#pragma unroll 1
         for (;;) {
             if (sys.S()->status != LDO_OK) {
                 M()->rejected = 1;
@@ -1771,6 +1839,7 @@ struct Engine {
             int o = 0;
             double p_c_open = 0;
             bool c_open = false;
+#pragma unroll 1
             while (!c_open && c_attempts != d_max_c_attempts) {
                 c_attempts++;
                 p_c_open = rg_trial(p, o);
@@ -1802,12 +1871,28 @@ struct Engine {
         if (feels == max_recoils || di == M()->n_regrow - 1) return true;
         rg_prepare_for_growth();
         bool c_avail = false;
+        if (RNG()->tape == nullptr && max_recoils == 1 && !stemd && d_max_c_attempts == 36) {
+            // Philox mode, one exhaustive feeler level: "some configuration opens" has probability
+            // 1 - prod(1 - p) whatever the trial order, so one draw replaces up to 36 trials
+            const RgSlot& sl = M()->slots[cur_slot];
+            double none = 1.0;
+#pragma unroll 1
+            for (int k = 0; k < 6; k++) {
+                if (sl.kind[k] != 0) none *= 1.0 - sl.p[k];
+            }
+            c_avail = rg_test_config_open(1.0 - none);
+            di--;
+            d = M()->regrow[di];
+            return c_avail;
+        }
+#pragma unroll 1
         for (;;) {
             if (sys.S()->status != LDO_OK) break;
             V3 p = v3(0, 0, 0);
             int o = 0;
             bool c_open = false;
             double p_c_open;
+#pragma unroll 1
             while (!c_open && c_attempts != d_max_c_attempts) {
                 c_attempts++;
                 p_c_open = rg_trial(p, o);
@@ -1834,6 +1919,7 @@ struct Engine {
                 rg_prepare_for_regrowth();
             }
         }
+#pragma unroll 1
         while (feels != 0) {
             di--;
             feels--;
@@ -1849,6 +1935,7 @@ struct Engine {
     LDO_HDN void rg_calc_weights() {
         di = 0;
         d = M()->regrow[0];
+#pragma unroll 1
         while (di != M()->n_regrow - 1) {
             if (sys.S()->status != LDO_OK) return;
             di++;
@@ -1893,6 +1980,7 @@ struct Engine {
                     avail_cs += rg_count_avail_parallel(last_level);
                     catt = max_c_attempts;
                 }
+#pragma unroll 1
                 while (catt != max_c_attempts) {
                     catt++;
                     V3 p;
@@ -1950,11 +2038,13 @@ struct Engine {
         const RgSlot& own = M()->slots[cur_slot];
         // feeler availability probability per parent site (warp-uniform)
         double pav[6];
+#pragma unroll 1
         for (int pc = 0; pc < 6; pc++) {
             pav[pc] = -1; // not memoised: needs the general path
             if (last_level || !((memo_mask >> pc) & 1)) continue;
             const RgSlot& sl = M()->slots[LDO_RG_OWN_SLOTS + pc];
             double none = 1.0;
+#pragma unroll 1
             for (int k = 0; k < 6; k++) {
                 if (sl.kind[k] != 0) none *= 1.0 - sl.p[k]; // kind 1: six orientations share p (0 or 1)
             }
@@ -1964,6 +2054,7 @@ struct Engine {
         unsigned long long ctr = RNG()->counter;
         int count = 0;
         unsigned lo_mask = 0, hi_mask = 0; // configurations left to the general path
+#pragma unroll 1
         for (int ci = LDO_LANE; ci < 36; ci += LDO_NLANES) {
             if (!((rem >> ci) & 1ull)) continue;
             int pc = ci / 6, o = ci - 6 * pc;
@@ -2004,6 +2095,7 @@ struct Engine {
         // configurations that bind the parent (at most one orientation per site) go through the real
         // place / feel / take-back path, serially
         unsigned long long todo = ((unsigned long long)hi_mask << 32) | lo_mask;
+#pragma unroll 1
         while (todo) {
             int ci = nth_set_bit36(todo, 0);
             todo &= todo - 1;
@@ -2021,6 +2113,7 @@ struct Engine {
     LDO_HDN bool rg_feeler_from_slot(int slot) {
         const RgSlot& sl = M()->slots[slot];
         unsigned long long av = all_cis();
+#pragma unroll 1
         for (int catt = 0; catt != max_c_attempts; catt++) {
             int ci = uniform_int(0, popc36(av) - 1);
             int i = nth_set_bit36(av, ci);
@@ -2039,6 +2132,7 @@ struct Engine {
     LDO_HDN void rg_calc_old_c_opens() {
         di = 0;
         M()->c_opens[0] = 1;
+#pragma unroll 1
         while (di != M()->n_regrow - 1) {
             di++;
             d = M()->regrow[di];
@@ -2065,6 +2159,7 @@ struct Engine {
         }
     }
     LDO_HD void rg_copy_queues_to_wq() {
+#pragma unroll 1
         for (int k = 0; k < M()->n_regrow; k++) {
             M()->c_attempts_wq[k] = M()->c_attempts_q[k];
             M()->avail_wq[k] = M()->avail_q[k];
@@ -2083,6 +2178,7 @@ struct Engine {
 
         // new-configuration weights (setup_for_calc_new_weights, rg:147-153)
         rg_copy_queues_to_wq();
+#pragma unroll 1
         for (int k = 0; k < M()->n_regrow; k++) C()->oldc[M()->regrow[k]] = M()->prev[M()->regrow[k]];
         M()->n_modified = 0;
         rg_unassign_and_save_domains();
@@ -2099,6 +2195,7 @@ struct Engine {
         weight_new = weight;
         weight = 1;
         rg_copy_queues_to_wq();
+#pragma unroll 1
         for (int k = 0; k < M()->n_regrow; k++) C()->newc[M()->regrow[k]] = M()->prev[M()->regrow[k]];
         M()->n_modified = 0;
         rg_unassign_and_save_domains();
@@ -2109,6 +2206,7 @@ struct Engine {
         // test_rg_acceptance (rg:515-533)
         double ratio = weight_new / weight * exp(-delta_e);
         if (test_acceptance(ratio)) {
+#pragma unroll 1
             for (int k = 0; k < M()->n_regrow; k++) M()->prev[M()->regrow[k]] = C()->newc[M()->regrow[k]];
             reset_origami();
             return true;
@@ -2139,6 +2237,7 @@ struct Engine {
         ct_select_indices(md);
         if (sys.S()->status != LDO_OK) return false;
         // setup_constraints (rg:134-145)
+#pragma unroll 1
         for (int k = 0; k < C()->n_sel; k++) C()->in_sel[C()->sel_scaf[k]] = 1;
         M()->scaf_dir[0] = (int8_t)dir;
         cp_find_growthpoints_endpoints(C()->sel_scaf, C()->n_sel, 0);
@@ -2164,6 +2263,7 @@ struct Engine {
             int nd = sys.step(last, M()->scaf_dir[0]);
             if (nd >= 0) cp_add_active_endpoint_seg(nd, rec_pos(s->dom[nd]), 0);
         }
+#pragma unroll 1
         for (int k = 0; k < n_stems; k++) {
             int stem = C()->stems[k];
             int gp = s->bound[stem];
@@ -2171,6 +2271,7 @@ struct Engine {
             M()->stem_gp[stem] = (short)gp;
             int seg_i = 1 + 2 * k;
             M()->stem_seg0[stem] = (int8_t)seg_i;
+#pragma unroll 1
             for (int q = 0; q < 2; q++) {
                 int sg = seg_i + q;
                 int a = C()->seg_start[sg], b = C()->seg_start[sg + 1];
@@ -2182,6 +2283,7 @@ struct Engine {
             }
         }
         // calculate_constraintpoints(segs, dirs, excluded) (top_constraint_points.cpp:223-248)
+#pragma unroll 1
         for (int sg = 0; sg < n_segs; sg++) {
             int a = C()->seg_start[sg], b = C()->seg_start[sg + 1];
             if (b > a) cp_find_growthpoints_endpoints(C()->seg_dom + a, b - a, sg);
@@ -2189,6 +2291,7 @@ struct Engine {
         cp_save_initial();
         int first = C()->seg_dom[0];
         cp_remove_active_endpoint(first);
+#pragma unroll 1
         for (int k = 0; k < n_stems; k++) {
             int stem = C()->stems[k];
             int gp = s->bound[stem];
@@ -2202,6 +2305,7 @@ struct Engine {
     LDO_HD int select_movetype() {
         double prob = uniform_real();
         int i;
+#pragma unroll 1
         for (i = 0; i < MS().n; i++) {
             if (prob < MS().mt[i].cum_prob) break;
         }
