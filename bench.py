@@ -3,7 +3,7 @@
 
 Workload (BASELINE.json configs[2]): examples/ptmc.inp generalised to a batch:
 `ut_parallel_tempering`, exchange_interval 100, 32-temperature ladder 330..361 K (1 K steps), 4096
-replicas per GPU = 128*N ladders, GPU g holding ladder slots [g*32/N, (g+1)*32/N) of every ladder, start
+replicas per GPU = 128*N ladders, ladder slots dealt round-robin over the N GPUs (slot k on GPU k % N), start
 from snodin_unbound, moveset_standard. One "step" = one exchange round: 100 attempted moves on every
 replica, collection of the exchange quantities, (N > 1: NCCL all-gather), on-device swap decisions and
 the energy rebuild that follows a control-variable update.

@@ -237,8 +237,9 @@ int ldo_center(ldo_engine* e, int centering_domain);
 
 /* Replaces: PTGCMCSimulation::attempt_exchange for the 1-D variants (ptmc_simulation.cpp:360-412)
  * over `n_ladders` independent ladders of `ladder_len` control-variable slots, sharded over `n_ranks`
- * GPUs: rank g holds replicas [g*S, (g+1)*S) of EVERY ladder (S = ladder_len / n_ranks), replica k of
- * ladder l at local index l*S + k%S, so every exchange round has pairs that straddle GPUs. Decisions
+ * GPUs: the slots of EVERY ladder are dealt round-robin, replica k of ladder l living on rank k % n_ranks
+ * at local index l*S + k/n_ranks (S = ladder_len / n_ranks), so every neighbour pair straddles two GPUs
+ * and the temperature-dependent cost of a move is balanced across them. Decisions
  * are taken on device from a Philox stream shared by all ranks (identical on every rank, no
  * communication); accepted swaps relabel control variables (temperature table index and multipliers),
  * configurations never move. `dependent` is the all-gathered, rank-major [n_ranks][R][3 + n_staple_types]

@@ -428,7 +428,7 @@ struct __align__(16) WarpSmem {
 #define LDO_BLOCK_WARPS 2
 #endif
 #ifndef LDO_MIN_BLOCKS
-#define LDO_MIN_BLOCKS 12
+#define LDO_MIN_BLOCKS 14
 #endif
 template <class K>
 __global__ void __launch_bounds__(32 * LDO_BLOCK_WARPS, LDO_MIN_BLOCKS) k_exec_staged(DevPtrs<K> P, OpArgs a, int warps_per_block) {
@@ -494,12 +494,13 @@ struct ExchangeArgs {
 // One thread per ladder: the neighbour tests of one ladder are sequential in the reference only
 // through the shared RNG; here every (swap, ladder, pair) owns a Philox counter, so all ranks
 // reproduce the same decisions without communication.
-// Replica k of ladder l lives on rank k / S (S = ladder_len / n_ranks slots of every ladder per rank) at
-// local index l * S + k % S; the all-gathered buffer is rank-major.
-LDO_HD inline int exchange_rank_of(const ExchangeArgs& x, int k) { return k / (x.ladder_len / x.n_ranks); }
+// Replica k of ladder l lives on rank k % n_ranks (ladder slots are dealt round-robin, which balances the
+// temperature-dependent cost of a move across GPUs) at local index l * S + k / n_ranks with
+// S = ladder_len / n_ranks; the all-gathered buffer is rank-major.
+LDO_HD inline int exchange_rank_of(const ExchangeArgs& x, int k) { return k % x.n_ranks; }
 LDO_HD inline int exchange_local_index(const ExchangeArgs& x, int l, int k) {
     int S = x.ladder_len / x.n_ranks;
-    return l * S + k % S;
+    return l * S + k / x.n_ranks;
 }
 LDO_HD inline size_t exchange_gathered_index(const ExchangeArgs& x, int l, int k) {
     return (size_t)exchange_rank_of(x, k) * x.n_local + exchange_local_index(x, l, k);

@@ -417,6 +417,9 @@ struct Engine {
         }
         const TapeDraw& t = g->tape[g->tape_pos];
         if (t.kind != 0) {
+#if defined(LDO_DEBUG_SLOTS) && !defined(__CUDA_ARCH__)
+            printf("TAPE MISMATCH at %lld: requested real, tape has int(%d,%d)=%d\n", g->tape_pos, t.lo, t.hi, t.ival);
+#endif
             sys.fail(LDO_ERR_TAPE_MISMATCH, (int)g->tape_pos);
             return 0.5;
         }
@@ -431,6 +434,9 @@ struct Engine {
         }
         const TapeDraw& t = g->tape[g->tape_pos];
         if (t.kind != 1 || t.lo != lo || t.hi != hi) {
+#if defined(LDO_DEBUG_SLOTS) && !defined(__CUDA_ARCH__)
+            printf("TAPE MISMATCH at %lld: requested int(%d,%d), tape has kind %d (%d,%d)\n", g->tape_pos, lo, hi, t.kind, t.lo, t.hi);
+#endif
             sys.fail(LDO_ERR_TAPE_MISMATCH, (int)g->tape_pos);
             return lo;
         }
@@ -1785,6 +1791,7 @@ struct Engine {
         if (kind == 1) pv = sl.p[pc];
         else if (kind == 2 && o == sl.ore[pc]) pv = sl.p[pc];
 #if defined(LDO_DEBUG_SLOTS) && !defined(__CUDA_ARCH__)
+        if (getenv("LDO_DEBUG_RG")) printf("  trial di=%d d=(%d %d) ref=(%d %d) ci=%d p=(%d %d %d) o=%d kind=%d pv=%g tape_pos=%lld\n", di, sys.S()->chain_uid[sys.chain(d)], sys.dindex(d), sys.S()->chain_uid[sys.chain(ref_d)], sys.dindex(ref_d), i, p.x, p.y, p.z, o, kind, pv, RNG()->tape_pos);
         {
             DomRec saved = sys.S()->dom[d];
             double pref = rg_calc_p_config_open(p, o);
@@ -2169,6 +2176,18 @@ struct Engine {
     // Shared tail of the two CTRG scaffold moves (rg:636-689, 810-851). `whole_cyclic`: the
     // endpoint-removal guards evaluated by the caller (App. A2 keeps the contiguous variant's quirk).
     LDO_HDN bool rg_regrow_and_test(bool remove_first_a, bool remove_first_b, int first_dom) {
+#if defined(LDO_DEBUG_SLOTS) && !defined(__CUDA_ARCH__)
+        if (getenv("LDO_DEBUG_RG")) {
+            printf("RG regrow:");
+            for (int k = 0; k < M()->n_regrow; k++) {
+                int dd = M()->regrow[k];
+                printf(" (%d %d s%d d%d)", sys.S()->chain_uid[sys.chain(dd)], sys.dindex(dd), M()->seg_of[dd], cp_get_dir(dd));
+            }
+            printf("\n  ep0:");
+            for (int k = 0; k < C()->n_ep0; k++) printf(" [c%d s%d d%d (%d %d %d)]", sys.S()->chain_uid[C()->ep0_chain[k]], C()->ep0_seg[k], C()->ep0_d[k], C()->ep0_pos[k][0], C()->ep0_pos[k][1], C()->ep0_pos[k][2]);
+            printf("\n");
+        }
+#endif
         delta_e += rg_unassign_and_save_domains();
         delta_e += rg_recoil_regrow();
         if (M()->rejected) return false;
@@ -2287,6 +2306,9 @@ struct Engine {
         for (int sg = 0; sg < n_segs; sg++) {
             int a = C()->seg_start[sg], b = C()->seg_start[sg + 1];
             if (b > a) cp_find_growthpoints_endpoints(C()->seg_dom + a, b - a, sg);
+            // m_domain_to_dir is only filled for non-empty segments (:234-244); an empty one reads as
+            // direction 0, which matters to calc_remaining_steps on cyclic scaffolds (:585-587)
+            else M()->scaf_dir[sg] = 0;
         }
         cp_save_initial();
         int first = C()->seg_dom[0];

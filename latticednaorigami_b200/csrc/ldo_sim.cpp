@@ -454,7 +454,7 @@ ldo_sim* ldo_sim_create(const char* inp_path, int n_replicas, int device, int ra
             s->check(ldo_set_exchange_ladder(s->eng, s->num_reps, ladder_ti.data(), cm.data(), bmm.data(), smm.data()));
             int slots_per_rank {s->num_reps / s->n_ranks};
             for (int r {0}; r != n_replicas; r++) {
-                int k {s->rank * slots_per_rank + r % slots_per_rank};
+                int k {s->rank + (r % slots_per_rank) * s->n_ranks};
                 ti[r] = k;
                 um[r] = cm[k];
                 // OneDPTGCMCSimulation::initialize_control_qs stores the bias multiplier in the wrong
@@ -504,7 +504,7 @@ ldo_sim* ldo_sim_create(const char* inp_path, int n_replicas, int device, int ra
             int slots_per_rank {s->num_reps / s->n_ranks};
             std::vector<unsigned int> sub(n_replicas);
             for (int r {0}; r != n_replicas; r++) {
-                int l {r / slots_per_rank}, k {s->rank * slots_per_rank + r % slots_per_rank};
+                int l {r / slots_per_rank}, k {s->rank + (r % slots_per_rank) * s->n_ranks};
                 sub[r] = static_cast<unsigned int>(l * s->num_reps + k);
             }
             s->check(ldo_seed_subsequences(s->eng, seed, sub.data()));

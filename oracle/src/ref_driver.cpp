@@ -416,3 +416,32 @@ double oref_num_walks(int const* start, int const* end, int steps) {
 }
 
 } // extern "C"
+
+// ---- debugging aid: regrowth stack and initial active endpoints of the last CTRG move ----------------
+#include "LatticeDNAOrigami/rg_movetypes.hpp"
+extern "C" int oref_debug_rg(void* vh, int movetype, int* out, int cap) {
+    auto h = static_cast<Handle*>(vh);
+    auto* mt = dynamic_cast<movetypes::CTRGRegrowthMCMovetype*>(h->sim->m_movetypes[movetype].get());
+    if (mt == nullptr) return -1;
+    int n = 0;
+    auto put = [&](int v) { if (n < cap) out[n++] = v; };
+    put(static_cast<int>(mt->m_regrow_ds.size()));
+    for (auto d: mt->m_regrow_ds) {
+        put(d->m_c);
+        put(d->m_d);
+        put(mt->m_constraintpoints.m_segs[d]);
+        put(mt->m_constraintpoints.get_dir(d));
+    }
+    put(-999);
+    for (auto const& kv: mt->m_constraintpoints.m_initial_active_endpoints) {
+        for (auto const& ep: kv.second) {
+            put(kv.first.first);
+            put(kv.first.second);
+            put(ep.first);
+            put(ep.second.at(0));
+            put(ep.second.at(1));
+            put(ep.second.at(2));
+        }
+    }
+    return n;
+}

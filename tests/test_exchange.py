@@ -108,9 +108,9 @@ def test_two_rank_exchange_matches_single_rank(hostsim_lib, tmp_path):
     outs = [np.load(str(tmp_path / f"out{r}.npz")) for r in range(2)]
     for o in outs:
         assert np.array_equal(o["q2r"], q2r1) and np.array_equal(o["att"], att1) and np.array_equal(o["acc"], acc1)
-    # same trajectories: replica k of ladder l lives on rank k // 2 at local index l * 2 + k % 2
+    # same trajectories: replica k of ladder l lives on rank k % 2 at local index l * S + k // 2
     S = L // 2
     for l in range(n_ladders):
         for k in range(L):
-            got = outs[k // S]["energy"][l * S + k % S]
+            got = outs[k % 2]["energy"][l * S + k // 2]
             assert np.array_equal(got, e1[l, k]), (l, k)
