@@ -302,6 +302,10 @@ def run_ours(args, rank, world, local_rank):
         moves_per_launch = R * EXCHANGE_INTERVAL
         smem_gbs = SMEM_BYTES_PER_MOVE * moves_per_launch / (kernel_ms * 1e-3) / 1e9
         smem_peak = 148 * 128 * (clocks.get("sm_max_mhz") or 1965.0) * 1e6 / 1e9
+        traffic = None
+        traffic_path = os.path.join(ROOT, "profiles", "ncu_r1_run100.json")
+        if os.path.exists(traffic_path) and R == 4096:
+            traffic = json.load(open(traffic_path))["traffic_bytes_per_launch"]
         line = {
             "metric": "attempted MC moves/sec (whole box), snodin PTMC", "value": value, "unit": "attempted MC moves/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps,
@@ -310,10 +314,12 @@ def run_ours(args, rank, world, local_rank):
             "accepted_moves_per_s": value * accepted_frac,
             "e2e": {"value": e2e_value, "unit": "attempted MC moves/s", "h2d_bytes_per_step": int(blob_bytes),
                     "d2h_bytes_per_step": int(blob_bytes + energies.nbytes), "steps": e2e_steps},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "kernel": "k_exec_staged<CapsSmall> (run, 100 moves/replica)", "kernel_ms": kernel_ms,
                          "algorithmic_bytes_per_launch": hbm_bytes, "peak_source": peak_src,
-                         "note": "the path is latency/issue bound on shared memory, not HBM bound (SURVEY.md 8d): see smem",
+                         "note": "the path is instruction-fetch / latency bound, not HBM bound (SURVEY.md 8d, profiles/README.md); "
+                                 "traffic (ncu dram bytes of one 100-move launch) exceeds the algorithmic bytes because the "
+                                 "per-lane call stacks (local memory) spill past L2",
                          "smem": {"achieved": smem_gbs, "peak": smem_peak, "unit": "GB/s", "frac": smem_gbs / smem_peak,
                                   "bytes_per_move": SMEM_BYTES_PER_MOVE, "peak_source": "nominal 148 SM * 128 B/clk * sm_max_mhz"}},
         }
