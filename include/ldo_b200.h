@@ -255,6 +255,17 @@ int ldo_exchange_collect(ldo_engine* e, double* dependent_local);
 int ldo_exchange_pt(ldo_engine* e, int variant, long long swap_i, int n_ladders, int ladder_len,
                     int rank, int n_ranks, const double* dependent,
                     int* slot_to_replica, long long* attempts, long long* accepts);
+/* Replaces: PTMWUSGCMCSimulation::attempt_exchange (us_simulation.cpp:770-864) over n_ladders independent
+ * ladders of n_windows umbrella windows (replica l * n_windows + k starts in window k). Neighbouring
+ * windows swap when both current grid points lie inside both windows, with probability
+ * min(1, exp((b1(p1) - b2(p1)) + (b2(p2) - b1(p2)))) on the Grid bias `grid_bias`. An accepted swap
+ * exchanges the window-specific state of the two replicas (limits of the `window_biases` well biases,
+ * grid-bias values and visit histogram); the reference ships the two configurations instead, which is
+ * the same thing relabelled. window_to_replica is m_win_to_configi per ladder (the .swp row). Ladders are
+ * independent, so multi-GPU runs shard whole ladders and need no collective. */
+int ldo_exchange_windows(ldo_engine* e, long long swap_i, int n_ladders, int n_windows, int grid_bias,
+                         int n_window_biases, const int* window_biases, int* window_to_replica,
+                         long long* attempts, long long* accepts);
 /* Device pointers for the NCCL path: local send buffer / full receive buffer of the dependent
  * quantities ([n][3 + n_staple_types] doubles), so the all-gather runs device-to-device. */
 int ldo_exchange_buffers(ldo_engine* e, int n_global, void** send_dev, void** recv_dev, int* doubles_per_replica);

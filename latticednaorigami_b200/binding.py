@@ -19,7 +19,7 @@ ENGINE_SYMBOLS = [
     "ldo_get_energies", "ldo_get_counters", "ldo_get_staple_counts", "ldo_get_order_params",
     "ldo_get_move_stats", "ldo_recompute_energies", "ldo_check_all_constraints", "ldo_center",
     "ldo_set_exchange_ladder", "ldo_exchange_collect", "ldo_exchange_pt", "ldo_exchange_buffers",
-    "ldo_launch_count", "ldo_state_bytes", "ldo_checkpoint_size", "ldo_checkpoint_save", "ldo_checkpoint_load",
+    "ldo_exchange_windows", "ldo_launch_count", "ldo_state_bytes", "ldo_checkpoint_size", "ldo_checkpoint_save", "ldo_checkpoint_load",
 ]
 HOST_SYMBOLS = [
     "ldo_host_last_error", "ldo_sim_create", "ldo_sim_destroy", "ldo_sim_engine", "ldo_sim_run",
@@ -95,6 +95,7 @@ def load(path=None):
         "ldo_exchange_collect": (i, [vp, vp]),
         "ldo_exchange_pt": (i, [vp, i, ll, i, i, i, i, vp, vp, vp, vp]),
         "ldo_exchange_buffers": (i, [vp, i, vp, vp, vp]),
+        "ldo_exchange_windows": (i, [vp, ll, i, i, i, i, vp, vp, vp, vp]),
         "ldo_launch_count": (ll, [vp]),
         "ldo_state_bytes": (C.c_ulong, [vp]),
         "ldo_checkpoint_size": (C.c_ulong, [vp]),
@@ -282,6 +283,11 @@ class Engine:
         out = np.zeros(size, dtype=np.int64)
         self._check(self.L.ldo_get_grid_visits(self.h, replica, bias, _ptr(out), 1 if clear else 0))
         return out
+
+    def exchange_windows(self, swap_i, n_ladders, n_windows, grid_bias, window_biases, window_to_replica, attempts, accepts):
+        wb = np.ascontiguousarray(window_biases, dtype=np.int32)
+        self._check(self.L.ldo_exchange_windows(self.h, int(swap_i), n_ladders, n_windows, grid_bias, len(wb), _ptr(wb),
+                                                _ptr(window_to_replica), _ptr(attempts), _ptr(accepts)))
 
     # checkpoint
     def launch_count(self):

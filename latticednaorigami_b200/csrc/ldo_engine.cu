@@ -87,7 +87,7 @@ static const char* dev_err() { return cudaGetErrorString(g_last_cuda); }
 // Per-replica auxiliary state and shared (read-only) engine constants
 // ---------------------------------------------------------------------------------------------
 
-#define LDO_GRID_CAP 512 // grid-bias points per replica (sum over grid biases)
+#define LDO_GRID_CAP 1024 // grid-bias points per replica (sum over grid biases)
 
 struct __attribute__((aligned(16))) RepAux {
     Rng rng;
@@ -112,7 +112,9 @@ enum {
     OP_CHECK_CONSTRAINTS = 3,
     OP_CENTER = 4,
     OP_OBSERVE = 5,
-    OP_RECOMPUTE = 6
+    OP_RECOMPUTE = 6,
+    OP_REFRESH_OPS = 7,
+    OP_REINIT_BIASES = 8
 };
 
 struct OpArgs {
@@ -166,7 +168,7 @@ LDO_HD void rep_init_engine(Engine<K>& eng, SysState<K>* st, MoveScratch<K>* ms,
     eng.ms = &sh->ms;
     eng.ob = &sh->ob;
     eng.bs = &aux->bs;
-    eng.grid_vals = P.grid_vals ? P.grid_vals + (size_t)r * LDO_GRID_CAP : nullptr;
+    eng.grid_vals = P.grid_vals ? P.grid_vals + (size_t)aux->bs.grid_slot * LDO_GRID_CAP : nullptr;
     eng.ctl = aux->ctl;
     eng.stats = &aux->stats;
 }
@@ -346,7 +348,7 @@ LDO_HD void rep_execute(Engine<K>* engp, SysState<K>* st, MoveScratch<K>* ms, Re
     case OP_RUN: {
         if (st->status != LDO_OK) break;
         long long step = aux->step;
-        long long* visits = (P.shared->has_grid && P.grid_visits) ? P.grid_visits + (size_t)r * LDO_GRID_CAP : nullptr;
+        long long* visits = (P.shared->has_grid && P.grid_visits) ? P.grid_visits + (size_t)aux->bs.grid_slot * LDO_GRID_CAP : nullptr;
         for (long long n = 0; n < a.n_steps; n++) {
             step++;
             eng.mc_step();
@@ -385,6 +387,14 @@ LDO_HD void rep_execute(Engine<K>* engp, SysState<K>* st, MoveScratch<K>* ms, Re
     }
     case OP_OBSERVE: {
         rep_observe(eng, a, r);
+        break;
+    }
+    case OP_REFRESH_OPS: {
+        eng.update_move_params();
+        break;
+    }
+    case OP_REINIT_BIASES: {
+        rep_init_biases(eng);
         break;
     }
     case OP_RECOMPUTE: {
@@ -577,7 +587,122 @@ LDO_HD inline void exchange_ladder(const ExchangeArgs& x, int l) {
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Window exchange for replica-exchange multi-window umbrella sampling (us_simulation.cpp:770-864)
+// ---------------------------------------------------------------------------------------------
+
+struct WindowExchangeArgs {
+    long long swap_i;
+    int n_ladders, n_windows;
+    int grid_bias; // index of the Grid bias whose point / values decide the swap
+    int n_window_biases; // well biases overridden per window
+    int window_bias[LDO_MAX_BIASES];
+    unsigned long long seed;
+    int* window_to_replica; // [n_ladders][n_windows] (m_win_to_configi)
+    long long* attempts; // [n_ladders][n_windows - 1]
+    long long* accepts;
+    RepAux* aux;
+    const double* grid_vals;
+    const OpsBiasConst* ob;
+};
+
+LDO_HD inline double window_grid_value(const WindowExchangeArgs& x, const BiasState& owner, const int* point) {
+    int b = x.grid_bias;
+    int off = owner.grid_off[b];
+    if (off < 0) return 0;
+    const BiasDef& bd = x.ob->biases[b];
+    int idx = 0;
+    for (int k = 0; k < bd.n_ops; k++) {
+        int v = point[k] - owner.grid_lo[b][k];
+        if (v < 0 || v >= owner.grid_n[b][k]) return 0;
+        idx = idx * owner.grid_n[b][k] + v;
+    }
+    double g = x.grid_vals[(size_t)owner.grid_slot * LDO_GRID_CAP + off + idx];
+    return g == g ? g : 0; // absent points read as 0 (unordered_map::operator[], us_simulation.cpp:824-827)
+}
+
+// One thread per ladder of windows. An accepted swap exchanges the window-specific state of the two
+// replicas (limits of the window biases, grid boxes and grid slot = bias values and visit histogram);
+// the reference ships the configurations instead (:848-863), which is the same relabelled.
+LDO_HD inline void window_exchange_ladder(const WindowExchangeArgs& x, int l) {
+    int* w2r = x.window_to_replica + (size_t)l * x.n_windows;
+    const BiasDef& gb = x.ob->biases[x.grid_bias];
+    int swap_set = (int)(x.swap_i % 2);
+    for (int i = swap_set; i < x.n_windows - 1; i += 2) {
+        x.attempts[(size_t)l * (x.n_windows - 1) + i]++;
+        RepAux& a1 = x.aux[l * x.n_windows + w2r[i]];
+        RepAux& a2 = x.aux[l * x.n_windows + w2r[i + 1]];
+        int p1[LDO_MAX_GRID_DIM], p2[LDO_MAX_GRID_DIM];
+        bool same = true;
+        for (int k = 0; k < gb.n_ops; k++) {
+            p1[k] = a1.bs.op_val[gb.op_idx[k]];
+            p2[k] = a2.bs.op_val[gb.op_idx[k]];
+            if (p1[k] != p2[k]) same = false;
+        }
+        // both points must lie inside both windows (:800-815); window limits are those of the well biases
+        bool inside = true;
+        for (int j = 0; j < x.n_window_biases && inside; j++) {
+            int wb = x.window_bias[j];
+            int op = x.ob->biases[wb].op_idx[0];
+            int v1 = a1.bs.op_val[op], v2 = a2.bs.op_val[op];
+            if (v2 < a1.bs.win_min[wb] || v2 > a1.bs.win_max[wb]) inside = false;
+            if (v1 < a2.bs.win_min[wb] || v1 > a2.bs.win_max[wb]) inside = false;
+        }
+        if (!inside) continue;
+        bool accepted = true;
+        if (!same) {
+            double d1 = window_grid_value(x, a1.bs, p1) - window_grid_value(x, a2.bs, p1);
+            double d2 = window_grid_value(x, a2.bs, p2) - window_grid_value(x, a1.bs, p2);
+            double p_accept = fmin(1.0, exp(d1 + d2));
+            if (p_accept != 1) {
+                Rng g;
+                g.tape = nullptr;
+                g.key0 = (uint32_t)x.seed;
+                g.key1 = (uint32_t)(x.seed >> 32);
+                g.subseq = (uint32_t)(l * x.n_windows + i);
+                g.stream = 0x57494e44u; // "WIND"
+                uint32_t o[4];
+                philox4x32_10(g, (unsigned long long)x.swap_i, o);
+                unsigned long long u = ((unsigned long long)o[0] << 32) | o[1];
+                accepted = p_accept > (double)(u >> 11) * (1.0 / 9007199254740992.0);
+            }
+        }
+        if (!accepted) continue;
+        x.accepts[(size_t)l * (x.n_windows - 1) + i]++;
+        int t = w2r[i];
+        w2r[i] = w2r[i + 1];
+        w2r[i + 1] = t;
+        // swap the window-specific fields
+        for (int b = 0; b < x.ob->n_biases; b++) {
+            int ti = a1.bs.win_min[b];
+            a1.bs.win_min[b] = a2.bs.win_min[b];
+            a2.bs.win_min[b] = ti;
+            ti = a1.bs.win_max[b];
+            a1.bs.win_max[b] = a2.bs.win_max[b];
+            a2.bs.win_max[b] = ti;
+            ti = a1.bs.grid_off[b];
+            a1.bs.grid_off[b] = a2.bs.grid_off[b];
+            a2.bs.grid_off[b] = ti;
+            for (int k = 0; k < LDO_MAX_GRID_DIM; k++) {
+                ti = a1.bs.grid_lo[b][k];
+                a1.bs.grid_lo[b][k] = a2.bs.grid_lo[b][k];
+                a2.bs.grid_lo[b][k] = ti;
+                ti = a1.bs.grid_n[b][k];
+                a1.bs.grid_n[b][k] = a2.bs.grid_n[b][k];
+                a2.bs.grid_n[b][k] = ti;
+            }
+        }
+        int ts = a1.bs.grid_slot;
+        a1.bs.grid_slot = a2.bs.grid_slot;
+        a2.bs.grid_slot = ts;
+    }
+}
+
 #ifndef LDO_HOSTSIM
+__global__ void k_window_exchange(WindowExchangeArgs x) {
+    int l = blockIdx.x * blockDim.x + threadIdx.x;
+    if (l < x.n_ladders) window_exchange_ladder(x, l);
+}
 __global__ void k_exchange(ExchangeArgs x) {
     int l = blockIdx.x * blockDim.x + threadIdx.x;
     if (l < x.n_ladders) exchange_ladder(x, l);
@@ -623,6 +748,7 @@ struct EngineBase {
     virtual int attach_tape(int replica, const ldo_tape_draw* draws, long long n) = 0;
     virtual int exchange(ExchangeArgs& x, const double* dependent_host, int* slot_to_replica, long long* attempts, long long* accepts) = 0;
     virtual int exchange_buffers(int n_global, void** send, void** recv, int* nq) = 0;
+    virtual int window_exchange(WindowExchangeArgs& x, int* window_to_replica, long long* attempts, long long* accepts) = 0;
     virtual int alloc_outputs() = 0;
     virtual size_t blob_size() = 0;
     virtual size_t state_bytes() = 0;
@@ -739,6 +865,7 @@ struct EngineImpl: EngineBase {
             aux[r].ctl.stacking_mult = 1;
             aux[r].rng.subseq = (uint32_t)r;
             for (int b = 0; b < LDO_MAX_BIASES; b++) aux[r].bs.grid_off[b] = -1;
+            aux[r].bs.grid_slot = r;
         }
         if (dev_h2d(P.aux, aux.data(), sizeof(RepAux) * R, stream)) return fail(dev_err());
         return alloc_outputs();
@@ -1017,7 +1144,7 @@ struct EngineImpl: EngineBase {
         if (off + sz > LDO_GRID_CAP) return fail("grid bias exceeds LDO_GRID_CAP points");
         aux.bs.grid_off[bias] = off;
         if (put_aux(replica, 1, &aux)) return -1;
-        if (dev_h2d(P.grid_vals + (size_t)replica * LDO_GRID_CAP + off, vals, sizeof(double) * sz, stream)) return fail(dev_err());
+        if (dev_h2d(P.grid_vals + (size_t)aux.bs.grid_slot * LDO_GRID_CAP + off, vals, sizeof(double) * sz, stream)) return fail(dev_err());
         return 0;
     }
     int get_visits(int replica, int bias, long long* counts, int clear) override {
@@ -1028,7 +1155,7 @@ struct EngineImpl: EngineBase {
         if (off < 0) return fail("grid not set for this replica");
         int sz = 1;
         for (int k = 0; k < shared.ob.biases[bias].n_ops; k++) sz *= aux.bs.grid_n[bias][k];
-        long long* p = P.grid_visits + (size_t)replica * LDO_GRID_CAP + off;
+        long long* p = P.grid_visits + (size_t)aux.bs.grid_slot * LDO_GRID_CAP + off;
         if (dev_d2h(counts, p, sizeof(long long) * sz, stream)) return fail(dev_err());
         if (clear) {
             if (dev_memset(p, 0, sizeof(long long) * sz, stream)) return fail(dev_err());
@@ -1094,6 +1221,34 @@ struct EngineImpl: EngineBase {
         *send = d_dependent;
         *recv = d_dep_all;
         *nq = 3 + (shared.sc.n_types - 1);
+        return 0;
+    }
+
+    int window_exchange(WindowExchangeArgs& x, int* window_to_replica, long long* attempts, long long* accepts) override {
+        int n_slots = x.n_ladders * x.n_windows;
+        int n_pairs = x.n_ladders * (x.n_windows - 1);
+        if (n_slots != R) return fail("n_ladders * n_windows must equal the number of replicas");
+        if (ensure_exchange(R, n_slots)) return -1;
+        if (dev_h2d(d_q2r, window_to_replica, sizeof(int) * n_slots, stream)) return fail(dev_err());
+        if (dev_h2d(d_att, attempts, sizeof(long long) * n_pairs, stream)) return fail(dev_err());
+        if (dev_h2d(d_acc, accepts, sizeof(long long) * n_pairs, stream)) return fail(dev_err());
+        x.window_to_replica = d_q2r;
+        x.attempts = d_att;
+        x.accepts = d_acc;
+        x.aux = P.aux;
+        x.grid_vals = P.grid_vals;
+        x.ob = &d_shared->ob;
+#ifdef LDO_HOSTSIM
+        for (int l = 0; l < x.n_ladders; l++) window_exchange_ladder(x, l);
+#else
+        int threads = 128;
+        k_window_exchange<<<(x.n_ladders + threads - 1) / threads, threads, 0, stream>>>(x);
+        if (chk(cudaGetLastError())) return fail(dev_err());
+        launches++;
+#endif
+        if (dev_d2h(window_to_replica, d_q2r, sizeof(int) * n_slots, stream)) return fail(dev_err());
+        if (dev_d2h(attempts, d_att, sizeof(long long) * n_pairs, stream)) return fail(dev_err());
+        if (dev_d2h(accepts, d_acc, sizeof(long long) * n_pairs, stream)) return fail(dev_err());
         return 0;
     }
 
@@ -1686,6 +1841,35 @@ int ldo_exchange_pt(ldo_engine* e, int variant, long long swap_i, int n_ladders,
     // PTGCMCSimulation::run calls update_control_qs() at the top of every round, which always ends
     // in update_energy() (App. A19): rebuild the running energy with the (possibly new) tables
     return refresh_energy(e);
+}
+
+int ldo_exchange_windows(ldo_engine* e, long long swap_i, int n_ladders, int n_windows, int grid_bias,
+                         int n_window_biases, const int* window_biases, int* window_to_replica,
+                         long long* attempts, long long* accepts) {
+    EngineBase* b = e->b;
+    if (!b->shared.has_grid) return b->fail("no Grid bias configured");
+    if (grid_bias < 0 || grid_bias >= b->shared.ob.n_biases || b->shared.ob.biases[grid_bias].type != BIAS_GRID) {
+        return b->fail("grid_bias is not a Grid bias");
+    }
+    if (n_window_biases < 0 || n_window_biases > LDO_MAX_BIASES) return b->fail("bad window bias count");
+    // make the order parameters current, then decide, then restart the bias bookkeeping of every replica
+    OpArgs a;
+    memset(&a, 0, sizeof(a));
+    a.op = OP_REFRESH_OPS;
+    a.only_replica = -1;
+    if (b->exec(a, true)) return -1;
+    WindowExchangeArgs x;
+    memset(&x, 0, sizeof(x));
+    x.swap_i = swap_i;
+    x.n_ladders = n_ladders;
+    x.n_windows = n_windows;
+    x.grid_bias = grid_bias;
+    x.n_window_biases = n_window_biases;
+    for (int j = 0; j < n_window_biases; j++) x.window_bias[j] = window_biases[j];
+    x.seed = e->seed;
+    if (b->window_exchange(x, window_to_replica, attempts, accepts)) return -1;
+    a.op = OP_REINIT_BIASES;
+    return b->exec(a, true);
 }
 
 long long ldo_launch_count(const ldo_engine* e) { return e->b->launches; }

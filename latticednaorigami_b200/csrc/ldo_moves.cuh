@@ -128,7 +128,10 @@ struct BiasState {
     int win_min[LDO_MAX_BIASES], win_max[LDO_MAX_BIASES];
     int grid_lo[LDO_MAX_BIASES][LDO_MAX_GRID_DIM];
     int grid_n[LDO_MAX_BIASES][LDO_MAX_GRID_DIM];
-    int grid_off[LDO_MAX_BIASES]; // offset into the replica's grid value / visit arrays, -1 = none
+    int grid_off[LDO_MAX_BIASES]; // offset into the slot's grid value / visit arrays, -1 = none
+    // Which slot of the engine-wide grid arrays this replica currently uses. Window exchange swaps the
+    // window-specific fields (limits, boxes, slot) of two replicas instead of shipping configurations.
+    int grid_slot;
 };
 
 // ---------------------------------------------------------------------------------------------

@@ -8,7 +8,9 @@
 #include <fstream>
 #include <iomanip>
 #include <iostream>
+#include <map>
 #include <memory>
+#include <set>
 #include <random>
 #include <sstream>
 
@@ -45,7 +47,17 @@ struct ldo_sim {
     std::vector<int> q2r;
     std::vector<long long> attempts, accepts;
     std::vector<ReplicaFiles> files;
+    std::vector<int> file_owner; // file set -> replica (umbrella sampling: files follow windows)
+    std::string filebase_postfix; // "_iter-n" of the umbrella-sampling drivers
+    std::vector<std::string> window_postfix; // "_win-a--b" per window
     std::vector<int> ops_out_idx;
+    // umbrella sampling (us_simulation.hpp:60-150)
+    bool is_us {false}, is_mwus {false}, is_ptmwus {false};
+    int n_windows {1};
+    int grid_bias {-1};
+    std::vector<int> window_biases;
+    std::vector<int> grid_lo, grid_n;
+    WindowsFile windows;
     std::chrono::steady_clock::time_point start;
 
     ~ldo_sim() {
@@ -84,6 +96,14 @@ int bias_type_code(std::string const& t) {
 }
 
 std::string replica_filebase(ldo_sim& s, int r) {
+    if (s.is_us) {
+        // MWUSGCMCSimulation::setup_window_variables (us_simulation.cpp:486-501) + "_iter-n" (:107,131)
+        int ladder {r / s.n_windows}, w {r % s.n_windows};
+        std::string base {s.params.m_output_filebase};
+        if (s.is_mwus) base += s.window_postfix[w];
+        if (s.R / s.n_windows > 1) base += "_rep-" + std::to_string(s.rank * (s.R / s.n_windows) + ladder);
+        return base + s.filebase_postfix;
+    }
     // PTGCMCSimulation appends "-<rank>" (ptmc_simulation.cpp:48); batches of independent replicas do the same
     if (s.R * s.n_ranks == 1) return s.params.m_output_filebase;
     return s.params.m_output_filebase + "-" + std::to_string(s.rank * s.R + r);
@@ -169,9 +189,10 @@ void write_outputs(ldo_sim& s, long long step) {
     std::vector<int> ci(max_c), cid(max_c), cl(max_c), pos(3 * max_d), ore(3 * max_d), st(max_d), bd(2 * max_d);
     for (int r {0}; r != s.R; r++) {
         ReplicaFiles& f = s.files[r];
+        int rr {s.file_owner.empty() ? r : s.file_owner[r]}; // replica whose data this file set follows
         bool need_state {(w_trj && f.trj) || (w_counts && f.staplestates)};
         int nc {0};
-        if (need_state) s.check(ldo_get_state(s.eng, r, &nc, ci.data(), cid.data(), cl.data(), pos.data(), ore.data(), st.data(), bd.data()));
+        if (need_state) s.check(ldo_get_state(s.eng, rr, &nc, ci.data(), cid.data(), cl.data(), pos.data(), ore.data(), st.data(), bd.data()));
         if (w_trj && f.trj) {
             // OrigamiTrajOutputFile::write (files.cpp:529-548)
             std::ofstream& o = *f.trj;
@@ -191,14 +212,14 @@ void write_outputs(ldo_sim& s, long long step) {
             o.flush();
         }
         if (w_counts && f.counts) {
-            int const* c = &counters[9 * static_cast<size_t>(r)];
+            int const* c = &counters[9 * static_cast<size_t>(rr)];
             int unique {0};
             for (int t {0}; t != nst; t++)
-                if (staple_counts[static_cast<size_t>(r) * nst + t] > 0) unique++;
+                if (staple_counts[static_cast<size_t>(rr) * nst + t] > 0) unique++;
             *f.counts << step << " " << c[0] << " " << unique << " " << c[2] << " " << c[3] << " " << c[5] << " \n";
             f.counts->flush();
             *f.staples << step << " ";
-            for (int t {0}; t != nst; t++) *f.staples << staple_counts[static_cast<size_t>(r) * nst + t] << " ";
+            for (int t {0}; t != nst; t++) *f.staples << staple_counts[static_cast<size_t>(rr) * nst + t] << " ";
             *f.staples << "\n";
             f.staples->flush();
             // OrigamiStaplesFullyBoundOutputFile::write (files.cpp:667-690)
@@ -223,13 +244,13 @@ void write_outputs(ldo_sim& s, long long step) {
             f.times->flush();
         }
         if (w_ene && f.ene) {
-            double const* e = &ene[5 * static_cast<size_t>(r)];
+            double const* e = &ene[5 * static_cast<size_t>(rr)];
             *f.ene << step << " " << e[0] << " " << e[1] << " " << e[2] << " " << e[3] << " " << e[4] << " \n";
             f.ene->flush();
         }
         if (w_ops && f.ops) {
             *f.ops << step;
-            for (int idx: s.ops_out_idx) *f.ops << " " << opv[static_cast<size_t>(r) * s.ops.size() + idx];
+            for (int idx: s.ops_out_idx) *f.ops << " " << opv[static_cast<size_t>(rr) * s.ops.size() + idx];
             *f.ops << "\n";
             f.ops->flush();
         }
@@ -301,6 +322,290 @@ void set_all_control(ldo_sim& s, int temp_idx) {
     s.check(ldo_set_control(s.eng, 0, s.R, ti.data(), nullptr, nullptr, nullptr));
 }
 
+// ---------------------------------------------------------------------------------------------
+// Umbrella sampling drivers (us_simulation.cpp): single window, multi-window, replica-exchange MW
+// ---------------------------------------------------------------------------------------------
+
+using GridPoint = std::vector<int>;
+
+struct UsWindowState { // per window slot: USGCMCSimulation members m_S_n, m_s_i, m_f_i, m_E_w, m_p_i, m_w_i
+    std::set<GridPoint> S_n, s_i;
+    std::map<GridPoint, long long> f_i;
+    std::map<GridPoint, double> E_w, p_i, w_i;
+    std::vector<GridPoint> old_only;
+    long long steps {0};
+    std::unique_ptr<std::ofstream> us_stream;
+};
+
+std::vector<UsWindowState> g_unused_us_state; // (state lives in ldo_sim via a side table keyed by pointer)
+std::map<ldo_sim*, std::vector<UsWindowState>> g_us_states;
+
+// Upper bound of an order parameter, for the dense grid box the device uses in place of the reference's map
+int op_upper_bound(ldo_sim& s, int op) {
+    OrderParamSpec const& o = s.ops[op];
+    int n_scaf {static_cast<int>(s.sysfile->identities[0].size())};
+    int max_domains {n_scaf + s.params.m_max_total_staples * s.params.m_max_staple_size};
+    if (o.type == "NumStaples") return s.params.m_max_total_staples;
+    if (o.type == "NumStaplesType") return s.params.m_max_type_staples;
+    if (o.type == "StapleTypeFullyBound") return 1;
+    if (o.type == "NumBoundDomainPairs") return max_domains / 2;
+    if (o.type == "NumMisboundDomainPairs") return max_domains / 2;
+    if (o.type == "NumStackedPairs") return 2 * max_domains;
+    if (o.type == "Sum") {
+        int sum {0};
+        for (int k: o.sum_ops) sum += op_upper_bound(s, k);
+        return sum;
+    }
+    return 0;
+}
+
+void us_setup(ldo_sim& s) {
+    InputParameters const& p = s.params;
+    for (size_t b {0}; b != s.biases.size(); b++)
+        if (s.biases[b].tag == p.m_us_grid_bias_tag && s.biases[b].type == "Grid") s.grid_bias = static_cast<int>(b);
+    if (s.grid_bias < 0) throw SimulationMisuse {"us_grid_bias_tag does not name a Grid bias function"};
+    size_t total {1};
+    for (int op: s.biases[s.grid_bias].ops) {
+        s.grid_lo.push_back(0);
+        s.grid_n.push_back(op_upper_bound(s, op) + 1);
+        total *= s.grid_n.back();
+    }
+    if (total > 1024) throw SimulationMisuse {"grid bias box exceeds the device capacity of 1024 points"};
+    s.n_windows = 1;
+    if (s.is_mwus) {
+        s.windows = read_windows_file(p.m_windows_file);
+        s.n_windows = static_cast<int>(s.windows.mins.size());
+        if (s.n_windows < 1 || s.R % s.n_windows != 0) throw SimulationMisuse {"replica count must be a multiple of the number of windows"};
+        int wb {-1};
+        for (size_t b {0}; b != s.biases.size(); b++)
+            if (s.biases[b].tag == s.windows.bias_tag) wb = static_cast<int>(b);
+        if (wb < 0 || s.biases[wb].type == "Grid") throw SimulationMisuse {"windows file does not name a well bias function"};
+        s.window_biases = {wb};
+        for (int w {0}; w != s.n_windows; w++) {
+            // "_win-" + mins joined "-" + "-" + maxs each prefixed "-" (us_simulation.cpp:488-497)
+            std::string post {"_win-"};
+            for (int v: s.windows.mins[w]) post += std::to_string(v) + "-";
+            for (int v: s.windows.maxs[w]) post += "-" + std::to_string(v);
+            s.window_postfix.push_back(post);
+        }
+        for (int r {0}; r != s.R; r++) {
+            int w {r % s.n_windows};
+            s.check(ldo_set_window(s.eng, r, wb, s.windows.mins[w][0], s.windows.maxs[w][0]));
+        }
+    }
+    // empty grid (every point off-grid, bias 0) for every replica
+    std::vector<double> vals(total, std::nan(""));
+    for (int r {0}; r != s.R; r++) s.check(ldo_set_grid_bias(s.eng, r, s.grid_bias, s.grid_lo.data(), s.grid_n.data(), vals.data()));
+    auto& st = g_us_states[&s];
+    st.clear();
+    st.resize(s.R);
+    if (s.is_ptmwus) {
+        s.q2r.resize(s.R);
+        for (int r {0}; r != s.R; r++) s.q2r[r] = r % s.n_windows;
+        s.attempts.assign(static_cast<size_t>(s.R / s.n_windows) * std::max(s.n_windows - 1, 1), 0);
+        s.accepts = s.attempts;
+    }
+}
+
+size_t us_point_index(ldo_sim& s, GridPoint const& pt) {
+    size_t idx {0};
+    for (size_t k {0}; k != pt.size(); k++) idx = idx * s.grid_n[k] + static_cast<size_t>(pt[k] - s.grid_lo[k]);
+    return idx;
+}
+
+// replica currently holding window slot `slot` (slot = ladder * n_windows + window)
+int us_replica_of_slot(ldo_sim& s, int slot) {
+    if (!s.is_ptmwus) return slot;
+    int ladder {slot / s.n_windows}, w {slot % s.n_windows};
+    return ladder * s.n_windows + s.q2r[static_cast<size_t>(ladder) * s.n_windows + w];
+}
+
+void us_upload_bias(ldo_sim& s, int slot) {
+    UsWindowState& ws = g_us_states[&s][slot];
+    size_t total {1};
+    for (int n: s.grid_n) total *= n;
+    std::vector<double> vals(total, std::nan(""));
+    for (auto const& kv: ws.E_w) vals[us_point_index(s, kv.first)] = kv.second;
+    s.check(ldo_set_grid_bias(s.eng, us_replica_of_slot(s, slot), s.grid_bias, s.grid_lo.data(), s.grid_n.data(), vals.data()));
+}
+
+// USGCMCSimulation::output_weights (us_simulation.cpp:207-244); entries sorted by point
+void us_output_weights(ldo_sim& s, int slot, std::string const& filename) {
+    UsWindowState& ws = g_us_states[&s][slot];
+    std::ofstream f {filename};
+    f << "{\n    \"biases\": [";
+    bool first {true};
+    for (auto const& kv: ws.E_w) {
+        f << (first ? "\n" : ",\n");
+        first = false;
+        f << "        {\n            \"point\": [\n";
+        for (size_t i {0}; i + 1 < kv.first.size(); i++) f << "                " << std::to_string(kv.first[i]) << ",\n";
+        f << "                " << std::to_string(kv.first.back()) << "\n            ],\n";
+        f << "            \"bias\": " << std::to_string(kv.second) << "\n        }";
+    }
+    f << "\n    ]\n}\n";
+}
+
+void us_clear_visits(ldo_sim& s) {
+    size_t total {1};
+    for (int n: s.grid_n) total *= n;
+    std::vector<long long> counts(total);
+    for (int r {0}; r != s.R; r++) s.check(ldo_get_grid_visits(s.eng, r, s.grid_bias, counts.data(), 1));
+}
+
+// process_iteration (us_simulation.cpp:154-170) for one window slot
+void us_process_iteration(ldo_sim& s, int slot, int n, long long steps) {
+    InputParameters const& p = s.params;
+    UsWindowState& ws = g_us_states[&s][slot];
+    size_t total {1};
+    for (int k: s.grid_n) total *= k;
+    std::vector<long long> counts(total);
+    s.check(ldo_get_grid_visits(s.eng, us_replica_of_slot(s, slot), s.grid_bias, counts.data(), 1));
+    ws.s_i.clear();
+    ws.f_i.clear();
+    for (size_t idx {0}; idx != total; idx++) {
+        if (counts[idx] == 0) continue;
+        GridPoint pt(s.grid_n.size());
+        size_t rem {idx};
+        for (size_t k {s.grid_n.size()}; k-- > 0;) {
+            pt[k] = static_cast<int>(rem % s.grid_n[k]) + s.grid_lo[k];
+            rem /= s.grid_n[k];
+        }
+        ws.s_i.insert(pt);
+        ws.f_i[pt] = counts[idx];
+    }
+    // fill_grid_sets (:307-340): points seen before but not in this iteration
+    ws.old_only.clear();
+    for (auto const& pt: ws.S_n)
+        if (!ws.s_i.count(pt)) ws.old_only.push_back(pt);
+    ws.S_n.insert(ws.s_i.begin(), ws.s_i.end());
+    // estimate_current_weights (:286-305)
+    auto bias_of = [&](GridPoint const& pt) {
+        auto it = ws.E_w.find(pt);
+        return it == ws.E_w.end() ? 0.0 : it->second;
+    };
+    double ave {0};
+    for (auto const& pt: ws.s_i) ave += ws.f_i[pt] * std::exp(bias_of(pt));
+    for (auto const& pt: ws.s_i) ws.p_i[pt] = ws.f_i[pt] * std::exp(bias_of(pt)) / ave;
+    for (auto const& pt: ws.old_only) ws.p_i[pt] = 0;
+    // update_grids (:418-434)
+    for (auto const& pt: ws.s_i) ws.w_i[pt] = static_cast<double>(ws.f_i[pt]) / steps;
+    for (auto const& pt: ws.old_only) ws.w_i[pt] = 0;
+    // SimpleUSGCMCSimulation::update_bias (:385-416)
+    for (auto const& pt: ws.S_n) {
+        double old_bias {ws.E_w[pt]};
+        double p_k_n {ws.p_i[pt]};
+        double D_bias, new_bias;
+        if (p_k_n == 0) {
+            D_bias = -p.m_max_D_bias;
+            new_bias = old_bias + D_bias;
+        }
+        else {
+            new_bias = std::log(p_k_n);
+            D_bias = new_bias - old_bias;
+        }
+        double updated {new_bias};
+        if (std::abs(D_bias) > p.m_max_D_bias) updated = D_bias > 0 ? old_bias + p.m_max_D_bias : old_bias - p.m_max_D_bias;
+        ws.E_w[pt] = updated;
+    }
+    us_upload_bias(s, slot);
+    // output_summary (:436-452)
+    if (ws.us_stream) {
+        std::ostream& o = *ws.us_stream;
+        o << "Iteration: " << n << "\n\nGridpoint w, P, E:\n";
+        for (auto const& pt: ws.S_n) {
+            for (int c: pt) o << c << " ";
+            o << std::setprecision(3) << ": " << std::setw(10) << ws.w_i[pt] << std::setw(10) << ws.p_i[pt] << std::setw(10) << ws.E_w[pt] << "\n";
+        }
+        o << "\n";
+        o.flush();
+    }
+}
+
+void us_open_iteration_files(ldo_sim& s, std::string const& postfix) {
+    s.filebase_postfix = postfix;
+    s.files.clear();
+    open_output_files(s);
+    s.file_owner.resize(s.R);
+    for (int slot {0}; slot != s.R; slot++) s.file_owner[slot] = us_replica_of_slot(s, slot);
+}
+
+void us_run(ldo_sim& s) {
+    InputParameters const& p = s.params;
+    auto& st = g_us_states[&s];
+    int n_ladders {s.R / s.n_windows};
+    // per-window summary streams "<filebase><window postfix>.out" (us_simulation.cpp:545-547)
+    if (!p.m_output_filebase.empty()) {
+        for (int slot {0}; slot != s.R; slot++) {
+            s.filebase_postfix = "";
+            st[slot].us_stream.reset(new std::ofstream {replica_filebase(s, slot) + ".out"});
+            *st[slot].us_stream << "No biases read in\nStarting from configuration in system file\nStarting new iteration\n";
+        }
+    }
+    double saved_max_duration {s.params.m_max_duration};
+    // run_equilibration (:93-116)
+    if (!(s.is_ptmwus && (p.m_restart_us_iter || p.m_read_biases))) {
+        us_open_iteration_files(s, "_iter-equil");
+        s.params.m_max_duration = static_cast<double>(p.m_max_equil_dur);
+        s.start = std::chrono::steady_clock::now();
+        s.step = 0;
+        simulate(s, p.m_equil_steps);
+        us_clear_visits(s);
+    }
+    for (int n {0}; n != p.m_max_num_iters; n++) {
+        // prepare_iteration (:127-147)
+        us_open_iteration_files(s, "_iter-" + std::to_string(n));
+        if (!p.m_output_filebase.empty())
+            for (int slot {0}; slot != s.R; slot++) us_output_weights(s, slot, replica_filebase(s, slot) + "-inp.biases");
+        s.params.m_max_duration = static_cast<double>(p.m_max_iter_dur);
+        s.start = std::chrono::steady_clock::now();
+        s.step = 0;
+        long long steps_done {0};
+        if (s.is_ptmwus) {
+            // run_swaps (:662-706); swap file "<filebase>_iter-n.swp" (:900-918), first ladder
+            std::ofstream swp;
+            if (!p.m_output_filebase.empty()) swp.open(p.m_output_filebase + "_iter-" + std::to_string(n) + ".swp");
+            auto write_swap_entry = [&](long long step) {
+                if (!swp.is_open() || p.m_configs_output_freq == 0 || step % p.m_configs_output_freq != 0) return;
+                for (int w {0}; w != s.n_windows; w++) swp << s.q2r[w] << " ";
+                swp << "\n";
+            };
+            write_swap_entry(0);
+            for (long long swap_i {1}; swap_i != p.m_iter_swaps + 1; swap_i++) {
+                bool more {simulate(s, p.m_exchange_interval)};
+                steps_done += p.m_exchange_interval;
+                if (!more) break;
+                write_swap_entry(s.step);
+                s.check(ldo_exchange_windows(
+                        s.eng, swap_i, n_ladders, s.n_windows, s.grid_bias, static_cast<int>(s.window_biases.size()),
+                        s.window_biases.data(), s.q2r.data(), s.attempts.data(), s.accepts.data()));
+                for (int slot {0}; slot != s.R; slot++) s.file_owner[slot] = us_replica_of_slot(s, slot);
+            }
+            write_swap_entry(s.step);
+            // write_acceptance_freqs (:884-898)
+            std::cout << "Iter " << n << "\nWindow 1, Window 2, Swaps, Attempts, Frequency\n";
+            for (int w {0}; w + 1 < s.n_windows; w++) {
+                std::cout << w << " " << w + 1 << " " << s.accepts[w] << " " << s.attempts[w] << " "
+                          << static_cast<double>(s.accepts[w]) / s.attempts[w] << "\n";
+            }
+            std::cout << "\n";
+            std::fill(s.attempts.begin(), s.attempts.end(), 0);
+            std::fill(s.accepts.begin(), s.accepts.end(), 0);
+        }
+        else {
+            simulate(s, p.m_iter_steps);
+            steps_done = s.step;
+        }
+        // process_iteration
+        for (int slot {0}; slot != s.R; slot++) {
+            us_process_iteration(s, slot, n, steps_done);
+            if (!p.m_output_filebase.empty()) us_output_weights(s, slot, replica_filebase(s, slot) + ".biases");
+        }
+    }
+    s.params.m_max_duration = saved_max_duration;
+    s.filebase_postfix = "";
+}
+
 } // namespace
 
 extern "C" {
@@ -335,8 +640,11 @@ ldo_sim* ldo_sim_create(const char* inp_path, int n_replicas, int device, int ra
 
         // temperatures
         std::string const& st = p.m_simulation_type;
-        if (st == "constant_temp" || st == "umbrella_sampling" || st == "mw_umbrella_sampling") {
+        if (st == "constant_temp" || st == "umbrella_sampling" || st == "mw_umbrella_sampling" || st == "ptmw_umbrella_sampling") {
             s->temps = {p.m_temp};
+            s->is_us = st != "constant_temp";
+            s->is_mwus = st == "mw_umbrella_sampling" || st == "ptmw_umbrella_sampling";
+            s->is_ptmwus = st == "ptmw_umbrella_sampling";
         }
         else if (st == "annealing") {
             for (double t {p.m_max_temp}; t >= p.m_min_temp; t -= p.m_temp_interval) s->temps.push_back(t);
@@ -441,6 +749,8 @@ ldo_sim* ldo_sim_create(const char* inp_path, int n_replicas, int device, int ra
             s->check(ldo_set_biases(s->eng, static_cast<int>(bd.size()), bd.data()));
         }
 
+        if (s->is_us) us_setup(*s);
+
         // control variables
         std::vector<int> ti(n_replicas, 0);
         std::vector<double> um(n_replicas, p.m_staple_u_mult), bm(n_replicas, p.m_bias_funcs_mult), sm(n_replicas, 1.0);
@@ -520,7 +830,10 @@ ldo_sim* ldo_sim_create(const char* inp_path, int n_replicas, int device, int ra
     return s.release();
 }
 
-void ldo_sim_destroy(ldo_sim* s) { delete s; }
+void ldo_sim_destroy(ldo_sim* s) {
+    g_us_states.erase(s);
+    delete s;
+}
 ldo_engine* ldo_sim_engine(ldo_sim* s) { return s->eng; }
 
 int ldo_sim_exchange_advance(ldo_sim* s) {
@@ -557,7 +870,7 @@ int ldo_sim_exchange_state(ldo_sim* s, int* slot_to_replica, long long* attempts
 int ldo_sim_run(ldo_sim* s) {
     try {
         InputParameters const& p = s->params;
-        open_output_files(*s);
+        if (!s->is_us) open_output_files(*s);
         s->start = std::chrono::steady_clock::now();
         std::string const& st = p.m_simulation_type;
         if (st == "constant_temp") {
@@ -569,6 +882,9 @@ int ldo_sim_run(ldo_sim* s) {
                 set_all_control(*s, static_cast<int>(i));
                 if (!simulate(*s, p.m_steps_per_temp)) break;
             }
+        }
+        else if (s->is_us) {
+            us_run(*s);
         }
         else if (s->is_pt) {
             if (s->n_ranks != 1) throw SimulationMisuse {"ldo_sim_run drives single-GPU exchange only"};
