@@ -164,6 +164,49 @@ struct MoveSet {
     double exchange_mults[LDO_MAX_TYPES];
 };
 
+// Extended-precision accumulator for the configurational-bias Rosenbluth weights. The reference keeps
+// m_bias / m_new_bias in x87 long double (cb_movetypes.hpp:126) and only the final min(1, ratio) is
+// rounded to double (movetypes.cpp:142-143); whether that rounds to exactly 1 decides if a random number
+// is drawn, so fp64 products are not enough for replay parity. A double-double (hi + lo, ~106 bits,
+// error-free products through fma) rounds to the same double as the 64-bit x87 mantissa except within
+// 2^-64 of a rounding boundary.
+struct DD {
+    double hi, lo;
+};
+LDO_HD inline DD dd_from(double a) {
+    DD r;
+    r.hi = a;
+    r.lo = 0;
+    return r;
+}
+LDO_HD inline DD dd_renorm(double a, double b) {
+    DD r;
+    r.hi = a + b;
+    r.lo = b - (r.hi - a);
+    return r;
+}
+LDO_HD inline DD dd_mul(DD a, double b) {
+    double p = a.hi * b;
+    double e = fma(a.hi, b, -p) + a.lo * b;
+    return dd_renorm(p, e);
+}
+LDO_HD inline DD dd_div(DD a, double b) {
+    double q1 = a.hi / b;
+    double r = fma(-q1, b, a.hi) + a.lo;
+    return dd_renorm(q1, r / b);
+}
+// a / b rounded like the reference's (long double ratio -> fmin(1, .) -> double)
+LDO_HD inline double dd_ratio_min1(DD a, DD b) {
+    double q1 = a.hi / b.hi;
+    // remainder a - q1 * b in double-double
+    double p = q1 * b.hi;
+    double e = fma(q1, b.hi, -p) + q1 * b.lo;
+    double r = (a.hi - p) - e + a.lo;
+    DD q = dd_renorm(q1, r / b.hi);
+    if (q.hi > 1.0 || (q.hi == 1.0 && q.lo >= 0)) return 1.0;
+    return q.hi;
+}
+
 // 36-bit configuration masks: population count and position of the n-th (0-based) set bit
 LDO_HD inline int popc36(unsigned long long m) {
 #if defined(__CUDA_ARCH__)
@@ -917,7 +960,7 @@ struct Engine {
         LDO_SYNCWARP();
     }
     // select_and_set_config for CBStapleRegrowth (cb_movetypes.cpp:104-160, 363-387)
-    LDO_HDN void cb_select_and_set_config(int dom, int prev_dom, bool regrow_old, double& bias) {
+    LDO_HDN void cb_select_and_set_config(int dom, int prev_dom, bool regrow_old, DD& bias) {
         V3 p_prev = rec_pos(sys.S()->dom[prev_dom]);
         cb_site_weights(p_prev, dom);
         sys.S()->constraints_violated = 0;
@@ -930,7 +973,7 @@ struct Engine {
             M()->rejected = 1;
             return;
         }
-        bias *= ros;
+        bias = dd_mul(bias, ros);
         if (!regrow_old) {
             double cum = 0;
             double r = uniform_real();
@@ -955,23 +998,23 @@ struct Engine {
         }
         push_assigned(dom);
     }
-    LDO_HD void cb_grow_chain(int first, int stepdir, int count, bool regrow_old, double& bias) {
+    LDO_HD void cb_grow_chain(int first, int stepdir, int count, bool regrow_old, DD& bias) {
 #pragma unroll 1
         for (int i = 1; i < count; i++) {
             cb_select_and_set_config(first + stepdir * i, first + stepdir * (i - 1), regrow_old, bias);
             if (M()->rejected) break;
         }
     }
-    LDO_HD void cb_set_growthpoint_and_grow_staple(int g_new, int g_old, int c, bool regrow_old, double& bias) {
+    LDO_HD void cb_set_growthpoint_and_grow_staple(int g_new, int g_old, int c, bool regrow_old, DD& bias) {
         if (regrow_old) {
             // set_old_growth_point (cb_movetypes.cpp:168-180)
             double de = sys.set_checked_domain_config(g_new, rec_pos(sys.S()->dom[g_old]), C()->oldc[g_new].ore);
-            bias *= exp(-de);
+            bias = dd_mul(bias, exp(-de));
             push_assigned(g_new);
         }
         else {
             double de = set_growth_point(g_new, g_old);
-            bias *= exp(-de);
+            bias = dd_mul(bias, exp(-de));
         }
         if (!M()->rejected) {
             int base = sys.chain_base(c);
@@ -997,7 +1040,7 @@ struct Engine {
         if (s->num_staples == 0) return false;
         int c = s->order[uniform_int(1, s->num_staples)];
         if (staple_is_connector(c)) return false;
-        double bias = 1;
+        DD bias = dd_from(1.0);
         int n_bd = count_bound_to_other_chains(c);
         if (n_bd == 0) {
             sys.fail(LDO_ERR_UNBOUND_STAPLE, c);
@@ -1017,19 +1060,19 @@ struct Engine {
             sys.fail(LDO_ERR_CAPACITY, 4);
             return false;
         }
-        bias *= n_bd;
+        bias = dd_mul(bias, (double)n_bd);
         int gi = uniform_int(0, n_bd - 1);
         cb_unassign_domains(c);
         cb_set_growthpoint_and_grow_staple(bd_new[gi], bd_old[gi], c, false, bias);
         if (M()->rejected) return false;
-        bias /= num_bound_staple_domains(c);
+        bias = dd_div(bias, (double)num_bound_staple_domains(c));
         // add_external_bias (cb_movetypes.cpp:52-56)
         update_move_params();
-        bias *= exp(-calc_move_bias());
+        bias = dd_mul(bias, exp(-calc_move_bias()));
         // setup_for_regrow_old (cb_movetypes.cpp:237-247)
-        double new_bias = bias;
+        DD new_bias = bias;
         double new_modifier = M()->modifier;
-        bias = 1;
+        bias = dd_from(1.0);
         M()->n_modified = 0;
         M()->n_assigned = 0;
         {
@@ -1042,7 +1085,7 @@ struct Engine {
         cb_set_growthpoint_and_grow_staple(bd_new[gi], bd_old[gi], c, true, bias);
         M()->modifier = new_modifier;
         // test_cb_acceptance (cb_movetypes.cpp:182-198)
-        double ratio = new_bias / bias;
+        double ratio = dd_ratio_min1(new_bias, bias);
         if (test_acceptance(ratio)) {
             reset_origami();
             update_move_params();
