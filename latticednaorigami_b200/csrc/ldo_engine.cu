@@ -1426,8 +1426,7 @@ int ldo_set_moveset(ldo_engine* e, int n, const ldo_movetype_desc* mts, int allo
     for (int i = 0; i < n; i++) {
         MoveDef& md = ms.mt[i];
         md.type = mts[i].type;
-        if (md.type == MT_CTCB_SCAFFOLD_REGROWTH || md.type == MT_CTCB_JUMP_SCAFFOLD_REGROWTH || md.type < 0 ||
-            md.type > MT_CTRG_JUMP_SCAFFOLD_REGROWTH) {
+        if (md.type < 0 || md.type > MT_CTRG_JUMP_SCAFFOLD_REGROWTH) {
             return b->fail("movetype not available on device");
         }
         cum += mts[i].freq;
@@ -1445,6 +1444,9 @@ int ldo_set_moveset(ldo_engine* e, int n, const ldo_movetype_desc* mts, int allo
                 ms.exchange_mults[em_off + t] = t < mts[i].n_exchange_mults ? mts[i].exchange_mults[t] : 1.0;
             }
             em_off += nst;
+        }
+        if ((md.type == MT_CTCB_SCAFFOLD_REGROWTH || md.type == MT_CTCB_JUMP_SCAFFOLD_REGROWTH) && md.max_regrowth < 2) {
+            return b->fail("CTCB options out of range (max_regrowth >= 2)");
         }
         if ((md.type == MT_CTRG_SCAFFOLD_REGROWTH || md.type == MT_CTRG_JUMP_SCAFFOLD_REGROWTH) &&
             (md.max_c_attempts < 1 || md.max_c_attempts > 36 || md.max_regrowth < 2 || md.max_num_recoils < 0 ||

@@ -190,6 +190,25 @@ LDO_HD inline DD dd_mul(DD a, double b) {
     double e = fma(a.hi, b, -p) + a.lo * b;
     return dd_renorm(p, e);
 }
+LDO_HD inline DD dd_mul_dd(DD a, DD b) {
+    double p = a.hi * b.hi;
+    double e = fma(a.hi, b.hi, -p) + (a.hi * b.lo + a.lo * b.hi);
+    return dd_renorm(p, e);
+}
+LDO_HD inline DD dd_add(DD a, double b) {
+    double s = a.hi + b;
+    double bb = s - a.hi;
+    double e = (a.hi - (s - bb)) + (b - bb);
+    return dd_renorm(s, e + a.lo);
+}
+// double(a / b) for a double a and a double-double b (the reference divides two long doubles)
+LDO_HD inline double dd_quot(double a, DD b) {
+    double q1 = a / b.hi;
+    double p = q1 * b.hi;
+    double e = fma(q1, b.hi, -p) + q1 * b.lo;
+    double r = (a - p) - e;
+    return q1 + r / b.hi;
+}
 LDO_HD inline DD dd_div(DD a, double b) {
     double q1 = a.hi / b;
     double r = fma(-q1, b, a.hi) + a.lo;
@@ -371,6 +390,10 @@ struct ColdScratch {
     short seg_dom[2 * K::D + 2];
     short stems[K::D + 1];
     short stem_queue[4 * K::D + 8];
+
+    // CTCB: chains of the internally bound staple networks (m_regrowth_staples) and the growth work stack
+    uint8_t regrow_chain[K::C];
+    short work[K::LV + 1][4];
 };
 
 // Move statistics (MovetypeTracking, movetypes.hpp:49-52)
@@ -1109,7 +1132,10 @@ struct Engine {
             C()->in_sel[k] = 0;
         }
 #pragma unroll 1
-        for (int k = 0; k < K::C; k++) C()->checked_chain[k] = 0;
+        for (int k = 0; k < K::C; k++) {
+            C()->checked_chain[k] = 0;
+            C()->regrow_chain[k] = 0;
+        }
 #pragma unroll 1
         for (int k = 0; k < MoveScratch<K>::S; k++) M()->scaf_dir[k] = 0;
         M()->n_ep = 0;
@@ -1405,6 +1431,11 @@ struct Engine {
                 }
 #pragma unroll 1
                 for (int k = 0; k < C()->n_pot_iaes; k++) M()->inactive[C()->pot_iaes[k][0]] = C()->pot_iaes[k][1];
+                // add_regrowth_staples (:517-530)
+#pragma unroll 1
+                for (int k = 1; k < K::C; k++) {
+                    if (C()->net_chain[k]) C()->regrow_chain[k] = 1;
+                }
 #pragma unroll 1
                 for (int k = 0; k < C()->n_pot_ds; k++) {
                     int pd = C()->pot_ds[k];
@@ -2316,12 +2347,10 @@ struct Engine {
     }
 
     // CTRGJumpScaffoldRegrowthMCMovetype::internal_attempt_move (rg:791-851)
-    LDO_HDN bool move_ctrg_jump_scaffold(const MoveDef& md) {
+    // What select_noncontig_segs registers (movetypes.cpp:618-647) followed by
+    // calculate_constraintpoints(segs, dirs, excluded) (top_constraint_points.cpp:223-248)
+    LDO_HDN void rg_register_jump_constraints(int n_segs, int n_stems) {
         SysState<K>* s = sys.S();
-        rg_reset(md);
-        int n_stems = 0;
-        int n_segs = ct_select_noncontig_segs(md, n_stems);
-        if (s->status != LDO_OK) return false;
         // endpoints registered by select_noncontig_segs (movetypes.cpp:618-647)
         {
             int last = C()->seg_dom[C()->seg_start[1] - 1];
@@ -2357,6 +2386,14 @@ struct Engine {
             else M()->scaf_dir[sg] = 0;
         }
         cp_save_initial();
+    }
+    LDO_HDN bool move_ctrg_jump_scaffold(const MoveDef& md) {
+        SysState<K>* s = sys.S();
+        rg_reset(md);
+        int n_stems = 0;
+        int n_segs = ct_select_noncontig_segs(md, n_stems);
+        if (s->status != LDO_OK) return false;
+        rg_register_jump_constraints(n_segs, n_stems);
         int first = C()->seg_dom[0];
         cp_remove_active_endpoint(first);
 #pragma unroll 1
@@ -2367,6 +2404,274 @@ struct Engine {
             M()->stem_gp[stem] = (short)gp;
         }
         return rg_regrow_and_test(true, true, first);
+    }
+
+    // ---- CTCB scaffold regrowth (cb_movetypes.cpp:463-983) ----
+    // CTCBRegrowthMCMovetype::calc_bias (:486-539) on the six site weights of cb_site_weights
+    LDO_HDN void ctcb_select_and_set_config(int dom, int prev_dom, bool regrow_old, DD& bias) {
+        V3 p_prev = rec_pos(sys.S()->dom[prev_dom]);
+        cb_site_weights(p_prev, dom);
+        sys.S()->constraints_violated = 0;
+        DD sum = dd_from(0.0);
+        for (int k = 0; k < 6; k++) {
+            if (M()->site_kind[k] == 0) continue;
+            V3 cur = p_prev + ore_vec(k);
+            double w = M()->site_w[k];
+            if (M()->site_kind[k] == 2) {
+                int j = sys.occupant(cur);
+                bool same_chain = sys.chain(j) == sys.chain(dom);
+                if (!(same_chain || cp_endpoint_reached(dom, cur))) w = 0;
+            }
+            if (!cp_walks_remain(dom, cur)) w = 0;
+            M()->site_w[k] = w;
+            sum = dd_add(sum, w);
+        }
+        if (sum.hi == 0) {
+            M()->rejected = 1;
+            return;
+        }
+        bias = dd_mul_dd(bias, sum);
+        if (!regrow_old) {
+            double cum = 0;
+            double r = uniform_real();
+            V3 p_new = v3(0, 0, 0);
+            int o_new = ORE_ZERO;
+            for (int k = 0; k < 6; k++) {
+                if (M()->site_kind[k] == 0) continue;
+                cum += dd_quot(M()->site_w[k], sum);
+                if (r < cum) {
+                    p_new = p_prev + ore_vec(k);
+                    o_new = M()->site_kind[k] == 2 ? M()->site_o[k] : ORE_ZERO;
+                    break;
+                }
+            }
+            if (o_new == ORE_ZERO) o_new = uniform_int(0, 5);
+            sys.set_checked_domain_config(dom, p_new, o_new);
+        }
+        else {
+            const DomRec& r = C()->oldc[dom];
+            sys.set_checked_domain_config(dom, rec_pos(r), r.ore);
+        }
+        push_assigned(dom);
+    }
+    // Explicit work stack of chain pieces to grow: (first domain, +-1, count, next index), replacing
+    // the recursion grow_chain -> grow_staple_and_update_endpoints -> grow_staple -> grow_chain
+    // (cb_movetypes.cpp:463-484, 541-562; movetypes.cpp:343-370)
+    LDO_HD bool ctcb_push(int first, int stepdir, int count, int& sp) {
+        if (count <= 1) return true;
+        if (sp >= K::LV) {
+            sys.fail(LDO_ERR_CAPACITY, 12);
+            return false;
+        }
+        C()->work[sp][0] = (short)first;
+        C()->work[sp][1] = (short)stepdir;
+        C()->work[sp][2] = (short)count;
+        C()->work[sp][3] = 1;
+        sp++;
+        return true;
+    }
+    // grow_staple_and_update_endpoints (:541-562): pushes the two pieces of the staple grown from growth_d_old
+    LDO_HDN void ctcb_grow_staple_from(int growth_d_old, bool regrow_old, DD& bias, int& sp) {
+        int g_new = M()->gp_stem[growth_d_old];
+        int c = sys.chain(g_new);
+        if (c == 0) return; // "HACK TO PREVENT ACCIDENTLY GROWING SCAFFOLD SEGMENTS" (:547-550)
+        if (regrow_old) {
+            double de = sys.set_checked_domain_config(g_new, rec_pos(sys.S()->dom[growth_d_old]), C()->oldc[g_new].ore);
+            bias = dd_mul(bias, exp(-de));
+            push_assigned(g_new);
+        }
+        else {
+            double de = set_growth_point(g_new, growth_d_old);
+            bias = dd_mul(bias, exp(-de));
+        }
+        if (M()->rejected) return;
+        cp_update_endpoints(g_new);
+        int base = sys.chain_base(c), len = sys.S()->chain_len[c], d_i = sys.dindex(g_new);
+        // 3' piece is grown first: push the 5' piece below it
+        ctcb_push(base + d_i, -1, d_i + 1, sp);
+        ctcb_push(base + d_i, +1, len - d_i, sp);
+    }
+    // CTCBRegrowthMCMovetype::grow_chain over an explicit list of domains (scaffold segments)
+    LDO_HDN void ctcb_run_stack(bool regrow_old, DD& bias, int& sp, int floor) {
+#pragma unroll 1
+        while (sp > floor && !M()->rejected && sys.S()->status == LDO_OK) {
+            short* w = C()->work[sp - 1];
+            int i = w[3];
+            if (i >= w[2]) {
+                sp--;
+                continue;
+            }
+            w[3] = (short)(i + 1);
+            int dom = w[0] + w[1] * i, prev = w[0] + w[1] * (i - 1);
+            ctcb_select_and_set_config(dom, prev, regrow_old, bias);
+            if (M()->rejected) break;
+            cp_update_endpoints(dom);
+            if (M()->gp_stem[dom] >= 0) ctcb_grow_staple_from(dom, regrow_old, bias, sp);
+        }
+    }
+    LDO_HDN void ctcb_grow_list(const short* doms, int n, bool regrow_old, DD& bias) {
+        int sp = 0;
+#pragma unroll 1
+        for (int i = 1; i < n && !M()->rejected && sys.S()->status == LDO_OK; i++) {
+            ctcb_select_and_set_config(doms[i], doms[i - 1], regrow_old, bias);
+            if (M()->rejected) break;
+            cp_update_endpoints(doms[i]);
+            if (M()->gp_stem[doms[i]] >= 0) {
+                ctcb_grow_staple_from(doms[i], regrow_old, bias, sp);
+                ctcb_run_stack(regrow_old, bias, sp, 0);
+            }
+        }
+    }
+    // staples_to_be_regrown is a std::set<int> of unique chain indices: ascending order (:167-169)
+    LDO_HDN void ctcb_unassign(const short* doms, int n_doms, bool with_staples) {
+#pragma unroll 1
+        for (int k = 0; k < n_doms; k++) {
+            int dd = doms[k];
+            M()->prev[dd] = sys.S()->dom[dd];
+            push_modified(dd);
+            sys.unassign_domain(dd);
+        }
+        if (!with_staples) return;
+        int last_uid = -1;
+#pragma unroll 1
+        for (;;) {
+            int best = -1, best_uid = 0x7fffffff;
+#pragma unroll 1
+            for (int c = 1; c < K::C; c++) {
+                if (!C()->regrow_chain[c]) continue;
+                int uid = sys.S()->chain_uid[c];
+                if (uid > last_uid && uid < best_uid) {
+                    best = c;
+                    best_uid = uid;
+                }
+            }
+            if (best < 0) break;
+            last_uid = best_uid;
+            cb_unassign_domains(best);
+        }
+    }
+    LDO_HDN void ctcb_setup_regrow_old(DD& bias, DD& new_bias) {
+        // setup_for_regrow_old (cb_movetypes.cpp:237-247)
+        new_bias = bias;
+        bias = dd_from(1.0);
+        M()->n_modified = 0;
+        M()->n_assigned = 0;
+#pragma unroll 1
+        for (int k = 0; k < K::D; k++) C()->oldc[k] = M()->prev[k];
+        cp_reset_active_endpoints();
+    }
+    LDO_HDN bool ctcb_finish(DD new_bias, DD bias) {
+        M()->modifier = 1;
+        double ratio = dd_ratio_min1(new_bias, bias);
+        if (test_acceptance(ratio)) {
+            reset_origami();
+            update_move_params();
+            calc_move_bias();
+            return true;
+        }
+        M()->n_modified = 0;
+        M()->n_assigned = 0;
+        return false;
+    }
+    // CTCBScaffoldRegrowthMCMovetype::internal_attempt_move (:663-748)
+    LDO_HDN bool move_ctcb_scaffold(const MoveDef& md) {
+        cp_reset();
+        ct_select_indices(md);
+        if (sys.S()->status != LDO_OK) return false;
+#pragma unroll 1
+        for (int k = 0; k < C()->n_sel; k++) C()->in_sel[C()->sel_scaf[k]] = 1;
+        M()->scaf_dir[0] = (int8_t)dir;
+        cp_find_growthpoints_endpoints(C()->sel_scaf, C()->n_sel, 0);
+        cp_save_initial();
+        bool whole = sys.SC().cyclic != 0 && C()->n_sel == sys.S()->chain_len[0];
+        if (!whole) cp_remove_active_endpoint(C()->sel_scaf[0]);
+        DD bias = dd_from(1.0), new_bias = dd_from(1.0);
+        for (int pass = 0; pass < 2; pass++) {
+            bool regrow_old = pass == 1;
+            if (regrow_old) {
+                ctcb_setup_regrow_old(bias, new_bias);
+                if (!whole) cp_remove_active_endpoint(C()->sel_scaf[0]);
+            }
+            ctcb_unassign(C()->sel_scaf + 1, C()->n_sel - 1, true);
+            if (M()->gp_stem[C()->sel_scaf[0]] >= 0) {
+                int sp = 0;
+                ctcb_grow_staple_from(C()->sel_scaf[0], regrow_old, bias, sp);
+                ctcb_run_stack(regrow_old, bias, sp, 0);
+                if (M()->rejected && !regrow_old) return false;
+            }
+            ctcb_grow_list(C()->sel_scaf, C()->n_sel, regrow_old, bias);
+            if (!regrow_old) {
+                if (M()->rejected) return false;
+                update_move_params();
+                bias = dd_mul(bias, exp(-calc_move_bias()));
+            }
+        }
+        return ctcb_finish(new_bias, bias);
+    }
+    // CTCBJumpScaffoldRegrowthMCMovetype::internal_attempt_move (:872-966)
+    LDO_HDN bool move_ctcb_jump_scaffold(const MoveDef& md) {
+        SysState<K>* s = sys.S();
+        cp_reset();
+        int n_stems = 0;
+        int n_segs = ct_select_noncontig_segs(md, n_stems);
+        if (s->status != LDO_OK) return false;
+        rg_register_jump_constraints(n_segs, n_stems);
+        int first = C()->seg_dom[0];
+        cp_remove_active_endpoint(first);
+        DD bias = dd_from(1.0), new_bias = dd_from(1.0);
+        for (int pass = 0; pass < 2; pass++) {
+            bool regrow_old = pass == 1;
+            if (regrow_old) {
+                ctcb_setup_regrow_old(bias, new_bias);
+                cp_remove_active_endpoint(first);
+            }
+            ctcb_unassign(M()->regrow + 1, M()->n_regrow - 1, false);
+            if (M()->gp_stem[first] >= 0) {
+                int sp = 0;
+                ctcb_grow_staple_from(first, regrow_old, bias, sp);
+                ctcb_run_stack(regrow_old, bias, sp, 0);
+                if (M()->rejected) return false;
+            }
+            ctcb_grow_list(C()->seg_dom + C()->seg_start[0], C()->seg_start[1] - C()->seg_start[0], regrow_old, bias);
+            if (M()->rejected) return false;
+#pragma unroll 1
+            for (int k = 0; k < n_stems; k++) {
+                int stem = C()->stems[k];
+                // set_first_seg_domain (:973-983)
+                int d_old = M()->stem_gp[stem];
+                if (!cp_walks_remain(stem, rec_pos(s->dom[d_old]))) {
+                    M()->rejected = 1;
+                    return false;
+                }
+                double de = set_growth_point(stem, d_old);
+                bias = dd_mul(bias, exp(-de));
+                if (M()->rejected) return false;
+                for (int q = 0; q < 2; q++) {
+                    int sg = 1 + 2 * k + q;
+                    int a = C()->seg_start[sg], b = C()->seg_start[sg + 1];
+                    // paired segment with the stem prepended (:905-907); segment q == 0 already carries it
+                    short tmp[2];
+                    const short* list = C()->seg_dom + a;
+                    int n = b - a;
+                    if (n == 0 || C()->seg_dom[a] != stem) {
+                        // build [stem] + seg in the scratch tail of seg_dom
+                        short* buf = C()->seg_dom + 2 * K::D + 1 - (n + 1);
+                        buf[0] = (short)stem;
+                        for (int t = 0; t < n; t++) buf[1 + t] = C()->seg_dom[a + t];
+                        list = buf;
+                        n = n + 1;
+                    }
+                    (void)tmp;
+                    ctcb_grow_list(list, n, regrow_old, bias);
+                    if (M()->rejected) return false;
+                }
+            }
+            if (!regrow_old) {
+                update_move_params();
+                bias = dd_mul(bias, exp(-calc_move_bias()));
+            }
+        }
+        return ctcb_finish(new_bias, bias);
     }
 
     // ---- one Monte Carlo step (simulation.cpp:568-596, 655-665) ----
@@ -2390,6 +2695,8 @@ struct Engine {
         case MT_MET_STAPLE_EXCHANGE: accepted = move_staple_exchange(md); break;
         case MT_MET_STAPLE_REGROWTH: accepted = move_met_staple_regrowth(); break;
         case MT_CB_STAPLE_REGROWTH: accepted = move_cb_staple_regrowth(); break;
+        case MT_CTCB_SCAFFOLD_REGROWTH: accepted = move_ctcb_scaffold(md); break;
+        case MT_CTCB_JUMP_SCAFFOLD_REGROWTH: accepted = move_ctcb_jump_scaffold(md); break;
         case MT_CTRG_SCAFFOLD_REGROWTH: accepted = move_ctrg_scaffold(md); break;
         case MT_CTRG_JUMP_SCAFFOLD_REGROWTH: accepted = move_ctrg_jump_scaffold(md); break;
         default: sys.fail(LDO_ERR_INTERNAL, 100 + md.type); break;

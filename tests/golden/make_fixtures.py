@@ -5,6 +5,8 @@ Run in the build container only (needs /root/reference and oracle/_ref):
 
 inputs/            the reference's example systems / movesets / order-parameter / bias / windows files
                    (data, re-serialised), so that nothing at test time reads /root/reference
+inputs/moveset_ctcb.json  hand-written (not from the reference): the standard moveset with the two CTRG scaffold moves
+                   replaced by CTCBScaffoldRegrowth / CTCBJumpScaffoldRegrowth, same schema as examples/moveset_standard.json
 replay_*.npz       value-level RNG tapes recorded from the UNMODIFIED reference (oracle/_ref) with the
                    lattice state, counters and energy after every chunk of MC steps
 energies.json      energies / counters / enthalpy-entropy split / pair-energy tables of reference systems
@@ -153,4 +155,8 @@ if __name__ == "__main__":
                   chunk=8, n_chunks=5)
     record_replay("snodin_unbound_335K", opts("snodin_unbound.json", "moveset_standard.json", temp=335), seed=5,
                   chunk=50, n_chunks=6)
+    record_replay("snodin_assembled_ctcb_332K", opts("snodin_assembled.json", "moveset_ctcb.json", temp=332), seed=13,
+                  chunk=50, n_chunks=8)
+    record_replay("snodin_unbound_ctcb_334K", opts("snodin_unbound.json", "moveset_ctcb.json", temp=334), seed=17,
+                  chunk=60, n_chunks=6)
     enumeration_fixture()

@@ -14,7 +14,8 @@ from latticednaorigami_b200.binding import Simulation
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("name", ["four_unbound_340K", "snodin_assembled_330K", "snodin_unbound_335K"])
+@pytest.mark.parametrize("name", ["four_unbound_340K", "snodin_assembled_330K", "snodin_unbound_335K",
+                                  "snodin_assembled_ctcb_332K", "snodin_unbound_ctcb_334K"])
 def test_replay_fixture_bit_exact(tmp_path, name):
     fx = np.load(os.path.join(GOLDEN, f"replay_{name}.npz"))
     sim = Simulation(write_inp(str(tmp_path / "r.inp"), options_from_fixture(fx)), 5, 0)
@@ -41,8 +42,9 @@ def test_live_replay_against_oracle(oracle, tmp_path):
     cases = [("snodin_assembled.json", 330, 201, 120, {}), ("snodin_unbound.json", 335, 202, 600, {}),
              ("snodin_unbound.json", 345, 203, 600, {}),
              ("four_unbound.json", 330, 204, 2000, {"movetype_file": None, "max_total_staples": 2, "max_type_staples": 2})]
+    cases += [("snodin_assembled.json", 336, 205, 800, {"ctcb": True}), ("snodin_unbound.json", 333, 206, 1200, {"ctcb": True})]
     for system, temp, seed, steps, extra in cases:
-        opts = make_options(system, temp=temp)
+        opts = make_options(system, "moveset_ctcb.json" if extra.get("ctcb") else "moveset_standard.json", temp=temp)
         if "movetype_file" in extra:
             opts = make_options(system, "moveset_four.json", temp=temp, max_total_staples=2, max_type_staples=2)
         r = oracle.RefSystem(opts)

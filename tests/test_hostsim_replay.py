@@ -11,7 +11,8 @@ from conftest import GOLDEN, make_options, options_from_fixture, replay_fixture_
 from latticednaorigami_b200.binding import Simulation
 
 
-@pytest.mark.parametrize("name", ["four_unbound_340K", "snodin_assembled_330K", "snodin_unbound_335K"])
+@pytest.mark.parametrize("name", ["four_unbound_340K", "snodin_assembled_330K", "snodin_unbound_335K",
+                                  "snodin_assembled_ctcb_332K", "snodin_unbound_ctcb_334K"])
 def test_replay_fixture(hostsim_lib, tmp_path, name):
     fx = np.load(os.path.join(GOLDEN, f"replay_{name}.npz"))
     inp = write_inp(str(tmp_path / "r.inp"), options_from_fixture(fx))
@@ -21,8 +22,10 @@ def test_replay_fixture(hostsim_lib, tmp_path, name):
 
 def test_live_replay_against_oracle(hostsim_lib, oracle, tmp_path):
     """Fresh seeds each run: record from the reference, replay through the device logic."""
-    for system, temp, seed, steps in [("snodin_assembled.json", 330, 101, 60), ("snodin_unbound.json", 340, 102, 400)]:
-        opts = make_options(system, temp=temp)
+    for system, temp, seed, steps, moveset in [("snodin_assembled.json", 330, 101, 60, "moveset_standard.json"),
+                                               ("snodin_unbound.json", 340, 102, 400, "moveset_standard.json"),
+                                               ("snodin_assembled.json", 338, 103, 400, "moveset_ctcb.json")]:
+        opts = make_options(system, moveset, temp=temp)
         r = oracle.RefSystem(opts)
         r.seed(seed)
         sim = Simulation(write_inp(str(tmp_path / f"{seed}.inp"), opts), 1, 0, lib_path=hostsim_lib)

@@ -5,7 +5,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import assert_state_equal, has_cuda, make_options, write_inp
+from conftest import INPUTS, assert_state_equal, has_cuda, make_options, write_inp
 from latticednaorigami_b200.binding import Simulation
 from synthetic import UNIFORM_OPTIONS, write_raster_system
 
@@ -56,6 +56,26 @@ def test_large_raster_hostsim(hostsim_lib, oracle, tmp_path):
     """168-domain scaffold, 84 staple types (config 5): large capacities, state kept in place (HBM/L2)."""
     opts = _options(tmp_path, 12, 14, temp=295, max_total=168, staple_M=1e-3, centering_freq=50, constraint_check_freq=40)
     _replay(oracle, opts, tmp_path, hostsim_lib, seed=43, steps=400)
+
+
+def test_ctcb_moves_on_synthetic_systems_hostsim(hostsim_lib, oracle, tmp_path):
+    """CTCB scaffold regrowth (contiguous and jump) on ThreeQuarterTurn, cyclic and large (in-place) systems."""
+    ctcb = os.path.join(INPUTS, "moveset_ctcb.json")
+    _replay(oracle, _options(tmp_path, 3, 4, temp=300, max_total=8, movetype_file=ctcb), tmp_path, hostsim_lib, seed=51, steps=1200)
+    _replay(oracle, _options(tmp_path, 3, 4, temp=300, max_total=8, cyclic=True, movetype_file=ctcb), tmp_path, hostsim_lib,
+            seed=52, steps=1200)
+    _replay(oracle, _options(tmp_path, 12, 14, temp=295, max_total=168, staple_M=1e-3, movetype_file=ctcb), tmp_path,
+            hostsim_lib, seed=53, steps=200)
+
+
+@pytest.mark.gpu
+def test_ctcb_moves_on_synthetic_systems_gpu(oracle, tmp_path):
+    ctcb = os.path.join(INPUTS, "moveset_ctcb.json")
+    _replay(oracle, _options(tmp_path, 3, 4, temp=300, max_total=8, movetype_file=ctcb), tmp_path, None, seed=54, steps=2000)
+    _replay(oracle, _options(tmp_path, 3, 4, temp=300, max_total=8, cyclic=True, movetype_file=ctcb), tmp_path, None,
+            seed=55, steps=2000)
+    _replay(oracle, _options(tmp_path, 12, 14, temp=295, max_total=168, staple_M=1e-3, movetype_file=ctcb), tmp_path,
+            None, seed=56, steps=400)
 
 
 @pytest.mark.gpu
