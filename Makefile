@@ -31,7 +31,14 @@ tests/hostsim/libldo_hostsim.so: $(CSRC)/ldo_engine.cu $(HOST_SRCS) $(HDRS)
 	mkdir -p tests/hostsim
 	$(HOSTCXX) $(CXXFLAGS) -O1 -g -DLDO_HOSTSIM -shared -o $@ -x c++ $(CSRC)/ldo_engine.cu $(HOST_SRCS)
 
+# A/B variants for profiling: make variant NAME=generic DEFS="-DLDO_GENERIC_ACCESS" -> ab/lib_generic.so
+# (selected at run time with LDO_B200_LIB=ab/lib_generic.so)
+variant:
+	mkdir -p ab
+	$(NVCC) $(NVFLAGS) $(DEFS) -c $(CSRC)/ldo_engine.cu -o ab/ldo_engine_$(NAME).o
+	$(NVCC) -shared -ccbin $(HOSTCXX) -o ab/lib_$(NAME).so ab/ldo_engine_$(NAME).o $(OUT)/build/ldo_host.o $(OUT)/build/ldo_sim.o -lcudart
+
 clean:
 	rm -rf $(OUT)/build $(OUT)/libldo_b200.so $(OUT)/latticeDNAOrigami_b200 tests/hostsim/libldo_hostsim.so
 
-.PHONY: all hostsim clean
+.PHONY: all hostsim clean variant

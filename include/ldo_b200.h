@@ -226,6 +226,9 @@ int ldo_get_staple_counts(ldo_engine* e, int* out);
 int ldo_get_order_params(ldo_engine* e, int* out);
 /* [n_replicas][n_movetypes] attempts / accepts (MovetypeTracking, movetypes.hpp:49-52; .moves). */
 int ldo_get_move_stats(ldo_engine* e, long long* attempts, long long* accepts);
+/* Diagnostics (no reference counterpart): [n_replicas][3] = start ns, end ns (device global timer) and SM id
+ * of every replica's warp in the last ldo_run launch; used by profiles/ to measure load imbalance. */
+int ldo_get_run_timing(ldo_engine* e, long long* out);
 /* Full energy of every replica recomputed from scratch on device without touching the state
  * (the same pass check_all_constraints relies on): [n_replicas] energies, [n_replicas] stacked pairs. */
 int ldo_recompute_energies(ldo_engine* e, double* energy, int* stacked_pairs);

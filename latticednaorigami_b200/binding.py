@@ -17,7 +17,7 @@ ENGINE_SYMBOLS = [
     "ldo_seed", "ldo_seed_subsequences", "ldo_attach_tape", "ldo_tape_position", "ldo_set_state", "ldo_state_capacity",
     "ldo_get_state", "ldo_run", "ldo_get_status", "ldo_run_async", "ldo_synchronize", "ldo_stream",
     "ldo_get_energies", "ldo_get_counters", "ldo_get_staple_counts", "ldo_get_order_params",
-    "ldo_get_move_stats", "ldo_recompute_energies", "ldo_check_all_constraints", "ldo_center",
+    "ldo_get_move_stats", "ldo_get_run_timing", "ldo_recompute_energies", "ldo_check_all_constraints", "ldo_center",
     "ldo_set_exchange_ladder", "ldo_exchange_collect", "ldo_exchange_pt", "ldo_exchange_buffers",
     "ldo_exchange_windows", "ldo_launch_count", "ldo_state_bytes", "ldo_checkpoint_size", "ldo_checkpoint_save", "ldo_checkpoint_load",
 ]
@@ -88,6 +88,7 @@ def load(path=None):
         "ldo_get_staple_counts": (i, [vp, vp]),
         "ldo_get_order_params": (i, [vp, vp]),
         "ldo_get_move_stats": (i, [vp, vp, vp]),
+        "ldo_get_run_timing": (i, [vp, vp]),
         "ldo_recompute_energies": (i, [vp, vp, vp]),
         "ldo_check_all_constraints": (i, [vp]),
         "ldo_center": (i, [vp, i]),
@@ -249,6 +250,12 @@ class Engine:
     def order_params(self):
         out = np.zeros((self.R, max(self.n_ops, 1)), dtype=np.int32)
         self._check(self.L.ldo_get_order_params(self.h, _ptr(out)))
+        return out
+
+    def run_timing(self):
+        """[R][3]: start ns, end ns, SM id of every replica's warp in the last run launch (diagnostics)."""
+        out = np.zeros((self.R, 3), dtype=np.int64)
+        self._check(self.L.ldo_get_run_timing(self.h, _ptr(out)))
         return out
 
     def move_stats(self):

@@ -179,17 +179,22 @@ struct SysConst {
 __constant__ SysConst ldo_c_sc;
 #endif
 
-// Generic pointers that are known to address shared memory (staged replicas) let the compiler emit
-// LDS/STS instead of generic loads and stores
-#if defined(__CUDA_ARCH__)
-#if defined(LDO_ENABLE_ASSUME_SHARED)
-#define LDO_ASSUME_SHARED(K, ptr) do { if (K::STAGED) __builtin_assume(__isShared(ptr)); } while (0)
-#else
-#define LDO_ASSUME_SHARED(K, ptr) ((void)0)
+// Staged replicas live in the dynamic shared memory of the block, one WarpSmem block per warp (ldo_engine.cu).
+// The accessors of System / Engine form their addresses from the shared-memory symbol itself, so that the
+// compiler emits LDS/STS with 32-bit addresses instead of generic loads and stores (which need a 64-bit
+// address and a descriptor in uniform registers each time). SmemLayout<K> (byte offsets inside one warp's
+// block) is defined next to WarpSmem.
+#if defined(__CUDACC__) && !defined(LDO_HOSTSIM)
+extern __shared__ __align__(16) unsigned char ldo_smem_raw[];
 #endif
+#if defined(__CUDA_ARCH__) && !defined(LDO_GENERIC_ACCESS)
+#define LDO_SMEM_PTR(K, T, member, fallback) \
+    (K::STAGED ? reinterpret_cast<T*>(ldo_smem_raw + (threadIdx.x >> 5) * SmemLayout<K>::stride + SmemLayout<K>::member) : (fallback))
 #else
-#define LDO_ASSUME_SHARED(K, ptr) ((void)0)
+#define LDO_SMEM_PTR(K, T, member, fallback) (fallback)
 #endif
+template <class K>
+struct SmemLayout;
 
 // Per-temperature energy tables (origami_potential.cpp:1057-1221); shared by replicas at that T
 struct TempTables {
@@ -282,9 +287,7 @@ struct System {
     DomRec orec;
 
     LDO_HD SysState<K>* S() const {
-        SysState<K>* p = s;
-        LDO_ASSUME_SHARED(K, p);
-        return p;
+        return LDO_SMEM_PTR(K, SysState<K>, state, s);
     }
     LDO_HD const SysConst& SC() const {
 #if defined(__CUDA_ARCH__)

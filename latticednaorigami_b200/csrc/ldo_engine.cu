@@ -152,6 +152,7 @@ struct DevPtrs {
     const TempTables* tables;
     double* grid_vals; // [R][LDO_GRID_CAP]
     long long* grid_visits; // [R][LDO_GRID_CAP]
+    long long* run_timing; // [R][3] diagnostics of the last run launch: start ns, end ns (globaltimer), SM id
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -430,6 +431,19 @@ struct __align__(16) WarpSmem {
     Engine<K> eng;
 };
 
+namespace ldo {
+template <class K>
+struct SmemLayout {
+    static const unsigned stride = sizeof(WarpSmem<K>);
+    static const unsigned state = offsetof(WarpSmem<K>, st);
+    static const unsigned scratch = offsetof(WarpSmem<K>, ms);
+    static const unsigned engine = offsetof(WarpSmem<K>, eng);
+    static const unsigned rng = offsetof(WarpSmem<K>, aux) + offsetof(RepAux, rng);
+    static const unsigned bias = offsetof(WarpSmem<K>, aux) + offsetof(RepAux, bs);
+    static const unsigned stats = offsetof(WarpSmem<K>, aux) + offsetof(RepAux, stats);
+};
+} // namespace ldo
+
 // Staged: the replica state is copied HBM -> shared memory (coalesced 128-bit), all moves run on
 // shared memory, and the state is copied back once at the end.
 // Launch shape of the staged kernel: LDO_BLOCK_WARPS warps per block, at least LDO_MIN_BLOCKS blocks per
@@ -442,17 +456,27 @@ struct __align__(16) WarpSmem {
 #endif
 template <class K>
 __global__ void __launch_bounds__(32 * LDO_BLOCK_WARPS, LDO_MIN_BLOCKS) k_exec_staged(DevPtrs<K> P, OpArgs a, int warps_per_block) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    WarpSmem<K>* ws = reinterpret_cast<WarpSmem<K>*>(smem_raw);
+    WarpSmem<K>* ws = reinterpret_cast<WarpSmem<K>*>(ldo_smem_raw);
     int warp = threadIdx.x >> 5;
     int r = blockIdx.x * warps_per_block + warp;
     if (r >= a.n_replicas) return;
     if (a.only_replica >= 0 && r != a.only_replica) return;
     WarpSmem<K>& w = ws[warp];
+    long long t0 = 0;
+    if (a.op == OP_RUN) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
     warp_copy16(&w.st, &P.states[r]);
     warp_copy16(&w.aux, &P.aux[r]);
     rep_execute<K>(&w.eng, &w.st, &w.ms, &w.aux, P, a, r);
     __syncwarp();
+    if (a.op == OP_RUN && (threadIdx.x & 31) == 0) {
+        long long t1;
+        unsigned smid;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        P.run_timing[3 * r] = t0;
+        P.run_timing[3 * r + 1] = t1;
+        P.run_timing[3 * r + 2] = smid;
+    }
     if (a.op != OP_OBSERVE && a.op != OP_RECOMPUTE) {
         warp_copy16(&P.states[r], &w.st);
         warp_copy16(&P.aux[r], &w.aux);
@@ -738,6 +762,7 @@ struct EngineBase {
     virtual int set_tables(int n_temps, int n_ident, const double* temps, const double* e, const double* h, const double* s, const double* init) = 0;
     virtual int push_shared() = 0;
     virtual int exec(OpArgs& a, bool sync) = 0;
+    virtual long long* run_timing_ptr() = 0;
     virtual int get_aux(int first, int count, RepAux* out) = 0;
     virtual int put_aux(int first, int count, const RepAux* in) = 0;
     virtual int get_state_raw(int replica, std::vector<unsigned char>& blob) = 0;
@@ -807,6 +832,7 @@ struct EngineImpl: EngineBase {
         dev_free(d_table_data);
         dev_free(P.grid_vals);
         dev_free(P.grid_visits);
+        dev_free(P.run_timing);
         dev_free(d_recompute_tmp);
         dev_free(d_cfg);
         dev_free(d_energies);
@@ -879,6 +905,7 @@ struct EngineImpl: EngineBase {
         if (dev_malloc((void**)&d_staples, sizeof(int) * (nst > 0 ? nst : 1) * R)) return fail(dev_err());
         if (dev_malloc((void**)&d_dependent, sizeof(double) * (3 + nst) * R)) return fail(dev_err());
         if (dev_malloc((void**)&d_recomputed, sizeof(double) * R)) return fail(dev_err());
+        if (dev_malloc((void**)&P.run_timing, sizeof(long long) * 3 * R)) return fail(dev_err());
         if (dev_malloc((void**)&d_recomputed_stacked, sizeof(int) * R)) return fail(dev_err());
         if (dev_malloc((void**)&d_status, sizeof(int) * 2 * R)) return fail(dev_err());
         return 0;
@@ -1004,6 +1031,7 @@ struct EngineImpl: EngineBase {
     }
 
     // Opaque checkpoint blobs: state + per-replica auxiliary data (RNG, control, biases, statistics)
+    long long* run_timing_ptr() override { return P.run_timing; }
     size_t blob_size() override { return sizeof(SysState<K>) + sizeof(RepAux); }
     size_t state_bytes() override { return sizeof(SysState<K>); }
     int get_blobs(int first, int count, void* host) override {
@@ -1748,6 +1776,12 @@ int ldo_get_move_stats(ldo_engine* e, long long* attempts, long long* accepts) {
             accepts[(size_t)r * n + i] = aux[r].stats.accepts[i];
         }
     }
+    return 0;
+}
+
+int ldo_get_run_timing(ldo_engine* e, long long* out) {
+    EngineBase* b = e->b;
+    if (dev_d2h(out, b->run_timing_ptr(), sizeof(long long) * 3 * b->R, b->stream)) return b->fail(dev_err());
     return 0;
 }
 

@@ -429,25 +429,17 @@ struct Engine {
 
     // ---- accessors: shared-memory hints and constant-memory copies on the device ----
     LDO_HD MoveScratch<K>* M() const {
-        MoveScratch<K>* p = m;
-        LDO_ASSUME_SHARED(K, p);
-        return p;
+        return LDO_SMEM_PTR(K, MoveScratch<K>, scratch, m);
     }
     LDO_HD ColdScratch<K>* C() const { return mc; }
     LDO_HD Rng* RNG() const {
-        Rng* p = rng;
-        LDO_ASSUME_SHARED(K, p);
-        return p;
+        return LDO_SMEM_PTR(K, Rng, rng, rng);
     }
     LDO_HD BiasState* BS() const {
-        BiasState* p = bs;
-        LDO_ASSUME_SHARED(K, p);
-        return p;
+        return LDO_SMEM_PTR(K, BiasState, bias, bs);
     }
     LDO_HD MoveStats* STATS() const {
-        MoveStats* p = stats;
-        LDO_ASSUME_SHARED(K, p);
-        return p;
+        return LDO_SMEM_PTR(K, MoveStats, stats, stats);
     }
     LDO_HD const MoveSet& MS() const {
 #if defined(__CUDA_ARCH__)
