@@ -282,9 +282,24 @@ struct System {
     const SysConst* sc;
     TempTables tt;
 
-    // Overlay (read-only candidate evaluation): domain od placed at orec, bound to oj (or -1)
-    int od, oj;
-    DomRec orec;
+    // Overlay (read-only candidate evaluation): domain od placed at rec, bound to oj (or -1). Staged
+    // replicas keep one overlay per lane in shared memory (lanes evaluate different candidates at the
+    // same time); otherwise it is a member and lanes work on private copies of the System object.
+    struct Overlay { // 12 bytes: 32 lanes * 3 words hit 32 distinct banks
+        short od, oj;
+        struct {
+            short x, y, z;
+            int8_t ore;
+            uint8_t state;
+        } rec;
+    };
+    mutable Overlay ov_;
+    LDO_HD Overlay* OV() const {
+#if defined(__CUDA_ARCH__) && !defined(LDO_GENERIC_ACCESS)
+        if (K::STAGED) return LDO_SMEM_PTR(K, Overlay, overlay, &ov_) + (threadIdx.x & 31);
+#endif
+        return &ov_;
+    }
 
     LDO_HD SysState<K>* S() const {
         return LDO_SMEM_PTR(K, SysState<K>, state, s);
@@ -301,8 +316,8 @@ struct System {
         s = s_;
         sc = sc_;
         tt = tt_;
-        od = -1;
-        oj = -1;
+        OV()->od = -1;
+        OV()->oj = -1;
     }
 
     LDO_HDN void fail(int code, int detail = 0) {
@@ -314,21 +329,25 @@ struct System {
 
     // ---- accessors (overlay aware) ----
     LDO_HD V3 pos(int d) const {
-        if (d == od) return v3(orec.x, orec.y, orec.z);
+        const Overlay* o = OV();
+        if (d == o->od) return v3(o->rec.x, o->rec.y, o->rec.z);
         const DomRec& r = S()->dom[d];
         return v3(r.x, r.y, r.z);
     }
     LDO_HD V3 ore(int d) const {
-        if (d == od) return ore_vec(orec.ore);
+        const Overlay* o = OV();
+        if (d == o->od) return ore_vec(o->rec.ore);
         return ore_vec(S()->dom[d].ore);
     }
     LDO_HD int state(int d) const {
-        if (d == od || d == oj) return orec.state;
+        const Overlay* o = OV();
+        if (d == o->od || d == o->oj) return o->rec.state;
         return S()->dom[d].state;
     }
     LDO_HD int bound(int d) const {
-        if (d == od) return oj;
-        if (d == oj) return od;
+        const Overlay* o = OV();
+        if (d == o->od) return o->oj;
+        if (d == o->oj) return o->od;
         return S()->bound[d];
     }
     LDO_HD int chain(int d) const { return S()->dchain[d]; }
@@ -1045,17 +1064,19 @@ struct System {
         }
         *partner = j;
         bool comp = S()->ident[d] == -S()->ident[j];
-        od = d;
-        oj = j;
-        orec.x = (short)p.x;
-        orec.y = (short)p.y;
-        orec.z = (short)p.z;
-        orec.ore = (int8_t)o;
-        orec.state = comp ? ST_BOUND : ST_MISBOUND;
-        *new_state = orec.state;
+        Overlay* ov = OV();
+        ov->od = (short)d;
+        ov->oj = (short)j;
+        ov->rec.x = (short)p.x;
+        ov->rec.y = (short)p.y;
+        ov->rec.z = (short)p.z;
+        ov->rec.ore = (int8_t)o;
+        ov->rec.state = comp ? ST_BOUND : ST_MISBOUND;
+        *new_state = ov->rec.state;
         dc = bind_domain(d);
-        od = -1;
-        oj = -1;
+        ov = OV();
+        ov->od = -1;
+        ov->oj = -1;
         if (SC().apply_mean_field_cor && !dc.violated && comp) {
             // origami_system.cpp:858-868 (counter already incremented in the reference at this point)
             int nfb = S()->num_fully_bound_pairs + 1;

@@ -93,9 +93,11 @@ struct __attribute__((aligned(16))) RepAux {
     Rng rng;
     Control ctl;
     BiasState bs;
-    MoveStats stats;
     long long step;
+    // not staged to shared memory (touched twice per move): everything from here on stays in HBM/L2
+    __attribute__((aligned(16))) MoveStats stats;
 };
+#define LDO_AUX_HOT_BYTES offsetof(RepAux, stats)
 
 struct Shared {
     SysConst sc;
@@ -171,7 +173,7 @@ LDO_HD void rep_init_engine(Engine<K>& eng, SysState<K>* st, MoveScratch<K>* ms,
     eng.bs = &aux->bs;
     eng.grid_vals = P.grid_vals ? P.grid_vals + (size_t)aux->bs.grid_slot * LDO_GRID_CAP : nullptr;
     eng.ctl = aux->ctl;
-    eng.stats = &aux->stats;
+    eng.stats = &P.aux[r].stats;
 }
 
 template <class K>
@@ -426,9 +428,10 @@ __device__ inline void warp_copy16(T* dst, const T* src) {
 template <class K>
 struct __align__(16) WarpSmem {
     SysState<K> st;
-    RepAux aux;
+    __align__(16) unsigned char aux[LDO_AUX_HOT_BYTES]; // RepAux up to (not including) stats
     MoveScratch<K> ms;
     Engine<K> eng;
+    typename System<K>::Overlay overlay[32]; // one hypothetical placement per lane
 };
 
 namespace ldo {
@@ -440,9 +443,17 @@ struct SmemLayout {
     static const unsigned engine = offsetof(WarpSmem<K>, eng);
     static const unsigned rng = offsetof(WarpSmem<K>, aux) + offsetof(RepAux, rng);
     static const unsigned bias = offsetof(WarpSmem<K>, aux) + offsetof(RepAux, bs);
-    static const unsigned stats = offsetof(WarpSmem<K>, aux) + offsetof(RepAux, stats);
+    static const unsigned overlay = offsetof(WarpSmem<K>, overlay);
 };
 } // namespace ldo
+
+__device__ inline void warp_copy_bytes16(void* dst, const void* src, int bytes) {
+    const uint4* s = reinterpret_cast<const uint4*>(src);
+    uint4* d = reinterpret_cast<uint4*>(dst);
+    for (int i = threadIdx.x & 31; i < bytes / 16; i += 32) d[i] = s[i];
+    __syncwarp();
+}
+static_assert(LDO_AUX_HOT_BYTES % 16 == 0, "staged part of RepAux must be a multiple of 16 bytes");
 
 // Staged: the replica state is copied HBM -> shared memory (coalesced 128-bit), all moves run on
 // shared memory, and the state is copied back once at the end.
@@ -465,8 +476,9 @@ __global__ void __launch_bounds__(32 * LDO_BLOCK_WARPS, LDO_MIN_BLOCKS) k_exec_s
     long long t0 = 0;
     if (a.op == OP_RUN) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
     warp_copy16(&w.st, &P.states[r]);
-    warp_copy16(&w.aux, &P.aux[r]);
-    rep_execute<K>(&w.eng, &w.st, &w.ms, &w.aux, P, a, r);
+    RepAux* aux = reinterpret_cast<RepAux*>(w.aux);
+    warp_copy_bytes16(w.aux, &P.aux[r], LDO_AUX_HOT_BYTES);
+    rep_execute<K>(&w.eng, &w.st, &w.ms, aux, P, a, r);
     __syncwarp();
     if (a.op == OP_RUN && (threadIdx.x & 31) == 0) {
         long long t1;
@@ -479,7 +491,7 @@ __global__ void __launch_bounds__(32 * LDO_BLOCK_WARPS, LDO_MIN_BLOCKS) k_exec_s
     }
     if (a.op != OP_OBSERVE && a.op != OP_RECOMPUTE) {
         warp_copy16(&P.states[r], &w.st);
-        warp_copy16(&P.aux[r], &w.aux);
+        warp_copy_bytes16(&P.aux[r], w.aux, LDO_AUX_HOT_BYTES);
     }
 }
 

@@ -318,7 +318,6 @@ struct MoveScratch {
     short assigned[A];
     int n_assigned;
     int added_chain; // chain slot or -1 (at most one chain is added per move)
-    DomRec prev[K::D]; // m_prev_pos / m_prev_ore
     int rejected;
     double modifier;
 
@@ -354,8 +353,8 @@ struct MoveScratch {
 
     // lane-parallel candidate evaluation results (6 neighbour sites)
     double site_w[8];
-    int site_o[8];
-    int site_kind[8];
+    int8_t site_o[8];
+    int8_t site_kind[8];
 };
 
 // Cold part: selection / topology set-up and the saved configurations, touched a few times per move;
@@ -364,6 +363,7 @@ template <class K>
 struct ColdScratch {
     static const int E = K::E;
     static const int S = K::SEG;
+    DomRec prev[K::D]; // m_prev_pos / m_prev_ore (written once per modified domain, read on rejection)
     DomRec oldc[K::D]; // m_old_pos / m_old_ore
     DomRec newc[K::D]; // m_new_pos / m_new_ore
     short sel_scaf[K::D + 1];
@@ -438,9 +438,7 @@ struct Engine {
     LDO_HD BiasState* BS() const {
         return LDO_SMEM_PTR(K, BiasState, bias, bs);
     }
-    LDO_HD MoveStats* STATS() const {
-        return LDO_SMEM_PTR(K, MoveStats, stats, stats);
-    }
+    LDO_HD MoveStats* STATS() const { return stats; } // global memory: touched twice per move
     LDO_HD const MoveSet& MS() const {
 #if defined(__CUDA_ARCH__)
         return ldo_c_ms;
@@ -454,6 +452,16 @@ struct Engine {
 #else
         return *ob;
 #endif
+    }
+
+    // Candidate evaluation on this lane: the overlay is per lane (shared memory) for staged replicas;
+    // otherwise the engine object is shared by the warp and the lane works on a private copy
+    LDO_HD DeltaConfig eval_place_lane(int dom, V3 p, int o, int* new_state, int* partner) {
+#if defined(__CUDA_ARCH__) && !defined(LDO_GENERIC_ACCESS)
+        if (K::STAGED) return sys.eval_place(dom, p, o, new_state, partner);
+#endif
+        System<K> view = sys;
+        return view.eval_place(dom, p, o, new_state, partner);
     }
 
     // ---- RNG (random_gens.cpp:29-49) ----
@@ -659,7 +667,7 @@ struct Engine {
 #pragma unroll 1
         for (int k = 0; k < M()->n_modified; k++) {
             int dd = M()->modified[k];
-            const DomRec& r = M()->prev[dd];
+            const DomRec& r = C()->prev[dd];
             sys.set_checked_domain_config(dd, rec_pos(r), r.ore);
         }
         sys.S()->constraints_violated = 0;
@@ -830,7 +838,7 @@ struct Engine {
 #pragma unroll 1
         for (int k = 0; k < sys.S()->chain_len[c]; k++) {
             int dd = base + k;
-            M()->prev[dd] = sys.S()->dom[dd];
+            C()->prev[dd] = sys.S()->dom[dd];
             push_modified(dd);
             delta_e += sys.unassign_domain(dd);
         }
@@ -961,15 +969,14 @@ struct Engine {
                 int oj = sys.S()->dom[j].ore;
                 o = oj < 6 ? (oj ^ 1) : oj;
                 int ns, partner;
-                System<K> view = sys; // private overlay per lane
-                DeltaConfig dc = view.eval_place(dom, p, o, &ns, &partner);
+                DeltaConfig dc = eval_place_lane(dom, p, o, &ns, &partner);
                 if (!dc.violated) {
                     kind = 2;
                     w = exp(-dc.e);
                 }
             }
-            M()->site_kind[k] = kind;
-            M()->site_o[k] = o;
+            M()->site_kind[k] = (int8_t)kind;
+            M()->site_o[k] = (int8_t)o;
             M()->site_w[k] = w;
         }
         LDO_SYNCWARP();
@@ -1045,7 +1052,7 @@ struct Engine {
 #pragma unroll 1
         for (int k = 0; k < sys.S()->chain_len[c]; k++) {
             int dd = base + k;
-            M()->prev[dd] = sys.S()->dom[dd];
+            C()->prev[dd] = sys.S()->dom[dd];
             push_modified(dd);
             sys.unassign_domain(dd);
         }
@@ -1093,7 +1100,7 @@ struct Engine {
         {
             int base = sys.chain_base(c);
 #pragma unroll 1
-            for (int k = 0; k < s->chain_len[c]; k++) C()->oldc[base + k] = M()->prev[base + k];
+            for (int k = 0; k < s->chain_len[c]; k++) C()->oldc[base + k] = C()->prev[base + k];
         }
         gi = uniform_int(0, n_bd - 1);
         cb_unassign_domains(c);
@@ -1649,11 +1656,11 @@ struct Engine {
     // unassign_and_save_domains() (rg:67-87)
     LDO_HDN double rg_unassign_and_save_domains() {
         double de = 0;
-        M()->prev[M()->regrow[0]] = sys.S()->dom[M()->regrow[0]];
+        C()->prev[M()->regrow[0]] = sys.S()->dom[M()->regrow[0]];
 #pragma unroll 1
         for (int k = 1; k < M()->n_regrow; k++) {
             int dd = M()->regrow[k];
-            M()->prev[dd] = sys.S()->dom[dd];
+            C()->prev[dd] = sys.S()->dom[dd];
             push_modified(dd);
             de += sys.unassign_domain(dd);
         }
@@ -1732,8 +1739,7 @@ struct Engine {
         else if (sys.S()->dom[j].state == ST_UNBOUND && sys.S()->dom[j].ore < 6) {
             o = sys.S()->dom[j].ore ^ 1;
             int ns, partner;
-            System<K> view = sys; // lane-private overlay (the engine object is shared by the warp)
-            DeltaConfig dc = view.eval_place(dom, r, o, &ns, &partner);
+            DeltaConfig dc = eval_place_lane(dom, r, o, &ns, &partner);
             if (!dc.violated && cp_walks_remain(dom, r, ov)) {
                 bool same_chain = sys.chain(j) == sys.chain(dom);
                 if (same_chain || dom_is_stem || cp_endpoint_reached(dom, r, ov)) {
@@ -2077,7 +2083,7 @@ struct Engine {
                 }
             }
             weight *= avail_cs / M()->c_opens[di - 1];
-            const DomRec& r = M()->prev[d];
+            const DomRec& r = C()->prev[d];
             sys.set_checked_domain_config(d, rec_pos(r), r.ore);
             cp_update_endpoints(d);
             eq_push_erased();
@@ -2267,7 +2273,7 @@ struct Engine {
         // new-configuration weights (setup_for_calc_new_weights, rg:147-153)
         rg_copy_queues_to_wq();
 #pragma unroll 1
-        for (int k = 0; k < M()->n_regrow; k++) C()->oldc[M()->regrow[k]] = M()->prev[M()->regrow[k]];
+        for (int k = 0; k < M()->n_regrow; k++) C()->oldc[M()->regrow[k]] = C()->prev[M()->regrow[k]];
         M()->n_modified = 0;
         rg_unassign_and_save_domains();
         cp_reset_active_endpoints();
@@ -2284,7 +2290,7 @@ struct Engine {
         weight = 1;
         rg_copy_queues_to_wq();
 #pragma unroll 1
-        for (int k = 0; k < M()->n_regrow; k++) C()->newc[M()->regrow[k]] = M()->prev[M()->regrow[k]];
+        for (int k = 0; k < M()->n_regrow; k++) C()->newc[M()->regrow[k]] = C()->prev[M()->regrow[k]];
         M()->n_modified = 0;
         rg_unassign_and_save_domains();
         cp_reset_active_endpoints();
@@ -2295,7 +2301,7 @@ struct Engine {
         double ratio = weight_new / weight * exp(-delta_e);
         if (test_acceptance(ratio)) {
 #pragma unroll 1
-            for (int k = 0; k < M()->n_regrow; k++) M()->prev[M()->regrow[k]] = C()->newc[M()->regrow[k]];
+            for (int k = 0; k < M()->n_regrow; k++) C()->prev[M()->regrow[k]] = C()->newc[M()->regrow[k]];
             reset_origami();
             return true;
         }
@@ -2519,7 +2525,7 @@ struct Engine {
 #pragma unroll 1
         for (int k = 0; k < n_doms; k++) {
             int dd = doms[k];
-            M()->prev[dd] = sys.S()->dom[dd];
+            C()->prev[dd] = sys.S()->dom[dd];
             push_modified(dd);
             sys.unassign_domain(dd);
         }
@@ -2549,7 +2555,7 @@ struct Engine {
         M()->n_modified = 0;
         M()->n_assigned = 0;
 #pragma unroll 1
-        for (int k = 0; k < K::D; k++) C()->oldc[k] = M()->prev[k];
+        for (int k = 0; k < K::D; k++) C()->oldc[k] = C()->prev[k];
         cp_reset_active_endpoints();
     }
     LDO_HDN bool ctcb_finish(DD new_bias, DD bias) {
