@@ -155,6 +155,8 @@ struct DevPtrs {
     double* grid_vals; // [R][LDO_GRID_CAP]
     long long* grid_visits; // [R][LDO_GRID_CAP]
     long long* run_timing; // [R][3] diagnostics of the last run launch: start ns, end ns (globaltimer), SM id
+    int* queue; // work-queue head of the staged kernel (reset before every launch)
+    int* order; // [R] replicas in the order they are handed out by a run launch (most expensive first)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -465,33 +467,89 @@ static_assert(LDO_AUX_HOT_BYTES % 16 == 0, "staged part of RepAux must be a mult
 #ifndef LDO_MIN_BLOCKS
 #define LDO_MIN_BLOCKS 14
 #endif
+// Persistent: the grid is sized to what is resident on the chip and every warp pulls replicas from a
+// queue until it is empty, so that ensembles larger than one wave keep all warp slots busy. Run launches
+// hand replicas out most-expensive-first (k_build_order: cost = duration in the previous run launch), the
+// classic longest-processing-time rule for the tail.
 template <class K>
-__global__ void __launch_bounds__(32 * LDO_BLOCK_WARPS, LDO_MIN_BLOCKS) k_exec_staged(DevPtrs<K> P, OpArgs a, int warps_per_block) {
+__global__ void __launch_bounds__(32 * LDO_BLOCK_WARPS, LDO_MIN_BLOCKS) k_exec_staged(DevPtrs<K> P, OpArgs a, int n_items) {
     WarpSmem<K>* ws = reinterpret_cast<WarpSmem<K>*>(ldo_smem_raw);
     int warp = threadIdx.x >> 5;
-    int r = blockIdx.x * warps_per_block + warp;
-    if (r >= a.n_replicas) return;
-    if (a.only_replica >= 0 && r != a.only_replica) return;
     WarpSmem<K>& w = ws[warp];
-    long long t0 = 0;
-    if (a.op == OP_RUN) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-    warp_copy16(&w.st, &P.states[r]);
     RepAux* aux = reinterpret_cast<RepAux*>(w.aux);
-    warp_copy_bytes16(w.aux, &P.aux[r], LDO_AUX_HOT_BYTES);
-    rep_execute<K>(&w.eng, &w.st, &w.ms, aux, P, a, r);
-    __syncwarp();
-    if (a.op == OP_RUN && (threadIdx.x & 31) == 0) {
-        long long t1;
-        unsigned smid;
-        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-        P.run_timing[3 * r] = t0;
-        P.run_timing[3 * r + 1] = t1;
-        P.run_timing[3 * r + 2] = smid;
+    for (;;) {
+        int idx = 0;
+        if ((threadIdx.x & 31) == 0) idx = atomicAdd(P.queue, 1);
+        idx = __shfl_sync(0xffffffffu, idx, 0);
+        if (idx >= n_items) break;
+        int r = a.only_replica >= 0 ? a.only_replica : (a.op == OP_RUN ? P.order[idx] : idx);
+        long long t0 = 0;
+        if (a.op == OP_RUN) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        warp_copy16(&w.st, &P.states[r]);
+        warp_copy_bytes16(w.aux, &P.aux[r], LDO_AUX_HOT_BYTES);
+        rep_execute<K>(&w.eng, &w.st, &w.ms, aux, P, a, r);
+        __syncwarp();
+        if (a.op != OP_OBSERVE && a.op != OP_RECOMPUTE) {
+            warp_copy16(&P.states[r], &w.st);
+            warp_copy_bytes16(&P.aux[r], w.aux, LDO_AUX_HOT_BYTES);
+        }
+        if (a.op == OP_RUN && (threadIdx.x & 31) == 0) {
+            long long t1;
+            unsigned smid;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            P.run_timing[3 * r] = t0;
+            P.run_timing[3 * r + 1] = t1;
+            P.run_timing[3 * r + 2] = smid;
+        }
+        __syncwarp();
     }
-    if (a.op != OP_OBSERVE && a.op != OP_RECOMPUTE) {
-        warp_copy16(&P.states[r], &w.st);
-        warp_copy_bytes16(&P.aux[r], w.aux, LDO_AUX_HOT_BYTES);
+}
+
+// Order in which the next run launch hands out replicas: descending duration of the previous run launch
+// (counting sort over 256 cost buckets, one block). All zeros (first launch) gives the identity.
+__global__ void __launch_bounds__(1024) k_build_order(const long long* run_timing, int* order, int* queue, int n) {
+    __shared__ long long s_max;
+    __shared__ int hist[256], cursor[256];
+    int t = threadIdx.x;
+    if (t == 0) {
+        s_max = 0;
+        *queue = 0;
+    }
+    if (t < 256) hist[t] = 0;
+    __syncthreads();
+    long long m = 0;
+    for (int r = t; r < n; r += blockDim.x) {
+        long long d = run_timing[3 * r + 1] - run_timing[3 * r];
+#ifdef LDO_NO_LPT
+        d = 0;
+        order[r] = r;
+#endif
+        m = d > m ? d : m;
+    }
+    atomicMax((unsigned long long*)&s_max, (unsigned long long)m);
+    __syncthreads();
+#ifdef LDO_NO_LPT
+    return;
+#endif
+    long long mx = s_max + 1;
+    for (int r = t; r < n; r += blockDim.x) {
+        long long d = run_timing[3 * r + 1] - run_timing[3 * r];
+        atomicAdd(&hist[255 - (int)(d * 255 / mx)], 1);
+    }
+    __syncthreads();
+    if (t == 0) {
+        int acc = 0;
+        for (int b = 0; b < 256; b++) {
+            cursor[b] = acc;
+            acc += hist[b];
+        }
+    }
+    __syncthreads();
+    // the order inside a bucket is arbitrary: replicas are independent, results do not depend on it
+    for (int r = t; r < n; r += blockDim.x) {
+        long long d = run_timing[3 * r + 1] - run_timing[3 * r];
+        order[atomicAdd(&cursor[255 - (int)(d * 255 / mx)], 1)] = r;
     }
 }
 
@@ -828,6 +886,7 @@ struct EngineImpl: EngineBase {
     double* d_red_u = nullptr;
     int exch_cap = 0;
     int warps_per_block = 4;
+    int resident_blocks = 1; // staged kernel: blocks resident on the whole device (persistent grid)
 
     EngineImpl() {
         memset(&P, 0, sizeof(P));
@@ -845,6 +904,8 @@ struct EngineImpl: EngineBase {
         dev_free(P.grid_vals);
         dev_free(P.grid_visits);
         dev_free(P.run_timing);
+        dev_free(P.queue);
+        dev_free(P.order);
         dev_free(d_recompute_tmp);
         dev_free(d_cfg);
         dev_free(d_energies);
@@ -918,6 +979,8 @@ struct EngineImpl: EngineBase {
         if (dev_malloc((void**)&d_dependent, sizeof(double) * (3 + nst) * R)) return fail(dev_err());
         if (dev_malloc((void**)&d_recomputed, sizeof(double) * R)) return fail(dev_err());
         if (dev_malloc((void**)&P.run_timing, sizeof(long long) * 3 * R)) return fail(dev_err());
+        if (dev_malloc((void**)&P.queue, sizeof(int))) return fail(dev_err());
+        if (dev_malloc((void**)&P.order, sizeof(int) * R)) return fail(dev_err());
         if (dev_malloc((void**)&d_recomputed_stacked, sizeof(int) * R)) return fail(dev_err());
         if (dev_malloc((void**)&d_status, sizeof(int) * 2 * R)) return fail(dev_err());
         return 0;
@@ -995,7 +1058,15 @@ struct EngineImpl: EngineBase {
         if (upload_constants()) return -1;
         if constexpr (STAGED) {
             size_t smem = sizeof(WarpSmem<K>) * wpb;
-            k_exec_staged<K><<<blocks, wpb * 32, smem, stream>>>(P, a, wpb);
+            int n_items = a.only_replica >= 0 ? 1 : R;
+            if (a.op == OP_RUN && a.only_replica < 0) {
+                k_build_order<<<1, 1024, 0, stream>>>(P.run_timing, P.order, P.queue, R);
+                launches++;
+            }
+            else if (chk(cudaMemsetAsync(P.queue, 0, sizeof(int), stream))) return fail(dev_err());
+            blocks = (n_items + wpb - 1) / wpb;
+            if (blocks > resident_blocks) blocks = resident_blocks;
+            k_exec_staged<K><<<blocks, wpb * 32, smem, stream>>>(P, a, n_items);
         }
         else {
             k_exec_inplace<K><<<blocks, wpb * 32, 0, stream>>>(P, a, wpb, d_recompute_tmp);
@@ -1037,6 +1108,11 @@ struct EngineImpl: EngineBase {
             if (chk(cudaFuncSetAttribute(k_exec_staged<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(per_warp * wpb)))) {
                 return fail(dev_err());
             }
+            int per_sm = 0, n_sm = 0;
+            if (chk(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_exec_staged<K>, wpb * 32, per_warp * wpb))) return fail(dev_err());
+            cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device);
+            resident_blocks = per_sm * n_sm;
+            if (resident_blocks < 1) return fail("staged kernel does not fit on the device");
         }
 #endif
         return 0;
