@@ -87,6 +87,7 @@ static const char* dev_err() { return cudaGetErrorString(g_last_cuda); }
 // Per-replica auxiliary state and shared (read-only) engine constants
 // ---------------------------------------------------------------------------------------------
 
+#define LDO_MAX_LISTS 256 // work lists of the staged kernel (one per SM, indexed by %smid modulo the count)
 #define LDO_GRID_CAP 1024 // grid-bias points per replica (sum over grid biases)
 
 struct __attribute__((aligned(16))) RepAux {
@@ -155,7 +156,7 @@ struct DevPtrs {
     double* grid_vals; // [R][LDO_GRID_CAP]
     long long* grid_visits; // [R][LDO_GRID_CAP]
     long long* run_timing; // [R][3] diagnostics of the last run launch: start ns, end ns (globaltimer), SM id
-    int* queue; // work-queue head of the staged kernel (reset before every launch)
+    int* queue; // [LDO_MAX_LISTS] work-queue heads of the staged kernel (reset before every launch)
     int* order; // [R] replicas in the order they are handed out by a run launch (most expensive first)
 };
 
@@ -469,19 +470,36 @@ static_assert(LDO_AUX_HOT_BYTES % 16 == 0, "staged part of RepAux must be a mult
 #endif
 // Persistent: the grid is sized to what is resident on the chip and every warp pulls replicas from a
 // queue until it is empty, so that ensembles larger than one wave keep all warp slots busy. Run launches
-// hand replicas out most-expensive-first (k_build_order: cost = duration in the previous run launch), the
-// classic longest-processing-time rule for the tail.
+// hand replicas out most-expensive-first (k_build_order: cost = duration in the previous run launch, the
+// longest-processing-time rule for the tail), dealt round-robin into one list per SM so that every SM
+// works through the same mix of expensive and cheap replicas; a warp whose list is empty steals from the
+// next lists.
+__device__ inline int take_item(int* heads, int n_items, int n_lists, int my_list) {
+    for (int j = 0; j < n_lists; j++) {
+        int l = my_list + j;
+        if (l >= n_lists) l -= n_lists;
+        int len = (n_items - l + n_lists - 1) / n_lists; // items l, l + n_lists, ...
+        if (len <= 0 || *(volatile int*)&heads[l] >= len) continue;
+        int k = atomicAdd(&heads[l], 1);
+        if (k < len) return k * n_lists + l;
+    }
+    return -1;
+}
+
 template <class K>
-__global__ void __launch_bounds__(32 * LDO_BLOCK_WARPS, LDO_MIN_BLOCKS) k_exec_staged(DevPtrs<K> P, OpArgs a, int n_items) {
+__global__ void __launch_bounds__(32 * LDO_BLOCK_WARPS, LDO_MIN_BLOCKS) k_exec_staged(DevPtrs<K> P, OpArgs a, int n_items, int n_lists) {
     WarpSmem<K>* ws = reinterpret_cast<WarpSmem<K>*>(ldo_smem_raw);
     int warp = threadIdx.x >> 5;
     WarpSmem<K>& w = ws[warp];
     RepAux* aux = reinterpret_cast<RepAux*>(w.aux);
+    unsigned my_list;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(my_list));
+    my_list %= (unsigned)n_lists;
     for (;;) {
         int idx = 0;
-        if ((threadIdx.x & 31) == 0) idx = atomicAdd(P.queue, 1);
+        if ((threadIdx.x & 31) == 0) idx = take_item(P.queue, n_items, n_lists, (int)my_list);
         idx = __shfl_sync(0xffffffffu, idx, 0);
-        if (idx >= n_items) break;
+        if (idx < 0) break;
         int r = a.only_replica >= 0 ? a.only_replica : (a.op == OP_RUN ? P.order[idx] : idx);
         long long t0 = 0;
         if (a.op == OP_RUN) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
@@ -512,11 +530,9 @@ __global__ void __launch_bounds__(1024) k_build_order(const long long* run_timin
     __shared__ long long s_max;
     __shared__ int hist[256], cursor[256];
     int t = threadIdx.x;
-    if (t == 0) {
-        s_max = 0;
-        *queue = 0;
-    }
+    if (t == 0) s_max = 0;
     if (t < 256) hist[t] = 0;
+    if (t < LDO_MAX_LISTS) queue[t] = 0;
     __syncthreads();
     long long m = 0;
     for (int r = t; r < n; r += blockDim.x) {
@@ -886,6 +902,7 @@ struct EngineImpl: EngineBase {
     double* d_red_u = nullptr;
     int exch_cap = 0;
     int warps_per_block = 4;
+    int n_sm = 1;
     int resident_blocks = 1; // staged kernel: blocks resident on the whole device (persistent grid)
 
     EngineImpl() {
@@ -979,7 +996,7 @@ struct EngineImpl: EngineBase {
         if (dev_malloc((void**)&d_dependent, sizeof(double) * (3 + nst) * R)) return fail(dev_err());
         if (dev_malloc((void**)&d_recomputed, sizeof(double) * R)) return fail(dev_err());
         if (dev_malloc((void**)&P.run_timing, sizeof(long long) * 3 * R)) return fail(dev_err());
-        if (dev_malloc((void**)&P.queue, sizeof(int))) return fail(dev_err());
+        if (dev_malloc((void**)&P.queue, sizeof(int) * LDO_MAX_LISTS)) return fail(dev_err());
         if (dev_malloc((void**)&P.order, sizeof(int) * R)) return fail(dev_err());
         if (dev_malloc((void**)&d_recomputed_stacked, sizeof(int) * R)) return fail(dev_err());
         if (dev_malloc((void**)&d_status, sizeof(int) * 2 * R)) return fail(dev_err());
@@ -1063,10 +1080,11 @@ struct EngineImpl: EngineBase {
                 k_build_order<<<1, 1024, 0, stream>>>(P.run_timing, P.order, P.queue, R);
                 launches++;
             }
-            else if (chk(cudaMemsetAsync(P.queue, 0, sizeof(int), stream))) return fail(dev_err());
+            else if (chk(cudaMemsetAsync(P.queue, 0, sizeof(int) * LDO_MAX_LISTS, stream))) return fail(dev_err());
             blocks = (n_items + wpb - 1) / wpb;
             if (blocks > resident_blocks) blocks = resident_blocks;
-            k_exec_staged<K><<<blocks, wpb * 32, smem, stream>>>(P, a, n_items);
+            int n_lists = a.op == OP_RUN && n_items > 1 ? (n_sm < LDO_MAX_LISTS ? n_sm : LDO_MAX_LISTS) : 1;
+            k_exec_staged<K><<<blocks, wpb * 32, smem, stream>>>(P, a, n_items, n_lists);
         }
         else {
             k_exec_inplace<K><<<blocks, wpb * 32, 0, stream>>>(P, a, wpb, d_recompute_tmp);
@@ -1108,7 +1126,7 @@ struct EngineImpl: EngineBase {
             if (chk(cudaFuncSetAttribute(k_exec_staged<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(per_warp * wpb)))) {
                 return fail(dev_err());
             }
-            int per_sm = 0, n_sm = 0;
+            int per_sm = 0;
             if (chk(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_exec_staged<K>, wpb * 32, per_warp * wpb))) return fail(dev_err());
             cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device);
             resident_blocks = per_sm * n_sm;
