@@ -2,8 +2,10 @@
 """bench.py — attempted MC moves / second (whole job) of snodin temperature replica exchange.
 
 Workload (BASELINE.json configs[2]): examples/ptmc.inp generalised to a batch:
-`ut_parallel_tempering`, exchange_interval 100, 32-temperature ladder 330..361 K (1 K steps), 4096
-replicas per GPU = 128*N ladders, ladder slots dealt round-robin over the N GPUs (slot k on GPU k % N), start
+`ut_parallel_tempering`, exchange_interval 100, 32-temperature ladder 330..361 K (1 K steps), 16384
+replicas per GPU = 512*N ladders (BASELINE: ">= 4096 concurrent snodin replicas per B200"; four waves of the
+persistent run kernel keep every warp slot busy through the tail of slow, cold replicas — 4096 per GPU
+is reported in profiles/README.md), ladder slots dealt round-robin over the N GPUs (slot k on GPU k % N), start
 from snodin_unbound, moveset_standard. One "step" = one exchange round: 100 attempted moves on every
 replica, collection of the exchange quantities, (N > 1: NCCL all-gather), on-device swap decisions and
 the energy rebuild that follows a control-variable update.
@@ -122,11 +124,16 @@ def run_reference_arm(args, rank):
     }))
 
 
-def workload_config(n_gpus):
+DEFAULT_REPLICAS_PER_GPU = 16384
+
+
+def workload_config(n_gpus, replicas_per_gpu=DEFAULT_REPLICAS_PER_GPU):
+    R = replicas_per_gpu
     return {"workload": "snodin ut_parallel_tempering (examples/ptmc.inp batched): 32-temperature ladder 330..361 K, "
                         "exchange_interval 100, moveset_standard, start snodin_unbound",
-            "replicas_per_gpu": 4096, "ladders": 128 * n_gpus, "ladder_len": 32, "moves_per_step": 4096 * n_gpus * EXCHANGE_INTERVAL,
-            "l2_policy": "state (13 MB/GPU) is re-staged from HBM every launch; per-step working set is shared memory"}
+            "replicas_per_gpu": R, "ladders": R // len(LADDER) * n_gpus, "ladder_len": len(LADDER),
+            "moves_per_step": R * n_gpus * EXCHANGE_INTERVAL,
+            "l2_policy": f"state ({R * 3.1e3 / 1e6:.0f} MB/GPU) is re-staged from HBM every launch; per-step working set is shared memory"}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -303,14 +310,16 @@ def run_ours(args, rank, world, local_rank):
         smem_gbs = SMEM_BYTES_PER_MOVE * moves_per_launch / (kernel_ms * 1e-3) / 1e9
         smem_peak = 148 * 128 * (clocks.get("sm_max_mhz") or 1965.0) * 1e6 / 1e9
         traffic = None
-        traffic_path = os.path.join(ROOT, "profiles", "ncu_r1_run100.json")
-        if os.path.exists(traffic_path) and R == 4096:
-            traffic = json.load(open(traffic_path))["traffic_bytes_per_launch"]
+        traffic_path = os.path.join(ROOT, "profiles", "ncu_run100_traffic.json")
+        if os.path.exists(traffic_path):
+            t = json.load(open(traffic_path))
+            if t.get("replicas") == R:
+                traffic = t["traffic_bytes_per_launch"]
         line = {
             "metric": "attempted MC moves/sec (whole box), snodin PTMC", "value": value, "unit": "attempted MC moves/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(world), "clocks": clocks, "gpu_launches": int(launches),
+            "config": workload_config(world, R), "clocks": clocks, "gpu_launches": int(launches),
             "accepted_moves_per_s": value * accepted_frac,
             "e2e": {"value": e2e_value, "unit": "attempted MC moves/s", "h2d_bytes_per_step": int(blob_bytes),
                     "d2h_bytes_per_step": int(blob_bytes + energies.nbytes), "steps": e2e_steps},
@@ -339,7 +348,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--replicas-per-gpu", type=int, default=4096)
+    ap.add_argument("--replicas-per-gpu", type=int, default=DEFAULT_REPLICAS_PER_GPU)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -188,11 +188,12 @@ __constant__ SysConst ldo_c_sc;
 extern __shared__ __align__(16) unsigned char ldo_smem_raw[];
 #endif
 #if defined(__CUDA_ARCH__) && !defined(LDO_GENERIC_ACCESS)
-#define LDO_SMEM_PTR(K, T, member, fallback) \
-    (K::STAGED ? reinterpret_cast<T*>(ldo_smem_raw + (threadIdx.x >> 5) * SmemLayout<K>::stride + SmemLayout<K>::member) : (fallback))
+#define LDO_SMEM_AT(K, T, offset, fallback) \
+    (K::STAGED ? reinterpret_cast<T*>(ldo_smem_raw + (threadIdx.x >> 5) * SmemLayout<K>::stride + (offset)) : (fallback))
 #else
-#define LDO_SMEM_PTR(K, T, member, fallback) (fallback)
+#define LDO_SMEM_AT(K, T, offset, fallback) (fallback)
 #endif
+#define LDO_SMEM_PTR(K, T, member, fallback) LDO_SMEM_AT(K, T, SmemLayout<K>::member, fallback)
 template <class K>
 struct SmemLayout;
 
@@ -304,6 +305,8 @@ struct System {
     LDO_HD SysState<K>* S() const {
         return LDO_SMEM_PTR(K, SysState<K>, state, s);
     }
+    // The engine's System object of a staged replica sits at a fixed place of the warp's shared block
+    LDO_HD const TempTables& TT() const { return *LDO_SMEM_AT(K, const TempTables, SmemLayout<K>::engine + offsetof(System<K>, tt), &tt); }
     LDO_HD const SysConst& SC() const {
 #if defined(__CUDA_ARCH__)
         return ldo_c_sc;
@@ -389,9 +392,9 @@ struct System {
         int n = SC().n_ident;
         return (a + n) * (2 * n + 1) + (b + n);
     }
-    LDO_HD double hyb_energy(int di, int dj) const { return tt.hyb_energy[pair_index(ident(di), ident(dj))]; }
-    LDO_HD double hyb_enthalpy(int di, int dj) const { return tt.hyb_enthalpy[pair_index(ident(di), ident(dj))]; }
-    LDO_HD double hyb_entropy(int di, int dj) const { return tt.hyb_entropy[pair_index(ident(di), ident(dj))]; }
+    LDO_HD double hyb_energy(int di, int dj) const { return TT().hyb_energy[pair_index(ident(di), ident(dj))]; }
+    LDO_HD double hyb_enthalpy(int di, int dj) const { return TT().hyb_enthalpy[pair_index(ident(di), ident(dj))]; }
+    LDO_HD double hyb_entropy(int di, int dj) const { return TT().hyb_entropy[pair_index(ident(di), ident(dj))]; }
     LDO_HD double stack_energy() const { return S()->stack_e; }
 
     // ---- occupancy table ----
@@ -1287,7 +1290,7 @@ struct System {
     LDO_HD int add_chain(int type) {
         S()->current_c_i += 1;
         if (SC().apply_mean_field_cor) S()->energy += log(6.0);
-        S()->energy += tt.init_energy;
+        S()->energy += TT().init_energy;
         return add_chain_with_uid(type, S()->current_c_i);
     }
     // delete_chain (origami_system.cpp:445-472); the chain's domains must be unassigned
@@ -1314,7 +1317,7 @@ struct System {
         S()->num_unassigned -= len;
         S()->chain_used[c] = 0;
         if (SC().apply_mean_field_cor) S()->energy -= log(6.0);
-        S()->energy -= tt.init_energy;
+        S()->energy -= TT().init_energy;
     }
 
     // k-th staple of a given identity in insertion order (m_identity_to_index[type][k]; App. B)
@@ -1432,7 +1435,7 @@ struct System {
         }
         int ns = S()->n_chains - 1;
         if (SC().apply_mean_field_cor) S()->energy -= ns * log(6.0);
-        S()->energy -= ns * tt.init_energy;
+        S()->energy -= ns * TT().init_energy;
         if (S()->num_stacked_pairs != 0) {
             int sp = S()->num_stacked_pairs;
             set_all_domains();
@@ -1448,7 +1451,7 @@ struct System {
         S()->energy = 0;
         if (!set_all_domains()) return false;
         if (SC().apply_mean_field_cor) S()->energy += ns * log(6.0);
-        S()->energy += ns * tt.init_energy;
+        S()->energy += ns * TT().init_energy;
         return true;
     }
 
@@ -1458,7 +1461,7 @@ struct System {
         S()->energy = 0;
         int ns = S()->n_chains - 1;
         if (SC().apply_mean_field_cor) S()->energy += ns * log(6.0);
-        S()->energy += ns * tt.init_energy;
+        S()->energy += ns * TT().init_energy;
         return set_all_domains();
     }
 
@@ -1503,8 +1506,8 @@ struct System {
             if (S()->num_fully_bound_pairs >= 1) Sent -= 2 * log(6.0);
             if (S()->num_fully_bound_pairs >= 2) Sent -= log(3.0);
         }
-        H += ns * tt.init_enthalpy;
-        Sent += ns * tt.init_entropy;
+        H += ns * TT().init_enthalpy;
+        Sent += ns * TT().init_entropy;
         *enthalpy = H;
         *entropy = Sent;
         *stacking = S()->energy - (H - Sent);

@@ -250,7 +250,7 @@ LDO_HD void rep_load_config(Engine<K>& eng, const OpArgs& a) {
     }
     int ns = a.cfg_n_chains - 1;
     if (sc->apply_mean_field_cor) s->energy += ns * log(6.0);
-    s->energy += ns * sys.tt.init_energy;
+    s->energy += ns * sys.TT().init_energy;
     s->current_c_i = max_uid;
     if (s->status != LDO_OK) return;
     // positions and orientations, then set_all_domains (:588-616)

@@ -408,7 +408,7 @@ struct MoveStats {
 
 template <class K>
 struct Engine {
-    System<K> sys;
+    System<K> sys; // first member: SmemLayout<K>::engine is also the offset of the System object
     MoveScratch<K>* m;
     ColdScratch<K>* mc;
     Rng* rng;
@@ -419,26 +419,33 @@ struct Engine {
     Control ctl;
     MoveStats* stats;
 
-    // RG per-domain working state (rg_movetypes.hpp:118-126)
-    int di, d, ref_d, stemd, dir, c_attempts, d_max_c_attempts;
-    unsigned long long avail;
-    int max_recoils, max_c_attempts;
-    double delta_e, weight, weight_new;
-    // slot holding the current domain's trial probabilities; feeler memo bookkeeping
-    int cur_slot, memo_level, memo_key, memo_mask, last_pc, last_kind;
+    struct Work {
+        // RG per-domain working state (rg_movetypes.hpp:118-126)
+        int di, d, ref_d, stemd, dir, c_attempts, d_max_c_attempts;
+        unsigned long long avail;
+        int max_recoils, max_c_attempts;
+        double delta_e, weight, weight_new;
+        // slot holding the current domain's trial probabilities; feeler memo bookkeeping
+        int cur_slot, memo_level, memo_key, memo_mask, last_pc, last_kind;
+    };
+    Work wk;
 
     // ---- accessors: shared-memory hints and constant-memory copies on the device ----
     LDO_HD MoveScratch<K>* M() const {
         return LDO_SMEM_PTR(K, MoveScratch<K>, scratch, m);
     }
-    LDO_HD ColdScratch<K>* C() const { return mc; }
+#define LDO_ENG_FIELD(T, member) (*LDO_SMEM_AT(K, T, SmemLayout<K>::engine + offsetof(Engine<K>, member), const_cast<T*>(&member)))
+    LDO_HD Work* W() const { return &LDO_ENG_FIELD(Work, wk); }
+    LDO_HD ColdScratch<K>* C() const { return LDO_ENG_FIELD(ColdScratch<K>*, mc); }
+    LDO_HD const Control& CTL() const { return LDO_ENG_FIELD(Control, ctl); }
+    LDO_HD const double* GV() const { return LDO_ENG_FIELD(const double*, grid_vals); }
     LDO_HD Rng* RNG() const {
         return LDO_SMEM_PTR(K, Rng, rng, rng);
     }
     LDO_HD BiasState* BS() const {
         return LDO_SMEM_PTR(K, BiasState, bias, bs);
     }
-    LDO_HD MoveStats* STATS() const { return stats; } // global memory: touched twice per move
+    LDO_HD MoveStats* STATS() const { return LDO_ENG_FIELD(MoveStats*, stats); } // global memory: touched twice per move
     LDO_HD const MoveSet& MS() const {
 #if defined(__CUDA_ARCH__)
         return ldo_c_ms;
@@ -590,7 +597,7 @@ struct Engine {
             if (v < 0 || v >= BS()->grid_n[b][k]) return 0;
             idx = idx * BS()->grid_n[b][k] + v;
         }
-        double g = grid_vals[off + idx];
+        double g = GV()[off + idx];
         return g == g ? g : 0; // NaN marks a point absent from the grid (m_off_grid_bias = 0)
     }
     LDO_HD double calc_bias_fn(int b) const {
@@ -619,9 +626,9 @@ struct Engine {
             diff += nb - prev;
         }
         BS()->move_update_bias += diff;
-        return diff * ctl.bias_mult;
+        return diff * CTL().bias_mult;
     }
-    LDO_HD double total_bias() const { return BS()->move_update_bias * ctl.bias_mult; }
+    LDO_HD double total_bias() const { return BS()->move_update_bias * CTL().bias_mult; }
 
     // ---- MCMovetype shared helpers (movetypes.cpp:98-158) ----
     LDO_HD int select_random_domain() {
@@ -817,7 +824,7 @@ struct Engine {
             int prev = first + stepdir * (i - 1);
             V3 p = rec_pos(sys.S()->dom[prev]) + ore_vec(uniform_int(0, 5));
             int o = uniform_int(0, 5);
-            delta_e += sys.set_domain_config(dd, p, o);
+            W()->delta_e += sys.set_domain_config(dd, p, o);
             if (sys.S()->constraints_violated) {
                 M()->rejected = 1;
                 break;
@@ -840,12 +847,12 @@ struct Engine {
             int dd = base + k;
             C()->prev[dd] = sys.S()->dom[dd];
             push_modified(dd);
-            delta_e += sys.unassign_domain(dd);
+            W()->delta_e += sys.unassign_domain(dd);
         }
     }
     LDO_HD void met_add_external_bias() {
         update_move_params();
-        delta_e += calc_move_bias();
+        W()->delta_e += calc_move_bias();
     }
 
     // ---- MetStapleExchange (met_movetypes.cpp:192-403) ----
@@ -863,7 +870,7 @@ struct Engine {
     }
     LDO_HDN bool move_staple_exchange(const MoveDef& md) {
         SysState<K>* s = sys.S();
-        delta_e = 0;
+        W()->delta_e = 0;
         int insertion_sites = s->num_domains;
         if (uniform_real() < 0.5) {
             // insert_staple (:303-359)
@@ -872,8 +879,8 @@ struct Engine {
             if (s->type_count[type] == sys.SC().max_type_staples) return false;
             int c = sys.add_chain(type);
             if (c < 0) return false;
-            if (sys.SC().apply_mean_field_cor) delta_e += log(6.0);
-            delta_e += sys.tt.init_energy;
+            if (sys.SC().apply_mean_field_cor) W()->delta_e += log(6.0);
+            W()->delta_e += sys.TT().init_energy;
             M()->added_chain = c;
             // select_new_growthpoint (movetypes.cpp:372-383)
             int len = s->chain_len[c];
@@ -881,7 +888,7 @@ struct Engine {
             int g_old = select_random_domain();
 #pragma unroll 1
             while (sys.chain(g_old) == c && s->status == LDO_OK) g_old = select_random_domain();
-            delta_e += set_growth_point(g_new, g_old);
+            W()->delta_e += set_growth_point(g_new, g_old);
             if (M()->rejected) return false;
             met_grow_staple(c, s->dindex[g_new]);
             if (M()->rejected) return false;
@@ -889,7 +896,7 @@ struct Engine {
             int num_bd = num_bound_staple_domains(c);
             // staple_insertion_accepted (:212-253)
             met_add_external_bias();
-            double boltz = exp(-delta_e);
+            double boltz = exp(-W()->delta_e);
             int Ni_new = s->type_count[type];
             double pratio = (double)len / 6.0 / Ni_new * boltz;
             pratio *= insertion_sites * sys.SC().staple_M;
@@ -909,13 +916,13 @@ struct Engine {
         int num_bd = num_bound_staple_domains(c);
         int len = s->chain_len[c];
         met_unassign_domains(c);
-        if (sys.SC().apply_mean_field_cor) delta_e -= log(6.0);
-        delta_e -= sys.tt.init_energy;
+        if (sys.SC().apply_mean_field_cor) W()->delta_e -= log(6.0);
+        W()->delta_e -= sys.TT().init_energy;
         // staple_deletion_accepted (:255-301)
         s->num_staples--;
         met_add_external_bias();
         s->num_staples++;
-        double boltz = exp(-delta_e);
+        double boltz = exp(-W()->delta_e);
         int Ni = s->type_count[type];
         double pratio = Ni * 6.0 / (double)len * boltz;
         pratio /= sys.SC().staple_M * (insertion_sites - len);
@@ -928,7 +935,7 @@ struct Engine {
     // ---- MetStapleRegrowth (met_movetypes.cpp:470-513) ----
     LDO_HDN bool move_met_staple_regrowth() {
         SysState<K>* s = sys.S();
-        delta_e = 0;
+        W()->delta_e = 0;
         if (s->num_staples == 0) return false;
         int c = s->order[uniform_int(1, s->num_staples)];
         if (staple_is_connector(c)) return false;
@@ -940,13 +947,13 @@ struct Engine {
         int g_new = kth_bound_to_other_chains(c, uniform_int(0, n_bd - 1));
         int g_old = s->bound[g_new];
         met_unassign_domains(c);
-        delta_e += set_growth_point(g_new, g_old);
+        W()->delta_e += set_growth_point(g_new, g_old);
         if (M()->rejected) return false;
         met_grow_staple(c, s->dindex[g_new]);
         if (M()->rejected) return false;
         met_add_external_bias();
         int new_num_bd = num_bound_staple_domains(c);
-        double pratio = exp(-delta_e) * n_bd / new_num_bd;
+        double pratio = exp(-W()->delta_e) * n_bd / new_num_bd;
         return test_acceptance(pratio);
     }
 
@@ -1467,8 +1474,8 @@ struct Engine {
             int max_length = n < md.max_regrowth ? n : md.max_regrowth;
             int sel_length = uniform_int(2, max_length);
             int start_i = uniform_int(0, n - 1);
-            dir = uniform_int(0, 1);
-            if (dir == 0) dir = -1;
+            W()->dir = uniform_int(0, 1);
+            if (W()->dir == 0) W()->dir = -1;
             // forward part
             short* buf = C()->seg_dom; // scratch: forward list then backward list
             int nf = 0, nb = 0;
@@ -1476,14 +1483,14 @@ struct Engine {
 #pragma unroll 1
             while (cur >= 0 && nf != sel_length) {
                 buf[nf++] = (short)cur;
-                cur = sys.step(cur, dir);
+                cur = sys.step(cur, W()->dir);
             }
-            int back = sys.step(sys.chain_base(0) + start_i, -dir);
+            int back = sys.step(sys.chain_base(0) + start_i, -W()->dir);
 #pragma unroll 1
             while (back >= 0 && nf + nb != sel_length) {
                 buf[K::D + 1 + nb] = (short)back;
                 nb++;
-                back = sys.step(back, -dir);
+                back = sys.step(back, -W()->dir);
             }
             if (nf + nb < 2) continue;
             C()->n_sel = 0;
@@ -1641,7 +1648,7 @@ struct Engine {
     }
     // restore_endpoints (rg:288-295)
     LDO_HDN void rg_restore_endpoints() {
-        cp_remove_activated_endpoint(d);
+        cp_remove_activated_endpoint(W()->d);
         if (M()->eq_depth <= 0) {
             sys.fail(LDO_ERR_INTERNAL, 1);
             return;
@@ -1649,7 +1656,7 @@ struct Engine {
         int start = M()->eq_start[--M()->eq_depth];
 #pragma unroll 1
         for (int k = start; k < M()->eq_npos; k++) {
-            cp_add_active_endpoint(d, v3(M()->eq_pos[k][0], M()->eq_pos[k][1], M()->eq_pos[k][2]));
+            cp_add_active_endpoint(W()->d, v3(M()->eq_pos[k][0], M()->eq_pos[k][1], M()->eq_pos[k][2]));
         }
         M()->eq_npos = start;
     }
@@ -1678,27 +1685,27 @@ struct Engine {
     LDO_HDN double rg_set_config(int dd, V3 p, int o) {
         double de = sys.set_checked_domain_config(dd, p, o);
         push_assigned(dd);
-        cp_update_endpoints(d);
+        cp_update_endpoints(W()->d);
         eq_push_erased();
         return de;
     }
     LDO_HD static unsigned long long all_cis() { return (1ull << 36) - 1; }
     // prepare_for_growth (rg:246-262)
     LDO_HDN void rg_prepare_for_growth() {
-        di++;
-        d = M()->regrow[di];
-        stemd = M()->stem_gp[d] >= 0;
-        dir = cp_get_dir(d);
-        c_attempts = 0;
-        if (stemd) {
-            d_max_c_attempts = 1;
-            avail = 0;
-            ref_d = M()->stem_gp[d];
+        W()->di++;
+        W()->d = M()->regrow[W()->di];
+        W()->stemd = M()->stem_gp[W()->d] >= 0;
+        W()->dir = cp_get_dir(W()->d);
+        W()->c_attempts = 0;
+        if (W()->stemd) {
+            W()->d_max_c_attempts = 1;
+            W()->avail = 0;
+            W()->ref_d = M()->stem_gp[W()->d];
         }
         else {
-            d_max_c_attempts = max_c_attempts;
-            avail = all_cis();
-            ref_d = sys.step(d, -dir);
+            W()->d_max_c_attempts = W()->max_c_attempts;
+            W()->avail = all_cis();
+            W()->ref_d = sys.step(W()->d, -W()->dir);
             rg_acquire_slot();
         }
     }
@@ -1706,23 +1713,23 @@ struct Engine {
     // the first feeler level of calc_weights and the parent sits on an empty site (the feeler's results
     // do not depend on the parent's orientation then), else the level's own slot.
     LDO_HD void rg_acquire_slot() {
-        bool use_memo = di == memo_level && memo_key >= 0;
+        bool use_memo = W()->di == W()->memo_level && W()->memo_key >= 0;
         if (use_memo) {
             // the memo is keyed by the parent's site only: unusable when the current domain could bind
             // to the (unbound) parent itself, because that depends on the parent's orientation
-            V3 dq = rec_pos(sys.S()->dom[M()->regrow[di - 1]]) - rec_pos(sys.S()->dom[ref_d]);
+            V3 dq = rec_pos(sys.S()->dom[M()->regrow[W()->di - 1]]) - rec_pos(sys.S()->dom[W()->ref_d]);
             if (abssum(dq) == 1) use_memo = false;
         }
         if (use_memo) {
-            cur_slot = LDO_RG_OWN_SLOTS + memo_key;
-            if (!((memo_mask >> memo_key) & 1)) {
-                rg_compute_slot(cur_slot);
-                memo_mask |= 1 << memo_key;
+            W()->cur_slot = LDO_RG_OWN_SLOTS + W()->memo_key;
+            if (!((W()->memo_mask >> W()->memo_key) & 1)) {
+                rg_compute_slot(W()->cur_slot);
+                W()->memo_mask |= 1 << W()->memo_key;
             }
         }
         else {
-            cur_slot = di & (LDO_RG_OWN_SLOTS - 1);
-            rg_compute_slot(cur_slot);
+            W()->cur_slot = W()->di & (LDO_RG_OWN_SLOTS - 1);
+            rg_compute_slot(W()->cur_slot);
         }
     }
     // Open probability data of domain `dom` at site r (calc_p_config_open, rg:315-343, for the six
@@ -1753,12 +1760,12 @@ struct Engine {
     // lane, read-only.
     LDO_HDN void rg_compute_slot(int slot) {
         RgSlot& sl = M()->slots[slot];
-        V3 refp = rec_pos(sys.S()->dom[ref_d]);
+        V3 refp = rec_pos(sys.S()->dom[W()->ref_d]);
 #pragma unroll 1
         for (int k = LDO_LANE; k < 6; k += LDO_NLANES) {
             int kind, o;
             double pv;
-            rg_eval_site(d, stemd != 0, refp + ore_vec(k), nullptr, kind, o, pv);
+            rg_eval_site(W()->d, W()->stemd != 0, refp + ore_vec(k), nullptr, kind, o, pv);
             sl.kind[k] = (uint8_t)kind;
             sl.ore[k] = (int8_t)o;
             sl.p[k] = pv;
@@ -1771,9 +1778,9 @@ struct Engine {
     // carried by an EpOverlay. Fills the memo slots and memo_mask. `fd` / `fref`: feeler domain and its
     // reference domain (the parent itself, or an already placed domain).
     LDO_HDN void rg_fill_feeler_memo(int fd, int fref) {
-        const RgSlot& own = M()->slots[cur_slot];
-        V3 refp = rec_pos(sys.S()->dom[ref_d]);
-        bool fref_is_parent = fref == d;
+        const RgSlot& own = M()->slots[W()->cur_slot];
+        V3 refp = rec_pos(sys.S()->dom[W()->ref_d]);
+        bool fref_is_parent = fref == W()->d;
         V3 frefp = fref_is_parent ? v3(0, 0, 0) : rec_pos(sys.S()->dom[fref]);
         int mask = 0;
 #pragma unroll 1
@@ -1784,10 +1791,10 @@ struct Engine {
             mask |= 1 << pc;
         }
         EpOverlay ov;
-        ov.rm_chain = sys.chain(d);
-        ov.rm_seg = M()->seg_of[d];
-        ov.rm_d = sys.dindex(d);
-        int ie = M()->inactive[d];
+        ov.rm_chain = sys.chain(W()->d);
+        ov.rm_seg = M()->seg_of[W()->d];
+        ov.rm_d = sys.dindex(W()->d);
+        int ie = M()->inactive[W()->d];
         ov.add_chain = -1;
         ov.add_seg = 0;
         ov.add_d = 0;
@@ -1812,69 +1819,69 @@ struct Engine {
             sl.p[k] = pv;
         }
         LDO_SYNCWARP();
-        memo_mask = mask;
+        W()->memo_mask = mask;
     }
     // prepare_for_regrowth (rg:264-286)
     LDO_HDN double rg_prepare_for_regrowth() {
-        di--;
-        d = M()->regrow[di];
-        dir = cp_get_dir(d);
-        double de = sys.unassign_domain(d);
+        W()->di--;
+        W()->d = M()->regrow[W()->di];
+        W()->dir = cp_get_dir(W()->d);
+        double de = sys.unassign_domain(W()->d);
         if (M()->n_assigned > 0) M()->n_assigned--;
         rg_restore_endpoints();
-        stemd = M()->stem_gp[d] >= 0;
-        if (stemd) {
-            d_max_c_attempts = 1;
-            c_attempts = 1;
-            avail = 0;
-            ref_d = M()->stem_gp[d];
+        W()->stemd = M()->stem_gp[W()->d] >= 0;
+        if (W()->stemd) {
+            W()->d_max_c_attempts = 1;
+            W()->c_attempts = 1;
+            W()->avail = 0;
+            W()->ref_d = M()->stem_gp[W()->d];
         }
         else {
-            d_max_c_attempts = max_c_attempts;
-            c_attempts = M()->c_attempts_q[di];
-            avail = M()->avail_q[di];
-            ref_d = sys.step(d, -dir);
-            cur_slot = di & (LDO_RG_OWN_SLOTS - 1);
-            rg_compute_slot(cur_slot);
+            W()->d_max_c_attempts = W()->max_c_attempts;
+            W()->c_attempts = M()->c_attempts_q[W()->di];
+            W()->avail = M()->avail_q[W()->di];
+            W()->ref_d = sys.step(W()->d, -W()->dir);
+            W()->cur_slot = W()->di & (LDO_RG_OWN_SLOTS - 1);
+            rg_compute_slot(W()->cur_slot);
         }
         return de;
     }
     // select_trial_config + calc_p_config_open (rg:297-343): draws the k-th remaining entry of the
     // ordered configuration list and returns its open probability from the current slot
     LDO_HDN double rg_trial(V3& p, int& o) {
-        if (stemd) {
-            const DomRec& r = sys.S()->dom[ref_d];
+        if (W()->stemd) {
+            const DomRec& r = sys.S()->dom[W()->ref_d];
             p = rec_pos(r);
             o = r.ore < 6 ? (r.ore ^ 1) : r.ore;
-            last_pc = -1;
-            last_kind = 0;
+            W()->last_pc = -1;
+            W()->last_kind = 0;
             return rg_calc_p_config_open(p, o);
         }
-        int n_avail = popc36(avail);
+        int n_avail = popc36(W()->avail);
         int ci = uniform_int(0, n_avail - 1);
-        int i = nth_set_bit36(avail, ci);
-        avail &= ~(1ull << i);
+        int i = nth_set_bit36(W()->avail, ci);
+        W()->avail &= ~(1ull << i);
         // m_all_configs = all_pairs(vectors): position-major, orientation-minor (utility.hpp:167-177)
         int pc = i / 6;
         o = i - 6 * pc;
-        p = ore_vec(pc) + rec_pos(sys.S()->dom[ref_d]);
-        const RgSlot& sl = M()->slots[cur_slot];
+        p = ore_vec(pc) + rec_pos(sys.S()->dom[W()->ref_d]);
+        const RgSlot& sl = M()->slots[W()->cur_slot];
         int kind = sl.kind[pc];
-        last_pc = pc;
-        last_kind = kind;
+        W()->last_pc = pc;
+        W()->last_kind = kind;
         double pv = 0;
         if (kind == 1) pv = sl.p[pc];
         else if (kind == 2 && o == sl.ore[pc]) pv = sl.p[pc];
 #if defined(LDO_DEBUG_SLOTS) && !defined(__CUDA_ARCH__)
-        if (getenv("LDO_DEBUG_RG")) printf("  trial di=%d d=(%d %d) ref=(%d %d) ci=%d p=(%d %d %d) o=%d kind=%d pv=%g tape_pos=%lld\n", di, sys.S()->chain_uid[sys.chain(d)], sys.dindex(d), sys.S()->chain_uid[sys.chain(ref_d)], sys.dindex(ref_d), i, p.x, p.y, p.z, o, kind, pv, RNG()->tape_pos);
+        if (getenv("LDO_DEBUG_RG")) printf("  trial di=%d d=(%d %d) ref=(%d %d) ci=%d p=(%d %d %d) o=%d kind=%d pv=%g tape_pos=%lld\n", W()->di, sys.S()->chain_uid[sys.chain(W()->d)], sys.dindex(W()->d), sys.S()->chain_uid[sys.chain(W()->ref_d)], sys.dindex(W()->ref_d), i, p.x, p.y, p.z, o, kind, pv, RNG()->tape_pos);
         {
-            DomRec saved = sys.S()->dom[d];
+            DomRec saved = sys.S()->dom[W()->d];
             double pref = rg_calc_p_config_open(p, o);
-            sys.S()->dom[d] = saved;
+            sys.S()->dom[W()->d] = saved;
             if (pref != pv) {
 #pragma unroll 1
                 for (int q = 0; q < M()->n_ep; q++) printf("   ep chain=%d seg=%d d=%d pos=(%d %d %d)\n", M()->ep_chain[q], M()->ep_seg[q], M()->ep_d[q], M()->ep_pos[q][0], M()->ep_pos[q][1], M()->ep_pos[q][2]);
-                printf("SLOT MISMATCH p=(%d %d %d) di=%d d=%d ci=%d pc=%d o=%d kind=%d slot=%d pv=%g ref=%g stemd=%d memo_level=%d memo_key=%d\n", p.x, p.y, p.z, di, d, i, pc, o, kind, cur_slot, pv, pref, stemd, memo_level, memo_key);
+                printf("SLOT MISMATCH p=(%d %d %d) di=%d d=%d ci=%d pc=%d o=%d kind=%d slot=%d pv=%g ref=%g stemd=%d memo_level=%d memo_key=%d\n", p.x, p.y, p.z, W()->di, W()->d, i, pc, o, kind, W()->cur_slot, pv, pref, W()->stemd, W()->memo_level, W()->memo_key);
             }
         }
 #endif
@@ -1882,17 +1889,17 @@ struct Engine {
     }
     // calc_p_config_open (rg:315-343)
     LDO_HDN double rg_calc_p_config_open(V3 p, int o) {
-        double de = sys.check_domain_constraints(d, p, o);
+        double de = sys.check_domain_constraints(W()->d, p, o);
         if (sys.S()->constraints_violated) {
             sys.S()->constraints_violated = 0;
             return 0;
         }
-        if (!cp_walks_remain(d, p)) return 0;
+        if (!cp_walks_remain(W()->d, p)) return 0;
         int j = sys.occupant(p);
         if (j >= 0 && sys.S()->dom[j].state == ST_UNBOUND) {
-            bool same_chain = sys.chain(j) == sys.chain(d);
-            bool endpoint = cp_endpoint_reached(d, p);
-            if (!(same_chain || endpoint || stemd)) return 0;
+            bool same_chain = sys.chain(j) == sys.chain(W()->d);
+            bool endpoint = cp_endpoint_reached(W()->d, p);
+            if (!(same_chain || endpoint || W()->stemd)) return 0;
         }
         return fmin(1.0, exp(-de));
     }
@@ -1905,9 +1912,9 @@ struct Engine {
     // recoil_regrow (rg:177-231)
     LDO_HDN double rg_recoil_regrow() {
         double de = 0;
-        di = 0;
-        d = M()->regrow[0];
-        dir = cp_get_dir(d);
+        W()->di = 0;
+        W()->d = M()->regrow[0];
+        W()->dir = cp_get_dir(W()->d);
         M()->c_opens[0] = 1;
         rg_prepare_for_growth();
         int recoils = 0;
@@ -1922,22 +1929,22 @@ struct Engine {
             double p_c_open = 0;
             bool c_open = false;
 #pragma unroll 1
-            while (!c_open && c_attempts != d_max_c_attempts) {
-                c_attempts++;
+            while (!c_open && W()->c_attempts != W()->d_max_c_attempts) {
+                W()->c_attempts++;
                 p_c_open = rg_trial(p, o);
                 c_open = rg_test_config_open(p_c_open);
             }
             if (c_open) {
                 if (recoils != 0) recoils--;
-                de += rg_set_config(d, p, o);
-                M()->c_attempts_q[di] = (uint8_t)c_attempts;
-                M()->avail_q[di] = avail;
-                M()->c_opens[di] = p_c_open;
-                if (di == M()->n_regrow - 1) break;
+                de += rg_set_config(W()->d, p, o);
+                M()->c_attempts_q[W()->di] = (uint8_t)W()->c_attempts;
+                M()->avail_q[W()->di] = W()->avail;
+                M()->c_opens[W()->di] = p_c_open;
+                if (W()->di == M()->n_regrow - 1) break;
                 rg_prepare_for_growth();
             }
             else {
-                if (recoils == max_recoils || di == 1) {
+                if (recoils == W()->max_recoils || W()->di == 1) {
                     M()->rejected = 1;
                     break;
                 }
@@ -1950,21 +1957,21 @@ struct Engine {
     // test_config_avail (rg:422-480)
     LDO_HDN bool rg_test_config_avail() {
         int feels = 0;
-        if (feels == max_recoils || di == M()->n_regrow - 1) return true;
+        if (feels == W()->max_recoils || W()->di == M()->n_regrow - 1) return true;
         rg_prepare_for_growth();
         bool c_avail = false;
-        if (RNG()->tape == nullptr && max_recoils == 1 && !stemd && d_max_c_attempts == 36) {
+        if (RNG()->tape == nullptr && W()->max_recoils == 1 && !W()->stemd && W()->d_max_c_attempts == 36) {
             // Philox mode, one exhaustive feeler level: "some configuration opens" has probability
             // 1 - prod(1 - p) whatever the trial order, so one draw replaces up to 36 trials
-            const RgSlot& sl = M()->slots[cur_slot];
+            const RgSlot& sl = M()->slots[W()->cur_slot];
             double none = 1.0;
 #pragma unroll 1
             for (int k = 0; k < 6; k++) {
                 if (sl.kind[k] != 0) none *= 1.0 - sl.p[k];
             }
             c_avail = rg_test_config_open(1.0 - none);
-            di--;
-            d = M()->regrow[di];
+            W()->di--;
+            W()->d = M()->regrow[W()->di];
             return c_avail;
         }
 #pragma unroll 1
@@ -1975,21 +1982,21 @@ struct Engine {
             bool c_open = false;
             double p_c_open;
 #pragma unroll 1
-            while (!c_open && c_attempts != d_max_c_attempts) {
-                c_attempts++;
+            while (!c_open && W()->c_attempts != W()->d_max_c_attempts) {
+                W()->c_attempts++;
                 p_c_open = rg_trial(p, o);
                 c_open = rg_test_config_open(p_c_open);
             }
             if (c_open) {
                 feels++;
-                if (feels == max_recoils || di == M()->n_regrow - 1) {
+                if (feels == W()->max_recoils || W()->di == M()->n_regrow - 1) {
                     feels--;
                     c_avail = true;
                     break;
                 }
-                rg_set_config(d, p, o);
-                M()->c_attempts_q[di] = (uint8_t)c_attempts;
-                M()->avail_q[di] = avail;
+                rg_set_config(W()->d, p, o);
+                M()->c_attempts_q[W()->di] = (uint8_t)W()->c_attempts;
+                M()->avail_q[W()->di] = W()->avail;
                 rg_prepare_for_growth();
             }
             else {
@@ -2003,52 +2010,52 @@ struct Engine {
         }
 #pragma unroll 1
         while (feels != 0) {
-            di--;
+            W()->di--;
             feels--;
-            d = M()->regrow[di];
-            sys.unassign_domain(d);
+            W()->d = M()->regrow[W()->di];
+            sys.unassign_domain(W()->d);
             rg_restore_endpoints();
         }
-        di--;
-        d = M()->regrow[di];
+        W()->di--;
+        W()->d = M()->regrow[W()->di];
         return c_avail;
     }
     // calc_weights (rg:363-417)
     LDO_HDN void rg_calc_weights() {
-        di = 0;
-        d = M()->regrow[0];
+        W()->di = 0;
+        W()->d = M()->regrow[0];
 #pragma unroll 1
-        while (di != M()->n_regrow - 1) {
+        while (W()->di != M()->n_regrow - 1) {
             if (sys.S()->status != LDO_OK) return;
-            di++;
-            d = M()->regrow[di];
-            stemd = M()->stem_gp[d] >= 0;
-            dir = cp_get_dir(d);
+            W()->di++;
+            W()->d = M()->regrow[W()->di];
+            W()->stemd = M()->stem_gp[W()->d] >= 0;
+            W()->dir = cp_get_dir(W()->d);
             int avail_cs = 1;
-            if (!stemd) {
-                ref_d = sys.step(d, -dir);
-                int catt = M()->c_attempts_wq[di];
-                avail = M()->avail_wq[di];
-                memo_level = -1;
-                memo_mask = 0;
-                cur_slot = di & (LDO_RG_OWN_SLOTS - 1);
-                if (catt != max_c_attempts) rg_compute_slot(cur_slot);
+            if (!W()->stemd) {
+                W()->ref_d = sys.step(W()->d, -W()->dir);
+                int catt = M()->c_attempts_wq[W()->di];
+                W()->avail = M()->avail_wq[W()->di];
+                W()->memo_level = -1;
+                W()->memo_mask = 0;
+                W()->cur_slot = W()->di & (LDO_RG_OWN_SLOTS - 1);
+                if (catt != W()->max_c_attempts) rg_compute_slot(W()->cur_slot);
                 // With one feeler level (max_num_recoils == 1) an open trial configuration on an EMPTY
                 // site only needs "does the next domain have an open configuration"; that depends on the
                 // site, not on the orientation, so after the first orientation of a site has been
                 // examined for real the remaining ones replay the feeler's draws on the memoised slot
                 // without touching the lattice. (The reference sets and unsets the domain each time,
                 // rg:378-402; the net state change is nil.)
-                bool last_level = di == M()->n_regrow - 1;
+                bool last_level = W()->di == M()->n_regrow - 1;
                 bool feeler_simple = false;
                 V3 feeler_refp = v3(0, 0, 0);
                 bool feeler_ref_is_parent = false;
-                if (!last_level && max_recoils == 1 && catt != max_c_attempts) {
-                    int fd = M()->regrow[di + 1];
+                if (!last_level && W()->max_recoils == 1 && catt != W()->max_c_attempts) {
+                    int fd = M()->regrow[W()->di + 1];
                     if (M()->stem_gp[fd] < 0) {
                         int fref = sys.step(fd, -cp_get_dir(fd));
                         feeler_simple = true;
-                        feeler_ref_is_parent = fref == d;
+                        feeler_ref_is_parent = fref == W()->d;
                         if (!feeler_ref_is_parent) feeler_refp = rec_pos(sys.S()->dom[fref]);
                         rg_fill_feeler_memo(fd, fref);
                     }
@@ -2057,57 +2064,57 @@ struct Engine {
                 // examined whatever the order, and its contribution is an independent Bernoulli variable,
                 // so the configurations are spread over the lanes, each with its own Philox block, and the
                 // count is reduced across the warp. Replay (tape) mode keeps the reference's serial order.
-                if (RNG()->tape == nullptr && max_c_attempts == 36 && max_recoils == 1 && catt != max_c_attempts &&
+                if (RNG()->tape == nullptr && W()->max_c_attempts == 36 && W()->max_recoils == 1 && catt != W()->max_c_attempts &&
                     (last_level || feeler_simple)) {
                     avail_cs += rg_count_avail_parallel(last_level);
-                    catt = max_c_attempts;
+                    catt = W()->max_c_attempts;
                 }
 #pragma unroll 1
-                while (catt != max_c_attempts) {
+                while (catt != W()->max_c_attempts) {
                     catt++;
                     V3 p;
                     int o;
                     double p_c_open = rg_trial(p, o);
                     if (rg_test_config_open(p_c_open)) {
-                        if (last_level && max_recoils >= 1) {
+                        if (last_level && W()->max_recoils >= 1) {
                             avail_cs += 1;
                             continue;
                         }
-                        if (feeler_simple && last_kind == 1 && ((memo_mask >> last_pc) & 1) &&
+                        if (feeler_simple && W()->last_kind == 1 && ((W()->memo_mask >> W()->last_pc) & 1) &&
                             (feeler_ref_is_parent || abssum(p - feeler_refp) != 1)) {
-                            avail_cs += rg_feeler_from_slot(LDO_RG_OWN_SLOTS + last_pc) ? 1 : 0;
+                            avail_cs += rg_feeler_from_slot(LDO_RG_OWN_SLOTS + W()->last_pc) ? 1 : 0;
                             continue;
                         }
                         avail_cs += rg_feeler_general(p, o) ? 1 : 0;
                     }
                 }
             }
-            weight *= avail_cs / M()->c_opens[di - 1];
-            const DomRec& r = C()->prev[d];
-            sys.set_checked_domain_config(d, rec_pos(r), r.ore);
-            cp_update_endpoints(d);
+            W()->weight *= avail_cs / M()->c_opens[W()->di - 1];
+            const DomRec& r = C()->prev[W()->d];
+            sys.set_checked_domain_config(W()->d, rec_pos(r), r.ore);
+            cp_update_endpoints(W()->d);
             eq_push_erased();
         }
-        weight /= M()->c_opens[di];
+        W()->weight /= M()->c_opens[W()->di];
     }
     // One open trial configuration of calc_weights examined the reference's way: place the domain, grow
     // feelers, take it back (rg:384-400)
     LDO_HDN bool rg_feeler_general(V3 p, int o) {
-        sys.set_checked_domain_config(d, p, o);
-        cp_update_endpoints(d);
+        sys.set_checked_domain_config(W()->d, p, o);
+        cp_update_endpoints(W()->d);
         eq_push_erased();
-        int dir_s = dir, ref_s = ref_d, stem_s = stemd, slot_s = cur_slot;
-        unsigned long long avail_s = avail;
-        memo_level = di + 1;
-        memo_key = last_kind == 1 ? last_pc : -1;
+        int dir_s = W()->dir, ref_s = W()->ref_d, stem_s = W()->stemd, slot_s = W()->cur_slot;
+        unsigned long long avail_s = W()->avail;
+        W()->memo_level = W()->di + 1;
+        W()->memo_key = W()->last_kind == 1 ? W()->last_pc : -1;
         bool c_avail = rg_test_config_avail();
-        memo_key = -1;
-        avail = avail_s;
-        stemd = stem_s;
-        ref_d = ref_s;
-        dir = dir_s;
-        cur_slot = slot_s;
-        sys.unassign_domain(d);
+        W()->memo_key = -1;
+        W()->avail = avail_s;
+        W()->stemd = stem_s;
+        W()->ref_d = ref_s;
+        W()->dir = dir_s;
+        W()->cur_slot = slot_s;
+        sys.unassign_domain(W()->d);
         rg_restore_endpoints();
         return c_avail;
     }
@@ -2117,13 +2124,13 @@ struct Engine {
     // among all 36 of its own: probability 1 - prod(1 - p') over the feeler slot, independent of the
     // order in which the reference would have tried them.
     LDO_HDN int rg_count_avail_parallel(bool last_level) {
-        const RgSlot& own = M()->slots[cur_slot];
+        const RgSlot& own = M()->slots[W()->cur_slot];
         // feeler availability probability per parent site (warp-uniform)
         double pav[6];
 #pragma unroll 1
         for (int pc = 0; pc < 6; pc++) {
             pav[pc] = -1; // not memoised: needs the general path
-            if (last_level || !((memo_mask >> pc) & 1)) continue;
+            if (last_level || !((W()->memo_mask >> pc) & 1)) continue;
             const RgSlot& sl = M()->slots[LDO_RG_OWN_SLOTS + pc];
             double none = 1.0;
 #pragma unroll 1
@@ -2132,7 +2139,7 @@ struct Engine {
             }
             pav[pc] = 1.0 - none;
         }
-        unsigned long long rem = avail;
+        unsigned long long rem = W()->avail;
         unsigned long long ctr = RNG()->counter;
         int count = 0;
         unsigned lo_mask = 0, hi_mask = 0; // configurations left to the general path
@@ -2182,12 +2189,12 @@ struct Engine {
             int ci = nth_set_bit36(todo, 0);
             todo &= todo - 1;
             int pc = ci / 6, o = ci - 6 * pc;
-            last_pc = pc;
-            last_kind = own.kind[pc];
-            V3 p = ore_vec(pc) + rec_pos(sys.S()->dom[ref_d]);
+            W()->last_pc = pc;
+            W()->last_kind = own.kind[pc];
+            V3 p = ore_vec(pc) + rec_pos(sys.S()->dom[W()->ref_d]);
             count += rg_feeler_general(p, o) ? 1 : 0;
         }
-        avail = 0;
+        W()->avail = 0;
         return count;
     }
     // test_config_avail (rg:422-480) for a single feeler level, replayed on an already computed slot:
@@ -2196,7 +2203,7 @@ struct Engine {
         const RgSlot& sl = M()->slots[slot];
         unsigned long long av = all_cis();
 #pragma unroll 1
-        for (int catt = 0; catt != max_c_attempts; catt++) {
+        for (int catt = 0; catt != W()->max_c_attempts; catt++) {
             int ci = uniform_int(0, popc36(av) - 1);
             int i = nth_set_bit36(av, ci);
             av &= ~(1ull << i);
@@ -2212,31 +2219,31 @@ struct Engine {
     }
     // calc_old_c_opens (rg:482-513)
     LDO_HDN void rg_calc_old_c_opens() {
-        di = 0;
+        W()->di = 0;
         M()->c_opens[0] = 1;
 #pragma unroll 1
-        while (di != M()->n_regrow - 1) {
-            di++;
-            d = M()->regrow[di];
-            M()->c_attempts_q[di] = 1;
-            const DomRec r = C()->oldc[d];
+        while (W()->di != M()->n_regrow - 1) {
+            W()->di++;
+            W()->d = M()->regrow[W()->di];
+            M()->c_attempts_q[W()->di] = 1;
+            const DomRec r = C()->oldc[W()->d];
             V3 p = rec_pos(r);
-            stemd = M()->stem_gp[d] >= 0;
-            M()->c_opens[di] = rg_calc_p_config_open(p, r.ore);
-            rg_set_config(d, p, r.ore);
-            if (stemd) {
-                M()->avail_q[di] = 0;
+            W()->stemd = M()->stem_gp[W()->d] >= 0;
+            M()->c_opens[W()->di] = rg_calc_p_config_open(p, r.ore);
+            rg_set_config(W()->d, p, r.ore);
+            if (W()->stemd) {
+                M()->avail_q[W()->di] = 0;
             }
             else {
-                dir = cp_get_dir(d);
-                ref_d = sys.step(d, -dir);
-                V3 rel = p - rec_pos(C()->oldc[ref_d]);
+                W()->dir = cp_get_dir(W()->d);
+                W()->ref_d = sys.step(W()->d, -W()->dir);
+                V3 rel = p - rec_pos(C()->oldc[W()->ref_d]);
                 int pc = ore_code(rel);
                 int ci = pc * 6 + r.ore;
                 unsigned long long a = all_cis();
                 if (pc < 6 && r.ore >= 0 && r.ore < 6) a &= ~(1ull << ci);
                 else sys.fail(LDO_ERR_INTERNAL, 2); // m_config_to_i.at(c) would throw
-                M()->avail_q[di] = a;
+                M()->avail_q[W()->di] = a;
             }
         }
     }
@@ -2263,12 +2270,12 @@ struct Engine {
             printf("\n");
         }
 #endif
-        delta_e += rg_unassign_and_save_domains();
-        delta_e += rg_recoil_regrow();
+        W()->delta_e += rg_unassign_and_save_domains();
+        W()->delta_e += rg_recoil_regrow();
         if (M()->rejected) return false;
         // excluded staples: the reference hard-codes zero of them (simulation.cpp:410,527)
         update_move_params();
-        delta_e += calc_move_bias();
+        W()->delta_e += calc_move_bias();
 
         // new-configuration weights (setup_for_calc_new_weights, rg:147-153)
         rg_copy_queues_to_wq();
@@ -2286,8 +2293,8 @@ struct Engine {
         if (remove_first_b) cp_remove_active_endpoint(first_dom);
         rg_calc_old_c_opens();
         // setup_for_calc_old_weights (rg:155-163)
-        weight_new = weight;
-        weight = 1;
+        W()->weight_new = W()->weight;
+        W()->weight = 1;
         rg_copy_queues_to_wq();
 #pragma unroll 1
         for (int k = 0; k < M()->n_regrow; k++) C()->newc[M()->regrow[k]] = C()->prev[M()->regrow[k]];
@@ -2298,7 +2305,7 @@ struct Engine {
         rg_calc_weights();
 
         // test_rg_acceptance (rg:515-533)
-        double ratio = weight_new / weight * exp(-delta_e);
+        double ratio = W()->weight_new / W()->weight * exp(-W()->delta_e);
         if (test_acceptance(ratio)) {
 #pragma unroll 1
             for (int k = 0; k < M()->n_regrow; k++) C()->prev[M()->regrow[k]] = C()->newc[M()->regrow[k]];
@@ -2312,15 +2319,15 @@ struct Engine {
 
     LDO_HD void rg_reset(const MoveDef& md) {
         cp_reset();
-        delta_e = 0;
-        weight = 1;
-        weight_new = 1;
-        max_recoils = md.max_num_recoils;
-        max_c_attempts = md.max_c_attempts;
-        memo_level = -1;
-        memo_key = -1;
-        memo_mask = 0;
-        cur_slot = 0;
+        W()->delta_e = 0;
+        W()->weight = 1;
+        W()->weight_new = 1;
+        W()->max_recoils = md.max_num_recoils;
+        W()->max_c_attempts = md.max_c_attempts;
+        W()->memo_level = -1;
+        W()->memo_key = -1;
+        W()->memo_mask = 0;
+        W()->cur_slot = 0;
         M()->eq_depth = 0;
         M()->eq_npos = 0;
     }
@@ -2333,7 +2340,7 @@ struct Engine {
         // setup_constraints (rg:134-145)
 #pragma unroll 1
         for (int k = 0; k < C()->n_sel; k++) C()->in_sel[C()->sel_scaf[k]] = 1;
-        M()->scaf_dir[0] = (int8_t)dir;
+        M()->scaf_dir[0] = (int8_t)W()->dir;
         cp_find_growthpoints_endpoints(C()->sel_scaf, C()->n_sel, 0);
         cp_save_initial();
         int n_scaf = sys.S()->chain_len[0];
@@ -2578,7 +2585,7 @@ struct Engine {
         if (sys.S()->status != LDO_OK) return false;
 #pragma unroll 1
         for (int k = 0; k < C()->n_sel; k++) C()->in_sel[C()->sel_scaf[k]] = 1;
-        M()->scaf_dir[0] = (int8_t)dir;
+        M()->scaf_dir[0] = (int8_t)W()->dir;
         cp_find_growthpoints_endpoints(C()->sel_scaf, C()->n_sel, 0);
         cp_save_initial();
         bool whole = sys.SC().cyclic != 0 && C()->n_sel == sys.S()->chain_len[0];
