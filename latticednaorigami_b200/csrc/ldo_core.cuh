@@ -49,49 +49,86 @@ namespace ldo {
 // Lattice vectors (utility.hpp:66-95, utility.cpp:26-161)
 // ---------------------------------------------------------------------------------------------
 
+// A lattice vector is ONE 32-bit word: x + (y << 11) + (z << 22) in wrap-around (mod 2^32) arithmetic.
+// The map is linear, so sums, differences and negation of vectors are single integer instructions on
+// the packed words and equality is one compare, which is what the potential does almost exclusively;
+// components are extracted only for |.|_1 (ideal-walk counts) and I/O. Positions obey |x|,|y| <= 511 and
+// |z| <= 255 (checked when a domain is placed), so every difference of two positions (|dx|,|dy| <= 1022,
+// |dz| <= 510) still has a unique packed word and unpacks exactly.
 struct V3 {
-    int x, y, z;
+    uint32_t k;
 };
+#define LDO_COORD_MAX_XY 511
+#define LDO_COORD_MAX_Z 255
 
 LDO_HD inline V3 v3(int x, int y, int z) {
     V3 v;
-    v.x = x;
-    v.y = y;
-    v.z = z;
+    v.k = (uint32_t)x + ((uint32_t)y << 11) + ((uint32_t)z << 22);
     return v;
 }
-LDO_HD inline V3 operator+(V3 a, V3 b) { return v3(a.x + b.x, a.y + b.y, a.z + b.z); }
-LDO_HD inline V3 operator-(V3 a, V3 b) { return v3(a.x - b.x, a.y - b.y, a.z - b.z); }
-LDO_HD inline V3 operator-(V3 a) { return v3(-a.x, -a.y, -a.z); }
-LDO_HD inline bool operator==(V3 a, V3 b) { return a.x == b.x && a.y == b.y && a.z == b.z; }
-LDO_HD inline bool operator!=(V3 a, V3 b) { return !(a == b); }
-LDO_HD inline int abssum(V3 a) { return abs(a.x) + abs(a.y) + abs(a.z); }
+LDO_HD inline int vx(V3 v) { return (int)(v.k << 21) >> 21; }
+LDO_HD inline int vy(V3 v) { return (int)((v.k - (uint32_t)vx(v)) << 10) >> 21; }
+LDO_HD inline int vz(V3 v) { return (int)(v.k - (uint32_t)vx(v) - ((uint32_t)vy(v) << 11)) >> 22; }
+LDO_HD inline V3 operator+(V3 a, V3 b) {
+    V3 v;
+    v.k = a.k + b.k;
+    return v;
+}
+LDO_HD inline V3 operator-(V3 a, V3 b) {
+    V3 v;
+    v.k = a.k - b.k;
+    return v;
+}
+LDO_HD inline V3 operator-(V3 a) {
+    V3 v;
+    v.k = 0u - a.k;
+    return v;
+}
+LDO_HD inline bool operator==(V3 a, V3 b) { return a.k == b.k; }
+LDO_HD inline bool operator!=(V3 a, V3 b) { return a.k != b.k; }
+LDO_HD inline int abssum(V3 a) {
+    int x = (int)(a.k << 21) >> 21;
+    uint32_t r = a.k - (uint32_t)x;
+    int y = (int)(r << 10) >> 21;
+    int z = (int)(r - ((uint32_t)y << 11)) >> 22;
+    return abs(x) + abs(y) + abs(z);
+}
+LDO_HD inline bool in_coord_range(V3 p) {
+    return abs(vx(p)) <= LDO_COORD_MAX_XY && abs(vy(p)) <= LDO_COORD_MAX_XY && abs(vz(p)) <= LDO_COORD_MAX_Z;
+}
 
 // Orientation codes index utility::vectors (utility.hpp:156-162): +x,-x,+y,-y,+z,-z; 6 = zero vector
 enum { ORE_ZERO = 6 };
 
 LDO_HD inline V3 ore_vec(int code) {
-    int s = 1 - 2 * (code & 1);
-    int a = code >> 1;
-    return v3(a == 0 ? s : 0, a == 1 ? s : 0, a == 2 ? s : 0);
+    V3 v;
+    uint32_t unit = 1u << (11 * ((code >> 1) & 3)); // axis 0,1,2 -> bit 0, 11, 22
+    v.k = code >= ORE_ZERO ? 0u : ((code & 1) ? 0u - unit : unit);
+    return v;
 }
 
 // Returns 0..5 for unit vectors, ORE_ZERO for (0,0,0), 7 for anything else
 LDO_HD inline int ore_code(V3 v) {
-    if (abssum(v) == 0) return ORE_ZERO;
-    if (abssum(v) != 1) return 7;
-    if (v.x != 0) return v.x > 0 ? 0 : 1;
-    if (v.y != 0) return v.y > 0 ? 2 : 3;
-    return v.z > 0 ? 4 : 5;
+    uint32_t k = v.k, n = 0u - v.k;
+    if (k == 1u) return 0;
+    if (n == 1u) return 1;
+    if (k == (1u << 11)) return 2;
+    if (n == (1u << 11)) return 3;
+    if (k == (1u << 22)) return 4;
+    if (n == (1u << 22)) return 5;
+    return k == 0u ? ORE_ZERO : 7;
 }
 
 // VectorThree::rotate_half (utility.cpp:68-86): only acts when |axis| is a basis vector
 LDO_HD inline V3 rotate_half(V3 v, V3 axis) {
-    int ax = abs(axis.x), ay = abs(axis.y), az = abs(axis.z);
-    if (ax == 1 && ay == 0 && az == 0) return v3(v.x, -v.y, -v.z);
-    if (ax == 0 && ay == 1 && az == 0) return v3(-v.x, v.y, -v.z);
-    if (ax == 0 && ay == 0 && az == 1) return v3(-v.x, -v.y, v.z);
-    return v;
+    int a = ore_code(axis);
+    if (a > 5) return v;
+    int c = ore_code(v);
+    if (c <= 5) return (c >> 1) == (a >> 1) ? v : -v; // unit vector: parallel stays, perpendicular flips
+    int x = vx(v), y = vy(v), z = vz(v);
+    if ((a >> 1) == 0) return v3(x, -y, -z);
+    if ((a >> 1) == 1) return v3(-x, y, -z);
+    return v3(-x, -y, z);
 }
 
 // VectorThree::rotate(axis, turns) (utility.cpp:103-142)
@@ -100,12 +137,13 @@ LDO_HD inline V3 rotate_turns(V3 v, V3 axis, int turns) {
     bool odd_turns_even = ((turns - 1) / 2 % 2 == 0);
     bool turns_neg = turns < 0;
     int dir = (!turns_neg && odd_turns_even) ? 1 : -1;
-    V3 aa = v3(abs(axis.x), abs(axis.y), abs(axis.z));
-    if (axis != aa) dir *= -1;
-    if (aa == v3(1, 0, 0)) return v3(v.x, -dir * v.z, dir * v.y);
-    if (aa == v3(0, 1, 0)) return v3(-dir * v.z, v.y, dir * v.x);
-    if (aa == v3(0, 0, 1)) return v3(-dir * v.y, dir * v.x, v.z);
-    return v;
+    int a = ore_code(axis);
+    if (a > 5) return v;
+    if (a & 1) dir *= -1;
+    int x = vx(v), y = vy(v), z = vz(v);
+    if ((a >> 1) == 0) return v3(x, -dir * z, dir * y);
+    if ((a >> 1) == 1) return v3(-dir * z, y, dir * x);
+    return v3(-dir * y, dir * x, z);
 }
 
 // VectorThree::rotate(origin, axis, turns) (utility.cpp:88-101)
@@ -144,14 +182,19 @@ enum {
     LDO_ERR_INTERNAL = 15
 };
 
-#define LDO_COORD_MAX 511
 
-// One domain: position, orientation code, occupancy state. 8 bytes = one LDS.64.
+// One domain: packed position, orientation code, occupancy state. 8 bytes = one LDS.64.
 struct __attribute__((aligned(8))) DomRec {
-    short x, y, z;
+    uint32_t k; // V3::k
     int8_t ore;
     uint8_t state;
+    uint16_t pad_;
 };
+LDO_HD inline V3 rec_pos(const DomRec& r) {
+    V3 v;
+    v.k = r.k;
+    return v;
+}
 
 // System description shared by every replica (read-only on the device)
 #define LDO_MAX_TYPES 192
@@ -228,7 +271,7 @@ struct Caps {
     static const int H = 1 << HBITS_; // occupancy table slots
 };
 
-#define LDO_HEMPTY 0xFFFFFFFFu
+#define LDO_HEMPTY 0x80000000u // z = -512: outside the coordinate range
 
 // Persistent configuration of one replica
 template <class K>
@@ -264,9 +307,8 @@ struct DeltaConfig {
     bool violated;
 };
 
-LDO_HD inline uint32_t pack_pos(V3 p) {
-    return ((uint32_t)(p.x & 0x3FF) << 20) | ((uint32_t)(p.y & 0x3FF) << 10) | (uint32_t)(p.z & 0x3FF);
-}
+// Table key = the packed position itself
+LDO_HD inline uint32_t pack_pos(V3 p) { return p.k; }
 
 template <class K>
 LDO_HD inline uint32_t hash_slot(uint32_t key) {
@@ -289,7 +331,7 @@ struct System {
     struct Overlay { // 12 bytes: 32 lanes * 3 words hit 32 distinct banks
         short od, oj;
         struct {
-            short x, y, z;
+            uint16_t k_lo, k_hi; // V3::k in two halves (keeps the record 2-byte aligned: 12-byte stride)
             int8_t ore;
             uint8_t state;
         } rec;
@@ -333,14 +375,22 @@ struct System {
     // ---- accessors (overlay aware) ----
     LDO_HD V3 pos(int d) const {
         const Overlay* o = OV();
-        if (d == o->od) return v3(o->rec.x, o->rec.y, o->rec.z);
-        const DomRec& r = S()->dom[d];
-        return v3(r.x, r.y, r.z);
+        if (d == o->od) {
+            V3 v;
+            v.k = (uint32_t)o->rec.k_lo | ((uint32_t)o->rec.k_hi << 16);
+            return v;
+        }
+        return rec_pos(S()->dom[d]);
     }
     LDO_HD V3 ore(int d) const {
         const Overlay* o = OV();
         if (d == o->od) return ore_vec(o->rec.ore);
         return ore_vec(S()->dom[d].ore);
+    }
+    LDO_HD int orc(int d) const { // orientation code 0..6
+        const Overlay* o = OV();
+        if (d == o->od) return o->rec.ore;
+        return S()->dom[d].ore;
     }
     LDO_HD int state(int d) const {
         const Overlay* o = OV();
@@ -412,9 +462,7 @@ struct System {
         return -1;
     }
     LDO_HDN void table_put(V3 p, int d) {
-        if (abs(p.x) > LDO_COORD_MAX || abs(p.y) > LDO_COORD_MAX || abs(p.z) > LDO_COORD_MAX) {
-            fail(LDO_ERR_COORD_RANGE, d);
-        }
+        if (!in_coord_range(p)) fail(LDO_ERR_COORD_RANGE, d);
         uint32_t key = pack_pos(p);
         uint32_t i = hash_slot<K>(key);
 #pragma unroll 1
@@ -463,9 +511,13 @@ struct System {
 
     // ---- domain constraint checkers (domain.cpp:33-118) ----
     LDO_HDN bool check_twist(int d1, V3 ndr, int d2) const {
-        V3 o1 = ore(d1);
-        V3 rot = SC().domain_type == DOMAIN_HALFTURN ? rotate_half(o1, ndr) : rotate_turns(o1, ndr, -1);
-        return rot == ore(d2);
+        if (SC().domain_type == DOMAIN_HALFTURN) {
+            // rotate_half on orientation codes: a unit vector parallel to the axis stays, a perpendicular one flips
+            int a = ore_code(ndr), c1 = orc(d1), c2 = orc(d2);
+            if (a > 5 || c1 >= ORE_ZERO || (c1 >> 1) == (a >> 1)) return c1 == c2;
+            return (c1 ^ 1) == c2;
+        }
+        return rotate_turns(ore(d1), ndr, -1) == ore(d2);
     }
     LDO_HDN bool check_kink(int d1, V3 ndr, int d2) const {
         V3 o1 = ore(d1), o2 = ore(d2);
@@ -1017,7 +1069,8 @@ struct System {
         dc.e = 0;
         dc.stacked = 0;
         dc.violated = false;
-        bool opposing = ore(di) == -ore(dj);
+        int ci = orc(di), cj = orc(dj);
+        bool opposing = ci == (cj < ORE_ZERO ? (cj ^ 1) : cj);
         if (ident(di) == -ident(dj)) {
             // BindingPotential::bind_domains (origami_potential.cpp:131-147)
             if (!opposing) {
@@ -1070,9 +1123,8 @@ struct System {
         Overlay* ov = OV();
         ov->od = (short)d;
         ov->oj = (short)j;
-        ov->rec.x = (short)p.x;
-        ov->rec.y = (short)p.y;
-        ov->rec.z = (short)p.z;
+        ov->rec.k_lo = (uint16_t)(p.k & 0xFFFFu);
+        ov->rec.k_hi = (uint16_t)(p.k >> 16);
         ov->rec.ore = (int8_t)o;
         ov->rec.state = comp ? ST_BOUND : ST_MISBOUND;
         *new_state = ov->rec.state;
@@ -1092,9 +1144,7 @@ struct System {
     // ---- mutation ----
     LDO_HD void write_dom(int d, V3 p, int o) {
         DomRec& r = S()->dom[d];
-        r.x = (short)p.x;
-        r.y = (short)p.y;
-        r.z = (short)p.z;
+        r.k = p.k;
         r.ore = (int8_t)o;
     }
 
@@ -1223,7 +1273,7 @@ struct System {
             S()->dom[d].state = ST_UNASSIGNED;
             S()->dom[j].state = ST_UNBOUND;
             const DomRec& r = S()->dom[d];
-            table_put(v3(r.x, r.y, r.z), j);
+            table_put(rec_pos(r), j);
             if (SC().apply_mean_field_cor && st == ST_BOUND) {
                 if (S()->num_fully_bound_pairs == 0) e -= 2 * log(6.0);
                 else if (S()->num_fully_bound_pairs == 1) e -= log(3.0);
@@ -1231,7 +1281,7 @@ struct System {
         }
         else if (st == ST_UNBOUND) {
             const DomRec& r = S()->dom[d];
-            table_erase(v3(r.x, r.y, r.z));
+            table_erase(rec_pos(r));
             S()->dom[d].state = ST_UNASSIGNED;
         }
         else {
@@ -1272,9 +1322,7 @@ struct System {
 #pragma unroll 1
         for (int i = 0; i < len; i++) {
             int d = base + i;
-            S()->dom[d].x = 0;
-            S()->dom[d].y = 0;
-            S()->dom[d].z = 0;
+            S()->dom[d].k = 0;
             S()->dom[d].ore = ORE_ZERO;
             S()->dom[d].state = ST_UNASSIGNED;
             S()->bound[d] = -1;
@@ -1349,7 +1397,7 @@ struct System {
     // OrigamiSystem::center (origami_system.cpp:553-571)
     LDO_HDN void center(int centering_domain) {
         const DomRec& c0 = S()->dom[chain_base(0) + centering_domain];
-        V3 ref = v3(c0.x, c0.y, c0.z);
+        V3 ref = rec_pos(c0);
         table_clear();
 #pragma unroll 1
         for (int w = 0; w < S()->n_chains; w++) {
@@ -1358,10 +1406,8 @@ struct System {
 #pragma unroll 1
             for (int i = 0; i < S()->chain_len[c]; i++) {
                 DomRec& r = S()->dom[base + i];
-                r.x = (short)(r.x - ref.x);
-                r.y = (short)(r.y - ref.y);
-                r.z = (short)(r.z - ref.z);
-                if (r.state != ST_UNASSIGNED) table_put(v3(r.x, r.y, r.z), base + i);
+                r.k -= ref.k;
+                if (r.state != ST_UNASSIGNED) table_put(rec_pos(r), base + i);
             }
         }
         // a site shared by a bound pair must resolve to a valid occupant: either is fine
@@ -1377,7 +1423,7 @@ struct System {
             for (int i = 0; i < S()->chain_len[c]; i++) {
                 int d = base + i;
                 const DomRec r = S()->dom[d];
-                set_domain_config(d, v3(r.x, r.y, r.z), r.ore);
+                set_domain_config(d, rec_pos(r), r.ore);
                 if (S()->constraints_violated) {
                     fail(LDO_ERR_CONSTRAINTS, d);
                     return false;
@@ -1395,7 +1441,7 @@ struct System {
                 if (n < 0) continue;
                 const DomRec& a = S()->dom[d];
                 const DomRec& b = S()->dom[n];
-                if (abs(b.x - a.x) + abs(b.y - a.y) + abs(b.z - a.z) != 1) {
+                if (abssum(rec_pos(b) - rec_pos(a)) != 1) {
                     fail(LDO_ERR_DISTANCE, d);
                     return false;
                 }

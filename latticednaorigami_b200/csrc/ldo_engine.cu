@@ -259,6 +259,11 @@ LDO_HD void rep_load_config(Engine<K>& eng, const OpArgs& a) {
         int c = s->order[w];
         int base = sys.chain_base(c);
         for (int i = 0; i < s->chain_len[c]; i++) {
+            if (abs(a.cfg_pos[3 * k]) > LDO_COORD_MAX_XY || abs(a.cfg_pos[3 * k + 1]) > LDO_COORD_MAX_XY ||
+                abs(a.cfg_pos[3 * k + 2]) > LDO_COORD_MAX_Z) {
+                sys.fail(LDO_ERR_COORD_RANGE, base + i);
+                return;
+            }
             V3 p = v3(a.cfg_pos[3 * k], a.cfg_pos[3 * k + 1], a.cfg_pos[3 * k + 2]);
             V3 o = v3(a.cfg_ore[3 * k], a.cfg_ore[3 * k + 1], a.cfg_ore[3 * k + 2]);
             int oc = ore_code(o);
@@ -1196,13 +1201,13 @@ struct EngineImpl: EngineBase {
             int base = c == 0 ? 0 : sc.n_scaffold + (c - 1) * sc.lmax;
             for (int i = 0; i < s->chain_len[c]; i++) {
                 const DomRec& r = s->dom[base + i];
-                pos[3 * k] = r.x;
-                pos[3 * k + 1] = r.y;
-                pos[3 * k + 2] = r.z;
+                pos[3 * k] = vx(rec_pos(r));
+                pos[3 * k + 1] = vy(rec_pos(r));
+                pos[3 * k + 2] = vz(rec_pos(r));
                 V3 o = r.ore == ORE_ZERO ? v3(0, 0, 0) : ore_vec(r.ore);
-                ore[3 * k] = o.x;
-                ore[3 * k + 1] = o.y;
-                ore[3 * k + 2] = o.z;
+                ore[3 * k] = vx(o);
+                ore[3 * k + 1] = vy(o);
+                ore[3 * k + 2] = vz(o);
                 st[k] = r.state;
                 int b = s->bound[base + i];
                 if (b >= 0 && r.state != ST_UNASSIGNED && r.state != ST_UNBOUND) {

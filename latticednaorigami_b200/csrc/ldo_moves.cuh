@@ -331,7 +331,7 @@ struct MoveScratch {
     int eq_depth;
     short eq_start[A + 1];
     int eq_npos;
-    short eq_pos[E][3];
+    uint32_t eq_pos[E]; // packed positions (V3::k)
 
     // Constraintpoints
     int8_t seg_of[K::D]; // m_segs (-1 = absent)
@@ -344,9 +344,9 @@ struct MoveScratch {
     short ep_chain[E];
     int8_t ep_seg[E];
     short ep_d[E];
-    short ep_pos[E][3];
+    uint32_t ep_pos[E];
     int n_erased; // m_erased_endpoints
-    short erased_pos[8][3];
+    uint32_t erased_pos[8];
 
     // CTRG trial-configuration caches: own[level % 4] and feeler memo keyed by the parent's site
     RgSlot slots[LDO_RG_SLOTS];
@@ -374,7 +374,7 @@ struct ColdScratch {
     short ep0_chain[E];
     int8_t ep0_seg[E];
     short ep0_d[E];
-    short ep0_pos[E][3];
+    uint32_t ep0_pos[E];
 
     // StapleNetwork scratch (top_constraint_points.hpp:40-108)
     uint8_t net_chain[K::C];
@@ -493,9 +493,6 @@ struct Engine {
         }
         const TapeDraw& t = g->tape[g->tape_pos];
         if (t.kind != 0) {
-#if defined(LDO_DEBUG_SLOTS) && !defined(__CUDA_ARCH__)
-            printf("TAPE MISMATCH at %lld: requested real, tape has int(%d,%d)=%d\n", g->tape_pos, t.lo, t.hi, t.ival);
-#endif
             sys.fail(LDO_ERR_TAPE_MISMATCH, (int)g->tape_pos);
             return 0.5;
         }
@@ -510,9 +507,6 @@ struct Engine {
         }
         const TapeDraw& t = g->tape[g->tape_pos];
         if (t.kind != 1 || t.lo != lo || t.hi != hi) {
-#if defined(LDO_DEBUG_SLOTS) && !defined(__CUDA_ARCH__)
-            printf("TAPE MISMATCH at %lld: requested int(%d,%d), tape has kind %d (%d,%d)\n", g->tape_pos, lo, hi, t.kind, t.lo, t.hi);
-#endif
             sys.fail(LDO_ERR_TAPE_MISMATCH, (int)g->tape_pos);
             return lo;
         }
@@ -661,7 +655,6 @@ struct Engine {
         }
         M()->modified[M()->n_modified++] = (short)dd;
     }
-    LDO_HD V3 rec_pos(const DomRec& r) const { return v3(r.x, r.y, r.z); }
 
     // MCMovetype::reset_origami (movetypes.cpp:53-85)
     LDO_HDN void reset_origami() {
@@ -1167,9 +1160,7 @@ struct Engine {
         M()->ep_chain[e] = (short)sys.chain(dd);
         M()->ep_seg[e] = (int8_t)seg;
         M()->ep_d[e] = (short)sys.dindex(dd);
-        M()->ep_pos[e][0] = (short)p.x;
-        M()->ep_pos[e][1] = (short)p.y;
-        M()->ep_pos[e][2] = (short)p.z;
+        M()->ep_pos[e] = p.k;
     }
     LDO_HD void cp_add_active_endpoint(int dd, V3 p) { cp_add_active_endpoint_seg(dd, p, M()->seg_of[dd]); }
     LDO_HD void cp_erase_ep(int e) {
@@ -1178,9 +1169,7 @@ struct Engine {
             M()->ep_chain[k] = M()->ep_chain[k + 1];
             M()->ep_seg[k] = M()->ep_seg[k + 1];
             M()->ep_d[k] = M()->ep_d[k + 1];
-            M()->ep_pos[k][0] = M()->ep_pos[k + 1][0];
-            M()->ep_pos[k][1] = M()->ep_pos[k + 1][1];
-            M()->ep_pos[k][2] = M()->ep_pos[k + 1][2];
+            M()->ep_pos[k] = M()->ep_pos[k + 1];
         }
         M()->n_ep--;
     }
@@ -1191,9 +1180,7 @@ struct Engine {
             C()->ep0_chain[k] = M()->ep_chain[k];
             C()->ep0_seg[k] = M()->ep_seg[k];
             C()->ep0_d[k] = M()->ep_d[k];
-            C()->ep0_pos[k][0] = M()->ep_pos[k][0];
-            C()->ep0_pos[k][1] = M()->ep_pos[k][1];
-            C()->ep0_pos[k][2] = M()->ep_pos[k][2];
+            C()->ep0_pos[k] = M()->ep_pos[k];
         }
     }
     LDO_HDN void cp_reset_active_endpoints() {
@@ -1203,9 +1190,7 @@ struct Engine {
             M()->ep_chain[k] = C()->ep0_chain[k];
             M()->ep_seg[k] = C()->ep0_seg[k];
             M()->ep_d[k] = C()->ep0_d[k];
-            M()->ep_pos[k][0] = C()->ep0_pos[k][0];
-            M()->ep_pos[k][1] = C()->ep0_pos[k][1];
-            M()->ep_pos[k][2] = C()->ep0_pos[k][2];
+            M()->ep_pos[k] = C()->ep0_pos[k];
         }
     }
     // remove_active_endpoint (:299-320): erased positions are kept in m_erased_endpoints
@@ -1217,9 +1202,7 @@ struct Engine {
         while (k < M()->n_ep) {
             if (M()->ep_chain[k] == c && M()->ep_seg[k] == seg && M()->ep_d[k] == di_) {
                 if (M()->n_erased < 8) {
-                    M()->erased_pos[M()->n_erased][0] = M()->ep_pos[k][0];
-                    M()->erased_pos[M()->n_erased][1] = M()->ep_pos[k][1];
-                    M()->erased_pos[M()->n_erased][2] = M()->ep_pos[k][2];
+                    M()->erased_pos[M()->n_erased] = M()->ep_pos[k];
                     M()->n_erased++;
                 }
                 else {
@@ -1258,8 +1241,7 @@ struct Engine {
         if (ov && ov->rm_chain == c && ov->rm_seg == seg && ov->rm_d == di_) return false;
 #pragma unroll 1
         for (int k = 0; k < M()->n_ep; k++) {
-            if (M()->ep_chain[k] == c && M()->ep_seg[k] == seg && M()->ep_d[k] == di_ && M()->ep_pos[k][0] == p.x &&
-                M()->ep_pos[k][1] == p.y && M()->ep_pos[k][2] == p.z) {
+            if (M()->ep_chain[k] == c && M()->ep_seg[k] == seg && M()->ep_d[k] == di_ && M()->ep_pos[k] == p.k) {
                 return true;
             }
         }
@@ -1291,7 +1273,8 @@ struct Engine {
             if (M()->ep_chain[k] != c || M()->ep_seg[k] != seg) continue;
             if (rm && M()->ep_d[k] == ov->rm_d) continue;
             int steps = cp_remaining_steps(M()->ep_d[k], dd, dir_);
-            V3 ep = v3(M()->ep_pos[k][0], M()->ep_pos[k][1], M()->ep_pos[k][2]);
+            V3 ep;
+            ep.k = M()->ep_pos[k];
             if (no_walks(p, ep, steps)) return false;
         }
         if (ov && ov->add_chain == c && ov->add_seg == seg) {
@@ -1640,9 +1623,7 @@ struct Engine {
         M()->eq_start[M()->eq_depth++] = (short)M()->eq_npos;
 #pragma unroll 1
         for (int k = 0; k < M()->n_erased; k++) {
-            M()->eq_pos[M()->eq_npos][0] = M()->erased_pos[k][0];
-            M()->eq_pos[M()->eq_npos][1] = M()->erased_pos[k][1];
-            M()->eq_pos[M()->eq_npos][2] = M()->erased_pos[k][2];
+            M()->eq_pos[M()->eq_npos] = M()->erased_pos[k];
             M()->eq_npos++;
         }
     }
@@ -1656,7 +1637,7 @@ struct Engine {
         int start = M()->eq_start[--M()->eq_depth];
 #pragma unroll 1
         for (int k = start; k < M()->eq_npos; k++) {
-            cp_add_active_endpoint(W()->d, v3(M()->eq_pos[k][0], M()->eq_pos[k][1], M()->eq_pos[k][2]));
+            cp_add_active_endpoint(W()->d, V3{M()->eq_pos[k]});
         }
         M()->eq_npos = start;
     }
@@ -1872,19 +1853,6 @@ struct Engine {
         double pv = 0;
         if (kind == 1) pv = sl.p[pc];
         else if (kind == 2 && o == sl.ore[pc]) pv = sl.p[pc];
-#if defined(LDO_DEBUG_SLOTS) && !defined(__CUDA_ARCH__)
-        if (getenv("LDO_DEBUG_RG")) printf("  trial di=%d d=(%d %d) ref=(%d %d) ci=%d p=(%d %d %d) o=%d kind=%d pv=%g tape_pos=%lld\n", W()->di, sys.S()->chain_uid[sys.chain(W()->d)], sys.dindex(W()->d), sys.S()->chain_uid[sys.chain(W()->ref_d)], sys.dindex(W()->ref_d), i, p.x, p.y, p.z, o, kind, pv, RNG()->tape_pos);
-        {
-            DomRec saved = sys.S()->dom[W()->d];
-            double pref = rg_calc_p_config_open(p, o);
-            sys.S()->dom[W()->d] = saved;
-            if (pref != pv) {
-#pragma unroll 1
-                for (int q = 0; q < M()->n_ep; q++) printf("   ep chain=%d seg=%d d=%d pos=(%d %d %d)\n", M()->ep_chain[q], M()->ep_seg[q], M()->ep_d[q], M()->ep_pos[q][0], M()->ep_pos[q][1], M()->ep_pos[q][2]);
-                printf("SLOT MISMATCH p=(%d %d %d) di=%d d=%d ci=%d pc=%d o=%d kind=%d slot=%d pv=%g ref=%g stemd=%d memo_level=%d memo_key=%d\n", p.x, p.y, p.z, W()->di, W()->d, i, pc, o, kind, W()->cur_slot, pv, pref, W()->stemd, W()->memo_level, W()->memo_key);
-            }
-        }
-#endif
         return pv;
     }
     // calc_p_config_open (rg:315-343)
@@ -2258,18 +2226,6 @@ struct Engine {
     // Shared tail of the two CTRG scaffold moves (rg:636-689, 810-851). `whole_cyclic`: the
     // endpoint-removal guards evaluated by the caller (App. A2 keeps the contiguous variant's quirk).
     LDO_HDN bool rg_regrow_and_test(bool remove_first_a, bool remove_first_b, int first_dom) {
-#if defined(LDO_DEBUG_SLOTS) && !defined(__CUDA_ARCH__)
-        if (getenv("LDO_DEBUG_RG")) {
-            printf("RG regrow:");
-            for (int k = 0; k < M()->n_regrow; k++) {
-                int dd = M()->regrow[k];
-                printf(" (%d %d s%d d%d)", sys.S()->chain_uid[sys.chain(dd)], sys.dindex(dd), M()->seg_of[dd], cp_get_dir(dd));
-            }
-            printf("\n  ep0:");
-            for (int k = 0; k < C()->n_ep0; k++) printf(" [c%d s%d d%d (%d %d %d)]", sys.S()->chain_uid[C()->ep0_chain[k]], C()->ep0_seg[k], C()->ep0_d[k], C()->ep0_pos[k][0], C()->ep0_pos[k][1], C()->ep0_pos[k][2]);
-            printf("\n");
-        }
-#endif
         W()->delta_e += rg_unassign_and_save_domains();
         W()->delta_e += rg_recoil_regrow();
         if (M()->rejected) return false;
