@@ -231,8 +231,14 @@ __constant__ SysConst ldo_c_sc;
 extern __shared__ __align__(16) unsigned char ldo_smem_raw[];
 #endif
 #if defined(__CUDA_ARCH__) && !defined(LDO_GENERIC_ACCESS)
+// With one warp per block the warp's block starts at the symbol itself: every address is a constant
+#if defined(LDO_BLOCK_WARPS) && LDO_BLOCK_WARPS == 1
+#define LDO_WARP_IN_BLOCK 0u
+#else
+#define LDO_WARP_IN_BLOCK (threadIdx.x >> 5)
+#endif
 #define LDO_SMEM_AT(K, T, offset, fallback) \
-    (K::STAGED ? reinterpret_cast<T*>(ldo_smem_raw + (threadIdx.x >> 5) * SmemLayout<K>::stride + (offset)) : (fallback))
+    (K::STAGED ? reinterpret_cast<T*>(ldo_smem_raw + LDO_WARP_IN_BLOCK * SmemLayout<K>::stride + (offset)) : (fallback))
 #else
 #define LDO_SMEM_AT(K, T, offset, fallback) (fallback)
 #endif

@@ -1134,6 +1134,11 @@ struct EngineImpl: EngineBase {
             int per_sm = 0;
             if (chk(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_exec_staged<K>, wpb * 32, per_warp * wpb))) return fail(dev_err());
             cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device);
+            // profiling knob (profiles/sweep_occupancy.py): fewer resident blocks per SM than fit
+            if (const char* cap = getenv("LDO_MAX_BLOCKS_PER_SM")) {
+                int c = atoi(cap);
+                if (c >= 1 && c < per_sm) per_sm = c;
+            }
             resident_blocks = per_sm * n_sm;
             if (resident_blocks < 1) return fail("staged kernel does not fit on the device");
         }

@@ -32,6 +32,15 @@ struct TapeDraw {
     double real;
 };
 
+#ifndef LDO_PHILOX_BLOCKS
+#define LDO_PHILOX_BLOCKS 8
+#endif
+// LDO_NO_TAPE builds (profiling variants) drop the replay branches from the draw functions
+#ifdef LDO_NO_TAPE
+#define LDO_TAPE_MODE(g) false
+#else
+#define LDO_TAPE_MODE(g) ((g)->tape != nullptr)
+#endif
 struct Rng {
     // replay tape (parity mode) when tape != nullptr
     const TapeDraw* tape;
@@ -42,8 +51,9 @@ struct Rng {
     uint32_t subseq;
     uint32_t stream;
     unsigned long long counter;
-    // unconsumed words of the last Philox block (one block = 4 words: a real takes 2, an int 1)
-    uint32_t buf[4];
+    // unconsumed words of the last refill: LDO_PHILOX_BLOCKS blocks of 4 words, block j computed by lane j
+    // from counter + j (a real takes 2 words, an int 1)
+    uint32_t buf[4 * LDO_PHILOX_BLOCKS];
     int buf_n;
 };
 
@@ -60,9 +70,8 @@ LDO_HD inline void philox_round(uint32_t& c0, uint32_t& c1, uint32_t& c2, uint32
     c3 = lo0;
 }
 
-LDO_HD inline void philox4x32_10(const Rng& r, unsigned long long ctr, uint32_t out[4]) {
-    uint32_t c0 = (uint32_t)ctr, c1 = (uint32_t)(ctr >> 32), c2 = r.subseq, c3 = r.stream;
-    uint32_t k0 = r.key0, k1 = r.key1;
+LDO_HD inline void philox4x32_10(uint32_t k0, uint32_t k1, uint32_t subseq, uint32_t stream, unsigned long long ctr, uint32_t* out) {
+    uint32_t c0 = (uint32_t)ctr, c1 = (uint32_t)(ctr >> 32), c2 = subseq, c3 = stream;
 #pragma unroll 1
     for (int i = 0; i < 10; i++) {
         philox_round(c0, c1, c2, c3, k0, k1);
@@ -73,6 +82,9 @@ LDO_HD inline void philox4x32_10(const Rng& r, unsigned long long ctr, uint32_t 
     out[1] = c1;
     out[2] = c2;
     out[3] = c3;
+}
+LDO_HD inline void philox4x32_10(const Rng& r, unsigned long long ctr, uint32_t* out) {
+    philox4x32_10(r.key0, r.key1, r.subseq, r.stream, ctr, out);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -476,8 +488,13 @@ struct Engine {
     // functions stay a few instructions long inside the trial loops (instruction-cache footprint)
     LDO_HDN void philox_refill() {
         Rng* g = RNG();
-        philox4x32_10(*g, g->counter++, g->buf);
-        g->buf_n = 4;
+        unsigned long long c = g->counter;
+#pragma unroll 1
+        for (int j = LDO_LANE; j < LDO_PHILOX_BLOCKS; j += LDO_NLANES) philox4x32_10(g->key0, g->key1, g->subseq, g->stream, c + j, g->buf + 4 * j);
+        LDO_SYNCWARP();
+        g->counter = c + LDO_PHILOX_BLOCKS;
+        g->buf_n = 4 * LDO_PHILOX_BLOCKS;
+        LDO_SYNCWARP();
     }
     LDO_HD uint32_t next_word() {
         Rng* g = RNG();
@@ -514,7 +531,7 @@ struct Engine {
         return t.ival;
     }
     LDO_HD double uniform_real() {
-        if (RNG()->tape != nullptr) return tape_real();
+        if (LDO_TAPE_MODE(RNG())) return tape_real();
         uint32_t hi = next_word();
         uint32_t lo = next_word();
         unsigned long long u = ((unsigned long long)hi << 32) | lo;
@@ -528,7 +545,7 @@ struct Engine {
         return mm;
     }
     LDO_HD int uniform_int(int lo, int hi) {
-        if (RNG()->tape != nullptr) return tape_int(lo, hi);
+        if (LDO_TAPE_MODE(RNG())) return tape_int(lo, hi);
         uint32_t n = (uint32_t)(hi - lo) + 1u;
         unsigned long long mm = (unsigned long long)next_word() * n;
         if ((uint32_t)mm < n) mm = uniform_int_reject(mm, n);
@@ -1928,7 +1945,7 @@ struct Engine {
         if (feels == W()->max_recoils || W()->di == M()->n_regrow - 1) return true;
         rg_prepare_for_growth();
         bool c_avail = false;
-        if (RNG()->tape == nullptr && W()->max_recoils == 1 && !W()->stemd && W()->d_max_c_attempts == 36) {
+        if (!LDO_TAPE_MODE(RNG()) && W()->max_recoils == 1 && !W()->stemd && W()->d_max_c_attempts == 36) {
             // Philox mode, one exhaustive feeler level: "some configuration opens" has probability
             // 1 - prod(1 - p) whatever the trial order, so one draw replaces up to 36 trials
             const RgSlot& sl = M()->slots[W()->cur_slot];
@@ -2032,7 +2049,7 @@ struct Engine {
                 // examined whatever the order, and its contribution is an independent Bernoulli variable,
                 // so the configurations are spread over the lanes, each with its own Philox block, and the
                 // count is reduced across the warp. Replay (tape) mode keeps the reference's serial order.
-                if (RNG()->tape == nullptr && W()->max_c_attempts == 36 && W()->max_recoils == 1 && catt != W()->max_c_attempts &&
+                if (!LDO_TAPE_MODE(RNG()) && W()->max_c_attempts == 36 && W()->max_recoils == 1 && catt != W()->max_c_attempts &&
                     (last_level || feeler_simple)) {
                     avail_cs += rg_count_avail_parallel(last_level);
                     catt = W()->max_c_attempts;
@@ -2121,10 +2138,9 @@ struct Engine {
             else if (kind == 2 && o == own.ore[pc]) pv = own.p[pc];
             if (pv == 0) continue;
             // private Philox block of this configuration: stream word tagged with the configuration index
-            Rng g = *RNG();
-            g.stream = 0x52470000u + (uint32_t)ci;
+            const Rng* g = RNG();
             uint32_t w[4];
-            philox4x32_10(g, ctr, w);
+            philox4x32_10(g->key0, g->key1, g->subseq, 0x52470000u + (uint32_t)ci, ctr, w);
             double ua = (double)((((unsigned long long)w[0] << 32) | w[1]) >> 11) * (1.0 / 9007199254740992.0);
             double ub = (double)((((unsigned long long)w[2] << 32) | w[3]) >> 11) * (1.0 / 9007199254740992.0);
             if (!(pv == 1.0 || pv > ua)) continue;
@@ -2146,8 +2162,9 @@ struct Engine {
         lo_mask = __reduce_or_sync(0xffffffffu, lo_mask);
         hi_mask = __reduce_or_sync(0xffffffffu, hi_mask);
 #endif
+        // the private blocks live on their own stream words: buffered words of the main stream stay valid
+        LDO_SYNCWARP();
         RNG()->counter = ctr + 1;
-        RNG()->buf_n = 0;
         LDO_SYNCWARP();
         // configurations that bind the parent (at most one orientation per site) go through the real
         // place / feel / take-back path, serially
