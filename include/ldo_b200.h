@@ -33,7 +33,10 @@ enum { /* movetype "type" strings of the moveset JSON (simulation.cpp:283-318) *
     LDO_MT_CTCB_SCAFFOLD_REGROWTH = 4,
     LDO_MT_CTCB_JUMP_SCAFFOLD_REGROWTH = 5,
     LDO_MT_CTRG_SCAFFOLD_REGROWTH = 6,
-    LDO_MT_CTRG_JUMP_SCAFFOLD_REGROWTH = 7
+    LDO_MT_CTRG_JUMP_SCAFFOLD_REGROWTH = 7,
+    LDO_MT_CTCB_LINKER_REGROWTH = 8,           /* transform_movetypes.cpp:859-938 */
+    LDO_MT_CTCB_CLUSTERED_LINKER_REGROWTH = 9, /* same move, ClusteredLinkerRegrowthMCMovetype selection (:607-775) */
+    LDO_MT_CTRG_LINKER_REGROWTH = 10           /* transform_movetypes.cpp:1135-1207 */
 };
 
 enum { /* order parameter "type" strings (order_params.cpp:471-545) */
@@ -88,6 +91,10 @@ typedef struct {
     int max_seg_regrowth;
     int max_num_recoils; /* simulation.cpp:528 */
     int max_c_attempts;  /* simulation.cpp:529 */
+    int max_disp;          /* linker/transform moves, simulation.cpp:453-458 */
+    int max_turns;
+    int max_linker_length;
+    int num_transforms;
     int adaptive_exchange;
     int n_exchange_mults;
     const double* exchange_mults; /* simulation.cpp:349-352 */

@@ -1570,7 +1570,7 @@ int ldo_set_moveset(ldo_engine* e, int n, const ldo_movetype_desc* mts, int allo
     for (int i = 0; i < n; i++) {
         MoveDef& md = ms.mt[i];
         md.type = mts[i].type;
-        if (md.type < 0 || md.type > MT_CTRG_JUMP_SCAFFOLD_REGROWTH) {
+        if (md.type < 0 || md.type > MT_CTRG_LINKER_REGROWTH) {
             return b->fail("movetype not available on device");
         }
         cum += mts[i].freq;
@@ -1579,6 +1579,10 @@ int ldo_set_moveset(ldo_engine* e, int n, const ldo_movetype_desc* mts, int allo
         md.max_seg_regrowth = mts[i].max_seg_regrowth;
         md.max_num_recoils = mts[i].max_num_recoils;
         md.max_c_attempts = mts[i].max_c_attempts;
+        md.max_disp = mts[i].max_disp;
+        md.max_turns = mts[i].max_turns;
+        md.max_linker_length = mts[i].max_linker_length;
+        md.num_transforms = mts[i].num_transforms;
         md.adaptive_exchange = mts[i].adaptive_exchange;
         md.exchange_mults_off = 0;
         if (md.type == MT_MET_STAPLE_EXCHANGE) {
@@ -1592,9 +1596,16 @@ int ldo_set_moveset(ldo_engine* e, int n, const ldo_movetype_desc* mts, int allo
         if ((md.type == MT_CTCB_SCAFFOLD_REGROWTH || md.type == MT_CTCB_JUMP_SCAFFOLD_REGROWTH) && md.max_regrowth < 2) {
             return b->fail("CTCB options out of range (max_regrowth >= 2)");
         }
-        if ((md.type == MT_CTRG_SCAFFOLD_REGROWTH || md.type == MT_CTRG_JUMP_SCAFFOLD_REGROWTH) &&
+        bool linker = md.type == MT_CTCB_LINKER_REGROWTH || md.type == MT_CTCB_CLUSTERED_LINKER_REGROWTH || md.type == MT_CTRG_LINKER_REGROWTH;
+        if (linker && (md.num_transforms < 1 || md.num_transforms > LDO_MAX_TRANSFORMS || md.max_disp < 0 || md.max_turns < 0 ||
+                       md.max_linker_length < 1 || (md.type != MT_CTCB_CLUSTERED_LINKER_REGROWTH && md.max_regrowth < 1) ||
+                       b->shared.sc.n_scaffold < 3)) {
+            return b->fail("linker regrowth options out of range (num_transforms 1..16, max_disp >= 0, max_turns >= 0, max_linker_length >= 1, max_regrowth >= 1, scaffold of 3+ domains)");
+        }
+        if ((md.type == MT_CTRG_SCAFFOLD_REGROWTH || md.type == MT_CTRG_JUMP_SCAFFOLD_REGROWTH || md.type == MT_CTRG_LINKER_REGROWTH) &&
             (md.max_c_attempts < 1 || md.max_c_attempts > 36 || md.max_regrowth < 2 || md.max_num_recoils < 0 ||
-             md.max_num_recoils >= LDO_RG_OWN_SLOTS)) {
+             md.max_num_recoils >= LDO_RG_OWN_SLOTS) && !(md.type == MT_CTRG_LINKER_REGROWTH && md.max_c_attempts >= 1 &&
+             md.max_c_attempts <= 36 && md.max_num_recoils >= 0 && md.max_num_recoils < LDO_RG_OWN_SLOTS)) {
             return b->fail("CTRG options out of range (max_c_attempts 1..36, max_regrowth >= 2, max_num_recoils 0..3)");
         }
     }

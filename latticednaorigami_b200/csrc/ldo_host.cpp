@@ -638,10 +638,24 @@ std::vector<MovetypeSpec> read_movetype_file(std::string const& filename) {
             m.desc.max_regrowth = j["max_regrowth"].as_int();
             m.desc.max_seg_regrowth = j["max_seg_regrowth"].as_int();
         }
-        else if (
-                m.type == "CTCBLinkerRegrowth" || m.type == "CTCBClusteredLinkerRegrowth" ||
-                m.type == "CTRGLinkerRegrowth" || m.type == "CTRGClusteredLinkerRegrowth") {
-            throw NotImplemented {m.type + ": transform/linker movetypes are not available on the device path yet"};
+        else if (m.type == "CTCBLinkerRegrowth" || m.type == "CTCBClusteredLinkerRegrowth" || m.type == "CTRGLinkerRegrowth") {
+            // setup_scaffold_transform_movetype (simulation.cpp:444-513)
+            m.desc.type = m.type == "CTCBLinkerRegrowth" ? LDO_MT_CTCB_LINKER_REGROWTH
+                    : m.type == "CTCBClusteredLinkerRegrowth" ? LDO_MT_CTCB_CLUSTERED_LINKER_REGROWTH : LDO_MT_CTRG_LINKER_REGROWTH;
+            m.desc.max_disp = j["max_disp"].as_int();
+            m.desc.max_turns = j["max_turns"].as_int();
+            m.desc.max_regrowth = j["max_regrowth"].as_int();
+            m.desc.max_linker_length = j["max_linker_length"].as_int();
+            m.desc.num_transforms = j["num_transforms"].as_int();
+            if (m.type == "CTRGLinkerRegrowth") {
+                m.desc.max_num_recoils = j["max_num_recoils"].as_int();
+                m.desc.max_c_attempts = j["max_c_attempts"].as_int();
+            }
+        }
+        else if (m.type == "CTRGClusteredLinkerRegrowth") {
+            // accepted by the reference's type dispatch (simulation.cpp:302) but never constructed
+            // (setup_scaffold_transform_movetype has no case for it and returns a null movetype)
+            throw NotImplemented {m.type + ": the reference does not construct this movetype either"};
         }
         else {
             throw SimulationMisuse {m.type + ": no such movetype"};

@@ -158,14 +158,19 @@ enum {
     MT_CTCB_SCAFFOLD_REGROWTH = 4,
     MT_CTCB_JUMP_SCAFFOLD_REGROWTH = 5,
     MT_CTRG_SCAFFOLD_REGROWTH = 6,
-    MT_CTRG_JUMP_SCAFFOLD_REGROWTH = 7
+    MT_CTRG_JUMP_SCAFFOLD_REGROWTH = 7,
+    MT_CTCB_LINKER_REGROWTH = 8,
+    MT_CTCB_CLUSTERED_LINKER_REGROWTH = 9,
+    MT_CTRG_LINKER_REGROWTH = 10
 };
+#define LDO_MAX_TRANSFORMS 16 // num_transforms capacity of the linker moves
 
 #define LDO_MAX_MOVETYPES 12
 struct MoveDef {
     int type;
     double cum_prob; // m_cumulative_probs (simulation.cpp:233-237)
     int max_regrowth, max_seg_regrowth, max_num_recoils, max_c_attempts;
+    int max_disp, max_turns, max_linker_length, num_transforms; // linker / transform moves
     int adaptive_exchange;
     int exchange_mults_off; // offset into MoveSet::exchange_mults
 };
@@ -406,6 +411,21 @@ struct ColdScratch {
     // CTCB: chains of the internally bound staple networks (m_regrowth_staples) and the growth work stack
     uint8_t regrow_chain[K::C];
     short work[K::LV + 1][4];
+
+    // Linker regrowth (transform_movetypes.hpp:92-100): the two linkers (element 0 = end of the central
+    // segment), their fixed endpoints, the central segment's domains with those of its staples, and the
+    // accepted trial transformations of transform_segment
+    short lnk[2][K::LV + 1];
+    int n_lnk[2];
+    short lnk_ep[2]; // m_linker_endpoints (-1 = none)
+    short cen_dom[K::D + 1]; // central_domains; the first C()->n_sel entries are sel_scaf (central_segment)
+    int n_cen;
+    uint8_t lk_mark[K::D]; // bit 0: in central_segment, bit 1: in central_domains
+    uint8_t cen_chain[K::C]; // central_staples (find_staples)
+    int n_tf;
+    uint32_t tf_center[LDO_MAX_TRANSFORMS], tf_disp[LDO_MAX_TRANSFORMS];
+    int8_t tf_axis[LDO_MAX_TRANSFORMS], tf_turns[LDO_MAX_TRANSFORMS];
+    double tf_bfactor[LDO_MAX_TRANSFORMS];
 };
 
 // Move statistics (MovetypeTracking, movetypes.hpp:49-52)
@@ -1464,15 +1484,16 @@ struct Engine {
     }
 
     // ---- CT selection (movetypes.cpp:469-719) ----
-    // select_indices on the whole scaffold, min_length 2, seg 0
-    LDO_HDN void ct_select_indices(const MoveDef& md) {
+    // select_indices on the whole scaffold, seg 0 (min_length 2 for the scaffold regrowth moves, 1 for
+    // the central segment of the linker moves)
+    LDO_HDN void ct_select_indices(const MoveDef& md, int min_length = 2) {
         SysState<K>* s = sys.S();
         int n = s->chain_len[0];
 #pragma unroll 1
         for (;;) {
             if (s->status != LDO_OK) return;
             int max_length = n < md.max_regrowth ? n : md.max_regrowth;
-            int sel_length = uniform_int(2, max_length);
+            int sel_length = uniform_int(min_length, max_length);
             int start_i = uniform_int(0, n - 1);
             W()->dir = uniform_int(0, 1);
             if (W()->dir == 0) W()->dir = -1;
@@ -1492,7 +1513,7 @@ struct Engine {
                 nb++;
                 back = sys.step(back, -W()->dir);
             }
-            if (nf + nb < 2) continue;
+            if (nf + nb < min_length) continue;
             C()->n_sel = 0;
 #pragma unroll 1
             for (int k = nb - 1; k >= 0; k--) C()->sel_scaf[C()->n_sel++] = buf[K::D + 1 + k];
@@ -1999,6 +2020,10 @@ struct Engine {
             feels--;
             W()->d = M()->regrow[W()->di];
             sys.unassign_domain(W()->d);
+            // The reference leaves these feelers in m_assigned_domains (an unbounded vector); the entries
+            // are dropped here to bound the list. Equivalent: unassigning twice is a no-op
+            // (origami_system.cpp:723-727) and every feeler is also a modified domain.
+            if (M()->n_assigned > 0) M()->n_assigned--;
             rg_restore_endpoints();
         }
         W()->di--;
@@ -2652,6 +2677,558 @@ struct Engine {
         return ctcb_finish(new_bias, bias);
     }
 
+
+    // ---- Linker regrowth: rigid transformation of a scaffold segment with its staples, followed by
+    // regrowth of the two linkers that join it to the rest (transform_movetypes.cpp:14-1213) ----
+
+    // scan_for_external_scaffold_domain (:262-314), iterative; `participating` starts as {scaffold}
+    LDO_HDN bool lk_scan_external(int start) {
+        short (*st)[2] = C()->scan_stack;
+        int sp = 0;
+        st[0][0] = (short)start;
+        st[0][1] = 0;
+        C()->net_chain[sys.chain(start)] = 1;
+#pragma unroll 1
+        while (sp >= 0) {
+            int dom = st[sp][0];
+            int c = sys.chain(dom);
+            int base = sys.chain_base(c);
+            int len = sys.S()->chain_len[c];
+            bool descended = false;
+#pragma unroll 1
+            while (st[sp][1] < len) {
+                int cur = base + st[sp][1];
+                st[sp][1]++;
+                if (cur == dom) continue;
+                int b = sys.S()->bound[cur];
+                if (b < 0) continue;
+                if (sys.chain(b) == c) continue;
+                if (sys.chain(b) == 0) {
+                    if (!(C()->lk_mark[b] & 1)) return true;
+                    continue;
+                }
+                if (C()->net_chain[sys.chain(b)]) continue;
+                if (sp + 1 >= K::C) {
+                    sys.fail(LDO_ERR_CAPACITY, 13);
+                    return true;
+                }
+                C()->net_chain[sys.chain(b)] = 1;
+                sp++;
+                st[sp][0] = (short)b;
+                st[sp][1] = 0;
+                descended = true;
+                break;
+            }
+            if (!descended) sp--;
+        }
+        return false;
+    }
+    // domains_bound_externally (:238-260) on the central segment C()->sel_scaf
+    LDO_HDN bool lk_bound_externally() {
+#pragma unroll 1
+        for (int k = 0; k < K::D; k++) C()->lk_mark[k] = 0;
+#pragma unroll 1
+        for (int k = 0; k < C()->n_sel; k++) C()->lk_mark[C()->sel_scaf[k]] = 1;
+#pragma unroll 1
+        for (int k = 0; k < C()->n_sel; k++) {
+            int dd = C()->sel_scaf[k];
+            if (sys.S()->dom[dd].state == ST_UNBOUND) continue;
+            int b = sys.S()->bound[dd];
+            if (b < 0 || sys.chain(b) == 0) continue;
+#pragma unroll 1
+            for (int q = 0; q < K::C; q++) C()->net_chain[q] = 0;
+            C()->net_chain[0] = 1;
+            if (lk_scan_external(b)) return true;
+        }
+        return false;
+    }
+    // setup_fixed_end_biases (:210-236): terminal constraint points of the two linkers, then
+    // calculate_constraintpoints(linkers without their first domain, {-dir, dir}, {})
+    LDO_HDN void lk_setup_fixed_end_biases() {
+        SysState<K>* s = sys.S();
+        int dir_ = W()->dir;
+#pragma unroll 1
+        for (int q = 0; q < 2; q++) {
+            int last = C()->lnk[q][C()->n_lnk[q] - 1];
+            int ep = sys.step(last, q == 0 ? -dir_ : dir_);
+            C()->lnk_ep[q] = (short)ep;
+            if (ep >= 0) cp_add_active_endpoint_seg(ep, rec_pos(s->dom[ep]), q);
+        }
+#pragma unroll 1
+        for (int q = 0; q < 2; q++) {
+#pragma unroll 1
+            for (int k = 1; k < C()->n_lnk[q]; k++) C()->in_sel[C()->lnk[q][k]] = 1;
+        }
+        // the CTRG variant regrows from the end of the central segment: m_regrow_ds.insert(begin, linker1.front())
+        M()->regrow[0] = C()->lnk[0][0];
+        M()->n_regrow = 1;
+#pragma unroll 1
+        for (int q = 0; q < 2; q++) {
+            if (C()->n_lnk[q] > 1) {
+                M()->scaf_dir[q] = (int8_t)(q == 0 ? -dir_ : dir_);
+                cp_find_growthpoints_endpoints(C()->lnk[q] + 1, C()->n_lnk[q] - 1, q);
+            }
+            else {
+                M()->scaf_dir[q] = 0; // m_domain_to_dir has no entry for an empty segment
+            }
+        }
+        cp_save_initial();
+    }
+    // LinkerRegrowthMCMovetype::select_and_setup_segments (:156-208)
+    LDO_HDN void lk_select_and_setup(const MoveDef& md) {
+        bool externally_bound = true;
+        int attempts = 0;
+#pragma unroll 1
+        while (externally_bound && attempts != 10) {
+            if (sys.S()->status != LDO_OK) return;
+            ct_select_indices(md, 1);
+            int dir_ = W()->dir;
+            int front = C()->sel_scaf[0], back = C()->sel_scaf[C()->n_sel - 1];
+            int l1 = uniform_int(2, md.max_linker_length + 1);
+            int n = 0;
+            int ld = front;
+            int stop = sys.step(back, 2 * dir_);
+#pragma unroll 1
+            while (n != l1 && ld >= 0 && ld != stop) {
+                C()->lnk[0][n++] = (short)ld;
+                ld = sys.step(ld, -dir_);
+            }
+            C()->n_lnk[0] = n;
+            if (sys.SC().cyclic && n == 1) {
+                M()->rejected = 1;
+                return;
+            }
+            int l2 = uniform_int(2, md.max_linker_length + 1);
+            n = 0;
+            ld = back;
+            stop = sys.step(C()->lnk[0][C()->n_lnk[0] - 1], -dir_);
+#pragma unroll 1
+            while (n != l2 && ld >= 0 && ld != stop) {
+                C()->lnk[1][n++] = (short)ld;
+                ld = sys.step(ld, dir_);
+            }
+            C()->n_lnk[1] = n;
+            externally_bound = lk_bound_externally();
+            attempts++;
+        }
+        if (externally_bound) {
+            M()->rejected = 1;
+            return;
+        }
+        lk_setup_fixed_end_biases();
+    }
+    // ClusteredLinkerRegrowthMCMovetype::linear/cyclic_select_central_segment (:671-775): the maximal run
+    // of bound scaffold domains around (or next to) a random kernel domain, into C()->sel_scaf
+    LDO_HDN void lk_select_cluster() {
+        SysState<K>* s = sys.S();
+        bool cyc = sys.SC().cyclic != 0;
+        int n = s->chain_len[0];
+        W()->dir = 1;
+        short* seg = C()->sel_scaf;
+        int m = 0;
+        int kd = sys.chain_base(0) + uniform_int(1, n - 2);
+        bool started = false;
+        if (s->dom[kd].state == ST_BOUND) {
+            started = true;
+            seg[m++] = (short)kd;
+            int p = sys.step(kd, -1);
+#pragma unroll 1
+            while ((cyc || p >= 0) && s->dom[p].state == ST_BOUND && m != n - 1) {
+                seg[m++] = (short)p;
+                p = sys.step(p, -1);
+            }
+        }
+        if (m == n - 1) {
+            C()->n_sel = 0;
+            return;
+        }
+#pragma unroll 1
+        for (int a = 0, b = m - 1; a < b; a++, b--) {
+            short t = seg[a];
+            seg[a] = seg[b];
+            seg[b] = t;
+        }
+        int nd = sys.step(kd, 1);
+        bool ended = false;
+#pragma unroll 1
+        while (!ended && (cyc ? nd != kd : nd >= 0)) {
+            bool bnd = s->dom[nd].state == ST_BOUND;
+            if (bnd) {
+                started = true;
+                if (m < K::D) seg[m++] = (short)nd;
+            }
+            else if (started) {
+                ended = true;
+            }
+            nd = sys.step(nd, 1);
+        }
+        if (!cyc) {
+            nd = sys.step(kd, -1);
+            if (!started) {
+#pragma unroll 1
+                while (!ended && nd >= 0) {
+                    bool bnd = s->dom[nd].state == ST_BOUND;
+                    if (bnd) {
+                        started = true;
+                        seg[m++] = (short)nd;
+                    }
+                    else if (started) {
+                        ended = true;
+                    }
+                    nd = sys.step(nd, -1);
+                }
+#pragma unroll 1
+                for (int a = 0, b = m - 1; a < b; a++, b--) {
+                    short t = seg[a];
+                    seg[a] = seg[b];
+                    seg[b] = t;
+                }
+            }
+        }
+        C()->n_sel = m;
+    }
+    // ClusteredLinkerRegrowthMCMovetype::select_and_setup_segments (:607-669)
+    LDO_HDN void lk_select_and_setup_clustered(const MoveDef& md) {
+        SysState<K>* s = sys.S();
+        bool externally_bound = true;
+        int attempts = 0;
+#pragma unroll 1
+        while (externally_bound && attempts != 10) {
+            if (s->status != LDO_OK) return;
+            lk_select_cluster();
+            if (C()->n_sel == 0) {
+                M()->rejected = 1;
+                return;
+            }
+            externally_bound = lk_bound_externally();
+            attempts++;
+        }
+        if (externally_bound) {
+            M()->rejected = 1;
+            return;
+        }
+        int front = C()->sel_scaf[0], back = C()->sel_scaf[C()->n_sel - 1];
+        int n = 0;
+        C()->lnk[0][n++] = (short)front;
+        int p = sys.step(front, -1);
+        if (p != back && p != sys.step(back, 1)) {
+            int stop = sys.step(back, 2);
+#pragma unroll 1
+            while (p >= 0 && s->dom[p].state != ST_BOUND && n != md.max_linker_length && p != stop) {
+                C()->lnk[0][n++] = (short)p;
+                p = sys.step(p, -1);
+            }
+        }
+        C()->n_lnk[0] = n;
+        if (n == 1) {
+            M()->rejected = 1;
+            return;
+        }
+        n = 0;
+        C()->lnk[1][n++] = (short)back;
+        int nd = sys.step(back, 1);
+        if (nd != C()->lnk[0][C()->n_lnk[0] - 1]) {
+            int stop = sys.step(C()->lnk[0][C()->n_lnk[0] - 1], -1);
+#pragma unroll 1
+            while (nd >= 0 && s->dom[nd].state != ST_BOUND && n != md.max_linker_length && nd != stop) {
+                C()->lnk[1][n++] = (short)nd;
+                nd = sys.step(nd, 1);
+            }
+        }
+        C()->n_lnk[1] = n;
+        lk_setup_fixed_end_biases();
+    }
+    // central_domains = central_segment + the domains of find_staples(central_segment) in ascending
+    // unique chain index (movetypes.cpp:179-189; transform_movetypes.cpp:871-878)
+    LDO_HDN void lk_find_central_domains() {
+        SysState<K>* s = sys.S();
+#pragma unroll 1
+        for (int q = 0; q < K::C; q++) C()->cen_chain[q] = 0;
+        int m = 0;
+#pragma unroll 1
+        for (int k = 0; k < C()->n_sel; k++) {
+            int dd = C()->sel_scaf[k];
+            C()->cen_dom[m++] = (short)dd;
+            int b = s->bound[dd];
+            if (b >= 0 && sys.chain(b) != 0) scan_for_scaffold_domain(b, C()->cen_chain);
+        }
+        int last_uid = -1;
+#pragma unroll 1
+        for (;;) {
+            int best = -1, best_uid = 0x7fffffff;
+#pragma unroll 1
+            for (int c = 1; c < K::C; c++) {
+                if (!C()->cen_chain[c]) continue;
+                int uid = s->chain_uid[c];
+                if (uid > last_uid && uid < best_uid) {
+                    best = c;
+                    best_uid = uid;
+                }
+            }
+            if (best < 0) break;
+            last_uid = best_uid;
+            int base = sys.chain_base(best);
+#pragma unroll 1
+            for (int k = 0; k < s->chain_len[best]; k++) {
+                if (m >= K::D) {
+                    sys.fail(LDO_ERR_CAPACITY, 14);
+                    return;
+                }
+                C()->cen_dom[m++] = (short)(base + k);
+            }
+        }
+        C()->n_cen = m;
+#pragma unroll 1
+        for (int k = 0; k < m; k++) C()->lk_mark[C()->cen_dom[k]] |= 2;
+    }
+    // CBMCMovetype::unassign_domains / CTRGRegrowthMCMovetype::unassign_and_save_domains(domains) on the
+    // central domains (cb_movetypes.cpp:200-213, rg_movetypes.cpp:109-123)
+    LDO_HDN void lk_unassign_central() {
+#pragma unroll 1
+        for (int k = 0; k < C()->n_cen; k++) {
+            int dd = C()->cen_dom[k];
+            C()->prev[dd] = sys.S()->dom[dd];
+            push_modified(dd);
+            sys.unassign_domain(dd);
+        }
+    }
+    // reset_segment (:145-154)
+    LDO_HD void lk_reset_segment(int last_di) {
+#pragma unroll 1
+        for (int di = 0; di < last_di; di++) {
+            sys.unassign_domain(C()->cen_dom[di]);
+            if (M()->n_assigned > 0) M()->n_assigned--;
+        }
+    }
+    // apply_transformation (:401-465): rotation about `center` by `turns` quarter turns around basis
+    // vector `axis_i`, then translation by `disp`, of the configuration saved in m_prev_pos / m_prev_ore
+    LDO_HDN double lk_apply_transformation(V3 disp, V3 center, int axis_i, int turns) {
+        SysState<K>* s = sys.S();
+        V3 axis = ore_vec(2 * axis_i);
+        double bfactor = 1;
+        double delta_e = 0;
+#pragma unroll 1
+        for (int di = 0; di < C()->n_cen; di++) {
+            int dd = C()->cen_dom[di];
+            const DomRec& r = C()->prev[dd];
+            V3 pos = rotate_about(rec_pos(r), center, axis, turns) + disp;
+            int o = ore_code(rotate_about(ore_vec(r.ore), v3(0, 0, 0), axis, turns));
+            if (!in_coord_range(pos)) {
+                sys.fail(LDO_ERR_COORD_RANGE, dd);
+                return 0;
+            }
+            int j = sys.occupant(pos);
+            if (j >= 0) {
+                if (s->dom[j].state != ST_UNBOUND) {
+                    lk_reset_segment(di);
+                    bfactor = 0;
+                    break;
+                }
+                bool scaffold_misbinding = sys.chain(dd) == 0 && sys.chain(j) == 0;
+                bool new_binding_pair = !(C()->lk_mark[j] & 2);
+                if (!scaffold_misbinding && new_binding_pair) {
+                    lk_reset_segment(di);
+                    bfactor = 0;
+                    break;
+                }
+                else if (scaffold_misbinding && new_binding_pair) {
+                    sys.check_domain_constraints(dd, pos, o);
+                    if (s->constraints_violated) {
+                        bfactor = 0;
+                        s->constraints_violated = 0;
+                        lk_reset_segment(di);
+                        break;
+                    }
+                }
+            }
+            delta_e += sys.set_checked_domain_config(dd, pos, o);
+            push_assigned(dd);
+        }
+        if (bfactor != 0) bfactor = exp(-delta_e);
+        return bfactor;
+    }
+    // steps_less_than_distance (:524-545)
+    LDO_HD bool lk_steps_less_than_distance() const {
+        const SysState<K>* s = sys.S();
+        int dist[2];
+#pragma unroll 1
+        for (int q = 0; q < 2; q++) {
+            int ep = C()->lnk_ep[q];
+            dist[q] = ep >= 0 ? abssum(rec_pos(s->dom[C()->lnk[q][0]]) - rec_pos(s->dom[ep])) : 0;
+        }
+        return !(dist[0] <= C()->n_lnk[0] && dist[1] <= C()->n_lnk[1]);
+    }
+    // One trial transformation (:329-366, repeated verbatim at :474-506): draws centre, axis, turns and
+    // displacement, applies it and takes it back; returns its Boltzmann factor, 0 when it cannot be used
+    LDO_HDN double lk_trial_transformation(const MoveDef& md, V3& center, int& axis_i, int& turns, V3& disp) {
+        int center_di = uniform_int(0, C()->n_sel - 1);
+        center = rec_pos(C()->prev[C()->sel_scaf[center_di]]);
+        axis_i = uniform_int(0, 2);
+        turns = uniform_int(0, md.max_turns);
+        int dx = uniform_int(-md.max_disp, md.max_disp);
+        int dy = uniform_int(-md.max_disp, md.max_disp);
+        int dz = uniform_int(-md.max_disp, md.max_disp);
+        disp = v3(dx, dy, dz);
+        double bfactor = lk_apply_transformation(disp, center, axis_i, turns);
+        if (bfactor != 0) {
+            if (lk_steps_less_than_distance()) bfactor = 0;
+            lk_reset_segment(C()->n_cen);
+        }
+        return bfactor;
+    }
+    // transform_segment (:316-399): modified Rosenbluth choice among m_k trial transformations
+    LDO_HDN double lk_transform_segment(const MoveDef& md) {
+        C()->n_tf = 0;
+#pragma unroll 1
+        for (int k_i = 0; k_i != md.num_transforms; k_i++) {
+            if (sys.S()->status != LDO_OK) return 0;
+            V3 center, disp;
+            int axis_i, turns;
+            // a transformation that fits but leaves too few linker steps is dropped (:358-366) ...
+            double applied = lk_trial_transformation(md, center, axis_i, turns, disp);
+            if (applied != 0) {
+                int t = C()->n_tf++;
+                C()->tf_center[t] = center.k;
+                C()->tf_disp[t] = disp.k;
+                C()->tf_axis[t] = (int8_t)axis_i;
+                C()->tf_turns[t] = (int8_t)turns;
+                C()->tf_bfactor[t] = applied;
+            }
+        }
+        double bias = 0;
+#pragma unroll 1
+        for (int t = 0; t < C()->n_tf; t++) bias += C()->tf_bfactor[t];
+        if (bias == 0) {
+            M()->rejected = 1;
+        }
+        else {
+            double random_real = bias * uniform_real();
+            double cum = 0;
+            int sel = 0;
+#pragma unroll 1
+            for (;;) {
+                cum += C()->tf_bfactor[sel];
+                if (random_real < cum || sel == C()->n_tf - 1) break; // the reference runs off the end here
+                sel++;
+            }
+            V3 center, disp;
+            center.k = C()->tf_center[sel];
+            disp.k = C()->tf_disp[sel];
+            lk_apply_transformation(disp, center, C()->tf_axis[sel], C()->tf_turns[sel]);
+        }
+        return bias;
+    }
+    // revert_transformation (:467-522): m_k - 1 further trial transformations (of the configuration
+    // m_prev_pos holds at that point), then the old configuration, whose domains enter one by one (sic)
+    LDO_HDN double lk_revert_transformation(const MoveDef& md) {
+        double bias = 0;
+#pragma unroll 1
+        for (int k_i = 0; k_i != md.num_transforms - 1; k_i++) {
+            if (sys.S()->status != LDO_OK) return 1;
+            V3 center, disp;
+            int axis_i, turns;
+            bias += lk_trial_transformation(md, center, axis_i, turns, disp);
+        }
+#pragma unroll 1
+        for (int k = 0; k < C()->n_cen; k++) {
+            int dd = C()->cen_dom[k];
+            const DomRec& r = C()->oldc[dd];
+            double de = sys.set_checked_domain_config(dd, rec_pos(r), r.ore);
+            bias += exp(-de);
+            push_assigned(dd);
+        }
+        return bias;
+    }
+    // CTCBLinkerRegrowthMCMovetype::internal_attempt_move (:859-938); the clustered variant differs in
+    // the selection only
+    LDO_HDN bool move_ctcb_linker(const MoveDef& md, bool clustered) {
+        cp_reset();
+        if (clustered) lk_select_and_setup_clustered(md);
+        else lk_select_and_setup(md);
+        if (M()->rejected || sys.S()->status != LDO_OK) return false;
+        lk_find_central_domains();
+        DD bias = dd_from(1.0), new_bias = dd_from(1.0);
+#pragma unroll 1
+        for (int pass = 0; pass < 2; pass++) {
+            bool regrow_old = pass == 1;
+            if (regrow_old) {
+                update_move_params();
+                bias = dd_mul(bias, exp(-calc_move_bias()));
+                ctcb_setup_regrow_old(bias, new_bias);
+            }
+            ctcb_unassign(C()->lnk[0] + 1, C()->n_lnk[0] - 1, false);
+            ctcb_unassign(C()->lnk[1] + 1, C()->n_lnk[1] - 1, true);
+            lk_unassign_central();
+            bias = dd_mul(bias, regrow_old ? lk_revert_transformation(md) : lk_transform_segment(md));
+            if (sys.S()->status != LDO_OK) return false;
+            if (M()->rejected && !regrow_old) return false;
+#pragma unroll 1
+            for (int q = 0; q < 2; q++) {
+                ctcb_grow_list(C()->lnk[q], C()->n_lnk[q], regrow_old, bias);
+                if (M()->rejected && !regrow_old) return false;
+            }
+        }
+        return ctcb_finish(new_bias, bias);
+    }
+    // CTRGLinkerRegrowthMCMovetype::internal_attempt_move (:1135-1207)
+    LDO_HDN bool move_ctrg_linker(const MoveDef& md) {
+        rg_reset(md);
+        lk_select_and_setup(md);
+        if (M()->rejected || sys.S()->status != LDO_OK) return false;
+        lk_find_central_domains();
+        if (M()->n_regrow < 2) {
+            // both linkers empty: the reference indexes m_regrow_ds[1] past its end here
+            sys.fail(LDO_ERR_INTERNAL, 3);
+            return false;
+        }
+        W()->delta_e += rg_unassign_and_save_domains();
+        lk_unassign_central();
+        W()->weight *= lk_transform_segment(md);
+        if (M()->rejected || sys.S()->status != LDO_OK) return false;
+        W()->delta_e += rg_recoil_regrow();
+        if (M()->rejected) return false;
+        update_move_params();
+        W()->delta_e += calc_move_bias();
+
+        // new-configuration weights
+        rg_copy_queues_to_wq();
+#pragma unroll 1
+        for (int k = 0; k < K::D; k++) C()->oldc[k] = C()->prev[k];
+        M()->n_modified = 0;
+        rg_unassign_and_save_domains();
+        cp_reset_active_endpoints();
+        rg_calc_weights();
+
+        // old-configuration weights
+        rg_unassign_domains();
+        lk_unassign_central();
+        W()->weight /= lk_revert_transformation(md);
+        cp_reset_active_endpoints();
+        rg_calc_old_c_opens();
+        W()->weight_new = W()->weight;
+        W()->weight = 1;
+        rg_copy_queues_to_wq();
+#pragma unroll 1
+        for (int k = 0; k < K::D; k++) C()->newc[k] = C()->prev[k];
+        M()->n_modified = 0;
+        rg_unassign_and_save_domains();
+#pragma unroll 1
+        for (int k = 0; k < C()->n_cen; k++) push_modified(C()->cen_dom[k]);
+        cp_reset_active_endpoints();
+        rg_calc_weights();
+
+        double ratio = W()->weight_new / W()->weight * exp(-W()->delta_e);
+        if (test_acceptance(ratio)) {
+#pragma unroll 1
+            for (int k = 0; k < K::D; k++) C()->prev[k] = C()->newc[k];
+            reset_origami();
+            return true;
+        }
+        M()->n_modified = 0;
+        M()->n_assigned = 0;
+        return false;
+    }
+
     // ---- one Monte Carlo step (simulation.cpp:568-596, 655-665) ----
     LDO_HD int select_movetype() {
         double prob = uniform_real();
@@ -2677,6 +3254,9 @@ struct Engine {
         case MT_CTCB_JUMP_SCAFFOLD_REGROWTH: accepted = move_ctcb_jump_scaffold(md); break;
         case MT_CTRG_SCAFFOLD_REGROWTH: accepted = move_ctrg_scaffold(md); break;
         case MT_CTRG_JUMP_SCAFFOLD_REGROWTH: accepted = move_ctrg_jump_scaffold(md); break;
+        case MT_CTCB_LINKER_REGROWTH: accepted = move_ctcb_linker(md, false); break;
+        case MT_CTCB_CLUSTERED_LINKER_REGROWTH: accepted = move_ctcb_linker(md, true); break;
+        case MT_CTRG_LINKER_REGROWTH: accepted = move_ctrg_linker(md); break;
         default: sys.fail(LDO_ERR_INTERNAL, 100 + md.type); break;
         }
         if (sys.S()->status != LDO_OK) return false;

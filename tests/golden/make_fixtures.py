@@ -5,6 +5,8 @@ Run in the build container only (needs /root/reference and oracle/_ref):
 
 inputs/            the reference's example systems / movesets / order-parameter / bias / windows files
                    (data, re-serialised), so that nothing at test time reads /root/reference
+inputs/moveset_linker.json, inputs/moveset_linker_heavy.json  hand-written (not from the reference): movesets with the
+                   three transform / linker movetypes, option names as read by simulation.cpp:444-513
 inputs/moveset_ctcb.json  hand-written (not from the reference): the standard moveset with the two CTRG scaffold moves
                    replaced by CTCBScaffoldRegrowth / CTCBJumpScaffoldRegrowth, same schema as examples/moveset_standard.json
 replay_*.npz       value-level RNG tapes recorded from the UNMODIFIED reference (oracle/_ref) with the
@@ -146,17 +148,27 @@ def enumeration_fixture():
         f.write("\n")
 
 
+REPLAYS = {
+    "four_unbound_340K": (("four_unbound.json", "moveset_four.json"), dict(temp=340, max_total_staples=2, max_type_staples=2), 7, 50, 24),
+    "snodin_assembled_330K": (("snodin_assembled.json", "moveset_standard.json"), dict(temp=330), 11, 8, 5),
+    "snodin_unbound_335K": (("snodin_unbound.json", "moveset_standard.json"), dict(temp=335), 5, 50, 6),
+    "snodin_assembled_ctcb_332K": (("snodin_assembled.json", "moveset_ctcb.json"), dict(temp=332), 13, 50, 8),
+    "snodin_unbound_ctcb_334K": (("snodin_unbound.json", "moveset_ctcb.json"), dict(temp=334), 17, 60, 6),
+    # inputs/moveset_linker*.json are hand-written (the reference ships no moveset with the transform /
+    # linker movetypes): CTCBLinkerRegrowth, CTCBClusteredLinkerRegrowth, CTRGLinkerRegrowth
+    "snodin_assembled_linker_341K": (("snodin_assembled.json", "moveset_linker_heavy.json"), dict(temp=341), 16, 50, 8),
+    "snodin_unbound_linker_336K": (("snodin_unbound.json", "moveset_linker.json"), dict(temp=336), 15, 60, 8),
+}
+
 if __name__ == "__main__":
-    copy_inputs()
-    energies_fixture()
-    record_replay("four_unbound_340K", opts("four_unbound.json", "moveset_four.json", temp=340, max_total_staples=2,
-                                            max_type_staples=2), seed=7, chunk=50, n_chunks=24)
-    record_replay("snodin_assembled_330K", opts("snodin_assembled.json", "moveset_standard.json", temp=330), seed=11,
-                  chunk=8, n_chunks=5)
-    record_replay("snodin_unbound_335K", opts("snodin_unbound.json", "moveset_standard.json", temp=335), seed=5,
-                  chunk=50, n_chunks=6)
-    record_replay("snodin_assembled_ctcb_332K", opts("snodin_assembled.json", "moveset_ctcb.json", temp=332), seed=13,
-                  chunk=50, n_chunks=8)
-    record_replay("snodin_unbound_ctcb_334K", opts("snodin_unbound.json", "moveset_ctcb.json", temp=334), seed=17,
-                  chunk=60, n_chunks=6)
-    enumeration_fixture()
+    # python tests/golden/make_fixtures.py [replay names...]: with names, only those replays are re-recorded
+    only = sys.argv[1:]
+    if not only:
+        copy_inputs()
+        energies_fixture()
+    for name, (files, kw, seed, chunk, n_chunks) in REPLAYS.items():
+        if only and name not in only:
+            continue
+        record_replay(name, opts(*files, **kw), seed=seed, chunk=chunk, n_chunks=n_chunks)
+    if not only:
+        enumeration_fixture()

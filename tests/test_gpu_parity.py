@@ -15,7 +15,8 @@ pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.parametrize("name", ["four_unbound_340K", "snodin_assembled_330K", "snodin_unbound_335K",
-                                  "snodin_assembled_ctcb_332K", "snodin_unbound_ctcb_334K"])
+                                  "snodin_assembled_ctcb_332K", "snodin_unbound_ctcb_334K",
+                                  "snodin_assembled_linker_341K", "snodin_unbound_linker_336K"])
 def test_replay_fixture_bit_exact(tmp_path, name):
     fx = np.load(os.path.join(GOLDEN, f"replay_{name}.npz"))
     sim = Simulation(write_inp(str(tmp_path / "r.inp"), options_from_fixture(fx)), 5, 0)

@@ -12,7 +12,8 @@ from latticednaorigami_b200.binding import Simulation
 
 
 @pytest.mark.parametrize("name", ["four_unbound_340K", "snodin_assembled_330K", "snodin_unbound_335K",
-                                  "snodin_assembled_ctcb_332K", "snodin_unbound_ctcb_334K"])
+                                  "snodin_assembled_ctcb_332K", "snodin_unbound_ctcb_334K",
+                                  "snodin_assembled_linker_341K", "snodin_unbound_linker_336K"])
 def test_replay_fixture(hostsim_lib, tmp_path, name):
     fx = np.load(os.path.join(GOLDEN, f"replay_{name}.npz"))
     inp = write_inp(str(tmp_path / "r.inp"), options_from_fixture(fx))

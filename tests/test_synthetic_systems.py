@@ -68,6 +68,41 @@ def test_ctcb_moves_on_synthetic_systems_hostsim(hostsim_lib, oracle, tmp_path):
             hostsim_lib, seed=53, steps=200)
 
 
+def _linker_cases(tmp_path):
+    """Transform / linker movetypes (CTCBLinkerRegrowth, CTCBClusteredLinkerRegrowth, CTRGLinkerRegrowth) on
+    partially assembled rasters, where the clustered selection finds bound runs: ThreeQuarterTurn and
+    HalfTurn domains, linear and cyclic scaffolds, both hand-written movesets (one with two recoil levels)."""
+    for k, ms in enumerate(["moveset_linker.json", "moveset_linker_heavy.json"]):
+        path = os.path.join(INPUTS, ms)
+        for cyclic in (False, True):
+            yield _options(tmp_path, 3, 4, temp=300, max_total=8, cyclic=cyclic, movetype_file=path), 60 + 4 * k + int(cyclic)
+            yield _options(tmp_path, 3, 4, temp=310, max_total=8, cyclic=cyclic, movetype_file=path, domain_type="HalfTurn"), 62 + 4 * k + int(cyclic)
+
+
+def test_linker_moves_on_synthetic_systems_hostsim(hostsim_lib, oracle, tmp_path):
+    accepts = np.zeros(3, dtype=np.int64)
+    for opts, seed in _linker_cases(tmp_path):
+        r, sim = _replay(oracle, opts, tmp_path, hostsim_lib, seed=seed, steps=800)
+        att, acc = sim.engine.move_stats()
+        accepts += acc[0][-3:]
+    assert np.all(accepts > 0)  # every linker movetype was accepted somewhere: the whole move ran
+    _replay(oracle, _options(tmp_path, 12, 14, temp=295, max_total=168, staple_M=1e-3,
+                             movetype_file=os.path.join(INPUTS, "moveset_linker.json")), tmp_path, hostsim_lib, seed=71, steps=200)
+
+
+@pytest.mark.gpu
+def test_linker_moves_on_synthetic_systems_gpu(oracle, tmp_path):
+    accepts = np.zeros(3, dtype=np.int64)
+    for opts, seed in _linker_cases(tmp_path):
+        r, sim = _replay(oracle, opts, tmp_path, None, seed=seed + 100, steps=1200)
+        att, acc = sim.engine.move_stats()
+        accepts += acc[0][-3:]
+    assert np.all(accepts > 0)
+    # the large (in-place, HBM-resident) instantiation
+    _replay(oracle, _options(tmp_path, 12, 14, temp=295, max_total=168, staple_M=1e-3,
+                             movetype_file=os.path.join(INPUTS, "moveset_linker.json")), tmp_path, None, seed=171, steps=200)
+
+
 @pytest.mark.gpu
 def test_ctcb_moves_on_synthetic_systems_gpu(oracle, tmp_path):
     ctcb = os.path.join(INPUTS, "moveset_ctcb.json")
