@@ -429,7 +429,17 @@ struct System {
         return -1;
     }
     // Domain::operator+ (domain.cpp:9-31)
+#ifdef LDO_INLINE_STEP
+    // single steps (nearly every call) inline; the multi-step walk stays out of line
+    LDO_HD int step(int d, int incr) const {
+        if (incr == 1) return d >= 0 ? fwd(d) : d;
+        if (incr == -1) return d >= 0 ? bac(d) : d;
+        return step_n(d, incr);
+    }
+    LDO_HDN int step_n(int d, int incr) const {
+#else
     LDO_HDN int step(int d, int incr) const {
+#endif
 #pragma unroll 1
         while (incr > 0 && d >= 0) {
             d = fwd(d);

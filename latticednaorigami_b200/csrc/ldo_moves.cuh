@@ -1915,6 +1915,120 @@ struct Engine {
         if (p == 1) return true;
         return p > uniform_real();
     }
+    // Open probability of trial configuration ci according to the current slot (what rg_trial returns)
+    LDO_HD double rg_slot_p(const RgSlot& sl, int ci) const {
+        int pc = ci / 6, o = ci - 6 * pc;
+        int kind = sl.kind[pc];
+        if (kind == 1) return sl.p[pc];
+        if (kind == 2 && o == sl.ore[pc]) return sl.p[pc];
+        return 0;
+    }
+    // The trial loop of recoil_regrow (rg:193-198) in production (Philox) mode with exhaustive trials
+    // (max_c_attempts == 36, so the attempts left always equal the configurations left). The loop tries
+    // the untried configurations in a uniformly random order until one opens; its outcome is
+    //   * "none opens, all tried" without any draw when no untried configuration has p > 0 (the common
+    //     dead end on a crowded lattice, which the serial loop pays up to 36 iterations for);
+    //   * otherwise the first open configuration in a random order: every untried configuration gets an
+    //     i.i.d. random key (its place in the order) and an independent Bernoulli(p) outcome, both from
+    //     a private Philox block of its lane; the winner is the open configuration with the smallest
+    //     key, c_attempts advances by the number of keys not above it and those configurations leave
+    //     the untried set. Same distribution as the serial loop, different stream consumption.
+    // When most untried configurations can open the serial loop ends after a draw or two and is kept.
+    // Returns whether a configuration opened.
+    LDO_HDN bool rg_select_open_config(V3& p, int& o, double& p_c_open) {
+        const RgSlot& sl = M()->slots[W()->cur_slot];
+        unsigned long long rem = W()->avail;
+        int n_rem = popc36(rem);
+        // untried configurations that can open: 6 per empty site with a walk left, 1 per bindable site
+        int n_pos = 0;
+#pragma unroll 1
+        for (int pc = 0; pc < 6; pc++) {
+            if (sl.kind[pc] == 0 || !(sl.p[pc] > 0)) continue;
+            unsigned site = (unsigned)(rem >> (6 * pc)) & 63u;
+            if (sl.kind[pc] == 1) n_pos += popc36(site);
+            else n_pos += (site >> sl.ore[pc]) & 1u;
+        }
+        if (n_pos == 0) {
+            W()->c_attempts += n_rem;
+            W()->avail = 0;
+            W()->last_pc = -1;
+            W()->last_kind = 0;
+            return false;
+        }
+        if (4 * n_pos >= n_rem) {
+            bool c_open = false;
+#pragma unroll 1
+            while (!c_open && W()->c_attempts != W()->d_max_c_attempts) {
+                W()->c_attempts++;
+                p_c_open = rg_trial(p, o);
+                c_open = rg_test_config_open(p_c_open);
+            }
+            return c_open;
+        }
+        // lane L owns configurations L and L + 32; words 0,1 / 2,3 of its block: key and Bernoulli draw
+        const int PER = (36 + LDO_NLANES - 1) / LDO_NLANES;
+        uint32_t key[PER];
+        unsigned long long ctr = RNG()->counter;
+        uint32_t best = 0xffffffffu; // smallest key of an open configuration of this lane, low 6 bits = ci
+        int slot_i = 0;
+        const Rng* g = RNG();
+#if defined(__CUDA_ARCH__)
+        uint32_t w[4];
+        philox4x32_10(g->key0, g->key1, g->subseq, 0x54520000u + (uint32_t)LDO_LANE, ctr, w);
+#endif
+#pragma unroll 1
+        for (int ci = LDO_LANE; ci < 36; ci += LDO_NLANES, slot_i++) {
+            key[slot_i] = 0xffffffffu;
+            if (!((rem >> ci) & 1ull)) continue;
+#if !defined(__CUDA_ARCH__)
+            uint32_t w[4];
+            philox4x32_10(g->key0, g->key1, g->subseq, 0x54520000u + (uint32_t)(ci & 31), ctr, w);
+#endif
+            uint32_t k = ((ci < 32 ? w[0] : w[2]) & ~63u) | (uint32_t)ci;
+            if (k == 0xffffffffu) k -= 64u;
+            key[slot_i] = k;
+            double pv = rg_slot_p(sl, ci);
+            double u = (double)(ci < 32 ? w[1] : w[3]) * (1.0 / 4294967296.0);
+            if (pv > 0 && (pv == 1.0 || pv > u) && k < best) best = k;
+        }
+#if defined(__CUDA_ARCH__)
+        best = __reduce_min_sync(0xffffffffu, best);
+#endif
+        // configurations tried up to and including the winner (all of them when none opened)
+        int tried = 0;
+        unsigned lo_mask = 0, hi_mask = 0;
+        slot_i = 0;
+#pragma unroll 1
+        for (int ci = LDO_LANE; ci < 36; ci += LDO_NLANES, slot_i++) {
+            if (key[slot_i] == 0xffffffffu || key[slot_i] > best) continue;
+            tried++;
+            if (ci < 32) lo_mask |= 1u << ci;
+            else hi_mask |= 1u << (ci - 32);
+        }
+#if defined(__CUDA_ARCH__)
+        tried = __reduce_add_sync(0xffffffffu, tried);
+        lo_mask = __reduce_or_sync(0xffffffffu, lo_mask);
+        hi_mask = __reduce_or_sync(0xffffffffu, hi_mask);
+#endif
+        LDO_SYNCWARP();
+        RNG()->counter = ctr + 1;
+        W()->c_attempts += tried;
+        W()->avail = rem & ~(((unsigned long long)hi_mask << 32) | lo_mask);
+        LDO_SYNCWARP();
+        if (best == 0xffffffffu) {
+            W()->last_pc = -1;
+            W()->last_kind = 0;
+            return false;
+        }
+        int ci = (int)(best & 63u);
+        int pc = ci / 6;
+        o = ci - 6 * pc;
+        p = ore_vec(pc) + rec_pos(sys.S()->dom[W()->ref_d]);
+        W()->last_pc = pc;
+        W()->last_kind = sl.kind[pc];
+        p_c_open = sl.p[pc];
+        return true;
+    }
     // recoil_regrow (rg:177-231)
     LDO_HDN double rg_recoil_regrow() {
         double de = 0;
@@ -1934,11 +2048,16 @@ struct Engine {
             int o = 0;
             double p_c_open = 0;
             bool c_open = false;
+            if (!LDO_TAPE_MODE(RNG()) && !W()->stemd && W()->d_max_c_attempts == 36) {
+                c_open = rg_select_open_config(p, o, p_c_open);
+            }
+            else {
 #pragma unroll 1
-            while (!c_open && W()->c_attempts != W()->d_max_c_attempts) {
-                W()->c_attempts++;
-                p_c_open = rg_trial(p, o);
-                c_open = rg_test_config_open(p_c_open);
+                while (!c_open && W()->c_attempts != W()->d_max_c_attempts) {
+                    W()->c_attempts++;
+                    p_c_open = rg_trial(p, o);
+                    c_open = rg_test_config_open(p_c_open);
+                }
             }
             if (c_open) {
                 if (recoils != 0) recoils--;
