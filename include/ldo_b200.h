@@ -61,7 +61,8 @@ enum { /* replica exchange variants (ptmc_simulation.cpp:595-680) */
     LDO_PT_T = 0,   /* t_parallel_tempering   : temperature                        */
     LDO_PT_UT = 1,  /* ut_parallel_tempering  : temperature + staple chem. pot.    */
     LDO_PT_HUT = 2, /* hut_parallel_tempering : + bias multiplier                  */
-    LDO_PT_ST = 3   /* st_parallel_tempering  : stacking multiplier                */
+    LDO_PT_ST = 3,  /* st_parallel_tempering  : stacking multiplier                */
+    LDO_PT_2D = 4   /* 2d_parallel_tempering  : temperature x stacking multiplier (ldo_exchange_pt_2d) */
 };
 
 /* ---- descriptors -------------------------------------------------------------------------- */
@@ -265,6 +266,15 @@ int ldo_exchange_collect(ldo_engine* e, double* dependent_local);
 int ldo_exchange_pt(ldo_engine* e, int variant, long long swap_i, int n_ladders, int ladder_len,
                     int rank, int n_ranks, const double* dependent,
                     int* slot_to_replica, long long* attempts, long long* accepts);
+/* Replaces: TwoDPTGCMCSimulation::attempt_exchange (ptmc_simulation.cpp:495-560): the slots of a ladder form a
+ * [v1_dim temperatures][v2_dim stacking multipliers] grid, slot (i, j) = i * v2_dim + j as the reference
+ * numbers its ranks (:454-471); round swap_i tests the pair set swap_i % 4 (T direction even / stacking
+ * direction even / T odd / stacking odd, ptmc_simulation.hpp:158-164). The ladder set with
+ * ldo_set_exchange_ladder has v1_dim * v2_dim slots. attempts / accepts are [n_ladders][2][v1_dim][v2_dim]
+ * (m_attempt_count / m_swap_count, first index = direction). Sharding as ldo_exchange_pt. */
+int ldo_exchange_pt_2d(ldo_engine* e, long long swap_i, int n_ladders, int v1_dim, int v2_dim,
+                       int rank, int n_ranks, const double* dependent,
+                       int* slot_to_replica, long long* attempts, long long* accepts);
 /* Replaces: PTMWUSGCMCSimulation::attempt_exchange (us_simulation.cpp:770-864) over n_ladders independent
  * ladders of n_windows umbrella windows (replica l * n_windows + k starts in window k). Neighbouring
  * windows swap when both current grid points lie inside both windows, with probability

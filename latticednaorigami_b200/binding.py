@@ -18,7 +18,7 @@ ENGINE_SYMBOLS = [
     "ldo_get_state", "ldo_run", "ldo_get_status", "ldo_run_async", "ldo_synchronize", "ldo_stream",
     "ldo_get_energies", "ldo_get_counters", "ldo_get_staple_counts", "ldo_get_order_params",
     "ldo_get_move_stats", "ldo_get_run_timing", "ldo_recompute_energies", "ldo_check_all_constraints", "ldo_center",
-    "ldo_set_exchange_ladder", "ldo_exchange_collect", "ldo_exchange_pt", "ldo_exchange_buffers",
+    "ldo_set_exchange_ladder", "ldo_exchange_collect", "ldo_exchange_pt", "ldo_exchange_pt_2d", "ldo_exchange_buffers",
     "ldo_exchange_windows", "ldo_launch_count", "ldo_state_bytes", "ldo_checkpoint_size", "ldo_checkpoint_save", "ldo_checkpoint_load",
 ]
 HOST_SYMBOLS = [
@@ -95,6 +95,7 @@ def load(path=None):
         "ldo_set_exchange_ladder": (i, [vp, i, vp, vp, vp, vp]),
         "ldo_exchange_collect": (i, [vp, vp]),
         "ldo_exchange_pt": (i, [vp, i, ll, i, i, i, i, vp, vp, vp, vp]),
+        "ldo_exchange_pt_2d": (i, [vp, ll, i, i, i, i, i, vp, vp, vp, vp]),
         "ldo_exchange_buffers": (i, [vp, i, vp, vp, vp]),
         "ldo_exchange_windows": (i, [vp, ll, i, i, i, i, vp, vp, vp, vp]),
         "ldo_launch_count": (ll, [vp]),
@@ -379,10 +380,13 @@ class Simulation:
         dep = None if dependent_all is None else np.ascontiguousarray(dependent_all, dtype=np.float64)
         self._check(self.L.ldo_sim_exchange_apply(self.h, int(swap_i), _ptr(dep)))
 
-    def exchange_state(self, n_ladders, num_reps):
+    def exchange_state(self, n_ladders, num_reps, two_d=False):
+        """slot -> replica map and the swap counters: [n_ladders][num_reps - 1] for the 1-D variants,
+        [n_ladders][2][num_reps] (direction, slot) for 2d_parallel_tempering."""
         q = np.zeros((n_ladders, num_reps), dtype=np.int32)
-        a = np.zeros((n_ladders, num_reps - 1), dtype=np.int64)
-        b = np.zeros((n_ladders, num_reps - 1), dtype=np.int64)
+        shape = (n_ladders, 2, num_reps) if two_d else (n_ladders, num_reps - 1)
+        a = np.zeros(shape, dtype=np.int64)
+        b = np.zeros(shape, dtype=np.int64)
         self.L.ldo_sim_exchange_state(self.h, _ptr(q), _ptr(a), _ptr(b))
         return q, a, b
 

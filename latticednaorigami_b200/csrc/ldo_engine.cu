@@ -597,6 +597,7 @@ __global__ void __launch_bounds__(128) k_exec_inplace(DevPtrs<K> P, OpArgs a, in
 
 struct ExchangeArgs {
     int variant;
+    int v2_dim; // 2-D exchange (LDO_PT_2D): slots form a [ladder_len / v2_dim][v2_dim] grid; 0 otherwise
     long long swap_i;
     int n_ladders, ladder_len;
     int rank, n_ranks, n_local, n_global;
@@ -631,19 +632,19 @@ LDO_HD inline size_t exchange_gathered_index(const ExchangeArgs& x, int l, int k
     return (size_t)exchange_rank_of(x, k) * x.n_local + exchange_local_index(x, l, k);
 }
 
-LDO_HD inline void exchange_ladder(const ExchangeArgs& x, int l) {
+// Swap test of the slots si, sj of ladder l (calc_acceptance_p + test_acceptance, ptmc_simulation.cpp:255-313);
+// `counter` indexes attempts / accepts
+LDO_HD inline void exchange_pair(const ExchangeArgs& x, int l, int* q2r, int i, int j, size_t counter) {
     int nq = 3 + x.n_staple_types;
-    int* q2r = x.slot_to_replica + (size_t)l * x.ladder_len;
-    int swap_set = (int)(x.swap_i % 2);
-    for (int i = swap_set; i < x.ladder_len - 1; i += 2) {
-        size_t si = (size_t)i;
-        x.attempts[(size_t)l * (x.ladder_len - 1) + i]++;
-        int rep1 = q2r[i], rep2 = q2r[i + 1];
+    {
+        size_t si = (size_t)i, sj = (size_t)j;
+        x.attempts[counter]++;
+        int rep1 = q2r[i], rep2 = q2r[j];
         const double* d1 = x.dependent + exchange_gathered_index(x, l, rep1) * nq;
         const double* d2 = x.dependent + exchange_gathered_index(x, l, rep2) * nq;
-        double temp1 = x.slot_temp[si], temp2 = x.slot_temp[si + 1];
-        double sm1 = x.slot_stacking_mult[si], sm2 = x.slot_stacking_mult[si + 1];
-        double um1 = x.slot_staple_u_mult[si], um2 = x.slot_staple_u_mult[si + 1];
+        double temp1 = x.slot_temp[si], temp2 = x.slot_temp[sj];
+        double sm1 = x.slot_stacking_mult[si], sm2 = x.slot_stacking_mult[sj];
+        double um1 = x.slot_staple_u_mult[si], um2 = x.slot_staple_u_mult[sj];
         // calc_acceptance_p (ptmc_simulation.cpp:275-313); the staple sum runs over the n_types - 1
         // staple identities (the reference's loop bound reads one past the end, App. A1)
         double DBU_DN = 0;
@@ -677,9 +678,36 @@ LDO_HD inline void exchange_ladder(const ExchangeArgs& x, int l) {
             accept = p_accept > prob;
         }
         if (accept) {
-            x.accepts[(size_t)l * (x.ladder_len - 1) + i]++;
+            x.accepts[counter]++;
             q2r[i] = rep2;
-            q2r[i + 1] = rep1;
+            q2r[j] = rep1;
+        }
+    }
+}
+
+LDO_HD inline void exchange_ladder(const ExchangeArgs& x, int l) {
+    int* q2r = x.slot_to_replica + (size_t)l * x.ladder_len;
+    if (x.variant == LDO_PT_2D) {
+        // TwoDPTGCMCSimulation::attempt_exchange (ptmc_simulation.cpp:495-560): slot (i, j) = i * v2 + j with
+        // i the temperature index and j the stacking-multiplier index; four alternating pair sets
+        // (ptmc_simulation.hpp:158-164); counters are [swap_i % 2][i][j]
+        int v2 = x.v2_dim, v1 = x.ladder_len / x.v2_dim;
+        int set = (int)(x.swap_i % 4), swap_v = (int)(x.swap_i % 2);
+        int i_start = set == 2 ? 1 : 0, j_start = set == 3 ? 1 : 0;
+        int i_incr = (set & 1) ? 1 : 2, j_incr = (set & 1) ? 2 : 1;
+        int i_end = (set & 1) ? v1 : v1 - 1, j_end = (set & 1) ? v2 - 1 : v2;
+        int rep_incr = (set & 1) ? 1 : v2;
+        for (int i = i_start; i < i_end; i += i_incr) {
+            for (int j = j_start; j < j_end; j += j_incr) {
+                int a = i * v2 + j;
+                exchange_pair(x, l, q2r, a, a + rep_incr, ((size_t)l * 2 + swap_v) * x.ladder_len + a);
+            }
+        }
+    }
+    else {
+        int swap_set = (int)(x.swap_i % 2);
+        for (int i = swap_set; i < x.ladder_len - 1; i += 2) {
+            exchange_pair(x, l, q2r, i, i + 1, (size_t)l * (x.ladder_len - 1) + i);
         }
     }
     // master_send (ptmc_simulation.cpp:212-226): every replica receives the control variables of its slot
@@ -692,6 +720,13 @@ LDO_HD inline void exchange_ladder(const ExchangeArgs& x, int l) {
             c.temp_idx = x.slot_temp_idx[si];
             c.temp = x.slot_temp[si];
             c.stacking_mult = x.slot_stacking_mult[si];
+        }
+        else if (x.variant == LDO_PT_2D) {
+            // TwoDPTGCMCSimulation::update_control_qs (ptmc_simulation.cpp:595-601)
+            c.temp_idx = x.slot_temp_idx[si];
+            c.temp = x.slot_temp[si];
+            c.stacking_mult = x.slot_stacking_mult[si];
+            c.staple_u_mult = x.slot_staple_u_mult[si];
         }
         else {
             c.temp_idx = x.slot_temp_idx[si];
@@ -1399,9 +1434,9 @@ struct EngineImpl: EngineBase {
     // slot control variables are passed through x.slot_* as HOST arrays by the caller
     int exchange(ExchangeArgs& x, const double* dependent_host, int* slot_to_replica, long long* attempts, long long* accepts) override {
         int n_slots = x.n_ladders * x.ladder_len;
-        int n_pairs = x.n_ladders * (x.ladder_len - 1);
+        int n_pairs = x.variant == LDO_PT_2D ? 2 * n_slots : x.n_ladders * (x.ladder_len - 1);
         int nq = 3 + x.n_staple_types;
-        if (ensure_exchange(x.n_global, n_slots)) return -1;
+        if (ensure_exchange(x.n_global, 2 * n_slots)) return -1;
         if (dependent_host) {
             if (dev_h2d(d_dep_all, dependent_host, sizeof(double) * nq * x.n_global, stream)) return fail(dev_err());
         }
@@ -1973,9 +2008,27 @@ int ldo_set_exchange_ladder(ldo_engine* e, int ladder_len, const int* temp_idx, 
     return 0;
 }
 
+static int exchange_pt_impl(ldo_engine* e, int variant, int v2_dim, long long swap_i, int n_ladders, int ladder_len, int rank,
+                            int n_ranks, const double* dependent, int* slot_to_replica, long long* attempts,
+                            long long* accepts);
+
 int ldo_exchange_pt(ldo_engine* e, int variant, long long swap_i, int n_ladders, int ladder_len, int rank,
                     int n_ranks, const double* dependent, int* slot_to_replica, long long* attempts,
                     long long* accepts) {
+    if (variant < LDO_PT_T || variant > LDO_PT_ST) return e->b->fail("ldo_exchange_pt: 1-D variants only (see ldo_exchange_pt_2d)");
+    return exchange_pt_impl(e, variant, 0, swap_i, n_ladders, ladder_len, rank, n_ranks, dependent, slot_to_replica, attempts, accepts);
+}
+
+int ldo_exchange_pt_2d(ldo_engine* e, long long swap_i, int n_ladders, int v1_dim, int v2_dim, int rank,
+                       int n_ranks, const double* dependent, int* slot_to_replica, long long* attempts,
+                       long long* accepts) {
+    if (v1_dim < 1 || v2_dim < 1) return e->b->fail("ldo_exchange_pt_2d: bad grid");
+    return exchange_pt_impl(e, LDO_PT_2D, v2_dim, swap_i, n_ladders, v1_dim * v2_dim, rank, n_ranks, dependent, slot_to_replica, attempts, accepts);
+}
+
+static int exchange_pt_impl(ldo_engine* e, int variant, int v2_dim, long long swap_i, int n_ladders, int ladder_len, int rank,
+                            int n_ranks, const double* dependent, int* slot_to_replica, long long* attempts,
+                            long long* accepts) {
     EngineBase* b = e->b;
     if ((int)b->ladder_temp_idx.size() != ladder_len) return b->fail("ldo_set_exchange_ladder not called for this ladder length");
     if (n_ranks < 1 || rank < 0 || rank >= n_ranks || ladder_len % n_ranks != 0) return b->fail("ladder_len must be a multiple of n_ranks");
@@ -1986,6 +2039,7 @@ int ldo_exchange_pt(ldo_engine* e, int variant, long long swap_i, int n_ladders,
     ExchangeArgs x;
     memset(&x, 0, sizeof(x));
     x.variant = variant;
+    x.v2_dim = v2_dim;
     x.swap_i = swap_i;
     x.n_ladders = n_ladders;
     x.ladder_len = ladder_len;

@@ -42,6 +42,7 @@ struct ldo_sim {
     long long step {0};
     bool is_pt {false};
     int pt_variant {LDO_PT_T};
+    int v1_dim {0}, v2_dim {0}; // 2d_parallel_tempering: temperatures x stacking multipliers
     int num_reps {1};
     int n_ladders {1};
     std::vector<int> q2r;
@@ -662,6 +663,22 @@ ldo_sim* ldo_sim_create(const char* inp_path, int n_replicas, int device, int ra
             s->n_ladders = n_replicas / (s->num_reps / s->n_ranks);
             s->temps = p.m_temps;
         }
+        else if (st == "2d_parallel_tempering") {
+            // TwoDPTGCMCSimulation (ptmc_simulation.cpp:428-493): replica (rank) v1_i * v2_dim + v2_i runs at
+            // temps[v1_i] with stacking_mults[v2_i]
+            s->is_pt = true;
+            s->pt_variant = LDO_PT_2D;
+            s->v1_dim = static_cast<int>(p.m_temps.size());
+            s->v2_dim = static_cast<int>(p.m_stacking_mults.size());
+            if (s->v1_dim < 1 || s->v2_dim < 1) throw SimulationMisuse {"2d_parallel_tempering needs temps and stacking_mults"};
+            s->num_reps = s->v1_dim * s->v2_dim;
+            if (s->num_reps % s->n_ranks != 0) throw SimulationMisuse {"temps x stacking_mults must be a multiple of the number of ranks"};
+            if (n_replicas % (s->num_reps / s->n_ranks) != 0) {
+                throw SimulationMisuse {"replicas per rank must be a multiple of (temps x stacking_mults) / ranks"};
+            }
+            s->n_ladders = n_replicas / (s->num_reps / s->n_ranks);
+            s->temps = p.m_temps;
+        }
         else {
             throw NotImplemented {st + ": simulation type not available on the device path"};
         }
@@ -761,11 +778,20 @@ ldo_sim* ldo_sim_create(const char* inp_path, int n_replicas, int device, int ra
             smm.resize(s->num_reps, 1.0);
             std::vector<int> ladder_ti(s->num_reps);
             for (int k {0}; k != s->num_reps; k++) ladder_ti[k] = k;
+            if (s->pt_variant == LDO_PT_2D) {
+                // initialize_control_qs (ptmc_simulation.cpp:454-493)
+                for (int k {0}; k != s->num_reps; k++) {
+                    ladder_ti[k] = k / s->v2_dim;
+                    cm[k] = p.m_staple_u_mult;
+                    bmm[k] = 1;
+                    smm[k] = p.m_stacking_mults[k % s->v2_dim];
+                }
+            }
             s->check(ldo_set_exchange_ladder(s->eng, s->num_reps, ladder_ti.data(), cm.data(), bmm.data(), smm.data()));
             int slots_per_rank {s->num_reps / s->n_ranks};
             for (int r {0}; r != n_replicas; r++) {
                 int k {s->rank + (r % slots_per_rank) * s->n_ranks};
-                ti[r] = k;
+                ti[r] = ladder_ti[k];
                 um[r] = cm[k];
                 // OneDPTGCMCSimulation::initialize_control_qs stores the bias multiplier in the wrong
                 // slot (App. A17); with the shipped all-ones multipliers both readings coincide
@@ -775,8 +801,10 @@ ldo_sim* ldo_sim_create(const char* inp_path, int n_replicas, int device, int ra
             s->q2r.resize(static_cast<size_t>(s->n_ladders) * s->num_reps);
             for (int l {0}; l != s->n_ladders; l++)
                 for (int k {0}; k != s->num_reps; k++) s->q2r[static_cast<size_t>(l) * s->num_reps + k] = k;
-            s->attempts.assign(static_cast<size_t>(s->n_ladders) * (s->num_reps - 1), 0);
-            s->accepts.assign(static_cast<size_t>(s->n_ladders) * (s->num_reps - 1), 0);
+            // 1-D: one counter per neighbour pair; 2-D: [direction][v1][v2] (m_attempt_count, ptmc_simulation.cpp:438-443)
+            size_t n_counters {s->pt_variant == LDO_PT_2D ? 2 * static_cast<size_t>(s->num_reps) : static_cast<size_t>(s->num_reps - 1)};
+            s->attempts.assign(static_cast<size_t>(s->n_ladders) * n_counters, 0);
+            s->accepts.assign(static_cast<size_t>(s->n_ladders) * n_counters, 0);
         }
         s->check(ldo_set_control(s->eng, 0, n_replicas, ti.data(), um.data(), bm.data(), sm.data()));
 
@@ -850,9 +878,16 @@ int ldo_sim_exchange_advance(ldo_sim* s) {
 
 int ldo_sim_exchange_apply(ldo_sim* s, long long swap_i, const double* dependent_all) {
     try {
-        s->check(ldo_exchange_pt(
-                s->eng, s->pt_variant, swap_i, s->n_ladders, s->num_reps, s->rank, s->n_ranks,
-                dependent_all, s->q2r.data(), s->attempts.data(), s->accepts.data()));
+        if (s->pt_variant == LDO_PT_2D) {
+            s->check(ldo_exchange_pt_2d(
+                    s->eng, swap_i, s->n_ladders, s->v1_dim, s->v2_dim, s->rank, s->n_ranks,
+                    dependent_all, s->q2r.data(), s->attempts.data(), s->accepts.data()));
+        }
+        else {
+            s->check(ldo_exchange_pt(
+                    s->eng, s->pt_variant, swap_i, s->n_ladders, s->num_reps, s->rank, s->n_ranks,
+                    dependent_all, s->q2r.data(), s->attempts.data(), s->accepts.data()));
+        }
     } catch (std::exception const& e) {
         g_host_error = e.what();
         return -1;
@@ -897,6 +932,11 @@ int ldo_sim_run(ldo_sim* s) {
                 bmm.resize(s->num_reps, 1.0);
                 smm.resize(s->num_reps, 1.0);
                 for (int k {0}; k != s->num_reps; k++) {
+                    if (s->pt_variant == LDO_PT_2D) {
+                        // m_exchange_q_is = {temp, staple_u_mult, stacking_mult} (ptmc_simulation.cpp:446-448)
+                        swp << p.m_temps[k / s->v2_dim] << "/" << p.m_staple_u_mult << "/" << p.m_stacking_mults[k % s->v2_dim] << "/ ";
+                        continue;
+                    }
                     swp << p.m_temps[k] << "/";
                     if (s->pt_variant == LDO_PT_UT || s->pt_variant == LDO_PT_HUT) swp << cm[k] << "/";
                     if (s->pt_variant == LDO_PT_HUT) swp << bmm[k] << "/";
@@ -924,8 +964,26 @@ int ldo_sim_run(ldo_sim* s) {
                 if (ldo_sim_exchange_apply(s, swap_i, nullptr) != 0) throw std::runtime_error(g_host_error);
             }
             write_swap_entry(s->step);
+            if (s->pt_variant == LDO_PT_2D) {
+                // TwoDPTGCMCSimulation::write_acceptance_freqs (ptmc_simulation.cpp:562-593), first ladder
+                int v1 {s->v1_dim}, v2 {s->v2_dim};
+                for (int a {0}; a != v1 - 1; a++)
+                    for (int b {0}; b != v2; b++) {
+                        long long sw {s->accepts[a * v2 + b]}, at {s->attempts[a * v2 + b]};
+                        std::cout << p.m_temps[a] << " " << p.m_temps[a + 1] << " " << p.m_stacking_mults[b] << " " << sw << " " << at
+                                  << " " << static_cast<double>(sw) / at << " \n";
+                    }
+                std::cout << "\n";
+                for (int b {0}; b != v2 - 1; b++)
+                    for (int a {0}; a != v1; a++) {
+                        long long sw {s->accepts[v1 * v2 + a * v2 + b]}, at {s->attempts[v1 * v2 + a * v2 + b]};
+                        std::cout << p.m_stacking_mults[b] << " " << p.m_stacking_mults[b + 1] << " " << p.m_temps[a] << " " << sw << " "
+                                  << at << " " << static_cast<double>(sw) / at << " \n";
+                    }
+                std::cout << "\n";
+            }
             // write_acceptance_freqs (ptmc_simulation.cpp:414-426), first ladder
-            for (int i {0}; i + 1 < s->num_reps; i++) {
+            for (int i {0}; s->pt_variant != LDO_PT_2D && i + 1 < s->num_reps; i++) {
                 std::cout << p.m_temps[i] << " " << p.m_temps[i + 1] << " " << s->accepts[i] << " " << s->attempts[i] << " "
                           << static_cast<double>(s->accepts[i]) / s->attempts[i] << " \n";
             }

@@ -114,3 +114,79 @@ def test_two_rank_exchange_matches_single_rank(hostsim_lib, tmp_path):
         for k in range(L):
             got = outs[k % 2]["energy"][l * S + k // 2]
             assert np.array_equal(got, e1[l, k]), (l, k)
+
+
+def _two_d_exchange_rule(lib, tmp_path):
+    """2d_parallel_tempering (TwoDPTGCMCSimulation, ptmc_simulation.cpp:428-601): temperatures x stacking
+    multipliers, four alternating pair sets; decisions checked against a numpy restatement of
+    calc_acceptance_p and of the pair schedule (ptmc_simulation.hpp:158-164)."""
+    temps, smults = [330.0, 334.0, 338.0], [1.0, 0.8]
+    v1, v2 = len(temps), len(smults)
+    L = v1 * v2
+    n_ladders = 5
+    opts = make_options("snodin_unbound.json", simulation_type="2d_parallel_tempering", num_reps=L, temps=temps,
+                        stacking_mults=smults, exchange_interval=20, swaps=4, random_seed=77)
+    sim = Simulation(write_inp(str(tmp_path / "pt2d.inp"), opts), n_ladders * L, 0, lib_path=lib)
+    ctl = sim.engine.control()
+    assert np.array_equal(ctl["temp_idx"].reshape(n_ladders, L)[0], np.repeat(np.arange(v1), v2))
+    assert np.allclose(ctl["stacking_mult"].reshape(n_ladders, L)[0], np.tile(smults, v1))
+    slot_t = np.repeat(temps, v2)
+    slot_sm = np.tile(smults, v1)
+    q2r_prev = np.tile(np.arange(L, dtype=np.int32), (n_ladders, 1))
+    expected_attempts = np.zeros((2, L), dtype=np.int64)
+    starts = {0: (0, 0, 2, 1, v1 - 1, v2, v2), 1: (0, 0, 1, 2, v1, v2 - 1, 1),
+              2: (1, 0, 2, 1, v1 - 1, v2, v2), 3: (0, 1, 1, 2, v1, v2 - 1, 1)}
+    for swap_i in range(1, 10):
+        assert sim.exchange_advance() == 0
+        dep = sim.engine.exchange_collect().reshape(n_ladders, L, -1)
+        sim.exchange_apply(swap_i)
+        q2r, att, acc = sim.exchange_state(n_ladders, L, two_d=True)
+        i0, j0, di, dj, i1, j1, incr = starts[swap_i % 4]
+        pairs = [(i * v2 + j, i * v2 + j + incr) for i in range(i0, i1, di) for j in range(j0, j1, dj)]
+        for a, _ in pairs:
+            expected_attempts[swap_i % 2, a] += 1
+        for l in range(n_ladders):
+            touched = set()
+            for a, b in pairs:
+                touched.update((a, b))
+                r1, r2 = q2r_prev[l, a], q2r_prev[l, b]
+                t1, t2 = slot_t[a], slot_t[b]
+                d1, d2 = dep[l, r1], dep[l, r2]
+                DB = 1 / t2 - 1 / t1
+                DH = d2[0] * t2 - d1[0] * t1
+                DBias = d2[1] * t2 - d1[1] * t1
+                Dst = d2[2] * t2 - d1[2] * t1
+                DBM = slot_sm[b] / t2 - slot_sm[a] / t1
+                # equal staple_u multipliers: the chemical-potential term vanishes
+                p = min(1.0, np.exp(DB * (DH + DBias) + DBM * Dst))
+                swapped = q2r[l, a] == r2 and q2r[l, b] == r1
+                if p == 1.0:
+                    assert swapped
+                if p < 1e-12:
+                    assert not swapped
+                assert swapped or (q2r[l, a] == r1 and q2r[l, b] == r2)
+            for k in range(L):
+                if k not in touched:
+                    assert q2r[l, k] == q2r_prev[l, k]
+            assert sorted(q2r[l]) == list(range(L))
+            # control variables follow the permutation
+            ctl = sim.engine.control()
+            for k in range(L):
+                r = l * L + q2r[l, k]
+                assert ctl["temp_idx"][r] == k // v2 and ctl["stacking_mult"][r] == slot_sm[k]
+            assert np.array_equal(att[l], expected_attempts)
+        q2r_prev = q2r.copy()
+    assert acc.sum() > 0
+    sim.engine.assert_ok()
+    e = sim.engine.energies()[:, 0]
+    re, _ = sim.engine.recompute_energies()
+    assert np.allclose(e, re, rtol=1e-10, atol=1e-9)
+
+
+def test_two_d_exchange_rule(hostsim_lib, tmp_path):
+    _two_d_exchange_rule(hostsim_lib, tmp_path)
+
+
+@pytest.mark.gpu
+def test_two_d_exchange_rule_gpu(tmp_path):
+    _two_d_exchange_rule(None, tmp_path)
