@@ -22,6 +22,8 @@ import sys
 import tempfile
 import time
 
+os.environ.setdefault("LDO_QUIET", "1")  # the host library must not write to stdout: the bench prints ONE JSON line
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 INPUTS = os.path.join(ROOT, "tests", "golden", "inputs")
@@ -310,11 +312,13 @@ def run_ours(args, rank, world, local_rank):
         smem_gbs = SMEM_BYTES_PER_MOVE * moves_per_launch / (kernel_ms * 1e-3) / 1e9
         smem_peak = 148 * 128 * (clocks.get("sm_max_mhz") or 1965.0) * 1e6 / 1e9
         traffic = None
+        issue = None  # ncu figures of the same launch (not measured live): what actually bounds the kernel
         traffic_path = os.path.join(ROOT, "profiles", "ncu_run100_traffic.json")
         if os.path.exists(traffic_path):
             t = json.load(open(traffic_path))
             if t.get("replicas") == R:
                 traffic = t["traffic_bytes_per_launch"]
+                issue = dict(t.get("issue") or {}, peak_ipc_per_sm=4.0)
         line = {
             "metric": "attempted MC moves/sec (whole box), snodin PTMC", "value": value, "unit": "attempted MC moves/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps,
@@ -326,9 +330,11 @@ def run_ours(args, rank, world, local_rank):
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                          "kernel": "k_exec_staged<CapsSmall> (run, 100 moves/replica)", "kernel_ms": kernel_ms,
                          "algorithmic_bytes_per_launch": hbm_bytes, "peak_source": peak_src,
-                         "note": "the path is instruction-fetch / latency bound, not HBM bound (SURVEY.md 8d, profiles/README.md); "
-                                 "traffic (ncu dram bytes of one 100-move launch) exceeds the algorithmic bytes because the "
-                                 "per-lane call stacks (local memory) spill past L2",
+                         "note": "the path is bound by instruction supply (stall_no_inst 87 %, L1.5 instruction cache hit rate 52 %), "
+                                 "not by HBM or shared memory (SURVEY.md 8d, profiles/README.md); traffic (ncu dram bytes of one "
+                                 "100-move launch) exceeds the algorithmic bytes because the per-lane call stacks (local memory) "
+                                 "spill past L2",
+                         "issue": issue,
                          "smem": {"achieved": smem_gbs, "peak": smem_peak, "unit": "GB/s", "frac": smem_gbs / smem_peak,
                                   "bytes_per_move": SMEM_BYTES_PER_MOVE, "peak_source": "nominal 148 SM * 128 B/clk * sm_max_mhz"}},
         }

@@ -3,6 +3,7 @@
 // reference's text output files. See include/ldo_host.h for the reference file:line of each piece.
 
 #include <chrono>
+#include <cstdlib>
 #include <cmath>
 #include <cstring>
 #include <fstream>
@@ -830,12 +831,14 @@ ldo_sim* ldo_sim_create(const char* inp_path, int n_replicas, int device, int ra
         unsigned long long seed;
         if (p.m_random_seed != -1) {
             seed = static_cast<unsigned long long>(p.m_random_seed);
-            std::cout << "Using specified seed: " << p.m_random_seed << "\n";
+            // the reference reports the seed on stdout (simulation.cpp:203); LDO_QUIET keeps stdout clean for
+            // callers that print machine-readable output themselves (bench.py)
+            if (!std::getenv("LDO_QUIET")) std::cout << "Using specified seed: " << p.m_random_seed << "\n";
         }
         else {
             std::random_device rd {};
             seed = (static_cast<unsigned long long>(rd()) << 32) ^ rd();
-            std::cout << "Truly random seed: " << seed << "\n";
+            if (!std::getenv("LDO_QUIET")) std::cout << "Truly random seed: " << seed << "\n";
         }
         if (s->is_pt) {
             // replica k of ladder l keeps stream l * num_reps + k whichever rank holds it
