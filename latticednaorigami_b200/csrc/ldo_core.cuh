@@ -440,6 +440,16 @@ struct System {
 #else
     LDO_HDN int step(int d, int incr) const {
 #endif
+        // single steps (nearly every call) without the loops
+        if (d < 0) return d;
+        if (incr == 1 || incr == -1) {
+            int c = S()->dchain[d];
+            int i = (int)S()->dindex[d] + incr;
+            int L = S()->chain_len[c];
+            if ((unsigned)i < (unsigned)L) return d + incr;
+            if (c == 0 && SC().cyclic) return incr > 0 ? chain_base(0) : chain_base(0) + L - 1;
+            return -1;
+        }
 #pragma unroll 1
         while (incr > 0 && d >= 0) {
             d = fwd(d);
