@@ -24,6 +24,23 @@ import time
 
 os.environ.setdefault("LDO_QUIET", "1")  # the host library must not write to stdout: the bench prints ONE JSON line
 
+# Native libraries (NCCL's version banner, the C++ host) write to file descriptor 1 directly: keep the real
+# stdout for the single JSON line and point fd 1 at stderr for everything else.
+_REAL_STDOUT = None
+
+
+def capture_stdout():
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, (json.dumps(obj) + "\n").encode())
+
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 INPUTS = os.path.join(ROOT, "tests", "golden", "inputs")
@@ -102,7 +119,7 @@ def run_reference_arm(args, rank):
     if rank != 0:
         return
     if not reference_available():
-        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/latticeDNAOrigami not built (needs /root/reference at build time)"}))
+        emit(({"impl": "reference", "unavailable": "oracle/_ref/latticeDNAOrigami not built (needs /root/reference at build time)"}))
         return
     cores = os.cpu_count() or 1
     moves = 30000
@@ -116,7 +133,7 @@ def run_reference_arm(args, rank):
     value = cores * moves * args.steps / wall
     sample = (f"per step: {cores} processes of the unmodified reference CLI, one per host core, {moves} constant-T moves each "
               f"at ladder temperatures from snodin_unbound")
-    print(json.dumps({
+    emit(({
         "impl": "reference", "metric": "attempted MC moves/sec (whole box), snodin PTMC", "value": value,
         "unit": "attempted MC moves/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * wall / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -312,6 +329,7 @@ def run_ours(args, rank, world, local_rank):
         smem_gbs = SMEM_BYTES_PER_MOVE * moves_per_launch / (kernel_ms * 1e-3) / 1e9
         smem_peak = 148 * 128 * (clocks.get("sm_max_mhz") or 1965.0) * 1e6 / 1e9
         traffic = None
+        smem_counted = None  # the device's own shared-memory operation count (ncu wavefronts), next to SURVEY's reference count
         issue = None  # ncu figures of the same launch (not measured live): what actually bounds the kernel
         traffic_path = os.path.join(ROOT, "profiles", "ncu_run100_traffic.json")
         if os.path.exists(traffic_path):
@@ -319,6 +337,7 @@ def run_ours(args, rank, world, local_rank):
             if t.get("replicas") == R:
                 traffic = t["traffic_bytes_per_launch"]
                 issue = dict(t.get("issue") or {}, peak_ipc_per_sm=4.0)
+                smem_counted = t.get("smem")
         line = {
             "metric": "attempted MC moves/sec (whole box), snodin PTMC", "value": value, "unit": "attempted MC moves/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": elapsed_ms / args.steps,
@@ -336,19 +355,21 @@ def run_ours(args, rank, world, local_rank):
                                  "spill past L2",
                          "issue": issue,
                          "smem": {"achieved": smem_gbs, "peak": smem_peak, "unit": "GB/s", "frac": smem_gbs / smem_peak,
-                                  "bytes_per_move": SMEM_BYTES_PER_MOVE, "peak_source": "nominal 148 SM * 128 B/clk * sm_max_mhz"}},
+                                  "bytes_per_move": SMEM_BYTES_PER_MOVE, "peak_source": "nominal 148 SM * 128 B/clk * sm_max_mhz",
+                                  "device_count": smem_counted}},
         }
         if world == 1 and reference_available() and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline()
         else:
             line["cpu_baseline"] = None
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
     shutil.rmtree(tmp, ignore_errors=True)
 
 
 def main():
+    capture_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
