@@ -266,6 +266,15 @@ int ldo_exchange_collect(ldo_engine* e, double* dependent_local);
 int ldo_exchange_pt(ldo_engine* e, int variant, long long swap_i, int n_ladders, int ladder_len,
                     int rank, int n_ranks, const double* dependent,
                     int* slot_to_replica, long long* attempts, long long* accepts);
+/* Reduced staple chemical potentials ln(staple_M) - (2 L - 1) ln 6 per staple type (m_reduced_staple_us,
+ * origami_system.cpp:965-990) as the exchange uses them; returns the number of staple types. */
+int ldo_get_reduced_staple_u(ldo_engine* e, double* out);
+/* The swap probability the exchange kernels use, evaluated on the host (same inline function): replaces
+ * PTGCMCSimulation::calc_acceptance_p (ptmc_simulation.cpp:275-313). dependent1/2 = {enthalpy, bias, stacking,
+ * staple counts[n_staple_types]} of the two replicas; reduced_staple_u as origami_system.cpp:965-990. */
+double ldo_exchange_acceptance_p(int n_staple_types, const double* reduced_staple_u, double temp1, double temp2,
+                                 double staple_u_mult1, double staple_u_mult2, double stacking_mult1, double stacking_mult2,
+                                 const double* dependent1, const double* dependent2);
 /* Replaces: TwoDPTGCMCSimulation::attempt_exchange (ptmc_simulation.cpp:495-560): the slots of a ladder form a
  * [v1_dim temperatures][v2_dim stacking multipliers] grid, slot (i, j) = i * v2_dim + j as the reference
  * numbers its ranks (:454-471); round swap_i tests the pair set swap_i % 4 (T direction even / stacking

@@ -632,6 +632,26 @@ LDO_HD inline size_t exchange_gathered_index(const ExchangeArgs& x, int l, int k
     return (size_t)exchange_rank_of(x, k) * x.n_local + exchange_local_index(x, l, k);
 }
 
+// calc_acceptance_p (ptmc_simulation.cpp:275-313). d1 / d2 = {enthalpy, bias, stacking, staple counts...} of the
+// two replicas, each in units of its own kT. The staple sum runs over the n_types - 1 staple identities (the
+// reference's loop bound reads one past the end, App. A1).
+LDO_HD inline double exchange_acceptance_p(int n_staple_types, const double* reduced_staple_u, double temp1, double temp2,
+                                           double um1, double um2, double sm1, double sm2, const double* d1, const double* d2) {
+    double DBU_DN = 0;
+    for (int t = 0; t < n_staple_types; t++) {
+        double N1 = d1[3 + t], N2 = d2[3 + t];
+        double u1 = reduced_staple_u[t] * temp1 * um1;
+        double u2 = reduced_staple_u[t] * temp2 * um2;
+        DBU_DN += (u2 / temp2 - u1 / temp1) * (N2 - N1);
+    }
+    double DB = 1 / temp2 - 1 / temp1;
+    double DH = d2[0] * temp2 - d1[0] * temp1;
+    double Dstacking = d2[2] * temp2 - d1[2] * temp1;
+    double DBM = sm2 / temp2 - sm1 / temp1;
+    double DBias = d2[1] * temp2 - d1[1] * temp1;
+    return fmin(1.0, exp(DB * (DH + DBias) + DBM * Dstacking - DBU_DN));
+}
+
 // Swap test of the slots si, sj of ladder l (calc_acceptance_p + test_acceptance, ptmc_simulation.cpp:255-313);
 // `counter` indexes attempts / accepts
 LDO_HD inline void exchange_pair(const ExchangeArgs& x, int l, int* q2r, int i, int j, size_t counter) {
@@ -645,21 +665,7 @@ LDO_HD inline void exchange_pair(const ExchangeArgs& x, int l, int* q2r, int i, 
         double temp1 = x.slot_temp[si], temp2 = x.slot_temp[sj];
         double sm1 = x.slot_stacking_mult[si], sm2 = x.slot_stacking_mult[sj];
         double um1 = x.slot_staple_u_mult[si], um2 = x.slot_staple_u_mult[sj];
-        // calc_acceptance_p (ptmc_simulation.cpp:275-313); the staple sum runs over the n_types - 1
-        // staple identities (the reference's loop bound reads one past the end, App. A1)
-        double DBU_DN = 0;
-        for (int t = 0; t < x.n_staple_types; t++) {
-            double N1 = d1[3 + t], N2 = d2[3 + t];
-            double u1 = x.reduced_staple_u[t] * temp1 * um1;
-            double u2 = x.reduced_staple_u[t] * temp2 * um2;
-            DBU_DN += (u2 / temp2 - u1 / temp1) * (N2 - N1);
-        }
-        double DB = 1 / temp2 - 1 / temp1;
-        double DH = d2[0] * temp2 - d1[0] * temp1;
-        double Dstacking = d2[2] * temp2 - d1[2] * temp1;
-        double DBM = sm2 / temp2 - sm1 / temp1;
-        double DBias = d2[1] * temp2 - d1[1] * temp1;
-        double p_accept = fmin(1.0, exp(DB * (DH + DBias) + DBM * Dstacking - DBU_DN));
+        double p_accept = exchange_acceptance_p(x.n_staple_types, x.reduced_staple_u, temp1, temp2, um1, um2, sm1, sm2, d1, d2);
         bool accept;
         if (p_accept == 1) {
             accept = true;
@@ -1585,6 +1591,10 @@ void ldo_engine_destroy(ldo_engine* e) {
 
 const char* ldo_last_error(const ldo_engine* e) { return e ? e->b->err.c_str() : g_create_error.c_str(); }
 int ldo_num_replicas(const ldo_engine* e) { return e->b->R; }
+int ldo_get_reduced_staple_u(ldo_engine* e, double* out) {
+    for (size_t t = 0; t < e->b->reduced_staple_u.size(); t++) out[t] = e->b->reduced_staple_u[t];
+    return (int)e->b->reduced_staple_u.size();
+}
 
 int ldo_set_temperature_tables(ldo_engine* e, int n_temps, int n_ident, const double* temps, const double* hyb_energy,
                                const double* hyb_enthalpy, const double* hyb_entropy, const double* init) {
@@ -2011,6 +2021,13 @@ int ldo_set_exchange_ladder(ldo_engine* e, int ladder_len, const int* temp_idx, 
 static int exchange_pt_impl(ldo_engine* e, int variant, int v2_dim, long long swap_i, int n_ladders, int ladder_len, int rank,
                             int n_ranks, const double* dependent, int* slot_to_replica, long long* attempts,
                             long long* accepts);
+
+double ldo_exchange_acceptance_p(int n_staple_types, const double* reduced_staple_u, double temp1, double temp2,
+                                 double staple_u_mult1, double staple_u_mult2, double stacking_mult1, double stacking_mult2,
+                                 const double* dependent1, const double* dependent2) {
+    return exchange_acceptance_p(n_staple_types, reduced_staple_u, temp1, temp2, staple_u_mult1, staple_u_mult2,
+                                 stacking_mult1, stacking_mult2, dependent1, dependent2);
+}
 
 int ldo_exchange_pt(ldo_engine* e, int variant, long long swap_i, int n_ladders, int ladder_len, int rank,
                     int n_ranks, const double* dependent, int* slot_to_replica, long long* attempts,

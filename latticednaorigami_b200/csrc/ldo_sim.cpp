@@ -25,6 +25,7 @@ thread_local std::string g_host_error;
 
 struct ReplicaFiles {
     std::unique_ptr<std::ofstream> trj, counts, staples, staplestates, times, ene, ops;
+    std::unique_ptr<std::ofstream> vcf, states, ores; // setup_config_files (simulation.cpp:150-180)
 };
 } // namespace
 
@@ -128,6 +129,11 @@ void open_output_files(ldo_sim& s) {
         }
         ReplicaFiles& f = s.files[r];
         if (p.m_configs_output_freq != 0) f.trj.reset(new std::ofstream {base + ".trj"});
+        if (p.m_vtf_output_freq != 0) {
+            f.vcf.reset(new std::ofstream {base + ".vcf"});
+            f.states.reset(new std::ofstream {base + ".states"});
+            f.ores.reset(new std::ofstream {base + ".ores"});
+        }
         if (p.m_counts_output_freq != 0) {
             f.counts.reset(new std::ofstream {base + ".counts"});
             f.staples.reset(new std::ofstream {base + ".staples"});
@@ -166,8 +172,8 @@ void write_outputs(ldo_sim& s, long long step) {
     if (s.files.empty()) return;
     bool w_trj {due(p.m_configs_output_freq, step)}, w_counts {due(p.m_counts_output_freq, step)};
     bool w_times {due(p.m_times_output_freq, step)}, w_ene {due(p.m_energies_output_freq, step)};
-    bool w_ops {due(p.m_order_params_output_freq, step)};
-    if (!(w_trj || w_counts || w_times || w_ene || w_ops)) return;
+    bool w_ops {due(p.m_order_params_output_freq, step)}, w_vtf {due(p.m_vtf_output_freq, step)};
+    if (!(w_trj || w_counts || w_times || w_ene || w_ops || w_vtf)) return;
     int nst {static_cast<int>(s.sysfile->identities.size()) - 1};
     std::vector<double> ene;
     std::vector<int> counters, staple_counts, opv;
@@ -192,7 +198,7 @@ void write_outputs(ldo_sim& s, long long step) {
     for (int r {0}; r != s.R; r++) {
         ReplicaFiles& f = s.files[r];
         int rr {s.file_owner.empty() ? r : s.file_owner[r]}; // replica whose data this file set follows
-        bool need_state {(w_trj && f.trj) || (w_counts && f.staplestates)};
+        bool need_state {(w_trj && f.trj) || (w_counts && f.staplestates) || (w_vtf && f.vcf)};
         int nc {0};
         if (need_state) s.check(ldo_get_state(s.eng, rr, &nc, ci.data(), cid.data(), cl.data(), pos.data(), ore.data(), st.data(), bd.data()));
         if (w_trj && f.trj) {
@@ -212,6 +218,42 @@ void write_outputs(ldo_sim& s, long long step) {
             }
             o << "\n";
             o.flush();
+        }
+        if (w_vtf && f.vcf) {
+            // OrigamiVCFOutputFile / OrigamiOrientationOutputFile / OrigamiStateOutputFile::write (files.cpp:550-645):
+            // every chain padded to max_staple_size entries, the frame padded to the maximum number of domains
+            int n_scaf {static_cast<int>(s.sysfile->identities[0].size())};
+            int max_domains {n_scaf + p.m_max_total_staples * p.m_max_staple_size};
+            std::ofstream &v = *f.vcf, &so = *f.states, &oo = *f.ores;
+            v << "timestep\n";
+            int written {0}, k {0};
+            for (int c {0}; c != nc; c++) {
+                int n {0};
+                for (int d {0}; d != cl[c]; d++, n++) {
+                    for (int a {0}; a != 3; a++) v << pos[3 * (k + d) + a] << " ";
+                    v << "\n";
+                    for (int a {0}; a != 3; a++) oo << (st[k + d] != 0 ? ore[3 * (k + d) + a] : 0) << " ";
+                    so << (st[k + d] >= 1 && st[k + d] <= 3 ? st[k + d] : 0) << " ";
+                }
+                for (; n < p.m_max_staple_size; n++) {
+                    v << "0 0 0 \n";
+                    oo << "0 0 0 ";
+                    so << "-1 ";
+                }
+                written += n;
+                k += cl[c];
+            }
+            for (int d {written}; d < max_domains; d++) {
+                v << "0 0 0 \n";
+                oo << "0 0 0 ";
+                so << "-1 ";
+            }
+            v << "\n";
+            oo << "\n";
+            so << "\n";
+            v.flush();
+            oo.flush();
+            so.flush();
         }
         if (w_counts && f.counts) {
             int const* c = &counters[9 * static_cast<size_t>(rr)];
@@ -263,7 +305,8 @@ long long next_output_step(ldo_sim& s, long long cur, long long end) {
     InputParameters const& p = s.params;
     if (s.files.empty()) return end;
     long long next {end};
-    int freqs[] {p.m_configs_output_freq, p.m_counts_output_freq, p.m_times_output_freq, p.m_energies_output_freq, p.m_order_params_output_freq};
+    int freqs[] {p.m_configs_output_freq, p.m_counts_output_freq, p.m_times_output_freq, p.m_energies_output_freq, p.m_order_params_output_freq,
+                 p.m_vtf_output_freq};
     for (int f: freqs) {
         if (f == 0) continue;
         long long n {(cur / f + 1) * f};

@@ -60,6 +60,7 @@ def lib():
         L.oref_center.argtypes = [C.c_void_p, C.c_int]
         L.oref_update_temp.argtypes = [C.c_void_p, C.c_double, C.c_double]
         L.oref_update_staple_us.argtypes = [C.c_void_p, C.c_double, C.c_double]
+        L.oref_update_staple_us.restype = None
         L.oref_num_staple_types.argtypes = [C.c_void_p]
         L.oref_staple_us.argtypes = [C.c_void_p, C.c_void_p]
         L.oref_pair_energies.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
@@ -77,6 +78,7 @@ def lib():
         L.oref_nn_longest_contig_complement.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_int]
         L.oref_num_walks.restype = C.c_double
         L.oref_num_walks.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        L.oref_pt_acceptance_p.argtypes = [C.c_void_p] + [C.c_double] * 8 + [C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 5
         _lib = L
     return _lib
 
@@ -243,6 +245,14 @@ class RefSystem:
     def update_temp(self, temp, stacking_mult=1.0):
         self._check(self.L.oref_update_temp(self.h, temp, stacking_mult))
 
+    def staple_us(self, temp, staple_u_mult=1.0):
+        """m_staple_us after OrigamiSystem::update_staple_us(temp, mult) (origami_system.cpp:624-628)."""
+        self.L.oref_update_staple_us(self.h, temp, staple_u_mult)
+        n = self.L.oref_num_staple_types(self.h)
+        out = np.zeros(max(n, 1))
+        self.L.oref_staple_us(self.h, out.ctypes.data)
+        return out[:n]
+
     def pair_energies(self, a, b):
         out = np.zeros(4)
         if self.L.oref_pair_energies(self.h, a, b, out.ctypes.data) != 0:
@@ -278,6 +288,20 @@ class RefSystem:
 
     def unassign_domain(self, c, d):
         return self.L.oref_unassign_domain(self.h, c, d)
+
+
+def pt_acceptance_p(ref, temps, umults, bmults, smults, dep1, dep2, staple_u1, staple_u2, staple_n1, staple_n2):
+    """PTGCMCSimulation::calc_acceptance_p of the unmodified reference (ptmc_simulation.cpp:275-313) for one pair
+    of replicas; `ref` must have been created from ut_parallel_tempering options. The per-staple arrays carry
+    n_types entries (the reference's loop reads that many, App. A1)."""
+    arrs = [np.ascontiguousarray(a, dtype=np.float64) for a in (dep1, dep2, staple_u1, staple_u2, staple_n1, staple_n2)]
+    out = np.zeros(1)
+    rc = lib().oref_pt_acceptance_p(ref.h, temps[0], temps[1], umults[0], umults[1], bmults[0], bmults[1], smults[0], smults[1],
+                                    arrs[0].ctypes.data, arrs[1].ctypes.data, len(arrs[2]), arrs[2].ctypes.data,
+                                    arrs[3].ctypes.data, arrs[4].ctypes.data, arrs[5].ctypes.data, out.ctypes.data)
+    if rc != 0:
+        raise RuntimeError(lib().oref_last_error(ref.h).decode())
+    return float(out[0])
 
 
 def nn_unitless_thermo(seq, temp, cation_M):

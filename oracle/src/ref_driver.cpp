@@ -445,3 +445,37 @@ extern "C" int oref_debug_rg(void* vh, int movetype, int* out, int cap) {
     }
     return n;
 }
+
+// ---- replica exchange: the reference's own acceptance probability --------------------------------------
+// Builds a UTPTGCMCSimulation from the handle's parameters (which must describe a ut_parallel_tempering
+// run; rank 0 of the thread-backed MPI shim, nothing is communicated by the constructor) and evaluates
+// PTGCMCSimulation::calc_acceptance_p (ptmc_simulation.cpp:275-313) for one pair of replicas.
+// dep1 / dep2 = {enthalpy, bias, stacking}; staple_u / staple_n have n_staple entries each.
+#include "LatticeDNAOrigami/ptmc_simulation.hpp"
+extern "C" int oref_pt_acceptance_p(
+        void* vh, double temp1, double temp2, double umult1, double umult2, double bmult1, double bmult2,
+        double smult1, double smult2, const double* dep1, const double* dep2, int n_staple,
+        const double* staple_u1, const double* staple_u2, const double* staple_n1, const double* staple_n2,
+        double* p_out) {
+    auto h = static_cast<Handle*>(vh);
+    try {
+        CoutSilencer quiet {};
+        static ptmc::UTPTGCMCSimulation* pt {nullptr};
+        static Handle* owner {nullptr};
+        if (owner != h) {
+            pt = new ptmc::UTPTGCMCSimulation {
+                    *h->origami, h->origami->get_system_order_params(), h->origami->get_system_biases(), *h->params};
+            owner = h;
+        }
+        std::vector<std::pair<double, double>> control {{temp1, temp2}, {umult1, umult2}, {bmult1, bmult2}, {smult1, smult2}};
+        std::vector<std::pair<double, double>> dependent {{dep1[0], dep2[0]}, {dep1[1], dep2[1]}, {dep1[2], dep2[2]}};
+        std::vector<double> u1(staple_u1, staple_u1 + n_staple), u2(staple_u2, staple_u2 + n_staple);
+        std::vector<double> n1(staple_n1, staple_n1 + n_staple), n2(staple_n2, staple_n2 + n_staple);
+        std::vector<std::pair<std::vector<double>, std::vector<double>>> per_staple {{u1, u2}, {n1, n2}};
+        *p_out = pt->calc_acceptance_p(control, dependent, per_staple);
+    } catch (std::exception const& e) {
+        h->err = e.what();
+        return -1;
+    }
+    return 0;
+}

@@ -190,3 +190,38 @@ def test_two_d_exchange_rule(hostsim_lib, tmp_path):
 @pytest.mark.gpu
 def test_two_d_exchange_rule_gpu(tmp_path):
     _two_d_exchange_rule(None, tmp_path)
+
+
+def test_swap_probability_matches_reference_code(hostsim_lib, oracle, tmp_path):
+    """The swap probability the exchange kernels evaluate (`exchange_acceptance_p`, through its host export)
+    against PTGCMCSimulation::calc_acceptance_p of the unmodified reference, on random control variables and
+    dependent quantities including unequal chemical-potential and stacking multipliers; 1e-12 relative. Also
+    pins the reduced staple chemical potentials the engine holds."""
+    opts = pt_options(output_filebase=str(tmp_path / "ref"))
+    ref = oracle.RefSystem(opts, with_sim=False)
+    sim = Simulation(write_inp(str(tmp_path / "pt.inp"), pt_options()), len(TEMPS), 0, lib_path=hostsim_lib)
+    eng = sim.engine
+    red = np.zeros(64)
+    nst = eng.L.ldo_get_reduced_staple_u(eng.h, red.ctypes.data)
+    red = red[:nst]
+    us = ref.staple_us(341.0, 1.3)
+    assert len(us) == nst == 12
+    assert np.allclose(us, red * 341.0 * 1.3, rtol=1e-13, atol=0)
+    rng = np.random.default_rng(5)
+    seen_partial = 0
+    for _ in range(200):
+        t1, t2 = rng.uniform(320, 360, 2)
+        um1, um2 = rng.uniform(0.8, 1.2, 2)
+        sm1, sm2 = rng.uniform(0.5, 1.0, 2)
+        scale = rng.choice([0.01, 0.3, 3.0])
+        d1 = np.concatenate([rng.normal(-300, 60, 1) * scale, rng.normal(0, 3, 1) * scale, rng.normal(-20, 5, 1) * scale,
+                             rng.integers(0, 3, nst).astype(float)])
+        d2 = np.concatenate([rng.normal(-300, 60, 1) * scale, rng.normal(0, 3, 1) * scale, rng.normal(-20, 5, 1) * scale,
+                             rng.integers(0, 3, nst).astype(float)])
+        ours = eng.L.ldo_exchange_acceptance_p(nst, red.ctypes.data, t1, t2, um1, um2, sm1, sm2, d1.ctypes.data, d2.ctypes.data)
+        pad = lambda a: np.concatenate([a, [0.0]])  # the reference's loop reads n_types entries (App. A1)
+        want = oracle.pt_acceptance_p(ref, (t1, t2), (um1, um2), (1.0, 1.0), (sm1, sm2), d1[:3], d2[:3],
+                                      pad(ref.staple_us(t1, um1)), pad(ref.staple_us(t2, um2)), pad(d1[3:]), pad(d2[3:]))
+        assert abs(ours - want) <= 1e-12 * max(want, 1e-300), (ours, want)
+        seen_partial += 0.0 < want < 1.0
+    assert seen_partial > 20
