@@ -576,7 +576,11 @@ __global__ void __launch_bounds__(1024) k_build_order(const long long* run_timin
 
 // In place: state and scratch stay in HBM / L2 (large systems)
 template <class K>
-__global__ void __launch_bounds__(128) k_exec_inplace(DevPtrs<K> P, OpArgs a, int warps_per_block, SysState<K>* recompute_tmp) {
+// 7 blocks of 4 warps per SM (72 registers, as the staged kernel): 4096 replicas are one wave
+#ifndef LDO_INPLACE_MIN_BLOCKS
+#define LDO_INPLACE_MIN_BLOCKS 7
+#endif
+__global__ void __launch_bounds__(128, LDO_INPLACE_MIN_BLOCKS) k_exec_inplace(DevPtrs<K> P, OpArgs a, int warps_per_block, SysState<K>* recompute_tmp) {
     int warp = threadIdx.x >> 5;
     int r = blockIdx.x * warps_per_block + warp;
     if (r >= a.n_replicas) return;
@@ -869,7 +873,14 @@ __global__ void k_exchange(ExchangeArgs x) {
 // Engine object
 // ---------------------------------------------------------------------------------------------
 
+#ifdef LDO_SMALL_INPLACE
+// profiling variant: snodin-class systems run in place (HBM / L2 / L1) like the large ones
+typedef Caps<80, 26, 7, 16, false, 48, 40, 40> CapsSmall;
+#define LDO_SMALL_STAGED false
+#else
 typedef Caps<80, 26, 7, 16, true, 48, 40, 40> CapsSmall; // snodin-class systems: staged in shared memory
+#define LDO_SMALL_STAGED true
+#endif
 typedef Caps<512, 176, 11, 96, false, 511, 512, 1026> CapsLarge; // large scaffolds: in place in HBM/L2
 
 static std::string g_create_error;
@@ -1574,7 +1585,7 @@ int ldo_engine_create(const ldo_system_desc* d, int n_replicas, int device, ldo_
     int need_d = sc.n_scaffold + d->max_total_staples * sc.lmax;
     int need_c = 1 + d->max_total_staples;
     if (need_d <= CapsSmall::D && need_c <= CapsSmall::C && d->n_types <= CapsSmall::T) {
-        return make_engine<CapsSmall, true>(d, sc, n_replicas, device, out);
+        return make_engine<CapsSmall, LDO_SMALL_STAGED>(d, sc, n_replicas, device, out);
     }
     if (need_d <= CapsLarge::D && need_c <= CapsLarge::C && d->n_types <= CapsLarge::T) {
         return make_engine<CapsLarge, false>(d, sc, n_replicas, device, out);
