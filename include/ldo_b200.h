@@ -48,7 +48,9 @@ enum { /* order parameter "type" strings (order_params.cpp:471-545) */
     LDO_OP_NUM_STACKED_PAIRS = 5,
     LDO_OP_NUM_LINEAR_HELICES = 6,
     LDO_OP_NUM_STACKED_JUNCTS = 7,
-    LDO_OP_SUM = 8
+    LDO_OP_SUM = 8,
+    LDO_OP_DIST = 9,          /* "Dist", update_per_domain = false, scaffold domains (order_params.cpp:34-48) */
+    LDO_OP_ADJACENT_SITE = 10 /* "AdjacentSite", likewise (order_params.cpp:84-104) */
 };
 
 enum { /* bias function "type" strings (bias_functions.cpp:366-413) */
@@ -104,6 +106,7 @@ typedef struct {
 typedef struct {
     int type;    /* LDO_OP_* */
     int staple;  /* "staple" option of NumStaplesType / StapleTypeFullyBound */
+    int chain1, domain1, chain2, domain2; /* Dist / AdjacentSite (order_params.cpp:496-511); chains must be 0 */
     int n_sum;   /* Sum: indices of earlier order parameters */
     const int* sum_ops;
 } ldo_order_param_desc;

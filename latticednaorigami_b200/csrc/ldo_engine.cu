@@ -193,6 +193,7 @@ LDO_HD void rep_refresh_stack_energy(SysState<K>* st, const Shared* sh, const Co
 // Bias bookkeeping restart (SystemBiases constructor: every m_bias evaluated once, bias_functions.cpp:60-66,423-426)
 template <class K>
 LDO_HD void rep_init_biases(Engine<K>& eng) {
+    eng.BS()->op_undefined = 0;
     eng.update_move_params();
     eng.BS()->move_update_bias = 0;
     for (int b = 0; b < eng.OB().n_biases; b++) {
@@ -1676,7 +1677,17 @@ int ldo_set_order_params(ldo_engine* e, int n, const ldo_order_param_desc* ops) 
     for (int i = 0; i < n; i++) {
         ob.ops[i].type = ops[i].type;
         ob.ops[i].arg = ops[i].staple;
+        ob.ops[i].arg2 = 0;
         ob.ops[i].n_sum = 0;
+        if (ops[i].type == OP_DIST || ops[i].type == OP_ADJACENT_SITE) {
+            int n_scaf = b->shared.sc.n_scaffold;
+            if (ops[i].chain1 != 0 || ops[i].chain2 != 0 || ops[i].domain1 < 0 || ops[i].domain1 >= n_scaf ||
+                ops[i].domain2 < 0 || ops[i].domain2 >= n_scaf) {
+                return b->fail("Dist / AdjacentSite order parameters must refer to scaffold domains (chain 0)");
+            }
+            ob.ops[i].arg = ops[i].domain1;
+            ob.ops[i].arg2 = ops[i].domain2;
+        }
         if (ops[i].type == OP_SUM) {
             if (ops[i].n_sum > LDO_MAX_SUM) return b->fail("Sum order parameter has too many terms");
             ob.ops[i].n_sum = ops[i].n_sum;

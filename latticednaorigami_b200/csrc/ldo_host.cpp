@@ -681,6 +681,16 @@ std::vector<OrderParamSpec> read_order_params_file(std::string const& filename) 
         op.tag = jops[i]["tag"].as_string();
         op.level = jops[i]["level"].as_int();
         op.staple = jops[i]["staple"].as_int();
+        if (op.type == "Dist" || op.type == "AdjacentSite") {
+            // order_params.cpp:496-516. The per-domain kind (OrigamiSystemWithBias) is not on the device path.
+            if (jops[i]["update_per_domain"].as_bool()) {
+                throw NotImplemented {op.type + ": update_per_domain = true is not available on the device path (DESIGN.md §7)"};
+            }
+            op.chain1 = jops[i]["chain1"].as_int();
+            op.domain1 = jops[i]["domain1"].as_int();
+            op.chain2 = jops[i]["chain2"].as_int();
+            op.domain2 = jops[i]["domain2"].as_int();
+        }
         max_level = std::max(max_level, op.level);
         file_order.push_back(op);
     }
@@ -706,9 +716,6 @@ std::vector<OrderParamSpec> read_order_params_file(std::string const& filename) 
                 if (found < 0) throw SimulationMisuse {"Sum order parameter refers to unknown tag " + tag};
                 out[k].sum_ops.push_back(found);
             }
-        }
-        else if (out[k].type == "Dist" || out[k].type == "AdjacentSite") {
-            throw NotImplemented {out[k].type + ": per-domain order parameters are not available on the device path yet"};
         }
     }
     return out;

@@ -179,6 +179,7 @@ struct OrderParamSpec {
     std::string type, label, tag;
     int level {0};
     int staple {0};
+    int chain1 {0}, domain1 {0}, chain2 {0}, domain2 {0}; // Dist / AdjacentSite
     std::vector<int> sum_ops;
 };
 // Returned in the reference's evaluation order (level-major, file order within a level)

@@ -100,7 +100,9 @@ enum {
     OP_NUM_STACKED_PAIRS = 5,
     OP_NUM_LINEAR_HELICES = 6,
     OP_NUM_STACKED_JUNCTS = 7,
-    OP_SUM = 8
+    OP_SUM = 8,
+    OP_DIST = 9, // DistOrderParam (order_params.cpp:34-48), move-update kind, scaffold domains
+    OP_ADJACENT_SITE = 10 // AdjacentSiteOrderParam (order_params.cpp:84-104)
 };
 enum { BIAS_LINEAR_STEP_WELL = 0, BIAS_SQUARE_WELL = 1, BIAS_GRID = 2 };
 
@@ -111,7 +113,8 @@ enum { BIAS_LINEAR_STEP_WELL = 0, BIAS_SQUARE_WELL = 1, BIAS_GRID = 2 };
 
 struct OpDef {
     int type;
-    int arg; // staple identity for the *Type ops
+    int arg; // staple identity for the *Type ops; first scaffold domain of Dist / AdjacentSite
+    int arg2; // second scaffold domain of Dist / AdjacentSite
     int n_sum;
     int sum_idx[LDO_MAX_SUM];
 };
@@ -135,6 +138,7 @@ struct OpsBiasConst {
 // us_simulation.cpp:503-516) and dense grid-bias boxes (GridBiasFunction, bias_functions.cpp:242-283)
 struct BiasState {
     int op_val[LDO_MAX_OPS]; // m_param of every order parameter
+    unsigned op_undefined; // bit i: OrderParam::m_defined == false (a Dist / AdjacentSite domain is unassigned)
     double bias_val[LDO_MAX_BIASES]; // BiasFunction::m_bias
     double move_update_bias; // SystemBiases::m_move_update_bias
     int win_min[LDO_MAX_BIASES], win_max[LDO_MAX_BIASES];
@@ -604,10 +608,32 @@ struct Engine {
         case OP_NUM_LINEAR_HELICES: return 0; // never modified in the reference (App. A5)
         case OP_NUM_STACKED_JUNCTS: return 0;
         case OP_SUM: {
+            // SumOrderParam::calc_param (order_params.cpp:143-161): undefined when a term is; keeps its value then
             int sum = 0;
+            BS()->op_undefined &= ~(1u << i);
 #pragma unroll 1
-            for (int k = 0; k < o.n_sum; k++) sum += BS()->op_val[o.sum_idx[k]];
+            for (int k = 0; k < o.n_sum; k++) {
+                if ((BS()->op_undefined >> o.sum_idx[k]) & 1u) {
+                    BS()->op_undefined |= 1u << i;
+                    return BS()->op_val[i];
+                }
+                sum += BS()->op_val[o.sum_idx[k]];
+            }
             return sum;
+        }
+        case OP_DIST:
+        case OP_ADJACENT_SITE: {
+            // calc_param (order_params.cpp:34-48, 84-104): defined when both domains are assigned; m_param
+            // keeps its previous value otherwise
+            const DomRec& a = s->dom[o.arg];
+            const DomRec& b = s->dom[o.arg2];
+            if (a.state == ST_UNASSIGNED || b.state == ST_UNASSIGNED) {
+                BS()->op_undefined |= 1u << i;
+                return BS()->op_val[i];
+            }
+            BS()->op_undefined &= ~(1u << i);
+            int dist = abssum(rec_pos(b) - rec_pos(a));
+            return o.type == OP_DIST ? dist : (dist == 1 ? 1 : 0);
         }
         }
         return 0;
@@ -624,6 +650,7 @@ struct Engine {
         int idx = 0;
 #pragma unroll 1
         for (int k = 0; k < bd.n_ops; k++) {
+            if ((BS()->op_undefined >> bd.op_idx[k]) & 1u) return 0; // bias_functions.cpp:258-262
             int v = BS()->op_val[bd.op_idx[k]] - BS()->grid_lo[b][k];
             if (v < 0 || v >= BS()->grid_n[b][k]) return 0;
             idx = idx * BS()->grid_n[b][k] + v;
@@ -634,6 +661,7 @@ struct Engine {
     LDO_HD double calc_bias_fn(int b) const {
         const BiasDef& bd = OB().biases[b];
         if (bd.type == BIAS_GRID) return grid_lookup(b);
+        if ((BS()->op_undefined >> bd.op_idx[0]) & 1u) return 0; // update_bias: no bias while undefined (bias_functions.cpp:124-134)
         int param = BS()->op_val[bd.op_idx[0]];
         int lo = BS()->win_min[b], hi = BS()->win_max[b];
         if (bd.type == BIAS_LINEAR_STEP_WELL) {

@@ -89,6 +89,8 @@ int op_type_code(std::string const& t) {
     if (t == "NumLinearHelices") return LDO_OP_NUM_LINEAR_HELICES;
     if (t == "NumStackedJuncts") return LDO_OP_NUM_STACKED_JUNCTS;
     if (t == "Sum") return LDO_OP_SUM;
+    if (t == "Dist") return LDO_OP_DIST;
+    if (t == "AdjacentSite") return LDO_OP_ADJACENT_SITE;
     throw SimulationMisuse {t + ": order parameter type does not exist"}; // order_params.cpp:546-549
 }
 
@@ -787,6 +789,10 @@ ldo_sim* ldo_sim_create(const char* inp_path, int n_replicas, int device, int ra
             for (size_t i {0}; i != s->ops.size(); i++) {
                 od[i].type = op_type_code(s->ops[i].type);
                 od[i].staple = s->ops[i].staple;
+                od[i].chain1 = s->ops[i].chain1;
+                od[i].domain1 = s->ops[i].domain1;
+                od[i].chain2 = s->ops[i].chain2;
+                od[i].domain2 = s->ops[i].domain2;
                 od[i].n_sum = static_cast<int>(s->ops[i].sum_ops.size());
                 od[i].sum_ops = s->ops[i].sum_ops.data();
             }

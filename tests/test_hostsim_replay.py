@@ -66,3 +66,33 @@ def test_tape_mismatch_is_detected(hostsim_lib, tmp_path):
     sim.engine.run(int(fx["chunk"]))
     st, _ = sim.engine.status()
     assert st[0] == 2
+
+
+def test_distance_order_params_and_biases(hostsim_lib, oracle, tmp_path):
+    """Dist / AdjacentSite / Sum order parameters of the move-update kind with well biases on them
+    (order_params.cpp:34-161, bias_functions.cpp:114-222): replay against the live oracle; the biases enter every
+    acceptance test, so the lattice state stays bit-exact only if they match, and the order-parameter values
+    and the total bias are compared directly as well."""
+    tags = ["numstaples", "numfulldomains", "dist-ends", "dist-mid", "adj-2-9", "dist-sum"]
+    seen = set()
+    for system, temp, seed in [("snodin_unbound.json", 338, 5), ("snodin_assembled.json", 341, 6)]:
+        opts = make_options(system, temp=temp, bias_functions_file=os.path.join(GOLDEN, "inputs", "biases_dist.json"))
+        opts["order_parameter_file"] = os.path.join(GOLDEN, "inputs", "ops_dist.json")
+        r = oracle.RefSystem(opts)
+        r.seed(seed)
+        sim = Simulation(write_inp(str(tmp_path / f"d{seed}.inp"), opts), 1, 0, lib_path=hostsim_lib)
+        for k in range(24):
+            r.tape(clear=True)
+            r.simulate(25)
+            tape = r.tape(clear=True)
+            sim.engine.attach_tape(0, tape)
+            sim.engine.run(25, 0, 0, 0)
+            sim.engine.assert_ok()
+            assert sim.engine.tape_position(0) == len(tape)
+            assert_state_equal(sim.engine.state(0), r.state(), f"{system} chunk {k}")
+            got = sim.engine.order_params()[0]
+            for i, tag in enumerate(tags):
+                assert got[i] == r.order_param(tag), (tag, got)
+            assert abs(sim.engine.energies()[0, 4] - r.total_bias()) < 1e-12
+            seen.add((int(got[2]), int(got[3]), int(got[4]), round(r.total_bias(), 6)))
+    assert len(seen) > 8  # the distances and the biases actually move
