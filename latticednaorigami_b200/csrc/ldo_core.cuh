@@ -33,6 +33,11 @@
 #define LDO_HDN
 #endif
 
+// Warps (= replicas) per block of the staged kernel (the in-place kernel uses 4-warp blocks)
+#ifndef LDO_BLOCK_WARPS
+#define LDO_BLOCK_WARPS 1
+#endif
+
 #if defined(__CUDA_ARCH__)
 #define LDO_LANE ((int)(threadIdx.x & 31))
 #define LDO_NLANES 32
@@ -231,8 +236,9 @@ __constant__ SysConst ldo_c_sc;
 extern __shared__ __align__(16) unsigned char ldo_smem_raw[];
 #endif
 #if defined(__CUDA_ARCH__) && !defined(LDO_GENERIC_ACCESS)
-// With one warp per block the warp's block starts at the symbol itself: every address is a constant
-#if defined(LDO_BLOCK_WARPS) && LDO_BLOCK_WARPS == 1
+// With one warp per block the warp's shared block starts at the symbol itself: every shared-memory address is
+// a constant plus the CTA's window base
+#if LDO_BLOCK_WARPS == 1
 #define LDO_WARP_IN_BLOCK 0u
 #else
 #define LDO_WARP_IN_BLOCK (threadIdx.x >> 5)

@@ -468,11 +468,8 @@ static_assert(LDO_AUX_HOT_BYTES % 16 == 0, "staged part of RepAux must be a mult
 // shared memory, and the state is copied back once at the end.
 // Launch shape of the staged kernel: LDO_BLOCK_WARPS warps per block, at least LDO_MIN_BLOCKS blocks per
 // SM (this caps the registers per thread; see DESIGN.md for the measured occupancy trade-off)
-#ifndef LDO_BLOCK_WARPS
-#define LDO_BLOCK_WARPS 2
-#endif
 #ifndef LDO_MIN_BLOCKS
-#define LDO_MIN_BLOCKS 14
+#define LDO_MIN_BLOCKS (28 / LDO_BLOCK_WARPS)
 #endif
 // Persistent: the grid is sized to what is resident on the chip and every warp pulls replicas from a
 // queue until it is empty, so that ensembles larger than one wave keep all warp slots busy. Run launches

@@ -345,8 +345,8 @@ struct MoveScratch {
     // CTRG (rg_movetypes.hpp:83-115)
     short regrow[K::LV + 1];
     int n_regrow;
-    uint8_t c_attempts_q[K::LV + 1], c_attempts_wq[K::LV + 1];
-    unsigned long long avail_q[K::LV + 1], avail_wq[K::LV + 1];
+    uint8_t c_attempts_q[K::LV + 1];
+    unsigned long long avail_q[K::LV + 1];
     double c_opens[K::LV + 1];
     // m_erased_endpoints_q: stack of position lists
     int eq_depth;
@@ -411,6 +411,10 @@ struct ColdScratch {
     short seg_dom[2 * K::D + 2];
     short stems[K::D + 1];
     short stem_queue[4 * K::D + 8];
+
+    // CTRG: m_c_attempts_wq / m_avail_cis_wq (rg_movetypes.hpp:107-108), written twice and read once per level per move
+    uint8_t c_attempts_wq[K::LV + 1];
+    unsigned long long avail_wq[K::LV + 1];
 
     // CTCB: chains of the internally bound staple networks (m_regrowth_staples) and the growth work stack
     uint8_t regrow_chain[K::C];
@@ -2191,8 +2195,8 @@ struct Engine {
             int avail_cs = 1;
             if (!W()->stemd) {
                 W()->ref_d = sys.step(W()->d, -W()->dir);
-                int catt = M()->c_attempts_wq[W()->di];
-                W()->avail = M()->avail_wq[W()->di];
+                int catt = C()->c_attempts_wq[W()->di];
+                W()->avail = C()->avail_wq[W()->di];
                 W()->memo_level = -1;
                 W()->memo_mask = 0;
                 W()->cur_slot = W()->di & (LDO_RG_OWN_SLOTS - 1);
@@ -2407,8 +2411,8 @@ struct Engine {
     LDO_HD void rg_copy_queues_to_wq() {
 #pragma unroll 1
         for (int k = 0; k < M()->n_regrow; k++) {
-            M()->c_attempts_wq[k] = M()->c_attempts_q[k];
-            M()->avail_wq[k] = M()->avail_q[k];
+            C()->c_attempts_wq[k] = M()->c_attempts_q[k];
+            C()->avail_wq[k] = M()->avail_q[k];
         }
     }
 
