@@ -195,6 +195,13 @@ struct __attribute__((aligned(8))) DomRec {
     uint8_t state;
     uint16_t pad_;
 };
+// Same fields, 4-byte aligned (per-lane placement overlays use a 12-byte stride)
+struct __attribute__((aligned(4))) DomRec4 {
+    uint32_t k;
+    int8_t ore;
+    uint8_t state;
+    uint16_t pad_;
+};
 LDO_HD inline V3 rec_pos(const DomRec& r) {
     V3 v;
     v.k = r.k;
@@ -243,9 +250,21 @@ extern __shared__ __align__(16) unsigned char ldo_smem_raw[];
 #else
 #define LDO_WARP_IN_BLOCK (threadIdx.x >> 5)
 #endif
-#ifndef LDO_SMEM_FROM_THIS
+#if defined(LDO_SMEM_FROM_SYMBOL)
 #define LDO_SMEM_AT(K, T, offset, fallback) \
     (K::STAGED ? reinterpret_cast<T*>(ldo_smem_raw + LDO_WARP_IN_BLOCK * SmemLayout<K>::stride + (offset)) : (fallback))
+#elif !defined(LDO_SMEM_FROM_THIS)
+// Forming an address from the shared-memory symbol costs `S2R SR_CgaCtaId; MOV; LEA` in the prologue of every
+// out-of-line function (ptxas composes the CTA's rank in its cluster into the window address). The dynamic
+// shared memory of a non-cluster launch starts at a fixed offset of the CTA's window (after the 1 KB the system
+// reserves on sm_100), so the accessors use that offset as a literal: every address is an immediate. The
+// value is verified, not assumed: the engine probes it at creation (k_probe_smem_base) and the staged kernel
+// checks it at entry (LDO_ERR_INTERNAL on every replica otherwise).
+#define LDO_SMEM_WINDOW_BASE 0x400u
+#define LDO_SMEM_AT(K, T, offset, fallback)                                                                         \
+    (K::STAGED ? reinterpret_cast<T*>(__cvta_shared_to_generic(                                                    \
+                         LDO_SMEM_WINDOW_BASE + LDO_WARP_IN_BLOCK * SmemLayout<K>::stride + (unsigned)(offset)))    \
+               : (fallback))
 #else
 // A/B variant (profiles/README.md): the accessors are member functions of the engine object (or of its first
 // member, the System), which for a staged replica sits at SmemLayout<K>::engine inside the warp's block, so the
@@ -352,13 +371,9 @@ struct System {
     // Overlay (read-only candidate evaluation): domain od placed at rec, bound to oj (or -1). Staged
     // replicas keep one overlay per lane in shared memory (lanes evaluate different candidates at the
     // same time); otherwise it is a member and lanes work on private copies of the System object.
-    struct Overlay { // 12 bytes: 32 lanes * 3 words hit 32 distinct banks
+    struct Overlay { // 12 bytes = 3 words: the 32 lanes' overlays hit 32 distinct banks word by word
         short od, oj;
-        struct {
-            uint16_t k_lo, k_hi; // V3::k in two halves (keeps the record 2-byte aligned: 12-byte stride)
-            int8_t ore;
-            uint8_t state;
-        } rec;
+        DomRec4 rec; // the candidate record of od, 4-byte aligned (one LDS for the position)
     };
     mutable Overlay ov_;
     LDO_HD Overlay* OV() const {
@@ -401,7 +416,7 @@ struct System {
         const Overlay* o = OV();
         if (d == o->od) {
             V3 v;
-            v.k = (uint32_t)o->rec.k_lo | ((uint32_t)o->rec.k_hi << 16);
+            v.k = o->rec.k;
             return v;
         }
         return rec_pos(S()->dom[d]);
@@ -1167,8 +1182,7 @@ struct System {
         Overlay* ov = OV();
         ov->od = (short)d;
         ov->oj = (short)j;
-        ov->rec.k_lo = (uint16_t)(p.k & 0xFFFFu);
-        ov->rec.k_hi = (uint16_t)(p.k >> 16);
+        ov->rec.k = p.k;
         ov->rec.ore = (int8_t)o;
         ov->rec.state = comp ? ST_BOUND : ST_MISBOUND;
         *new_state = ov->rec.state;

@@ -495,6 +495,16 @@ __global__ void __launch_bounds__(32 * LDO_BLOCK_WARPS, LDO_MIN_BLOCKS) k_exec_s
     int warp = threadIdx.x >> 5;
     WarpSmem<K>& w = ws[warp];
     RepAux* aux = reinterpret_cast<RepAux*>(w.aux);
+#ifdef LDO_SMEM_WINDOW_BASE
+    // the accessors address shared memory with literal window offsets (ldo_core.cuh): refuse to run otherwise
+    if ((unsigned)__cvta_generic_to_shared(ldo_smem_raw) != LDO_SMEM_WINDOW_BASE) {
+        for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < a.n_replicas; r += gridDim.x * blockDim.x) {
+            P.states[r].status = LDO_ERR_INTERNAL;
+            P.states[r].status_detail = 900;
+        }
+        return;
+    }
+#endif
     unsigned my_list;
     asm volatile("mov.u32 %0, %%smid;" : "=r"(my_list));
     my_list %= (unsigned)n_lists;
@@ -525,6 +535,11 @@ __global__ void __launch_bounds__(32 * LDO_BLOCK_WARPS, LDO_MIN_BLOCKS) k_exec_s
         }
         __syncwarp();
     }
+}
+
+// Reports where the dynamic shared memory of a launch shaped like the staged kernel starts in the CTA's window
+__global__ void k_probe_smem_base(unsigned* out) {
+    if (threadIdx.x == 0) *out = (unsigned)__cvta_generic_to_shared(ldo_smem_raw);
 }
 
 // Order in which the next run launch hands out replicas: descending duration of the previous run launch
@@ -1181,6 +1196,18 @@ struct EngineImpl: EngineBase {
             if (chk(cudaFuncSetAttribute(k_exec_staged<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(per_warp * wpb)))) {
                 return fail(dev_err());
             }
+#ifdef LDO_SMEM_WINDOW_BASE
+            {
+                unsigned* d_base = nullptr;
+                unsigned h_base = 0;
+                if (chk(cudaFuncSetAttribute(k_probe_smem_base, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(per_warp * wpb)))) return fail(dev_err());
+                if (dev_malloc((void**)&d_base, sizeof(unsigned))) return fail(dev_err());
+                k_probe_smem_base<<<1, wpb * 32, per_warp * wpb, stream>>>(d_base);
+                if (chk(cudaGetLastError()) || dev_d2h(&h_base, d_base, sizeof(unsigned), stream) || dev_sync(stream)) return fail(dev_err());
+                dev_free(d_base);
+                if (h_base != LDO_SMEM_WINDOW_BASE) return fail("dynamic shared memory does not start at the window offset the kernels were built for");
+            }
+#endif
             int per_sm = 0;
             if (chk(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_exec_staged<K>, wpb * 32, per_warp * wpb))) return fail(dev_err());
             cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device);
