@@ -39,7 +39,13 @@
 #endif
 
 #if defined(__CUDA_ARCH__)
-#define LDO_LANE ((int)(threadIdx.x & 31))
+// %laneid: one S2R instead of S2R tid + mask
+__device__ __forceinline__ int ldo_laneid() {
+    unsigned l;
+    asm("mov.u32 %0, %%laneid;" : "=r"(l));
+    return (int)l;
+}
+#define LDO_LANE ldo_laneid()
 #define LDO_NLANES 32
 #define LDO_SYNCWARP() __syncwarp()
 #else
@@ -378,7 +384,7 @@ struct System {
     mutable Overlay ov_;
     LDO_HD Overlay* OV() const {
 #if defined(__CUDA_ARCH__) && !defined(LDO_GENERIC_ACCESS)
-        if (K::STAGED) return LDO_SMEM_PTR(K, Overlay, overlay, &ov_) + (threadIdx.x & 31);
+        if (K::STAGED) return LDO_SMEM_PTR(K, Overlay, overlay, &ov_) + LDO_LANE;
 #endif
         return &ov_;
     }
