@@ -81,27 +81,34 @@ for swap_i in range(1, 6):
     gathered = [torch.zeros_like(dep) for _ in range(world)]
     dist.all_gather(gathered, dep)
     sim.exchange_apply(swap_i, torch.stack(gathered).numpy())
-q2r, att, acc = sim.exchange_state(n_ladders, L)
+q2r, att, acc = sim.exchange_state(n_ladders, L, two_d={two_d!r})
 np.savez({out!r} + str(rank), q2r=q2r, att=att, acc=acc, energy=sim.engine.energies(), ctl=sim.engine.control()["temp_idx"])
 dist.destroy_process_group()
 """
 
 
-def test_two_rank_exchange_matches_single_rank(hostsim_lib, tmp_path):
+@pytest.mark.parametrize("two_d", [False, True])
+def test_two_rank_exchange_matches_single_rank(hostsim_lib, tmp_path, two_d):
     """world_size 2 over gloo: ranks hold half of every ladder, all-gather the dependent quantities and
-    must take exactly the decisions of a single rank holding everything."""
-    inp = write_inp(str(tmp_path / "pt.inp"), pt_options())
+    must take exactly the decisions of a single rank holding everything (1-D ladder and 2-D
+    temperature x stacking-multiplier grid)."""
+    if two_d:
+        opts = make_options("snodin_unbound.json", simulation_type="2d_parallel_tempering", num_reps=4, temps=[330.0, 336.0],
+                            stacking_mults=[1.0, 0.8], exchange_interval=20, swaps=4, random_seed=99)
+    else:
+        opts = pt_options()
+    inp = write_inp(str(tmp_path / "pt.inp"), opts)
     n_ladders, L = 5, len(TEMPS)
     one = Simulation(inp, n_ladders * L, 0, lib_path=hostsim_lib)
     for swap_i in range(1, 6):
         assert one.exchange_advance() == 0
         one.exchange_apply(swap_i)
-    q2r1, att1, acc1 = one.exchange_state(n_ladders, L)
+    q2r1, att1, acc1 = one.exchange_state(n_ladders, L, two_d=two_d)
     e1 = one.engine.energies().reshape(n_ladders, L, 5)
 
     script = tmp_path / "worker.py"
-    script.write_text(WORKER.format(root=ROOT, inp=inp, lib=hostsim_lib, out=str(tmp_path / "out")))
-    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29631", WORLD_SIZE="2")
+    script.write_text(WORKER.format(root=ROOT, inp=inp, lib=hostsim_lib, out=str(tmp_path / "out"), two_d=two_d))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29632" if two_d else "29631", WORLD_SIZE="2")
     procs = [subprocess.Popen([sys.executable, str(script)], env=dict(env, RANK=str(r))) for r in range(2)]
     for p in procs:
         assert p.wait(timeout=600) == 0
