@@ -201,13 +201,6 @@ struct __attribute__((aligned(8))) DomRec {
     uint8_t state;
     uint16_t pad_;
 };
-// Same fields, 4-byte aligned (per-lane placement overlays use a 12-byte stride)
-struct __attribute__((aligned(4))) DomRec4 {
-    uint32_t k;
-    int8_t ore;
-    uint8_t state;
-    uint16_t pad_;
-};
 LDO_HD inline V3 rec_pos(const DomRec& r) {
     V3 v;
     v.k = r.k;
@@ -374,21 +367,6 @@ struct System {
     const SysConst* sc;
     TempTables tt;
 
-    // Overlay (read-only candidate evaluation): domain od placed at rec, bound to oj (or -1). Staged
-    // replicas keep one overlay per lane in shared memory (lanes evaluate different candidates at the
-    // same time); otherwise it is a member and lanes work on private copies of the System object.
-    struct Overlay { // 12 bytes = 3 words: the 32 lanes' overlays hit 32 distinct banks word by word
-        short od, oj;
-        DomRec4 rec; // the candidate record of od, 4-byte aligned (one LDS for the position)
-    };
-    mutable Overlay ov_;
-    LDO_HD Overlay* OV() const {
-#if defined(__CUDA_ARCH__) && !defined(LDO_GENERIC_ACCESS)
-        if (K::STAGED) return LDO_SMEM_PTR(K, Overlay, overlay, &ov_) + LDO_LANE;
-#endif
-        return &ov_;
-    }
-
     LDO_HD SysState<K>* S() const {
         return LDO_SMEM_PTR(K, SysState<K>, state, s);
     }
@@ -406,8 +384,6 @@ struct System {
         s = s_;
         sc = sc_;
         tt = tt_;
-        OV()->od = -1;
-        OV()->oj = -1;
     }
 
     LDO_HDN void fail(int code, int detail = 0) {
@@ -417,37 +393,12 @@ struct System {
         }
     }
 
-    // ---- accessors (overlay aware) ----
-    LDO_HD V3 pos(int d) const {
-        const Overlay* o = OV();
-        if (d == o->od) {
-            V3 v;
-            v.k = o->rec.k;
-            return v;
-        }
-        return rec_pos(S()->dom[d]);
-    }
-    LDO_HD V3 ore(int d) const {
-        const Overlay* o = OV();
-        if (d == o->od) return ore_vec(o->rec.ore);
-        return ore_vec(S()->dom[d].ore);
-    }
-    LDO_HD int orc(int d) const { // orientation code 0..6
-        const Overlay* o = OV();
-        if (d == o->od) return o->rec.ore;
-        return S()->dom[d].ore;
-    }
-    LDO_HD int state(int d) const {
-        const Overlay* o = OV();
-        if (d == o->od || d == o->oj) return o->rec.state;
-        return S()->dom[d].state;
-    }
-    LDO_HD int bound(int d) const {
-        const Overlay* o = OV();
-        if (d == o->od) return o->oj;
-        if (d == o->oj) return o->od;
-        return S()->bound[d];
-    }
+    // ---- accessors ----
+    LDO_HD V3 pos(int d) const { return rec_pos(S()->dom[d]); }
+    LDO_HD V3 ore(int d) const { return ore_vec(S()->dom[d].ore); }
+    LDO_HD int orc(int d) const { return S()->dom[d].ore; } // orientation code 0..6
+    LDO_HD int state(int d) const { return S()->dom[d].state; }
+    LDO_HD int bound(int d) const { return S()->bound[d]; }
     LDO_HD int chain(int d) const { return S()->dchain[d]; }
     LDO_HD int dindex(int d) const { return S()->dindex[d]; }
     LDO_HD int ident(int d) const { return S()->ident[d]; }
@@ -1161,10 +1112,27 @@ struct System {
         return dc;
     }
 
+    // Placing d with orientation code o on the site of the unbound, NON-complementary domain j: the misbinding
+    // potentials look at the two orientations and the pair's hybridization energy only
+    // (origami_potential.cpp:938-950), so this needs no placement and is safe to call from any lane.
+    LDO_HD DeltaConfig eval_misbind(int d, int j, int o) const {
+        DeltaConfig dc;
+        dc.e = 0;
+        dc.stacked = 0;
+        dc.violated = false;
+        int cj = S()->dom[j].ore;
+        bool opposing = o == (cj < ORE_ZERO ? (cj ^ 1) : cj);
+        if (SC().misbinding_pot == MISBIND_DISALLOWED || !opposing) dc.violated = true;
+        else dc.e = hyb_energy(d, j);
+        return dc;
+    }
+
     // -----------------------------------------------------------------------------------------
-    // Read-only evaluation of placing unassigned domain d at (p, o): what
-    // OrigamiSystem::check_domain_constraints (origami_system.cpp:343-355, 828-871) returns, without
-    // touching the state. `new_state` receives the state d would take.
+    // Evaluation of placing unassigned domain d at (p, o): what OrigamiSystem::check_domain_constraints
+    // (origami_system.cpp:343-355, 828-871) returns; the state is the same before and after. Warp-uniform:
+    // every lane of the warp calls it with the same arguments (the lane-parallel evaluators of the moves look
+    // sites up on their own lanes and leave the complementary bindings to the whole warp). `new_state` receives
+    // the state d would take.
     // -----------------------------------------------------------------------------------------
     LDO_HDN DeltaConfig eval_place(int d, V3 p, int o, int* new_state, int* partner) {
         DeltaConfig dc;
@@ -1185,17 +1153,34 @@ struct System {
         }
         *partner = j;
         bool comp = S()->ident[d] == -S()->ident[j];
-        Overlay* ov = OV();
-        ov->od = (short)d;
-        ov->oj = (short)j;
-        ov->rec.k = p.k;
-        ov->rec.ore = (int8_t)o;
-        ov->rec.state = comp ? ST_BOUND : ST_MISBOUND;
-        *new_state = ov->rec.state;
+        if (!comp) {
+            *new_state = ST_MISBOUND;
+            return eval_misbind(d, j, o);
+        }
+        // The pair is entered into the domain records for the duration of the evaluation and taken out again
+        // (what the reference does, origami_system.cpp:343-355, without the occupancy-map and counter updates:
+        // the potential reads domain records only). Every lane writes the same values; the barriers keep a
+        // lane that is ahead from restoring the records while another still reads them.
+        LDO_SYNCWARP();
+        DomRec saved = S()->dom[d];
+        short saved_bd = S()->bound[d], saved_bj = S()->bound[j];
+        int st = comp ? ST_BOUND : ST_MISBOUND;
+        LDO_SYNCWARP();
+        S()->dom[d].k = p.k;
+        S()->dom[d].ore = (int8_t)o;
+        S()->dom[d].state = (uint8_t)st;
+        S()->dom[j].state = (uint8_t)st;
+        S()->bound[d] = (short)j;
+        S()->bound[j] = (short)d;
+        *new_state = st;
+        LDO_SYNCWARP();
         dc = bind_domain(d);
-        ov = OV();
-        ov->od = -1;
-        ov->oj = -1;
+        LDO_SYNCWARP();
+        S()->dom[d] = saved;
+        S()->dom[j].state = ST_UNBOUND;
+        S()->bound[d] = saved_bd;
+        S()->bound[j] = saved_bj;
+        LDO_SYNCWARP();
         if (SC().apply_mean_field_cor && !dc.violated && comp) {
             // origami_system.cpp:858-868 (counter already incremented in the reference at this point)
             int nfb = S()->num_fully_bound_pairs + 1;

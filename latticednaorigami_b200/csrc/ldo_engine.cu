@@ -440,7 +440,6 @@ struct __align__(16) WarpSmem {
     __align__(16) unsigned char aux[LDO_AUX_HOT_BYTES]; // RepAux up to (not including) stats
     MoveScratch<K> ms;
     Engine<K> eng;
-    typename System<K>::Overlay overlay[32]; // one hypothetical placement per lane
 };
 
 namespace ldo {
@@ -452,7 +451,6 @@ struct SmemLayout {
     static const unsigned engine = offsetof(WarpSmem<K>, eng);
     static const unsigned rng = offsetof(WarpSmem<K>, aux) + offsetof(RepAux, rng);
     static const unsigned bias = offsetof(WarpSmem<K>, aux) + offsetof(RepAux, bs);
-    static const unsigned overlay = offsetof(WarpSmem<K>, overlay);
 };
 } // namespace ldo
 

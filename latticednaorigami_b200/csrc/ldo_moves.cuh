@@ -501,16 +501,6 @@ struct Engine {
 #endif
     }
 
-    // Candidate evaluation on this lane: the overlay is per lane (shared memory) for staged replicas;
-    // otherwise the engine object is shared by the warp and the lane works on a private copy
-    LDO_HD DeltaConfig eval_place_lane(int dom, V3 p, int o, int* new_state, int* partner) {
-#if defined(__CUDA_ARCH__) && !defined(LDO_GENERIC_ACCESS)
-        if (K::STAGED) return sys.eval_place(dom, p, o, new_state, partner);
-#endif
-        System<K> view = sys;
-        return view.eval_place(dom, p, o, new_state, partner);
-    }
-
     // ---- RNG (random_gens.cpp:29-49) ----
     // Refill of the 4-word buffer is the only out-of-line part of the Philox path, so that the draw
     // functions stay a few instructions long inside the trial loops (instruction-cache footprint)
@@ -1024,6 +1014,8 @@ struct Engine {
     // (CBMCMovetype::calc_biases, cb_movetypes.cpp:58-102). Results: site_kind 0 = skipped,
     // 1 = empty site (orientation drawn later), 2 = binds the unbound occupant with orientation site_o.
     LDO_HDN void cb_site_weights(V3 p_prev, int dom) {
+        // lattice lookups and misbinding weights, one site per lane; a site holding the unbound complement of
+        // `dom` is left pending (kind 3)
 #pragma unroll 1
         for (int k = LDO_LANE; k < 6; k += LDO_NLANES) {
             V3 p = p_prev + ore_vec(k);
@@ -1037,11 +1029,15 @@ struct Engine {
             else if (sys.S()->dom[j].state == ST_UNBOUND) {
                 int oj = sys.S()->dom[j].ore;
                 o = oj < 6 ? (oj ^ 1) : oj;
-                int ns, partner;
-                DeltaConfig dc = eval_place_lane(dom, p, o, &ns, &partner);
-                if (!dc.violated) {
-                    kind = 2;
-                    w = exp(-dc.e);
+                if (sys.ident(dom) == -sys.ident(j)) {
+                    kind = 3;
+                }
+                else {
+                    DeltaConfig dc = sys.eval_misbind(dom, j, o);
+                    if (!dc.violated) {
+                        kind = 2;
+                        w = exp(-dc.e);
+                    }
                 }
             }
             M()->site_kind[k] = (int8_t)kind;
@@ -1049,6 +1045,17 @@ struct Engine {
             M()->site_w[k] = w;
         }
         LDO_SYNCWARP();
+        // binding evaluations of the pending sites, by the whole warp (System::eval_place is warp-uniform)
+#pragma unroll 1
+        for (int k = 0; k < 6; k++) {
+            if (M()->site_kind[k] != 3) continue;
+            int ns, partner;
+            DeltaConfig dc = sys.eval_place(dom, p_prev + ore_vec(k), M()->site_o[k], &ns, &partner);
+            LDO_SYNCWARP();
+            M()->site_kind[k] = (int8_t)(dc.violated ? 0 : 2);
+            M()->site_w[k] = dc.violated ? 0.0 : exp(-dc.e);
+            LDO_SYNCWARP();
+        }
     }
     // select_and_set_config for CBStapleRegrowth (cb_movetypes.cpp:104-160, 363-387)
     LDO_HDN void cb_select_and_set_config(int dom, int prev_dom, bool regrow_old, DD& bias) {
@@ -1784,8 +1791,24 @@ struct Engine {
         }
     }
     // Open probability data of domain `dom` at site r (calc_p_config_open, rg:315-343, for the six
-    // orientations of the site at once); read-only, callable concurrently by different lanes.
-    LDO_HDN void rg_eval_site(int dom, bool dom_is_stem, V3 r, const EpOverlay* ov, int& kind, int& o, double& pv) {
+    // orientations of the site at once), in two steps. rg_site_lookup is read-only and runs on one lane per
+    // site: an empty site is finished (kind 1), so is a site holding an unbound non-complementary domain
+    // (misbinding needs no geometry); a site holding the unbound complement is left pending (kind 3, with the
+    // orientation that binds it). rg_site_bind finishes a pending site and is executed by the whole warp, because
+    // System::eval_place enters the candidate pair into the domain records while the potential is evaluated.
+    // What a binding with energy change dc to domain j contributes (rg:326-343)
+    LDO_HD void rg_site_finish(int dom, bool dom_is_stem, V3 r, int j, const DeltaConfig& dc, const EpOverlay* ov, int& kind, double& pv) {
+        kind = 0;
+        pv = 0;
+        if (!dc.violated && cp_walks_remain(dom, r, ov)) {
+            bool same_chain = sys.chain(j) == sys.chain(dom);
+            if (same_chain || dom_is_stem || cp_endpoint_reached(dom, r, ov)) {
+                kind = 2;
+                pv = fmin(1.0, exp(-dc.e));
+            }
+        }
+    }
+    LDO_HDN void rg_site_lookup(int dom, bool dom_is_stem, V3 r, const EpOverlay* ov, int& kind, int& o, double& pv) {
         kind = 0;
         o = ORE_ZERO;
         pv = 0;
@@ -1796,19 +1819,24 @@ struct Engine {
         }
         else if (sys.S()->dom[j].state == ST_UNBOUND && sys.S()->dom[j].ore < 6) {
             o = sys.S()->dom[j].ore ^ 1;
-            int ns, partner;
-            DeltaConfig dc = eval_place_lane(dom, r, o, &ns, &partner);
-            if (!dc.violated && cp_walks_remain(dom, r, ov)) {
-                bool same_chain = sys.chain(j) == sys.chain(dom);
-                if (same_chain || dom_is_stem || cp_endpoint_reached(dom, r, ov)) {
-                    kind = 2;
-                    pv = fmin(1.0, exp(-dc.e));
-                }
+            if (sys.ident(dom) == -sys.ident(j)) {
+                kind = 3; // the complement: geometry matters, left to rg_site_bind
+            }
+            else {
+                DeltaConfig dc = sys.eval_misbind(dom, j, o);
+                rg_site_finish(dom, dom_is_stem, r, j, dc, ov, kind, pv);
             }
         }
     }
-    // Evaluates the six neighbour sites of the reference domain for the current domain, one site per
-    // lane, read-only.
+    LDO_HDN void rg_site_bind(int dom, bool dom_is_stem, V3 r, int o, const EpOverlay* ov, int& kind, double& pv) {
+        kind = 0;
+        pv = 0;
+        int ns, j;
+        DeltaConfig dc = sys.eval_place(dom, r, o, &ns, &j);
+        if (j >= 0) rg_site_finish(dom, dom_is_stem, r, j, dc, ov, kind, pv);
+    }
+    // Evaluates the six neighbour sites of the reference domain for the current domain: lookups one site per
+    // lane, then the pending bindings in turn.
     LDO_HDN void rg_compute_slot(int slot) {
         RgSlot& sl = M()->slots[slot];
         V3 refp = rec_pos(sys.S()->dom[W()->ref_d]);
@@ -1816,12 +1844,23 @@ struct Engine {
         for (int k = LDO_LANE; k < 6; k += LDO_NLANES) {
             int kind, o;
             double pv;
-            rg_eval_site(W()->d, W()->stemd != 0, refp + ore_vec(k), nullptr, kind, o, pv);
+            rg_site_lookup(W()->d, W()->stemd != 0, refp + ore_vec(k), nullptr, kind, o, pv);
             sl.kind[k] = (uint8_t)kind;
             sl.ore[k] = (int8_t)o;
             sl.p[k] = pv;
         }
         LDO_SYNCWARP();
+#pragma unroll 1
+        for (int k = 0; k < 6; k++) {
+            if (sl.kind[k] != 3) continue;
+            int kind;
+            double pv;
+            rg_site_bind(W()->d, W()->stemd != 0, refp + ore_vec(k), sl.ore[k], nullptr, kind, pv);
+            LDO_SYNCWARP();
+            sl.kind[k] = (uint8_t)kind;
+            sl.p[k] = pv;
+            LDO_SYNCWARP();
+        }
     }
     // Feeler slots of the NEXT domain for every empty parent site of the current domain, all 36
     // (parent site, feeler site) pairs spread over the lanes and evaluated read-only: the parent is not
@@ -1863,13 +1902,33 @@ struct Engine {
             V3 r = (fref_is_parent ? q : frefp) + ore_vec(k);
             int kind, o;
             double pv;
-            rg_eval_site(fd, false, r, &ov, kind, o, pv);
+            rg_site_lookup(fd, false, r, &ov, kind, o, pv);
             RgSlot& sl = M()->slots[LDO_RG_OWN_SLOTS + pc];
             sl.kind[k] = (uint8_t)kind;
             sl.ore[k] = (int8_t)o;
             sl.p[k] = pv;
         }
         LDO_SYNCWARP();
+        // pending bindings of the feeler, by the whole warp
+#pragma unroll 1
+        for (int pc = 0; pc < 6; pc++) {
+            if (!((mask >> pc) & 1)) continue;
+            RgSlot& sl = M()->slots[LDO_RG_OWN_SLOTS + pc];
+            V3 q = refp + ore_vec(pc);
+#pragma unroll 1
+            for (int k = 0; k < 6; k++) {
+                if (sl.kind[k] != 3) continue;
+                ov.add_pos = q;
+                V3 r = (fref_is_parent ? q : frefp) + ore_vec(k);
+                int kind;
+                double pv;
+                rg_site_bind(fd, false, r, sl.ore[k], &ov, kind, pv);
+                LDO_SYNCWARP();
+                sl.kind[k] = (uint8_t)kind;
+                sl.p[k] = pv;
+                LDO_SYNCWARP();
+            }
+        }
         W()->memo_mask = mask;
     }
     // prepare_for_regrowth (rg:264-286)
