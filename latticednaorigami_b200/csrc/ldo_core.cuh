@@ -4,9 +4,11 @@
 // Execution model. Every replica is owned by one warp. All 32 lanes execute the serial Monte Carlo
 // logic redundantly on identical data (warp-uniform control flow: loads broadcast, stores write the
 // same value); the places where a move evaluates several candidate lattice sites are distributed
-// over lanes (`for (k = LDO_LANE; k < n; k += LDO_NLANES)`), through a READ-ONLY evaluator: a
-// candidate placement is examined through an overlay `View` instead of the reference's
-// set-then-roll-back (origami_system.cpp:343-355), so lanes never race on the replica state.
+// over lanes (`for (k = LDO_LANE; k < n; k += LDO_NLANES)`) as far as they are read-only: the lattice
+// lookup, the ideal-walk predicates and the misbinding weight of a site. A candidate that binds its
+// complement is evaluated by the whole warp (eval_place): the pair is entered into the domain records,
+// the potential evaluated, and the records restored - the reference's set-then-roll-back
+// (origami_system.cpp:343-355) without the occupancy-map and counter updates.
 //
 // What this restates (reference file:line):
 //   * Domain records, chain walk, twist/kink/junction constraints     domain.hpp:14-92, domain.cpp:9-118
@@ -358,7 +360,7 @@ LDO_HD inline uint32_t hash_slot(uint32_t key) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// System: state + constants + tables, with an optional overlay of one hypothetical placement
+// System: state + constants + tables
 // ---------------------------------------------------------------------------------------------
 
 template <class K>
