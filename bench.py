@@ -5,7 +5,7 @@ Workload (BASELINE.json configs[2]): examples/ptmc.inp general
 `ut_parallel_tempering`, exchange_interval 100, 32-temperature ladder 330..361 K (1 K steps), 16384
 replicas per GPU = 512*N ladders (BASELINE: ">= 4096 concurrent snodin replicas per B200"; four waves of the
 persistent run kernel keep every warp slot busy through the tail of slow, cold replicas — 4096 per GPU
-is reported in profiles/README.md), ladder slots dealt round-robin over the N GPUs (slot k on GPU k % N), start
+is reported in profiles/README.md), ladder slots dealt in serpentine order over the N GPUs (0 1 .. N-1, N-1 .. 0, ...: equal cost per GPU), start
 from snodin_unbound, moveset_standard. One "step" = one exchange round: 100 attempted moves on every
 replica, collection of the exchange quantities, (N > 1: NCCL all-gather), on-device swap decisions and
 the energy rebuild that follows a control-variable update.

@@ -251,9 +251,10 @@ int ldo_center(ldo_engine* e, int centering_domain);
 
 /* Replaces: PTGCMCSimulation::attempt_exchange for the 1-D variants (ptmc_simulation.cpp:360-412)
  * over `n_ladders` independent ladders of `ladder_len` control-variable slots, sharded over `n_ranks`
- * GPUs: the slots of EVERY ladder are dealt round-robin, replica k of ladder l living on rank k % n_ranks
- * at local index l*S + k/n_ranks (S = ladder_len / n_ranks), so every neighbour pair straddles two GPUs
- * and the temperature-dependent cost of a move is balanced across them. Decisions
+ * GPUs: the slots of EVERY ladder are dealt in serpentine order (ranks 0 1 .. G-1, G-1 .. 1 0, 0 1 ..): replica
+ * k of ladder l lives on rank (k/G even ? k%G : G-1-k%G) at local index l*S + k/G (S = ladder_len / n_ranks), so
+ * nearly every neighbour pair straddles two GPUs and the temperature-dependent cost of a move is the same on all
+ * of them. Decisions
  * are taken on device from a Philox stream shared by all ranks (identical on every rank, no
  * communication); accepted swaps relabel control variables (temperature table index and multipliers),
  * configurations never move. `dependent` is the all-gathered, rank-major [n_ranks][R][3 + n_staple_types]

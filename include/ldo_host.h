@@ -27,7 +27,7 @@ const char* ldo_host_last_error(void);
 /* Reads `inp_path` (parser.cpp:477-479 format) and builds an engine with `n_replicas` replicas on CUDA
  * device `device`. `rank` / `n_ranks` place the engine inside a multi-GPU ensemble (0 / 1 for a single
  * GPU): independent replicas are simply numbered rank * n_replicas + r; for the replica-exchange types
- * every rank holds num_reps / n_ranks slots of every ladder, dealt round-robin (see ldo_exchange_pt), i.e.
+ * every rank holds num_reps / n_ranks slots of every ladder, dealt in serpentine order (see ldo_exchange_pt), i.e.
  * n_replicas / (num_reps / n_ranks) ladders. Every replica starts from the configuration of the system
  * file (or restart_traj_file / restart_step). With n_ranks > 1 random_seed must be set (all ranks must
  * share the exchange stream). Returns NULL on error. */

@@ -100,6 +100,10 @@ int bias_type_code(std::string const& t) {
     return LDO_BIAS_GRID;
 }
 
+// Ladder slot held by this rank at local slot index b: the slots of a ladder are dealt to the ranks in serpentine
+// order (ldo_exchange_pt, ldo_b200.h), which balances the temperature-dependent cost of a move across GPUs
+int ladder_slot_of(ldo_sim const& s, int b) { return b * s.n_ranks + ((b & 1) ? s.n_ranks - 1 - s.rank : s.rank); }
+
 std::string replica_filebase(ldo_sim& s, int r) {
     if (s.is_us) {
         // MWUSGCMCSimulation::setup_window_variables (us_simulation.cpp:486-501) + "_iter-n" (:107,131)
@@ -840,7 +844,7 @@ ldo_sim* ldo_sim_create(const char* inp_path, int n_replicas, int device, int ra
             s->check(ldo_set_exchange_ladder(s->eng, s->num_reps, ladder_ti.data(), cm.data(), bmm.data(), smm.data()));
             int slots_per_rank {s->num_reps / s->n_ranks};
             for (int r {0}; r != n_replicas; r++) {
-                int k {s->rank + (r % slots_per_rank) * s->n_ranks};
+                int k {ladder_slot_of(*s, r % slots_per_rank)};
                 ti[r] = ladder_ti[k];
                 um[r] = cm[k];
                 // OneDPTGCMCSimulation::initialize_control_qs stores the bias multiplier in the wrong
@@ -894,7 +898,7 @@ ldo_sim* ldo_sim_create(const char* inp_path, int n_replicas, int device, int ra
             int slots_per_rank {s->num_reps / s->n_ranks};
             std::vector<unsigned int> sub(n_replicas);
             for (int r {0}; r != n_replicas; r++) {
-                int l {r / slots_per_rank}, k {s->rank + (r % slots_per_rank) * s->n_ranks};
+                int l {r / slots_per_rank}, k {ladder_slot_of(*s, r % slots_per_rank)};
                 sub[r] = static_cast<unsigned int>(l * s->num_reps + k);
             }
             s->check(ldo_seed_subsequences(s->eng, seed, sub.data()));

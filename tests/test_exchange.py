@@ -115,11 +115,13 @@ def test_two_rank_exchange_matches_single_rank(hostsim_lib, tmp_path, two_d):
     outs = [np.load(str(tmp_path / f"out{r}.npz")) for r in range(2)]
     for o in outs:
         assert np.array_equal(o["q2r"], q2r1) and np.array_equal(o["att"], att1) and np.array_equal(o["acc"], acc1)
-    # same trajectories: replica k of ladder l lives on rank k % 2 at local index l * S + k // 2
+    # same trajectories: replica k of ladder l lives on rank (k % 2, reversed in odd groups of 2) at local
+    # index l * S + k // 2 (serpentine dealing of the ladder slots)
     S = L // 2
     for l in range(n_ladders):
         for k in range(L):
-            got = outs[k % 2]["energy"][l * S + k // 2]
+            rank_of_k = k % 2 if (k // 2) % 2 == 0 else 1 - k % 2
+            got = outs[rank_of_k]["energy"][l * S + k // 2]
             assert np.array_equal(got, e1[l, k]), (l, k)
 
 
