@@ -234,3 +234,21 @@ def test_swap_probability_matches_reference_code(hostsim_lib, oracle, tmp_path):
         assert abs(ours - want) <= 1e-12 * max(want, 1e-300), (ours, want)
         seen_partial += 0.0 < want < 1.0
     assert seen_partial > 20
+
+
+def test_two_d_driver_writes_swap_file(hostsim_lib, tmp_path):
+    """ldo_sim_run for 2d_parallel_tempering: the .swp header lists temperature / staple_u_mult / stacking_mult of
+    every slot (m_exchange_q_is, ptmc_simulation.cpp:92-104,446-448) and every entry is a permutation."""
+    temps, smults = [330.0, 336.0], [1.0, 0.8]
+    opts = make_options("snodin_unbound.json", simulation_type="2d_parallel_tempering", num_reps=4, temps=temps,
+                        stacking_mults=smults, exchange_interval=10, swaps=4, random_seed=5, configs_output_freq=10,
+                        max_pt_dur=1e9, output_filebase=str(tmp_path / "pt2d"))
+    sim = Simulation(write_inp(str(tmp_path / "pt2d.inp"), opts), 4, 0, lib_path=hostsim_lib)
+    sim.run()
+    lines = (tmp_path / "pt2d.swp").read_text().splitlines()
+    assert lines[0].split() == ["330/1/1/", "330/1/0.8/", "336/1/1/", "336/1/0.8/"]
+    assert len(lines) >= 5
+    for row in lines[1:]:
+        assert sorted(int(x) for x in row.split()) == [0, 1, 2, 3]
+    # per-replica configuration files carry the "-<rank>" postfix of the reference
+    assert (tmp_path / "pt2d-0.trj").exists() and (tmp_path / "pt2d-3.trj").exists()
