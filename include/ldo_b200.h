@@ -196,6 +196,11 @@ int ldo_get_state(ldo_engine* e, int replica, int* n_chains, int* chain_index, i
 /* Replaces: GCMCSimulation::simulate (simulation.cpp:568-653) for every replica: n_steps attempted
  * moves each, centring every centering_freq steps and check_all_constraints every
  * constraint_check_freq steps (0 = never), step counter continuing from the previous call. */
+/* Sets the step counter of every replica (the `step` the centring / constraint-check frequencies refer to). The
+ * annealing driver needs it: AnnealingGCMCSimulation::run adds simulate()'s return value - the LAST step number
+ * plus one - to its step counter (annealing_simulation.cpp:47, simulation.cpp:574,652), so the step numbers jump
+ * between temperatures. */
+int ldo_set_step(ldo_engine* e, long long step);
 int ldo_run(ldo_engine* e, long long n_steps, int centering_freq, int centering_domain,
             int constraint_check_freq);
 /* Per-replica status: 0 ok, else the LDO_ERR_* code mirroring the reference's exception sites. */

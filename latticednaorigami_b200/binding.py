@@ -18,7 +18,7 @@ ENGINE_SYMBOLS = [
     "ldo_get_state", "ldo_run", "ldo_get_status", "ldo_run_async", "ldo_synchronize", "ldo_stream",
     "ldo_get_energies", "ldo_get_counters", "ldo_get_staple_counts", "ldo_get_order_params",
     "ldo_get_move_stats", "ldo_get_run_timing", "ldo_recompute_energies", "ldo_check_all_constraints", "ldo_center",
-    "ldo_set_exchange_ladder", "ldo_exchange_collect", "ldo_exchange_pt", "ldo_exchange_pt_2d", "ldo_exchange_acceptance_p", "ldo_get_reduced_staple_u", "ldo_exchange_buffers",
+    "ldo_set_exchange_ladder", "ldo_exchange_collect", "ldo_exchange_pt", "ldo_exchange_pt_2d", "ldo_exchange_acceptance_p", "ldo_get_reduced_staple_u", "ldo_set_step", "ldo_exchange_buffers",
     "ldo_exchange_windows", "ldo_launch_count", "ldo_state_bytes", "ldo_checkpoint_size", "ldo_checkpoint_save", "ldo_checkpoint_load",
 ]
 HOST_SYMBOLS = [
@@ -97,6 +97,7 @@ def load(path=None):
         "ldo_exchange_pt": (i, [vp, i, ll, i, i, i, i, vp, vp, vp, vp]),
         "ldo_exchange_pt_2d": (i, [vp, ll, i, i, i, i, i, vp, vp, vp, vp]),
         "ldo_get_reduced_staple_u": (i, [vp, vp]),
+        "ldo_set_step": (i, [vp, ll]),
         "ldo_exchange_acceptance_p": (C.c_double, [i, vp, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, vp, vp]),
         "ldo_exchange_buffers": (i, [vp, i, vp, vp, vp]),
         "ldo_exchange_windows": (i, [vp, ll, i, i, i, i, vp, vp, vp, vp]),

@@ -1630,6 +1630,13 @@ void ldo_engine_destroy(ldo_engine* e) {
 
 const char* ldo_last_error(const ldo_engine* e) { return e ? e->b->err.c_str() : g_create_error.c_str(); }
 int ldo_num_replicas(const ldo_engine* e) { return e->b->R; }
+int ldo_set_step(ldo_engine* e, long long step) {
+    EngineBase* b = e->b;
+    std::vector<RepAux> aux(b->R);
+    if (b->get_aux(0, b->R, aux.data())) return -1;
+    for (int r = 0; r < b->R; r++) aux[r].step = step;
+    return b->put_aux(0, b->R, aux.data());
+}
 int ldo_get_reduced_staple_u(ldo_engine* e, double* out) {
     for (size_t t = 0; t < e->b->reduced_staple_u.size(); t++) out[t] = e->b->reduced_staple_u[t];
     return (int)e->b->reduced_staple_u.size();

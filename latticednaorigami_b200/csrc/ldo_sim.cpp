@@ -969,9 +969,15 @@ int ldo_sim_run(ldo_sim* s) {
         }
         else if (st == "annealing") {
             // AnnealingGCMCSimulation::run (annealing_simulation.cpp:38-49)
+            // `step += simulate(m_steps_per_temp, step)`: simulate returns the last step number plus one
+            // (simulation.cpp:574,652), so the step numbers of the output files jump between temperatures:
+            // 1..n, 2(n+1)+1.., ... Reproduced, including for the centring / constraint-check frequencies.
             for (size_t i {0}; i != s->temps.size(); i++) {
                 set_all_control(*s, static_cast<int>(i));
+                long long start {s->step};
                 if (!simulate(*s, p.m_steps_per_temp)) break;
+                s->step = start + (start + p.m_steps_per_temp + 1);
+                s->check(ldo_set_step(s->eng, s->step));
             }
         }
         else if (s->is_us) {

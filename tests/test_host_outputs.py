@@ -42,3 +42,21 @@ def test_output_files_match_reference_cli(hostsim_lib, oracle, tmp_path):
     ref_moves = (tmp_path / "ref.moves").read_text().splitlines()[:4]
     our_moves = (tmp_path / "our.moves").read_text().splitlines()[:4]
     assert our_moves == ref_moves
+
+
+def test_annealing_output_files_match_reference_cli(hostsim_lib, oracle, tmp_path):
+    """The annealing driver (annealing_simulation.cpp:38-49) on the same frozen trajectory: three temperatures,
+    energies and order parameters re-evaluated at every temperature step."""
+    def options(base):
+        opts = _options(tmp_path, base)
+        opts.update(simulation_type="annealing", max_temp=302, min_temp=300, temp_interval=1, steps_per_temp=20)
+        return opts
+    ref_inp = write_inp(str(tmp_path / "ref_a.inp"), options("refa"))
+    subprocess.run([oracle.CLI_PATH, "-i", ref_inp], check=True, capture_output=True)
+    sim = Simulation(write_inp(str(tmp_path / "our_a.inp"), options("oura")), 1, 0, lib_path=hostsim_lib)
+    sim.run()
+    for ext in EXTS:
+        ref, our = (tmp_path / ("refa" + ext)).read_text(), (tmp_path / ("oura" + ext)).read_text()
+        assert ref, ext
+        assert our == ref, f"{ext} differs from the reference's file"
+    assert len((tmp_path / "oura.ene").read_text().splitlines()) == 7  # header + 60 steps / 10
