@@ -147,6 +147,11 @@ int ldo_set_temperature_tables(ldo_engine* e, int n_temps, int n_ident, const do
 
 /* Replaces: GCMCSimulation::construct_movetypes (simulation.cpp:267-320). */
 int ldo_set_moveset(ldo_engine* e, int n, const ldo_movetype_desc* movetypes, int allow_nonsensical_ps);
+/* Production (Philox) mode only. on != 0: the recoil-growth moves draw in the reference's serial trial order
+ * (rg_movetypes.cpp:193-198, 378-402, 435-440) instead of re-associating the draws to lanes - the branches a
+ * replay tape runs, driven by Philox. Same ensemble; slower. Used to validate the lane-parallel branches
+ * against the serial ones on the same device (tests/test_production_parity.py). Default off. */
+int ldo_set_reference_draw_order(ldo_engine* e, int on);
 /* Replaces: SystemOrderParams::setup_ops (order_params.cpp:471-577), move-update kind. */
 int ldo_set_order_params(ldo_engine* e, int n, const ldo_order_param_desc* ops);
 /* Replaces: SystemBiases::setup_biases (bias_functions.cpp:334-430), move-update kind. */
@@ -212,6 +217,9 @@ int ldo_synchronize(ldo_engine* e);
 /* The CUDA stream every kernel of this engine is launched on (cudaStream_t as void*). */
 void* ldo_stream(ldo_engine* e);
 
+/* Build marker of the library: "cuda sm_100a" for the product. Callers that must not run on anything else
+ * (the Python binding) check it. */
+const char* ldo_build_info(void);
 /* Number of CUDA kernels this engine has launched so far. */
 long long ldo_launch_count(const ldo_engine* e);
 /* Bytes of one replica's persistent state in HBM (what a run launch loads and stores once). */
@@ -220,10 +228,15 @@ unsigned long ldo_state_bytes(const ldo_engine* e);
 /* ---- checkpoint / resume ------------------------------------------------------------------------ */
 
 /* Device-side get_state / set_state for restart: `count` replicas starting at `first`
- * as opaque blobs of ldo_checkpoint_size() bytes each (configuration, occupancy table, counters,
- * running energy, RNG counter, control variables, bias state, move statistics). Blobs are only valid
- * for an engine created with the same system descriptor; tapes are not part of a checkpoint. The host
- * buffer may be pinned; ldo_checkpoint_load is asynchronous on the engine's stream. */
+ * as `count` contiguous opaque blobs of ldo_checkpoint_size() bytes each, blob i at host + i * size
+ * (configuration, occupancy table, counters, running energy, RNG counter, control variables, bias state,
+ * move statistics and - when a Grid bias is configured - the replica's grid-bias values and visit
+ * histogram). A blob is self-contained: any sub-range of a saved buffer can be loaded, into any replica
+ * index of an engine created with the same system descriptor, moveset, order parameters and biases (after
+ * ldo_exchange_windows relabelled grid ownership, load whole window ladders). Tapes are not part of a
+ * checkpoint: a loaded replica has none attached. ldo_checkpoint_size() depends on whether a Grid bias is
+ * configured, so query it after ldo_set_biases. The host buffer may be pinned; ldo_checkpoint_load is
+ * asynchronous on the engine's stream. */
 unsigned long ldo_checkpoint_size(const ldo_engine* e);
 int ldo_checkpoint_save(ldo_engine* e, int first, int count, void* host);
 int ldo_checkpoint_load(ldo_engine* e, int first, int count, const void* host);

@@ -19,7 +19,7 @@ ENGINE_SYMBOLS = [
     "ldo_get_energies", "ldo_get_counters", "ldo_get_staple_counts", "ldo_get_order_params",
     "ldo_get_move_stats", "ldo_get_run_timing", "ldo_recompute_energies", "ldo_check_all_constraints", "ldo_center",
     "ldo_set_exchange_ladder", "ldo_exchange_collect", "ldo_exchange_pt", "ldo_exchange_pt_2d", "ldo_exchange_acceptance_p", "ldo_get_reduced_staple_u", "ldo_set_step", "ldo_exchange_buffers",
-    "ldo_exchange_windows", "ldo_launch_count", "ldo_state_bytes", "ldo_checkpoint_size", "ldo_checkpoint_save", "ldo_checkpoint_load",
+    "ldo_exchange_windows", "ldo_set_reference_draw_order", "ldo_build_info", "ldo_launch_count", "ldo_state_bytes", "ldo_checkpoint_size", "ldo_checkpoint_save", "ldo_checkpoint_load",
 ]
 HOST_SYMBOLS = [
     "ldo_host_last_error", "ldo_sim_create", "ldo_sim_destroy", "ldo_sim_engine", "ldo_sim_run",
@@ -47,7 +47,8 @@ _libs = {}
 
 
 def load(path=None):
-    """Load the CUDA library. Fails loudly when it is missing: there is no CPU path."""
+    """Load the CUDA library. Fails loudly when it is missing or is not a CUDA build: there is no CPU path.
+    `path` / LDO_B200_LIB may name another CUDA build of the same sources (profiling variants under ab/)."""
     path = path or os.environ.get("LDO_B200_LIB") or LIB_PATH
     if path in _libs:
         return _libs[path]
@@ -55,7 +56,18 @@ def load(path=None):
         raise LdoError(
             f"{path} not found: build the CUDA library first (make, or __graft_entry__.build()); "
             "latticednaorigami_b200 has no CPU fallback")
-    L = C.CDLL(path)
+    L = bind(C.CDLL(path))
+    info = L.ldo_build_info().decode()
+    if not info.startswith("cuda"):
+        raise LdoError(f"{path} is not a CUDA build of the engine ({info!r}); latticednaorigami_b200 has no CPU path")
+    _libs[path] = L
+    return L
+
+
+def bind(L):
+    """Attach the C-ABI signatures of include/ldo_b200.h and include/ldo_host.h to an already opened library."""
+    if not hasattr(L, "ldo_build_info"):
+        raise LdoError("library exports no ldo_build_info marker")
     vp, i, d, ll = C.c_void_p, C.c_int, C.c_double, C.c_longlong
     sig = {
         "ldo_engine_create": (i, [vp, i, i, vp]),
@@ -101,6 +113,8 @@ def load(path=None):
         "ldo_exchange_acceptance_p": (C.c_double, [i, vp, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, C.c_double, vp, vp]),
         "ldo_exchange_buffers": (i, [vp, i, vp, vp, vp]),
         "ldo_exchange_windows": (i, [vp, ll, i, i, i, i, vp, vp, vp, vp]),
+        "ldo_set_reference_draw_order": (i, [vp, i]),
+        "ldo_build_info": (C.c_char_p, []),
         "ldo_launch_count": (ll, [vp]),
         "ldo_state_bytes": (C.c_ulong, [vp]),
         "ldo_checkpoint_size": (C.c_ulong, [vp]),
@@ -133,7 +147,6 @@ def load(path=None):
         fn = getattr(L, name)
         fn.restype = res
         fn.argtypes = args
-    _libs[path] = L
     return L
 
 
@@ -181,6 +194,9 @@ class Engine:
         if len(bad):
             r = int(bad[0])
             raise LdoError(f"replica {r}: {STATUS_NAMES.get(int(st[r]), st[r])} (detail {int(dt[r])})")
+
+    def set_reference_draw_order(self, on=True):
+        self._check(self.L.ldo_set_reference_draw_order(self.h, 1 if on else 0))
 
     def seed(self, seed, first_subsequence=0):
         self._check(self.L.ldo_seed(self.h, int(seed), int(first_subsequence)))
@@ -341,8 +357,10 @@ class Engine:
 class Simulation:
     """A simulation described by a reference-format ``.inp`` file (ldo_sim_create)."""
 
-    def __init__(self, inp_path, n_replicas=1, device=0, rank=0, n_ranks=1, lib_path=None):
-        self.L = load(lib_path)
+    def __init__(self, inp_path, n_replicas=1, device=0, rank=0, n_ranks=1, lib_path=None, lib=None):
+        # `lib`: an already bound library handle (the test-suite's host emulation is loaded by tests/conftest.py,
+        # never through load())
+        self.L = lib if lib is not None else load(lib_path)
         self.h = self.L.ldo_sim_create(os.fsencode(inp_path), n_replicas, device, rank, n_ranks)
         if not self.h:
             raise LdoError(self.L.ldo_host_last_error().decode())
@@ -407,8 +425,8 @@ class Simulation:
 
 # ---- GPU-free host helpers (table builder, parameter-file reader) ---------------------------------
 
-def host_energy_tables(inp_path, temp, lib_path=None):
-    L = load(lib_path)
+def host_energy_tables(inp_path, temp, lib_path=None, lib=None):
+    L = lib if lib is not None else load(lib_path)
     n = C.c_int(0)
     if L.ldo_host_energy_tables(os.fsencode(inp_path), temp, C.byref(n), None, None, None, None, None) != 0:
         raise LdoError(L.ldo_host_last_error().decode())
@@ -421,31 +439,31 @@ def host_energy_tables(inp_path, temp, lib_path=None):
     return {"n_ident": n.value, "energy": e, "enthalpy": h, "entropy": s, "present": present, "init": init}
 
 
-def host_inp_value(inp_path, key, lib_path=None):
-    L = load(lib_path)
+def host_inp_value(inp_path, key, lib_path=None, lib=None):
+    L = lib if lib is not None else load(lib_path)
     buf = C.create_string_buffer(4096)
     if L.ldo_host_inp_value(os.fsencode(inp_path), key.encode(), buf, 4096) != 0:
         raise LdoError(L.ldo_host_last_error().decode())
     return buf.value.decode()
 
 
-def host_nn_unitless_thermo(seq, temp, cation_M, lib_path=None):
-    L = load(lib_path)
+def host_nn_unitless_thermo(seq, temp, cation_M, lib_path=None, lib=None):
+    L = lib if lib is not None else load(lib_path)
     out = np.zeros(2)
     if L.ldo_host_nn_unitless_thermo(seq.encode(), temp, cation_M, _ptr(out)) != 0:
         raise LdoError(L.ldo_host_last_error().decode())
     return out[0], out[1]
 
 
-def host_longest_contig_complement(a, b, lib_path=None):
-    L = load(lib_path)
+def host_longest_contig_complement(a, b, lib_path=None, lib=None):
+    L = lib if lib is not None else load(lib_path)
     buf = C.create_string_buffer(4096)
     L.ldo_host_longest_contig_complement(a.encode(), b.encode(), buf, 4096)
     return [x for x in buf.value.decode().split("\n") if x]
 
 
-def host_no_walks(start, end, steps, lib_path=None):
-    L = load(lib_path)
+def host_no_walks(start, end, steps, lib_path=None, lib=None):
+    L = lib if lib is not None else load(lib_path)
     s = np.asarray(start, dtype=np.int32)
     e = np.asarray(end, dtype=np.int32)
     return bool(L.ldo_host_no_walks(_ptr(s), _ptr(e), steps))

@@ -886,6 +886,87 @@ __global__ void k_exchange(ExchangeArgs x) {
 #endif
 
 // ---------------------------------------------------------------------------------------------
+// Checkpoint blobs (ldo_checkpoint_save / ldo_checkpoint_load): pack / unpack between the engine's arrays and a
+// contiguous staging buffer of per-replica blobs, so that the host copy is one transfer
+// ---------------------------------------------------------------------------------------------
+template <class K>
+struct BlobArgs {
+    SysState<K>* states;
+    RepAux* aux;
+    double* grid_vals;
+    long long* grid_visits;
+    unsigned char* stage;
+    int first, count;
+    unsigned blob_bytes;
+    bool with_grid;
+};
+// `lane` / `nlanes`: the words of one blob are spread over the lanes of a warp (1 on the host)
+template <class K>
+LDO_HD inline void blob_copy_words(void* dst, const void* src, size_t bytes, int lane, int nlanes) {
+    const uint32_t* s = reinterpret_cast<const uint32_t*>(src);
+    uint32_t* d = reinterpret_cast<uint32_t*>(dst);
+    for (size_t i = lane; i < bytes / 4; i += nlanes) d[i] = s[i];
+}
+template <class K>
+LDO_HD inline void blob_pack_one(const BlobArgs<K>& b, int i, int lane = 0, int nlanes = 1) {
+    int r = b.first + i;
+    unsigned char* o = b.stage + (size_t)i * b.blob_bytes;
+    blob_copy_words<K>(o, &b.states[r], sizeof(SysState<K>), lane, nlanes);
+    blob_copy_words<K>(o + sizeof(SysState<K>), &b.aux[r], sizeof(RepAux), lane, nlanes);
+    if (b.with_grid) {
+        size_t slot = (size_t)b.aux[r].bs.grid_slot * LDO_GRID_CAP;
+        unsigned char* g = o + sizeof(SysState<K>) + sizeof(RepAux);
+        blob_copy_words<K>(g, b.grid_vals + slot, sizeof(double) * LDO_GRID_CAP, lane, nlanes);
+        blob_copy_words<K>(g + sizeof(double) * LDO_GRID_CAP, b.grid_visits + slot, sizeof(long long) * LDO_GRID_CAP, lane, nlanes);
+    }
+#if defined(__CUDA_ARCH__)
+    __syncwarp();
+#endif
+    if (lane == 0) {
+        // tapes are not part of a checkpoint: no device pointer leaves the engine
+        RepAux* a = reinterpret_cast<RepAux*>(o + sizeof(SysState<K>));
+        a->rng.tape = nullptr;
+        a->rng.tape_len = 0;
+        a->rng.tape_pos = 0;
+    }
+}
+template <class K>
+LDO_HD inline void blob_unpack_one(const BlobArgs<K>& b, int i, int lane = 0, int nlanes = 1) {
+    int r = b.first + i;
+    const unsigned char* o = b.stage + (size_t)i * b.blob_bytes;
+    blob_copy_words<K>(&b.states[r], o, sizeof(SysState<K>), lane, nlanes);
+    blob_copy_words<K>(&b.aux[r], o + sizeof(SysState<K>), sizeof(RepAux), lane, nlanes);
+    if (b.with_grid) {
+        size_t slot = (size_t)r * LDO_GRID_CAP;
+        const unsigned char* g = o + sizeof(SysState<K>) + sizeof(RepAux);
+        blob_copy_words<K>(b.grid_vals + slot, g, sizeof(double) * LDO_GRID_CAP, lane, nlanes);
+        blob_copy_words<K>(b.grid_visits + slot, g + sizeof(double) * LDO_GRID_CAP, sizeof(long long) * LDO_GRID_CAP, lane, nlanes);
+    }
+#if defined(__CUDA_ARCH__)
+    __syncwarp();
+#endif
+    if (lane == 0) {
+        RepAux& a = b.aux[r];
+        a.rng.tape = nullptr;
+        a.rng.tape_len = 0;
+        a.rng.tape_pos = 0;
+        a.bs.grid_slot = r;
+    }
+}
+#ifndef LDO_HOSTSIM
+template <class K>
+__global__ void k_blob_pack(BlobArgs<K> b) {
+    int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (i < b.count) blob_pack_one(b, i, threadIdx.x & 31, 32);
+}
+template <class K>
+__global__ void k_blob_unpack(BlobArgs<K> b) {
+    int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (i < b.count) blob_unpack_one(b, i, threadIdx.x & 31, 32);
+}
+#endif
+
+// ---------------------------------------------------------------------------------------------
 // Engine object
 // ---------------------------------------------------------------------------------------------
 
@@ -1013,6 +1094,7 @@ struct EngineImpl: EngineBase {
         dev_free(d_slot_tidx);
         dev_free(d_slot_vals);
         dev_free(d_red_u);
+        dev_free(d_blob_stage);
         for (void* p: tape_bufs) dev_free(p);
         if (g_const_owner == this) g_const_owner = nullptr;
 #ifndef LDO_HOSTSIM
@@ -1226,31 +1308,65 @@ struct EngineImpl: EngineBase {
         return 0;
     }
 
-    // Opaque checkpoint blobs: state + per-replica auxiliary data (RNG, control, biases, statistics)
+    // Opaque checkpoint blobs, one per replica, contiguous: [SysState][RepAux][grid values][grid visits]
+    // (the grid part only when a Grid bias is configured). A blob is self-contained: the tape pointer is
+    // cleared (tapes are not part of a checkpoint) and the replica's grid-bias slice travels with it, so a
+    // blob saved from replica i can be loaded into replica j of another engine of the same description
+    // (on load the replica owns grid slot j again, whatever window exchange had relabelled before).
     long long* run_timing_ptr() override { return P.run_timing; }
-    size_t blob_size() override { return sizeof(SysState<K>) + sizeof(RepAux); }
+    size_t grid_blob_bytes() const { return shared.has_grid && P.grid_vals ? (sizeof(double) + sizeof(long long)) * LDO_GRID_CAP : 0; }
+    size_t blob_size() override { return sizeof(SysState<K>) + sizeof(RepAux) + grid_blob_bytes(); }
     size_t state_bytes() override { return sizeof(SysState<K>); }
+    unsigned char* d_blob_stage = nullptr;
+    size_t blob_stage_cap = 0;
+    int ensure_blob_stage(size_t bytes) {
+        if (bytes <= blob_stage_cap) return 0;
+        dev_free(d_blob_stage);
+        d_blob_stage = nullptr;
+        blob_stage_cap = 0;
+        if (dev_malloc((void**)&d_blob_stage, bytes)) return fail(dev_err());
+        blob_stage_cap = bytes;
+        return 0;
+    }
     int get_blobs(int first, int count, void* host) override {
-        unsigned char* h = static_cast<unsigned char*>(host);
+        size_t bs = blob_size();
+        if (ensure_blob_stage(bs * count)) return -1;
+        BlobArgs<K> b {P.states, P.aux, P.grid_vals, P.grid_visits, d_blob_stage, first, count, (unsigned)bs, grid_blob_bytes() != 0};
 #ifdef LDO_HOSTSIM
-        memcpy(h, P.states + first, sizeof(SysState<K>) * count);
-        memcpy(h + sizeof(SysState<K>) * count, P.aux + first, sizeof(RepAux) * count);
+        for (int i = 0; i < count; i++) blob_pack_one(b, i);
+        memcpy(host, d_blob_stage, bs * count);
 #else
-        if (chk(cudaMemcpyAsync(h, P.states + first, sizeof(SysState<K>) * count, cudaMemcpyDeviceToHost, stream))) return fail(dev_err());
-        if (chk(cudaMemcpyAsync(h + sizeof(SysState<K>) * count, P.aux + first, sizeof(RepAux) * count, cudaMemcpyDeviceToHost, stream))) return fail(dev_err());
+        k_blob_pack<K><<<(count + 3) / 4, 128, 0, stream>>>(b);
+        if (chk(cudaGetLastError())) return fail(dev_err());
+        launches++;
+        if (chk(cudaMemcpyAsync(host, d_blob_stage, bs * count, cudaMemcpyDeviceToHost, stream))) return fail(dev_err());
         if (dev_sync(stream)) return fail(dev_err());
 #endif
         return 0;
     }
     int put_blobs(int first, int count, const void* host) override {
-        const unsigned char* h = static_cast<const unsigned char*>(host);
+        size_t bs = blob_size();
+        if (ensure_blob_stage(bs * count)) return -1;
+        BlobArgs<K> b {P.states, P.aux, P.grid_vals, P.grid_visits, d_blob_stage, first, count, (unsigned)bs, grid_blob_bytes() != 0};
 #ifdef LDO_HOSTSIM
-        memcpy(P.states + first, h, sizeof(SysState<K>) * count);
-        memcpy(P.aux + first, h + sizeof(SysState<K>) * count, sizeof(RepAux) * count);
+        memcpy(d_blob_stage, host, bs * count);
+        for (int i = 0; i < count; i++) blob_unpack_one(b, i);
 #else
-        if (chk(cudaMemcpyAsync(P.states + first, h, sizeof(SysState<K>) * count, cudaMemcpyHostToDevice, stream))) return fail(dev_err());
-        if (chk(cudaMemcpyAsync(P.aux + first, h + sizeof(SysState<K>) * count, sizeof(RepAux) * count, cudaMemcpyHostToDevice, stream))) return fail(dev_err());
+        if (chk(cudaMemcpyAsync(d_blob_stage, host, bs * count, cudaMemcpyHostToDevice, stream))) return fail(dev_err());
+        k_blob_unpack<K><<<(count + 3) / 4, 128, 0, stream>>>(b);
+        if (chk(cudaGetLastError())) return fail(dev_err());
+        launches++;
 #endif
+        // the tapes of the overwritten replicas are gone with their aux records
+        for (int i = 0; i < count; i++) {
+            if (tape_bufs[first + i]) {
+#ifndef LDO_HOSTSIM
+                if (dev_sync(stream)) return fail(dev_err());
+#endif
+                dev_free(tape_bufs[first + i]);
+                tape_bufs[first + i] = nullptr;
+            }
+        }
         return 0;
     }
 
@@ -1373,6 +1489,7 @@ struct EngineImpl: EngineBase {
     }
     int get_visits(int replica, int bias, long long* counts, int clear) override {
         if (!shared.has_grid || !P.grid_visits) return fail("no Grid bias configured");
+        if (bias < 0 || bias >= shared.ob.n_biases || shared.ob.biases[bias].type != BIAS_GRID) return fail("not a Grid bias");
         RepAux aux;
         if (get_aux(replica, 1, &aux)) return -1;
         int off = aux.bs.grid_off[bias];
@@ -1652,7 +1769,9 @@ int ldo_set_moveset(ldo_engine* e, int n, const ldo_movetype_desc* mts, int allo
     EngineBase* b = e->b;
     if (n < 1 || n > LDO_MAX_MOVETYPES) return b->fail("bad movetype count");
     MoveSet& ms = b->shared.ms;
+    int keep_order = ms.reference_draw_order;
     memset(&ms, 0, sizeof(ms));
+    ms.reference_draw_order = keep_order;
     ms.n = n;
     ms.allow_nonsensical_ps = allow_nonsensical_ps;
     double cum = 0;
@@ -1703,6 +1822,11 @@ int ldo_set_moveset(ldo_engine* e, int n, const ldo_movetype_desc* mts, int allo
     return b->push_shared();
 }
 
+int ldo_set_reference_draw_order(ldo_engine* e, int on) {
+    e->b->shared.ms.reference_draw_order = on ? 1 : 0;
+    return e->b->push_shared();
+}
+
 int ldo_set_order_params(ldo_engine* e, int n, const ldo_order_param_desc* ops) {
     EngineBase* b = e->b;
     if (n < 0 || n > LDO_MAX_OPS) return b->fail("too many order parameters");
@@ -1750,7 +1874,9 @@ int ldo_set_biases(ldo_engine* e, int n, const ldo_bias_desc* biases) {
         BiasDef& bd = ob.biases[i];
         bd.type = biases[i].type;
         bd.n_ops = biases[i].n_ops;
+        if (bd.type != BIAS_LINEAR_STEP_WELL && bd.type != BIAS_SQUARE_WELL && bd.type != BIAS_GRID) return b->fail("unknown bias function type");
         if (bd.n_ops < 1 || bd.n_ops > LDO_MAX_GRID_DIM) return b->fail("bias function has a bad number of order parameters");
+        if (bd.type != BIAS_GRID && bd.n_ops != 1) return b->fail("well bias functions take exactly one order parameter");
         for (int k = 0; k < bd.n_ops; k++) {
             if (biases[i].ops[k] < 0 || biases[i].ops[k] >= ob.n_ops) return b->fail("bias refers to an unknown order parameter");
             bd.op_idx[k] = biases[i].ops[k];
@@ -2089,6 +2215,13 @@ int ldo_exchange_pt(ldo_engine* e, int variant, long long swap_i, int n_ladders,
                     int n_ranks, const double* dependent, int* slot_to_replica, long long* attempts,
                     long long* accepts) {
     if (variant < LDO_PT_T || variant > LDO_PT_ST) return e->b->fail("ldo_exchange_pt: 1-D variants only (see ldo_exchange_pt_2d)");
+    if (variant == LDO_PT_T || variant == LDO_PT_ST) {
+        // these variants do not exchange the staple chemical-potential multiplier (m_exchange_q_is,
+        // ptmc_simulation.cpp:602-623): every replica keeps its own, and the swap probability would need the
+        // replicas' multipliers rather than the slots'. Only a uniform ladder is the same thing.
+        for (double m: e->b->ladder_staple_u_mult)
+            if (m != e->b->ladder_staple_u_mult[0]) return e->b->fail("t_/st_parallel_tempering need uniform chem_pot_mults (the multiplier is not exchanged)");
+    }
     return exchange_pt_impl(e, variant, 0, swap_i, n_ladders, ladder_len, rank, n_ranks, dependent, slot_to_replica, attempts, accepts);
 }
 
@@ -2163,6 +2296,13 @@ int ldo_exchange_windows(ldo_engine* e, long long swap_i, int n_ladders, int n_w
 }
 
 long long ldo_launch_count(const ldo_engine* e) { return e->b->launches; }
+const char* ldo_build_info(void) {
+#ifdef LDO_HOSTSIM
+    return "hostsim (tests only: host emulation of the device sources, one emulated lane)";
+#else
+    return "cuda sm_100a";
+#endif
+}
 unsigned long ldo_state_bytes(const ldo_engine* e) { return e->b->state_bytes(); }
 
 unsigned long ldo_checkpoint_size(const ldo_engine* e) { return e->b->blob_size(); }

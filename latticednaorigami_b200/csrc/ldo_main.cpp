@@ -29,7 +29,7 @@ int main(int argc, char* argv[]) {
         std::cout << "Input parameter file must be provided" << std::endl << "Run with -h to see all options" << std::endl << std::endl;
         return 1;
     }
-    ldo_sim* sim = ldo_sim_create(inp.c_str(), replicas, device, 0, replicas);
+    ldo_sim* sim = ldo_sim_create(inp.c_str(), replicas, device, 0, 1);
     int rc = sim ? ldo_sim_run(sim) : -1;
     if (rc != 0) {
         // same failure report as apps/main.cpp:105-115

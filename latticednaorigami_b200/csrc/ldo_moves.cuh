@@ -41,6 +41,9 @@ struct TapeDraw {
 #else
 #define LDO_TAPE_MODE(g) ((g)->tape != nullptr)
 #endif
+// true when the move code must follow the reference's serial draw order: replay, or Philox with the
+// reference_draw_order switch of the moveset
+#define LDO_SERIAL_DRAWS() (LDO_TAPE_MODE(RNG()) || MS().reference_draw_order != 0)
 struct Rng {
     // replay tape (parity mode) when tape != nullptr
     const TapeDraw* tape;
@@ -181,6 +184,11 @@ struct MoveDef {
 struct MoveSet {
     int n;
     int allow_nonsensical_ps;
+    // Production (Philox) mode only: 1 = keep the reference's serial trial order in the three places where the
+    // draws are otherwise re-associated to lanes (rg_select_open_config, the single-draw feeler test,
+    // rg_count_avail_parallel), i.e. run Philox through exactly the branches a replay tape runs. Same ensemble,
+    // used by the tests to isolate the lane-parallel branches (ldo_set_reference_draw_order).
+    int reference_draw_order;
     MoveDef mt[LDO_MAX_MOVETYPES];
     double exchange_mults[LDO_MAX_TYPES];
 };
@@ -2139,7 +2147,7 @@ struct Engine {
             int o = 0;
             double p_c_open = 0;
             bool c_open = false;
-            if (!LDO_TAPE_MODE(RNG()) && !W()->stemd && W()->d_max_c_attempts == 36) {
+            if (!LDO_SERIAL_DRAWS() && !W()->stemd && W()->d_max_c_attempts == 36) {
                 c_open = rg_select_open_config(p, o, p_c_open);
             }
             else {
@@ -2176,7 +2184,7 @@ struct Engine {
         if (feels == W()->max_recoils || W()->di == M()->n_regrow - 1) return true;
         rg_prepare_for_growth();
         bool c_avail = false;
-        if (!LDO_TAPE_MODE(RNG()) && W()->max_recoils == 1 && !W()->stemd && W()->d_max_c_attempts == 36) {
+        if (!LDO_SERIAL_DRAWS() && W()->max_recoils == 1 && !W()->stemd && W()->d_max_c_attempts == 36) {
             // Philox mode, one exhaustive feeler level: "some configuration opens" has probability
             // 1 - prod(1 - p) whatever the trial order, so one draw replaces up to 36 trials
             const RgSlot& sl = M()->slots[W()->cur_slot];
@@ -2284,7 +2292,7 @@ struct Engine {
                 // examined whatever the order, and its contribution is an independent Bernoulli variable,
                 // so the configurations are spread over the lanes, each with its own Philox block, and the
                 // count is reduced across the warp. Replay (tape) mode keeps the reference's serial order.
-                if (!LDO_TAPE_MODE(RNG()) && W()->max_c_attempts == 36 && W()->max_recoils == 1 && catt != W()->max_c_attempts &&
+                if (!LDO_SERIAL_DRAWS() && W()->max_c_attempts == 36 && W()->max_recoils == 1 && catt != W()->max_c_attempts &&
                     (last_level || feeler_simple)) {
                     avail_cs += rg_count_avail_parallel(last_level);
                     catt = W()->max_c_attempts;

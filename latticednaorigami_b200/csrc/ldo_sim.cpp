@@ -841,16 +841,24 @@ ldo_sim* ldo_sim_create(const char* inp_path, int n_replicas, int device, int ra
                     smm[k] = p.m_stacking_mults[k % s->v2_dim];
                 }
             }
+            if (s->pt_variant == LDO_PT_T || s->pt_variant == LDO_PT_ST) {
+                for (double m: cm)
+                    if (m != cm[0]) throw SimulationMisuse {"t_/st_parallel_tempering do not exchange chem_pot_mults: they must be uniform"};
+            }
+            // (the ladder keeps stacking_mults for every variant: calc_acceptance_p reads m_control_qs[3] whether
+            // or not the variant applies the multiplier to the system, ptmc_simulation.cpp:283-284,307)
             s->check(ldo_set_exchange_ladder(s->eng, s->num_reps, ladder_ti.data(), cm.data(), bmm.data(), smm.data()));
             int slots_per_rank {s->num_reps / s->n_ranks};
             for (int r {0}; r != n_replicas; r++) {
                 int k {ladder_slot_of(*s, r % slots_per_rank)};
                 ti[r] = ladder_ti[k];
                 um[r] = cm[k];
-                // OneDPTGCMCSimulation::initialize_control_qs stores the bias multiplier in the wrong
-                // slot (App. A17); with the shipped all-ones multipliers both readings coincide
-                bm[r] = bmm[k] * p.m_bias_funcs_mult;
-                sm[r] = smm[k];
+                // Only hut_parallel_tempering ever applies bias_mults (HUTPTGCMCSimulation::update_control_qs,
+                // ptmc_simulation.cpp:665-672: update_bias_mult overwrites the multiplier with the ladder value from
+                // the first round on); the other variants keep bias_funcs_mult and ignore bias_mults.
+                bm[r] = s->pt_variant == LDO_PT_HUT ? bmm[k] : p.m_bias_funcs_mult;
+                // st_/2d_: update_temp(temp, stacking_mult); t_/ut_/hut_: update_temp(temp), multiplier 1 (:651-680)
+                sm[r] = (s->pt_variant == LDO_PT_ST || s->pt_variant == LDO_PT_2D) ? smm[k] : 1.0;
             }
             s->q2r.resize(static_cast<size_t>(s->n_ladders) * s->num_reps);
             for (int l {0}; l != s->n_ladders; l++)
@@ -889,6 +897,9 @@ ldo_sim* ldo_sim_create(const char* inp_path, int n_replicas, int device, int ra
             if (!std::getenv("LDO_QUIET")) std::cout << "Using specified seed: " << p.m_random_seed << "\n";
         }
         else {
+            // every rank must key the shared exchange stream identically (k_exchange draws from (seed, swap,
+            // ladder, pair)): a per-rank random_device seed would make the ranks disagree on the swaps
+            if (s->n_ranks > 1 && s->is_pt) throw SimulationMisuse {"random_seed must be set when replica exchange runs on more than one rank"};
             std::random_device rd {};
             seed = (static_cast<unsigned long long>(rd()) << 32) ^ rd();
             if (!std::getenv("LDO_QUIET")) std::cout << "Truly random seed: " << seed << "\n";

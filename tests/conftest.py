@@ -102,14 +102,31 @@ def replay_fixture_through(sim, fx, replica=0, replicas=None):
         assert list(att[r]) == list(fx["attempts"]) and list(acc[r]) == list(fx["accepts"])
 
 
+_hostsim = None
+
+
+def load_hostsim():
+    """Host emulation of the device sources (one emulated lane): test infrastructure, built on demand and
+    opened HERE - the package's own loader refuses anything but a CUDA build. Returns a bound library
+    handle for Simulation(..., lib=...)."""
+    global _hostsim
+    if _hostsim is None:
+        import ctypes
+
+        from latticednaorigami_b200 import binding
+        csrc = os.path.join(ROOT, "latticednaorigami_b200", "csrc")
+        srcs = [os.path.join(csrc, f) for f in os.listdir(csrc)] + [os.path.join(ROOT, "include", f) for f in os.listdir(os.path.join(ROOT, "include"))]
+        newest = max(os.path.getmtime(p) for p in srcs)
+        if not os.path.exists(HOSTSIM_LIB) or os.path.getmtime(HOSTSIM_LIB) < newest:
+            subprocess.run(["make", "-C", ROOT, "hostsim"], check=True, capture_output=True)
+        _hostsim = binding.bind(ctypes.CDLL(HOSTSIM_LIB))
+        assert _hostsim.ldo_build_info().decode().startswith("hostsim")
+    return _hostsim
+
+
 @pytest.fixture(scope="session")
 def hostsim_lib():
-    """Host emulation of the device sources (one emulated lane); test infrastructure, built on demand."""
-    srcs = [os.path.join(ROOT, "latticednaorigami_b200", "csrc", f) for f in os.listdir(os.path.join(ROOT, "latticednaorigami_b200", "csrc"))]
-    newest = max(os.path.getmtime(p) for p in srcs)
-    if not os.path.exists(HOSTSIM_LIB) or os.path.getmtime(HOSTSIM_LIB) < newest:
-        subprocess.run(["make", "-C", ROOT, "hostsim"], check=True, capture_output=True)
-    return HOSTSIM_LIB
+    return load_hostsim()
 
 
 @pytest.fixture(scope="session")

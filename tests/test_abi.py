@@ -41,3 +41,16 @@ def test_product_does_not_reference_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", ".h")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "oracle_ref" not in text and "liboracle" not in text and "hostsim.so" not in text, f
+
+
+def test_loader_refuses_a_non_cuda_build(hostsim_lib):
+    """The package's loader accepts CUDA builds only: the host emulation used by this test-suite exports the
+    whole ABI but carries another build marker and cannot be reached through binding.load / Simulation(lib_path=)."""
+    import pytest
+
+    from conftest import HOSTSIM_LIB
+    with pytest.raises(binding.LdoError, match="not a CUDA build"):
+        binding.load(HOSTSIM_LIB)
+    with pytest.raises(binding.LdoError, match="not a CUDA build"):
+        binding.Simulation("/nonexistent.inp", 1, 0, lib_path=HOSTSIM_LIB)
+    assert binding.load().ldo_build_info().decode() == "cuda sm_100a"

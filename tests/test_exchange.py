@@ -33,7 +33,7 @@ def acceptance_p(t1, t2, d1, d2):
 
 def test_single_rank_exchange_rule(hostsim_lib, tmp_path):
     n_ladders = 6
-    sim = Simulation(write_inp(str(tmp_path / "pt.inp"), pt_options()), n_ladders * len(TEMPS), 0, lib_path=hostsim_lib)
+    sim = Simulation(write_inp(str(tmp_path / "pt.inp"), pt_options()), n_ladders * len(TEMPS), 0, lib=hostsim_lib)
     L = len(TEMPS)
     q2r_prev = np.tile(np.arange(L, dtype=np.int32), (n_ladders, 1))
     for swap_i in range(1, 7):
@@ -70,11 +70,12 @@ import torch
 import torch.distributed as dist
 sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, "tests"))
 from latticednaorigami_b200.binding import Simulation
+import conftest
 rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"])
 dist.init_process_group("gloo", rank=rank, world_size=world)
 n_ladders, L = 5, 4
 S = L // world
-sim = Simulation({inp!r}, n_ladders * S, 0, rank=rank, n_ranks=world, lib_path={lib!r})
+sim = Simulation({inp!r}, n_ladders * S, 0, rank=rank, n_ranks=world, lib=conftest.load_hostsim())
 for swap_i in range(1, 6):
     assert sim.exchange_advance() == 0
     dep = torch.from_numpy(sim.engine.exchange_collect().copy())
@@ -99,7 +100,7 @@ def test_two_rank_exchange_matches_single_rank(hostsim_lib, tmp_path, two_d):
         opts = pt_options()
     inp = write_inp(str(tmp_path / "pt.inp"), opts)
     n_ladders, L = 5, len(TEMPS)
-    one = Simulation(inp, n_ladders * L, 0, lib_path=hostsim_lib)
+    one = Simulation(inp, n_ladders * L, 0, lib=hostsim_lib)
     for swap_i in range(1, 6):
         assert one.exchange_advance() == 0
         one.exchange_apply(swap_i)
@@ -107,7 +108,7 @@ def test_two_rank_exchange_matches_single_rank(hostsim_lib, tmp_path, two_d):
     e1 = one.engine.energies().reshape(n_ladders, L, 5)
 
     script = tmp_path / "worker.py"
-    script.write_text(WORKER.format(root=ROOT, inp=inp, lib=hostsim_lib, out=str(tmp_path / "out"), two_d=two_d))
+    script.write_text(WORKER.format(root=ROOT, inp=inp, out=str(tmp_path / "out"), two_d=two_d))
     env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29632" if two_d else "29631", WORLD_SIZE="2")
     procs = [subprocess.Popen([sys.executable, str(script)], env=dict(env, RANK=str(r))) for r in range(2)]
     for p in procs:
@@ -135,7 +136,7 @@ def _two_d_exchange_rule(lib, tmp_path):
     n_ladders = 5
     opts = make_options("snodin_unbound.json", simulation_type="2d_parallel_tempering", num_reps=L, temps=temps,
                         stacking_mults=smults, exchange_interval=20, swaps=4, random_seed=77)
-    sim = Simulation(write_inp(str(tmp_path / "pt2d.inp"), opts), n_ladders * L, 0, lib_path=lib)
+    sim = Simulation(write_inp(str(tmp_path / "pt2d.inp"), opts), n_ladders * L, 0, lib=lib)
     ctl = sim.engine.control()
     assert np.array_equal(ctl["temp_idx"].reshape(n_ladders, L)[0], np.repeat(np.arange(v1), v2))
     assert np.allclose(ctl["stacking_mult"].reshape(n_ladders, L)[0], np.tile(smults, v1))
@@ -208,7 +209,7 @@ def test_swap_probability_matches_reference_code(hostsim_lib, oracle, tmp_path):
     pins the reduced staple chemical potentials the engine holds."""
     opts = pt_options(output_filebase=str(tmp_path / "ref"))
     ref = oracle.RefSystem(opts, with_sim=False)
-    sim = Simulation(write_inp(str(tmp_path / "pt.inp"), pt_options()), len(TEMPS), 0, lib_path=hostsim_lib)
+    sim = Simulation(write_inp(str(tmp_path / "pt.inp"), pt_options()), len(TEMPS), 0, lib=hostsim_lib)
     eng = sim.engine
     red = np.zeros(64)
     nst = eng.L.ldo_get_reduced_staple_u(eng.h, red.ctypes.data)
@@ -243,7 +244,7 @@ def test_two_d_driver_writes_swap_file(hostsim_lib, tmp_path):
     opts = make_options("snodin_unbound.json", simulation_type="2d_parallel_tempering", num_reps=4, temps=temps,
                         stacking_mults=smults, exchange_interval=10, swaps=4, random_seed=5, configs_output_freq=10,
                         max_pt_dur=1e9, output_filebase=str(tmp_path / "pt2d"))
-    sim = Simulation(write_inp(str(tmp_path / "pt2d.inp"), opts), 4, 0, lib_path=hostsim_lib)
+    sim = Simulation(write_inp(str(tmp_path / "pt2d.inp"), opts), 4, 0, lib=hostsim_lib)
     sim.run()
     lines = (tmp_path / "pt2d.swp").read_text().splitlines()
     assert lines[0].split() == ["330/1/1/", "330/1/0.8/", "336/1/1/", "336/1/0.8/"]

@@ -24,14 +24,14 @@ def test_per_domain_order_parameter_is_refused(hostsim_lib, tmp_path):
     opts = make_options("snodin_unbound.json")
     opts["order_parameter_file"] = str(path)
     with pytest.raises(LdoError, match="update_per_domain"):
-        Simulation(write_inp(str(tmp_path / "a.inp"), opts), 1, 0, lib_path=hostsim_lib)
+        Simulation(write_inp(str(tmp_path / "a.inp"), opts), 1, 0, lib=hostsim_lib)
 
 
 def test_unconstructed_reference_movetype_is_refused(hostsim_lib, tmp_path):
     opts = make_options("snodin_unbound.json")
     opts["movetype_file"] = _moveset(tmp_path, {"label": "x", "type": "CTRGClusteredLinkerRegrowth"})
     with pytest.raises(LdoError, match="CTRGClusteredLinkerRegrowth"):
-        Simulation(write_inp(str(tmp_path / "b.inp"), opts), 1, 0, lib_path=hostsim_lib)
+        Simulation(write_inp(str(tmp_path / "b.inp"), opts), 1, 0, lib=hostsim_lib)
 
 
 def test_linker_options_out_of_range(hostsim_lib, tmp_path):
@@ -40,4 +40,4 @@ def test_linker_options_out_of_range(hostsim_lib, tmp_path):
         "label": "x", "type": "CTCBLinkerRegrowth", "max_disp": 1, "max_turns": 1, "max_regrowth": 4,
         "max_linker_length": 3, "num_transforms": 40})
     with pytest.raises(LdoError, match="linker regrowth options"):
-        Simulation(write_inp(str(tmp_path / "c.inp"), opts), 1, 0, lib_path=hostsim_lib)
+        Simulation(write_inp(str(tmp_path / "c.inp"), opts), 1, 0, lib=hostsim_lib)

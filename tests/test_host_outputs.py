@@ -31,7 +31,7 @@ def _options(tmp_path, base):
 def test_output_files_match_reference_cli(hostsim_lib, oracle, tmp_path):
     ref_inp = write_inp(str(tmp_path / "ref.inp"), _options(tmp_path, "ref"))
     subprocess.run([oracle.CLI_PATH, "-i", ref_inp], check=True, capture_output=True)
-    sim = Simulation(write_inp(str(tmp_path / "our.inp"), _options(tmp_path, "our")), 1, 0, lib_path=hostsim_lib)
+    sim = Simulation(write_inp(str(tmp_path / "our.inp"), _options(tmp_path, "our")), 1, 0, lib=hostsim_lib)
     sim.run()
     for ext in EXTS:
         ref, our = (tmp_path / ("ref" + ext)).read_text(), (tmp_path / ("our" + ext)).read_text()
@@ -53,7 +53,7 @@ def test_annealing_output_files_match_reference_cli(hostsim_lib, oracle, tmp_pat
         return opts
     ref_inp = write_inp(str(tmp_path / "ref_a.inp"), options("refa"))
     subprocess.run([oracle.CLI_PATH, "-i", ref_inp], check=True, capture_output=True)
-    sim = Simulation(write_inp(str(tmp_path / "our_a.inp"), options("oura")), 1, 0, lib_path=hostsim_lib)
+    sim = Simulation(write_inp(str(tmp_path / "our_a.inp"), options("oura")), 1, 0, lib=hostsim_lib)
     sim.run()
     for ext in EXTS:
         ref, our = (tmp_path / ("refa" + ext)).read_text(), (tmp_path / ("oura" + ext)).read_text()

@@ -17,7 +17,7 @@ from latticednaorigami_b200.binding import Simulation
 def test_replay_fixture(hostsim_lib, tmp_path, name):
     fx = np.load(os.path.join(GOLDEN, f"replay_{name}.npz"))
     inp = write_inp(str(tmp_path / "r.inp"), options_from_fixture(fx))
-    sim = Simulation(inp, 2, 0, lib_path=hostsim_lib)
+    sim = Simulation(inp, 2, 0, lib=hostsim_lib)
     replay_fixture_through(sim, fx, replicas=[0, 1])
 
 
@@ -29,7 +29,7 @@ def test_live_replay_against_oracle(hostsim_lib, oracle, tmp_path):
         opts = make_options(system, moveset, temp=temp)
         r = oracle.RefSystem(opts)
         r.seed(seed)
-        sim = Simulation(write_inp(str(tmp_path / f"{seed}.inp"), opts), 1, 0, lib_path=hostsim_lib)
+        sim = Simulation(write_inp(str(tmp_path / f"{seed}.inp"), opts), 1, 0, lib=hostsim_lib)
         for _ in range(4):
             r.tape(clear=True)
             r.simulate(steps // 4)
@@ -49,7 +49,7 @@ def test_centering_and_constraint_check(hostsim_lib, oracle, tmp_path):
     r.seed(9)
     r.simulate(40)
     tape = r.tape()
-    sim = Simulation(write_inp(str(tmp_path / "c.inp"), opts), 1, 0, lib_path=hostsim_lib)
+    sim = Simulation(write_inp(str(tmp_path / "c.inp"), opts), 1, 0, lib=hostsim_lib)
     sim.engine.attach_tape(0, tape)
     sim.engine.run(40, 7, 0, 5)
     sim.engine.assert_ok()
@@ -59,7 +59,7 @@ def test_centering_and_constraint_check(hostsim_lib, oracle, tmp_path):
 
 def test_tape_mismatch_is_detected(hostsim_lib, tmp_path):
     fx = np.load(os.path.join(GOLDEN, "replay_four_unbound_340K.npz"))
-    sim = Simulation(write_inp(str(tmp_path / "m.inp"), options_from_fixture(fx)), 1, 0, lib_path=hostsim_lib)
+    sim = Simulation(write_inp(str(tmp_path / "m.inp"), options_from_fixture(fx)), 1, 0, lib=hostsim_lib)
     tape = fx["tape"][: int(fx["tape_lens"][0])].copy()
     tape["hi"][np.nonzero(tape["kind"] == 1)[0][3]] += 1
     sim.engine.attach_tape(0, tape)
@@ -80,7 +80,7 @@ def test_distance_order_params_and_biases(hostsim_lib, oracle, tmp_path):
         opts["order_parameter_file"] = os.path.join(GOLDEN, "inputs", "ops_dist.json")
         r = oracle.RefSystem(opts)
         r.seed(seed)
-        sim = Simulation(write_inp(str(tmp_path / f"d{seed}.inp"), opts), 1, 0, lib_path=hostsim_lib)
+        sim = Simulation(write_inp(str(tmp_path / f"d{seed}.inp"), opts), 1, 0, lib=hostsim_lib)
         for k in range(24):
             r.tape(clear=True)
             r.simulate(25)

@@ -21,7 +21,7 @@ def _options(tmp_path, width, n_rows, temp, max_total, cyclic=False, staple_M=1e
 def _replay(oracle, opts, tmp_path, lib_path, seed, steps, chunks=4):
     r = oracle.RefSystem(opts)
     r.seed(seed)
-    sim = Simulation(write_inp(str(tmp_path / f"syn{seed}.inp"), opts), 2, 0, lib_path=lib_path)
+    sim = Simulation(write_inp(str(tmp_path / f"syn{seed}.inp"), opts), 2, 0, lib=lib_path)
     for _ in range(chunks):
         r.tape(clear=True)
         r.simulate(steps // chunks)

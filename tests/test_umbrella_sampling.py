@@ -26,7 +26,7 @@ def us_options(tmp_path, sim_type, **kw):
 
 def test_ptmwus_run_and_files(hostsim_lib, tmp_path):
     opts = us_options(tmp_path, "ptmw_umbrella_sampling")
-    sim = Simulation(write_inp(str(tmp_path / "us.inp"), opts), 6, 0, lib_path=hostsim_lib)  # 2 ladders x 3 windows
+    sim = Simulation(write_inp(str(tmp_path / "us.inp"), opts), 6, 0, lib=hostsim_lib)  # 2 ladders x 3 windows
     sim.run()
     sim.engine.assert_ok()
     names = set(os.listdir(tmp_path))
@@ -46,7 +46,7 @@ def test_ptmwus_run_and_files(hostsim_lib, tmp_path):
 
 def test_visit_histogram_counts_every_step(hostsim_lib, tmp_path):
     opts = us_options(tmp_path, "mw_umbrella_sampling", output_filebase="")
-    sim = Simulation(write_inp(str(tmp_path / "h.inp"), opts), 3, 0, lib_path=hostsim_lib)
+    sim = Simulation(write_inp(str(tmp_path / "h.inp"), opts), 3, 0, lib=hostsim_lib)
     eng = sim.engine
     idx = sim.op_tags.index("numfulldomains")
     n = 25 + 1  # box of numfulldomains: 0 .. (24 + 24*2)/2
@@ -65,7 +65,7 @@ def test_visit_histogram_counts_every_step(hostsim_lib, tmp_path):
 def test_window_exchange_rule(hostsim_lib, tmp_path):
     opts = us_options(tmp_path, "ptmw_umbrella_sampling", output_filebase="")
     n_ladders, n_win = 8, 3
-    sim = Simulation(write_inp(str(tmp_path / "x.inp"), opts), n_ladders * n_win, 0, lib_path=hostsim_lib)
+    sim = Simulation(write_inp(str(tmp_path / "x.inp"), opts), n_ladders * n_win, 0, lib=hostsim_lib)
     eng = sim.engine
     rng = np.random.default_rng(3)
     mins, maxs = [0, 2, 4], [4, 6, 8]
