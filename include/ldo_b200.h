@@ -275,9 +275,10 @@ int ldo_center(ldo_engine* e, int centering_domain);
  * of them. Decisions
  * are taken on device from a Philox stream shared by all ranks (identical on every rank, no
  * communication); accepted swaps relabel control variables (temperature table index and multipliers),
- * configurations never move. `dependent` is the all-gathered, rank-major [n_ranks][R][3 + n_staple_types]
- * array of (enthalpy, bias, stacking, staple counts...) as produced by ldo_exchange_collect on every
- * rank; pass NULL when n_ranks == 1, or after an NCCL all-gather wrote the engine's own receive buffer
+ * configurations never move. `dependent` is the all-gathered, rank-major [n_ranks][R][4 + n_staple_types]
+ * array of (enthalpy, bias, stacking, the replica's own staple chemical-potential multiplier, staple counts...)
+ * as produced by ldo_exchange_collect on every rank - what slave_send ships (ptmc_simulation.cpp:163-175; the
+ * reference sends m_staple_us = reduced_u * T * multiplier, here the multiplier travels and T is the slot's); pass NULL when n_ranks == 1, or after an NCCL all-gather wrote the engine's own receive buffer
  * (ldo_exchange_buffers). slot_to_replica is the reference's m_q_to_repi per ladder (the .swp row);
  * attempts / accepts are [n_ladders][ladder_len - 1]. */
 /* Control-variable ladder (m_control_qs, ptmc_simulation.cpp:341-346): temperature table index and
@@ -288,12 +289,21 @@ int ldo_exchange_collect(ldo_engine* e, double* dependent_local);
 int ldo_exchange_pt(ldo_engine* e, int variant, long long swap_i, int n_ladders, int ladder_len,
                     int rank, int n_ranks, const double* dependent,
                     int* slot_to_replica, long long* attempts, long long* accepts);
+/* Replay mode of the exchange (parity tests): the uniform reals the reference's master drew in its test_acceptance
+ * calls (ptmc_simulation.cpp:255-271; none is drawn when p == 1), in order, with round_offsets[k] = index of the first
+ * draw of exchange round k + 1 (round_offsets[n_rounds] = n). While a tape is set, ldo_exchange_pt / ldo_exchange_pt_2d
+ * (one ladder only) serve the draws of round swap_i from it instead of Philox; n_rounds = 0 detaches. A swap
+ * probability that rounds to exactly 1 in one code and to 1 - 1e-16 in the other (running energies agree to 1e-12,
+ * not bitwise) makes one of them draw and not the other: ldo_exchange_tape_status counts the draws the engine wanted
+ * beyond a round's supply (taken as accepted) and the draws of finished rounds it left unused. */
+int ldo_set_exchange_tape(ldo_engine* e, const double* reals, long long n, const long long* round_offsets, long long n_rounds);
+int ldo_exchange_tape_status(ldo_engine* e, long long* missing, long long* unused);
 /* Reduced staple chemical potentials ln(staple_M) - (2 L - 1) ln 6 per staple type (m_reduced_staple_us,
  * origami_system.cpp:965-990) as the exchange uses them; returns the number of staple types. */
 int ldo_get_reduced_staple_u(ldo_engine* e, double* out);
 /* The swap probability the exchange kernels use, evaluated on the host (same inline function): replaces
  * PTGCMCSimulation::calc_acceptance_p (ptmc_simulation.cpp:275-313). dependent1/2 = {enthalpy, bias, stacking,
- * staple counts[n_staple_types]} of the two replicas; reduced_staple_u as origami_system.cpp:965-990. */
+ * (ignored: the explicit staple_u_mult arguments are used), staple counts[n_staple_types]} of the two replicas; reduced_staple_u as origami_system.cpp:965-990. */
 double ldo_exchange_acceptance_p(int n_staple_types, const double* reduced_staple_u, double temp1, double temp2,
                                  double staple_u_mult1, double staple_u_mult2, double stacking_mult1, double stacking_mult2,
                                  const double* dependent1, const double* dependent2);
@@ -318,7 +328,7 @@ int ldo_exchange_windows(ldo_engine* e, long long swap_i, int n_ladders, int n_w
                          int n_window_biases, const int* window_biases, int* window_to_replica,
                          long long* attempts, long long* accepts);
 /* Device pointers for the NCCL path: local send buffer / full receive buffer of the dependent
- * quantities ([n][3 + n_staple_types] doubles), so the all-gather runs device-to-device. */
+ * quantities ([n][4 + n_staple_types] doubles), so the all-gather runs device-to-device. */
 int ldo_exchange_buffers(ldo_engine* e, int n_global, void** send_dev, void** recv_dev, int* doubles_per_replica);
 
 #ifdef __cplusplus

@@ -19,7 +19,7 @@ ENGINE_SYMBOLS = [
     "ldo_get_energies", "ldo_get_counters", "ldo_get_staple_counts", "ldo_get_order_params",
     "ldo_get_move_stats", "ldo_get_run_timing", "ldo_recompute_energies", "ldo_check_all_constraints", "ldo_center",
     "ldo_set_exchange_ladder", "ldo_exchange_collect", "ldo_exchange_pt", "ldo_exchange_pt_2d", "ldo_exchange_acceptance_p", "ldo_get_reduced_staple_u", "ldo_set_step", "ldo_exchange_buffers",
-    "ldo_exchange_windows", "ldo_set_reference_draw_order", "ldo_build_info", "ldo_launch_count", "ldo_state_bytes", "ldo_checkpoint_size", "ldo_checkpoint_save", "ldo_checkpoint_load",
+    "ldo_exchange_windows", "ldo_set_exchange_tape", "ldo_exchange_tape_status", "ldo_set_reference_draw_order", "ldo_build_info", "ldo_launch_count", "ldo_state_bytes", "ldo_checkpoint_size", "ldo_checkpoint_save", "ldo_checkpoint_load",
 ]
 HOST_SYMBOLS = [
     "ldo_host_last_error", "ldo_sim_create", "ldo_sim_destroy", "ldo_sim_engine", "ldo_sim_run",
@@ -114,6 +114,8 @@ def bind(L):
         "ldo_exchange_buffers": (i, [vp, i, vp, vp, vp]),
         "ldo_exchange_windows": (i, [vp, ll, i, i, i, i, vp, vp, vp, vp]),
         "ldo_set_reference_draw_order": (i, [vp, i]),
+        "ldo_set_exchange_tape": (i, [vp, vp, ll, vp, ll]),
+        "ldo_exchange_tape_status": (i, [vp, vp, vp]),
         "ldo_build_info": (C.c_char_p, []),
         "ldo_launch_count": (ll, [vp]),
         "ldo_state_bytes": (C.c_ulong, [vp]),
@@ -341,9 +343,19 @@ class Engine:
         if not to_host:
             self._check(self.L.ldo_exchange_collect(self.h, None))
             return None
-        out = np.zeros((self.R, 3 + self.n_staple_types))
+        out = np.zeros((self.R, 4 + self.n_staple_types))
         self._check(self.L.ldo_exchange_collect(self.h, _ptr(out)))
         return out
+
+    def set_exchange_tape(self, reals, round_offsets):
+        r = np.ascontiguousarray(reals, dtype=np.float64)
+        o = np.ascontiguousarray(round_offsets, dtype=np.int64)
+        self._check(self.L.ldo_set_exchange_tape(self.h, _ptr(r), len(r), _ptr(o), len(o) - 1))
+
+    def exchange_tape_status(self):
+        missing, unused = C.c_longlong(0), C.c_longlong(0)
+        self._check(self.L.ldo_exchange_tape_status(self.h, C.byref(missing), C.byref(unused)))
+        return missing.value, unused.value
 
     def exchange_buffers(self, n_global):
         send, recv, nq = C.c_void_p(0), C.c_void_p(0), C.c_int(0)

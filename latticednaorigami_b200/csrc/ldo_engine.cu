@@ -89,10 +89,22 @@ static const char* dev_err() { return cudaGetErrorString(g_last_cuda); }
 
 #define LDO_MAX_LISTS 256 // work lists of the staged kernel (one per SM, indexed by %smid modulo the count)
 #define LDO_GRID_CAP 1024 // grid-bias points per replica (sum over grid biases)
+// Exchange record of a replica (what slave_send ships, ptmc_simulation.cpp:163-175): enthalpy, bias, stacking, the
+// replica's own staple chemical-potential multiplier (the reference ships m_staple_us = reduced_u * T * multiplier,
+// origami_system.cpp:624-628; T is the slot's), then the staple counts per identity
+#define LDO_DEP_FIXED 4
 
 struct __attribute__((aligned(16))) RepAux {
     Rng rng;
     Control ctl;
+    // OrigamiPotential::update_temp keeps one table set per (temperature, stacking multiplier) it has seen and, on a
+    // cache hit, restores the hybridization and stacking tables but NOT m_init_enthalpy / m_init_entropy / m_init_energy
+    // (origami_potential.cpp:1019-1042 vs :1060-1063): a replica that returns to a temperature it has visited keeps the
+    // initiation terms of the last temperature it saw for the first time. Replica exchange revisits temperatures all the
+    // time, so the quirk is reproduced: `init_temp_idx` names the table whose initiation terms are current (-1: those of
+    // ctl.temp_idx), `table_cache_mask` has one bit per ladder slot key already seen (exchange_ladder).
+    int init_temp_idx;
+    unsigned long long table_cache_mask;
     BiasState bs;
     long long step;
     // not staged to shared memory (touched twice per move): everything from here on stays in HBM/L2
@@ -138,7 +150,7 @@ struct OpArgs {
     int* out_counters; // [R][9]
     int* out_ops; // [R][n_ops]
     int* out_staples; // [R][n_types - 1]
-    double* out_dependent; // [R][3 + n_types - 1] (exchange quantities)
+    double* out_dependent; // [R][LDO_DEP_FIXED + n_types - 1] (exchange quantities)
     int* out_status; // [R][2]
     double* out_recomputed; // [R]
     int* out_recomputed_stacked; // [R]
@@ -168,6 +180,12 @@ template <class K>
 LDO_HD void rep_init_engine(Engine<K>& eng, SysState<K>* st, MoveScratch<K>* ms, RepAux* aux, const DevPtrs<K>& P, int r) {
     const Shared* sh = P.shared;
     eng.sys.init(st, &sh->sc, P.tables[aux->ctl.temp_idx]);
+    if (aux->init_temp_idx >= 0 && aux->init_temp_idx != aux->ctl.temp_idx) {
+        const TempTables& it = P.tables[aux->init_temp_idx];
+        eng.sys.tt.init_energy = it.init_energy;
+        eng.sys.tt.init_enthalpy = it.init_enthalpy;
+        eng.sys.tt.init_entropy = it.init_entropy;
+    }
     eng.m = ms;
     eng.mc = &P.cold[r];
     eng.rng = &aux->rng;
@@ -296,11 +314,12 @@ LDO_HD void rep_observe(Engine<K>& eng, const OpArgs& a, int r) {
         // PTGCMCSimulation::update_dependent_qs (ptmc_simulation.cpp:152-161) + staple counts
         double H, S, stk;
         sys.enthalpy_and_entropy(&H, &S, &stk);
-        double* o = a.out_dependent + (size_t)r * (3 + nst);
+        double* o = a.out_dependent + (size_t)r * (LDO_DEP_FIXED + nst);
         o[0] = H;
         o[1] = eng.total_bias();
         o[2] = stk;
-        for (int t = 0; t < nst; t++) o[3 + t] = (double)s->type_count[t + 1];
+        o[3] = eng.CTL().staple_u_mult;
+        for (int t = 0; t < nst; t++) o[LDO_DEP_FIXED + t] = (double)s->type_count[t + 1];
     }
     if (a.out_counters) {
         int* o = a.out_counters + (size_t)r * 9;
@@ -618,7 +637,7 @@ struct ExchangeArgs {
     int rank, n_ranks, n_local, n_global;
     int n_staple_types;
     unsigned long long seed;
-    const double* dependent; // [n_global][3 + nst]
+    const double* dependent; // [n_global][LDO_DEP_FIXED + nst]
     int* slot_to_replica; // [n_ladders][ladder_len], updated in place (m_q_to_repi)
     // control variables per slot of a ladder [ladder_len] (m_control_qs), fixed for the whole run
     const int* slot_temp_idx;
@@ -630,6 +649,14 @@ struct ExchangeArgs {
     long long* accepts;
     const double* reduced_staple_u; // [nst]: ln M - (2L-1) ln 6 (origami_system.cpp:965-990)
     RepAux* aux; // local replicas
+    // replay mode (ldo_set_exchange_tape, single ladder): the uniform reals of the master's test_acceptance calls
+    // in the order the reference drew them, and where every exchange round's draws start;
+    // exchange_tape_state[0] = next position, [1] = end of this round's draws, [2] = draws wanted beyond them,
+    // [3] = draws of finished rounds left unused
+    const double* exchange_tape;
+    const long long* exchange_tape_offsets; // [n_rounds + 1]
+    long long exchange_tape_rounds;
+    long long* exchange_tape_state;
 };
 
 // One thread per ladder: the neighbour tests of one ladder are sequential in the reference only
@@ -659,7 +686,7 @@ LDO_HD inline double exchange_acceptance_p(int n_staple_types, const double* red
                                            double um1, double um2, double sm1, double sm2, const double* d1, const double* d2) {
     double DBU_DN = 0;
     for (int t = 0; t < n_staple_types; t++) {
-        double N1 = d1[3 + t], N2 = d2[3 + t];
+        double N1 = d1[LDO_DEP_FIXED + t], N2 = d2[LDO_DEP_FIXED + t];
         double u1 = reduced_staple_u[t] * temp1 * um1;
         double u2 = reduced_staple_u[t] * temp2 * um2;
         DBU_DN += (u2 / temp2 - u1 / temp1) * (N2 - N1);
@@ -675,7 +702,7 @@ LDO_HD inline double exchange_acceptance_p(int n_staple_types, const double* red
 // Swap test of the slots si, sj of ladder l (calc_acceptance_p + test_acceptance, ptmc_simulation.cpp:255-313);
 // `counter` indexes attempts / accepts
 LDO_HD inline void exchange_pair(const ExchangeArgs& x, int l, int* q2r, int i, int j, size_t counter) {
-    int nq = 3 + x.n_staple_types;
+    int nq = LDO_DEP_FIXED + x.n_staple_types;
     {
         size_t si = (size_t)i, sj = (size_t)j;
         x.attempts[counter]++;
@@ -684,11 +711,22 @@ LDO_HD inline void exchange_pair(const ExchangeArgs& x, int l, int* q2r, int i, 
         const double* d2 = x.dependent + exchange_gathered_index(x, l, rep2) * nq;
         double temp1 = x.slot_temp[si], temp2 = x.slot_temp[sj];
         double sm1 = x.slot_stacking_mult[si], sm2 = x.slot_stacking_mult[sj];
-        double um1 = x.slot_staple_u_mult[si], um2 = x.slot_staple_u_mult[sj];
+        // each replica's chemical potentials as it computed them itself: its own multiplier (the slot's once the variant
+        // exchanges it; what it was initialised with otherwise and in the first round, App. A17)
+        double um1 = d1[3], um2 = d2[3];
         double p_accept = exchange_acceptance_p(x.n_staple_types, x.reduced_staple_u, temp1, temp2, um1, um2, sm1, sm2, d1, d2);
         bool accept;
         if (p_accept == 1) {
             accept = true;
+        }
+        else if (x.exchange_tape) {
+            // a test the reference decided without a draw (its p rounded to exactly 1, ours to 1 - 1e-16) finds no draw
+            // of this round left: it is taken as accepted, and counted
+            long long* ts = x.exchange_tape_state;
+            double prob = 0.0;
+            if (ts[0] < ts[1]) prob = x.exchange_tape[ts[0]++];
+            else ts[2] += 1;
+            accept = p_accept > prob;
         }
         else {
             Rng g;
@@ -713,6 +751,17 @@ LDO_HD inline void exchange_pair(const ExchangeArgs& x, int l, int* q2r, int i, 
 
 LDO_HD inline void exchange_ladder(const ExchangeArgs& x, int l) {
     int* q2r = x.slot_to_replica + (size_t)l * x.ladder_len;
+    if (x.exchange_tape) {
+        long long* ts = x.exchange_tape_state;
+        long long r = x.swap_i - 1;
+        if (r >= 0 && r < x.exchange_tape_rounds) {
+            ts[0] = x.exchange_tape_offsets[r];
+            ts[1] = x.exchange_tape_offsets[r + 1];
+        }
+        else {
+            ts[1] = ts[0];
+        }
+    }
     if (x.variant == LDO_PT_2D) {
         // TwoDPTGCMCSimulation::attempt_exchange (ptmc_simulation.cpp:495-560): slot (i, j) = i * v2 + j with
         // i the temperature index and j the stacking-multiplier index; four alternating pair sets
@@ -736,12 +785,36 @@ LDO_HD inline void exchange_ladder(const ExchangeArgs& x, int l) {
             exchange_pair(x, l, q2r, i, i + 1, (size_t)l * (x.ladder_len - 1) + i);
         }
     }
+    if (x.exchange_tape) x.exchange_tape_state[3] += x.exchange_tape_state[1] - x.exchange_tape_state[0];
     // master_send (ptmc_simulation.cpp:212-226): every replica receives the control variables of its slot
     for (int i = 0; i < x.ladder_len; i++) {
         if (exchange_rank_of(x, q2r[i]) != x.rank) continue;
         int loc = exchange_local_index(x, l, q2r[i]);
         size_t si = (size_t)i;
         Control& c = x.aux[loc].ctl;
+        {
+            // table-cache bookkeeping of the replica (see RepAux): the key of update_temp is (temperature, stacking
+            // multiplier), the multiplier being 1 for the variants that call update_temp(temp) (ptmc_simulation.cpp:651-680)
+            bool with_mult = x.variant == LDO_PT_ST || x.variant == LDO_PT_2D;
+            RepAux& ra = x.aux[loc];
+            int cur_key = -1, new_key = -1;
+            for (int k = 0; k < x.ladder_len && (cur_key < 0 || new_key < 0); k++) {
+                bool same_mult_cur = !with_mult || x.slot_stacking_mult[k] == c.stacking_mult;
+                bool same_mult_new = !with_mult || x.slot_stacking_mult[k] == x.slot_stacking_mult[si];
+                if (cur_key < 0 && x.slot_temp_idx[k] == c.temp_idx && same_mult_cur) cur_key = k;
+                if (new_key < 0 && x.slot_temp_idx[k] == x.slot_temp_idx[si] && same_mult_new) new_key = k;
+            }
+            if (x.ladder_len <= 64 && new_key >= 0) {
+                if (cur_key >= 0) ra.table_cache_mask |= 1ull << cur_key; // the round that just ran used it
+                if (!((ra.table_cache_mask >> new_key) & 1ull)) {
+                    ra.table_cache_mask |= 1ull << new_key;
+                    ra.init_temp_idx = x.slot_temp_idx[si];
+                }
+                else if (ra.init_temp_idx < 0) {
+                    ra.init_temp_idx = c.temp_idx;
+                }
+            }
+        }
         if (x.variant == LDO_PT_ST) {
             c.temp_idx = x.slot_temp_idx[si];
             c.temp = x.slot_temp[si];
@@ -758,7 +831,10 @@ LDO_HD inline void exchange_ladder(const ExchangeArgs& x, int l) {
             c.temp_idx = x.slot_temp_idx[si];
             c.temp = x.slot_temp[si];
             if (x.variant == LDO_PT_UT || x.variant == LDO_PT_HUT) c.staple_u_mult = x.slot_staple_u_mult[si];
-            if (x.variant == LDO_PT_HUT) c.bias_mult = x.slot_bias_mult[si];
+            // hut_parallel_tempering: HUTPTGCMCSimulation::update_control_qs passes the exchanged bias multiplier to
+            // OrigamiSystem::update_bias_mult, which is an empty virtual that nothing overrides
+            // (origami_system.hpp:165): the system keeps bias_funcs_mult. The multiplier is relabelled in the
+            // .swp header only - nothing to apply here.
         }
     }
 }
@@ -1015,6 +1091,8 @@ struct EngineBase {
     virtual int exchange_buffers(int n_global, void** send, void** recv, int* nq) = 0;
     virtual int window_exchange(WindowExchangeArgs& x, int* window_to_replica, long long* attempts, long long* accepts) = 0;
     virtual int alloc_outputs() = 0;
+    virtual int set_exchange_tape(const double* reals, long long n, const long long* offsets, long long n_rounds) = 0;
+    virtual int exchange_tape_state(long long* missing, long long* unused) = 0;
     virtual size_t blob_size() = 0;
     virtual size_t state_bytes() = 0;
     virtual int get_blobs(int first, int count, void* host) = 0;
@@ -1095,6 +1173,9 @@ struct EngineImpl: EngineBase {
         dev_free(d_slot_vals);
         dev_free(d_red_u);
         dev_free(d_blob_stage);
+        dev_free(d_exch_tape);
+        dev_free(d_exch_tape_state);
+        dev_free(d_exch_tape_offsets);
         for (void* p: tape_bufs) dev_free(p);
         if (g_const_owner == this) g_const_owner = nullptr;
 #ifndef LDO_HOSTSIM
@@ -1134,6 +1215,8 @@ struct EngineImpl: EngineBase {
             aux[r].ctl.staple_u_mult = 1;
             aux[r].ctl.bias_mult = 1;
             aux[r].ctl.stacking_mult = 1;
+            aux[r].init_temp_idx = -1;
+            aux[r].table_cache_mask = 0;
             aux[r].rng.subseq = (uint32_t)r;
             for (int b = 0; b < LDO_MAX_BIASES; b++) aux[r].bs.grid_off[b] = -1;
             aux[r].bs.grid_slot = r;
@@ -1148,7 +1231,7 @@ struct EngineImpl: EngineBase {
         if (dev_malloc((void**)&d_counters, sizeof(int) * 9 * R)) return fail(dev_err());
         if (dev_malloc((void**)&d_ops, sizeof(int) * LDO_MAX_OPS * R)) return fail(dev_err());
         if (dev_malloc((void**)&d_staples, sizeof(int) * (nst > 0 ? nst : 1) * R)) return fail(dev_err());
-        if (dev_malloc((void**)&d_dependent, sizeof(double) * (3 + nst) * R)) return fail(dev_err());
+        if (dev_malloc((void**)&d_dependent, sizeof(double) * (LDO_DEP_FIXED + nst) * R)) return fail(dev_err());
         if (dev_malloc((void**)&d_recomputed, sizeof(double) * R)) return fail(dev_err());
         if (dev_malloc((void**)&P.run_timing, sizeof(long long) * 3 * R)) return fail(dev_err());
         if (dev_malloc((void**)&P.queue, sizeof(int) * LDO_MAX_LISTS)) return fail(dev_err());
@@ -1322,6 +1405,9 @@ struct EngineImpl: EngineBase {
     int ensure_blob_stage(size_t bytes) {
         if (bytes <= blob_stage_cap) return 0;
         dev_free(d_blob_stage);
+        dev_free(d_exch_tape);
+        dev_free(d_exch_tape_state);
+        dev_free(d_exch_tape_offsets);
         d_blob_stage = nullptr;
         blob_stage_cap = 0;
         if (dev_malloc((void**)&d_blob_stage, bytes)) return fail(dev_err());
@@ -1526,7 +1612,7 @@ struct EngineImpl: EngineBase {
     }
 
     int ensure_exchange(int n_global, int n_slots) {
-        int nq = 3 + (shared.sc.n_types - 1);
+        int nq = LDO_DEP_FIXED + (shared.sc.n_types - 1);
         if (n_global > dep_all_n) {
             dev_free(d_dep_all);
             d_dep_all = nullptr;
@@ -1557,11 +1643,40 @@ struct EngineImpl: EngineBase {
         }
         return 0;
     }
+    double* d_exch_tape = nullptr;
+    long long* d_exch_tape_state = nullptr;
+    long long* d_exch_tape_offsets = nullptr;
+    long long exch_tape_rounds = 0;
+    int set_exchange_tape(const double* reals, long long n, const long long* offsets, long long n_rounds) override {
+        dev_free(d_exch_tape);
+        dev_free(d_exch_tape_offsets);
+        d_exch_tape = nullptr;
+        d_exch_tape_offsets = nullptr;
+        exch_tape_rounds = 0;
+        if (n_rounds <= 0) return 0;
+        if (offsets[0] != 0 || offsets[n_rounds] != n) return fail("exchange tape offsets must run from 0 to n");
+        if (!d_exch_tape_state && dev_malloc((void**)&d_exch_tape_state, sizeof(long long) * 4)) return fail(dev_err());
+        if (dev_malloc((void**)&d_exch_tape, sizeof(double) * (n > 0 ? n : 1))) return fail(dev_err());
+        if (dev_malloc((void**)&d_exch_tape_offsets, sizeof(long long) * (n_rounds + 1))) return fail(dev_err());
+        if (n > 0 && dev_h2d(d_exch_tape, reals, sizeof(double) * n, stream)) return fail(dev_err());
+        if (dev_h2d(d_exch_tape_offsets, offsets, sizeof(long long) * (n_rounds + 1), stream)) return fail(dev_err());
+        long long st[4] = {0, 0, 0, 0};
+        if (dev_h2d(d_exch_tape_state, st, sizeof(st), stream)) return fail(dev_err());
+        exch_tape_rounds = n_rounds;
+        return 0;
+    }
+    int exchange_tape_state(long long* missing, long long* unused) override {
+        long long st[4] = {0, 0, 0, 0};
+        if (d_exch_tape && dev_d2h(st, d_exch_tape_state, sizeof(st), stream)) return fail(dev_err());
+        *missing = st[2];
+        *unused = st[3];
+        return 0;
+    }
     int exchange_buffers(int n_global, void** send, void** recv, int* nq) override {
         if (ensure_exchange(n_global, 1)) return -1;
         *send = d_dependent;
         *recv = d_dep_all;
-        *nq = 3 + (shared.sc.n_types - 1);
+        *nq = LDO_DEP_FIXED + (shared.sc.n_types - 1);
         return 0;
     }
 
@@ -1597,7 +1712,7 @@ struct EngineImpl: EngineBase {
     int exchange(ExchangeArgs& x, const double* dependent_host, int* slot_to_replica, long long* attempts, long long* accepts) override {
         int n_slots = x.n_ladders * x.ladder_len;
         int n_pairs = x.variant == LDO_PT_2D ? 2 * n_slots : x.n_ladders * (x.ladder_len - 1);
-        int nq = 3 + x.n_staple_types;
+        int nq = LDO_DEP_FIXED + x.n_staple_types;
         if (ensure_exchange(x.n_global, 2 * n_slots)) return -1;
         if (dependent_host) {
             if (dev_h2d(d_dep_all, dependent_host, sizeof(double) * nq * x.n_global, stream)) return fail(dev_err());
@@ -1633,6 +1748,11 @@ struct EngineImpl: EngineBase {
         dx.slot_stacking_mult = d_slot_vals + 3 * L;
         dx.reduced_staple_u = d_red_u;
         dx.aux = P.aux;
+        dx.exchange_tape = d_exch_tape;
+        dx.exchange_tape_offsets = d_exch_tape_offsets;
+        dx.exchange_tape_rounds = exch_tape_rounds;
+        dx.exchange_tape_state = d_exch_tape_state;
+        if (d_exch_tape && x.n_ladders != 1) return fail("an exchange tape replays a single ladder");
 #ifdef LDO_HOSTSIM
         for (int l = 0; l < x.n_ladders; l++) exchange_ladder(dx, l);
 #else
@@ -1937,6 +2057,9 @@ int ldo_set_control(ldo_engine* e, int first, int count, const int* temp_idx, co
             if (temp_idx[i] < 0 || temp_idx[i] >= b->shared.n_temps) return b->fail("temperature index out of range");
             aux[i].ctl.temp_idx = temp_idx[i];
             aux[i].ctl.temp = b->temps[temp_idx[i]];
+            // a control variable set from outside is a fresh potential (no table cache history)
+            aux[i].init_temp_idx = -1;
+            aux[i].table_cache_mask = 0;
         }
         if (staple_u_mult) aux[i].ctl.staple_u_mult = staple_u_mult[i];
         if (bias_mult) aux[i].ctl.bias_mult = bias_mult[i];
@@ -2172,7 +2295,7 @@ int ldo_center(ldo_engine* e, int centering_domain) {
 
 int ldo_exchange_collect(ldo_engine* e, double* dependent_local) {
     EngineBase* b = e->b;
-    int nq = 3 + (b->shared.sc.n_types - 1);
+    int nq = LDO_DEP_FIXED + (b->shared.sc.n_types - 1);
     OpArgs a;
     memset(&a, 0, sizeof(a));
     a.out_dependent = b->d_dependent;
@@ -2215,13 +2338,6 @@ int ldo_exchange_pt(ldo_engine* e, int variant, long long swap_i, int n_ladders,
                     int n_ranks, const double* dependent, int* slot_to_replica, long long* attempts,
                     long long* accepts) {
     if (variant < LDO_PT_T || variant > LDO_PT_ST) return e->b->fail("ldo_exchange_pt: 1-D variants only (see ldo_exchange_pt_2d)");
-    if (variant == LDO_PT_T || variant == LDO_PT_ST) {
-        // these variants do not exchange the staple chemical-potential multiplier (m_exchange_q_is,
-        // ptmc_simulation.cpp:602-623): every replica keeps its own, and the swap probability would need the
-        // replicas' multipliers rather than the slots'. Only a uniform ladder is the same thing.
-        for (double m: e->b->ladder_staple_u_mult)
-            if (m != e->b->ladder_staple_u_mult[0]) return e->b->fail("t_/st_parallel_tempering need uniform chem_pot_mults (the multiplier is not exchanged)");
-    }
     return exchange_pt_impl(e, variant, 0, swap_i, n_ladders, ladder_len, rank, n_ranks, dependent, slot_to_replica, attempts, accepts);
 }
 
@@ -2295,6 +2411,10 @@ int ldo_exchange_windows(ldo_engine* e, long long swap_i, int n_ladders, int n_w
     return b->exec(a, true);
 }
 
+int ldo_set_exchange_tape(ldo_engine* e, const double* reals, long long n, const long long* round_offsets, long long n_rounds) {
+    return e->b->set_exchange_tape(reals, n, round_offsets, n_rounds);
+}
+int ldo_exchange_tape_status(ldo_engine* e, long long* missing, long long* unused) { return e->b->exchange_tape_state(missing, unused); }
 long long ldo_launch_count(const ldo_engine* e) { return e->b->launches; }
 const char* ldo_build_info(void) {
 #ifdef LDO_HOSTSIM

@@ -841,10 +841,6 @@ ldo_sim* ldo_sim_create(const char* inp_path, int n_replicas, int device, int ra
                     smm[k] = p.m_stacking_mults[k % s->v2_dim];
                 }
             }
-            if (s->pt_variant == LDO_PT_T || s->pt_variant == LDO_PT_ST) {
-                for (double m: cm)
-                    if (m != cm[0]) throw SimulationMisuse {"t_/st_parallel_tempering do not exchange chem_pot_mults: they must be uniform"};
-            }
             // (the ladder keeps stacking_mults for every variant: calc_acceptance_p reads m_control_qs[3] whether
             // or not the variant applies the multiplier to the system, ptmc_simulation.cpp:283-284,307)
             s->check(ldo_set_exchange_ladder(s->eng, s->num_reps, ladder_ti.data(), cm.data(), bmm.data(), smm.data()));
@@ -852,11 +848,17 @@ ldo_sim* ldo_sim_create(const char* inp_path, int n_replicas, int device, int ra
             for (int r {0}; r != n_replicas; r++) {
                 int k {ladder_slot_of(*s, r % slots_per_rank)};
                 ti[r] = ladder_ti[k];
-                um[r] = cm[k];
-                // Only hut_parallel_tempering ever applies bias_mults (HUTPTGCMCSimulation::update_control_qs,
-                // ptmc_simulation.cpp:665-672: update_bias_mult overwrites the multiplier with the ladder value from
-                // the first round on); the other variants keep bias_funcs_mult and ignore bias_mults.
-                bm[r] = s->pt_variant == LDO_PT_HUT ? bmm[k] : p.m_bias_funcs_mult;
+                // What every replica holds BEFORE the first exchange (initialize_control_qs, ptmc_simulation.cpp:337-357 and
+                // :454-493): the bias multiplier is stored at index m_bias_i = 1, which is the staple-u-multiplier slot
+                // (App. A17), so a replica starts with staple_u_mult = bias_mults[rank] (1-D) / 1 (2-D) and, for
+                // hut_parallel_tempering, would start with bias multiplier 0 - had update_bias_mult any effect (below).
+                // master_send overwrites the exchanged quantities with the ladder values after the first exchange
+                // (m_exchange_q_is, :602-647); quantities a variant does not exchange keep these initial values.
+                um[r] = s->pt_variant == LDO_PT_2D ? 1.0 : bmm[k];
+                // No variant ever changes the bias multiplier: hut_parallel_tempering calls
+                // OrigamiSystem::update_bias_mult (:665-672), an empty virtual nothing overrides (origami_system.hpp:165),
+                // so SystemBiases keeps the constructor's bias_funcs_mult and bias_mults only decorate the .swp header.
+                bm[r] = p.m_bias_funcs_mult;
                 // st_/2d_: update_temp(temp, stacking_mult); t_/ut_/hut_: update_temp(temp), multiplier 1 (:651-680)
                 sm[r] = (s->pt_variant == LDO_PT_ST || s->pt_variant == LDO_PT_2D) ? smm[k] : 1.0;
             }

@@ -78,6 +78,22 @@ def lib():
         L.oref_nn_longest_contig_complement.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_int]
         L.oref_num_walks.restype = C.c_double
         L.oref_num_walks.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        L.oref_pt_run.restype = C.c_void_p
+        L.oref_pt_run.argtypes = [C.c_char_p, C.c_int, C.c_void_p, C.c_int, C.c_char_p, C.c_int]
+        L.oref_pt_destroy.argtypes = [C.c_void_p]
+        L.oref_pt_tape_len.restype = C.c_longlong
+        L.oref_pt_tape_len.argtypes = [C.c_void_p, C.c_int]
+        L.oref_pt_tape_copy.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.oref_pt_num_marks.restype = C.c_longlong
+        L.oref_pt_num_marks.argtypes = [C.c_void_p]
+        L.oref_pt_marks.argtypes = [C.c_void_p, C.c_void_p]
+        L.oref_pt_num_chains.argtypes = [C.c_void_p, C.c_int]
+        L.oref_pt_num_domains.argtypes = [C.c_void_p, C.c_int]
+        L.oref_pt_get_state.argtypes = [C.c_void_p, C.c_int] + [C.c_void_p] * 5
+        L.oref_pt_energy.restype = C.c_double
+        L.oref_pt_energy.argtypes = [C.c_void_p, C.c_int]
+        L.oref_pt_num_movetypes.argtypes = [C.c_void_p, C.c_int]
+        L.oref_pt_move_stats.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.oref_pt_acceptance_p.argtypes = [C.c_void_p] + [C.c_double] * 8 + [C.c_void_p, C.c_void_p, C.c_int] + [C.c_void_p] * 5
         _lib = L
     return _lib
@@ -288,6 +304,71 @@ class RefSystem:
 
     def unassign_domain(self, c, d):
         return self.L.oref_unassign_domain(self.h, c, d)
+
+
+def pt_run(options, n_ranks, seeds, record_tapes=True, workdir=None):
+    """The reference's own replica-exchange driver (PTGCMCSimulation::run, ptmc_simulation.cpp:106-150), one thread
+    per rank over the thread-backed boost::mpi shim. `options` must name a *_parallel_tempering simulation_type and
+    an output_filebase (the reference always writes <filebase>-<rank>.out/.vsf and <filebase>.swp). Returns a dict:
+    per-rank tapes, final states, energies, move statistics; rank 0's exchange draws separated from its MC draws
+    (`exchange_reals`, `mc_tapes[0]`); and the rows of the .swp file."""
+    tmp = None
+    if workdir is None:
+        tmp = tempfile.TemporaryDirectory(prefix="oref_pt_")
+        workdir = tmp.name
+    opts = dict(options)
+    opts.setdefault("output_filebase", os.path.join(workdir, "pt"))
+    inp = os.path.join(workdir, "oracle_pt.inp")
+    write_inp(inp, opts)
+    L = lib()
+    err = C.create_string_buffer(1024)
+    sd = np.ascontiguousarray(seeds, dtype=np.int32)
+    h = L.oref_pt_run(inp.encode(), n_ranks, sd.ctypes.data, 1 if record_tapes else 0, err, 1024)
+    if not h:
+        raise RuntimeError("oracle: " + err.value.decode())
+    out = {"tapes": [], "states": [], "energies": [], "attempts": [], "accepts": []}
+    for r in range(n_ranks):
+        n = L.oref_pt_tape_len(h, r)
+        t = np.zeros(n, dtype=DRAW_DTYPE)
+        if n:
+            L.oref_pt_tape_copy(h, r, t.ctypes.data)
+        out["tapes"].append(t)
+        nc, nd = L.oref_pt_num_chains(h, r), L.oref_pt_num_domains(h, r)
+        ci, cid, cl = (np.zeros(nc, dtype=np.int32) for _ in range(3))
+        pos, ore = np.zeros((nd, 3), dtype=np.int32), np.zeros((nd, 3), dtype=np.int32)
+        L.oref_pt_get_state(h, r, ci.ctypes.data, cid.ctypes.data, cl.ctypes.data, pos.ctypes.data, ore.ctypes.data)
+        out["states"].append({"chain_index": ci, "chain_ident": cid, "chain_len": cl, "pos": pos, "ore": ore})
+        out["energies"].append(L.oref_pt_energy(h, r))
+        nm = L.oref_pt_num_movetypes(h, r)
+        a, b = np.zeros(nm, dtype=np.int64), np.zeros(nm, dtype=np.int64)
+        L.oref_pt_move_stats(h, r, a.ctypes.data, b.ctypes.data)
+        out["attempts"].append(a)
+        out["accepts"].append(b)
+    nm = L.oref_pt_num_marks(h)
+    marks = np.zeros(nm, dtype=np.int64)
+    if nm:
+        L.oref_pt_marks(h, marks.ctypes.data)
+    L.oref_pt_destroy(h)
+    marks = marks.reshape(-1, 2)
+    out["marks"] = marks
+    # rank 0: MC draws with the master's exchange draws cut out, and those draws on their own
+    t0 = out["tapes"][0]
+    keep = np.ones(len(t0), dtype=bool)
+    for b, e in marks:
+        keep[b:e] = False
+    out["mc_tapes"] = [t0[keep]] + out["tapes"][1:]
+    ex = t0[~keep]
+    assert np.all(ex["kind"] == 0)
+    out["exchange_reals"] = ex["real"].copy()
+    # where every exchange round's draws start in exchange_reals
+    out["exchange_offsets"] = np.concatenate([[0], np.cumsum(marks[:, 1] - marks[:, 0])]).astype(np.int64)
+    swp = opts["output_filebase"] + ".swp"
+    rows = open(swp).read().splitlines()
+    out["swp_header"] = rows[0]
+    out["swp"] = [[int(x) for x in row.split()] for row in rows[1:]]
+    if tmp is not None:
+        tmp.cleanup()
+    return out
 
 
 def pt_acceptance_p(ref, temps, umults, bmults, smults, dep1, dep2, staple_u1, staple_u2, staple_n1, staple_n2):

@@ -479,3 +479,160 @@ extern "C" int oref_pt_acceptance_p(
     }
     return 0;
 }
+
+// ---- replica exchange: the reference's own PT drivers, one thread per rank ----------------------------
+//
+// Runs the UNMODIFIED PTGCMCSimulation subclasses (ptmc_simulation.cpp:106-150) with `n_ranks` replicas inside
+// this process: each rank is a std::thread over the thread-backed boost::mpi shim (shim/boost/mpi) and does what
+// apps/main.cpp does (InputParameters -> setup_origami -> simulation constructor -> run()). Every rank records
+// its own value-level tape; rank 0's tape also carries the master's exchange draws (App. A20), whose positions
+// are marked by a thin subclass that brackets attempt_exchange() - nothing of the reference is modified.
+
+#include <memory>
+#include <thread>
+
+#include "LatticeDNAOrigami/ptmc_simulation.hpp"
+#include <boost/mpi/communicator.hpp>
+
+namespace {
+
+struct NullBuf: std::streambuf {
+    int overflow(int c) override { return c; }
+    std::streamsize xsputn(const char*, std::streamsize n) override { return n; }
+};
+
+struct PtRank {
+    oracle_tape::Tape tape {};
+    std::vector<long long> marks {}; // rank 0: [begin, end) tape positions of every attempt_exchange call
+    std::vector<int> chain_index, chain_ident, chain_len, pos, ore;
+    std::vector<long long> attempts, accepts;
+    double energy {0};
+    std::string err {};
+};
+
+struct PtHandle {
+    std::vector<PtRank> ranks;
+    std::string err {};
+};
+
+template <class Base>
+struct MarkedPT: Base {
+    using Base::Base;
+    PtRank* rec {nullptr};
+    void attempt_exchange(int swap_i) override {
+        long long b {static_cast<long long>(rec->tape.size())};
+        Base::attempt_exchange(swap_i);
+        rec->marks.push_back(b);
+        rec->marks.push_back(static_cast<long long>(rec->tape.size()));
+    }
+};
+
+template <class Sim>
+void pt_rank_body(parser::InputParameters& params, origami::OrigamiSystem& origami, PtRank& rec, int seed, bool record) {
+    MarkedPT<Sim> sim {origami, origami.get_system_order_params(), origami.get_system_biases(), params};
+    sim.rec = &rec;
+    sim.m_random_gens.set_seed(seed);
+    if (record) oracle_tape::g_record = &rec.tape;
+    sim.run();
+    oracle_tape::g_record = nullptr;
+    for (auto& mt: sim.m_movetypes) {
+        rec.attempts.push_back(mt->get_attempts());
+        rec.accepts.push_back(mt->get_accepts());
+    }
+}
+
+void pt_rank_main(const char* inp_path, int rank, int seed, bool record, PtRank* rec) {
+    boost::mpi::shim_rank() = rank;
+    try {
+        std::string a0 {"oracle"}, a1 {"-i"}, a2 {inp_path};
+        char* argv[] {&a0[0], &a1[0], &a2[0]};
+        parser::InputParameters params {3, argv};
+        std::unique_ptr<origami::OrigamiSystem> origami {origami::setup_origami(params)};
+        std::string const& st = params.m_simulation_type;
+        if (st == "t_parallel_tempering") pt_rank_body<ptmc::TPTGCMCSimulation>(params, *origami, *rec, seed, record);
+        else if (st == "ut_parallel_tempering") pt_rank_body<ptmc::UTPTGCMCSimulation>(params, *origami, *rec, seed, record);
+        else if (st == "hut_parallel_tempering") pt_rank_body<ptmc::HUTPTGCMCSimulation>(params, *origami, *rec, seed, record);
+        else if (st == "st_parallel_tempering") pt_rank_body<ptmc::STPTGCMCSimulation>(params, *origami, *rec, seed, record);
+        else if (st == "2d_parallel_tempering") pt_rank_body<ptmc::TwoDPTGCMCSimulation>(params, *origami, *rec, seed, record);
+        else throw std::runtime_error {"oref_pt_run: not a parallel tempering simulation type"};
+        auto& o = *origami;
+        for (size_t i {0}; i != o.m_domains.size(); i++) {
+            rec->chain_index.push_back(o.m_chain_indices[i]);
+            rec->chain_ident.push_back(o.m_chain_identities[i]);
+            rec->chain_len.push_back(o.m_domains[i].size());
+            for (auto d: o.m_domains[i]) {
+                for (int a {0}; a != 3; a++) {
+                    rec->pos.push_back(d->m_pos.at(a));
+                    rec->ore.push_back(d->m_ore.at(a));
+                }
+            }
+        }
+        rec->energy = o.energy();
+    } catch (std::exception const& e) {
+        rec->err = e.what();
+        // a rank that dies would leave the others blocked in recv: there is no recovery, report and abort the run
+        std::cerr << "oracle PT rank " << rank << ": " << e.what() << std::endl;
+        std::abort();
+    }
+}
+
+} // namespace
+
+extern "C" {
+
+// seeds[n_ranks]: every rank's mt19937_64 seed (RandomGens::set_seed after construction, so that the ranks do not
+// share one stream as they would with a common random_seed, simulation.cpp:199-203)
+void* oref_pt_run(const char* inp_path, int n_ranks, const int* seeds, int record_tapes, char* err, int errlen) {
+    auto h = new PtHandle {};
+    h->ranks.resize(n_ranks);
+    NullBuf nullbuf {};
+    std::streambuf* old {std::cout.rdbuf(&nullbuf)};
+    boost::mpi::shim_world::get().size = n_ranks;
+    {
+        std::unique_lock<std::mutex> lk(boost::mpi::shim_world::get().mu);
+        boost::mpi::shim_world::get().box.clear();
+    }
+    std::vector<std::thread> threads;
+    for (int r {0}; r != n_ranks; r++) threads.emplace_back(pt_rank_main, inp_path, r, seeds[r], record_tapes != 0, &h->ranks[r]);
+    for (auto& t: threads) t.join();
+    boost::mpi::shim_world::get().size = 1;
+    std::cout.rdbuf(old);
+    for (auto& r: h->ranks) {
+        if (!r.err.empty()) {
+            set_err(err, errlen, r.err);
+            delete h;
+            return nullptr;
+        }
+    }
+    return h;
+}
+void oref_pt_destroy(void* vh) { delete static_cast<PtHandle*>(vh); }
+long long oref_pt_tape_len(void* vh, int rank) { return static_cast<PtHandle*>(vh)->ranks[rank].tape.size(); }
+void oref_pt_tape_copy(void* vh, int rank, oracle_tape::Draw* out) {
+    auto& t = static_cast<PtHandle*>(vh)->ranks[rank].tape;
+    std::memcpy(out, t.data(), t.size() * sizeof(oracle_tape::Draw));
+}
+long long oref_pt_num_marks(void* vh) { return static_cast<PtHandle*>(vh)->ranks[0].marks.size(); }
+void oref_pt_marks(void* vh, long long* out) {
+    auto& m = static_cast<PtHandle*>(vh)->ranks[0].marks;
+    std::memcpy(out, m.data(), m.size() * sizeof(long long));
+}
+int oref_pt_num_chains(void* vh, int rank) { return static_cast<PtHandle*>(vh)->ranks[rank].chain_index.size(); }
+int oref_pt_num_domains(void* vh, int rank) { return static_cast<PtHandle*>(vh)->ranks[rank].pos.size() / 3; }
+void oref_pt_get_state(void* vh, int rank, int* chain_index, int* chain_ident, int* chain_len, int* pos, int* ore) {
+    auto& r = static_cast<PtHandle*>(vh)->ranks[rank];
+    std::memcpy(chain_index, r.chain_index.data(), r.chain_index.size() * sizeof(int));
+    std::memcpy(chain_ident, r.chain_ident.data(), r.chain_ident.size() * sizeof(int));
+    std::memcpy(chain_len, r.chain_len.data(), r.chain_len.size() * sizeof(int));
+    std::memcpy(pos, r.pos.data(), r.pos.size() * sizeof(int));
+    std::memcpy(ore, r.ore.data(), r.ore.size() * sizeof(int));
+}
+double oref_pt_energy(void* vh, int rank) { return static_cast<PtHandle*>(vh)->ranks[rank].energy; }
+int oref_pt_num_movetypes(void* vh, int rank) { return static_cast<PtHandle*>(vh)->ranks[rank].attempts.size(); }
+void oref_pt_move_stats(void* vh, int rank, long long* attempts, long long* accepts) {
+    auto& r = static_cast<PtHandle*>(vh)->ranks[rank];
+    std::memcpy(attempts, r.attempts.data(), r.attempts.size() * sizeof(long long));
+    std::memcpy(accepts, r.accepts.data(), r.accepts.size() * sizeof(long long));
+}
+
+} // extern "C"

@@ -17,6 +17,7 @@ HOSTSIM_LIB = os.path.join(ROOT, "tests", "hostsim", "libldo_hostsim.so")
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    config.addinivalue_line("markers", "slow: minutes of GPU time (long equilibrium runs)")
 
 
 # Options of examples/constant-temp.inp with every output off (same dict as oracle_ref.SNODIN_OPTIONS)

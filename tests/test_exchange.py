@@ -224,14 +224,15 @@ def test_swap_probability_matches_reference_code(hostsim_lib, oracle, tmp_path):
         um1, um2 = rng.uniform(0.8, 1.2, 2)
         sm1, sm2 = rng.uniform(0.5, 1.0, 2)
         scale = rng.choice([0.01, 0.3, 3.0])
-        d1 = np.concatenate([rng.normal(-300, 60, 1) * scale, rng.normal(0, 3, 1) * scale, rng.normal(-20, 5, 1) * scale,
+        # exchange record layout: enthalpy, bias, stacking, the replica's staple_u multiplier, staple counts
+        d1 = np.concatenate([rng.normal(-300, 60, 1) * scale, rng.normal(0, 3, 1) * scale, rng.normal(-20, 5, 1) * scale, [um1],
                              rng.integers(0, 3, nst).astype(float)])
-        d2 = np.concatenate([rng.normal(-300, 60, 1) * scale, rng.normal(0, 3, 1) * scale, rng.normal(-20, 5, 1) * scale,
+        d2 = np.concatenate([rng.normal(-300, 60, 1) * scale, rng.normal(0, 3, 1) * scale, rng.normal(-20, 5, 1) * scale, [um2],
                              rng.integers(0, 3, nst).astype(float)])
         ours = eng.L.ldo_exchange_acceptance_p(nst, red.ctypes.data, t1, t2, um1, um2, sm1, sm2, d1.ctypes.data, d2.ctypes.data)
         pad = lambda a: np.concatenate([a, [0.0]])  # the reference's loop reads n_types entries (App. A1)
         want = oracle.pt_acceptance_p(ref, (t1, t2), (um1, um2), (1.0, 1.0), (sm1, sm2), d1[:3], d2[:3],
-                                      pad(ref.staple_us(t1, um1)), pad(ref.staple_us(t2, um2)), pad(d1[3:]), pad(d2[3:]))
+                                      pad(ref.staple_us(t1, um1)), pad(ref.staple_us(t2, um2)), pad(d1[4:]), pad(d2[4:]))
         assert abs(ours - want) <= 1e-12 * max(want, 1e-300), (ours, want)
         seen_partial += 0.0 < want < 1.0
     assert seen_partial > 20
@@ -253,3 +254,65 @@ def test_two_d_driver_writes_swap_file(hostsim_lib, tmp_path):
         assert sorted(int(x) for x in row.split()) == [0, 1, 2, 3]
     # per-replica configuration files carry the "-<rank>" postfix of the reference
     assert (tmp_path / "pt2d-0.trj").exists() and (tmp_path / "pt2d-3.trj").exists()
+
+
+def _swap_acceptance_frequency(lib, tmp_path, n_ladders, rounds):
+    """Decisions against probabilities over many ladders: every tested pair is a Bernoulli trial whose probability
+    is the engine's own exchange_acceptance_p (pinned to the reference's calc_acceptance_p above) of the collected
+    exchange records. The number of accepted swaps must match the sum of the probabilities within 4 binomial
+    standard deviations - overall and on the pairs with 0.05 < p < 0.95 alone, where a reversed comparison
+    (p < u instead of p > u) or a wrong pairing would show."""
+    temps = [336.0, 338.0, 340.0, 342.0]
+    L = len(temps)
+    opts = make_options("snodin_unbound.json", simulation_type="ut_parallel_tempering", num_reps=L, temps=temps, chem_pot_mults=[1] * L,
+                        bias_mults=[1] * L, stacking_mults=[1] * L, exchange_interval=100, swaps=rounds, random_seed=4711)
+    sim = Simulation(write_inp(str(tmp_path / "freq.inp"), opts), n_ladders * L, 0, lib=lib)
+    eng = sim.engine
+    red = np.zeros(64)
+    nst = eng.L.ldo_get_reduced_staple_u(eng.h, red.ctypes.data)
+    q2r_prev = np.tile(np.arange(L, dtype=np.int32), (n_ladders, 1))
+    sum_p = var = n_acc = 0.0
+    part_p = part_var = part_acc = 0.0
+    w_stat = w_var = w_power = 0.0  # sum (swapped - p)(2p - 1): a reversed comparison shifts it by -sum (2p - 1)^2
+    n_part = 0
+    for swap_i in range(1, rounds + 1):
+        assert sim.exchange_advance() == 0
+        dep = np.ascontiguousarray(eng.exchange_collect().reshape(n_ladders, L, -1))
+        sim.exchange_apply(swap_i)
+        q2r = sim.exchange_state(n_ladders, L)[0]
+        for l in range(n_ladders):
+            for i in range(swap_i % 2, L - 1, 2):
+                r1, r2 = q2r_prev[l, i], q2r_prev[l, i + 1]
+                d1, d2 = dep[l, r1], dep[l, r2]
+                p = eng.L.ldo_exchange_acceptance_p(nst, red.ctypes.data, temps[i], temps[i + 1], d1[3], d2[3], 1.0, 1.0,
+                                                    d1.ctypes.data, d2.ctypes.data)
+                swapped = q2r[l, i] == r2 and q2r[l, i + 1] == r1
+                assert swapped or (q2r[l, i] == r1 and q2r[l, i + 1] == r2)
+                sum_p += p
+                var += p * (1 - p)
+                n_acc += swapped
+                if 0.05 < p < 0.95:
+                    n_part += 1
+                    part_p += p
+                    part_var += p * (1 - p)
+                    part_acc += swapped
+                    w_stat += (float(swapped) - p) * (2 * p - 1)
+                    w_var += p * (1 - p) * (2 * p - 1) ** 2
+                    w_power += (2 * p - 1) ** 2
+        q2r_prev = q2r.copy()
+    eng.assert_ok()
+    assert n_part >= 30, n_part
+    assert abs(n_acc - sum_p) <= 4 * np.sqrt(var), (n_acc, sum_p, var)
+    assert abs(part_acc - part_p) <= 4 * np.sqrt(part_var), (part_acc, part_p, part_var, n_part)
+    # a reversed comparison (accepting with 1 - p) would move the weighted statistic by -w_power: the test can tell
+    assert abs(w_stat) <= 4 * np.sqrt(w_var), (w_stat, w_var)
+    assert w_power > 8 * np.sqrt(w_var), (w_power, w_var)
+
+
+def test_swap_acceptance_frequency(hostsim_lib, tmp_path):
+    _swap_acceptance_frequency(hostsim_lib, tmp_path, n_ladders=24, rounds=10)
+
+
+@pytest.mark.gpu
+def test_swap_acceptance_frequency_gpu(tmp_path):
+    _swap_acceptance_frequency(None, tmp_path, n_ladders=512, rounds=16)

@@ -1,0 +1,158 @@
+"""Production-mode parity: the code `bench.py` times (Philox draws, lane-parallel recoil-growth branches) against
+the UNMODIFIED reference, statistically - replay tapes cannot reach those branches (they follow the reference's
+serial draw order).
+
+1. snodin at five state points against reference-MC run with the same short protocol on 512 seeds
+   (tests/golden/refmc_snodin.json, made by tests/golden/make_refmc_snodin.py): ensemble means of the order
+   parameters and the energy AND the acceptance rate of every movetype, within 4 combined standard errors, no
+   additive slack.
+2. the lane-parallel branches (rg_select_open_config, the one-draw feeler test, rg_count_avail_parallel) against
+   the serial reference-order branches driven by the same Philox generator (ldo_set_reference_draw_order) - the
+   branches every bit-exact replay test runs - on the same observables.
+3. four_unbound at equilibrium against the reference's exact enumeration (tests/golden/enum_four_unbound.json):
+   chi-square over the states of (numfulldomains, nummisdomains, numstackedpairs, numstaples) at 330 K and 340 K.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, make_options, write_inp
+from latticednaorigami_b200.binding import Simulation
+
+pytestmark = pytest.mark.gpu
+
+REF = os.path.join(GOLDEN, "refmc_snodin.json")
+POINTS = ["snodin_unbound@335", "snodin_unbound@340", "snodin_unbound@345", "snodin_assembled@330", "snodin_assembled@336"]
+OBS = ["numstaples", "numfulldomains", "nummisdomains", "numstackedpairs", "energy"]
+
+
+def run_protocol(tmp_path, system, temp, R, burn, samples, stride, seed, reference_draw_order=False):
+    """Per-replica time averages of OBS and per-replica acceptance rates under the fixture's protocol."""
+    sim = Simulation(write_inp(str(tmp_path / f"p{seed}.inp"), make_options(system, temp=temp, random_seed=seed)), R, 0)
+    eng = sim.engine
+    if reference_draw_order:
+        eng.set_reference_draw_order(True)
+    eng.run(burn)
+    acc = np.zeros((R, len(OBS)))
+    for _ in range(samples):
+        eng.run(stride)
+        c = eng.counters()
+        acc[:, 0] += c[:, 0]
+        acc[:, 1] += c[:, 3]
+        acc[:, 2] += c[:, 5]
+        acc[:, 3] += c[:, 6]
+        acc[:, 4] += eng.energies()[:, 0]
+    eng.assert_ok()
+    att, ok = eng.move_stats()
+    assert np.all(att.sum(axis=1) == burn + samples * stride)
+    return acc / samples, ok / np.maximum(att, 1), sim.movetype_labels
+
+
+def mean_sem(x):
+    return x.mean(axis=0), x.std(axis=0, ddof=1) / np.sqrt(x.shape[0])
+
+
+@pytest.mark.parametrize("point", POINTS)
+def test_snodin_production_matches_reference_mc(tmp_path, point):
+    ref = json.load(open(REF))
+    pt = ref["points"][point]
+    R = 16384
+    obs, rate, labels = run_protocol(tmp_path, pt["system"], pt["temp"], R, ref["burn"], ref["samples"], ref["stride"], seed=20260000 + pt["temp"])
+    m, s = mean_sem(obs)
+    report = []
+    worst = 0.0
+    # an observable that never varied over the reference's 512 seeds x 20 samples (sem 0, e.g. 12 staples at 330 K)
+    # carries the zero-count bound of that sample instead: 3 / 10240 events
+    zero_count = 3.0 / (ref["seeds"] * ref["samples"])
+    for k, name in enumerate(OBS):
+        tol = 4 * np.hypot(s[k], pt["sem"][name]) + (zero_count * max(1.0, abs(pt["mean"][name])) if pt["sem"][name] == 0 else 0.0)
+        z = abs(m[k] - pt["mean"][name]) / max(np.hypot(s[k], pt["sem"][name]), 1e-300)
+        report.append((name, m[k], pt["mean"][name], z))
+        worst = max(worst, z)
+        assert abs(m[k] - pt["mean"][name]) <= tol, (point, name, m[k], pt["mean"][name], tol)
+    rm, rs = mean_sem(rate)
+    for i, label in enumerate(labels):
+        sem = np.hypot(rs[i], pt["accept_rate_sem"][i])
+        if pt["accept_rate_sem"][i] == 0:
+            # all (or none) of the reference's attempts were accepted: zero-count bound of its sample
+            n_ref = ref["seeds"] * (ref["burn"] + ref["samples"] * ref["stride"]) * pt["attempt_share"][i]
+            assert abs(rm[i] - pt["accept_rate"][i]) <= 4 * rs[i] + 3.0 / n_ref, (point, label, rm[i], pt["accept_rate"][i])
+            continue
+        z = abs(rm[i] - pt["accept_rate"][i]) / sem
+        report.append((label, rm[i], pt["accept_rate"][i], z))
+        worst = max(worst, z)
+        assert z <= 4, (point, label, rm[i], pt["accept_rate"][i], sem)
+    print(point, "worst z = %.2f" % worst, report)
+
+
+@pytest.mark.parametrize("point", ["snodin_unbound@340", "snodin_assembled@330"])
+def test_lane_parallel_branches_match_reference_draw_order(tmp_path, point):
+    ref = json.load(open(REF))
+    pt = ref["points"][point]
+    R = 4096
+    a_obs, a_rate, labels = run_protocol(tmp_path, pt["system"], pt["temp"], R, ref["burn"], ref["samples"], ref["stride"], seed=31)
+    b_obs, b_rate, _ = run_protocol(tmp_path, pt["system"], pt["temp"], R, ref["burn"], ref["samples"], ref["stride"], seed=32,
+                                    reference_draw_order=True)
+    for name, a, b in [(n, a_obs[:, k], b_obs[:, k]) for k, n in enumerate(OBS)] + [(l, a_rate[:, i], b_rate[:, i]) for i, l in enumerate(labels)]:
+        (ma, sa), (mb, sb) = mean_sem(a), mean_sem(b)
+        sem = np.hypot(sa, sb)
+        if sem == 0:
+            assert ma == mb, (point, name)
+            continue
+        assert abs(ma - mb) <= 4 * sem, (point, name, ma, mb, sem)
+    # the serial ensemble also agrees with the reference itself
+    m, s = mean_sem(b_obs)
+    for k, name in enumerate(OBS):
+        assert abs(m[k] - pt["mean"][name]) <= 4 * np.hypot(s[k], pt["sem"][name]), (point, name)
+
+
+# ---- four_unbound at equilibrium against exact enumeration ---------------------
+
+FOUR_BURN, FOUR_SAMPLES, FOUR_STRIDE = 200000, 1000, 1000  # >= 1e6 sampled moves per replica after burn-in
+
+
+def four_unbound_frequencies(tmp_path, temp, R, seed):
+    opts = make_options("four_unbound.json", "moveset_four.json", temp=temp, max_total_staples=2, max_type_staples=2, random_seed=seed)
+    sim = Simulation(write_inp(str(tmp_path / f"f{seed}.inp"), opts), R, 0)
+    eng = sim.engine
+    idx = [sim.op_tags.index(t) for t in ("numfulldomains", "nummisdomains", "numstackedpairs", "numstaples")]
+    eng.run(FOUR_BURN, 10000, 0, 0)
+    per_rep = {}
+    for _ in range(FOUR_SAMPLES):
+        eng.run(FOUR_STRIDE, 10000, 0, 0)
+        ops = eng.order_params()[:, idx]
+        code = ((ops[:, 0] * 8 + ops[:, 1]) * 8 + ops[:, 2]) * 8 + ops[:, 3]
+        for c in np.unique(code):
+            per_rep.setdefault(int(c), np.zeros(R))[code == c] += 1
+    eng.assert_ok()
+    out = {}
+    for c, v in per_rep.items():
+        key = "(%d %d %d %d)" % (c >> 9, (c >> 6) & 7, (c >> 3) & 7, c & 7)
+        out[key] = v / FOUR_SAMPLES
+    return out
+
+
+@pytest.mark.slow
+@pytest.mark.parametrize("temp", [330, 340])
+def test_four_unbound_equilibrium_matches_exact_enumeration(tmp_path, temp):
+    w = json.load(open(os.path.join(GOLDEN, "enum_four_unbound.json")))[str(temp)]["weights"]
+    R = 4096
+    freq = four_unbound_frequencies(tmp_path, temp, R, seed=9000 + temp)
+    chi2, dof, report = 0.0, 0, []
+    for key, want in sorted(w.items(), key=lambda kv: -kv[1]):
+        per_rep = freq.get(key, np.zeros(R))
+        p, sem = per_rep.mean(), per_rep.std(ddof=1) / np.sqrt(R)
+        if want < 1e-4 or sem == 0:
+            continue
+        z = (p - want) / sem
+        report.append((key, want, p, sem, z))
+        chi2 += z * z
+        dof += 1
+        assert abs(z) < 4.5, (temp, key, want, p, sem, z)
+    print(temp, "chi2 = %.1f over %d states" % (chi2, dof), report)
+    assert dof >= 4
+    # 99.99 % quantile of chi-square with `dof` degrees of freedom (Wilson-Hilferty)
+    crit = dof * (1 - 2 / (9 * dof) + 3.719 * np.sqrt(2 / (9 * dof))) ** 3
+    assert chi2 < crit, (temp, chi2, dof, crit)
