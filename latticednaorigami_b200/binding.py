@@ -203,6 +203,11 @@ class Engine:
     def seed(self, seed, first_subsequence=0):
         self._check(self.L.ldo_seed(self.h, int(seed), int(first_subsequence)))
 
+    def seed_subsequences(self, seed, subsequences):
+        sub = np.ascontiguousarray(subsequences, dtype=np.uint32)
+        assert len(sub) == self.R
+        self._check(self.L.ldo_seed_subsequences(self.h, int(seed), _ptr(sub)))
+
     def attach_tape(self, replica, tape):
         tape = np.ascontiguousarray(tape, dtype=DRAW_DTYPE)
         self._check(self.L.ldo_attach_tape(self.h, replica, _ptr(tape), len(tape)))

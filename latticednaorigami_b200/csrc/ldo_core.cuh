@@ -319,7 +319,7 @@ struct Caps {
 
 // Persistent configuration of one replica
 template <class K>
-struct SysState {
+struct alignas(16) SysState { // staged to / from shared memory with 128-bit copies
     DomRec dom[K::D];
     short bound[K::D]; // partner domain id or -1
     short ident[K::D]; // domain identity (m_d_ident)
@@ -340,6 +340,10 @@ struct SysState {
     int constraints_violated;
     int status;
     int status_detail;
+    // != 0 inside the weight passes of the recoil-growth moves: placements and removals keep the lattice, the domain
+    // records and the pair counters current but leave the running energy and the stacked-pair count alone (the
+    // caller restores both from its snapshots); see Engine::rg_regrow_and_test
+    int weight_pass;
     double energy;
     double stack_e; // stacking_ene * stacking_mult / T for this replica
     int type_count[K::T]; // staples per identity (|m_identity_to_index[i]|)
@@ -1281,6 +1285,10 @@ struct System {
     // OrigamiSystem::set_checked_domain_config (origami_system.cpp:478-515)
     LDO_HDN double set_checked_domain_config(int d, V3 p, int o) {
         commit_place(d, p, o);
+        if (S()->weight_pass) {
+            S()->num_unassigned--;
+            return 0;
+        }
         double delta_e = 0;
         int st = S()->dom[d].state;
         if (st == ST_MISBOUND) {
@@ -1308,24 +1316,27 @@ struct System {
         int stacked = 0;
         if (st == ST_BOUND || st == ST_MISBOUND) {
             int j = S()->bound[d];
+            bool with_energy = S()->weight_pass == 0;
             S()->num_bound_pairs -= 1;
             if (st == ST_BOUND) {
                 S()->num_fully_bound_pairs -= 1;
-                DeltaConfig dc = check_stacking(d, j);
-                e = -dc.e;
-                stacked = -dc.stacked;
+                if (with_energy) {
+                    DeltaConfig dc = check_stacking(d, j);
+                    e = -dc.e;
+                    stacked = -dc.stacked;
+                }
             }
             else if (S()->dchain[j] == S()->dchain[d]) {
                 S()->num_self_bound_pairs -= 1;
             }
-            e += -hyb_energy(d, j);
+            if (with_energy) e += -hyb_energy(d, j);
             S()->bound[d] = -1;
             S()->bound[j] = -1;
             S()->dom[d].state = ST_UNASSIGNED;
             S()->dom[j].state = ST_UNBOUND;
             const DomRec& r = S()->dom[d];
             table_put(rec_pos(r), j);
-            if (SC().apply_mean_field_cor && st == ST_BOUND) {
+            if (with_energy && SC().apply_mean_field_cor && st == ST_BOUND) {
                 if (S()->num_fully_bound_pairs == 0) e -= 2 * log(6.0);
                 else if (S()->num_fully_bound_pairs == 1) e -= log(3.0);
             }

@@ -229,6 +229,7 @@ LDO_HD void rep_load_config(Engine<K>& eng, const OpArgs& a) {
     s->status = LDO_OK;
     s->status_detail = 0;
     s->constraints_violated = 0;
+    s->weight_pass = 0;
     sys.table_clear();
     for (int c = 0; c < K::C; c++) s->chain_used[c] = 0;
     for (int t = 0; t < K::T; t++) s->type_count[t] = 0;
@@ -494,9 +495,10 @@ static_assert(LDO_AUX_HOT_BYTES % 16 == 0, "staged part of RepAux must be a mult
 // longest-processing-time rule for the tail), dealt round-robin into one list per SM so that every SM
 // works through the same mix of expensive and cheap replicas; a warp whose list is empty steals from the
 // next lists.
-__device__ inline int take_item(int* heads, int n_items, int n_lists, int my_list) {
+__device__ inline int take_item(int* heads, int n_items, int n_lists, int my_list, int grouped) {
     for (int j = 0; j < n_lists; j++) {
-        int l = my_list + j;
+        // own list first; then the next lists (dealt mode), or the most expensive lists first (grouped mode)
+        int l = (grouped && j > 0) ? j - 1 : my_list + j;
         if (l >= n_lists) l -= n_lists;
         int len = (n_items - l + n_lists - 1) / n_lists; // items l, l + n_lists, ...
         if (len <= 0 || *(volatile int*)&heads[l] >= len) continue;
@@ -507,7 +509,7 @@ __device__ inline int take_item(int* heads, int n_items, int n_lists, int my_lis
 }
 
 template <class K>
-__global__ void __launch_bounds__(32 * LDO_BLOCK_WARPS, LDO_MIN_BLOCKS) k_exec_staged(DevPtrs<K> P, OpArgs a, int n_items, int n_lists) {
+__global__ void __launch_bounds__(32 * LDO_BLOCK_WARPS, LDO_MIN_BLOCKS) k_exec_staged(DevPtrs<K> P, OpArgs a, int n_items, int n_lists, int grouped) {
     WarpSmem<K>* ws = reinterpret_cast<WarpSmem<K>*>(ldo_smem_raw);
     int warp = threadIdx.x >> 5;
     WarpSmem<K>& w = ws[warp];
@@ -527,7 +529,7 @@ __global__ void __launch_bounds__(32 * LDO_BLOCK_WARPS, LDO_MIN_BLOCKS) k_exec_s
     my_list %= (unsigned)n_lists;
     for (;;) {
         int idx = 0;
-        if ((threadIdx.x & 31) == 0) idx = take_item(P.queue, n_items, n_lists, (int)my_list);
+        if ((threadIdx.x & 31) == 0) idx = take_item(P.queue, n_items, n_lists, (int)my_list, grouped);
         idx = __shfl_sync(0xffffffffu, idx, 0);
         if (idx < 0) break;
         int r = a.only_replica >= 0 ? a.only_replica : (a.op == OP_RUN ? P.order[idx] : idx);
@@ -561,7 +563,9 @@ __global__ void k_probe_smem_base(unsigned* out) {
 
 // Order in which the next run launch hands out replicas: descending duration of the previous run launch
 // (counting sort over 256 cost buckets, one block). All zeros (first launch) gives the identity.
-__global__ void __launch_bounds__(1024) k_build_order(const long long* run_timing, int* order, int* queue, int n) {
+// `grouped`: list l (items l, l + n_lists, ... of `order`) receives a CONTIGUOUS run of the cost-sorted replicas instead of
+// every n_lists-th one, so that the warps of one SM work on replicas of the same regime (same hot code).
+__global__ void __launch_bounds__(1024) k_build_order(const long long* run_timing, int* order, int* queue, int n, int n_lists, int grouped) {
     __shared__ long long s_max;
     __shared__ int hist[256], cursor[256];
     int t = threadIdx.x;
@@ -600,7 +604,20 @@ __global__ void __launch_bounds__(1024) k_build_order(const long long* run_timin
     // the order inside a bucket is arbitrary: replicas are independent, results do not depend on it
     for (int r = t; r < n; r += blockDim.x) {
         long long d = run_timing[3 * r + 1] - run_timing[3 * r];
-        order[atomicAdd(&cursor[255 - (int)(d * 255 / mx)], 1)] = r;
+        int q = atomicAdd(&cursor[255 - (int)(d * 255 / mx)], 1);
+        if (grouped && n_lists > 1) {
+            int base = n / n_lists, rem = n % n_lists, l, k;
+            if (q < rem * (base + 1)) {
+                l = q / (base + 1);
+                k = q % (base + 1);
+            }
+            else {
+                l = rem + (q - rem * (base + 1)) / base;
+                k = (q - rem * (base + 1)) % base;
+            }
+            q = k * n_lists + l;
+        }
+        order[q] = r;
     }
 }
 
@@ -1136,6 +1153,7 @@ struct EngineImpl: EngineBase {
     int warps_per_block = 4;
     int n_sm = 1;
     int resident_blocks = 1; // staged kernel: blocks resident on the whole device (persistent grid)
+    int order_grouped = 0; // LDO_ORDER_MODE=grouped: one SM works on replicas of one cost class (profiling knob)
 
     EngineImpl() {
         memset(&P, 0, sizeof(P));
@@ -1314,15 +1332,16 @@ struct EngineImpl: EngineBase {
         if constexpr (STAGED) {
             size_t smem = sizeof(WarpSmem<K>) * wpb;
             int n_items = a.only_replica >= 0 ? 1 : R;
+            int n_lists = a.op == OP_RUN && n_items > 1 ? (n_sm < LDO_MAX_LISTS ? n_sm : LDO_MAX_LISTS) : 1;
+            int grouped = order_grouped && n_lists > 1 && R >= n_lists ? 1 : 0;
             if (a.op == OP_RUN && a.only_replica < 0) {
-                k_build_order<<<1, 1024, 0, stream>>>(P.run_timing, P.order, P.queue, R);
+                k_build_order<<<1, 1024, 0, stream>>>(P.run_timing, P.order, P.queue, R, n_lists, grouped);
                 launches++;
             }
             else if (chk(cudaMemsetAsync(P.queue, 0, sizeof(int) * LDO_MAX_LISTS, stream))) return fail(dev_err());
             blocks = (n_items + wpb - 1) / wpb;
             if (blocks > resident_blocks) blocks = resident_blocks;
-            int n_lists = a.op == OP_RUN && n_items > 1 ? (n_sm < LDO_MAX_LISTS ? n_sm : LDO_MAX_LISTS) : 1;
-            k_exec_staged<K><<<blocks, wpb * 32, smem, stream>>>(P, a, n_items, n_lists);
+            k_exec_staged<K><<<blocks, wpb * 32, smem, stream>>>(P, a, n_items, n_lists, grouped);
         }
         else {
             k_exec_inplace<K><<<blocks, wpb * 32, 0, stream>>>(P, a, wpb, d_recompute_tmp);
@@ -1379,6 +1398,7 @@ struct EngineImpl: EngineBase {
             int per_sm = 0;
             if (chk(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_exec_staged<K>, wpb * 32, per_warp * wpb))) return fail(dev_err());
             cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device);
+            if (const char* om = getenv("LDO_ORDER_MODE")) order_grouped = strcmp(om, "grouped") == 0;
             // profiling knob (profiles/sweep_occupancy.py): fewer resident blocks per SM than fit
             if (const char* cap = getenv("LDO_MAX_BLOCKS_PER_SM")) {
                 int c = atoi(cap);

@@ -2486,12 +2486,28 @@ struct Engine {
     // Shared tail of the two CTRG scaffold moves (rg:636-689, 810-851). `whole_cyclic`: the
     // endpoint-removal guards evaluated by the caller (App. A2 keeps the contiguous variant's quirk).
     LDO_HDN bool rg_regrow_and_test(bool remove_first_a, bool remove_first_b, int first_dom) {
+        // The weight passes below tear the regrown domains down and put them back five times (new configuration,
+        // old configuration, new configuration again on acceptance). The reference evaluates the binding potential
+        // for every one of those placements and removals (set_checked_domain_config / unassign_domain,
+        // rg_movetypes.cpp:363-417, 482-533) although the energy changes cancel and nobody reads them: only the
+        // lattice, the domain records and the pair counters matter to the trial evaluations in between. Here the
+        // passes run with SysState::weight_pass set - no potential evaluation for placements and removals - and the
+        // running energy and the stacked-pair count are restored from snapshots: those of the old configuration on
+        // rejection, those of the new one on acceptance. Same decisions, same lattice; the running energy differs
+        // from the reference's by the rounding of terms that cancel (it agrees to 1e-12, as everywhere).
+        const double e_old = sys.S()->energy;
+        const int sp_old = sys.S()->num_stacked_pairs;
         W()->delta_e += rg_unassign_and_save_domains();
         W()->delta_e += rg_recoil_regrow();
         if (M()->rejected) return false;
         // excluded staples: the reference hard-codes zero of them (simulation.cpp:410,527)
         update_move_params();
         W()->delta_e += calc_move_bias();
+        const double e_new = sys.S()->energy;
+        const int sp_new = sys.S()->num_stacked_pairs;
+#ifndef LDO_NO_WEIGHT_PASS // A/B knob (profiles/ab_r2.txt): evaluate the potential in the weight passes like the reference
+        sys.S()->weight_pass = 1;
+#endif
 
         // new-configuration weights (setup_for_calc_new_weights, rg:147-153)
         rg_copy_queues_to_wq();
@@ -2522,12 +2538,16 @@ struct Engine {
 
         // test_rg_acceptance (rg:515-533)
         double ratio = W()->weight_new / W()->weight * exp(-W()->delta_e);
-        if (test_acceptance(ratio)) {
+        bool accepted = test_acceptance(ratio);
+        if (accepted) {
 #pragma unroll 1
             for (int k = 0; k < M()->n_regrow; k++) C()->prev[M()->regrow[k]] = C()->newc[M()->regrow[k]];
             reset_origami();
-            return true;
         }
+        sys.S()->weight_pass = 0;
+        sys.S()->energy = accepted ? e_new : e_old;
+        sys.S()->num_stacked_pairs = accepted ? sp_new : sp_old;
+        if (accepted) return true;
         M()->n_modified = 0;
         M()->n_assigned = 0;
         return false;
