@@ -884,6 +884,42 @@ ldo_sim* ldo_sim_create(const char* inp_path, int n_replicas, int device, int ra
             ore.insert(ore.end(), c.orientations.begin(), c.orientations.end());
         }
         s->check(ldo_set_state(s->eng, -1, static_cast<int>(chains.size()), ci.data(), cid.data(), cl.data(), pos.data(), ore.data()));
+        if (s->is_pt && p.m_restart_from_config) {
+            // PTGCMCSimulation constructor (ptmc_simulation.cpp:38-46): replica `rank` restarts from frame restart_step of
+            // restart_traj_filebase-<rank><restart_traj_postfix>; every ladder of the batch starts from the same files
+            int slots_per_rank {s->num_reps / s->n_ranks};
+            for (int b {0}; b != slots_per_rank; b++) {
+                int k {ladder_slot_of(*s, b)};
+                Chains rc {read_trj_config(p.m_restart_traj_filebase + "-" + std::to_string(k) + p.m_restart_traj_postfix, p.m_restart_step)};
+                std::vector<int> rci, rcid, rcl, rpos, rore;
+                for (auto const& c: rc) {
+                    rci.push_back(c.index);
+                    rcid.push_back(c.identity);
+                    rcl.push_back(static_cast<int>(c.positions.size() / 3));
+                    rpos.insert(rpos.end(), c.positions.begin(), c.positions.end());
+                    rore.insert(rore.end(), c.orientations.begin(), c.orientations.end());
+                }
+                for (int l {0}; l != s->n_ladders; l++) {
+                    s->check(ldo_set_state(s->eng, l * slots_per_rank + b, static_cast<int>(rc.size()), rci.data(), rcid.data(), rcl.data(),
+                                           rpos.data(), rore.data()));
+                }
+            }
+        }
+        if (s->is_pt && p.m_restart_from_swap) {
+            // m_q_to_repi from the last row of restart_swap_file (ptmc_simulation.cpp:61-83). The replicas themselves
+            // start with the control variables of their RANK, as in the reference (initialize_control_qs does not look
+            // at the restored map); the first exchange puts them where the map says.
+            std::ifstream swp {p.m_restart_swap_file};
+            if (!swp) throw FileError {"Restart swap file " + p.m_restart_swap_file + " does not exist"};
+            std::string line, last;
+            while (std::getline(swp, line)) last = line;
+            std::istringstream ls {last};
+            for (int k {0}; k != s->num_reps; k++) {
+                int repi {0};
+                ls >> repi;
+                for (int l {0}; l != s->n_ladders; l++) s->q2r[static_cast<size_t>(l) * s->num_reps + k] = repi;
+            }
+        }
         std::vector<int> status(n_replicas), detail(n_replicas);
         s->check(ldo_get_status(s->eng, status.data(), detail.data()));
         if (status[0] != 0) {

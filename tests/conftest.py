@@ -144,3 +144,42 @@ def has_cuda():
         return torch.cuda.is_available()
     except Exception:
         return False
+
+
+def live_replay(oracle, tmp_path, lib, opts, seed, steps, chunks=4, replicas=1, name="live"):
+    """Record `steps` moves of the live oracle (unmodified reference) in `chunks` tapes and replay them through the
+    engine: lattice state bit-exact and energy to 1e-12 after every chunk, move statistics at the end.
+    Returns (reference system, simulation)."""
+    from latticednaorigami_b200.binding import Simulation
+    r = oracle.RefSystem(opts)
+    r.seed(seed)
+    sim = Simulation(write_inp(str(tmp_path / f"{name}{seed}.inp"), opts), replicas, 0, lib=lib)
+    scale = 1.0
+    for k in range(chunks):
+        r.tape(clear=True)
+        r.simulate(steps // chunks)
+        tape = r.tape(clear=True)
+        for rep in range(replicas):
+            sim.engine.attach_tape(rep, tape)
+        sim.engine.run(steps // chunks)
+        sim.engine.assert_ok()
+        want = r.state()
+        e = r.energy()
+        got_e = sim.engine.energies()
+        for rep in range(replicas):
+            assert sim.engine.tape_position(rep) == len(tape), f"{name} chunk {k}: tape not fully consumed"
+            assert_state_equal(sim.engine.state(rep), want, f"{name} seed {seed} chunk {k}")
+            # 1e-12 relative to the terms the RUNNING sum has been made of since it was last rebuilt (no constraint
+            # check in these runs): the energy is enthalpy / T minus entropy, each of which can be orders of magnitude
+            # larger than their difference, and both codes carry the rounding of everything added and removed so far
+            sp = r.energy_split()
+            scale = max(scale, abs(e), abs(sp["enthalpy"]), abs(sp["entropy"]))
+            assert abs(got_e[rep, 0] - e) <= 1e-12 * scale, (name, k, got_e[rep, 0], e, scale)
+        c = r.counters()
+        assert [int(x) for x in sim.engine.counters()[0]] == [c[k2] for k2 in ("staples", "domains", "bound_pairs", "fully_bound_pairs",
+                                                                              "self_bound_pairs", "misbound_pairs", "stacked_pairs",
+                                                                              "unassigned", "current_c_i")]
+    att, acc = sim.engine.move_stats()
+    ra, rb = r.move_stats()
+    assert list(att[0]) == list(ra) and list(acc[0]) == list(rb)
+    return r, sim

@@ -30,14 +30,22 @@ CASES = {
 }
 
 
-def exchange_against_oracle(oracle, tmp_path, lib, case, system="snodin_unbound.json", swaps=12, interval=150, seed0=900):
+def exchange_against_oracle(oracle, tmp_path, lib, case, system="snodin_unbound.json", swaps=12, interval=150, seed0=900, restart=False):
     extra = dict(CASES[case])
     n = extra.pop("num_reps", 3)
+    if restart:
+        # a first run of the reference writes per-replica trajectories and the swap file; the compared run restarts from
+        # the configurations of its 4th frame and from the last row of its .swp (ptmc_simulation.cpp:38-83)
+        first = make_options(system, num_reps=n, swaps=6, exchange_interval=interval, max_pt_dur=1e9, configs_output_freq=interval,
+                             restart_from_swap=False, output_filebase=str(tmp_path / "first"), **extra)
+        oracle.pt_run(first, n, [seed0 + 5 + r for r in range(n)], record_tapes=False, workdir=str(tmp_path))
+        extra.update(restart_from_config=True, restart_traj_filebase=str(tmp_path / "first"), restart_traj_postfix=".trj", restart_step=3,
+                     restart_swap_file=str(tmp_path / "first.swp"))
     opts = make_options(system, num_reps=n, swaps=swaps, exchange_interval=interval, max_pt_dur=1e9, configs_output_freq=interval,
-                        restart_from_swap=False, **extra)
+                        restart_from_swap=restart, **extra)
     ref_opts = dict(opts, output_filebase=str(tmp_path / f"ref_{case}"))
     ref = oracle.pt_run(ref_opts, n, [seed0 + 17 * r for r in range(n)], workdir=str(tmp_path))
-    assert len(ref["swp"]) == swaps + 1 and ref["swp"][0] == list(range(n))
+    assert len(ref["swp"]) == swaps + 1 and (restart or ref["swp"][0] == list(range(n)))
     assert len(ref["marks"]) == swaps
 
     ours = dict(opts, random_seed=1, output_filebase="")

@@ -7,7 +7,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import GOLDEN, make_options, options_from_fixture, replay_fixture_through, write_inp, assert_state_equal
+from conftest import GOLDEN, make_options, options_from_fixture, replay_fixture_through, write_inp, assert_state_equal, live_replay
 from latticednaorigami_b200.binding import Simulation
 
 
@@ -68,7 +68,7 @@ def test_tape_mismatch_is_detected(hostsim_lib, tmp_path):
     assert st[0] == 2
 
 
-def test_distance_order_params_and_biases(hostsim_lib, oracle, tmp_path):
+def distance_order_params_and_biases(lib, oracle, tmp_path):
     """Dist / AdjacentSite / Sum order parameters of the move-update kind with well biases on them
     (order_params.cpp:34-161, bias_functions.cpp:114-222): replay against the live oracle; the biases enter every
     acceptance test, so the lattice state stays bit-exact only if they match, and the order-parameter values
@@ -80,7 +80,7 @@ def test_distance_order_params_and_biases(hostsim_lib, oracle, tmp_path):
         opts["order_parameter_file"] = os.path.join(GOLDEN, "inputs", "ops_dist.json")
         r = oracle.RefSystem(opts)
         r.seed(seed)
-        sim = Simulation(write_inp(str(tmp_path / f"d{seed}.inp"), opts), 1, 0, lib=hostsim_lib)
+        sim = Simulation(write_inp(str(tmp_path / f"d{seed}.inp"), opts), 1, 0, lib=lib)
         for k in range(24):
             r.tape(clear=True)
             r.simulate(25)
@@ -96,3 +96,62 @@ def test_distance_order_params_and_biases(hostsim_lib, oracle, tmp_path):
             assert abs(sim.engine.energies()[0, 4] - r.total_bias()) < 1e-12
             seen.add((int(got[2]), int(got[3]), int(got[4]), round(r.total_bias(), 6)))
     assert len(seen) > 8  # the distances and the biases actually move
+
+
+def test_distance_order_params_and_biases(hostsim_lib, oracle, tmp_path):
+    distance_order_params_and_biases(hostsim_lib, oracle, tmp_path)
+
+
+@pytest.mark.gpu
+def test_distance_order_params_and_biases_gpu(oracle, tmp_path):
+    """GPU twin (row a24): the same live-oracle comparison through the CUDA library."""
+    distance_order_params_and_biases(None, oracle, tmp_path)
+
+
+# ---- potential options no shipped input uses: Disallowed misbinding, the mean-field correction -----------------
+
+def disallowed_misbinding(lib, oracle, tmp_path):
+    """misbinding_pot=Disallowed (DisallowedMisbindingPotential, origami_potential.cpp:947-950): every misbound
+    placement violates; replayed against the live oracle from both snodin starts."""
+    for system, temp, seed, steps in [("snodin_unbound.json", 337, 61, 1200), ("snodin_assembled.json", 339, 62, 400)]:
+        r, sim = live_replay(oracle, tmp_path, lib, make_options(system, temp=temp, misbinding_pot="Disallowed"), seed, steps, name="dis")
+        assert r.counters()["misbound_pairs"] == 0
+    # the option matters: with Opposing the same seed misbinds along the way
+    r = oracle.RefSystem(make_options("snodin_unbound.json", temp=337))
+    r.seed(61)
+    seen = 0
+    for _ in range(12):
+        r.simulate(100)
+        seen = max(seen, r.counters()["misbound_pairs"])
+    assert seen > 0
+
+
+def mean_field_correction(lib, oracle, tmp_path):
+    """apply_mean_field_cor=true (origami_system.cpp:387-400, 858-868; origami_potential.cpp:1060-1100): the log 6 terms of
+    chain insertion and of the first two fully bound pairs enter energies and acceptance ratios."""
+    for system, temp, seed, steps in [("snodin_unbound.json", 336, 71, 1600), ("four_unbound.json", 338, 72, 2400)]:
+        kw = dict(temp=temp, apply_mean_field_cor=True)
+        if system == "four_unbound.json":
+            opts = make_options(system, "moveset_four.json", max_total_staples=2, max_type_staples=2, **kw)
+        else:
+            opts = make_options(system, **kw)
+        r, sim = live_replay(oracle, tmp_path, lib, opts, seed, steps, chunks=8, name="mf")
+        split = r.energy_split()
+        e = sim.engine.energies()[0]
+        assert abs(e[1] - split["enthalpy"]) <= 1e-12 * max(1.0, abs(split["enthalpy"]))
+        assert abs(e[2] - split["entropy"]) <= 1e-12 * max(1.0, abs(split["entropy"]))
+    assert r.counters()["staples"] >= 1  # staples were inserted: the chain terms were exercised
+
+
+def test_disallowed_misbinding(hostsim_lib, oracle, tmp_path):
+    disallowed_misbinding(hostsim_lib, oracle, tmp_path)
+
+
+def test_mean_field_correction(hostsim_lib, oracle, tmp_path):
+    mean_field_correction(hostsim_lib, oracle, tmp_path)
+
+
+@pytest.mark.gpu
+def test_disallowed_misbinding_and_mean_field_gpu(oracle, tmp_path):
+    disallowed_misbinding(None, oracle, tmp_path)
+    mean_field_correction(None, oracle, tmp_path)

@@ -1,0 +1,113 @@
+"""Output / restart surface on an EVOLVING trajectory.
+
+* The host driver fed with the tape of a live run of the unmodified reference (outputs enabled) must write the same
+  .trj .vcf .states .ores .counts .staples .staplestates .ene .ops files byte for byte, and the same .moves
+  counters (files.cpp:519-793, simulation.cpp:641-646, 706-718).
+* restart_traj_file / restart_step (files.cpp:129-218, origami_system.cpp:1000-1003): a trajectory written by the
+  reference is read back by both codes, which then continue identically under a replayed tape.
+* Replica-exchange restart (ptmc_simulation.cpp:38-83): per-replica restart_traj_filebase-<rank><postfix> and the last
+  row of restart_swap_file.
+CPU: host emulation of the device sources; GPU: the CUDA library."""
+import numpy as np
+import pytest
+
+from conftest import assert_state_equal, make_options, write_inp
+from latticednaorigami_b200.binding import Simulation
+
+EXTS = [".trj", ".vsf", ".vcf", ".states", ".ores", ".counts", ".staples", ".staplestates", ".ene", ".ops"]
+OUT = dict(configs_output_freq=100, vtf_output_freq=100, counts_output_freq=100, order_params_output_freq=100, energies_output_freq=100,
+           ops_to_output="numstaples numfulldomains nummisdomains numstackedpairs")
+
+
+def evolving_outputs(lib, oracle, tmp_path, system="snodin_unbound.json", temp=337, steps=800, seed=21):
+    ref_opts = make_options(system, temp=temp, ct_steps=steps, output_filebase=str(tmp_path / "ref"), **OUT)
+    r = oracle.RefSystem(ref_opts, workdir=str(tmp_path))
+    r.seed(seed)
+    r.simulate(steps)
+    tape = r.tape()
+    final = r.state()
+    att, acc = r.move_stats()
+    r.close()  # closes the reference's output files
+    our_opts = make_options(system, temp=temp, ct_steps=steps, random_seed=1, output_filebase=str(tmp_path / "our"), **OUT)
+    sim = Simulation(write_inp(str(tmp_path / "our.inp"), our_opts), 1, 0, lib=lib)
+    sim.engine.attach_tape(0, tape)
+    sim.run()
+    sim.engine.assert_ok()
+    assert sim.engine.tape_position(0) == len(tape)
+    assert_state_equal(sim.engine.state(0), final)
+    for ext in EXTS:
+        ref, our = (tmp_path / ("ref" + ext)).read_text(), (tmp_path / ("our" + ext)).read_text()
+        assert ref, ext
+        if ext == ".ene":
+            # energies are running fp64 sums printed with 10 digits: equal to 1e-12 of their terms, not bitwise (the
+            # stacking column of an unstacked system is the rounding residue energy - (enthalpy - entropy) itself)
+            assert our.splitlines()[0] == ref.splitlines()[0]
+            a, b = np.loadtxt(tmp_path / "ref.ene", skiprows=1), np.loadtxt(tmp_path / "our.ene", skiprows=1)
+            assert a.shape == b.shape and np.array_equal(a[:, 0], b[:, 0])
+            assert np.all(np.abs(a - b) <= 1e-9 * np.maximum(1.0, np.abs(a).max(axis=1, keepdims=True)))
+            continue
+        assert our == ref, f"{ext} differs from the reference's file"
+    # the trajectory evolves: frames differ and staples come and go
+    frames = [f for f in (tmp_path / "our.trj").read_text().split("\n\n") if f.strip()]
+    assert len(frames) == steps // 100 and len({f.split("\n", 1)[1] for f in frames}) == len(frames)
+    counts = np.loadtxt(tmp_path / "our.counts")
+    assert len(set(counts[:, 1])) > 1
+    moves = (tmp_path / "our.moves").read_text()
+    for i, label in enumerate(sim.movetype_labels):
+        assert f"Movetype: {label}\n    Attempts: {att[i]}\n    Accepts: {acc[i]}\n" in moves
+
+
+def trj_restart(lib, oracle, tmp_path):
+    # a trajectory written by the reference ...
+    a_opts = make_options("snodin_unbound.json", temp=336, output_filebase=str(tmp_path / "a"), configs_output_freq=150)
+    a = oracle.RefSystem(a_opts, workdir=str(tmp_path))
+    a.seed(5)
+    a.simulate(600)
+    frame3 = a.state()  # the 4th frame (restart_step counts frames from 0)
+    a.close()
+    # ... is read back by the reference and by the host driver; both continue under the same tape
+    kw = dict(temp=338, restart_traj_file=str(tmp_path / "a.trj"), restart_step=3)
+    b = oracle.RefSystem(make_options("snodin_unbound.json", output_filebase=str(tmp_path / "b"), **kw), workdir=str(tmp_path))
+    assert_state_equal(b.state(), frame3, "reference restart")
+    sim = Simulation(write_inp(str(tmp_path / "r.inp"), make_options("snodin_unbound.json", random_seed=1, **kw)), 2, 0, lib=lib)
+    for rep in (0, 1):
+        assert_state_equal(sim.engine.state(rep), frame3, "restart")
+    e = b.energy()
+    assert abs(sim.engine.energies()[0, 0] - e) <= 1e-12 * max(1.0, abs(e))
+    b.seed(6)
+    b.simulate(300)
+    tape = b.tape()
+    for rep in (0, 1):
+        sim.engine.attach_tape(rep, tape)
+    sim.engine.run(300)
+    sim.engine.assert_ok()
+    for rep in (0, 1):
+        assert_state_equal(sim.engine.state(rep), b.state(), "continued")
+    # a missing frame is an error in both (files.cpp:203-206)
+    with pytest.raises(Exception):
+        Simulation(write_inp(str(tmp_path / "bad.inp"), make_options("snodin_unbound.json", restart_traj_file=str(tmp_path / "a.trj"),
+                                                                     restart_step=9)), 1, 0, lib=lib)
+
+
+def test_output_files_on_an_evolving_trajectory(hostsim_lib, oracle, tmp_path):
+    evolving_outputs(hostsim_lib, oracle, tmp_path)
+
+
+def test_trj_restart(hostsim_lib, oracle, tmp_path):
+    trj_restart(hostsim_lib, oracle, tmp_path)
+
+
+def test_replica_exchange_restart(hostsim_lib, oracle, tmp_path):
+    from test_exchange_oracle import exchange_against_oracle
+    exchange_against_oracle(oracle, tmp_path, hostsim_lib, "ut", swaps=8, restart=True)
+
+
+@pytest.mark.gpu
+def test_outputs_and_restart_gpu(oracle, tmp_path):
+    from test_exchange_oracle import exchange_against_oracle
+    (tmp_path / "o").mkdir()
+    (tmp_path / "r").mkdir()
+    (tmp_path / "p").mkdir()
+    evolving_outputs(None, oracle, tmp_path / "o")
+    trj_restart(None, oracle, tmp_path / "r")
+    exchange_against_oracle(oracle, tmp_path / "p", None, "ut", swaps=8, restart=True)
