@@ -439,10 +439,7 @@ void us_setup(ldo_sim& s) {
             for (int v: s.windows.maxs[w]) post += "-" + std::to_string(v);
             s.window_postfix.push_back(post);
         }
-        for (int r {0}; r != s.R; r++) {
-            int w {r % s.n_windows};
-            s.check(ldo_set_window(s.eng, r, wb, s.windows.mins[w][0], s.windows.maxs[w][0]));
-        }
+        // (the window limits themselves are applied by us_apply_window_limits once the starting configuration is set)
     }
     // empty grid (every point off-grid, bias 0) for every replica
     std::vector<double> vals(total, std::nan(""));
@@ -455,6 +452,18 @@ void us_setup(ldo_sim& s) {
         for (int r {0}; r != s.R; r++) s.q2r[r] = r % s.n_windows;
         s.attempts.assign(static_cast<size_t>(s.R / s.n_windows) * std::max(s.n_windows - 1, 1), 0);
         s.accepts = s.attempts;
+    }
+}
+
+// MWUSGCMCSimulation::setup_window_restraints (us_simulation.cpp:503-516) overrides min_op / max_op of the window
+// bias AFTER SystemBiases was constructed and evaluated (origami_system.cpp:69-70): the stored bias value is still the
+// one of the file's limits until the first move re-evaluates it, so that move sees the whole jump as its bias change.
+// Same order here: the configuration is loaded (biases evaluated with the file's limits) before the limits change.
+void us_apply_window_limits(ldo_sim& s) {
+    if (!s.is_mwus) return;
+    for (int r {0}; r != s.R; r++) {
+        int w {r % s.n_windows};
+        s.check(ldo_set_window(s.eng, r, s.window_biases[0], s.windows.mins[w][0], s.windows.maxs[w][0]));
     }
 }
 
@@ -561,8 +570,11 @@ void us_process_iteration(ldo_sim& s, int slot, int n, long long steps) {
     }
     us_upload_bias(s, slot);
     // output_summary (:436-452)
-    if (ws.us_stream) {
-        std::ostream& o = *ws.us_stream;
+    // the summary goes to the window's .out stream (MWUS, us_simulation.cpp:545-547) or to stdout (single window:
+    // m_us_stream stays &cout, us_simulation.hpp:77)
+    bool to_stdout {!ws.us_stream && !s.is_mwus && !std::getenv("LDO_QUIET")};
+    if (ws.us_stream || to_stdout) {
+        std::ostream& o = ws.us_stream ? static_cast<std::ostream&>(*ws.us_stream) : std::cout;
         o << "Iteration: " << n << "\n\nGridpoint w, P, E:\n";
         for (auto const& pt: ws.S_n) {
             for (int c: pt) o << c << " ";
@@ -589,8 +601,10 @@ void us_run(ldo_sim& s) {
     if (!p.m_output_filebase.empty()) {
         for (int slot {0}; slot != s.R; slot++) {
             s.filebase_postfix = "";
-            st[slot].us_stream.reset(new std::ofstream {replica_filebase(s, slot) + ".out"});
-            *st[slot].us_stream << "No biases read in\nStarting from configuration in system file\nStarting new iteration\n";
+            // The constructor messages ("No biases read in", ...) are written before MWUS redirects the stream
+            // (us_simulation.cpp:68-90 vs :545-547): they go to stdout, the .out file starts with the first summary
+            if (!std::getenv("LDO_QUIET")) std::cout << "No biases read in\nStarting from configuration in system file\nStarting new iteration\n";
+            if (s.is_mwus) st[slot].us_stream.reset(new std::ofstream {replica_filebase(s, slot) + ".out"});
         }
     }
     double saved_max_duration {s.params.m_max_duration};
@@ -645,7 +659,9 @@ void us_run(ldo_sim& s) {
         }
         else {
             simulate(s, p.m_iter_steps);
-            steps_done = s.step;
+            // run_simulation stores simulate()'s return value - the last step number plus one (simulation.cpp:574,652) -
+            // in m_steps, which update_grids divides the visit counts by (us_simulation.cpp:146-151, 418-422)
+            steps_done = s.step + 1;
         }
         // process_iteration
         for (int slot {0}; slot != s.R; slot++) {
@@ -925,6 +941,7 @@ ldo_sim* ldo_sim_create(const char* inp_path, int n_replicas, int device, int ra
         if (status[0] != 0) {
             throw OrigamiMisuse {"Constaints in violation after move complete (status " + std::to_string(status[0]) + ")"};
         }
+        if (s->is_us) us_apply_window_limits(*s);
 
         // seed (simulation.cpp:199-203; random_gens.cpp:12-19 when unspecified)
         unsigned long long seed;

@@ -363,12 +363,20 @@ def pt_run(options, n_ranks, seeds, record_tapes=True, workdir=None):
     # where every exchange round's draws start in exchange_reals
     out["exchange_offsets"] = np.concatenate([[0], np.cumsum(marks[:, 1] - marks[:, 0])]).astype(np.int64)
     swp = opts["output_filebase"] + ".swp"
-    rows = open(swp).read().splitlines()
-    out["swp_header"] = rows[0]
-    out["swp"] = [[int(x) for x in row.split()] for row in rows[1:]]
+    if os.path.exists(swp):
+        rows = open(swp).read().splitlines()
+        out["swp_header"] = rows[0]
+        out["swp"] = [[int(x) for x in row.split()] for row in rows[1:]]
     if tmp is not None:
         tmp.cleanup()
     return out
+
+
+def us_run(options, n_ranks, seeds, workdir):
+    """The reference's umbrella-sampling drivers (us_simulation.cpp): umbrella_sampling (one rank),
+    mw_umbrella_sampling / ptmw_umbrella_sampling (one rank = one thread per window). Output files (.biases per
+    iteration, ...) are left in `workdir` under options['output_filebase']; returns what pt_run returns."""
+    return pt_run(options, n_ranks, seeds, record_tapes=True, workdir=workdir)
 
 
 def pt_acceptance_p(ref, temps, umults, bmults, smults, dep1, dep2, staple_u1, staple_u2, staple_n1, staple_n2):

@@ -490,8 +490,10 @@ extern "C" int oref_pt_acceptance_p(
 
 #include <memory>
 #include <thread>
+#include <type_traits>
 
 #include "LatticeDNAOrigami/ptmc_simulation.hpp"
+#include "LatticeDNAOrigami/us_simulation.hpp"
 #include <boost/mpi/communicator.hpp>
 
 namespace {
@@ -541,6 +543,27 @@ void pt_rank_body(parser::InputParameters& params, origami::OrigamiSystem& origa
     }
 }
 
+// Umbrella-sampling drivers (us_simulation.cpp:75-91, 475-484, 647-660). The multi-window classes own an inner
+// SimpleUSGCMCSimulation with its own RandomGens (the one that drives the MC moves); the outer object's generator only
+// serves PTMWUS' exchange tests. Both are seeded per rank.
+template <class Sim>
+void us_rank_body(parser::InputParameters& params, origami::OrigamiSystem& origami, PtRank& rec, int seed, bool record) {
+    Sim sim {origami, origami.get_system_order_params(), origami.get_system_biases(), params};
+    sim.m_random_gens.set_seed(seed);
+    simulation::GCMCSimulation* mc {&sim};
+    if constexpr (std::is_base_of<us::MWUSGCMCSimulation, Sim>::value) {
+        sim.m_us_sim->m_random_gens.set_seed(seed + 1000003);
+        mc = sim.m_us_sim;
+    }
+    if (record) oracle_tape::g_record = &rec.tape;
+    sim.run();
+    oracle_tape::g_record = nullptr;
+    for (auto& mt: mc->m_movetypes) {
+        rec.attempts.push_back(mt->get_attempts());
+        rec.accepts.push_back(mt->get_accepts());
+    }
+}
+
 void pt_rank_main(const char* inp_path, int rank, int seed, bool record, PtRank* rec) {
     boost::mpi::shim_rank() = rank;
     try {
@@ -554,7 +577,10 @@ void pt_rank_main(const char* inp_path, int rank, int seed, bool record, PtRank*
         else if (st == "hut_parallel_tempering") pt_rank_body<ptmc::HUTPTGCMCSimulation>(params, *origami, *rec, seed, record);
         else if (st == "st_parallel_tempering") pt_rank_body<ptmc::STPTGCMCSimulation>(params, *origami, *rec, seed, record);
         else if (st == "2d_parallel_tempering") pt_rank_body<ptmc::TwoDPTGCMCSimulation>(params, *origami, *rec, seed, record);
-        else throw std::runtime_error {"oref_pt_run: not a parallel tempering simulation type"};
+        else if (st == "umbrella_sampling") us_rank_body<us::SimpleUSGCMCSimulation>(params, *origami, *rec, seed, record);
+        else if (st == "mw_umbrella_sampling") us_rank_body<us::MWUSGCMCSimulation>(params, *origami, *rec, seed, record);
+        else if (st == "ptmw_umbrella_sampling") us_rank_body<us::PTMWUSGCMCSimulation>(params, *origami, *rec, seed, record);
+        else throw std::runtime_error {"oref_pt_run: not a replica-exchange or umbrella-sampling simulation type"};
         auto& o = *origami;
         for (size_t i {0}; i != o.m_domains.size(); i++) {
             rec->chain_index.push_back(o.m_chain_indices[i]);
