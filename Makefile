@@ -20,10 +20,10 @@ $(OUT)/build/%.o: $(CSRC)/%.cpp $(HDRS)
 	$(HOSTCXX) $(CXXFLAGS) -c $< -o $@
 
 $(OUT)/libldo_b200.so: $(OUT)/build/ldo_engine.o $(OUT)/build/ldo_host.o $(OUT)/build/ldo_sim.o
-	$(NVCC) -shared -ccbin $(HOSTCXX) -o $@ $^ -lcudart
+	$(NVCC) -shared -ccbin $(HOSTCXX) -o $@ $^ -lcudart -ldl
 
 $(OUT)/latticeDNAOrigami_b200: $(CSRC)/ldo_main.cpp $(OUT)/libldo_b200.so
-	$(HOSTCXX) $(CXXFLAGS) -o $@ $< -L$(OUT) -lldo_b200 -Wl,-rpath,'$$ORIGIN'
+	$(HOSTCXX) $(CXXFLAGS) -o $@ $< -L$(OUT) -lldo_b200 -lpthread -Wl,-rpath,'$$ORIGIN'
 
 # Device-logic emulation on the host (one emulated lane per replica); test infrastructure only.
 hostsim: tests/hostsim/libldo_hostsim.so
@@ -36,7 +36,7 @@ tests/hostsim/libldo_hostsim.so: $(CSRC)/ldo_engine.cu $(HOST_SRCS) $(HDRS)
 variant:
 	mkdir -p ab
 	$(NVCC) $(NVFLAGS) $(DEFS) -c $(CSRC)/ldo_engine.cu -o ab/ldo_engine_$(NAME).o
-	$(NVCC) -shared -ccbin $(HOSTCXX) -o ab/lib_$(NAME).so ab/ldo_engine_$(NAME).o $(OUT)/build/ldo_host.o $(OUT)/build/ldo_sim.o -lcudart
+	$(NVCC) -shared -ccbin $(HOSTCXX) -o ab/lib_$(NAME).so ab/ldo_engine_$(NAME).o $(OUT)/build/ldo_host.o $(OUT)/build/ldo_sim.o -lcudart -ldl
 
 clean:
 	rm -rf $(OUT)/build $(OUT)/libldo_b200.so $(OUT)/latticeDNAOrigami_b200 tests/hostsim/libldo_hostsim.so

@@ -298,6 +298,18 @@ int ldo_exchange_pt(ldo_engine* e, int variant, long long swap_i, int n_ladders,
  * beyond a round's supply (taken as accepted) and the draws of finished rounds it left unused. */
 int ldo_set_exchange_tape(ldo_engine* e, const double* reals, long long n, const long long* round_offsets, long long n_rounds);
 int ldo_exchange_tape_status(ldo_engine* e, long long* missing, long long* unused);
+/* The same round without any host synchronisation, for drivers that keep the whole exchange on the engine's stream
+ * (ldo_sim_exchange_round, include/ldo_host.h): ldo_exchange_collect_async enqueues the collection of the exchange
+ * records into the send buffer of ldo_exchange_buffers; the caller enqueues its all-gather into the receive buffer on
+ * ldo_stream() (not needed when n_ranks == 1); ldo_exchange_pt_async enqueues the swap decisions on the
+ * DEVICE-RESIDENT slot -> replica map and counters (ldo_exchange_state_set uploads them once - n_slots = n_ladders *
+ * ladder_len, n_counters as ldo_exchange_pt / ldo_exchange_pt_2d size attempts / accepts - and
+ * ldo_exchange_state_get reads them back, synchronising) followed by the energy rebuild. v2_dim is used by LDO_PT_2D. */
+int ldo_exchange_collect_async(ldo_engine* e);
+int ldo_exchange_state_set(ldo_engine* e, int n_slots, int n_counters, const int* slot_to_replica, const long long* attempts,
+                           const long long* accepts);
+int ldo_exchange_state_get(ldo_engine* e, int n_slots, int n_counters, int* slot_to_replica, long long* attempts, long long* accepts);
+int ldo_exchange_pt_async(ldo_engine* e, int variant, int v2_dim, long long swap_i, int n_ladders, int ladder_len, int rank, int n_ranks);
 /* Reduced staple chemical potentials ln(staple_M) - (2 L - 1) ln 6 per staple type (m_reduced_staple_us,
  * origami_system.cpp:965-990) as the exchange uses them; returns the number of staple types. */
 int ldo_get_reduced_staple_u(ldo_engine* e, double* out);

@@ -35,11 +35,27 @@ ldo_sim* ldo_sim_create(const char* inp_path, int n_replicas, int device, int ra
 void ldo_sim_destroy(ldo_sim* s);
 ldo_engine* ldo_sim_engine(ldo_sim* s);
 
-/* Runs the driver selected by simulation_type (constant_temp, annealing, t_/ut_/hut_/st_parallel_tempering)
- * to completion, writing the reference's output files for every replica (`<filebase>-<replica>.*` when
- * there is more than one). Single-GPU only for the exchange types (the multi-GPU exchange is driven by the
- * caller through ldo_sim_exchange_round with its own all-gather). Returns 0 or -1. */
+/* Multi-GPU replica exchange (replaces: the Boost.MPI communicator PTGCMCSimulation owns,
+ * include/LatticeDNAOrigami/ptmc_simulation.hpp:45-49, and its slave_send / master_receive traffic,
+ * src/ptmc_simulation.cpp:163-253): one ldo_sim per GPU, one host thread (or process) per ldo_sim, one NCCL
+ * communicator across them. Rank 0 obtains a 128-byte unique id (ncclGetUniqueId) and hands it to every rank by
+ * whatever channel the caller has (threads of one process: memory; processes: a file, MPI, torch.distributed);
+ * every rank then calls ldo_sim_comm_init, which is collective. NCCL is bound at run time (libnccl.so.2) - a
+ * single-GPU run never touches it. */
+int ldo_comm_unique_id(void* id_out_128_bytes);
+int ldo_sim_comm_init(ldo_sim* s, const void* unique_id_128_bytes);
+
+/* Runs the driver selected by simulation_type (constant_temp, annealing, t_/ut_/hut_/st_/2d_parallel_tempering,
+ * umbrella_sampling, mw_/ptmw_umbrella_sampling) to completion, writing the reference's output files for every
+ * replica (`<filebase>-<replica>.*` when there is more than one). With n_ranks > 1 (exchange types, after
+ * ldo_sim_comm_init) every rank calls it; rank 0 writes the .swp file. Returns 0 or -1. */
 int ldo_sim_run(ldo_sim* s);
+
+/* One whole replica-exchange round (ptmc_simulation.cpp:113-141) enqueued on the engine's stream without a host
+ * synchronisation: exchange_interval moves, collection of the exchange records, ncclAllGather over the ranks (when
+ * n_ranks > 1), swap decisions on the device-resident map, energy rebuild. The host waits only when an output file is
+ * due. Returns 0, 1 when max_duration was hit, -1 on error. ldo_sim_exchange_state reads the map back. */
+int ldo_sim_exchange_round(ldo_sim* s, long long swap_i);
 
 /* One replica-exchange round (ptmc_simulation.cpp:113-141): `exchange_interval` MC steps on every local
  * replica, then collection of the dependent quantities. After the caller has all-gathered them (or when

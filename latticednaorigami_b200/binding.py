@@ -19,10 +19,10 @@ ENGINE_SYMBOLS = [
     "ldo_get_energies", "ldo_get_counters", "ldo_get_staple_counts", "ldo_get_order_params",
     "ldo_get_move_stats", "ldo_get_run_timing", "ldo_recompute_energies", "ldo_check_all_constraints", "ldo_center",
     "ldo_set_exchange_ladder", "ldo_exchange_collect", "ldo_exchange_pt", "ldo_exchange_pt_2d", "ldo_exchange_acceptance_p", "ldo_get_reduced_staple_u", "ldo_set_step", "ldo_exchange_buffers",
-    "ldo_exchange_windows", "ldo_set_exchange_tape", "ldo_exchange_tape_status", "ldo_set_reference_draw_order", "ldo_build_info", "ldo_launch_count", "ldo_state_bytes", "ldo_checkpoint_size", "ldo_checkpoint_save", "ldo_checkpoint_load",
+    "ldo_exchange_windows", "ldo_exchange_collect_async", "ldo_exchange_state_set", "ldo_exchange_state_get", "ldo_exchange_pt_async", "ldo_set_exchange_tape", "ldo_exchange_tape_status", "ldo_set_reference_draw_order", "ldo_build_info", "ldo_launch_count", "ldo_state_bytes", "ldo_checkpoint_size", "ldo_checkpoint_save", "ldo_checkpoint_load",
 ]
 HOST_SYMBOLS = [
-    "ldo_host_last_error", "ldo_sim_create", "ldo_sim_destroy", "ldo_sim_engine", "ldo_sim_run",
+    "ldo_host_last_error", "ldo_comm_unique_id", "ldo_sim_comm_init", "ldo_sim_exchange_round", "ldo_sim_create", "ldo_sim_destroy", "ldo_sim_engine", "ldo_sim_run",
     "ldo_sim_exchange_advance", "ldo_sim_exchange_apply", "ldo_sim_exchange_state", "ldo_sim_num_temps",
     "ldo_sim_num_order_params", "ldo_sim_order_param_tag", "ldo_sim_num_movetypes",
     "ldo_sim_movetype_label", "ldo_sim_num_staple_types", "ldo_sim_step", "ldo_sim_pair_energies",
@@ -114,6 +114,10 @@ def bind(L):
         "ldo_exchange_buffers": (i, [vp, i, vp, vp, vp]),
         "ldo_exchange_windows": (i, [vp, ll, i, i, i, i, vp, vp, vp, vp]),
         "ldo_set_reference_draw_order": (i, [vp, i]),
+        "ldo_exchange_collect_async": (i, [vp]),
+        "ldo_exchange_state_set": (i, [vp, i, i, vp, vp, vp]),
+        "ldo_exchange_state_get": (i, [vp, i, i, vp, vp, vp]),
+        "ldo_exchange_pt_async": (i, [vp, i, i, ll, i, i, i, i]),
         "ldo_set_exchange_tape": (i, [vp, vp, ll, vp, ll]),
         "ldo_exchange_tape_status": (i, [vp, vp, vp]),
         "ldo_build_info": (C.c_char_p, []),
@@ -128,6 +132,9 @@ def bind(L):
         "ldo_sim_engine": (vp, [vp]),
         "ldo_sim_run": (i, [vp]),
         "ldo_sim_exchange_advance": (i, [vp]),
+        "ldo_sim_exchange_round": (i, [vp, ll]),
+        "ldo_comm_unique_id": (i, [vp]),
+        "ldo_sim_comm_init": (i, [vp, vp]),
         "ldo_sim_exchange_apply": (i, [vp, ll, vp]),
         "ldo_sim_exchange_state": (i, [vp, vp, vp, vp]),
         "ldo_sim_num_temps": (i, [vp]),
@@ -411,6 +418,14 @@ class Simulation:
     def step(self):
         return self.L.ldo_sim_step(self.h)
 
+    def exchange_round(self, swap_i):
+        """One whole exchange round on the engine's stream (moves, collection, NCCL all-gather, decisions)."""
+        return self._check(self.L.ldo_sim_exchange_round(self.h, int(swap_i)))
+
+    def comm_init(self, unique_id):
+        buf = C.create_string_buffer(bytes(unique_id), 128)
+        self._check(self.L.ldo_sim_comm_init(self.h, buf))
+
     def exchange_advance(self):
         return self._check(self.L.ldo_sim_exchange_advance(self.h))
 
@@ -438,6 +453,15 @@ class Simulation:
         out = np.zeros(3)
         self.L.ldo_sim_init_energies(self.h, temp_idx, _ptr(out))
         return out
+
+
+def comm_unique_id(lib_path=None, lib=None):
+    """128-byte NCCL unique id (rank 0 creates it; every rank passes it to Simulation.comm_init)."""
+    L = lib if lib is not None else load(lib_path)
+    buf = C.create_string_buffer(128)
+    if L.ldo_comm_unique_id(buf) != 0:
+        raise LdoError(L.ldo_host_last_error().decode())
+    return buf.raw
 
 
 # ---- GPU-free host helpers (table builder, parameter-file reader) ---------------------------------

@@ -54,7 +54,7 @@ static const char* dev_err() { return "hostsim"; }
 #include <cuda_runtime.h>
 #define LDO_GLOBAL __global__
 typedef cudaStream_t dev_stream_t;
-static cudaError_t g_last_cuda = cudaSuccess;
+static thread_local cudaError_t g_last_cuda = cudaSuccess;
 static int chk(cudaError_t e) {
     if (e != cudaSuccess) {
         g_last_cuda = e;
@@ -1073,10 +1073,14 @@ typedef Caps<80, 26, 7, 16, true, 48, 40, 40> CapsSmall; // snodin-class systems
 #endif
 typedef Caps<512, 176, 11, 96, false, 511, 512, 1026> CapsLarge; // large scaffolds: in place in HBM/L2
 
-static std::string g_create_error;
-static const void* g_const_owner = nullptr; // engine whose descriptions are in constant memory
-static long long g_const_version = -1;
-static long long g_const_counter = 0;
+static thread_local std::string g_create_error;
+// Constant memory is per device: the engine whose descriptions currently sit in each device's copy. One host thread
+// drives one engine / GPU (ldo_b200.h), so entries of different devices are touched by different threads.
+#define LDO_MAX_DEVICES 64
+static const void* g_const_owner[LDO_MAX_DEVICES] = {nullptr};
+static long long g_const_version[LDO_MAX_DEVICES] = {0};
+#include <atomic>
+static std::atomic<long long> g_const_counter {0};
 
 struct EngineBase {
     virtual ~EngineBase() {}
@@ -1105,6 +1109,9 @@ struct EngineBase {
     virtual int get_visits(int replica, int bias, long long* counts, int clear) = 0;
     virtual int attach_tape(int replica, const ldo_tape_draw* draws, long long n) = 0;
     virtual int exchange(ExchangeArgs& x, const double* dependent_host, int* slot_to_replica, long long* attempts, long long* accepts) = 0;
+    virtual int exchange_state_set(int n_slots, int n_counters, const int* q2r, const long long* att, const long long* acc) = 0;
+    virtual int exchange_state_get(int n_slots, int n_counters, int* q2r, long long* att, long long* acc) = 0;
+    virtual int exchange_resident(ExchangeArgs& x) = 0;
     virtual int exchange_buffers(int n_global, void** send, void** recv, int* nq) = 0;
     virtual int window_exchange(WindowExchangeArgs& x, int* window_to_replica, long long* attempts, long long* accepts) = 0;
     virtual int alloc_outputs() = 0;
@@ -1195,7 +1202,7 @@ struct EngineImpl: EngineBase {
         dev_free(d_exch_tape_state);
         dev_free(d_exch_tape_offsets);
         for (void* p: tape_bufs) dev_free(p);
-        if (g_const_owner == this) g_const_owner = nullptr;
+        if (g_const_owner[device % LDO_MAX_DEVICES] == this) g_const_owner[device % LDO_MAX_DEVICES] = nullptr;
 #ifndef LDO_HOSTSIM
         cudaStreamDestroy(stream);
 #endif
@@ -1357,14 +1364,15 @@ struct EngineImpl: EngineBase {
     // every engine of the process: re-upload when another engine (or a new description) owns it.
     int upload_constants() {
 #ifndef LDO_HOSTSIM
-        if (g_const_owner == this && g_const_version == const_version) return 0;
+        int dslot = device % LDO_MAX_DEVICES;
+        if (g_const_owner[dslot] == this && g_const_version[dslot] == const_version) return 0;
         if (chk(cudaDeviceSynchronize())) return fail(dev_err());
         if (chk(cudaMemcpyToSymbol(ldo_c_sc, &shared.sc, sizeof(SysConst)))) return fail(dev_err());
         if (chk(cudaMemcpyToSymbol(ldo_c_ms, &shared.ms, sizeof(MoveSet)))) return fail(dev_err());
         if (chk(cudaMemcpyToSymbol(ldo_c_ob, &shared.ob, sizeof(OpsBiasConst)))) return fail(dev_err());
         if (chk(cudaDeviceSynchronize())) return fail(dev_err());
-        g_const_owner = this;
-        g_const_version = const_version;
+        g_const_owner[dslot] = this;
+        g_const_version[dslot] = const_version;
 #endif
         return 0;
     }
@@ -1655,6 +1663,9 @@ struct EngineImpl: EngineBase {
             if (dev_malloc((void**)&d_slot_tidx, sizeof(int) * n_slots)) return fail(dev_err());
             if (dev_malloc((void**)&d_slot_vals, sizeof(double) * 4 * n_slots)) return fail(dev_err());
             exch_cap = n_slots;
+            slot_cache.clear();
+            slot_tidx_cache.clear();
+            exch_resident_slots = 0;
         }
         if (!d_red_u) {
             int nst = shared.sc.n_types - 1;
@@ -1728,34 +1739,60 @@ struct EngineImpl: EngineBase {
         return 0;
     }
 
-    // slot control variables are passed through x.slot_* as HOST arrays by the caller
-    int exchange(ExchangeArgs& x, const double* dependent_host, int* slot_to_replica, long long* attempts, long long* accepts) override {
+    // Slot control variables (x.slot_* are HOST arrays of the caller): uploaded when they change
+    std::vector<double> slot_cache;
+    std::vector<int> slot_tidx_cache;
+    int upload_slots(const ExchangeArgs& x) {
+        int L = x.ladder_len;
+        std::vector<double> sv(4 * (size_t)L);
+        memcpy(&sv[0], x.slot_temp, sizeof(double) * L);
+        memcpy(&sv[L], x.slot_staple_u_mult, sizeof(double) * L);
+        memcpy(&sv[2 * L], x.slot_bias_mult, sizeof(double) * L);
+        memcpy(&sv[3 * L], x.slot_stacking_mult, sizeof(double) * L);
+        std::vector<int> ti(x.slot_temp_idx, x.slot_temp_idx + L);
+        if (sv == slot_cache && ti == slot_tidx_cache) return 0;
+        if (dev_h2d(d_slot_tidx, ti.data(), sizeof(int) * L, stream)) return fail(dev_err());
+        if (dev_h2d(d_slot_vals, sv.data(), sizeof(double) * 4 * L, stream)) return fail(dev_err());
+        slot_cache = sv;
+        slot_tidx_cache = ti;
+        return 0;
+    }
+    // The exchange kernel on the device-resident map / counters and the gathered records already in d_dep_all
+    // (or, single GPU, the local ones); nothing is copied to the host and nothing synchronises
+    int exchange_resident(ExchangeArgs& x) override {
         int n_slots = x.n_ladders * x.ladder_len;
-        int n_pairs = x.variant == LDO_PT_2D ? 2 * n_slots : x.n_ladders * (x.ladder_len - 1);
-        int nq = LDO_DEP_FIXED + x.n_staple_types;
         if (ensure_exchange(x.n_global, 2 * n_slots)) return -1;
-        if (dependent_host) {
-            if (dev_h2d(d_dep_all, dependent_host, sizeof(double) * nq * x.n_global, stream)) return fail(dev_err());
-        }
-        else if (x.n_global == R) {
-            // single-GPU: the local dependent quantities are the global ones
+        if (exch_resident_slots != n_slots) return fail("ldo_exchange_state_set not called for this ladder shape");
+        if (x.n_global == R) {
+            int nq = LDO_DEP_FIXED + x.n_staple_types;
 #ifdef LDO_HOSTSIM
             memcpy(d_dep_all, d_dependent, sizeof(double) * nq * R);
 #else
             if (chk(cudaMemcpyAsync(d_dep_all, d_dependent, sizeof(double) * nq * R, cudaMemcpyDeviceToDevice, stream))) return fail(dev_err());
 #endif
         }
-        if (dev_h2d(d_q2r, slot_to_replica, sizeof(int) * n_slots, stream)) return fail(dev_err());
-        if (dev_h2d(d_att, attempts, sizeof(long long) * n_pairs, stream)) return fail(dev_err());
-        if (dev_h2d(d_acc, accepts, sizeof(long long) * n_pairs, stream)) return fail(dev_err());
+        if (upload_slots(x)) return -1;
+        return exchange_launch(x);
+    }
+    int exch_resident_slots = 0;
+    int exchange_state_set(int n_slots, int n_counters, const int* q2r, const long long* att, const long long* acc) override {
+        if (ensure_exchange(1, 2 * n_slots)) return -1;
+        if (n_counters > 2 * n_slots) return fail("too many exchange counters");
+        if (dev_h2d(d_q2r, q2r, sizeof(int) * n_slots, stream)) return fail(dev_err());
+        if (dev_h2d(d_att, att, sizeof(long long) * n_counters, stream)) return fail(dev_err());
+        if (dev_h2d(d_acc, acc, sizeof(long long) * n_counters, stream)) return fail(dev_err());
+        exch_resident_slots = n_slots;
+        return 0;
+    }
+    int exchange_state_get(int n_slots, int n_counters, int* q2r, long long* att, long long* acc) override {
+        if (exch_resident_slots != n_slots) return fail("no resident exchange state of this shape");
+        if (q2r && dev_d2h(q2r, d_q2r, sizeof(int) * n_slots, stream)) return fail(dev_err());
+        if (att && dev_d2h(att, d_att, sizeof(long long) * n_counters, stream)) return fail(dev_err());
+        if (acc && dev_d2h(acc, d_acc, sizeof(long long) * n_counters, stream)) return fail(dev_err());
+        return 0;
+    }
+    int exchange_launch(ExchangeArgs& x) {
         int L = x.ladder_len;
-        if (dev_h2d(d_slot_tidx, x.slot_temp_idx, sizeof(int) * L, stream)) return fail(dev_err());
-        std::vector<double> sv(4 * (size_t)L);
-        memcpy(&sv[0], x.slot_temp, sizeof(double) * L);
-        memcpy(&sv[L], x.slot_staple_u_mult, sizeof(double) * L);
-        memcpy(&sv[2 * L], x.slot_bias_mult, sizeof(double) * L);
-        memcpy(&sv[3 * L], x.slot_stacking_mult, sizeof(double) * L);
-        if (dev_h2d(d_slot_vals, sv.data(), sizeof(double) * 4 * L, stream)) return fail(dev_err());
         ExchangeArgs dx = x;
         dx.dependent = d_dep_all;
         dx.slot_to_replica = d_q2r;
@@ -1781,10 +1818,28 @@ struct EngineImpl: EngineBase {
         if (chk(cudaGetLastError())) return fail(dev_err());
         launches++;
 #endif
-        if (dev_d2h(slot_to_replica, d_q2r, sizeof(int) * n_slots, stream)) return fail(dev_err());
-        if (dev_d2h(attempts, d_att, sizeof(long long) * n_pairs, stream)) return fail(dev_err());
-        if (dev_d2h(accepts, d_acc, sizeof(long long) * n_pairs, stream)) return fail(dev_err());
         return 0;
+    }
+    int exchange(ExchangeArgs& x, const double* dependent_host, int* slot_to_replica, long long* attempts, long long* accepts) override {
+        int n_slots = x.n_ladders * x.ladder_len;
+        int n_pairs = x.variant == LDO_PT_2D ? 2 * n_slots : x.n_ladders * (x.ladder_len - 1);
+        int nq = LDO_DEP_FIXED + x.n_staple_types;
+        if (ensure_exchange(x.n_global, 2 * n_slots)) return -1;
+        if (dependent_host) {
+            if (dev_h2d(d_dep_all, dependent_host, sizeof(double) * nq * x.n_global, stream)) return fail(dev_err());
+        }
+        else if (x.n_global == R) {
+            // single-GPU: the local dependent quantities are the global ones
+#ifdef LDO_HOSTSIM
+            memcpy(d_dep_all, d_dependent, sizeof(double) * nq * R);
+#else
+            if (chk(cudaMemcpyAsync(d_dep_all, d_dependent, sizeof(double) * nq * R, cudaMemcpyDeviceToDevice, stream))) return fail(dev_err());
+#endif
+        }
+        if (exchange_state_set(n_slots, n_pairs, slot_to_replica, attempts, accepts)) return -1;
+        if (upload_slots(x)) return -1;
+        if (exchange_launch(x)) return -1;
+        return exchange_state_get(n_slots, n_pairs, slot_to_replica, attempts, accepts);
     }
 };
 
@@ -2058,12 +2113,12 @@ int ldo_get_grid_visits(ldo_engine* e, int replica, int bias, long long* counts,
     return e->b->get_visits(replica, bias, counts, clear);
 }
 
-static int refresh_energy(ldo_engine* e) {
+static int refresh_energy(ldo_engine* e, bool sync = true) {
     OpArgs a;
     memset(&a, 0, sizeof(a));
     a.op = OP_UPDATE_ENERGY;
     a.only_replica = -1;
-    return e->b->exec(a, true);
+    return e->b->exec(a, sync);
 }
 
 int ldo_set_control(ldo_engine* e, int first, int count, const int* temp_idx, const double* staple_u_mult,
@@ -2313,6 +2368,16 @@ int ldo_center(ldo_engine* e, int centering_domain) {
     return e->b->exec(a, true);
 }
 
+int ldo_exchange_collect_async(ldo_engine* e) {
+    EngineBase* b = e->b;
+    OpArgs a;
+    memset(&a, 0, sizeof(a));
+    a.out_dependent = b->d_dependent;
+    a.op = OP_OBSERVE;
+    a.only_replica = -1;
+    return b->exec(a, false);
+}
+
 int ldo_exchange_collect(ldo_engine* e, double* dependent_local) {
     EngineBase* b = e->b;
     int nq = LDO_DEP_FIXED + (b->shared.sc.n_types - 1);
@@ -2368,17 +2433,14 @@ int ldo_exchange_pt_2d(ldo_engine* e, long long swap_i, int n_ladders, int v1_di
     return exchange_pt_impl(e, LDO_PT_2D, v2_dim, swap_i, n_ladders, v1_dim * v2_dim, rank, n_ranks, dependent, slot_to_replica, attempts, accepts);
 }
 
-static int exchange_pt_impl(ldo_engine* e, int variant, int v2_dim, long long swap_i, int n_ladders, int ladder_len, int rank,
-                            int n_ranks, const double* dependent, int* slot_to_replica, long long* attempts,
-                            long long* accepts) {
+static int exchange_fill_args(ldo_engine* e, ExchangeArgs& x, std::vector<double>& slot_temp, int variant, int v2_dim, long long swap_i,
+                              int n_ladders, int ladder_len, int rank, int n_ranks) {
     EngineBase* b = e->b;
     if ((int)b->ladder_temp_idx.size() != ladder_len) return b->fail("ldo_set_exchange_ladder not called for this ladder length");
     if (n_ranks < 1 || rank < 0 || rank >= n_ranks || ladder_len % n_ranks != 0) return b->fail("ladder_len must be a multiple of n_ranks");
     if (n_ladders * (ladder_len / n_ranks) != b->R) return b->fail("this rank must hold ladder_len / n_ranks slots of every ladder");
-    int n_global = n_ladders * ladder_len;
-    std::vector<double> slot_temp(ladder_len);
+    slot_temp.resize(ladder_len);
     for (int i = 0; i < ladder_len; i++) slot_temp[i] = b->temps[b->ladder_temp_idx[i]];
-    ExchangeArgs x;
     memset(&x, 0, sizeof(x));
     x.variant = variant;
     x.v2_dim = v2_dim;
@@ -2388,7 +2450,7 @@ static int exchange_pt_impl(ldo_engine* e, int variant, int v2_dim, long long sw
     x.rank = rank;
     x.n_ranks = n_ranks;
     x.n_local = b->R;
-    x.n_global = n_global;
+    x.n_global = n_ladders * ladder_len;
     x.n_staple_types = b->shared.sc.n_types - 1;
     x.seed = e->seed;
     x.slot_temp_idx = b->ladder_temp_idx.data();
@@ -2396,10 +2458,35 @@ static int exchange_pt_impl(ldo_engine* e, int variant, int v2_dim, long long sw
     x.slot_staple_u_mult = b->ladder_staple_u_mult.data();
     x.slot_bias_mult = b->ladder_bias_mult.data();
     x.slot_stacking_mult = b->ladder_stacking_mult.data();
-    if (b->exchange(x, dependent, slot_to_replica, attempts, accepts)) return -1;
+    return 0;
+}
+
+static int exchange_pt_impl(ldo_engine* e, int variant, int v2_dim, long long swap_i, int n_ladders, int ladder_len, int rank,
+                            int n_ranks, const double* dependent, int* slot_to_replica, long long* attempts,
+                            long long* accepts) {
+    ExchangeArgs x;
+    std::vector<double> slot_temp;
+    if (exchange_fill_args(e, x, slot_temp, variant, v2_dim, swap_i, n_ladders, ladder_len, rank, n_ranks)) return -1;
+    if (e->b->exchange(x, dependent, slot_to_replica, attempts, accepts)) return -1;
     // PTGCMCSimulation::run calls update_control_qs() at the top of every round, which always ends
     // in update_energy() (App. A19): rebuild the running energy with the (possibly new) tables
     return refresh_energy(e);
+}
+
+int ldo_exchange_state_set(ldo_engine* e, int n_slots, int n_counters, const int* slot_to_replica, const long long* attempts,
+                           const long long* accepts) {
+    return e->b->exchange_state_set(n_slots, n_counters, slot_to_replica, attempts, accepts);
+}
+int ldo_exchange_state_get(ldo_engine* e, int n_slots, int n_counters, int* slot_to_replica, long long* attempts, long long* accepts) {
+    return e->b->exchange_state_get(n_slots, n_counters, slot_to_replica, attempts, accepts);
+}
+int ldo_exchange_pt_async(ldo_engine* e, int variant, int v2_dim, long long swap_i, int n_ladders, int ladder_len, int rank, int n_ranks) {
+    if (variant < LDO_PT_T || variant > LDO_PT_2D) return e->b->fail("bad exchange variant");
+    ExchangeArgs x;
+    std::vector<double> slot_temp;
+    if (exchange_fill_args(e, x, slot_temp, variant, variant == LDO_PT_2D ? v2_dim : 0, swap_i, n_ladders, ladder_len, rank, n_ranks)) return -1;
+    if (e->b->exchange_resident(x)) return -1;
+    return refresh_energy(e, false);
 }
 
 int ldo_exchange_windows(ldo_engine* e, long long swap_i, int n_ladders, int n_windows, int grid_bias,

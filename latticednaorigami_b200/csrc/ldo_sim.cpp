@@ -11,12 +11,17 @@
 #include <iostream>
 #include <map>
 #include <memory>
+#include <mutex>
 #include <set>
 #include <random>
 #include <sstream>
 
 #include "../../include/ldo_host.h"
 #include "ldo_host.hpp"
+
+#ifndef LDO_HOSTSIM
+#include <dlfcn.h>
+#endif
 
 using namespace ldohost;
 
@@ -62,10 +67,13 @@ struct ldo_sim {
     std::vector<int> grid_lo, grid_n;
     WindowsFile windows;
     std::chrono::steady_clock::time_point start;
+    // multi-GPU replica exchange: NCCL communicator (one rank per GPU) and the engine's exchange buffers
+    void* nccl_comm {nullptr};
+    void *dep_send {nullptr}, *dep_recv {nullptr};
+    int dep_nq {0};
+    bool exchange_resident {false}; // slot -> replica map and counters currently live on the device
 
-    ~ldo_sim() {
-        if (eng) ldo_engine_destroy(eng);
-    }
+    ~ldo_sim();
     void check(int rc) {
         if (rc != 0) throw std::runtime_error(std::string("engine: ") + ldo_last_error(eng));
     }
@@ -675,6 +683,111 @@ void us_run(ldo_sim& s) {
 
 } // namespace
 
+// ---------------------------------------------------------------------------------------------
+// NCCL, bound at run time (only a multi-GPU run needs it: the single-GPU library has no NCCL dependency, and a
+// process that already carries a libnccl - PyTorch's - shares that one). Minimal declarations of nccl.h.
+// ---------------------------------------------------------------------------------------------
+namespace {
+struct NcclId {
+    char internal[128];
+};
+struct NcclApi {
+    void* lib {nullptr};
+    int (*GetUniqueId)(NcclId*) {nullptr};
+    int (*CommInitRank)(void**, int, NcclId, int) {nullptr};
+    int (*AllGather)(const void*, void*, size_t, int, void*, void*) {nullptr};
+    int (*CommDestroy)(void*) {nullptr};
+    const char* (*GetErrorString)(int) {nullptr};
+};
+const int NCCL_FLOAT64 {8};
+
+NcclApi& nccl() {
+    static NcclApi api;
+#ifndef LDO_HOSTSIM
+    static std::once_flag once;
+    std::call_once(once, [] {
+        for (const char* name: {"libnccl.so.2", "libnccl.so"}) {
+            api.lib = dlopen(name, RTLD_NOW | RTLD_GLOBAL);
+            if (api.lib) break;
+        }
+        if (!api.lib) return;
+        api.GetUniqueId = reinterpret_cast<int (*)(NcclId*)>(dlsym(api.lib, "ncclGetUniqueId"));
+        api.CommInitRank = reinterpret_cast<int (*)(void**, int, NcclId, int)>(dlsym(api.lib, "ncclCommInitRank"));
+        api.AllGather = reinterpret_cast<int (*)(const void*, void*, size_t, int, void*, void*)>(dlsym(api.lib, "ncclAllGather"));
+        api.CommDestroy = reinterpret_cast<int (*)(void*)>(dlsym(api.lib, "ncclCommDestroy"));
+        api.GetErrorString = reinterpret_cast<const char* (*)(int)>(dlsym(api.lib, "ncclGetErrorString"));
+    });
+#endif
+    return api;
+}
+
+void nccl_check(int rc, const char* what) {
+    if (rc == 0) return;
+    NcclApi& a = nccl();
+    throw std::runtime_error(std::string("NCCL ") + what + ": " + (a.GetErrorString ? a.GetErrorString(rc) : "error " + std::to_string(rc)));
+}
+
+NcclApi& nccl_or_throw() {
+    NcclApi& a = nccl();
+    if (!a.lib || !a.GetUniqueId || !a.CommInitRank || !a.AllGather) {
+        throw std::runtime_error("NCCL (libnccl.so.2) is not available: multi-GPU replica exchange needs it");
+    }
+    return a;
+}
+
+// One exchange round with nothing but stream-ordered work (ptmc_simulation.cpp:113-141): exchange_interval moves on every
+// local replica, collection of the exchange records, NCCL all-gather over the ranks, on-device swap decisions, energy
+// rebuild. The host only waits when an output file is due at the end of the interval.
+bool exchange_round(ldo_sim& s, long long swap_i) {
+    InputParameters const& p = s.params;
+    long long end {s.step + p.m_exchange_interval};
+    if (next_output_step(s, s.step, end) < end) {
+        // an output step falls inside the interval: the blocking path writes it where the reference does
+        if (!simulate(s, p.m_exchange_interval)) return false;
+    }
+    else {
+        s.check(ldo_run_async(s.eng, p.m_exchange_interval, p.m_centering_freq, p.m_centering_domain, p.m_constraint_check_freq));
+        s.step = end;
+        if (next_output_step(s, end - 1, end) == end && !s.files.empty()) {
+            std::vector<int> status(s.R), detail(s.R);
+            s.check(ldo_get_status(s.eng, status.data(), detail.data()));
+            for (int r {0}; r != s.R; r++) {
+                if (status[r] != 0) {
+                    throw OrigamiMisuse {"replica " + std::to_string(s.rank * s.R + r) + " stopped with status " + std::to_string(status[r]) +
+                                         " (detail " + std::to_string(detail[r]) + ")"};
+                }
+            }
+            write_outputs(s, s.step);
+        }
+    }
+    if (!s.exchange_resident) {
+        s.check(ldo_exchange_state_set(s.eng, static_cast<int>(s.q2r.size()), static_cast<int>(s.attempts.size()), s.q2r.data(),
+                                       s.attempts.data(), s.accepts.data()));
+        s.exchange_resident = true;
+    }
+    s.check(ldo_exchange_collect_async(s.eng));
+    if (s.n_ranks > 1) {
+        if (!s.nccl_comm) throw SimulationMisuse {"replica exchange on several ranks needs ldo_sim_comm_init (or the caller's own all-gather)"};
+        nccl_check(nccl().AllGather(s.dep_send, s.dep_recv, static_cast<size_t>(s.R) * s.dep_nq, NCCL_FLOAT64, s.nccl_comm, ldo_stream(s.eng)),
+                   "all-gather");
+    }
+    s.check(ldo_exchange_pt_async(s.eng, s.pt_variant, s.v2_dim, swap_i, s.n_ladders, s.num_reps, s.rank, s.n_ranks));
+    return true;
+}
+
+void exchange_download(ldo_sim& s) {
+    if (!s.exchange_resident) return;
+    s.check(ldo_exchange_state_get(s.eng, static_cast<int>(s.q2r.size()), static_cast<int>(s.attempts.size()), s.q2r.data(),
+                                   s.attempts.data(), s.accepts.data()));
+}
+
+} // namespace
+
+ldo_sim::~ldo_sim() {
+    if (nccl_comm && nccl().CommDestroy) nccl().CommDestroy(nccl_comm);
+    if (eng) ldo_engine_destroy(eng);
+}
+
 extern "C" {
 
 const char* ldo_host_last_error(void) { return g_host_error.c_str(); }
@@ -998,8 +1111,52 @@ int ldo_sim_exchange_advance(ldo_sim* s) {
     return 0;
 }
 
+int ldo_comm_unique_id(void* id_out) {
+    try {
+        NcclId id {};
+        nccl_check(nccl_or_throw().GetUniqueId(&id), "unique id");
+        std::memcpy(id_out, &id, sizeof(id));
+    } catch (std::exception const& e) {
+        g_host_error = e.what();
+        return -1;
+    }
+    return 0;
+}
+
+int ldo_sim_comm_init(ldo_sim* s, const void* unique_id) {
+    try {
+#ifdef LDO_HOSTSIM
+        (void)unique_id;
+        throw std::runtime_error("ldo_sim_comm_init: the NCCL path needs the CUDA build");
+#else
+        if (s->n_ranks < 2) return 0;
+        NcclId id {};
+        std::memcpy(&id, unique_id, sizeof(id));
+        nccl_check(nccl_or_throw().CommInitRank(&s->nccl_comm, s->n_ranks, id, s->rank), "communicator");
+        s->check(ldo_exchange_buffers(s->eng, s->R * s->n_ranks, &s->dep_send, &s->dep_recv, &s->dep_nq));
+#endif
+    } catch (std::exception const& e) {
+        g_host_error = e.what();
+        return -1;
+    }
+    return 0;
+}
+
+int ldo_sim_exchange_round(ldo_sim* s, long long swap_i) {
+    try {
+        if (!s->is_pt) throw SimulationMisuse {"not a replica-exchange simulation"};
+        if (!exchange_round(*s, swap_i)) return 1;
+    } catch (std::exception const& e) {
+        g_host_error = e.what();
+        return -1;
+    }
+    return 0;
+}
+
 int ldo_sim_exchange_apply(ldo_sim* s, long long swap_i, const double* dependent_all) {
     try {
+        exchange_download(*s);
+        s->exchange_resident = false;
         if (s->pt_variant == LDO_PT_2D) {
             s->check(ldo_exchange_pt_2d(
                     s->eng, swap_i, s->n_ladders, s->v1_dim, s->v2_dim, s->rank, s->n_ranks,
@@ -1018,6 +1175,12 @@ int ldo_sim_exchange_apply(ldo_sim* s, long long swap_i, const double* dependent
 }
 
 int ldo_sim_exchange_state(ldo_sim* s, int* slot_to_replica, long long* attempts, long long* accepts) {
+    try {
+        exchange_download(*s);
+    } catch (std::exception const& e) {
+        g_host_error = e.what();
+        return -1;
+    }
     if (slot_to_replica) std::memcpy(slot_to_replica, s->q2r.data(), sizeof(int) * s->q2r.size());
     if (attempts) std::memcpy(attempts, s->attempts.data(), sizeof(long long) * s->attempts.size());
     if (accepts) std::memcpy(accepts, s->accepts.data(), sizeof(long long) * s->accepts.size());
@@ -1050,10 +1213,11 @@ int ldo_sim_run(ldo_sim* s) {
             us_run(*s);
         }
         else if (s->is_pt) {
-            if (s->n_ranks != 1) throw SimulationMisuse {"ldo_sim_run drives single-GPU exchange only"};
-            // PTGCMCSimulation::run (ptmc_simulation.cpp:106-150); .swp as :92-104, :315-322
+            if (s->n_ranks != 1 && !s->nccl_comm) throw SimulationMisuse {"replica exchange on several ranks: call ldo_sim_comm_init first"};
+            // PTGCMCSimulation::run (ptmc_simulation.cpp:106-150); .swp as :92-104, :315-322 (written by rank 0)
+            bool master {s->rank == 0};
             std::ofstream swp;
-            if (!p.m_output_filebase.empty()) {
+            if (master && !p.m_output_filebase.empty()) {
                 swp.open(p.m_output_filebase + ".swp");
                 std::vector<double> cm {p.m_chem_pot_mults}, bmm {p.m_bias_mults}, smm {p.m_stacking_mults};
                 cm.resize(s->num_reps, 1.0);
@@ -1076,22 +1240,36 @@ int ldo_sim_run(ldo_sim* s) {
             auto write_swap_entry = [&](long long step) {
                 if (!swp.is_open() || p.m_configs_output_freq == 0) return;
                 if (step % p.m_configs_output_freq == 0) {
+                    exchange_download(*s); // the map lives on the device between the rows that are written
                     for (int k {0}; k != s->num_reps; k++) swp << s->q2r[k] << " ";
                     swp << "\n";
                 }
             };
             for (long long swap_i {1}; swap_i != p.m_swaps + 1; swap_i++) {
-                int rc {ldo_sim_exchange_advance(s)};
-                if (rc < 0) throw std::runtime_error(g_host_error);
+                // the round's moves, then the row of the map as it stood during them, then the exchange
+                // (ptmc_simulation.cpp:113-141); the decisions are only enqueued here, so the row is read first
+                InputParameters const& pp = s->params;
+                long long end {s->step + pp.m_exchange_interval};
                 double dt {std::chrono::duration<double>(std::chrono::steady_clock::now() - s->start).count()};
-                if (rc == 1 || dt > p.m_max_pt_dur) {
+                // (the wall-clock limit is a per-process decision: with several ranks it would need the master's kill
+                // message of ptmc_simulation.cpp:120-127; it is honoured on a single rank only)
+                if (s->n_ranks == 1 && dt > p.m_max_pt_dur) {
                     std::cout << "Maximum time allowed reached\n";
                     break;
                 }
-                write_swap_entry(s->step);
-                if (ldo_sim_exchange_apply(s, swap_i, nullptr) != 0) throw std::runtime_error(g_host_error);
+                if (master && p.m_configs_output_freq != 0 && end % p.m_configs_output_freq == 0) write_swap_entry(end);
+                if (!exchange_round(*s, swap_i)) {
+                    if (master) std::cout << "Maximum time allowed reached\n";
+                    break;
+                }
             }
+            s->check(ldo_synchronize(s->eng));
+            exchange_download(*s);
             write_swap_entry(s->step);
+            if (!master) {
+                write_move_summary(*s);
+                return 0;
+            }
             if (s->pt_variant == LDO_PT_2D) {
                 // TwoDPTGCMCSimulation::write_acceptance_freqs (ptmc_simulation.cpp:562-593), first ladder
                 int v1 {s->v1_dim}, v2 {s->v2_dim};

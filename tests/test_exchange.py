@@ -316,3 +316,45 @@ def test_swap_acceptance_frequency(hostsim_lib, tmp_path):
 @pytest.mark.gpu
 def test_swap_acceptance_frequency_gpu(tmp_path):
     _swap_acceptance_frequency(None, tmp_path, n_ladders=512, rounds=16)
+
+
+def _stream_ordered_round_matches_stepwise(lib, tmp_path, two_d):
+    """ldo_sim_exchange_round (everything enqueued on the engine's stream, map and counters resident on the device)
+    takes the decisions and trajectories of the advance / collect / apply sequence the tests above pin."""
+    if two_d:
+        opts = make_options("snodin_unbound.json", simulation_type="2d_parallel_tempering", num_reps=4, temps=[332.0, 338.0],
+                            stacking_mults=[1.0, 0.8], exchange_interval=30, swaps=4, random_seed=5)
+        L = 4
+    else:
+        opts, L = pt_options(), len(TEMPS)
+    inp = write_inp(str(tmp_path / "r.inp"), opts)
+    n_ladders = 7
+    a = Simulation(inp, n_ladders * L, 0, lib=lib)
+    b = Simulation(inp, n_ladders * L, 0, lib=lib)
+    for swap_i in range(1, 8):
+        assert a.exchange_advance() == 0
+        a.exchange_apply(swap_i)
+        assert b.exchange_round(swap_i) == 0
+        if swap_i == 4:  # reading the map back in the middle must not disturb the resident copy
+            assert np.array_equal(a.exchange_state(n_ladders, L, two_d=two_d)[0], b.exchange_state(n_ladders, L, two_d=two_d)[0])
+    for x, y in zip(a.exchange_state(n_ladders, L, two_d=two_d), b.exchange_state(n_ladders, L, two_d=two_d)):
+        assert np.array_equal(x, y)
+    assert a.exchange_state(n_ladders, L, two_d=two_d)[2].sum() > 0
+    assert np.array_equal(a.engine.energies(), b.engine.energies())
+    assert np.array_equal(a.engine.control()["temp_idx"], b.engine.control()["temp_idx"])
+    # switching back to the stepwise calls continues from the resident state
+    assert a.exchange_advance() == 0 and b.exchange_advance() == 0
+    a.exchange_apply(8)
+    b.exchange_apply(8)
+    assert np.array_equal(a.exchange_state(n_ladders, L, two_d=two_d)[0], b.exchange_state(n_ladders, L, two_d=two_d)[0])
+    assert np.array_equal(a.engine.energies(), b.engine.energies())
+
+
+@pytest.mark.parametrize("two_d", [False, True])
+def test_stream_ordered_round_matches_stepwise(hostsim_lib, tmp_path, two_d):
+    _stream_ordered_round_matches_stepwise(hostsim_lib, tmp_path, two_d)
+
+
+@pytest.mark.gpu
+def test_stream_ordered_round_matches_stepwise_gpu(tmp_path):
+    _stream_ordered_round_matches_stepwise(None, tmp_path, False)
