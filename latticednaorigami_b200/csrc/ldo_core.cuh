@@ -56,6 +56,16 @@ __device__ __forceinline__ int ldo_laneid() {
 #define LDO_SYNCWARP() ((void)0)
 #endif
 
+// Operation counters of the host emulation (profiles/count_ops.py): how often a move calls the expensive primitives.
+#if defined(LDO_HOSTSIM)
+extern "C" long long ldo_dbg_counts[16];
+#define LDO_COUNT(i) (ldo_dbg_counts[i]++)
+#else
+#define LDO_COUNT(i) ((void)0)
+#endif
+// 0 occupant lookups, 1 table puts, 2 table erases, 3 bind_domain (complementary), 4 check_stacking, 5 eval_place,
+// 6 cp_walks_remain_seg, 7 rg_site_lookup, 8 rg_compute_slot, 9 rg_fill_feeler_memo, 10 rg_feeler_general, 11 step
+
 namespace ldo {
 
 // ---------------------------------------------------------------------------------------------
@@ -120,16 +130,20 @@ LDO_HD inline V3 ore_vec(int code) {
     return v;
 }
 
-// Returns 0..5 for unit vectors, ORE_ZERO for (0,0,0), 7 for anything else
+// Returns 0..5 for unit vectors, ORE_ZERO for (0,0,0), 7 for anything else. Branch-free: a unit vector is +-(1 << t) with
+// t = 0, 11 or 22 the position of its lowest set bit.
 LDO_HD inline int ore_code(V3 v) {
-    uint32_t k = v.k, n = 0u - v.k;
-    if (k == 1u) return 0;
-    if (n == 1u) return 1;
-    if (k == (1u << 11)) return 2;
-    if (n == (1u << 11)) return 3;
-    if (k == (1u << 22)) return 4;
-    if (n == (1u << 22)) return 5;
-    return k == 0u ? ORE_ZERO : 7;
+    uint32_t k = v.k;
+#if defined(__CUDA_ARCH__)
+    int t = __ffs((int)k) - 1; // -1 for k == 0
+#else
+    int t = k ? __builtin_ctz(k) : -1;
+#endif
+    uint32_t neg = k >> 31;
+    uint32_t unit = 1u << (t & 31);
+    bool is_unit = (k == (neg ? 0u - unit : unit)) & ((t == 0) | (t == 11) | (t == 22));
+    int code = 2 * ((t + 1) >> 3) + (int)neg; // t = 0, 11, 22 -> axis 0, 1, 2
+    return is_unit ? code : (k == 0u ? ORE_ZERO : 7);
 }
 
 // VectorThree::rotate_half (utility.cpp:68-86): only acts when |axis| is a basis vector
@@ -437,6 +451,7 @@ struct System {
     LDO_HDN int step(int d, int incr) const {
 #endif
         // single steps (nearly every call) without the loops
+        LDO_COUNT(11);
         if (d < 0) return d;
         if (incr == 1 || incr == -1) {
             int c = S()->dchain[d];
@@ -472,6 +487,7 @@ struct System {
     // ---- occupancy table ----
     // Returns the occupant domain id at p, or -1 (origami_system.cpp:193-202, 130-132)
     LDO_HDN int occupant(V3 p) const {
+        LDO_COUNT(0);
         uint32_t key = pack_pos(p);
         uint32_t i = hash_slot<K>(key);
 #pragma unroll 1
@@ -484,6 +500,7 @@ struct System {
         return -1;
     }
     LDO_HDN void table_put(V3 p, int d) {
+        LDO_COUNT(1);
         if (!in_coord_range(p)) fail(LDO_ERR_COORD_RANGE, d);
         uint32_t key = pack_pos(p);
         uint32_t i = hash_slot<K>(key);
@@ -501,6 +518,7 @@ struct System {
     }
     // Linear-probing erase with backward shift (no tombstones: erases are as frequent as inserts)
     LDO_HDN void table_erase(V3 p) {
+        LDO_COUNT(2);
         uint32_t key = pack_pos(p);
         uint32_t i = hash_slot<K>(key);
         int n = 0;
@@ -607,7 +625,6 @@ struct System {
         if (ndr_1 == ore(h1)) return;
         V3 ndr_2 = pos(h3) - pos(h2);
         if (ndr_1 != ndr_2) {
-            dc.e -= stack_energy();
             dc.stacked -= 1;
         }
     }
@@ -615,8 +632,6 @@ struct System {
         V3 ndr_1 = pos(h2) - pos(h1);
         V3 ndr_2 = pos(h3) - pos(h2);
         if (ndr_1 != ndr_2) {
-            dc.e -= stack_energy() / 2;
-            dc.e -= stack_energy() / 2;
             dc.stacked -= 1;
         }
     }
@@ -646,13 +661,9 @@ struct System {
         }
         int penalty = junction_stacking_penalty(j1, j2, j3, j4, k1, k2);
         if (penalty == 1) {
-            dc.e -= stack_energy() / 2;
-            dc.e -= stack_energy() / 2;
             dc.stacked -= 1;
         }
         else if (penalty == 2) {
-            dc.e -= stack_energy();
-            dc.e -= stack_energy();
             dc.stacked -= 2;
         }
     }
@@ -959,7 +970,6 @@ struct System {
             return;
         }
         if (pair_stacked(d1, d2)) {
-            dc.e += stack_energy();
             dc.stacked += 1;
             if (i == -1) backward_single_junction(dc, d1, d2);
             else forward_single_junction(dc, d1, d2);
@@ -981,7 +991,6 @@ struct System {
             return;
         }
         if (check_twist(d1, ndr, d2)) {
-            dc.e += stack_energy();
             dc.stacked += 1;
         }
         else {
@@ -1029,24 +1038,23 @@ struct System {
         }
     }
 
-    // origami_potential.cpp:231-286
-    LDO_HDN void check_constraints(DeltaConfig& dc, int cd, int j) const {
-#pragma unroll 1
-        for (int i = -1; i <= 0; i++) {
-            int d1 = step(cd, i);
-            int d2 = step(cd, i + 1);
-            if (!(exists_bound(d1) && exists_bound(d2))) continue;
-            int b1 = bound(d1), b2 = bound(d2);
-            if (chain(b1) == chain(b2)) {
-                if (dindex(b1) == dindex(b2) - 1) doubly_contig_helix_pair(dc, d1, d2, i, j);
-                else if (dindex(b1) == dindex(b2) + 1) doubly_contig_junction_pair(dc, d1, d2, j);
-                else regular_pair_constraints(dc, d1, d2, i);
-            }
-            else {
-                regular_pair_constraints(dc, d1, d2, i);
-            }
-            if (dc.violated) return;
+    // origami_potential.cpp:231-286, in its three independent parts: the pair (cd + i, cd + i + 1) for i = -1, 0 and the
+    // triplet centred on cd
+    LDO_HDN void check_constraints_pair(DeltaConfig& dc, int cd, int i, int j) const {
+        int d1 = step(cd, i);
+        int d2 = step(cd, i + 1);
+        if (!(exists_bound(d1) && exists_bound(d2))) return;
+        int b1 = bound(d1), b2 = bound(d2);
+        if (chain(b1) == chain(b2)) {
+            if (dindex(b1) == dindex(b2) - 1) doubly_contig_helix_pair(dc, d1, d2, i, j);
+            else if (dindex(b1) == dindex(b2) + 1) doubly_contig_junction_pair(dc, d1, d2, j);
+            else regular_pair_constraints(dc, d1, d2, i);
         }
+        else {
+            regular_pair_constraints(dc, d1, d2, i);
+        }
+    }
+    LDO_HDN void check_constraints_middle(DeltaConfig& dc, int cd) const {
         int prev = step(cd, -1);
         int forw = step(cd, 1);
         if (exists_bound(prev) && exists_bound(forw)) {
@@ -1065,17 +1073,54 @@ struct System {
         }
     }
 
-    // JunctionBindingPotential::calc_stacking_and_steric_terms (origami_potential.cpp:212-229)
+    // JunctionBindingPotential::calc_stacking_and_steric_terms (origami_potential.cpp:212-229):
+    // check_constraints(di, 0), check_constraints(dj, 1), check_central_triplet_stacking_combos(di, dj). The seven
+    // parts - two pairs and the middle triplet for each of the two domains, and the central triplet combinations - read
+    // the domain records only and add independent terms, so each is evaluated by one lane and the contributions are
+    // reduced across the warp (every term of the potential is a whole number of stacked pairs: the energy follows as
+    // stacked x stacking energy). Called warp-uniformly. The reference stops at the first violation; a violation
+    // anywhere gives the same outcome.
+    LDO_HDN void stacking_task(DeltaConfig& dc, int task, int di, int dj) const {
+        if (task == 6) {
+            central_triplet_combos(dc, di, dj);
+            return;
+        }
+        int cd = task < 3 ? di : dj, j = task < 3 ? 0 : 1, t = task < 3 ? task : task - 3;
+        if (t < 2) check_constraints_pair(dc, cd, t - 1, j);
+        else check_constraints_middle(dc, cd);
+    }
     LDO_HDN void stacking_and_steric_terms(DeltaConfig& dc, int di, int dj) const {
-        check_constraints(dc, di, 0);
-        if (dc.violated) return;
-        check_constraints(dc, dj, 1);
-        if (dc.violated) return;
-        central_triplet_combos(dc, di, dj);
+        int stacked = 0;
+        bool violated = false;
+#if defined(__CUDA_ARCH__) && !defined(LDO_SERIAL_POTENTIAL)
+        DeltaConfig part;
+        part.e = 0;
+        part.stacked = 0;
+        part.violated = false;
+        int lane = LDO_LANE;
+        if (lane < 7) stacking_task(part, lane, di, dj);
+        violated = __any_sync(0xffffffffu, part.violated);
+        stacked = __reduce_add_sync(0xffffffffu, part.stacked);
+#else
+#pragma unroll 1
+        for (int task = 0; task < 7; task++) {
+            DeltaConfig part;
+            part.e = 0;
+            part.stacked = 0;
+            part.violated = false;
+            stacking_task(part, task, di, dj);
+            stacked += part.stacked;
+            violated = violated || part.violated;
+        }
+#endif
+        dc.violated = dc.violated || violated;
+        dc.stacked += stacked;
+        dc.e += stacked * stack_energy();
     }
 
     // BindingPotential::check_stacking (origami_potential.cpp:149-156)
     LDO_HDN DeltaConfig check_stacking(int di, int dj) const {
+        LDO_COUNT(4);
         DeltaConfig dc;
         dc.e = 0;
         dc.stacked = 0;
@@ -1094,6 +1139,7 @@ struct System {
         int ci = orc(di), cj = orc(dj);
         bool opposing = ci == (cj < ORE_ZERO ? (cj ^ 1) : cj);
         if (ident(di) == -ident(dj)) {
+            LDO_COUNT(3);
             // BindingPotential::bind_domains (origami_potential.cpp:131-147)
             if (!opposing) {
                 dc.violated = true;
@@ -1141,6 +1187,7 @@ struct System {
     // the state d would take.
     // -----------------------------------------------------------------------------------------
     LDO_HDN DeltaConfig eval_place(int d, V3 p, int o, int* new_state, int* partner) {
+        LDO_COUNT(5);
         DeltaConfig dc;
         dc.e = 0;
         dc.stacked = 0;

@@ -24,6 +24,9 @@
 #include "../../include/ldo_b200.h"
 
 using namespace ldo;
+#ifdef LDO_HOSTSIM
+extern "C" long long ldo_dbg_counts[16] = {0};
+#endif
 
 // ---------------------------------------------------------------------------------------------
 // Backend

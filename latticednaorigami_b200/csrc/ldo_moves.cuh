@@ -1350,6 +1350,7 @@ struct Engine {
     }
     // walks_remain (:397-445)
     LDO_HDN bool cp_walks_remain_seg(int c, int seg, int dd, V3 p, const EpOverlay* ov) const {
+        LDO_COUNT(6);
         int dir_ = cp_dir_of(c, seg);
         bool rm = ov && ov->rm_chain == c && ov->rm_seg == seg;
 #pragma unroll 1
@@ -1817,6 +1818,7 @@ struct Engine {
         }
     }
     LDO_HDN void rg_site_lookup(int dom, bool dom_is_stem, V3 r, const EpOverlay* ov, int& kind, int& o, double& pv) {
+        LDO_COUNT(7);
         kind = 0;
         o = ORE_ZERO;
         pv = 0;
@@ -1846,6 +1848,7 @@ struct Engine {
     // Evaluates the six neighbour sites of the reference domain for the current domain: lookups one site per
     // lane, then the pending bindings in turn.
     LDO_HDN void rg_compute_slot(int slot) {
+        LDO_COUNT(8);
         RgSlot& sl = M()->slots[slot];
         V3 refp = rec_pos(sys.S()->dom[W()->ref_d]);
 #pragma unroll 1
@@ -1876,6 +1879,7 @@ struct Engine {
     // carried by an EpOverlay. Fills the memo slots and memo_mask. `fd` / `fref`: feeler domain and its
     // reference domain (the parent itself, or an already placed domain).
     LDO_HDN void rg_fill_feeler_memo(int fd, int fref) {
+        LDO_COUNT(9);
         const RgSlot& own = M()->slots[W()->cur_slot];
         V3 refp = rec_pos(sys.S()->dom[W()->ref_d]);
         bool fref_is_parent = fref == W()->d;
@@ -2328,6 +2332,7 @@ struct Engine {
     // One open trial configuration of calc_weights examined the reference's way: place the domain, grow
     // feelers, take it back (rg:384-400)
     LDO_HDN bool rg_feeler_general(V3 p, int o) {
+        LDO_COUNT(10);
         sys.set_checked_domain_config(W()->d, p, o);
         cp_update_endpoints(W()->d);
         eq_push_erased();
