@@ -479,11 +479,13 @@ def run_ours(args, rank, world, local_rank, wl):
         tile_states(eng, starts, R // unit, unit, opts["random_seed"], lambda r: rank * R + r)
     eng.assert_ok()
     stream = torch.cuda.ExternalStream(eng.stream(), device=local_rank)
-    send = recv = None
     if world > 1 and is_pt:
-        send_ptr, recv_ptr, nq = eng.exchange_buffers(R * world)
-        send = torch.as_tensor(DevArray(send_ptr, R * nq), device=f"cuda:{local_rank}")
-        recv = torch.as_tensor(DevArray(recv_ptr, R * world * nq), device=f"cuda:{local_rank}")
+        # the exchange lives in the C++ host: one NCCL communicator across the ranks, created from a unique id that
+        # rank 0 makes and torch.distributed only carries to the others
+        from latticednaorigami_b200.binding import comm_unique_id
+        box = [comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        sim.comm_init(box[0])
 
     swap = [0]
     kernel_events = []
@@ -498,17 +500,17 @@ def run_ours(args, rank, world, local_rank, wl):
         if record:
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record(stream)
-        eng.run_async(wl.moves_per_step, cf, 0, ccf)
+        if is_pt:
+            # ldo_sim_exchange_round: moves, collection of the exchange records, ncclAllGather (N > 1), swap decisions
+            # and the energy rebuild, all enqueued on the engine's stream by the C++ host - no host synchronisation
+            sim.exchange_round(swap[0])
+        else:
+            eng.run_async(wl.moves_per_step, cf, 0, ccf)
         if record:
             b.record(stream)
             kernel_events.append((a, b))
         if is_pt:
-            eng.exchange_collect(to_host=False)
-            if world > 1:
-                eng.synchronize()
-                dist.all_gather_into_tensor(recv, send)
-                torch.cuda.current_stream().synchronize()
-            sim.exchange_apply(swap[0], None)
+            pass
         elif isinstance(wl, PTMWUS):
             eng.exchange_windows(swap[0], n_lad, len(WINDOWS), 1, [0], w2r, w_att, w_acc)
 
@@ -594,7 +596,10 @@ def run_ours(args, rank, world, local_rank, wl):
         staged = state_bytes < 8192
         roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
                 "kernel": ("k_exec_staged<CapsSmall>" if staged else "k_exec_inplace<CapsLarge>") + f" (run, {wl.moves_per_step} moves/replica)",
-                "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": hbm_bytes, "peak_source": peak_src}
+                "kernel_ms": kernel_ms, "algorithmic_bytes_per_launch": hbm_bytes, "peak_source": peak_src,
+                "kernel_ms_note": "CUDA events on the engine's stream around one step" +
+                                  (" (run launch + the exchange's collection / decision / energy-rebuild launches, < 1 % of it: "
+                                   "profiles/launches_r2.csv)" if is_pt else "")}
         prof_path = os.path.join(ROOT, "profiles", f"ncu_{wl.name}_traffic.json")
         if os.path.exists(prof_path):
             t = json.load(open(prof_path))

@@ -109,6 +109,9 @@ typedef struct {
     int chain1, domain1, chain2, domain2; /* Dist / AdjacentSite (order_params.cpp:496-511); chains must be 0 */
     int n_sum;   /* Sum: indices of earlier order parameters */
     const int* sum_ops;
+    int update_per_domain; /* Dist / AdjacentSite: "update_per_domain" (order_params.cpp:505-511): recomputed whenever one of
+                              its domains is unassigned or placed (OrigamiSystemWithBias, origami_system.cpp:923-945) instead
+                              of once per move */
 } ldo_order_param_desc;
 
 typedef struct {
@@ -152,9 +155,14 @@ int ldo_set_moveset(ldo_engine* e, int n, const ldo_movetype_desc* movetypes, in
  * replay tape runs, driven by Philox. Same ensemble; slower. Used to validate the lane-parallel branches
  * against the serial ones on the same device (tests/test_production_parity.py). Default off. */
 int ldo_set_reference_draw_order(ldo_engine* e, int on);
-/* Replaces: SystemOrderParams::setup_ops (order_params.cpp:471-577), move-update kind. */
+/* Replaces: the choice of OrigamiSystemWithBias over OrigamiSystem by `domain_update_biases_present`
+ * (origami::setup_origami, origami_system.cpp:1006-1028). Call before ldo_set_order_params. Without it order
+ * parameters marked update_per_domain keep their initial values, as in the reference. */
+int ldo_set_domain_update_biases(ldo_engine* e, int present);
+/* Replaces: SystemOrderParams::setup_ops (order_params.cpp:471-577), both kinds. */
 int ldo_set_order_params(ldo_engine* e, int n, const ldo_order_param_desc* ops);
-/* Replaces: SystemBiases::setup_biases (bias_functions.cpp:334-430), move-update kind. */
+/* Replaces: SystemBiases::setup_biases (bias_functions.cpp:334-430). Every bias is evaluated once per move: the
+ * reference's dependency test never registers one as per-domain (see System::pd_update in csrc/ldo_core.cuh). */
 int ldo_set_biases(ldo_engine* e, int n, const ldo_bias_desc* biases);
 /* Replaces: MWUSGCMCSimulation window override of a well bias (us_simulation.cpp:503-516). */
 int ldo_set_window(ldo_engine* e, int replica, int bias, int min_op, int max_op);

@@ -12,7 +12,7 @@ DRAW_DTYPE = np.dtype([("kind", "<i4"), ("lo", "<i4"), ("hi", "<i4"), ("ival", "
 # Symbols declared in include/ldo_b200.h and include/ldo_host.h (checked by tests/test_abi.py)
 ENGINE_SYMBOLS = [
     "ldo_engine_create", "ldo_engine_destroy", "ldo_last_error", "ldo_num_replicas",
-    "ldo_set_temperature_tables", "ldo_set_moveset", "ldo_set_order_params", "ldo_set_biases",
+    "ldo_set_temperature_tables", "ldo_set_moveset", "ldo_set_domain_update_biases", "ldo_set_order_params", "ldo_set_biases",
     "ldo_set_window", "ldo_set_grid_bias", "ldo_get_grid_visits", "ldo_set_control", "ldo_get_control",
     "ldo_seed", "ldo_seed_subsequences", "ldo_attach_tape", "ldo_tape_position", "ldo_set_state", "ldo_state_capacity",
     "ldo_get_state", "ldo_run", "ldo_get_status", "ldo_run_async", "ldo_synchronize", "ldo_stream",
@@ -76,6 +76,7 @@ def bind(L):
         "ldo_num_replicas": (i, [vp]),
         "ldo_set_temperature_tables": (i, [vp, i, i, vp, vp, vp, vp, vp]),
         "ldo_set_moveset": (i, [vp, i, vp, i]),
+        "ldo_set_domain_update_biases": (i, [vp, i]),
         "ldo_set_order_params": (i, [vp, i, vp]),
         "ldo_set_biases": (i, [vp, i, vp]),
         "ldo_set_window": (i, [vp, i, i, i, i]),

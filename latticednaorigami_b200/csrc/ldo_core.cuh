@@ -372,6 +372,77 @@ struct DeltaConfig {
 // Table key = the packed position itself
 LDO_HD inline uint32_t pack_pos(V3 p) { return p.k; }
 
+// ---------------------------------------------------------------------------------------------
+// Order parameters and biases: the kind evaluated once per move (`update_per_domain: false`, Engine::calc_op /
+// calc_move_bias in ldo_moves.cuh) and the kind updated with every domain placement (System::pd_*)
+// ---------------------------------------------------------------------------------------------
+
+enum {
+    OP_NUM_STAPLES = 0,
+    OP_NUM_STAPLES_TYPE = 1,
+    OP_STAPLE_TYPE_FULLY_BOUND = 2,
+    OP_NUM_BOUND_DOMAIN_PAIRS = 3,
+    OP_NUM_MISBOUND_DOMAIN_PAIRS = 4,
+    OP_NUM_STACKED_PAIRS = 5,
+    OP_NUM_LINEAR_HELICES = 6,
+    OP_NUM_STACKED_JUNCTS = 7,
+    OP_SUM = 8,
+    OP_DIST = 9, // DistOrderParam (order_params.cpp:34-48), move-update kind, scaffold domains
+    OP_ADJACENT_SITE = 10 // AdjacentSiteOrderParam (order_params.cpp:84-104)
+};
+enum { BIAS_LINEAR_STEP_WELL = 0, BIAS_SQUARE_WELL = 1, BIAS_GRID = 2 };
+
+#define LDO_MAX_OPS 16
+#define LDO_MAX_BIASES 8
+#define LDO_MAX_SUM 8
+#define LDO_MAX_GRID_DIM 3
+
+struct OpDef {
+    int type;
+    int per_domain; // update_per_domain: true (Dist / AdjacentSite on scaffold domains): order_params.cpp:566-575
+    int arg; // staple identity for the *Type ops; first scaffold domain of Dist / AdjacentSite
+    int arg2; // second scaffold domain of Dist / AdjacentSite
+    int n_sum;
+    int sum_idx[LDO_MAX_SUM];
+};
+
+struct BiasDef {
+    int type;
+    int n_ops;
+    int op_idx[LDO_MAX_GRID_DIM];
+    int min_op, max_op; // LinearStepWell / SquareWell
+    double well_bias, min_bias, slope, outside_bias;
+};
+
+struct OpsBiasConst {
+    int n_ops;
+    int n_biases;
+    int n_pd_ops; // per-domain order parameters; 0 switches every per-domain hook off
+    OpDef ops[LDO_MAX_OPS];
+    BiasDef biases[LDO_MAX_BIASES];
+};
+
+// Per-replica bias state: window limits (MWUS overrides min_op/max_op per window,
+// us_simulation.cpp:503-516) and dense grid-bias boxes (GridBiasFunction, bias_functions.cpp:242-283)
+struct BiasState {
+    int op_val[LDO_MAX_OPS]; // m_param of every order parameter
+    unsigned op_undefined; // bit i: OrderParam::m_defined == false (a Dist / AdjacentSite domain is unassigned)
+    double bias_val[LDO_MAX_BIASES]; // BiasFunction::m_bias
+    double move_update_bias; // SystemBiases::m_move_update_bias (m_domain_update_bias is always 0, see System::pd_update)
+    int pd_disabled; // != 0 while a configuration is being loaded (the reference builds ops / biases after set_all_domains)
+    int win_min[LDO_MAX_BIASES], win_max[LDO_MAX_BIASES];
+    int grid_lo[LDO_MAX_BIASES][LDO_MAX_GRID_DIM];
+    int grid_n[LDO_MAX_BIASES][LDO_MAX_GRID_DIM];
+    int grid_off[LDO_MAX_BIASES]; // offset into the slot's grid value / visit arrays, -1 = none
+    // Which slot of the engine-wide grid arrays this replica currently uses. Window exchange swaps the
+    // window-specific fields (limits, boxes, slot) of two replicas instead of shipping configurations.
+    int grid_slot;
+};
+
+#if defined(__CUDACC__)
+__constant__ OpsBiasConst ldo_c_ob;
+#endif
+
 template <class K>
 LDO_HD inline uint32_t hash_slot(uint32_t key) {
     return (key * 0x9E3779B1u) >> (32 - K::HBITS);
@@ -386,6 +457,17 @@ struct System {
     SysState<K>* s;
     const SysConst* sc;
     TempTables tt;
+    BiasState* bsp; // per-domain order parameters (the hooks below)
+    const OpsBiasConst* obp;
+
+    LDO_HD BiasState* BSP() const { return LDO_SMEM_PTR(K, BiasState, bias, bsp); }
+    LDO_HD const OpsBiasConst& OBC() const {
+#if defined(__CUDA_ARCH__)
+        return ldo_c_ob;
+#else
+        return *obp;
+#endif
+    }
 
     LDO_HD SysState<K>* S() const {
         return LDO_SMEM_PTR(K, SysState<K>, state, s);
@@ -404,6 +486,8 @@ struct System {
         s = s_;
         sc = sc_;
         tt = tt_;
+        bsp = nullptr;
+        obp = nullptr;
     }
 
     LDO_HDN void fail(int code, int detail = 0) {
@@ -1243,6 +1327,38 @@ struct System {
         return dc;
     }
 
+    // -----------------------------------------------------------------------------------------
+    // Per-domain-update order parameters (OrigamiSystemWithBias, origami_system.cpp:873-957; SystemOrderParams::
+    // update_one_domain, order_params.cpp:603-612): Dist / AdjacentSite parameters between scaffold domains marked
+    // update_per_domain are recomputed (calc_param: value and `defined`) whenever one of their domains is unassigned or
+    // placed by set_checked_domain_config - and NOT by set_domain_config, which leaves them as the preceding unassignment
+    // left them (undefined) until a later move touches the domain again. Biases on them are read at the end of the move
+    // like any other (SystemBiases::calc_move): the reference can never register a bias function as per-domain - its
+    // dependency test reads the empty "bias_funcs" entry as one tag without domains (bias_functions.cpp:371-384,
+    // utility.cpp:238-248) - so calc_one_domain / check_one_domain always return 0 and no candidate check carries a bias.
+    // check_param's writes to m_defined are never read before the next calc_param of the same parameter.
+    // -----------------------------------------------------------------------------------------
+    LDO_HD bool pd_active(int d) const { return OBC().n_pd_ops != 0 && S()->dchain[d] == 0 && !BSP()->pd_disabled; }
+    LDO_HDN void pd_update(int d) {
+        BiasState* bs = BSP();
+        int di_ = S()->dindex[d];
+#pragma unroll 1
+        for (int i = 0; i < OBC().n_ops; i++) {
+            const OpDef& o = OBC().ops[i];
+            if (!o.per_domain || (o.arg != di_ && o.arg2 != di_)) continue;
+            const DomRec& a = S()->dom[o.arg];
+            const DomRec& b = S()->dom[o.arg2];
+            if (a.state == ST_UNASSIGNED || b.state == ST_UNASSIGNED) {
+                bs->op_undefined |= 1u << i;
+            }
+            else {
+                bs->op_undefined &= ~(1u << i);
+                int dist = abssum(rec_pos(b) - rec_pos(a));
+                bs->op_val[i] = o.type == OP_DIST ? dist : (dist == 1 ? 1 : 0);
+            }
+        }
+    }
+
     // ---- mutation ----
     LDO_HD void write_dom(int d, V3 p, int o) {
         DomRec& r = S()->dom[d];
@@ -1281,7 +1397,7 @@ struct System {
     }
 
     // OrigamiSystem::set_domain_config (origami_system.cpp:517-541). Sets constraints_violated.
-    LDO_HDN double set_domain_config(int d, V3 p, int o) {
+    LDO_HDN double set_domain_config_base(int d, V3 p, int o) {
         if (S()->dom[d].state != ST_UNASSIGNED) {
             fail(LDO_ERR_SET_ASSIGNED, d);
             return 0;
@@ -1318,11 +1434,12 @@ struct System {
     // OrigamiSystem::check_domain_constraints (origami_system.cpp:343-355): side-effect free apart
     // from the violation flag and (as in the reference) the stored position/orientation of d.
     LDO_HDN double check_domain_constraints(int d, V3 p, int o) {
+        // OrigamiSystemWithBias::check_domain_constraints (origami_system.cpp:892-921) adds the per-domain bias check
         int ns, partner;
         DeltaConfig dc = eval_place(d, p, o, &ns, &partner);
         if (ns == ST_UNASSIGNED) {
             S()->constraints_violated = 1;
-            return dc.e;
+                return dc.e;
         }
         write_dom(d, p, o);
         if (partner >= 0) S()->constraints_violated = dc.violated ? 1 : 0;
@@ -1330,7 +1447,7 @@ struct System {
     }
 
     // OrigamiSystem::set_checked_domain_config (origami_system.cpp:478-515)
-    LDO_HDN double set_checked_domain_config(int d, V3 p, int o) {
+    LDO_HDN double set_checked_domain_config_base(int d, V3 p, int o) {
         commit_place(d, p, o);
         if (S()->weight_pass) {
             S()->num_unassigned--;
@@ -1357,7 +1474,7 @@ struct System {
     }
 
     // internal_unassign_domain + unassign_domain (origami_system.cpp:375-385, 695-760)
-    LDO_HDN double unassign_domain(int d) {
+    LDO_HDN double unassign_domain_base(int d) {
         int st = S()->dom[d].state;
         double e = 0;
         int stacked = 0;
@@ -1400,6 +1517,20 @@ struct System {
         S()->energy += e;
         S()->num_stacked_pairs += stacked;
         S()->num_unassigned++;
+        return e;
+    }
+
+    // OrigamiSystemWithBias::set_checked_domain_config / unassign_domain (origami_system.cpp:928-945); set_domain_config
+    // (:947-954) only adds calc_one_domain, which is always 0 (see above)
+    LDO_HD double set_domain_config(int d, V3 p, int o) { return set_domain_config_base(d, p, o); }
+    LDO_HD double set_checked_domain_config(int d, V3 p, int o) {
+        double e = set_checked_domain_config_base(d, p, o);
+        if (pd_active(d)) pd_update(d);
+        return e;
+    }
+    LDO_HD double unassign_domain(int d) {
+        double e = unassign_domain_base(d);
+        if (pd_active(d)) pd_update(d);
         return e;
     }
 

@@ -195,6 +195,8 @@ LDO_HD void rep_init_engine(Engine<K>& eng, SysState<K>* st, MoveScratch<K>* ms,
     eng.ms = &sh->ms;
     eng.ob = &sh->ob;
     eng.bs = &aux->bs;
+    eng.sys.bsp = &aux->bs;
+    eng.sys.obp = &sh->ob;
     eng.grid_vals = P.grid_vals ? P.grid_vals + (size_t)aux->bs.grid_slot * LDO_GRID_CAP : nullptr;
     eng.ctl = aux->ctl;
     eng.stats = &P.aux[r].stats;
@@ -214,9 +216,11 @@ LDO_HD void rep_refresh_stack_energy(SysState<K>* st, const Shared* sh, const Co
 // Bias bookkeeping restart (SystemBiases constructor: every m_bias evaluated once, bias_functions.cpp:60-66,423-426)
 template <class K>
 LDO_HD void rep_init_biases(Engine<K>& eng) {
+    // every parameter and every bias is evaluated once, whichever kind (order_params.cpp:31, bias_functions.cpp:414-426)
     eng.BS()->op_undefined = 0;
-    eng.update_move_params();
+    for (int i = 0; i < eng.OB().n_ops; i++) eng.BS()->op_val[i] = eng.calc_op(i);
     eng.BS()->move_update_bias = 0;
+    eng.BS()->pd_disabled = 0;
     for (int b = 0; b < eng.OB().n_biases; b++) {
         eng.BS()->bias_val[b] = eng.calc_bias_fn(b);
         eng.BS()->move_update_bias += eng.BS()->bias_val[b];
@@ -233,6 +237,7 @@ LDO_HD void rep_load_config(Engine<K>& eng, const OpArgs& a) {
     s->status_detail = 0;
     s->constraints_violated = 0;
     s->weight_pass = 0;
+    eng.BS()->pd_disabled = 1; // ops and biases are (re)built from the loaded configuration below
     sys.table_clear();
     for (int c = 0; c < K::C; c++) s->chain_used[c] = 0;
     for (int t = 0; t < K::T; t++) s->type_count[t] = 0;
@@ -1124,6 +1129,7 @@ struct EngineBase {
     virtual size_t state_bytes() = 0;
     virtual int get_blobs(int first, int count, void* host) = 0;
     virtual int put_blobs(int first, int count, const void* host) = 0;
+    int domain_update_biases = 0; // ldo_set_domain_update_biases
     long long launches = 0; // kernels launched so far (ldo_launch_count)
     long long const_version = 0;
     // device output buffers
@@ -2025,13 +2031,25 @@ int ldo_set_reference_draw_order(ldo_engine* e, int on) {
     return e->b->push_shared();
 }
 
+int ldo_set_domain_update_biases(ldo_engine* e, int present) {
+    e->b->domain_update_biases = present ? 1 : 0;
+    return 0;
+}
+
 int ldo_set_order_params(ldo_engine* e, int n, const ldo_order_param_desc* ops) {
     EngineBase* b = e->b;
     if (n < 0 || n > LDO_MAX_OPS) return b->fail("too many order parameters");
     OpsBiasConst& ob = b->shared.ob;
     ob.n_ops = n;
+    ob.n_pd_ops = 0;
+    // the per-domain hooks exist in OrigamiSystemWithBias only (domain_update_biases_present, origami_system.cpp:1006-1028);
+    // without it per-domain parameters are registered but never updated again
+    for (int i = 0; i < n && b->domain_update_biases; i++) {
+        if ((ops[i].type == OP_DIST || ops[i].type == OP_ADJACENT_SITE) && ops[i].update_per_domain) ob.n_pd_ops++;
+    }
     for (int i = 0; i < n; i++) {
         ob.ops[i].type = ops[i].type;
+        ob.ops[i].per_domain = 0;
         ob.ops[i].arg = ops[i].staple;
         ob.ops[i].arg2 = 0;
         ob.ops[i].n_sum = 0;
@@ -2043,9 +2061,18 @@ int ldo_set_order_params(ldo_engine* e, int n, const ldo_order_param_desc* ops) 
             }
             ob.ops[i].arg = ops[i].domain1;
             ob.ops[i].arg2 = ops[i].domain2;
+            ob.ops[i].per_domain = ops[i].update_per_domain ? 1 : 0;
+        }
+        else if (ops[i].update_per_domain) {
+            return b->fail("only Dist / AdjacentSite order parameters can be updated per domain");
         }
         if (ops[i].type == OP_SUM) {
             if (ops[i].n_sum > LDO_MAX_SUM) return b->fail("Sum order parameter has too many terms");
+            for (int k = 0; k < ops[i].n_sum; k++) {
+                if (ops[i].sum_ops[k] >= 0 && ops[i].sum_ops[k] < i && ob.ops[ops[i].sum_ops[k]].per_domain) {
+                    return b->fail("Sum of per-domain order parameters is not available (its evaluation order is not reproducible)");
+                }
+            }
             ob.ops[i].n_sum = ops[i].n_sum;
             for (int k = 0; k < ops[i].n_sum; k++) {
                 if (ops[i].sum_ops[k] < 0 || ops[i].sum_ops[k] >= i) return b->fail("Sum refers to a later order parameter");

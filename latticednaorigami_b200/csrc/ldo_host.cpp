@@ -682,10 +682,8 @@ std::vector<OrderParamSpec> read_order_params_file(std::string const& filename) 
         op.level = jops[i]["level"].as_int();
         op.staple = jops[i]["staple"].as_int();
         if (op.type == "Dist" || op.type == "AdjacentSite") {
-            // order_params.cpp:496-516. The per-domain kind (OrigamiSystemWithBias) is not on the device path.
-            if (jops[i]["update_per_domain"].as_bool()) {
-                throw NotImplemented {op.type + ": update_per_domain = true is not available on the device path (DESIGN.md §7)"};
-            }
+            // order_params.cpp:496-516; update_per_domain selects the per-domain kind (OrigamiSystemWithBias)
+            op.update_per_domain = jops[i]["update_per_domain"].as_bool();
             op.chain1 = jops[i]["chain1"].as_int();
             op.domain1 = jops[i]["domain1"].as_int();
             op.chain2 = jops[i]["chain2"].as_int();
@@ -702,6 +700,23 @@ std::vector<OrderParamSpec> read_order_params_file(std::string const& filename) 
             if (file_order[i].level == level) {
                 out.push_back(file_order[i]);
                 src.push_back(i);
+            }
+        }
+    }
+    // The reference's setup loop carries `update_per_domain` over from one entry of a level to the next
+    // (order_params.cpp:485-511: the flag is set by Dist / AdjacentSite / Sum entries and read by all): a counter-type
+    // parameter that follows a per-domain one in its level is registered nowhere and is never updated again. Refused.
+    for (size_t k {0}; k != out.size(); k++) {
+        bool dist_like {out[k].type == "Dist" || out[k].type == "AdjacentSite"};
+        if (!dist_like && out[k].type != "Sum") {
+            for (size_t q {k}; q-- > 0 && out[q].level == out[k].level;) {
+                bool q_dist {out[q].type == "Dist" || out[q].type == "AdjacentSite"};
+                if (q_dist || out[q].type == "Sum") {
+                    if (out[q].update_per_domain) {
+                        throw SimulationMisuse {out[k].tag + ": follows a per-domain order parameter in its level; the reference never updates such a parameter"};
+                    }
+                    break;
+                }
             }
         }
     }

@@ -180,6 +180,7 @@ struct OrderParamSpec {
     int level {0};
     int staple {0};
     int chain1 {0}, domain1 {0}, chain2 {0}, domain2 {0}; // Dist / AdjacentSite
+    bool update_per_domain {false}; // Dist / AdjacentSite: updated with every domain placement (order_params.cpp:505-511)
     std::vector<int> sum_ops;
 };
 // Returned in the reference's evaluation order (level-major, file order within a level)

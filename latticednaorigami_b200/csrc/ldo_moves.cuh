@@ -91,69 +91,6 @@ LDO_HD inline void philox4x32_10(const Rng& r, unsigned long long ctr, uint32_t*
 }
 
 // ---------------------------------------------------------------------------------------------
-// Order parameters and biases evaluated per move (the `update_per_domain: false` kind)
-// ---------------------------------------------------------------------------------------------
-
-enum {
-    OP_NUM_STAPLES = 0,
-    OP_NUM_STAPLES_TYPE = 1,
-    OP_STAPLE_TYPE_FULLY_BOUND = 2,
-    OP_NUM_BOUND_DOMAIN_PAIRS = 3,
-    OP_NUM_MISBOUND_DOMAIN_PAIRS = 4,
-    OP_NUM_STACKED_PAIRS = 5,
-    OP_NUM_LINEAR_HELICES = 6,
-    OP_NUM_STACKED_JUNCTS = 7,
-    OP_SUM = 8,
-    OP_DIST = 9, // DistOrderParam (order_params.cpp:34-48), move-update kind, scaffold domains
-    OP_ADJACENT_SITE = 10 // AdjacentSiteOrderParam (order_params.cpp:84-104)
-};
-enum { BIAS_LINEAR_STEP_WELL = 0, BIAS_SQUARE_WELL = 1, BIAS_GRID = 2 };
-
-#define LDO_MAX_OPS 16
-#define LDO_MAX_BIASES 8
-#define LDO_MAX_SUM 8
-#define LDO_MAX_GRID_DIM 3
-
-struct OpDef {
-    int type;
-    int arg; // staple identity for the *Type ops; first scaffold domain of Dist / AdjacentSite
-    int arg2; // second scaffold domain of Dist / AdjacentSite
-    int n_sum;
-    int sum_idx[LDO_MAX_SUM];
-};
-
-struct BiasDef {
-    int type;
-    int n_ops;
-    int op_idx[LDO_MAX_GRID_DIM];
-    int min_op, max_op; // LinearStepWell / SquareWell
-    double well_bias, min_bias, slope, outside_bias;
-};
-
-struct OpsBiasConst {
-    int n_ops;
-    int n_biases;
-    OpDef ops[LDO_MAX_OPS];
-    BiasDef biases[LDO_MAX_BIASES];
-};
-
-// Per-replica bias state: window limits (MWUS overrides min_op/max_op per window,
-// us_simulation.cpp:503-516) and dense grid-bias boxes (GridBiasFunction, bias_functions.cpp:242-283)
-struct BiasState {
-    int op_val[LDO_MAX_OPS]; // m_param of every order parameter
-    unsigned op_undefined; // bit i: OrderParam::m_defined == false (a Dist / AdjacentSite domain is unassigned)
-    double bias_val[LDO_MAX_BIASES]; // BiasFunction::m_bias
-    double move_update_bias; // SystemBiases::m_move_update_bias
-    int win_min[LDO_MAX_BIASES], win_max[LDO_MAX_BIASES];
-    int grid_lo[LDO_MAX_BIASES][LDO_MAX_GRID_DIM];
-    int grid_n[LDO_MAX_BIASES][LDO_MAX_GRID_DIM];
-    int grid_off[LDO_MAX_BIASES]; // offset into the slot's grid value / visit arrays, -1 = none
-    // Which slot of the engine-wide grid arrays this replica currently uses. Window exchange swaps the
-    // window-specific fields (limits, boxes, slot) of two replicas instead of shipping configurations.
-    int grid_slot;
-};
-
-// ---------------------------------------------------------------------------------------------
 // Moveset
 // ---------------------------------------------------------------------------------------------
 
@@ -316,7 +253,6 @@ struct RgSlot {
 
 #if defined(__CUDACC__)
 __constant__ MoveSet ldo_c_ms;
-__constant__ OpsBiasConst ldo_c_ob;
 #endif
 
 // ---------------------------------------------------------------------------------------------
@@ -643,7 +579,10 @@ struct Engine {
     // SystemOrderParams::update_move_params (order_params.cpp:595-601)
     LDO_HD void update_move_params() {
 #pragma unroll 1
-        for (int i = 0; i < OB().n_ops; i++) BS()->op_val[i] = calc_op(i);
+        for (int i = 0; i < OB().n_ops; i++) {
+            if (OB().ops[i].per_domain) continue; // updated with every domain placement (System::pd_update)
+            BS()->op_val[i] = calc_op(i);
+        }
     }
     LDO_HD double grid_lookup(int b) const {
         int off = BS()->grid_off[b];
@@ -689,6 +628,7 @@ struct Engine {
         BS()->move_update_bias += diff;
         return diff * CTL().bias_mult;
     }
+    // SystemBiases::get_total_bias (bias_functions.cpp:459-461); m_domain_update_bias is always 0
     LDO_HD double total_bias() const { return BS()->move_update_bias * CTL().bias_mult; }
 
     // ---- MCMovetype shared helpers (movetypes.cpp:98-158) ----

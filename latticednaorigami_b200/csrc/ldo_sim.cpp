@@ -813,9 +813,6 @@ ldo_sim* ldo_sim_create(const char* inp_path, int n_replicas, int device, int ra
             throw NotImplemented {"SequenceSpecific stacking is not available on the device path (unfinished in the reference)"};
         }
         if (p.m_stacking_pot != "Constant") throw NotImplemented {p.m_stacking_pot + ": No such stacking potential"};
-        if (p.m_domain_update_biases_present) {
-            throw NotImplemented {"domain_update_biases_present: per-domain biases are not available on the device path yet"};
-        }
         int domain_type {domain_type_code(p.m_domain_type)};
 
         // temperatures
@@ -916,6 +913,7 @@ ldo_sim* ldo_sim_create(const char* inp_path, int n_replicas, int device, int ra
         }
 
         // order parameters and biases
+        s->check(ldo_set_domain_update_biases(s->eng, p.m_domain_update_biases_present ? 1 : 0));
         if (!p.m_ops_filename.empty()) {
             s->ops = read_order_params_file(p.m_ops_filename);
             std::vector<ldo_order_param_desc> od(s->ops.size());
@@ -928,6 +926,10 @@ ldo_sim* ldo_sim_create(const char* inp_path, int n_replicas, int device, int ra
                 od[i].domain2 = s->ops[i].domain2;
                 od[i].n_sum = static_cast<int>(s->ops[i].sum_ops.size());
                 od[i].sum_ops = s->ops[i].sum_ops.data();
+                // per-domain updates happen in OrigamiSystemWithBias only, which setup_origami builds when
+                // domain_update_biases_present is set (origami_system.cpp:1006-1028); with a plain OrigamiSystem such
+                // parameters keep their initial value for ever - the device does the same through this flag
+                od[i].update_per_domain = s->ops[i].update_per_domain ? 1 : 0;
             }
             s->check(ldo_set_order_params(s->eng, static_cast<int>(od.size()), od.data()));
         }

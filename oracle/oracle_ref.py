@@ -66,8 +66,11 @@ def lib():
         L.oref_pair_energies.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         L.oref_init_energies.argtypes = [C.c_void_p, C.c_void_p]
         L.oref_order_param.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p]
+        L.oref_order_param_stored.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_void_p]
         L.oref_total_bias.restype = C.c_double
         L.oref_total_bias.argtypes = [C.c_void_p]
+        L.oref_total_bias_stored.restype = C.c_double
+        L.oref_total_bias_stored.argtypes = [C.c_void_p]
         L.oref_check_domain.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.oref_set_domain.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.oref_unassign_domain.restype = C.c_double
@@ -285,8 +288,18 @@ class RefSystem:
         self._check(self.L.oref_order_param(self.h, tag.encode(), C.byref(v)))
         return v.value
 
+    def order_param_stored(self, tag):
+        """(m_param, m_defined) as they stand, without the calc_param that order_param() does."""
+        v, d = C.c_int(0), C.c_int(0)
+        self._check(self.L.oref_order_param_stored(self.h, tag.encode(), C.byref(v), C.byref(d)))
+        return v.value, bool(d.value)
+
     def total_bias(self):
         return self.L.oref_total_bias(self.h)
+
+    def total_bias_stored(self):
+        """SystemBiases::get_total_bias as it stands (what .ene prints), without the re-evaluation total_bias() does."""
+        return self.L.oref_total_bias_stored(self.h)
 
     def check_domain(self, c, d, pos, ore):
         p = np.asarray(pos, dtype=np.int32)

@@ -344,12 +344,30 @@ int oref_order_param(void* vh, const char* tag, int* value) {
     return 0;
 }
 
+// The stored value and `defined` flag of an order parameter, without re-evaluating it (calc_param above refreshes a
+// per-domain parameter, which changes what the reference does next)
+int oref_order_param_stored(void* vh, const char* tag, int* value, int* defined) {
+    auto h = static_cast<Handle*>(vh);
+    try {
+        auto& op {h->origami->get_system_order_params().get_order_param(tag)};
+        *value = op.get_param();
+        *defined = op.defined() ? 1 : 0;
+    } catch (std::exception const& e) {
+        h->err = e.what();
+        return -1;
+    }
+    return 0;
+}
+
 double oref_total_bias(void* vh) {
     auto h = static_cast<Handle*>(vh);
     h->origami->get_system_order_params().update_move_params();
     h->origami->get_system_biases().calc_move();
     return h->origami->get_system_biases().get_total_bias();
 }
+
+// The stored total as the .ene writer reads it (files.cpp:707-720), without re-evaluating anything
+double oref_total_bias_stored(void* vh) { return static_cast<Handle*>(vh)->origami->get_system_biases().get_total_bias(); }
 
 // ---- single-domain operations (origami_system.cpp:343-385, 478-541) -------------------
 

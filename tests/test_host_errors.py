@@ -1,4 +1,4 @@
-"""Inputs the device path refuses, with the reason (no silent fallback): per-domain-update order parameters, the
+"""Inputs the device path refuses, with the reason (no silent fallback): a Sum of per-domain-update order parameters, the
 movetype the reference names but never constructs, and linker-move options out of range."""
 import json
 import os
@@ -16,14 +16,17 @@ def _moveset(tmp_path, entry):
     return str(path)
 
 
-def test_per_domain_order_parameter_is_refused(hostsim_lib, tmp_path):
+def test_sum_of_per_domain_order_parameters_is_refused(hostsim_lib, tmp_path):
+    """Per-domain Dist / AdjacentSite parameters are supported (tests/test_per_domain_biases.py); a Sum built on them is
+    not: the reference's result then depends on the order of its candidate checks."""
     ops = json.load(open(os.path.join(INPUTS, "ops_dist.json")))
-    ops["origami"]["order_params"][2]["update_per_domain"] = True
+    for k in (2, 3):
+        ops["origami"]["order_params"][k]["update_per_domain"] = True
     path = tmp_path / "ops.json"
     path.write_text(json.dumps(ops))
-    opts = make_options("snodin_unbound.json")
+    opts = make_options("snodin_unbound.json", domain_update_biases_present=True)
     opts["order_parameter_file"] = str(path)
-    with pytest.raises(LdoError, match="update_per_domain"):
+    with pytest.raises(LdoError, match="Sum of per-domain"):
         Simulation(write_inp(str(tmp_path / "a.inp"), opts), 1, 0, lib=hostsim_lib)
 
 
