@@ -108,6 +108,7 @@ struct __attribute__((aligned(16))) RepAux {
     // ctl.temp_idx), `table_cache_mask` has one bit per ladder slot key already seen (exchange_ladder).
     int init_temp_idx;
     unsigned long long table_cache_mask;
+    int window_swapped; // set by the window exchange for the two replicas of an accepted swap (OP_AFTER_WINDOW_SWAP)
     BiasState bs;
     long long step;
     // not staged to shared memory (touched twice per move): everything from here on stays in HBM/L2
@@ -132,7 +133,8 @@ enum {
     OP_OBSERVE = 5,
     OP_RECOMPUTE = 6,
     OP_REFRESH_OPS = 7,
-    OP_REINIT_BIASES = 8
+    OP_REINIT_BIASES = 8,
+    OP_AFTER_WINDOW_SWAP = 9
 };
 
 struct OpArgs {
@@ -343,7 +345,8 @@ LDO_HD void rep_observe(Engine<K>& eng, const OpArgs& a, int r) {
         o[8] = s->current_c_i;
     }
     if (a.out_ops) {
-        eng.update_move_params();
+        // the stored values, as OrigamiOrderParamsOutputFile::write prints them (files.cpp:772-778): reading them must
+        // not change what the next move sees
         for (int i = 0; i < eng.OB().n_ops; i++) a.out_ops[(size_t)r * eng.OB().n_ops + i] = eng.BS()->op_val[i];
     }
     if (a.out_staples) {
@@ -397,10 +400,11 @@ LDO_HD void rep_execute(Engine<K>* engp, SysState<K>* st, MoveScratch<K>* ms, Re
             if (a.constraint_check_freq != 0 && step % a.constraint_check_freq == 0) {
                 if (!eng.sys.check_all_constraints()) break;
             }
-            if (visits) {
-                eng.update_move_params();
-                rep_count_grid_visit(eng, visits);
-            }
+            // USGCMCSimulation::update_internal counts the grid bias' STORED point (us_simulation.cpp:262-266): the
+            // parameters as the last move left them. They are current except right after a window exchange, where they
+            // still describe the configuration that left until a move re-evaluates them (an accepted orientation
+            // rotation does not, orientation_movetype.cpp:30-65) - the reference counts that stale point, so do we.
+            if (visits) rep_count_grid_visit(eng, visits);
         }
         aux->step = step;
         break;
@@ -435,6 +439,21 @@ LDO_HD void rep_execute(Engine<K>* engp, SysState<K>* st, MoveScratch<K>* ms, Re
     }
     case OP_REINIT_BIASES: {
         rep_init_biases(eng);
+        break;
+    }
+    case OP_AFTER_WINDOW_SWAP: {
+        // The reference ships the two configurations (us_simulation.cpp:848-863) and rebuilds the receiving system with
+        // set_config -> initialize_staples (origami_system.cpp:327-341, 659-678), which restarts the unique chain counter
+        // from the largest index among the received chains. Same here for the two replicas of an accepted swap.
+        if (aux->window_swapped) {
+            int mx = st->chain_uid[0];
+            for (int w = 1; w < st->n_chains; w++) {
+                int uid = st->chain_uid[st->order[w]];
+                mx = uid > mx ? uid : mx;
+            }
+            st->current_c_i = mx;
+            aux->window_swapped = 0;
+        }
         break;
     }
     case OP_RECOMPUTE: {
@@ -881,6 +900,10 @@ struct WindowExchangeArgs {
     RepAux* aux;
     const double* grid_vals;
     const OpsBiasConst* ob;
+    // replay mode (ldo_set_exchange_tape): the master's test_acceptance draws in the order the reference made them
+    const double* exchange_tape;
+    long long exchange_tape_len;
+    long long* exchange_tape_state;
 };
 
 LDO_HD inline double window_grid_value(const WindowExchangeArgs& x, const BiasState& owner, const int* point) {
@@ -931,7 +954,14 @@ LDO_HD inline void window_exchange_ladder(const WindowExchangeArgs& x, int l) {
             double d1 = window_grid_value(x, a1.bs, p1) - window_grid_value(x, a2.bs, p1);
             double d2 = window_grid_value(x, a2.bs, p2) - window_grid_value(x, a1.bs, p2);
             double p_accept = fmin(1.0, exp(d1 + d2));
-            if (p_accept != 1) {
+            if (p_accept != 1 && x.exchange_tape) {
+                long long* ts = x.exchange_tape_state;
+                double prob = 0.0;
+                if (ts[0] < x.exchange_tape_len) prob = x.exchange_tape[ts[0]++];
+                else ts[2] += 1;
+                accepted = p_accept > prob;
+            }
+            else if (p_accept != 1) {
                 Rng g;
                 g.tape = nullptr;
                 g.key0 = (uint32_t)x.seed;
@@ -949,29 +979,25 @@ LDO_HD inline void window_exchange_ladder(const WindowExchangeArgs& x, int l) {
         int t = w2r[i];
         w2r[i] = w2r[i + 1];
         w2r[i + 1] = t;
-        // swap the window-specific fields
-        for (int b = 0; b < x.ob->n_biases; b++) {
-            int ti = a1.bs.win_min[b];
-            a1.bs.win_min[b] = a2.bs.win_min[b];
-            a2.bs.win_min[b] = ti;
-            ti = a1.bs.win_max[b];
-            a1.bs.win_max[b] = a2.bs.win_max[b];
-            a2.bs.win_max[b] = ti;
-            ti = a1.bs.grid_off[b];
-            a1.bs.grid_off[b] = a2.bs.grid_off[b];
-            a2.bs.grid_off[b] = ti;
-            for (int k = 0; k < LDO_MAX_GRID_DIM; k++) {
-                ti = a1.bs.grid_lo[b][k];
-                a1.bs.grid_lo[b][k] = a2.bs.grid_lo[b][k];
-                a2.bs.grid_lo[b][k] = ti;
-                ti = a1.bs.grid_n[b][k];
-                a1.bs.grid_n[b][k] = a2.bs.grid_n[b][k];
-                a2.bs.grid_n[b][k] = ti;
-            }
-        }
-        int ts = a1.bs.grid_slot;
-        a1.bs.grid_slot = a2.bs.grid_slot;
-        a2.bs.grid_slot = ts;
+        // Everything that belongs to the WINDOW changes hands, because in the reference the rank keeps its
+        // SystemOrderParams / SystemBiases objects, its bias grid and histogram and its random generator while the
+        // configuration moves: the stored parameter and bias values (stale with respect to the new configuration until
+        // the next move re-evaluates them, exactly as in the reference), the window limits, the grid box and slot, and -
+        // in replay mode - the window's tape.
+        BiasState tb = a1.bs;
+        a1.bs = a2.bs;
+        a2.bs = tb;
+        const TapeDraw* tt = a1.rng.tape;
+        a1.rng.tape = a2.rng.tape;
+        a2.rng.tape = tt;
+        long long tl = a1.rng.tape_len;
+        a1.rng.tape_len = a2.rng.tape_len;
+        a2.rng.tape_len = tl;
+        tl = a1.rng.tape_pos;
+        a1.rng.tape_pos = a2.rng.tape_pos;
+        a2.rng.tape_pos = tl;
+        a1.window_swapped = 1;
+        a2.window_swapped = 1;
     }
 }
 
@@ -1153,6 +1179,7 @@ struct EngineImpl: EngineBase {
     TempTables* d_tables = nullptr;
     double* d_table_data = nullptr;
     std::vector<void*> tape_bufs;
+    std::vector<void*> parked_tapes;
     SysState<K>* d_recompute_tmp = nullptr;
     int* d_cfg = nullptr;
     size_t cfg_cap = 0;
@@ -1211,6 +1238,7 @@ struct EngineImpl: EngineBase {
         dev_free(d_exch_tape_state);
         dev_free(d_exch_tape_offsets);
         for (void* p: tape_bufs) dev_free(p);
+        for (void* p: parked_tapes) dev_free(p);
         if (g_const_owner[device % LDO_MAX_DEVICES] == this) g_const_owner[device % LDO_MAX_DEVICES] = nullptr;
 #ifndef LDO_HOSTSIM
         cudaStreamDestroy(stream);
@@ -1632,8 +1660,18 @@ struct EngineImpl: EngineBase {
         static_assert(sizeof(ldo_tape_draw) == sizeof(TapeDraw), "tape layout");
         RepAux aux;
         if (get_aux(replica, 1, &aux)) return -1;
-        dev_free(tape_bufs[replica]);
-        tape_bufs[replica] = nullptr;
+        // free the buffer this replica is reading NOW: window exchange hands tapes from replica to replica
+        for (size_t j = 0; j < tape_bufs.size(); j++) {
+            if (tape_bufs[j] != nullptr && tape_bufs[j] == (const void*)aux.rng.tape) {
+                dev_free(tape_bufs[j]);
+                tape_bufs[j] = nullptr;
+            }
+        }
+        if (tape_bufs[replica] != nullptr) {
+            // still referenced by another replica after a swap: park it, it is freed with the engine
+            parked_tapes.push_back(tape_bufs[replica]);
+            tape_bufs[replica] = nullptr;
+        }
         aux.rng.tape = nullptr;
         aux.rng.tape_len = 0;
         aux.rng.tape_pos = 0;
@@ -1687,6 +1725,7 @@ struct EngineImpl: EngineBase {
     long long* d_exch_tape_state = nullptr;
     long long* d_exch_tape_offsets = nullptr;
     long long exch_tape_rounds = 0;
+    long long exch_tape_total = 0;
     int set_exchange_tape(const double* reals, long long n, const long long* offsets, long long n_rounds) override {
         dev_free(d_exch_tape);
         dev_free(d_exch_tape_offsets);
@@ -1703,6 +1742,7 @@ struct EngineImpl: EngineBase {
         long long st[4] = {0, 0, 0, 0};
         if (dev_h2d(d_exch_tape_state, st, sizeof(st), stream)) return fail(dev_err());
         exch_tape_rounds = n_rounds;
+        exch_tape_total = n;
         return 0;
     }
     int exchange_tape_state(long long* missing, long long* unused) override {
@@ -1734,6 +1774,9 @@ struct EngineImpl: EngineBase {
         x.aux = P.aux;
         x.grid_vals = P.grid_vals;
         x.ob = &d_shared->ob;
+        x.exchange_tape = d_exch_tape;
+        x.exchange_tape_len = d_exch_tape ? exch_tape_total : 0;
+        x.exchange_tape_state = d_exch_tape_state;
 #ifdef LDO_HOSTSIM
         for (int l = 0; l < x.n_ladders; l++) window_exchange_ladder(x, l);
 #else
@@ -2528,12 +2571,10 @@ int ldo_exchange_windows(ldo_engine* e, long long swap_i, int n_ladders, int n_w
         return b->fail("grid_bias is not a Grid bias");
     }
     if (n_window_biases < 0 || n_window_biases > LDO_MAX_BIASES) return b->fail("bad window bias count");
-    // make the order parameters current, then decide, then restart the bias bookkeeping of every replica
+    // the decisions read every window's STORED grid point (get_current_point, us_simulation.cpp:179-181, 773-786)
     OpArgs a;
     memset(&a, 0, sizeof(a));
-    a.op = OP_REFRESH_OPS;
     a.only_replica = -1;
-    if (b->exec(a, true)) return -1;
     WindowExchangeArgs x;
     memset(&x, 0, sizeof(x));
     x.swap_i = swap_i;
@@ -2544,7 +2585,7 @@ int ldo_exchange_windows(ldo_engine* e, long long swap_i, int n_ladders, int n_w
     for (int j = 0; j < n_window_biases; j++) x.window_bias[j] = window_biases[j];
     x.seed = e->seed;
     if (b->window_exchange(x, window_to_replica, attempts, accepts)) return -1;
-    a.op = OP_REINIT_BIASES;
+    a.op = OP_AFTER_WINDOW_SWAP;
     return b->exec(a, true);
 }
 

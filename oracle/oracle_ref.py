@@ -87,6 +87,9 @@ def lib():
         L.oref_pt_tape_len.restype = C.c_longlong
         L.oref_pt_tape_len.argtypes = [C.c_void_p, C.c_int]
         L.oref_pt_tape_copy.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
+        L.oref_pt_num_flags.restype = C.c_longlong
+        L.oref_pt_num_flags.argtypes = [C.c_void_p, C.c_int]
+        L.oref_pt_flags.argtypes = [C.c_void_p, C.c_int, C.c_void_p]
         L.oref_pt_num_marks.restype = C.c_longlong
         L.oref_pt_num_marks.argtypes = [C.c_void_p]
         L.oref_pt_marks.argtypes = [C.c_void_p, C.c_void_p]
@@ -357,6 +360,14 @@ def pt_run(options, n_ranks, seeds, record_tapes=True, workdir=None):
         L.oref_pt_move_stats(h, r, a.ctypes.data, b.ctypes.data)
         out["attempts"].append(a)
         out["accepts"].append(b)
+    # umbrella-sampling drivers: draws of the multi-window driver's own generator (rank 0: the exchange tests)
+    flags = []
+    for r in range(n_ranks):
+        nf = L.oref_pt_num_flags(h, r)
+        f = np.zeros(nf, dtype=np.uint8)
+        if nf:
+            L.oref_pt_flags(h, r, f.ctypes.data)
+        flags.append(f.astype(bool))
     nm = L.oref_pt_num_marks(h)
     marks = np.zeros(nm, dtype=np.int64)
     if nm:
@@ -369,6 +380,8 @@ def pt_run(options, n_ranks, seeds, record_tapes=True, workdir=None):
     keep = np.ones(len(t0), dtype=bool)
     for b, e in marks:
         keep[b:e] = False
+    if len(flags[0]) == len(t0) and len(t0):
+        keep = ~flags[0]
     out["mc_tapes"] = [t0[keep]] + out["tapes"][1:]
     ex = t0[~keep]
     assert np.all(ex["kind"] == 0)

@@ -17,4 +17,7 @@ extern thread_local Tape* g_record;
 extern thread_local Tape* g_replay;
 extern thread_local size_t g_replay_pos;
 extern thread_local bool g_quiet_seed;
+// the RandomGens object every recorded draw came from (PTMWUS: the multi-window driver's own generator serves the
+// exchange tests, the inner simulation's generator the Monte Carlo moves)
+extern thread_local std::vector<const void*>* g_record_src;
 } // namespace oracle_tape

@@ -524,6 +524,8 @@ struct NullBuf: std::streambuf {
 struct PtRank {
     oracle_tape::Tape tape {};
     std::vector<long long> marks {}; // rank 0: [begin, end) tape positions of every attempt_exchange call
+    std::vector<const void*> src {}; // generator of every taped draw (umbrella-sampling drivers)
+    std::vector<unsigned char> exchange_flag {}; // 1: the draw came from the multi-window driver's own generator
     std::vector<int> chain_index, chain_ident, chain_len, pos, ore;
     std::vector<long long> attempts, accepts;
     double energy {0};
@@ -573,9 +575,16 @@ void us_rank_body(parser::InputParameters& params, origami::OrigamiSystem& origa
         sim.m_us_sim->m_random_gens.set_seed(seed + 1000003);
         mc = sim.m_us_sim;
     }
-    if (record) oracle_tape::g_record = &rec.tape;
+    if (record) {
+        oracle_tape::g_record = &rec.tape;
+        oracle_tape::g_record_src = &rec.src;
+    }
     sim.run();
     oracle_tape::g_record = nullptr;
+    oracle_tape::g_record_src = nullptr;
+    if (mc != &sim) {
+        for (auto p: rec.src) rec.exchange_flag.push_back(p == static_cast<const void*>(&sim.m_random_gens) ? 1 : 0);
+    }
     for (auto& mt: mc->m_movetypes) {
         rec.attempts.push_back(mt->get_attempts());
         rec.accepts.push_back(mt->get_accepts());
@@ -655,6 +664,11 @@ long long oref_pt_tape_len(void* vh, int rank) { return static_cast<PtHandle*>(v
 void oref_pt_tape_copy(void* vh, int rank, oracle_tape::Draw* out) {
     auto& t = static_cast<PtHandle*>(vh)->ranks[rank].tape;
     std::memcpy(out, t.data(), t.size() * sizeof(oracle_tape::Draw));
+}
+long long oref_pt_num_flags(void* vh, int rank) { return static_cast<PtHandle*>(vh)->ranks[rank].exchange_flag.size(); }
+void oref_pt_flags(void* vh, int rank, unsigned char* out) {
+    auto& f = static_cast<PtHandle*>(vh)->ranks[rank].exchange_flag;
+    std::memcpy(out, f.data(), f.size());
 }
 long long oref_pt_num_marks(void* vh) { return static_cast<PtHandle*>(vh)->ranks[0].marks.size(); }
 void oref_pt_marks(void* vh, long long* out) {

@@ -22,6 +22,7 @@ thread_local Tape* g_record {nullptr};
 thread_local Tape* g_replay {nullptr};
 thread_local size_t g_replay_pos {0};
 thread_local bool g_quiet_seed {true};
+thread_local std::vector<const void*>* g_record_src {nullptr};
 } // namespace oracle_tape
 
 namespace randomGen {
@@ -56,11 +57,13 @@ double RandomGens::uniform_real() {
             throw std::runtime_error {"tape mismatch: real requested, int taped"};
         }
         if (oracle_tape::g_record != nullptr) oracle_tape::g_record->push_back(d);
+        if (oracle_tape::g_record_src != nullptr) oracle_tape::g_record_src->push_back(this);
         return d.real;
     }
     double v {m_uniform_real_dist(m_random_engine)};
     if (oracle_tape::g_record != nullptr) {
         oracle_tape::g_record->push_back(Draw {0, 0, 0, 0, v});
+        if (oracle_tape::g_record_src != nullptr) oracle_tape::g_record_src->push_back(this);
     }
     return v;
 }
@@ -78,6 +81,7 @@ int RandomGens::uniform_int(int lower, int upper) {
                     std::to_string(upper) + ") requested"};
         }
         if (oracle_tape::g_record != nullptr) oracle_tape::g_record->push_back(d);
+        if (oracle_tape::g_record_src != nullptr) oracle_tape::g_record_src->push_back(this);
         return d.ival;
     }
     int v;
@@ -93,6 +97,7 @@ int RandomGens::uniform_int(int lower, int upper) {
     }
     if (oracle_tape::g_record != nullptr) {
         oracle_tape::g_record->push_back(Draw {1, lower, upper, v, 0.0});
+        if (oracle_tape::g_record_src != nullptr) oracle_tape::g_record_src->push_back(this);
     }
     return v;
 }

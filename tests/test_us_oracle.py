@@ -62,6 +62,62 @@ def us_against_oracle(oracle, tmp_path, lib, sim_type):
     assert visited >= 3  # several grid points were visited and re-weighted
 
 
+def ptmwus_against_oracle(oracle, tmp_path, lib, temp=333, seed0=700):
+    """Replica-exchange multi-window US (PTMWUSGCMCSimulation, us_simulation.cpp:647-706, 770-864): the reference ships
+    configurations between window ranks, the engine relabels window ownership; tapes belong to the windows (the rank's
+    generator stays with the rank), the master's exchange draws are replayed through ldo_set_exchange_tape. Compared: the
+    window -> configuration map of every written exchange (<filebase>_iter-n.swp), the bias files of every window and
+    iteration, and the configuration each window ends with - chain indices included, which pins the restart of the
+    unique chain counter after every shipped configuration (origami_system.cpp:327-341, 659-678)."""
+    kw = dict(temp=temp, iter_swaps=12, exchange_interval=100, equil_steps=3000, max_num_iters=3, configs_output_freq=100, max_D_bias=1.5)
+    ref_opts = us_options(tmp_path, "ref", "ptmw_umbrella_sampling", **kw)
+    ref = oracle.us_run(ref_opts, 3, [seed0 + 13 * r for r in range(3)], workdir=str(tmp_path))
+    sim = Simulation(write_inp(str(tmp_path / "our.inp"), us_options(tmp_path, "our", "ptmw_umbrella_sampling", random_seed=1, **kw)), 3, 0, lib=lib)
+    for r in range(3):
+        sim.engine.attach_tape(r, ref["mc_tapes"][r])
+    ex = ref["exchange_reals"]
+    sim.engine.set_exchange_tape(ex, [0, len(ex)])
+    sim.run()
+    sim.engine.assert_ok()
+    missing, unused = sim.engine.exchange_tape_status()
+    assert missing == 0, (missing, unused)
+    swaps = 0
+    for it in range(3):
+        ref_rows = (tmp_path / f"ref_iter-{it}.swp").read_text().split()
+        our_rows = (tmp_path / f"our_iter-{it}.swp").read_text().split()
+        assert our_rows == ref_rows, (it, our_rows, ref_rows)
+        rows = np.array(ref_rows, dtype=int).reshape(-1, 3)
+        swaps += int((np.diff(rows, axis=0) != 0).any(axis=1).sum())
+        for post in ("_win-0--4", "_win-2--6", "_win-4--8"):
+            for tail in (f"_iter-{it}-inp.biases", f"_iter-{it}.biases"):
+                want, have = read_biases(tmp_path / f"ref{post}{tail}"), read_biases(tmp_path / f"our{post}{tail}")
+                assert want.keys() == have.keys(), (post, tail)
+                for pt in want:
+                    assert abs(want[pt] - have[pt]) <= 1e-6, (post, tail, pt, want[pt], have[pt])
+            assert (tmp_path / f"our{post}.out").read_text() == (tmp_path / f"ref{post}.out").read_text(), post
+    assert swaps >= 2  # configurations did change windows
+    # window w of the reference ends with the configuration our replica w2r[w] holds
+    w2r = [int(x) for x in (tmp_path / "our_iter-2.swp").read_text().split()[-3:]]
+    for w in range(3):
+        got = sim.engine.state(w2r[w])
+        for k in ("chain_index", "chain_ident", "chain_len", "pos", "ore"):
+            assert np.array_equal(got[k], ref["states"][w][k]), (w, k)
+    return len(ex)
+
+
+def test_window_exchange_matches_reference_driver(hostsim_lib, oracle, tmp_path):
+    draws = 0
+    for seed0 in (700, 730):
+        (tmp_path / str(seed0)).mkdir()
+        draws += ptmwus_against_oracle(oracle, tmp_path / str(seed0), hostsim_lib, seed0=seed0)
+    assert draws >= 8  # swap tests decided by a replayed draw (p < 1), not only the p == 1 shortcut
+
+
+@pytest.mark.gpu
+def test_window_exchange_matches_reference_driver_gpu(oracle, tmp_path):
+    ptmwus_against_oracle(oracle, tmp_path, None)
+
+
 @pytest.mark.parametrize("sim_type", ["umbrella_sampling", "mw_umbrella_sampling"])
 def test_bias_update_matches_reference_driver(hostsim_lib, oracle, tmp_path, sim_type):
     us_against_oracle(oracle, tmp_path, hostsim_lib, sim_type)
