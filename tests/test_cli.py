@@ -65,3 +65,40 @@ def test_cli_constant_temperature_batch(tmp_path):
     assert r.returncode == 0, r.stdout + r.stderr
     frames = [f for f in open(tmp_path / "ct-7.trj").read().split("\n\n") if f.strip()]
     assert len(frames) == 3
+
+
+def _n_gpus():
+    try:
+        import torch
+        return torch.cuda.device_count()
+    except Exception:
+        return 0
+
+
+@pytest.mark.gpu
+def test_cli_replica_exchange_over_two_gpus_matches_one_gpu(tmp_path):
+    """--gpus 2: one host thread per GPU, ladders sharded in serpentine order, exchange records all-gathered by NCCL inside
+    the C++ host (ldo_sim_exchange_round). Decisions come from a Philox stream shared by the ranks and every replica keeps
+    its stream wherever it lives, so the run must reproduce the single-GPU run: same .swp, same trajectories."""
+    if _n_gpus() < 2:
+        pytest.skip("needs two GPUs")
+    swaps = 5
+    outs = {}
+    for gpus in (1, 2):
+        d = tmp_path / f"g{gpus}"
+        d.mkdir()
+        opts = ptmc_options(d, swaps)
+        opts.update(num_reps=4, temps=[330.0, 333.0, 336.0, 339.0], chem_pot_mults=[1] * 4, bias_mults=[1] * 4, stacking_mults=[1] * 4)
+        inp = write_inp(str(d / "ptmc.inp"), opts)
+        r = subprocess.run([CLI, "-i", inp, "--replicas", "64", "--gpus", str(gpus)], capture_output=True, text=True, timeout=900)
+        assert r.returncode == 0, r.stdout + r.stderr
+        outs[gpus] = d
+    assert (outs[1] / "ptmc.swp").read_text() == (outs[2] / "ptmc.swp").read_text()
+    # replica k of ladder l: file index l * 4 + k on one GPU; on two GPUs rank (k % 2, reversed in odd pairs) at local
+    # index l * 2 + k // 2, file index rank * 32 + local index
+    for l in (0, 7, 15):
+        for k in range(4):
+            rank = k % 2 if (k // 2) % 2 == 0 else 1 - k % 2
+            one = (outs[1] / f"ptmc-{l * 4 + k}.trj").read_text()
+            two = (outs[2] / f"ptmc-{rank * 32 + l * 2 + k // 2}.trj").read_text()
+            assert one == two, (l, k)
