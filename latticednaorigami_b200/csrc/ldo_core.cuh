@@ -215,8 +215,17 @@ struct __attribute__((aligned(8))) DomRec {
     uint32_t k; // V3::k
     int8_t ore;
     uint8_t state;
-    uint16_t pad_;
+    uint16_t link; // LINK_* flags: where the chain neighbours of this domain are (fixed when the chain is created)
 };
+// Domain::m_forward_domain / m_backward_domain (domain.hpp:30-31): neighbour at d + 1 / d - 1, or - for the two ends
+// of a cyclic scaffold (origami_system.cpp:687-692) - at the other end of the chain
+enum : uint16_t { LINK_FWD = 1, LINK_BAC = 2, LINK_FWD_WRAP = 4, LINK_BAC_WRAP = 8 };
+LDO_HD inline uint16_t chain_link_flags(int i, int len, bool cyclic_scaffold) {
+    unsigned f = (i + 1 < len ? LINK_FWD : 0) | (i > 0 ? LINK_BAC : 0);
+    if (cyclic_scaffold && i + 1 == len) f |= LINK_FWD_WRAP;
+    if (cyclic_scaffold && i == 0) f |= LINK_BAC_WRAP;
+    return (uint16_t)f;
+}
 LDO_HD inline V3 rec_pos(const DomRec& r) {
     V3 v;
     v.k = r.k;
@@ -509,42 +518,29 @@ struct System {
     LDO_HD int chain_base(int c) const { return c == 0 ? 0 : SC().n_scaffold + (c - 1) * SC().lmax; }
     LDO_HD int dom_id(int c, int i) const { return chain_base(c) + i; }
 
-    // Domain::m_forward_domain / m_backward_domain (domain.hpp:30-31; cyclic scaffold origami_system.cpp:687-692)
+    // Domain::m_forward_domain / m_backward_domain: one 16-bit load of the record's link flags
     LDO_HD int fwd(int d) const {
-        int c = S()->dchain[d], i = S()->dindex[d], L = S()->chain_len[c];
-        if (i + 1 < L) return d + 1;
-        if (c == 0 && SC().cyclic) return chain_base(0);
-        return -1;
+        unsigned f = S()->dom[d].link;
+        return (f & LINK_FWD) ? d + 1 : ((f & LINK_FWD_WRAP) ? 0 : -1);
     }
     LDO_HD int bac(int d) const {
-        int c = S()->dchain[d], i = S()->dindex[d];
-        if (i > 0) return d - 1;
-        if (c == 0 && SC().cyclic) return chain_base(0) + S()->chain_len[0] - 1;
-        return -1;
+        unsigned f = S()->dom[d].link;
+        return (f & LINK_BAC) ? d - 1 : ((f & LINK_BAC_WRAP) ? (int)S()->chain_len[0] - 1 : -1);
     }
-    // Domain::operator+ (domain.cpp:9-31)
-#ifdef LDO_INLINE_STEP
-    // single steps (nearly every call) inline; the multi-step walk stays out of line
-    LDO_HD int step(int d, int incr) const {
-        if (incr == 1) return d >= 0 ? fwd(d) : d;
-        if (incr == -1) return d >= 0 ? bac(d) : d;
+    // Domain::operator+ (domain.cpp:9-31): single steps (nearly every call) inline, longer walks out of line
+#ifdef LDO_STEP_OUTLINE // A/B knob (profiles/ab_r2.txt): the single step as an out-of-line function, as in round 1
+    LDO_HDN
+#else
+    LDO_HD
+#endif
+    int step(int d, int incr) const {
+        LDO_COUNT(11);
+        if (d < 0) return d;
+        if (incr == 1) return fwd(d);
+        if (incr == -1) return bac(d);
         return step_n(d, incr);
     }
     LDO_HDN int step_n(int d, int incr) const {
-#else
-    LDO_HDN int step(int d, int incr) const {
-#endif
-        // single steps (nearly every call) without the loops
-        LDO_COUNT(11);
-        if (d < 0) return d;
-        if (incr == 1 || incr == -1) {
-            int c = S()->dchain[d];
-            int i = (int)S()->dindex[d] + incr;
-            int L = S()->chain_len[c];
-            if ((unsigned)i < (unsigned)L) return d + incr;
-            if (c == 0 && SC().cyclic) return incr > 0 ? chain_base(0) : chain_base(0) + L - 1;
-            return -1;
-        }
 #pragma unroll 1
         while (incr > 0 && d >= 0) {
             d = fwd(d);
@@ -1565,6 +1561,7 @@ struct System {
             S()->dom[d].k = 0;
             S()->dom[d].ore = ORE_ZERO;
             S()->dom[d].state = ST_UNASSIGNED;
+            S()->dom[d].link = chain_link_flags(i, len, false);
             S()->bound[d] = -1;
             S()->ident[d] = SC().idents[SC().type_off[type] + i];
             S()->dchain[d] = (uint16_t)c;

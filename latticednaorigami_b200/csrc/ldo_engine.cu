@@ -264,6 +264,7 @@ LDO_HD void rep_load_config(Engine<K>& eng, const OpArgs& a) {
         s->type_count[0] = 1;
         for (int i = 0; i < len; i++) {
             s->dom[i].state = ST_UNASSIGNED;
+            s->dom[i].link = chain_link_flags(i, len, sc->cyclic != 0);
             s->bound[i] = -1;
             s->ident[i] = sc->idents[sc->type_off[0] + i];
             s->dchain[i] = 0;

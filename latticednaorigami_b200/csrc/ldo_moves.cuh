@@ -359,6 +359,16 @@ struct ColdScratch {
     // CTRG: m_c_attempts_wq / m_avail_cis_wq (rg_movetypes.hpp:107-108), written twice and read once per level per move
     uint8_t c_attempts_wq[K::LV + 1];
     unsigned long long avail_wq[K::LV + 1];
+    // Trial-probability slots of every level as computed when the level's configuration was last chosen (growth) or
+    // examined (old configuration): calc_weights meets every level again in exactly that environment - the domains
+    // before it placed, the ones after it unassigned, the same active endpoints - so the six site evaluations (and the
+    // binding evaluations among them) need not be repeated. Pure-function caching: same values, same draws.
+    RgSlot slot_cache[K::LV + 1];
+    uint8_t slot_cached[K::LV + 1];
+    // energy change and stacked-pair change of every level's placement during growth: a recoil takes the placement
+    // back in the environment it was made in, so its energy change is the negative of these (no second evaluation)
+    double set_de[K::LV + 1];
+    short set_sp[K::LV + 1];
 
     // CTCB: chains of the internally bound staple networks (m_regrowth_staples) and the growth work stack
     uint8_t regrow_chain[K::C];
@@ -411,6 +421,8 @@ struct Engine {
         double delta_e, weight, weight_new;
         // slot holding the current domain's trial probabilities; feeler memo bookkeeping
         int cur_slot, memo_level, memo_key, memo_mask, last_pc, last_kind;
+        int slot_cache_on; // calc_weights may take the slots of C()->slot_cache (see there)
+        int in_growth; // inside recoil_regrow's own growth (not a feeler): recoils may reuse the level's cached slot / energy
     };
     Work wk;
 
@@ -1888,7 +1900,22 @@ struct Engine {
         W()->di--;
         W()->d = M()->regrow[W()->di];
         W()->dir = cp_get_dir(W()->d);
-        double de = sys.unassign_domain(W()->d);
+        double de;
+#ifndef LDO_NO_SLOT_CACHE
+        if (W()->in_growth) {
+            // the placement is taken back in the environment it was made in: minus its recorded changes
+            sys.S()->weight_pass = 1;
+            sys.unassign_domain(W()->d);
+            sys.S()->weight_pass = 0;
+            de = -C()->set_de[W()->di];
+            sys.S()->energy += de;
+            sys.S()->num_stacked_pairs -= C()->set_sp[W()->di];
+        }
+        else
+#endif
+        {
+            de = sys.unassign_domain(W()->d);
+        }
         if (M()->n_assigned > 0) M()->n_assigned--;
         rg_restore_endpoints();
         W()->stemd = M()->stem_gp[W()->d] >= 0;
@@ -1904,7 +1931,11 @@ struct Engine {
             W()->avail = M()->avail_q[W()->di];
             W()->ref_d = sys.step(W()->d, -W()->dir);
             W()->cur_slot = W()->di & (LDO_RG_OWN_SLOTS - 1);
-            rg_compute_slot(W()->cur_slot);
+            // a recoil returns to a level whose lower levels have not changed since its slot was computed
+            if (!rg_load_cached_slot(W()->in_growth != 0)) {
+                LDO_COUNT(14);
+                rg_compute_slot(W()->cur_slot);
+            }
         }
         return de;
     }
@@ -2072,6 +2103,32 @@ struct Engine {
         p_c_open = sl.p[pc];
         return true;
     }
+    // Keeps the current level's slot for calc_weights (ColdScratch::slot_cache); lanes copy the 64 bytes together
+    LDO_HD void rg_save_slot() {
+#ifndef LDO_NO_SLOT_CACHE // A/B knob (profiles/ab_r2.txt)
+        if (W()->stemd || sys.SC().cyclic) {
+            C()->slot_cached[W()->di] = 0;
+            return;
+        }
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(&M()->slots[W()->cur_slot]);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(&C()->slot_cache[W()->di]);
+#pragma unroll 1
+        for (int k = LDO_LANE; k < (int)(sizeof(RgSlot) / 4); k += LDO_NLANES) dst[k] = src[k];
+        C()->slot_cached[W()->di] = 1;
+        LDO_SYNCWARP();
+#endif
+    }
+    LDO_HD bool rg_load_cached_slot(bool allowed) {
+        if (!allowed || !C()->slot_cached[W()->di]) return false;
+        LDO_COUNT(12);
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(&C()->slot_cache[W()->di]);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(&M()->slots[W()->cur_slot]);
+        LDO_SYNCWARP();
+#pragma unroll 1
+        for (int k = LDO_LANE; k < (int)(sizeof(RgSlot) / 4); k += LDO_NLANES) dst[k] = src[k];
+        LDO_SYNCWARP();
+        return true;
+    }
     // recoil_regrow (rg:177-231)
     LDO_HDN double rg_recoil_regrow() {
         double de = 0;
@@ -2079,6 +2136,7 @@ struct Engine {
         W()->d = M()->regrow[0];
         W()->dir = cp_get_dir(W()->d);
         M()->c_opens[0] = 1;
+        W()->in_growth = 1;
         rg_prepare_for_growth();
         int recoils = 0;
 #pragma unroll 1
@@ -2104,7 +2162,14 @@ struct Engine {
             }
             if (c_open) {
                 if (recoils != 0) recoils--;
-                de += rg_set_config(W()->d, p, o);
+                rg_save_slot();
+                {
+                    int sp0 = sys.S()->num_stacked_pairs;
+                    double dset = rg_set_config(W()->d, p, o);
+                    C()->set_de[W()->di] = dset;
+                    C()->set_sp[W()->di] = (short)(sys.S()->num_stacked_pairs - sp0);
+                    de += dset;
+                }
                 M()->c_attempts_q[W()->di] = (uint8_t)W()->c_attempts;
                 M()->avail_q[W()->di] = W()->avail;
                 M()->c_opens[W()->di] = p_c_open;
@@ -2120,10 +2185,12 @@ struct Engine {
                 de += rg_prepare_for_regrowth();
             }
         }
+        W()->in_growth = 0;
         return de;
     }
     // test_config_avail (rg:422-480)
     LDO_HDN bool rg_test_config_avail() {
+        LDO_COUNT(13);
         int feels = 0;
         if (feels == W()->max_recoils || W()->di == M()->n_regrow - 1) return true;
         rg_prepare_for_growth();
@@ -2211,7 +2278,7 @@ struct Engine {
                 W()->memo_level = -1;
                 W()->memo_mask = 0;
                 W()->cur_slot = W()->di & (LDO_RG_OWN_SLOTS - 1);
-                if (catt != W()->max_c_attempts) rg_compute_slot(W()->cur_slot);
+                if (catt != W()->max_c_attempts && !rg_load_cached_slot(W()->slot_cache_on != 0)) rg_compute_slot(W()->cur_slot);
                 // With one feeler level (max_num_recoils == 1) an open trial configuration on an EMPTY
                 // site only needs "does the next domain have an open configuration"; that depends on the
                 // site, not on the orientation, so after the first orientation of a site has been
@@ -2402,14 +2469,29 @@ struct Engine {
             const DomRec r = C()->oldc[W()->d];
             V3 p = rec_pos(r);
             W()->stemd = M()->stem_gp[W()->d] >= 0;
-            M()->c_opens[W()->di] = rg_calc_p_config_open(p, r.ore);
+            C()->slot_cached[W()->di] = 0;
+            bool from_slot = false;
+            if (!W()->stemd) {
+                W()->dir = cp_get_dir(W()->d);
+                W()->ref_d = sys.step(W()->d, -W()->dir);
+                V3 rel0 = p - rec_pos(sys.S()->dom[W()->ref_d]);
+                int pc0 = ore_code(rel0);
+                if (W()->slot_cache_on && pc0 < 6 && r.ore >= 0 && r.ore < 6 && !sys.SC().cyclic) {
+                    // the six sites of this level evaluated once, for the open probability of the old configuration here
+                    // and for calc_weights afterwards (only when both run with the same active endpoints: the caller says)
+                    W()->cur_slot = W()->di & (LDO_RG_OWN_SLOTS - 1);
+                    rg_compute_slot(W()->cur_slot);
+                    M()->c_opens[W()->di] = rg_slot_p(M()->slots[W()->cur_slot], pc0 * 6 + r.ore);
+                    rg_save_slot();
+                    from_slot = true;
+                }
+            }
+            if (!from_slot) M()->c_opens[W()->di] = rg_calc_p_config_open(p, r.ore);
             rg_set_config(W()->d, p, r.ore);
             if (W()->stemd) {
                 M()->avail_q[W()->di] = 0;
             }
             else {
-                W()->dir = cp_get_dir(W()->d);
-                W()->ref_d = sys.step(W()->d, -W()->dir);
                 V3 rel = p - rec_pos(C()->oldc[W()->ref_d]);
                 int pc = ore_code(rel);
                 int ci = pc * 6 + r.ore;
@@ -2442,6 +2524,8 @@ struct Engine {
         // from the reference's by the rounding of terms that cancel (it agrees to 1e-12, as everywhere).
         const double e_old = sys.S()->energy;
         const int sp_old = sys.S()->num_stacked_pairs;
+        W()->slot_cache_on = 0;
+        W()->in_growth = 0;
         W()->delta_e += rg_unassign_and_save_domains();
         W()->delta_e += rg_recoil_regrow();
         if (M()->rejected) return false;
@@ -2462,12 +2546,18 @@ struct Engine {
         rg_unassign_and_save_domains();
         cp_reset_active_endpoints();
         if (remove_first_a) cp_remove_active_endpoint(first_dom);
+        // the growth above ran from the endpoints setup_constraints left (the first domain's removed, rg:134-145); this
+        // pass starts from the same set when its own guard removes it too
+        W()->slot_cache_on = remove_first_a ? 1 : 0;
         rg_calc_weights();
 
         // old-configuration weights
         rg_unassign_domains();
         cp_reset_active_endpoints();
         if (remove_first_b) cp_remove_active_endpoint(first_dom);
+        // calc_old_c_opens and the weight pass after it see the same endpoints only when their guards agree (they do not
+        // for the contiguous move on a linear scaffold, App. A2)
+        W()->slot_cache_on = remove_first_a == remove_first_b ? 1 : 0;
         rg_calc_old_c_opens();
         // setup_for_calc_old_weights (rg:155-163)
         W()->weight_new = W()->weight;
@@ -2480,8 +2570,10 @@ struct Engine {
         cp_reset_active_endpoints();
         if (remove_first_a) cp_remove_active_endpoint(first_dom);
         rg_calc_weights();
+        W()->slot_cache_on = 0;
 
         // test_rg_acceptance (rg:515-533)
+        LDO_COUNT(15);
         double ratio = W()->weight_new / W()->weight * exp(-W()->delta_e);
         bool accepted = test_acceptance(ratio);
         if (accepted) {
@@ -2505,6 +2597,7 @@ struct Engine {
         W()->weight_new = 1;
         W()->max_recoils = md.max_num_recoils;
         W()->max_c_attempts = md.max_c_attempts;
+        W()->slot_cache_on = 0;
         W()->memo_level = -1;
         W()->memo_key = -1;
         W()->memo_mask = 0;

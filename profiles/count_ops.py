@@ -14,7 +14,8 @@ import conftest  # noqa: E402
 from latticednaorigami_b200.binding import Simulation  # noqa: E402
 
 NAMES = ["occupant", "table_put", "table_erase", "bind_domain(compl.)", "check_stacking", "eval_place", "walks_remain_seg",
-         "rg_site_lookup", "rg_compute_slot", "rg_fill_feeler_memo", "rg_feeler_general", "step"]
+         "rg_site_lookup", "rg_compute_slot", "rg_fill_feeler_memo", "rg_feeler_general", "step", "slot cache hits", "rg_test_config_avail",
+         "recoil slot recomputes", "CTRG moves reaching the weight passes"]
 lib = conftest.load_hostsim()
 counts = (ctypes.c_longlong * 16).in_dll(lib, "ldo_dbg_counts")
 tmp = tempfile.mkdtemp()
