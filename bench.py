@@ -406,8 +406,7 @@ def tile_states(eng, states_of_local, n_units, unit, seed, subsequence_of):
         eng.set_state(b, st["chain_index"], st["chain_ident"], st["chain_len"], np.asarray(st["pos"]).reshape(-1, 3),
                       np.asarray(st["ore"]).reshape(-1, 3))
     blob = eng.checkpoint_save(first=0, count=unit)
-    for g in range(1, n_units):
-        eng.checkpoint_load(blob, first=g * unit, count=unit)
+    eng.checkpoint_load(np.tile(blob, n_units), first=0, count=n_units * unit)  # one upload, one unpack launch
     eng.synchronize()
     eng.seed_subsequences(seed, [subsequence_of(r) for r in range(n_units * unit)])
 
