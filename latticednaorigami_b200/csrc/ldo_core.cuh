@@ -60,6 +60,16 @@ __device__ __forceinline__ int ldo_laneid() {
 #if defined(LDO_HOSTSIM)
 extern "C" long long ldo_dbg_counts[16];
 #define LDO_COUNT(i) (ldo_dbg_counts[i]++)
+#if defined(LDO_CALLER_PROFILE) // profiles/step_callers.py: histogram of the call sites of System::step
+extern "C" unsigned long long ldo_dbg_callers[2 * 4096];
+static __attribute__((noinline)) void ldo_dbg_note_caller(void* ra) {
+    unsigned long long a = (unsigned long long)ra;
+    unsigned h = (unsigned)((a * 0x9E3779B97F4A7C15ull) >> 52);
+    while (ldo_dbg_callers[2 * h] && ldo_dbg_callers[2 * h] != a) h = (h + 1) & 4095;
+    ldo_dbg_callers[2 * h] = a;
+    ldo_dbg_callers[2 * h + 1]++;
+}
+#endif
 #else
 #define LDO_COUNT(i) ((void)0)
 #endif
@@ -527,14 +537,21 @@ struct System {
         unsigned f = S()->dom[d].link;
         return (f & LINK_BAC) ? d - 1 : ((f & LINK_BAC_WRAP) ? (int)S()->chain_len[0] - 1 : -1);
     }
-    // Domain::operator+ (domain.cpp:9-31): single steps (nearly every call) inline, longer walks out of line
-#ifdef LDO_STEP_OUTLINE // A/B knob (profiles/ab_r2.txt): the single step as an out-of-line function, as in round 1
-    LDO_HDN
-#else
+    // Domain::operator+ (domain.cpp:9-31). Out of line: inlining the single step at its ~150 call sites made the kernel
+    // 4 % slower (instruction-cache bound, profiles/ab_r2.txt); LDO_STEP_INLINE keeps the A/B twin buildable.
+#ifdef LDO_STEP_INLINE
     LDO_HD
+#else
+    LDO_HDN
+#endif
+#if defined(LDO_CALLER_PROFILE)
+    __attribute__((noinline))
 #endif
     int step(int d, int incr) const {
         LDO_COUNT(11);
+#if defined(LDO_CALLER_PROFILE)
+        ldo_dbg_note_caller(__builtin_return_address(0));
+#endif
         if (d < 0) return d;
         if (incr == 1) return fwd(d);
         if (incr == -1) return bac(d);
@@ -1443,7 +1460,9 @@ struct System {
     }
 
     // OrigamiSystem::set_checked_domain_config (origami_system.cpp:478-515)
-    LDO_HDN double set_checked_domain_config_base(int d, V3 p, int o) {
+    // `known`: the result System::eval_place returned for this very placement in the present environment (recoil growth
+    // keeps it with its trial slot): a complementary binding is then committed without a second evaluation.
+    LDO_HDN double set_checked_domain_config_base(int d, V3 p, int o, const DeltaConfig* known) {
         commit_place(d, p, o);
         if (S()->weight_pass) {
             S()->num_unassigned--;
@@ -1451,6 +1470,13 @@ struct System {
         }
         double delta_e = 0;
         int st = S()->dom[d].state;
+        if (st == ST_BOUND && known) {
+            // (stacking + hybridization) + mean-field term: the sum below, in an order that rounds the same
+            S()->num_stacked_pairs += known->stacked;
+            S()->energy += known->e;
+            S()->num_unassigned--;
+            return known->e;
+        }
         if (st == ST_MISBOUND) {
             delta_e += hyb_energy(d, S()->bound[d]);
         }
@@ -1519,8 +1545,8 @@ struct System {
     // OrigamiSystemWithBias::set_checked_domain_config / unassign_domain (origami_system.cpp:928-945); set_domain_config
     // (:947-954) only adds calc_one_domain, which is always 0 (see above)
     LDO_HD double set_domain_config(int d, V3 p, int o) { return set_domain_config_base(d, p, o); }
-    LDO_HD double set_checked_domain_config(int d, V3 p, int o) {
-        double e = set_checked_domain_config_base(d, p, o);
+    LDO_HD double set_checked_domain_config(int d, V3 p, int o, const DeltaConfig* known = nullptr) {
+        double e = set_checked_domain_config_base(d, p, o, known);
         if (pd_active(d)) pd_update(d);
         return e;
     }

@@ -26,6 +26,9 @@
 using namespace ldo;
 #ifdef LDO_HOSTSIM
 extern "C" long long ldo_dbg_counts[16] = {0};
+#if defined(LDO_CALLER_PROFILE)
+extern "C" unsigned long long ldo_dbg_callers[2 * 4096] = {0};
+#endif
 #endif
 
 // ---------------------------------------------------------------------------------------------

@@ -243,10 +243,14 @@ LDO_HD inline int nth_set_bit36(unsigned long long m, int n) {
 //   kind 0: site blocked or binding violates a constraint -> p = 0 for all orientations
 //   kind 1: empty site -> p (1, or 0 when no ideal walk remains) for every orientation
 //   kind 2: site holds an unbound domain -> p for the single opposing orientation `ore`, else 0
+// bind_pc / bind_e / bind_sp: the site whose complementary binding was evaluated last (kind 2), with the energy and
+// stacked-pair change System::eval_place returned for it; committing that configuration reuses them (-1: none).
 struct RgSlot {
     double p[6];
+    double bind_e;
     uint8_t kind[6];
     int8_t ore[6];
+    int8_t bind_pc, bind_sp;
 };
 #define LDO_RG_OWN_SLOTS 4
 #define LDO_RG_SLOTS (LDO_RG_OWN_SLOTS + 6)
@@ -458,6 +462,11 @@ struct Engine {
     }
 
     // ---- RNG (random_gens.cpp:29-49) ----
+#ifdef LDO_RNG_OUTLINE // A/B knob (profiles/ab_r2.txt): the two draw functions as out-of-line calls
+#define LDO_DRAW_FN LDO_HDN
+#else
+#define LDO_DRAW_FN LDO_HD
+#endif
     // Refill of the 4-word buffer is the only out-of-line part of the Philox path, so that the draw
     // functions stay a few instructions long inside the trial loops (instruction-cache footprint)
     LDO_HDN void philox_refill() {
@@ -504,7 +513,7 @@ struct Engine {
         g->tape_pos++;
         return t.ival;
     }
-    LDO_HD double uniform_real() {
+    LDO_DRAW_FN double uniform_real() {
         if (LDO_TAPE_MODE(RNG())) return tape_real();
         uint32_t hi = next_word();
         uint32_t lo = next_word();
@@ -518,7 +527,7 @@ struct Engine {
         while ((uint32_t)mm < t) mm = (unsigned long long)next_word() * n;
         return mm;
     }
-    LDO_HD int uniform_int(int lo, int hi) {
+    LDO_DRAW_FN int uniform_int(int lo, int hi) {
         if (LDO_TAPE_MODE(RNG())) return tape_int(lo, hi);
         uint32_t n = (uint32_t)(hi - lo) + 1u;
         unsigned long long mm = (unsigned long long)next_word() * n;
@@ -1701,8 +1710,8 @@ struct Engine {
         M()->eq_npos = 0;
     }
     // set_config (rg:233-244)
-    LDO_HDN double rg_set_config(int dd, V3 p, int o) {
-        double de = sys.set_checked_domain_config(dd, p, o);
+    LDO_HDN double rg_set_config(int dd, V3 p, int o, const DeltaConfig* known = nullptr) {
+        double de = sys.set_checked_domain_config(dd, p, o, known);
         push_assigned(dd);
         cp_update_endpoints(W()->d);
         eq_push_erased();
@@ -1790,12 +1799,21 @@ struct Engine {
             }
         }
     }
-    LDO_HDN void rg_site_bind(int dom, bool dom_is_stem, V3 r, int o, const EpOverlay* ov, int& kind, double& pv) {
+    LDO_HDN void rg_site_bind(int dom, bool dom_is_stem, V3 r, int o, const EpOverlay* ov, int& kind, double& pv, DeltaConfig& dc) {
         kind = 0;
         pv = 0;
         int ns, j;
-        DeltaConfig dc = sys.eval_place(dom, r, o, &ns, &j);
+        dc = sys.eval_place(dom, r, o, &ns, &j);
         if (j >= 0) rg_site_finish(dom, dom_is_stem, r, j, dc, ov, kind, pv);
+    }
+    // Records the binding just evaluated at site k of a slot for the commit (RgSlot::bind_*)
+    LDO_HD void rg_note_bind(RgSlot& sl, int k, int kind, const DeltaConfig& dc) {
+#ifndef LDO_NO_BIND_REUSE // A/B knob (profiles/ab_r2.txt)
+        if (kind != 2) return;
+        sl.bind_pc = (int8_t)k;
+        sl.bind_sp = (int8_t)dc.stacked;
+        sl.bind_e = dc.e;
+#endif
     }
     // Evaluates the six neighbour sites of the reference domain for the current domain: lookups one site per
     // lane, then the pending bindings in turn.
@@ -1812,16 +1830,19 @@ struct Engine {
             sl.ore[k] = (int8_t)o;
             sl.p[k] = pv;
         }
+        sl.bind_pc = -1;
         LDO_SYNCWARP();
 #pragma unroll 1
         for (int k = 0; k < 6; k++) {
             if (sl.kind[k] != 3) continue;
             int kind;
             double pv;
-            rg_site_bind(W()->d, W()->stemd != 0, refp + ore_vec(k), sl.ore[k], nullptr, kind, pv);
+            DeltaConfig dc;
+            rg_site_bind(W()->d, W()->stemd != 0, refp + ore_vec(k), sl.ore[k], nullptr, kind, pv, dc);
             LDO_SYNCWARP();
             sl.kind[k] = (uint8_t)kind;
             sl.p[k] = pv;
+            rg_note_bind(sl, k, kind, dc);
             LDO_SYNCWARP();
         }
     }
@@ -1843,6 +1864,7 @@ struct Engine {
             // a feeler that can reach the parent's own site would bind to the parent: orientation dependent
             if (!fref_is_parent && abssum(refp + ore_vec(pc) - frefp) == 1) continue;
             mask |= 1 << pc;
+            M()->slots[LDO_RG_OWN_SLOTS + pc].bind_pc = -1;
         }
         EpOverlay ov;
         ov.rm_chain = sys.chain(W()->d);
@@ -1886,10 +1908,12 @@ struct Engine {
                 V3 r = (fref_is_parent ? q : frefp) + ore_vec(k);
                 int kind;
                 double pv;
-                rg_site_bind(fd, false, r, sl.ore[k], &ov, kind, pv);
+                DeltaConfig dc;
+                rg_site_bind(fd, false, r, sl.ore[k], &ov, kind, pv, dc);
                 LDO_SYNCWARP();
                 sl.kind[k] = (uint8_t)kind;
                 sl.p[k] = pv;
+                rg_note_bind(sl, k, kind, dc);
                 LDO_SYNCWARP();
             }
         }
@@ -2103,6 +2127,16 @@ struct Engine {
         p_c_open = sl.p[pc];
         return true;
     }
+    // The evaluation of the binding the trial just selected, when the current slot still holds it (else null)
+    LDO_HD const DeltaConfig* rg_known_bind(DeltaConfig& known) const {
+        if (W()->stemd || W()->last_kind != 2) return nullptr;
+        const RgSlot& sl = M()->slots[W()->cur_slot];
+        if (sl.bind_pc < 0 || sl.bind_pc != W()->last_pc) return nullptr;
+        known.e = sl.bind_e;
+        known.stacked = sl.bind_sp;
+        known.violated = false;
+        return &known;
+    }
     // Keeps the current level's slot for calc_weights (ColdScratch::slot_cache); lanes copy the 64 bytes together
     LDO_HD void rg_save_slot() {
 #ifndef LDO_NO_SLOT_CACHE // A/B knob (profiles/ab_r2.txt)
@@ -2165,7 +2199,8 @@ struct Engine {
                 rg_save_slot();
                 {
                     int sp0 = sys.S()->num_stacked_pairs;
-                    double dset = rg_set_config(W()->d, p, o);
+                    DeltaConfig known;
+                    double dset = rg_set_config(W()->d, p, o, rg_known_bind(known));
                     C()->set_de[W()->di] = dset;
                     C()->set_sp[W()->di] = (short)(sys.S()->num_stacked_pairs - sp0);
                     de += dset;
@@ -2229,7 +2264,8 @@ struct Engine {
                     c_avail = true;
                     break;
                 }
-                rg_set_config(W()->d, p, o);
+                DeltaConfig known;
+                rg_set_config(W()->d, p, o, rg_known_bind(known));
                 M()->c_attempts_q[W()->di] = (uint8_t)W()->c_attempts;
                 M()->avail_q[W()->di] = W()->avail;
                 rg_prepare_for_growth();
