@@ -30,9 +30,17 @@
 // Out-of-line device functions: keeps the per-replica kernel's code size (instruction cache) and
 // ptxas time under control; the call overhead is negligible next to the shared-memory latency chains.
 #define LDO_HDN __host__ __device__ __noinline__
+// Small helpers with many call sites: out of line unless LDO_INLINE_HELPERS (A/B twin, profiles/ab_r2.txt) - the kernel
+// is bound by instruction supply and their inlined copies were a tenth of its code
+#ifdef LDO_INLINE_HELPERS
+#define LDO_HDC __host__ __device__
+#else
+#define LDO_HDC __host__ __device__ __noinline__
+#endif
 #else
 #define LDO_HD
 #define LDO_HDN
+#define LDO_HDC
 #endif
 
 // Warps (= replicas) per block of the staged kernel (the in-place kernel uses 4-warp blocks)
@@ -1460,9 +1468,7 @@ struct System {
     }
 
     // OrigamiSystem::set_checked_domain_config (origami_system.cpp:478-515)
-    // `known`: the result System::eval_place returned for this very placement in the present environment (recoil growth
-    // keeps it with its trial slot): a complementary binding is then committed without a second evaluation.
-    LDO_HDN double set_checked_domain_config_base(int d, V3 p, int o, const DeltaConfig* known) {
+    LDO_HDN double set_checked_domain_config_base(int d, V3 p, int o) {
         commit_place(d, p, o);
         if (S()->weight_pass) {
             S()->num_unassigned--;
@@ -1470,13 +1476,6 @@ struct System {
         }
         double delta_e = 0;
         int st = S()->dom[d].state;
-        if (st == ST_BOUND && known) {
-            // (stacking + hybridization) + mean-field term: the sum below, in an order that rounds the same
-            S()->num_stacked_pairs += known->stacked;
-            S()->energy += known->e;
-            S()->num_unassigned--;
-            return known->e;
-        }
         if (st == ST_MISBOUND) {
             delta_e += hyb_energy(d, S()->bound[d]);
         }
@@ -1545,12 +1544,12 @@ struct System {
     // OrigamiSystemWithBias::set_checked_domain_config / unassign_domain (origami_system.cpp:928-945); set_domain_config
     // (:947-954) only adds calc_one_domain, which is always 0 (see above)
     LDO_HD double set_domain_config(int d, V3 p, int o) { return set_domain_config_base(d, p, o); }
-    LDO_HD double set_checked_domain_config(int d, V3 p, int o, const DeltaConfig* known = nullptr) {
-        double e = set_checked_domain_config_base(d, p, o, known);
+    LDO_HDC double set_checked_domain_config(int d, V3 p, int o) {
+        double e = set_checked_domain_config_base(d, p, o);
         if (pd_active(d)) pd_update(d);
         return e;
     }
-    LDO_HD double unassign_domain(int d) {
+    LDO_HDC double unassign_domain(int d) {
         double e = unassign_domain_base(d);
         if (pd_active(d)) pd_update(d);
         return e;

@@ -243,14 +243,10 @@ LDO_HD inline int nth_set_bit36(unsigned long long m, int n) {
 //   kind 0: site blocked or binding violates a constraint -> p = 0 for all orientations
 //   kind 1: empty site -> p (1, or 0 when no ideal walk remains) for every orientation
 //   kind 2: site holds an unbound domain -> p for the single opposing orientation `ore`, else 0
-// bind_pc / bind_e / bind_sp: the site whose complementary binding was evaluated last (kind 2), with the energy and
-// stacked-pair change System::eval_place returned for it; committing that configuration reuses them (-1: none).
 struct RgSlot {
     double p[6];
-    double bind_e;
     uint8_t kind[6];
     int8_t ore[6];
-    int8_t bind_pc, bind_sp;
 };
 #define LDO_RG_OWN_SLOTS 4
 #define LDO_RG_SLOTS (LDO_RG_OWN_SLOTS + 6)
@@ -427,6 +423,8 @@ struct Engine {
         int cur_slot, memo_level, memo_key, memo_mask, last_pc, last_kind;
         int slot_cache_on; // calc_weights may take the slots of C()->slot_cache (see there)
         int in_growth; // inside recoil_regrow's own growth (not a feeler): recoils may reuse the level's cached slot / energy
+        int sp_start; // stacked pairs / energy before the move (mc_step: rejected moves restore them)
+        double e_start;
     };
     Work wk;
 
@@ -462,13 +460,7 @@ struct Engine {
     }
 
     // ---- RNG (random_gens.cpp:29-49) ----
-#ifdef LDO_RNG_OUTLINE // A/B knob (profiles/ab_r2.txt): the two draw functions as out-of-line calls
-#define LDO_DRAW_FN LDO_HDN
-#else
-#define LDO_DRAW_FN LDO_HD
-#endif
-    // Refill of the 4-word buffer is the only out-of-line part of the Philox path, so that the draw
-    // functions stay a few instructions long inside the trial loops (instruction-cache footprint)
+    // The two draw functions are out-of-line calls (LDO_HDC): inlined at their ~60 call sites they were 42 KB of code
     LDO_HDN void philox_refill() {
         Rng* g = RNG();
         unsigned long long c = g->counter;
@@ -513,7 +505,7 @@ struct Engine {
         g->tape_pos++;
         return t.ival;
     }
-    LDO_DRAW_FN double uniform_real() {
+    LDO_HDC double uniform_real() {
         if (LDO_TAPE_MODE(RNG())) return tape_real();
         uint32_t hi = next_word();
         uint32_t lo = next_word();
@@ -527,7 +519,7 @@ struct Engine {
         while ((uint32_t)mm < t) mm = (unsigned long long)next_word() * n;
         return mm;
     }
-    LDO_DRAW_FN int uniform_int(int lo, int hi) {
+    LDO_HDC int uniform_int(int lo, int hi) {
         if (LDO_TAPE_MODE(RNG())) return tape_int(lo, hi);
         uint32_t n = (uint32_t)(hi - lo) + 1u;
         unsigned long long mm = (unsigned long long)next_word() * n;
@@ -598,7 +590,7 @@ struct Engine {
         return 0;
     }
     // SystemOrderParams::update_move_params (order_params.cpp:595-601)
-    LDO_HD void update_move_params() {
+    LDO_HDC void update_move_params() {
 #pragma unroll 1
         for (int i = 0; i < OB().n_ops; i++) {
             if (OB().ops[i].per_domain) continue; // updated with every domain placement (System::pd_update)
@@ -653,11 +645,11 @@ struct Engine {
     LDO_HD double total_bias() const { return BS()->move_update_bias * CTL().bias_mult; }
 
     // ---- MCMovetype shared helpers (movetypes.cpp:98-158) ----
-    LDO_HD int select_random_domain() {
+    LDO_HDC int select_random_domain() {
         int idx = uniform_int(0, sys.S()->num_domains - 1);
         return sys.domain_by_flat_index(idx);
     }
-    LDO_HD bool test_acceptance(double p_ratio) {
+    LDO_HDC bool test_acceptance(double p_ratio) {
         double p_accept = fmin(1.0, p_ratio) * M()->modifier;
         if (p_accept == 1) return true;
         return p_accept > uniform_real();
@@ -669,14 +661,14 @@ struct Engine {
         M()->rejected = 0;
         M()->modifier = 1;
     }
-    LDO_HD void push_assigned(int dd) {
+    LDO_HDC void push_assigned(int dd) {
         if (M()->n_assigned >= MoveScratch<K>::A) {
             sys.fail(LDO_ERR_CAPACITY, 1);
             return;
         }
         M()->assigned[M()->n_assigned++] = (short)dd;
     }
-    LDO_HD void push_modified(int dd) {
+    LDO_HDC void push_modified(int dd) {
         if (M()->n_modified >= K::LV) {
             sys.fail(LDO_ERR_CAPACITY, 2);
             return;
@@ -1710,8 +1702,8 @@ struct Engine {
         M()->eq_npos = 0;
     }
     // set_config (rg:233-244)
-    LDO_HDN double rg_set_config(int dd, V3 p, int o, const DeltaConfig* known = nullptr) {
-        double de = sys.set_checked_domain_config(dd, p, o, known);
+    LDO_HDN double rg_set_config(int dd, V3 p, int o) {
+        double de = sys.set_checked_domain_config(dd, p, o);
         push_assigned(dd);
         cp_update_endpoints(W()->d);
         eq_push_erased();
@@ -1767,7 +1759,7 @@ struct Engine {
     // orientation that binds it). rg_site_bind finishes a pending site and is executed by the whole warp, because
     // System::eval_place enters the candidate pair into the domain records while the potential is evaluated.
     // What a binding with energy change dc to domain j contributes (rg:326-343)
-    LDO_HD void rg_site_finish(int dom, bool dom_is_stem, V3 r, int j, const DeltaConfig& dc, const EpOverlay* ov, int& kind, double& pv) {
+    LDO_HDC void rg_site_finish(int dom, bool dom_is_stem, V3 r, int j, const DeltaConfig& dc, const EpOverlay* ov, int& kind, double& pv) {
         kind = 0;
         pv = 0;
         if (!dc.violated && cp_walks_remain(dom, r, ov)) {
@@ -1799,21 +1791,12 @@ struct Engine {
             }
         }
     }
-    LDO_HDN void rg_site_bind(int dom, bool dom_is_stem, V3 r, int o, const EpOverlay* ov, int& kind, double& pv, DeltaConfig& dc) {
+    LDO_HDN void rg_site_bind(int dom, bool dom_is_stem, V3 r, int o, const EpOverlay* ov, int& kind, double& pv) {
         kind = 0;
         pv = 0;
         int ns, j;
-        dc = sys.eval_place(dom, r, o, &ns, &j);
+        DeltaConfig dc = sys.eval_place(dom, r, o, &ns, &j);
         if (j >= 0) rg_site_finish(dom, dom_is_stem, r, j, dc, ov, kind, pv);
-    }
-    // Records the binding just evaluated at site k of a slot for the commit (RgSlot::bind_*)
-    LDO_HD void rg_note_bind(RgSlot& sl, int k, int kind, const DeltaConfig& dc) {
-#ifndef LDO_NO_BIND_REUSE // A/B knob (profiles/ab_r2.txt)
-        if (kind != 2) return;
-        sl.bind_pc = (int8_t)k;
-        sl.bind_sp = (int8_t)dc.stacked;
-        sl.bind_e = dc.e;
-#endif
     }
     // Evaluates the six neighbour sites of the reference domain for the current domain: lookups one site per
     // lane, then the pending bindings in turn.
@@ -1830,19 +1813,16 @@ struct Engine {
             sl.ore[k] = (int8_t)o;
             sl.p[k] = pv;
         }
-        sl.bind_pc = -1;
         LDO_SYNCWARP();
 #pragma unroll 1
         for (int k = 0; k < 6; k++) {
             if (sl.kind[k] != 3) continue;
             int kind;
             double pv;
-            DeltaConfig dc;
-            rg_site_bind(W()->d, W()->stemd != 0, refp + ore_vec(k), sl.ore[k], nullptr, kind, pv, dc);
+            rg_site_bind(W()->d, W()->stemd != 0, refp + ore_vec(k), sl.ore[k], nullptr, kind, pv);
             LDO_SYNCWARP();
             sl.kind[k] = (uint8_t)kind;
             sl.p[k] = pv;
-            rg_note_bind(sl, k, kind, dc);
             LDO_SYNCWARP();
         }
     }
@@ -1864,7 +1844,6 @@ struct Engine {
             // a feeler that can reach the parent's own site would bind to the parent: orientation dependent
             if (!fref_is_parent && abssum(refp + ore_vec(pc) - frefp) == 1) continue;
             mask |= 1 << pc;
-            M()->slots[LDO_RG_OWN_SLOTS + pc].bind_pc = -1;
         }
         EpOverlay ov;
         ov.rm_chain = sys.chain(W()->d);
@@ -1908,12 +1887,10 @@ struct Engine {
                 V3 r = (fref_is_parent ? q : frefp) + ore_vec(k);
                 int kind;
                 double pv;
-                DeltaConfig dc;
-                rg_site_bind(fd, false, r, sl.ore[k], &ov, kind, pv, dc);
+                rg_site_bind(fd, false, r, sl.ore[k], &ov, kind, pv);
                 LDO_SYNCWARP();
                 sl.kind[k] = (uint8_t)kind;
                 sl.p[k] = pv;
-                rg_note_bind(sl, k, kind, dc);
                 LDO_SYNCWARP();
             }
         }
@@ -2008,7 +1985,7 @@ struct Engine {
         return fmin(1.0, exp(-de));
     }
     // test_config_open (rg:345-361)
-    LDO_HD bool rg_test_config_open(double p) {
+    LDO_HDC bool rg_test_config_open(double p) {
         p = fmin(1.0, p);
         if (p == 1) return true;
         return p > uniform_real();
@@ -2127,16 +2104,6 @@ struct Engine {
         p_c_open = sl.p[pc];
         return true;
     }
-    // The evaluation of the binding the trial just selected, when the current slot still holds it (else null)
-    LDO_HD const DeltaConfig* rg_known_bind(DeltaConfig& known) const {
-        if (W()->stemd || W()->last_kind != 2) return nullptr;
-        const RgSlot& sl = M()->slots[W()->cur_slot];
-        if (sl.bind_pc < 0 || sl.bind_pc != W()->last_pc) return nullptr;
-        known.e = sl.bind_e;
-        known.stacked = sl.bind_sp;
-        known.violated = false;
-        return &known;
-    }
     // Keeps the current level's slot for calc_weights (ColdScratch::slot_cache); lanes copy the 64 bytes together
     LDO_HD void rg_save_slot() {
 #ifndef LDO_NO_SLOT_CACHE // A/B knob (profiles/ab_r2.txt)
@@ -2199,8 +2166,7 @@ struct Engine {
                 rg_save_slot();
                 {
                     int sp0 = sys.S()->num_stacked_pairs;
-                    DeltaConfig known;
-                    double dset = rg_set_config(W()->d, p, o, rg_known_bind(known));
+                    double dset = rg_set_config(W()->d, p, o);
                     C()->set_de[W()->di] = dset;
                     C()->set_sp[W()->di] = (short)(sys.S()->num_stacked_pairs - sp0);
                     de += dset;
@@ -2264,8 +2230,7 @@ struct Engine {
                     c_avail = true;
                     break;
                 }
-                DeltaConfig known;
-                rg_set_config(W()->d, p, o, rg_known_bind(known));
+                rg_set_config(W()->d, p, o);
                 M()->c_attempts_q[W()->di] = (uint8_t)W()->c_attempts;
                 M()->avail_q[W()->di] = W()->avail;
                 rg_prepare_for_growth();
@@ -3577,9 +3542,24 @@ struct Engine {
     }
     LDO_HD bool mc_step() {
         int i = select_movetype();
+        W()->e_start = sys.S()->energy;
+        W()->sp_start = sys.S()->num_stacked_pairs;
         bool accepted = attempt(i);
         if (sys.S()->status != LDO_OK) return false;
         if (!accepted) {
+#ifndef LDO_NO_FAST_REVERT // A/B knob (profiles/ab_r2.txt)
+            if (!LDO_SERIAL_DRAWS()) {
+                // Production mode: the old configuration is put back without evaluating the potential and the energy
+                // and stacked-pair count return to their values before the move - exactly, where the reference's
+                // domain-by-domain sum (followed under replay) returns them up to rounding.
+                sys.S()->weight_pass = 1;
+                reset_origami();
+                sys.S()->weight_pass = 0;
+                sys.S()->energy = W()->e_start;
+                sys.S()->num_stacked_pairs = W()->sp_start;
+            }
+            else
+#endif
             reset_origami();
             update_move_params();
             calc_move_bias();

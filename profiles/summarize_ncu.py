@@ -1,9 +1,12 @@
 """Summarises an ncu report of the run kernel: headline raw metrics, stall mix and a per-function table
 (instructions / samples / stall reasons) built from the SASS page and the cubin symbol table.
-    python profiles/summarize_ncu.py gpurun_out/prof.ncu-rep > profiles/ncu_<name>.txt
+    python profiles/summarize_ncu.py gpurun_out/prof.ncu-rep [library of the profiled build] > profiles/ncu_<name>.txt
+The symbol table must come from the build that was profiled (default: the library in the tree).
 """
 import csv, subprocess, collections, bisect, sys
 rep = sys.argv[1]
+import os
+libso = os.path.abspath(sys.argv[2]) if len(sys.argv) > 2 else os.path.abspath('latticednaorigami_b200/libldo_b200.so')
 raw = subprocess.run(['ncu','-i',rep,'--page','raw','--csv'],capture_output=True,text=True).stdout
 rows = list(csv.reader(raw.splitlines()))
 hdr, units, vals = rows[0], rows[1], rows[2]
@@ -14,7 +17,7 @@ sass = subprocess.run(['ncu','-i',rep,'--page','source','--csv','--print-source'
 rows = list(csv.reader(sass.splitlines()))
 hdr = rows[1]; idx = {h:i for i,h in enumerate(hdr)}
 syms=[]
-out = subprocess.run("D=$(mktemp -d) && cd $D && cuobjdump -xelf all $OLDPWD/latticednaorigami_b200/libldo_b200.so >/dev/null 2>&1; readelf -sW ldo_engine.sm_100a.cubin 2>/dev/null | awk '$4==\"FUNC\" || $4==\"NOTYPE\" {print $2, $3, $8}' | grep 'k_exec_stagedIN3ldo4CapsILi80E'", shell=True, capture_output=True, text=True).stdout
+out = subprocess.run("D=$(mktemp -d) && cd $D && cuobjdump -xelf all " + libso + " >/dev/null 2>&1; readelf -sW *.sm_100a.cubin 2>/dev/null | awk '$4==\"FUNC\" || $4==\"NOTYPE\" {print $2, $3, $8}' | grep 'k_exec_stagedIN3ldo4CapsILi80E'", shell=True, capture_output=True, text=True).stdout
 for line in out.splitlines():
     v,size,name = line.split()[:3]; syms.append((int(v,16), name))
 syms.sort(); starts=[s[0] for s in syms]
