@@ -351,6 +351,37 @@ int ldo_exchange_windows(ldo_engine* e, long long swap_i, int n_ladders, int n_w
  * quantities ([n][4 + n_staple_types] doubles), so the all-gather runs device-to-device. */
 int ldo_exchange_buffers(ldo_engine* e, int n_global, void** send_dev, void** recv_dev, int* doubles_per_replica);
 
+/* ---- exact enumeration of small systems --------------------------------------------
+ * One call enumerates every conformation of ONE growthpoint set of ONE staple set - what
+ * ConformationalEnumerator::enumerate() does (enumerate.cpp:218-258, 378-664) - on all replica slots of the engine at once
+ * (each slot is a worker that takes a share of the recursion tree; replica states are not modified). Staple sets and
+ * growthpoint sets (StapleEnumerator / GrowthpointEnumerator, enumerate.cpp:813-1133) are enumerated by the caller:
+ * ldo_sim_run does it for simulation_type=enumerate. Chains are numbered 0 (scaffold) and 1 + k (k-th staple of
+ * staple_type[]). Returned per state (the values of the order parameters out_ops[], sorted): the sum over its leaves of
+ * exp(-energy - bias) x multiplier, WITHOUT the staple-set prefix (reduced fugacity and orientation factors,
+ * enumerate.cpp:264,276), which the caller applies; sums[] = {partition sum, sum of energy x weight, sum of bias x weight,
+ * number of configurations} in the same convention. */
+typedef struct ldo_enum_job {
+    int n_staples;
+    const int* staple_type;      /* [n_staples] staple identities (1-based types) */
+    int n_stack;
+    const int* stack_chain;      /* [n_stack] domains in the order create_domains_stack pops them (enumerate.cpp:591-637) */
+    const int* stack_d;
+    int n_growthpoints;          /* m_growthpoints: old domain -> new (staple) domain */
+    const int* gp_old_chain;
+    const int* gp_old_d;
+    const int* gp_new_chain;
+    const int* gp_new_d;
+    int n_ident;                 /* identities run over -n_ident .. n_ident */
+    const int* ident_unassigned; /* [2 n_ident + 1] m_identities_to_num_unassigned at the start, index identity + n_ident */
+    int overcount;               /* 0 MaxTwoDomainOvercountCalculator, 1 MisbindingOnlyOvercountCalculator (enumerate.cpp:83-159) */
+    int n_out_ops;
+    const int* out_ops;          /* [n_out_ops <= 6] indices of the order parameters that label a state (ops_to_output) */
+    int split_depth;             /* levels of the recursion dealt out as prefixes; <= 0: chosen by the engine */
+} ldo_enum_job;
+int ldo_enumerate_conformations(ldo_engine* e, const ldo_enum_job* job, int max_keys, int* n_keys, int* keys /* [max_keys][n_out_ops] */,
+                                double* weights /* [max_keys] */, double* sums /* [4] */, long long* n_leaves /* may be NULL */);
+
 #ifdef __cplusplus
 }
 #endif

@@ -46,7 +46,7 @@ int ldo_comm_unique_id(void* id_out_128_bytes);
 int ldo_sim_comm_init(ldo_sim* s, const void* unique_id_128_bytes);
 
 /* Runs the driver selected by simulation_type (constant_temp, annealing, t_/ut_/hut_/st_/2d_parallel_tempering,
- * umbrella_sampling, mw_/ptmw_umbrella_sampling) to completion, writing the reference's output files for every
+ * umbrella_sampling, mw_/ptmw_umbrella_sampling, enumerate) to completion, writing the reference's output files for every
  * replica (`<filebase>-<replica>.*` when there is more than one). With n_ranks > 1 (exchange types, after
  * ldo_sim_comm_init) every rank calls it; rank 0 writes the .swp file. Returns 0 or -1. */
 int ldo_sim_run(ldo_sim* s);
@@ -64,6 +64,12 @@ int ldo_sim_exchange_advance(ldo_sim* s);
 int ldo_sim_exchange_apply(ldo_sim* s, long long swap_i, const double* dependent_all);
 /* m_q_to_repi of every ladder ([n_ladders][num_reps]) and the per-pair counters. */
 int ldo_sim_exchange_state(ldo_sim* s, int* slot_to_replica, long long* attempts, long long* accepts);
+
+/* simulation_type=enumerate (enumerate.cpp:19-81): ldo_sim_run enumerates the staple sets and growthpoint sets on the
+ * host as the reference does and every conformation of each on the device (ldo_enumerate_conformations: all replica slots
+ * of the simulation are workers), writes <filebase>.weights and prints the reference's summary. After the run:
+ * out = {number of configurations (with multiplicities), average energy, average bias, conformations visited}. */
+int ldo_sim_enumeration_summary(ldo_sim* s, double* out);
 
 /* Introspection used by tests and tools */
 int ldo_sim_num_temps(ldo_sim* s);

@@ -20,6 +20,7 @@ ENGINE_SYMBOLS = [
     "ldo_get_move_stats", "ldo_get_run_timing", "ldo_recompute_energies", "ldo_check_all_constraints", "ldo_center",
     "ldo_set_exchange_ladder", "ldo_exchange_collect", "ldo_exchange_pt", "ldo_exchange_pt_2d", "ldo_exchange_acceptance_p", "ldo_get_reduced_staple_u", "ldo_set_step", "ldo_exchange_buffers",
     "ldo_exchange_windows", "ldo_exchange_collect_async", "ldo_exchange_state_set", "ldo_exchange_state_get", "ldo_exchange_pt_async", "ldo_set_exchange_tape", "ldo_exchange_tape_status", "ldo_set_reference_draw_order", "ldo_build_info", "ldo_launch_count", "ldo_state_bytes", "ldo_checkpoint_size", "ldo_checkpoint_save", "ldo_checkpoint_load",
+    "ldo_enumerate_conformations",
 ]
 HOST_SYMBOLS = [
     "ldo_host_last_error", "ldo_comm_unique_id", "ldo_sim_comm_init", "ldo_sim_exchange_round", "ldo_sim_create", "ldo_sim_destroy", "ldo_sim_engine", "ldo_sim_run",
@@ -27,7 +28,7 @@ HOST_SYMBOLS = [
     "ldo_sim_num_order_params", "ldo_sim_order_param_tag", "ldo_sim_num_movetypes",
     "ldo_sim_movetype_label", "ldo_sim_num_staple_types", "ldo_sim_step", "ldo_sim_pair_energies",
     "ldo_sim_init_energies", "ldo_host_nn_unitless_thermo", "ldo_host_longest_contig_complement",
-    "ldo_host_no_walks", "ldo_host_energy_tables", "ldo_host_inp_value",
+    "ldo_host_no_walks", "ldo_host_energy_tables", "ldo_host_inp_value", "ldo_sim_enumeration_summary",
 ]
 
 STATUS_NAMES = {
@@ -127,6 +128,8 @@ def bind(L):
         "ldo_checkpoint_size": (C.c_ulong, [vp]),
         "ldo_checkpoint_save": (i, [vp, i, i, vp]),
         "ldo_checkpoint_load": (i, [vp, i, i, vp]),
+        "ldo_enumerate_conformations": (i, [vp, vp, i, vp, vp, vp, vp, vp]),
+        "ldo_sim_enumeration_summary": (i, [vp, vp]),
         "ldo_host_last_error": (C.c_char_p, []),
         "ldo_sim_create": (vp, [C.c_char_p, i, i, i, i]),
         "ldo_sim_destroy": (None, [vp]),
@@ -418,6 +421,13 @@ class Simulation:
     @property
     def step(self):
         return self.L.ldo_sim_step(self.h)
+
+    def enumeration_summary(self):
+        """After run() with simulation_type=enumerate: configurations (with multiplicities), average energy, average
+        bias, conformations visited."""
+        out = np.zeros(4)
+        self._check(self.L.ldo_sim_enumeration_summary(self.h, _ptr(out)))
+        return {"num_configs": out[0], "average_energy": out[1], "average_bias": out[2], "leaves": int(out[3])}
 
     def exchange_round(self, swap_i):
         """One whole exchange round on the engine's stream (moves, collection, NCCL all-gather, decisions)."""

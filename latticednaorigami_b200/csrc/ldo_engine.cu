@@ -17,10 +17,12 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <map>
 #include <string>
 #include <vector>
 
 #include "ldo_moves.cuh"
+#include "ldo_enum.cuh"
 #include "../../include/ldo_b200.h"
 
 using namespace ldo;
@@ -470,6 +472,17 @@ LDO_HD void rep_execute(Engine<K>* engp, SysState<K>* st, MoveScratch<K>* ms, Re
     }
 }
 
+// Exact enumeration (ldo_enum.cuh): replica r is worker r of the job; its state is scratch and is never written back
+template <class K>
+LDO_HD void rep_enumerate(Engine<K>* engp, SysState<K>* st, MoveScratch<K>* ms, RepAux* aux, const DevPtrs<K>& P, const EnumJob* job, EnumAcc* accs, int r) {
+    rep_init_engine(*engp, st, ms, aux, P, r);
+    rep_refresh_stack_energy(st, P.shared, aux->ctl);
+    LDO_SYNCWARP();
+    Enumerator<K> en(*engp, *job, accs[r]);
+    en.run(r);
+    LDO_SYNCWARP();
+}
+
 // ---------------------------------------------------------------------------------------------
 // Kernels: one warp per replica
 // ---------------------------------------------------------------------------------------------
@@ -585,6 +598,22 @@ __global__ void __launch_bounds__(32 * LDO_BLOCK_WARPS, LDO_MIN_BLOCKS) k_exec_s
         }
         __syncwarp();
     }
+}
+
+// Enumeration workers: launch shape and shared-memory layout of the staged kernel (the accessors address the replica
+// through the same window offsets), one worker per warp; the recursion runs on the per-thread stack
+// (cudaLimitStackSize is raised by the host around the launch).
+template <class K>
+__global__ void __launch_bounds__(32 * LDO_BLOCK_WARPS) k_enum(DevPtrs<K> P, const EnumJob* job, EnumAcc* accs, int n_workers) {
+    WarpSmem<K>* ws = reinterpret_cast<WarpSmem<K>*>(ldo_smem_raw);
+    int warp = threadIdx.x >> 5;
+    WarpSmem<K>& w = ws[warp];
+    RepAux* aux = reinterpret_cast<RepAux*>(w.aux);
+    int r = blockIdx.x * LDO_BLOCK_WARPS + warp;
+    if (r >= n_workers) return;
+    warp_copy16(&w.st, &P.states[r]);
+    warp_copy_bytes16(w.aux, &P.aux[r], LDO_AUX_HOT_BYTES);
+    rep_enumerate<K>(&w.eng, &w.st, &w.ms, aux, P, job, accs, r);
 }
 
 // Reports where the dynamic shared memory of a launch shaped like the staged kernel starts in the CTA's window
@@ -1159,6 +1188,7 @@ struct EngineBase {
     virtual size_t state_bytes() = 0;
     virtual int get_blobs(int first, int count, void* host) = 0;
     virtual int put_blobs(int first, int count, const void* host) = 0;
+    virtual int enumerate(EnumJob& job, std::vector<EnumAcc>& accs) = 0;
     int domain_update_biases = 0; // ldo_set_domain_update_biases
     long long launches = 0; // kernels launched so far (ldo_launch_count)
     long long const_version = 0;
@@ -1241,6 +1271,8 @@ struct EngineImpl: EngineBase {
         dev_free(d_exch_tape);
         dev_free(d_exch_tape_state);
         dev_free(d_exch_tape_offsets);
+        dev_free(d_enum_job);
+        dev_free(d_enum_acc);
         for (void* p: tape_bufs) dev_free(p);
         for (void* p: parked_tapes) dev_free(p);
         if (g_const_owner[device % LDO_MAX_DEVICES] == this) g_const_owner[device % LDO_MAX_DEVICES] = nullptr;
@@ -1398,6 +1430,55 @@ struct EngineImpl: EngineBase {
         launches++;
         if (sync && dev_sync(stream)) return fail(dev_err());
         return 0;
+#endif
+    }
+
+    // One growthpoint set of the exact enumeration: every replica slot is a worker (ldo_enum.cuh)
+    EnumJob* d_enum_job = nullptr;
+    EnumAcc* d_enum_acc = nullptr;
+    int enumerate(EnumJob& job, std::vector<EnumAcc>& accs) override {
+        if (!P.tables) return fail("temperature tables not set");
+        job.n_workers = R;
+        accs.assign(R, EnumAcc());
+        memset(accs.data(), 0, sizeof(EnumAcc) * R);
+#ifdef LDO_HOSTSIM
+        for (int r = 0; r < R; r++) {
+            SysState<K>* tmp = STAGED ? d_recompute_tmp : &d_recompute_tmp[r];
+            memcpy(tmp, &P.states[r], sizeof(SysState<K>));
+            RepAux aux = P.aux[r];
+            MoveScratch<K>* ms = STAGED ? P.scratch : &P.scratch[r];
+            Engine<K> eng;
+            rep_enumerate<K>(&eng, tmp, ms, &aux, P, &job, accs.data(), r);
+        }
+        return 0;
+#else
+        if constexpr (!STAGED) {
+            return fail("exact enumeration runs on systems that fit the shared-memory replica (snodin class and smaller)");
+        }
+        else {
+            if (upload_constants()) return -1;
+            if (!d_enum_job && dev_malloc((void**)&d_enum_job, sizeof(EnumJob))) return fail(dev_err());
+            if (!d_enum_acc && dev_malloc((void**)&d_enum_acc, sizeof(EnumAcc) * R)) return fail(dev_err());
+            if (dev_h2d(d_enum_job, &job, sizeof(EnumJob), stream)) return fail(dev_err());
+            if (chk(cudaMemsetAsync(d_enum_acc, 0, sizeof(EnumAcc) * R, stream))) return fail(dev_err());
+            // the recursion is three frames per placed domain deep
+            size_t old_stack = 0, want = 2048 + 1024 * (size_t)job.n_stack;
+            if (chk(cudaDeviceGetLimit(&old_stack, cudaLimitStackSize))) return fail(dev_err());
+            if (want > old_stack) {
+                if (dev_sync(stream) || chk(cudaDeviceSetLimit(cudaLimitStackSize, want))) return fail(dev_err());
+            }
+            int wpb = warps_per_block;
+            size_t smem = sizeof(WarpSmem<K>) * wpb;
+            if (chk(cudaFuncSetAttribute(k_enum<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem))) return fail(dev_err());
+            k_enum<K><<<(R + wpb - 1) / wpb, wpb * 32, smem, stream>>>(P, d_enum_job, d_enum_acc, R);
+            if (chk(cudaGetLastError())) return fail(dev_err());
+            launches++;
+            if (dev_d2h(accs.data(), d_enum_acc, sizeof(EnumAcc) * R, stream) || dev_sync(stream)) return fail(dev_err());
+            if (want > old_stack) {
+                if (chk(cudaDeviceSetLimit(cudaLimitStackSize, old_stack))) return fail(dev_err());
+            }
+            return 0;
+        }
 #endif
     }
 
@@ -2619,6 +2700,93 @@ int ldo_checkpoint_load(ldo_engine* e, int first, int count, const void* host) {
 
 int ldo_exchange_buffers(ldo_engine* e, int n_global, void** send_dev, void** recv_dev, int* doubles_per_replica) {
     return e->b->exchange_buffers(n_global, send_dev, recv_dev, doubles_per_replica);
+}
+
+int ldo_enumerate_conformations(ldo_engine* e, const ldo_enum_job* j, int max_keys, int* n_keys, int* keys, double* weights, double* sums, long long* n_leaves) {
+    EngineBase* b = e->b;
+    if (j->n_staples < 0 || j->n_staples > LDO_ENUM_MAX_STAPLES) return b->fail("enumeration: too many staples in the set");
+    if (j->n_stack < 2 || j->n_stack > LDO_ENUM_MAX_DOMAINS) return b->fail("enumeration: between 2 and 32 domains");
+    if (j->n_growthpoints < 0 || j->n_growthpoints > LDO_ENUM_MAX_STAPLES) return b->fail("enumeration: too many growthpoints");
+    if (j->n_out_ops < 1 || j->n_out_ops > LDO_ENUM_MAX_OPS) return b->fail("enumeration: between 1 and 6 order parameters to output");
+    if (j->n_ident < 0 || j->n_ident > LDO_ENUM_MAX_IDENT) return b->fail("enumeration: domain identities out of range");
+    if (j->split_depth > LDO_ENUM_MAX_SPLIT) return b->fail("enumeration: split depth above 6");
+    EnumJob job;
+    memset(&job, 0, sizeof(job));
+    job.n_staples = j->n_staples;
+    for (int k = 0; k < j->n_staples; k++) {
+        if (j->staple_type[k] < 1 || j->staple_type[k] >= b->shared.sc.n_types) return b->fail("enumeration: staple type out of range");
+        job.staple_type[k] = j->staple_type[k];
+    }
+    job.n_stack = j->n_stack;
+    for (int k = 0; k < j->n_stack; k++) {
+        if (j->stack_chain[k] < 0 || j->stack_chain[k] > j->n_staples || j->stack_d[k] < 0) return b->fail("enumeration: bad domain in the stack");
+        job.stack_chain[k] = (short)j->stack_chain[k];
+        job.stack_d[k] = (short)j->stack_d[k];
+    }
+    job.n_gp = j->n_growthpoints;
+    for (int k = 0; k < j->n_growthpoints; k++) {
+        job.gp_old_chain[k] = (short)j->gp_old_chain[k];
+        job.gp_old_d[k] = (short)j->gp_old_d[k];
+        job.gp_new_chain[k] = (short)j->gp_new_chain[k];
+        job.gp_new_d[k] = (short)j->gp_new_d[k];
+    }
+    for (int i = -j->n_ident; i <= j->n_ident; i++) job.ident_unassigned[i + LDO_ENUM_MAX_IDENT] = j->ident_unassigned[i + j->n_ident];
+    job.overcount = j->overcount;
+    job.n_out_ops = j->n_out_ops;
+    for (int k = 0; k < j->n_out_ops; k++) {
+        if (j->out_ops[k] < 0 || j->out_ops[k] >= b->shared.ob.n_ops) return b->fail("enumeration: order parameter index out of range");
+        job.out_op[k] = j->out_ops[k];
+    }
+    // levels of the recursion: one per domain of the stack but the first, a growthpoint pair shares one
+    int levels = j->n_stack - 1 - j->n_growthpoints;
+    // enough prefixes to give every worker about eight, so that subtrees of unequal size even out
+    int split = 0;
+    if (j->split_depth > 0) {
+        split = j->split_depth;
+    }
+    else if (b->R > 1) {
+        long long n = 1;
+        while (split < levels && split < LDO_ENUM_MAX_SPLIT && n < 8LL * b->R) {
+            n *= 36;
+            split++;
+        }
+    }
+    job.split_depth = split;
+    job.n_prefixes = 1;
+    for (int l = 0; l < split; l++) job.n_prefixes *= 36;
+    std::vector<EnumAcc> accs;
+    if (b->enumerate(job, accs)) return -1;
+    // merge in worker order, keys sorted at the end: the result does not depend on the number of workers beyond rounding
+    std::map<std::vector<int>, double> table;
+    double z = 0, avg_e = 0, avg_b = 0, n_configs = 0;
+    long long leaves = 0;
+    for (const EnumAcc& a: accs) {
+        if (a.status != 0) {
+            char msg[96];
+            snprintf(msg, sizeof msg, "enumeration failed on the device: status %d detail %d", a.status, a.status_detail);
+            return b->fail(msg);
+        }
+        z += a.z;
+        avg_e += a.avg_e;
+        avg_b += a.avg_b;
+        n_configs += a.n_configs;
+        leaves += a.n_leaves;
+        for (int k = 0; k < a.n_keys; k++) table[std::vector<int>(a.keys[k], a.keys[k] + job.n_out_ops)] += a.w[k];
+    }
+    if ((int)table.size() > max_keys) return b->fail("enumeration: more states than the caller's table holds");
+    int k = 0;
+    for (auto const& kv: table) {
+        for (int i = 0; i < job.n_out_ops; i++) keys[k * job.n_out_ops + i] = kv.first[i];
+        weights[k] = kv.second;
+        k++;
+    }
+    *n_keys = k;
+    sums[0] = z;
+    sums[1] = avg_e;
+    sums[2] = avg_b;
+    sums[3] = n_configs;
+    if (n_leaves) *n_leaves = leaves;
+    return 0;
 }
 
 } // extern "C"

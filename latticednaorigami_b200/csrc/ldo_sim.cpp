@@ -2,6 +2,7 @@
 // ConstantTGCMCSimulation::run, AnnealingGCMCSimulation::run and PTGCMCSimulation::run, with the
 // reference's text output files. See include/ldo_host.h for the reference file:line of each piece.
 
+#include <algorithm>
 #include <chrono>
 #include <cstdlib>
 #include <cmath>
@@ -61,6 +62,10 @@ struct ldo_sim {
     std::vector<int> ops_out_idx;
     // umbrella sampling (us_simulation.hpp:60-150)
     bool is_us {false}, is_mwus {false}, is_ptmwus {false};
+    bool is_enum {false}; // simulation_type=enumerate (enumerate.cpp)
+    long long enum_leaves {0}; // conformations visited by the last enumeration / their number with multiplicities
+    double enum_num_configs {0};
+    double enum_average_energy {0}, enum_average_bias {0};
     int n_windows {1};
     int grid_bias {-1};
     std::vector<int> window_biases;
@@ -721,6 +726,354 @@ NcclApi& nccl() {
     return api;
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Exact enumeration (simulation_type=enumerate; enumerate.cpp). The staple sets (StapleEnumerator, :1070-1133) and the
+// growthpoint sets (GrowthpointEnumerator and its two subclasses, :813-1068) are enumerated here exactly as the reference
+// does, duplicates included and skipped the same way; every growthpoint set is handed to the device
+// (ldo_enumerate_conformations), which grows all conformations on all replica slots at once. A domain is (unique chain
+// index, domain index) like the reference's Domain*.
+// ---------------------------------------------------------------------------------------------------------------
+struct HostEnumerator {
+    using Dom = std::pair<int, int>;
+    using Growthpoint = std::pair<std::pair<int, int>, std::pair<int, int>>;
+    ldo_sim& s;
+    InputParameters const& p;
+    std::vector<std::vector<int>> const& identities;
+    bool quiet;
+    // ConformationalEnumerator state
+    std::vector<std::pair<int, int>> live; // staples present: (unique chain index, identity), in the order they were added
+    int next_c_i {0};
+    std::map<int, std::vector<int>> identity_to_indices;
+    std::map<Dom, Dom> conf_growthpoints;
+    std::map<int, int> ident_unassigned;
+    long double prefix {1};
+    std::map<std::vector<int>, long double> state_weights;
+    long double partition_f {0}, average_energy {0}, average_bias {0}, num_configs {0};
+    long long leaves {0};
+    // GrowthpointEnumerator state
+    bool misbinding;
+    std::vector<std::pair<int, int>> staples; // identity, copies
+    std::vector<std::vector<Growthpoint>> enumerated_growthpoints;
+    std::vector<Growthpoint> growthpoints;
+    std::vector<Dom> unbound_system_domains; // MisbindingGrowthpointEnumerator
+    std::vector<std::vector<Dom>> comp_system_domains; // NoMisbindingGrowthpointEnumerator, per staple identity
+    // StapleEnumerator state
+    int num_staple_combos {0}, cur_max_total_staples {0}, max_type_staples {0};
+
+    explicit HostEnumerator(ldo_sim& sim):
+            s {sim}, p {sim.params}, identities {sim.sysfile->identities}, quiet {std::getenv("LDO_QUIET") != nullptr} {
+        if (p.m_enumerate_staples_only) {
+            throw NotImplemented {"enumerate_staples_only is not available on the device path (scaffold conformations are enumerated)"};
+        }
+        if (p.m_max_staple_size != 2 && p.m_misbinding_pot != "Disallowed") throw NotImplemented {"No enumerator available for system"}; // :26-34
+        misbinding = p.m_misbinding_pot != "Disallowed";
+        for (int d_ident: identities[0]) ident_unassigned[d_ident] = 1; // :204-206
+        int scaffold_len {static_cast<int>(identities[0].size())};
+        if (misbinding) {
+            for (int d {0}; d != scaffold_len; d++) unbound_system_domains.push_back({0, d}); // :875
+        }
+        else {
+            // complementary_scaffold_domains (origami_system.cpp:125-128, 630-655): per staple domain, the first
+            // scaffold domain of the opposite identity
+            for (size_t c_ident {1}; c_ident != identities.size(); c_ident++) {
+                comp_system_domains.push_back({});
+                for (int sd: identities[c_ident]) {
+                    for (int d {0}; d != scaffold_len; d++) {
+                        if (sd == -identities[0][d]) {
+                            comp_system_domains.back().push_back({0, d});
+                            break;
+                        }
+                    }
+                }
+            }
+        }
+    }
+
+    int chain_number(int c_i) const { // device numbering: 0 scaffold, 1 + k for the k-th staple present
+        if (c_i == 0) return 0;
+        for (size_t k {0}; k != live.size(); k++)
+            if (live[k].first == c_i) return static_cast<int>(k) + 1;
+        throw std::logic_error("enumeration: unknown chain");
+    }
+    int chain_identity(int c_i) const { return c_i == 0 ? 0 : live[chain_number(c_i) - 1].second; }
+
+    // ---- ConformationalEnumerator bookkeeping (:260-342) ----
+    void add_staple(int staple) {
+        prefix *= p.m_staple_M; // m_reduced_fugacity (origami_system.cpp:58)
+        next_c_i++;
+        live.push_back({next_c_i, staple});
+        size_t len {identities[staple].size()};
+        prefix /= static_cast<long double>(std::pow(6, 2 * len - 1));
+        identity_to_indices[staple].push_back(next_c_i);
+        for (int d_ident: identities[staple]) {
+            if (ident_unassigned.count(d_ident) == 0) ident_unassigned[d_ident] = 1;
+            else ident_unassigned[d_ident]++;
+        }
+    }
+    void remove_staple(int staple) {
+        prefix /= p.m_staple_M;
+        size_t len {identities[staple].size()};
+        prefix *= static_cast<long double>(std::pow(6, 2 * len - 1));
+        int c_i {identity_to_indices[staple].back()};
+        identity_to_indices[staple].pop_back();
+        for (size_t k {0}; k != live.size(); k++) {
+            if (live[k].first == c_i) {
+                live.erase(live.begin() + k);
+                break;
+            }
+        }
+        for (int d_ident: identities[staple]) ident_unassigned[d_ident]--;
+    }
+    std::vector<Dom> add_growthpoint(int new_c_ident, int new_d_i, Dom old_domain) {
+        int new_c_i {identity_to_indices[new_c_ident].back()};
+        identity_to_indices[new_c_ident].pop_back();
+        conf_growthpoints[old_domain] = {new_c_i, new_d_i};
+        std::vector<Dom> rest;
+        for (int d {0}; d != static_cast<int>(identities[new_c_ident].size()); d++)
+            if (d != new_d_i) rest.push_back({new_c_i, d});
+        return rest;
+    }
+    void remove_growthpoint(Dom old_domain) {
+        Dom new_domain {conf_growthpoints[old_domain]};
+        conf_growthpoints.erase(old_domain);
+        identity_to_indices[chain_identity(new_domain.first)].push_back(new_domain.first);
+    }
+
+    // create_domains_stack / create_staple_stack (:591-637): the order in which the domains are popped
+    void staple_stack(Dom domain, std::vector<Dom>& order) {
+        int len {static_cast<int>(identities[chain_identity(domain.first)].size())};
+        order.push_back(domain);
+        for (int d_i {domain.second + 1}; d_i != len; d_i++) {
+            Dom d {domain.first, d_i};
+            order.push_back(d);
+            if (conf_growthpoints.count(d)) staple_stack(conf_growthpoints[d], order);
+        }
+        for (int d_i {domain.second - 1}; d_i != -1; d_i--) {
+            Dom d {domain.first, d_i};
+            order.push_back(d);
+            if (conf_growthpoints.count(d)) staple_stack(conf_growthpoints[d], order);
+        }
+    }
+
+    // ConformationalEnumerator::enumerate (:218-258) - on the device
+    void enumerate_conformations() {
+        std::vector<Dom> order;
+        for (int d {0}; d != static_cast<int>(identities[0].size()); d++) {
+            order.push_back({0, d});
+            if (conf_growthpoints.count({0, d})) staple_stack(conf_growthpoints[{0, d}], order);
+        }
+        std::vector<int> staple_type, stack_chain, stack_d, go_c, go_d, gn_c, gn_d;
+        for (auto const& st: live) staple_type.push_back(st.second);
+        for (Dom const& d: order) {
+            stack_chain.push_back(chain_number(d.first));
+            stack_d.push_back(d.second);
+        }
+        for (auto const& gp: conf_growthpoints) {
+            go_c.push_back(chain_number(gp.first.first));
+            go_d.push_back(gp.first.second);
+            gn_c.push_back(chain_number(gp.second.first));
+            gn_d.push_back(gp.second.second);
+        }
+        int n_ident {0};
+        for (auto const& chain: identities)
+            for (int d_ident: chain) n_ident = std::max(n_ident, std::abs(d_ident));
+        std::vector<int> unassigned(2 * n_ident + 1, 0);
+        for (auto const& kv: ident_unassigned) unassigned[kv.first + n_ident] = kv.second;
+        ldo_enum_job job {};
+        job.n_staples = static_cast<int>(staple_type.size());
+        job.staple_type = staple_type.data();
+        job.n_stack = static_cast<int>(order.size());
+        job.stack_chain = stack_chain.data();
+        job.stack_d = stack_d.data();
+        job.n_growthpoints = static_cast<int>(go_c.size());
+        job.gp_old_chain = go_c.data();
+        job.gp_old_d = go_d.data();
+        job.gp_new_chain = gn_c.data();
+        job.gp_new_d = gn_d.data();
+        job.n_ident = n_ident;
+        job.ident_unassigned = unassigned.data();
+        job.overcount = p.m_max_staple_size == 2 ? 0 : 1; // :26-31
+        job.n_out_ops = static_cast<int>(s.ops_out_idx.size());
+        job.out_ops = s.ops_out_idx.data();
+        job.split_depth = 0;
+        const int max_keys {4096};
+        std::vector<int> keys(static_cast<size_t>(max_keys) * job.n_out_ops);
+        std::vector<double> weights(max_keys);
+        double sums[4];
+        int n_keys {0};
+        long long n_leaves {0};
+        s.check(ldo_enumerate_conformations(s.eng, &job, max_keys, &n_keys, keys.data(), weights.data(), sums, &n_leaves));
+        // calc_and_save_weights (:639-664) with the staple set's prefix
+        for (int k {0}; k != n_keys; k++) {
+            std::vector<int> key(keys.begin() + static_cast<size_t>(k) * job.n_out_ops, keys.begin() + static_cast<size_t>(k + 1) * job.n_out_ops);
+            state_weights[key] += prefix * static_cast<long double>(weights[k]);
+        }
+        partition_f += prefix * static_cast<long double>(sums[0]);
+        average_energy += prefix * static_cast<long double>(sums[1]);
+        average_bias += prefix * static_cast<long double>(sums[2]);
+        num_configs += static_cast<long double>(sums[3]);
+        leaves += n_leaves;
+    }
+
+    // ---- GrowthpointEnumerator (:819-1068) ----
+    void enumerate_growthpoints() {
+        enumerated_growthpoints.clear();
+        staples.clear();
+        for (size_t c_ident {1}; c_ident != identities.size(); c_ident++) {
+            int n {0};
+            for (auto const& st: live) n += st.second == static_cast<int>(c_ident) ? 1 : 0;
+            if (n != 0) staples.push_back({static_cast<int>(c_ident), n});
+        }
+        iterate_staple_identities();
+    }
+    void iterate_staple_identities() {
+        for (size_t i {0}; i != staples.size(); i++) {
+            int staple_ident {staples[i].first};
+            int num_remaining {staples[i].second - 1};
+            if (num_remaining == 0) staples.erase(staples.begin() + i);
+            else staples[i] = {staple_ident, num_remaining};
+            iterate_domain_growthpoints(staple_ident);
+            bool staple_remain {false};
+            for (size_t k {0}; k != staples.size(); k++) {
+                if (staples[k].first == staple_ident) {
+                    staples[k].second++;
+                    staple_remain = true;
+                    break;
+                }
+            }
+            if (!staple_remain) staples.insert(staples.begin() + i, {staple_ident, num_remaining + 1});
+        }
+    }
+    void iterate_domain_growthpoints(int staple_ident) {
+        std::vector<Dom>& avail = misbinding ? unbound_system_domains : comp_system_domains[staple_ident - 1];
+        for (size_t j {0}; j != avail.size(); j++) {
+            Dom old_domain {avail[j]};
+            avail.erase(avail.begin() + j);
+            size_t staple_length {identities[staple_ident].size()};
+            for (size_t d_i {0}; d_i != staple_length; d_i++) {
+                if (!misbinding) {
+                    int old_ident {identities[chain_identity(old_domain.first)][old_domain.second]};
+                    if (identities[staple_ident][d_i] != -old_ident) continue; // :1001-1005
+                }
+                recurse_or_enumerate_conf(staple_ident, static_cast<int>(d_i), staple_length, old_domain);
+            }
+            avail.insert(avail.begin() + j, old_domain);
+        }
+    }
+    void recurse_or_enumerate_conf(int staple_ident, int d_i, size_t staple_length, Dom old_domain) {
+        growthpoints.push_back({{staple_ident, d_i}, {old_domain.first, old_domain.second}});
+        std::vector<Dom> new_unbound_domains {add_growthpoint(staple_ident, d_i, old_domain)};
+        if (!staples.empty()) {
+            if (misbinding) {
+                unbound_system_domains.insert(unbound_system_domains.end(), new_unbound_domains.begin(), new_unbound_domains.end());
+                iterate_staple_identities();
+                for (size_t k {0}; k != staple_length - 1; k++) unbound_system_domains.pop_back();
+            }
+            else {
+                iterate_staple_identities();
+            }
+        }
+        else if (!growthpoints_repeated()) {
+            enumerate_conformations();
+            if (!quiet) std::cout << "   Growthpoint set " << enumerated_growthpoints.size() + 1 << "\n";
+            enumerated_growthpoints.push_back(growthpoints);
+        }
+        remove_growthpoint(old_domain);
+        growthpoints.pop_back();
+    }
+    bool growthpoints_repeated() {
+        for (auto const& gps: enumerated_growthpoints) {
+            if (gps.size() != growthpoints.size()) continue;
+            bool repeated {true};
+            for (auto const& gp: gps) {
+                if (std::count(growthpoints.begin(), growthpoints.end(), gp) == 0) {
+                    repeated = false;
+                    break;
+                }
+            }
+            if (repeated) return true;
+        }
+        return false;
+    }
+
+    // ---- StapleEnumerator (:1082-1133) ----
+    void enumerate_staples() {
+        if (p.m_min_total_staples == 0) {
+            enumerate_conformations();
+            cur_max_total_staples = 1;
+        }
+        else {
+            cur_max_total_staples = p.m_min_total_staples;
+        }
+        max_type_staples = p.m_max_type_staples;
+        while (cur_max_total_staples <= p.m_max_total_staples) {
+            recurse(0, 1, 0);
+            cur_max_total_staples++;
+        }
+    }
+    void recurse(int cur_num_staples, int staple_type_i, int cur_num_staples_i) {
+        int num_staple_types {static_cast<int>(identities.size()) - 1};
+        if (cur_num_staples == cur_max_total_staples) {
+            num_staple_combos++;
+            if (!quiet) std::cout << "Staple set " << num_staple_combos << "\n";
+            enumerate_growthpoints();
+            return;
+        }
+        while (staple_type_i != num_staple_types + 1) {
+            bool excluded {std::find(p.m_excluded_staples.begin(), p.m_excluded_staples.end(), staple_type_i) != p.m_excluded_staples.end()};
+            if (cur_num_staples_i < max_type_staples && !excluded) {
+                add_staple(staple_type_i);
+                cur_num_staples_i++;
+                cur_num_staples++;
+                recurse(cur_num_staples, staple_type_i, cur_num_staples_i);
+                cur_num_staples--;
+                cur_num_staples_i--;
+                remove_staple(staple_type_i);
+            }
+            staple_type_i++;
+            cur_num_staples_i = 0;
+        }
+    }
+};
+
+// enumerate_main (enumerate.cpp:19-81): weights normalised and written to <filebase>.weights, summary on stdout
+void enumerate_run(ldo_sim& s) {
+    InputParameters const& p = s.params;
+    s.ops_out_idx.clear();
+    for (auto const& tag: p.m_ops_to_output) {
+        int found {-1};
+        for (size_t i {0}; i != s.ops.size(); i++)
+            if (s.ops[i].tag == tag) found = static_cast<int>(i);
+        if (found < 0) throw SimulationMisuse {"ops_to_output: unknown order parameter " + tag};
+        s.ops_out_idx.push_back(found);
+    }
+    bool quiet {std::getenv("LDO_QUIET") != nullptr};
+    if (!quiet) std::cout << "Running enumeration\n";
+    HostEnumerator en {s};
+    en.enumerate_staples();
+    if (!p.m_output_filebase.empty()) {
+        // print_weights (:361-376); the reference's table is an unordered_map, the states are written in key order here
+        std::ofstream out {p.m_output_filebase + ".weights"};
+        for (auto const& tag: p.m_ops_to_output) out << tag << " ";
+        out << "\n";
+        for (auto const& kv: en.state_weights) {
+            out << "(" << kv.first[0];
+            for (size_t i {1}; i != kv.first.size(); i++) out << " " << kv.first[i];
+            out << ") " << static_cast<double>(kv.second / en.partition_f) << "\n";
+        }
+        out << "\n";
+    }
+    if (!quiet) {
+        std::cout << en.num_configs << "\n\n";
+        std::cout << en.average_energy / en.partition_f << "\n";
+        std::cout << en.average_bias / en.partition_f << "\n";
+    }
+    s.enum_leaves = en.leaves;
+    s.enum_num_configs = static_cast<double>(en.num_configs);
+    s.enum_average_energy = static_cast<double>(en.average_energy / en.partition_f);
+    s.enum_average_bias = static_cast<double>(en.average_bias / en.partition_f);
+}
+
 void nccl_check(int rc, const char* what) {
     if (rc == 0) return;
     NcclApi& a = nccl();
@@ -854,6 +1207,10 @@ ldo_sim* ldo_sim_create(const char* inp_path, int n_replicas, int device, int ra
             }
             s->n_ladders = n_replicas / (s->num_reps / s->n_ranks);
             s->temps = p.m_temps;
+        }
+        else if (st == "enumerate") {
+            s->temps = {p.m_temp};
+            s->is_enum = true;
         }
         else {
             throw NotImplemented {st + ": simulation type not available on the device path"};
@@ -1192,10 +1549,14 @@ int ldo_sim_exchange_state(ldo_sim* s, int* slot_to_replica, long long* attempts
 int ldo_sim_run(ldo_sim* s) {
     try {
         InputParameters const& p = s->params;
-        if (!s->is_us) open_output_files(*s);
+        if (!s->is_us && !s->is_enum) open_output_files(*s);
         s->start = std::chrono::steady_clock::now();
         std::string const& st = p.m_simulation_type;
-        if (st == "constant_temp") {
+        if (s->is_enum) {
+            enumerate_run(*s);
+            return 0; // no move statistics
+        }
+        else if (st == "constant_temp") {
             simulate(*s, p.m_ct_steps);
         }
         else if (st == "annealing") {
@@ -1314,6 +1675,13 @@ const char* ldo_sim_order_param_tag(ldo_sim* s, int i) { return s->ops[i].tag.c_
 int ldo_sim_num_movetypes(ldo_sim* s) { return static_cast<int>(s->movetypes.size()); }
 const char* ldo_sim_movetype_label(ldo_sim* s, int i) { return s->movetypes[i].label.c_str(); }
 int ldo_sim_num_staple_types(ldo_sim* s) { return static_cast<int>(s->sysfile->identities.size()) - 1; }
+int ldo_sim_enumeration_summary(ldo_sim* s, double* out) {
+    out[0] = s->enum_num_configs;
+    out[1] = s->enum_average_energy;
+    out[2] = s->enum_average_bias;
+    out[3] = static_cast<double>(s->enum_leaves);
+    return s->is_enum ? 0 : -1;
+}
 long long ldo_sim_step(ldo_sim* s) { return s->step; }
 
 int ldo_sim_pair_energies(ldo_sim* s, int temp_idx, int a, int b, double* out) {

@@ -102,3 +102,28 @@ def test_cli_replica_exchange_over_two_gpus_matches_one_gpu(tmp_path):
             one = (outs[1] / f"ptmc-{l * 4 + k}.trj").read_text()
             two = (outs[2] / f"ptmc-{rank * 32 + l * 2 + k // 2}.trj").read_text()
             assert one == two, (l, k)
+
+
+@pytest.mark.gpu
+def test_cli_enumerates_like_the_reference(tmp_path):
+    """examples/enum.inp through the CLI: the reference's stdout summary and .weights (fixture of the reference's run)."""
+    import json
+
+    from conftest import GOLDEN
+    opts = make_options("four_unbound.json", temp=340, simulation_type="enumerate", min_total_staples=0, max_total_staples=2,
+                        max_type_staples=2, enumerate_staples_only=False, output_filebase=str(tmp_path / "enum"),
+                        ops_to_output="numfulldomains nummisdomains numstackedpairs numstaples")
+    inp = write_inp(str(tmp_path / "enum.inp"), opts)
+    r = subprocess.run([CLI, "-i", inp, "--replicas", "2072"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout + r.stderr
+    fx = json.load(open(os.path.join(GOLDEN, "enum_four_unbound.json")))["340"]
+    # the tail of the reference's stdout: growthpoint sets of the last staple set, number of configurations, averages
+    assert r.stdout.strip().split("\n")[-6:] == fx["stdout_tail"].strip().split("\n")[-6:]
+    mine = {}
+    for line in open(tmp_path / "enum.weights").read().splitlines()[1:]:
+        if line.strip():
+            key, value = line.rsplit(" ", 1)
+            mine[key] = float(value)
+    assert set(mine) == set(fx["weights"])
+    for key, value in fx["weights"].items():
+        assert mine[key] == pytest.approx(value, rel=2e-5)
