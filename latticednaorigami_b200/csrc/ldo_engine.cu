@@ -2739,14 +2739,14 @@ int ldo_enumerate_conformations(ldo_engine* e, const ldo_enum_job* j, int max_ke
     }
     // levels of the recursion: one per domain of the stack but the first, a growthpoint pair shares one
     int levels = j->n_stack - 1 - j->n_growthpoints;
-    // enough prefixes to give every worker about eight, so that subtrees of unequal size even out
     int split = 0;
     if (j->split_depth > 0) {
         split = j->split_depth;
     }
     else if (b->R > 1) {
-        long long n = 1;
-        while (split < levels && split < LDO_ENUM_MAX_SPLIT && n < 8LL * b->R) {
+        long long n = 1, per_worker = 256; // prefixes per worker: enough to even out subtrees of unequal size
+        if (const char* pw = getenv("LDO_ENUM_PREFIXES_PER_WORKER")) per_worker = atoll(pw) > 0 ? atoll(pw) : per_worker;
+        while (split < levels && split < LDO_ENUM_MAX_SPLIT && n < per_worker * b->R) {
             n *= 36;
             split++;
         }
