@@ -1189,6 +1189,7 @@ struct EngineBase {
     virtual int get_blobs(int first, int count, void* host) = 0;
     virtual int put_blobs(int first, int count, const void* host) = 0;
     virtual int enumerate(EnumJob& job, std::vector<EnumAcc>& accs) = 0;
+    std::vector<EnumAcc> enum_accs; // per-worker tables of the last enumeration job (host copy)
     int domain_update_biases = 0; // ldo_set_domain_update_biases
     long long launches = 0; // kernels launched so far (ldo_launch_count)
     long long const_version = 0;
@@ -1273,6 +1274,9 @@ struct EngineImpl: EngineBase {
         dev_free(d_exch_tape_offsets);
         dev_free(d_enum_job);
         dev_free(d_enum_acc);
+#ifndef LDO_HOSTSIM
+        if (enum_stack_raised) cudaDeviceSetLimit(cudaLimitStackSize, enum_old_stack);
+#endif
         for (void* p: tape_bufs) dev_free(p);
         for (void* p: parked_tapes) dev_free(p);
         if (g_const_owner[device % LDO_MAX_DEVICES] == this) g_const_owner[device % LDO_MAX_DEVICES] = nullptr;
@@ -1436,11 +1440,14 @@ struct EngineImpl: EngineBase {
     // One growthpoint set of the exact enumeration: every replica slot is a worker (ldo_enum.cuh)
     EnumJob* d_enum_job = nullptr;
     EnumAcc* d_enum_acc = nullptr;
+    bool enum_stack_raised = false;
+    size_t enum_old_stack = 0;
     int enumerate(EnumJob& job, std::vector<EnumAcc>& accs) override {
         if (!P.tables) return fail("temperature tables not set");
         job.n_workers = R;
-        accs.assign(R, EnumAcc());
-        memset(accs.data(), 0, sizeof(EnumAcc) * R);
+        // (16 KB per worker: sized once and reused; only the headers are cleared - entries beyond n_keys are never read)
+        if ((int)accs.size() != R) accs.resize(R);
+        for (EnumAcc& a: accs) memset(&a, 0, offsetof(EnumAcc, keys));
 #ifdef LDO_HOSTSIM
         for (int r = 0; r < R; r++) {
             SysState<K>* tmp = STAGED ? d_recompute_tmp : &d_recompute_tmp[r];
@@ -1460,12 +1467,15 @@ struct EngineImpl: EngineBase {
             if (!d_enum_job && dev_malloc((void**)&d_enum_job, sizeof(EnumJob))) return fail(dev_err());
             if (!d_enum_acc && dev_malloc((void**)&d_enum_acc, sizeof(EnumAcc) * R)) return fail(dev_err());
             if (dev_h2d(d_enum_job, &job, sizeof(EnumJob), stream)) return fail(dev_err());
-            if (chk(cudaMemsetAsync(d_enum_acc, 0, sizeof(EnumAcc) * R, stream))) return fail(dev_err());
-            // the recursion is three frames per placed domain deep
-            size_t old_stack = 0, want = 2048 + 1024 * (size_t)job.n_stack;
-            if (chk(cudaDeviceGetLimit(&old_stack, cudaLimitStackSize))) return fail(dev_err());
-            if (want > old_stack) {
+            if (chk(cudaMemset2DAsync(d_enum_acc, sizeof(EnumAcc), 0, offsetof(EnumAcc, keys), R, stream))) return fail(dev_err());
+            // The recursion is three frames per placed domain deep. Changing the limit reallocates the local memory of
+            // the whole device, so it is raised when a job needs more and stays raised while the engine lives.
+            size_t cur_stack = 0, want = 2048 + 1024 * (size_t)job.n_stack;
+            if (chk(cudaDeviceGetLimit(&cur_stack, cudaLimitStackSize))) return fail(dev_err());
+            if (want > cur_stack) {
+                if (!enum_stack_raised) enum_old_stack = cur_stack;
                 if (dev_sync(stream) || chk(cudaDeviceSetLimit(cudaLimitStackSize, want))) return fail(dev_err());
+                enum_stack_raised = true;
             }
             int wpb = warps_per_block;
             size_t smem = sizeof(WarpSmem<K>) * wpb;
@@ -1473,9 +1483,23 @@ struct EngineImpl: EngineBase {
             k_enum<K><<<(R + wpb - 1) / wpb, wpb * 32, smem, stream>>>(P, d_enum_job, d_enum_acc, R);
             if (chk(cudaGetLastError())) return fail(dev_err());
             launches++;
-            if (dev_d2h(accs.data(), d_enum_acc, sizeof(EnumAcc) * R, stream) || dev_sync(stream)) return fail(dev_err());
-            if (want > old_stack) {
-                if (chk(cudaDeviceSetLimit(cudaLimitStackSize, old_stack))) return fail(dev_err());
+            // the workers' tables are mostly empty: headers first, then only as many entries as the fullest table holds
+            const size_t head = offsetof(EnumAcc, keys);
+            if (chk(cudaMemcpy2DAsync(accs.data(), sizeof(EnumAcc), d_enum_acc, sizeof(EnumAcc), head, R, cudaMemcpyDeviceToHost, stream)) || dev_sync(stream)) {
+                return fail(dev_err());
+            }
+            int max_keys = 0;
+            for (const EnumAcc& a: accs) max_keys = a.n_keys > max_keys ? a.n_keys : max_keys;
+            if (max_keys > 0) {
+                char* h = reinterpret_cast<char*>(accs.data());
+                char* d = reinterpret_cast<char*>(d_enum_acc);
+                if (chk(cudaMemcpy2DAsync(h + offsetof(EnumAcc, keys), sizeof(EnumAcc), d + offsetof(EnumAcc, keys), sizeof(EnumAcc),
+                                          sizeof(int) * LDO_ENUM_MAX_OPS * max_keys, R, cudaMemcpyDeviceToHost, stream)) ||
+                    chk(cudaMemcpy2DAsync(h + offsetof(EnumAcc, w), sizeof(EnumAcc), d + offsetof(EnumAcc, w), sizeof(EnumAcc), sizeof(double) * max_keys, R,
+                                          cudaMemcpyDeviceToHost, stream)) ||
+                    dev_sync(stream)) {
+                    return fail(dev_err());
+                }
             }
             return 0;
         }
@@ -2744,7 +2768,7 @@ int ldo_enumerate_conformations(ldo_engine* e, const ldo_enum_job* j, int max_ke
         split = j->split_depth;
     }
     else if (b->R > 1) {
-        long long n = 1, per_worker = 256; // prefixes per worker: enough to even out subtrees of unequal size
+        long long n = 1, per_worker = 8; // prefixes per worker: a deeper cut evens the subtrees out but costs more walks (profiles/enum_time.py)
         if (const char* pw = getenv("LDO_ENUM_PREFIXES_PER_WORKER")) per_worker = atoll(pw) > 0 ? atoll(pw) : per_worker;
         while (split < levels && split < LDO_ENUM_MAX_SPLIT && n < per_worker * b->R) {
             n *= 36;
@@ -2754,7 +2778,7 @@ int ldo_enumerate_conformations(ldo_engine* e, const ldo_enum_job* j, int max_ke
     job.split_depth = split;
     job.n_prefixes = 1;
     for (int l = 0; l < split; l++) job.n_prefixes *= 36;
-    std::vector<EnumAcc> accs;
+    std::vector<EnumAcc>& accs = b->enum_accs;
     if (b->enumerate(job, accs)) return -1;
     // merge in worker order, keys sorted at the end: the result does not depend on the number of workers beyond rounding
     std::map<std::vector<int>, double> table;

@@ -13,5 +13,5 @@ def run(workers, per_worker):
     sim.run(); t2 = time.time()
     s = sim.enumeration_summary()
     print(f"workers {workers} prefixes/worker>={per_worker}: create {t1-t0:.2f} s, enumerate {t2-t1:.2f} s, leaves {s['leaves']}, configs {s['num_configs']:.6g}", flush=True)
-for workers, pw in [(4144, 8), (4144, 64), (4144, 256), (4144, 4096), (8288, 256), (1036, 256)]:
+for workers, pw in [(4144, 8), (4144, 8), (4144, 64), (518, 8), (1036, 8), (2072, 8), (8288, 8)]:
     run(workers, pw)
