@@ -150,6 +150,12 @@ int ldo_set_temperature_tables(ldo_engine* e, int n_temps, int n_ident, const do
 
 /* Replaces: GCMCSimulation::construct_movetypes (simulation.cpp:267-320). */
 int ldo_set_moveset(ldo_engine* e, int n, const ldo_movetype_desc* movetypes, int allow_nonsensical_ps);
+/* Exchange multipliers of staple-exchange movetype `movetype` as they stand, out[R][n_staple_types]: the movetype file's
+ * values, or - with adaptive_exchange - each replica's own (a multiplier that made an acceptance probability exceed one
+ * is divided by ten and the move rejected, met_movetypes.cpp:228-234, 275-282; the reference keeps them in the movetype
+ * object of each process, here they are per-replica device state and part of a checkpoint). */
+int ldo_get_exchange_mults(ldo_engine* e, int movetype, double* out);
+
 /* Production (Philox) mode only. on != 0: the recoil-growth moves draw in the reference's serial trial order
  * (rg_movetypes.cpp:193-198, 378-402, 435-440) instead of re-associating the draws to lanes - the branches a
  * replay tape runs, driven by Philox. Same ensemble; slower. Used to validate the lane-parallel branches
@@ -199,6 +205,13 @@ int ldo_tape_position(ldo_engine* e, int replica, long long* pos);
  * scaffold first; pos / ore are 3 ints per domain. replica = -1 sets every replica. */
 int ldo_set_state(ldo_engine* e, int replica, int n_chains, const int* chain_index,
                   const int* chain_ident, const int* chain_len, const int* pos, const int* ore);
+/* OrigamiSystem::set_config on a live system (origami_system.cpp:327-341): the chains of `replica` are replaced like
+ * ldo_set_state does, but the stored order parameters and bias values are NOT re-evaluated - the reference's set_config
+ * does not touch them, so they describe the previous configuration until the next move updates them (what the per-window
+ * restart of the multi-window umbrella-sampling drivers does, us_simulation.cpp:246-250, 531-537). */
+int ldo_replace_config(ldo_engine* e, int replica, int n_chains, const int* chain_index, const int* chain_ident,
+                       const int* chain_len, const int* pos, const int* ore);
+
 /* Replaces: OrigamiSystem::chains() (origami_system.cpp:173-191). Buffers sized by ldo_state_capacity. */
 int ldo_state_capacity(const ldo_engine* e, int* max_chains, int* max_domains);
 int ldo_get_state(ldo_engine* e, int replica, int* n_chains, int* chain_index, int* chain_ident,

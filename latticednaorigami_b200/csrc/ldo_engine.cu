@@ -150,6 +150,7 @@ struct OpArgs {
     int centering_freq, centering_domain, constraint_check_freq;
     // LOAD_CONFIG staging: one configuration applied to the selected replicas
     int cfg_n_chains;
+    int cfg_keep_bias; // OrigamiSystem::set_config on a live system: stored order parameters / biases stay (ldo_replace_config)
     const int* cfg_chain_index;
     const int* cfg_chain_ident;
     const int* cfg_chain_len;
@@ -309,7 +310,8 @@ LDO_HD void rep_load_config(Engine<K>& eng, const OpArgs& a) {
         }
     }
     sys.set_all_domains();
-    rep_init_biases(eng);
+    if (a.cfg_keep_bias) eng.BS()->pd_disabled = 0;
+    else rep_init_biases(eng);
 }
 
 template <class K>
@@ -1191,6 +1193,7 @@ struct EngineBase {
     virtual int enumerate(EnumJob& job, std::vector<EnumAcc>& accs) = 0;
     std::vector<EnumAcc> enum_accs; // per-worker tables of the last enumeration job (host copy)
     int domain_update_biases = 0; // ldo_set_domain_update_biases
+    int keep_bias_on_load = 0; // set around the load of ldo_replace_config
     long long launches = 0; // kernels launched so far (ldo_launch_count)
     long long const_version = 0;
     // device output buffers
@@ -1713,6 +1716,7 @@ struct EngineImpl: EngineBase {
         memset(&a, 0, sizeof(a));
         a.op = OP_LOAD_CONFIG;
         a.only_replica = replica;
+        a.cfg_keep_bias = keep_bias_on_load;
         a.cfg_n_chains = n_chains;
         a.cfg_chain_index = d_cfg;
         a.cfg_chain_ident = d_cfg + n_chains;
@@ -2175,7 +2179,30 @@ int ldo_set_moveset(ldo_engine* e, int n, const ldo_movetype_desc* mts, int allo
             return b->fail("CTRG options out of range (max_c_attempts 1..36, max_regrowth >= 2, max_num_recoils 0..3)");
         }
     }
+    // every replica starts its adaptive multipliers from the movetype file's
+    {
+        std::vector<RepAux> aux(b->R);
+        if (b->get_aux(0, b->R, aux.data())) return -1;
+        for (int r = 0; r < b->R; r++) memcpy(aux[r].stats.exchange_mults, ms.exchange_mults, sizeof(ms.exchange_mults));
+        if (b->put_aux(0, b->R, aux.data())) return -1;
+    }
     return b->push_shared();
+}
+
+int ldo_get_exchange_mults(ldo_engine* e, int movetype, double* out) {
+    EngineBase* b = e->b;
+    const MoveSet& ms = b->shared.ms;
+    if (movetype < 0 || movetype >= ms.n || ms.mt[movetype].type != MT_MET_STAPLE_EXCHANGE) return b->fail("not a staple-exchange movetype");
+    int nst = b->shared.sc.n_types - 1;
+    std::vector<RepAux> aux(b->R);
+    if (b->get_aux(0, b->R, aux.data())) return -1;
+    const MoveDef& md = ms.mt[movetype];
+    for (int r = 0; r < b->R; r++) {
+        for (int t = 0; t < nst; t++) {
+            out[(size_t)r * nst + t] = md.adaptive_exchange ? aux[r].stats.exchange_mults[md.exchange_mults_off + t] : ms.exchange_mults[md.exchange_mults_off + t];
+        }
+    }
+    return 0;
 }
 
 int ldo_set_reference_draw_order(ldo_engine* e, int on) {
@@ -2390,6 +2417,15 @@ int ldo_set_state(ldo_engine* e, int replica, int n_chains, const int* chain_ind
                   const int* chain_len, const int* pos, const int* ore) {
     if (replica < -1 || replica >= e->b->R) return e->b->fail("bad replica index");
     return e->load_config(e, replica, n_chains, chain_index, chain_ident, chain_len, pos, ore);
+}
+
+int ldo_replace_config(ldo_engine* e, int replica, int n_chains, const int* chain_index, const int* chain_ident,
+                       const int* chain_len, const int* pos, const int* ore) {
+    if (replica < -1 || replica >= e->b->R) return e->b->fail("bad replica index");
+    e->b->keep_bias_on_load = 1;
+    int rc = e->load_config(e, replica, n_chains, chain_index, chain_ident, chain_len, pos, ore);
+    e->b->keep_bias_on_load = 0;
+    return rc;
 }
 
 int ldo_state_capacity(const ldo_engine* e, int* max_chains, int* max_domains) {

@@ -299,6 +299,10 @@ void InputParameters::finalize() {
         for (auto const& tok: split_ws(m_raw["excluded_staples"])) m_excluded_staples.push_back(std::stoi(tok));
     }
     if (m_raw.count("restart_traj_files")) m_restart_traj_files = split_ws(m_raw["restart_traj_files"]);
+    if (m_raw.count("restart_steps")) {
+        m_restart_steps.clear();
+        for (auto const& tok: split_ws(m_raw["restart_steps"])) m_restart_steps.push_back(std::stoi(tok));
+    }
     if (m_raw.count("ops_to_output") && m_raw["ops_to_output"] != "") m_ops_to_output = split_ws(m_raw["ops_to_output"]);
 }
 

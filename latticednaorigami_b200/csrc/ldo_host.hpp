@@ -78,6 +78,7 @@ class InputParameters {
     bool m_restart_us_iter;
     std::string m_restart_us_filebase;
     int m_restart_step;
+    std::vector<int> m_restart_steps;
     bool m_restart_from_swap;
     bool m_read_rand_engine_state;
     std::string m_rand_engine_state_file;

@@ -394,6 +394,9 @@ struct ColdScratch {
 struct MoveStats {
     long long attempts[LDO_MAX_MOVETYPES];
     long long accepts[LDO_MAX_MOVETYPES];
+    // MetStapleExchangeMCMovetype::m_exchange_mults of the movetypes with adaptive_exchange (met_movetypes.cpp:127,
+    // 232-234, 279-282): state of the movetype object, i.e. of the replica; laid out like MoveSet::exchange_mults
+    double exchange_mults[LDO_MAX_TYPES];
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -871,9 +874,15 @@ struct Engine {
     // ---- MetStapleExchange (met_movetypes.cpp:192-403) ----
     LDO_HD bool exchange_accept(double pratio, int type, bool staple_bound, const MoveDef& md) {
         if (staple_bound) {
-            M()->modifier *= MS().exchange_mults[md.exchange_mults_off + type - 1];
+            int mi = md.exchange_mults_off + type - 1;
+            M()->modifier *= md.adaptive_exchange ? STATS()->exchange_mults[mi] : MS().exchange_mults[mi];
             if (M()->modifier * fmin(1.0, pratio) > 1) {
-                if (md.adaptive_exchange) return false; // adaptive multipliers are host-side state: not adapted on device
+                if (md.adaptive_exchange) {
+                    // a multiplier that produces a probability above one is cut tenfold and the move rejected
+                    if (LDO_LANE == 0) STATS()->exchange_mults[mi] /= 10;
+                    LDO_SYNCWARP();
+                    return false;
+                }
                 if (MS().allow_nonsensical_ps) return true;
                 sys.fail(LDO_ERR_NONSENSICAL_P, type);
                 return false;

@@ -616,8 +616,38 @@ void us_run(ldo_sim& s) {
             s.filebase_postfix = "";
             // The constructor messages ("No biases read in", ...) are written before MWUS redirects the stream
             // (us_simulation.cpp:68-90 vs :545-547): they go to stdout, the .out file starts with the first summary
-            if (!std::getenv("LDO_QUIET")) std::cout << "No biases read in\nStarting from configuration in system file\nStarting new iteration\n";
+            if (!std::getenv("LDO_QUIET")) {
+                std::cout << (p.m_read_biases ? "Reading biases from file\n" : "No biases read in\n")
+                          << (p.m_restart_from_config ? "Reading starting config from file\n" : "Starting from configuration in system file\n")
+                          << "Starting new iteration\n";
+            }
             if (s.is_mwus) st[slot].us_stream.reset(new std::ofstream {replica_filebase(s, slot) + ".out"});
+        }
+    }
+    if (p.m_restart_us_iter) {
+        throw NotImplemented {"restart_us_iter reads Boost text archives (.S_n / .s_i / .f_i, us_simulation.cpp:300-340): not available on the device path; restart with read_biases and restart_from_config"};
+    }
+    if (p.m_read_biases) {
+        // USGCMCSimulation constructor: read_weights + GridBiasFunction::replace_biases (us_simulation.cpp:50-66, 192-205;
+        // bias_functions.cpp:237-240); the multi-window drivers read <biases_filebase><window postfix>.biases (:526-529)
+        for (int slot {0}; slot != s.R; slot++) {
+            std::string file {s.is_mwus ? p.m_biases_filebase + s.window_postfix[slot % s.n_windows] + ".biases" : p.m_biases_file};
+            std::ifstream f {file};
+            if (!f) throw FileError {"Restart bias file " + file + " does not exist"};
+            std::stringstream buf;
+            buf << f.rdbuf();
+            try {
+                Json root {Json::parse(buf.str())};
+                st[slot].E_w.clear();
+                for (size_t k {0}; k != root["biases"].size(); k++) {
+                    GridPoint pt;
+                    for (size_t c {0}; c != root["biases"][k]["point"].size(); c++) pt.push_back(root["biases"][k]["point"][c].as_int());
+                    st[slot].E_w[pt] = root["biases"][k]["bias"].as_double();
+                }
+            } catch (std::exception const& e) {
+                throw FileError {"Restart bias file " + file + " is not well formed:\n" + e.what()};
+            }
+            us_upload_bias(s, slot);
         }
     }
     double saved_max_duration {s.params.m_max_duration};
@@ -1412,6 +1442,34 @@ ldo_sim* ldo_sim_create(const char* inp_path, int n_replicas, int device, int ra
         s->check(ldo_get_status(s->eng, status.data(), detail.data()));
         if (status[0] != 0) {
             throw OrigamiMisuse {"Constaints in violation after move complete (status " + std::to_string(status[0]) + ")"};
+        }
+        if (s->is_mwus && p.m_restart_from_config) {
+            // MWUSGCMCSimulation::setup_window_variables + USGCMCSimulation constructor (us_simulation.cpp:531-549, 74-81,
+            // 246-250): window w continues from frame restart_step of restart_traj_filebase<window postfix><restart_traj_postfix>
+            // (or restart_traj_files[w] / restart_steps[w]) through set_config, which leaves the stored order parameters
+            // and biases of the system-file configuration in place until the first move
+            for (int r {0}; r != s->R; r++) {
+                int w {r % s->n_windows};
+                std::string file {p.m_restart_traj_filebase + s->window_postfix[w] + p.m_restart_traj_postfix};
+                int step {p.m_restart_step};
+                if (!p.m_restart_traj_files.empty()) {
+                    if (static_cast<int>(p.m_restart_traj_files.size()) != s->n_windows || static_cast<int>(p.m_restart_steps.size()) != s->n_windows) {
+                        throw SimulationMisuse {"restart_traj_files / restart_steps must list one entry per window"};
+                    }
+                    file = p.m_restart_traj_files[w];
+                    step = p.m_restart_steps[w];
+                }
+                Chains rc {read_trj_config(file, step)};
+                std::vector<int> rci, rcid, rcl, rpos, rore;
+                for (auto const& c: rc) {
+                    rci.push_back(c.index);
+                    rcid.push_back(c.identity);
+                    rcl.push_back(static_cast<int>(c.positions.size() / 3));
+                    rpos.insert(rpos.end(), c.positions.begin(), c.positions.end());
+                    rore.insert(rore.end(), c.orientations.begin(), c.orientations.end());
+                }
+                s->check(ldo_replace_config(s->eng, r, static_cast<int>(rc.size()), rci.data(), rcid.data(), rcl.data(), rpos.data(), rore.data()));
+            }
         }
         if (s->is_us) us_apply_window_limits(*s);
 

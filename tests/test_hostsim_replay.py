@@ -7,7 +7,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import GOLDEN, make_options, options_from_fixture, replay_fixture_through, write_inp, assert_state_equal, live_replay
+from conftest import GOLDEN, INPUTS, make_options, options_from_fixture, replay_fixture_through, write_inp, assert_state_equal, live_replay
 from latticednaorigami_b200.binding import Simulation
 
 
@@ -143,6 +143,37 @@ def mean_field_correction(lib, oracle, tmp_path):
     assert r.counters()["staples"] >= 1  # staples were inserted: the chain terms were exercised
 
 
+def adaptive_exchange(lib, oracle, tmp_path):
+    """adaptive_exchange = true (met_movetypes.cpp:228-234, 275-282): an exchange multiplier that makes an acceptance
+    probability exceed one is divided by ten and the move rejected - state of the movetype, kept per replica on the
+    device. Replayed against the live oracle with multipliers large enough to be cut along the way."""
+    import json
+    ms = json.load(open(os.path.join(INPUTS, "moveset_standard.json")))
+    for mt in ms["origami"]["movetypes"]:
+        if mt["type"] == "MetStapleExchange":
+            mt["adaptive_exchange"] = True
+            mt["exchange_mults"] = [400.0] * 12
+            mt["freq"] = "3/8"
+        else:
+            mt["freq"] = {"OrientationRotation": "2/8"}.get(mt["type"], "1/8")
+    path = str(tmp_path / "ms_adaptive.json")
+    with open(path, "w") as f:
+        json.dump(ms, f)
+    cut = 0
+    for system, temp, seed, steps in [("snodin_unbound.json", 331, 81, 2000), ("snodin_assembled.json", 350, 82, 1200)]:
+        opts = make_options(system, temp=temp)
+        opts["movetype_file"] = path
+        r, sim = live_replay(oracle, tmp_path, lib, opts, seed, steps, name="adapt")
+        mults = sim.engine.exchange_mults(1)
+        assert mults.shape == (1, 12) and set(mults[0]) <= {400.0, 40.0, 4.0, 0.4}
+        cut += int((mults[0] != 400.0).sum())
+    assert cut > 0, "no multiplier was adapted: the test does not exercise the branch"
+
+
+def test_adaptive_exchange_multipliers(hostsim_lib, oracle, tmp_path):
+    adaptive_exchange(hostsim_lib, oracle, tmp_path)
+
+
 def test_disallowed_misbinding(hostsim_lib, oracle, tmp_path):
     disallowed_misbinding(hostsim_lib, oracle, tmp_path)
 
@@ -155,3 +186,4 @@ def test_mean_field_correction(hostsim_lib, oracle, tmp_path):
 def test_disallowed_misbinding_and_mean_field_gpu(oracle, tmp_path):
     disallowed_misbinding(None, oracle, tmp_path)
     mean_field_correction(None, oracle, tmp_path)
+    adaptive_exchange(None, oracle, tmp_path)

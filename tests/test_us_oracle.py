@@ -105,6 +105,51 @@ def ptmwus_against_oracle(oracle, tmp_path, lib, temp=333, seed0=700):
     return len(ex)
 
 
+def mwus_restart_against_oracle(oracle, tmp_path, lib):
+    """Restart surface of the multi-window driver (us_simulation.cpp:50-81, 192-205, 246-250, 526-537): every window
+    reads its grid biases from <biases_filebase><window postfix>.biases and continues from a frame of its own
+    trajectory through set_config - which leaves the stored order parameters of the system-file configuration in place
+    until the first move. A first reference run makes the files; the restarted reference run is then replayed."""
+    import shutil
+    posts = ["_win-0--4", "_win-2--6", "_win-4--8"]
+    first = us_options(tmp_path, "first", "mw_umbrella_sampling", max_num_iters=2, configs_output_freq=600)
+    oracle.us_run(first, 3, [410 + 7 * r for r in range(3)], workdir=str(tmp_path))
+    for post in posts:
+        shutil.copy(tmp_path / f"first{post}_iter-1.biases", tmp_path / f"rst{post}.biases")
+        assert read_biases(tmp_path / f"rst{post}.biases")
+    kw = dict(max_num_iters=2, read_biases=True, biases_filebase=str(tmp_path / "rst"), restart_from_config=True,
+              restart_traj_filebase=str(tmp_path / "first"), restart_traj_postfix="_iter-1.trj", restart_step=1)
+    ref = oracle.us_run(us_options(tmp_path, "ref", "mw_umbrella_sampling", **kw), 3, [520 + 9 * r for r in range(3)], workdir=str(tmp_path))
+    sim = Simulation(write_inp(str(tmp_path / "our.inp"), us_options(tmp_path, "our", "mw_umbrella_sampling", random_seed=1, **kw)), 3, 0, lib=lib)
+    for r in range(3):
+        sim.engine.attach_tape(r, ref["tapes"][r])
+    sim.run()
+    sim.engine.assert_ok()
+    for r, post in enumerate(posts):
+        assert sim.engine.tape_position(r) == len(ref["tapes"][r]), r
+        got = sim.engine.state(r)
+        for k in ("chain_index", "chain_ident", "chain_len", "pos", "ore"):
+            assert np.array_equal(got[k], ref["states"][r][k]), (r, k)
+        for it in range(2):
+            for tail in (f"_iter-{it}-inp.biases", f"_iter-{it}.biases"):
+                want, have = read_biases(tmp_path / f"ref{post}{tail}"), read_biases(tmp_path / f"our{post}{tail}")
+                assert want.keys() == have.keys(), (post, tail)
+                for pt in want:
+                    assert abs(want[pt] - have[pt]) <= 1e-6, (post, tail, pt, want[pt], have[pt])
+        # the biases the run started from are the ones that were read
+        assert read_biases(tmp_path / f"our{post}_iter-0-inp.biases") == read_biases(tmp_path / f"rst{post}.biases")
+        assert (tmp_path / f"our{post}.out").read_text() == (tmp_path / f"ref{post}.out").read_text(), post
+
+
+def test_multi_window_restart_matches_reference_driver(hostsim_lib, oracle, tmp_path):
+    mwus_restart_against_oracle(oracle, tmp_path, hostsim_lib)
+
+
+@pytest.mark.gpu
+def test_multi_window_restart_matches_reference_driver_gpu(oracle, tmp_path):
+    mwus_restart_against_oracle(oracle, tmp_path, None)
+
+
 def test_window_exchange_matches_reference_driver(hostsim_lib, oracle, tmp_path):
     draws = 0
     for seed0 in (700, 730):
