@@ -276,6 +276,20 @@ int ldo_get_staple_counts(ldo_engine* e, int* out);
 int ldo_get_order_params(ldo_engine* e, int* out);
 /* [n_replicas][n_movetypes] attempts / accepts (MovetypeTracking, movetypes.hpp:49-52; .moves). */
 int ldo_get_move_stats(ldo_engine* e, long long* attempts, long long* accepts);
+/* Typed move trackers (movetypes.hpp:327-339, utility.hpp:100-147): the breakdown the reference's .moves summary gives
+ * for each movetype - staple moves by staple type (exchange: insertions and deletions apart; regrowth: attempts with and
+ * without staples in the system apart), scaffold regrowth by the number of scaffold domains (CTCB: and of staples).
+ * Off by default (12 KB per replica, one extra store per move); ldo_sim_run enables them when it writes output files.
+ * counts[n_movetypes][2 fields][LDO_TRACKER_BINS values][attempts, accepts]; field / value per movetype type:
+ *   MetStapleExchange   field 0 insertions, 1 deletions; value = staple type
+ *   Met/CBStapleRegrowth field 0 staples present, 1 no staples in the system; value = staple type (as last set)
+ *   CTRG(Jump)Scaffold  field 0; value = scaffold domains selected (0 for the jump move, as in the reference)
+ *   CTCB(Jump)Scaffold  field 0 as above; field 1 value = staples regrown with the segment
+ * sticky[n_movetypes][2]: the tracker fields as the last move of each type left them (they persist between moves). */
+#define LDO_TRACKER_BINS 64
+int ldo_enable_move_trackers(ldo_engine* e, int on);
+int ldo_get_move_trackers(ldo_engine* e, int replica, int* sticky, unsigned int* counts);
+
 /* Diagnostics (no reference counterpart): [n_replicas][3] = start ns, end ns (device global timer) and SM id
  * of every replica's warp in the last ldo_run launch; used by profiles/ to measure load imbalance. */
 int ldo_get_run_timing(ldo_engine* e, long long* out);

@@ -181,6 +181,7 @@ struct DevPtrs {
     long long* run_timing; // [R][3] diagnostics of the last run launch: start ns, end ns (globaltimer), SM id
     int* queue; // [LDO_MAX_LISTS] work-queue heads of the staged kernel (reset before every launch)
     int* order; // [R] replicas in the order they are handed out by a run launch (most expensive first)
+    TrackStats* track; // [R] typed move trackers, null unless enabled (ldo_enable_move_trackers)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -208,6 +209,7 @@ LDO_HD void rep_init_engine(Engine<K>& eng, SysState<K>* st, MoveScratch<K>* ms,
     eng.grid_vals = P.grid_vals ? P.grid_vals + (size_t)aux->bs.grid_slot * LDO_GRID_CAP : nullptr;
     eng.ctl = aux->ctl;
     eng.stats = &P.aux[r].stats;
+    eng.trk = P.track ? &P.track[r] : nullptr;
 }
 
 template <class K>
@@ -1191,6 +1193,8 @@ struct EngineBase {
     virtual int get_blobs(int first, int count, void* host) = 0;
     virtual int put_blobs(int first, int count, const void* host) = 0;
     virtual int enumerate(EnumJob& job, std::vector<EnumAcc>& accs) = 0;
+    virtual int enable_trackers(bool on) = 0;
+    virtual int get_trackers(int replica, TrackStats* out) = 0;
     std::vector<EnumAcc> enum_accs; // per-worker tables of the last enumeration job (host copy)
     int domain_update_biases = 0; // ldo_set_domain_update_biases
     int keep_bias_on_load = 0; // set around the load of ldo_replace_config
@@ -1277,6 +1281,7 @@ struct EngineImpl: EngineBase {
         dev_free(d_exch_tape_offsets);
         dev_free(d_enum_job);
         dev_free(d_enum_acc);
+        dev_free(P.track);
 #ifndef LDO_HOSTSIM
         if (enum_stack_raised) cudaDeviceSetLimit(cudaLimitStackSize, enum_old_stack);
 #endif
@@ -1438,6 +1443,28 @@ struct EngineImpl: EngineBase {
         if (sync && dev_sync(stream)) return fail(dev_err());
         return 0;
 #endif
+    }
+
+    int enable_trackers(bool on) override {
+        if (on && !P.track) {
+            if (dev_malloc((void**)&P.track, sizeof(TrackStats) * R)) return fail(dev_err());
+#ifdef LDO_HOSTSIM
+            memset(P.track, 0, sizeof(TrackStats) * R);
+#else
+            if (chk(cudaMemsetAsync(P.track, 0, sizeof(TrackStats) * R, stream))) return fail(dev_err());
+#endif
+        }
+        else if (!on && P.track) {
+            if (dev_sync(stream)) return fail(dev_err());
+            dev_free(P.track);
+            P.track = nullptr;
+        }
+        return 0;
+    }
+    int get_trackers(int replica, TrackStats* out) override {
+        if (!P.track) return fail("move trackers are not enabled");
+        if (dev_d2h(out, &P.track[replica], sizeof(TrackStats), stream) || dev_sync(stream)) return fail(dev_err());
+        return 0;
     }
 
     // One growthpoint set of the exact enumeration: every replica slot is a worker (ldo_enum.cuh)
@@ -2545,6 +2572,23 @@ int ldo_get_move_stats(ldo_engine* e, long long* attempts, long long* accepts) {
             attempts[(size_t)r * n + i] = aux[r].stats.attempts[i];
             accepts[(size_t)r * n + i] = aux[r].stats.accepts[i];
         }
+    }
+    return 0;
+}
+
+static_assert(LDO_TRK_BINS == LDO_TRACKER_BINS, "tracker bins of the ABI and of the device code differ");
+int ldo_enable_move_trackers(ldo_engine* e, int on) { return e->b->enable_trackers(on != 0); }
+
+int ldo_get_move_trackers(ldo_engine* e, int replica, int* sticky, unsigned int* counts) {
+    EngineBase* b = e->b;
+    if (replica < 0 || replica >= b->R) return b->fail("bad replica index");
+    TrackStats t;
+    if (b->get_trackers(replica, &t)) return -1;
+    int n = b->shared.ms.n;
+    for (int i = 0; i < n; i++) {
+        sticky[2 * i] = t.sticky_a[i];
+        sticky[2 * i + 1] = t.sticky_b[i];
+        memcpy(counts + (size_t)i * 2 * LDO_TRK_BINS * 2, t.cnt[i], sizeof(unsigned) * 2 * LDO_TRK_BINS * 2);
     }
     return 0;
 }

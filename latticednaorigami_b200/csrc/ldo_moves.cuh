@@ -399,6 +399,17 @@ struct MoveStats {
     double exchange_mults[LDO_MAX_TYPES];
 };
 
+// Typed move trackers (m_tracker / m_tracking of the movetypes, movetypes.hpp:327-339, utility.hpp:100-147): what the
+// reference breaks its .moves summary down by - staple type for the staple moves (insertions and deletions apart),
+// number of scaffold domains (and of staples) for the scaffold regrowth moves. Optional (ldo_enable_move_trackers): kept
+// outside RepAux so that checkpoints and the run kernel's staged state do not grow. The tracker fields of a movetype
+// object persist between its moves in the reference (a field a move does not set keeps its last value): sticky_a/_b.
+#define LDO_TRK_BINS 64
+struct TrackStats {
+    int sticky_a[LDO_MAX_MOVETYPES], sticky_b[LDO_MAX_MOVETYPES];
+    unsigned cnt[LDO_MAX_MOVETYPES][2][LDO_TRK_BINS][2]; // [movetype][field][value][attempts, accepts]
+};
+
 // ---------------------------------------------------------------------------------------------
 // The per-replica engine
 // ---------------------------------------------------------------------------------------------
@@ -415,6 +426,7 @@ struct Engine {
     const double* grid_vals; // replica's grid-bias values (NaN = off grid)
     Control ctl;
     MoveStats* stats;
+    TrackStats* trk; // null unless trackers are enabled
 
     struct Work {
         // RG per-domain working state (rg_movetypes.hpp:118-126)
@@ -426,6 +438,7 @@ struct Engine {
         int cur_slot, memo_level, memo_key, memo_mask, last_pc, last_kind;
         int slot_cache_on; // calc_weights may take the slots of C()->slot_cache (see there)
         int in_growth; // inside recoil_regrow's own growth (not a feeler): recoils may reuse the level's cached slot / energy
+        int trk_a, trk_b; // tracker fields of the move under way (TrackStats)
         int sp_start; // stacked pairs / energy before the move (mc_step: rejected moves restore them)
         double e_start;
     };
@@ -447,6 +460,11 @@ struct Engine {
         return LDO_SMEM_PTR(K, BiasState, bias, bs);
     }
     LDO_HD MoveStats* STATS() const { return LDO_ENG_FIELD(MoveStats*, stats); } // global memory: touched twice per move
+#ifdef LDO_NO_TRACKERS // A/B knob (profiles/ab_r2.txt): the tracker hooks compiled out
+    LDO_HD TrackStats* TRK() const { return nullptr; }
+#else
+    LDO_HD TrackStats* TRK() const { return LDO_ENG_FIELD(TrackStats*, trk); }
+#endif
     LDO_HD const MoveSet& MS() const {
 #if defined(__CUDA_ARCH__)
         return ldo_c_ms;
@@ -897,6 +915,8 @@ struct Engine {
         if (uniform_real() < 0.5) {
             // insert_staple (:303-359)
             int type = uniform_int(1, sys.SC().n_types - 1);
+            W()->trk_a = type;
+            W()->trk_b = 0;
             if (s->num_staples == sys.SC().max_total_staples) return false;
             if (s->type_count[type] == sys.SC().max_type_staples) return false;
             int c = sys.add_chain(type);
@@ -927,6 +947,8 @@ struct Engine {
         }
         // delete_staple (:361-403)
         int type = uniform_int(1, sys.SC().n_types - 1);
+        W()->trk_a = type;
+        W()->trk_b = 1;
         int n_of_type = s->type_count[type];
         if (n_of_type == 0) {
             M()->rejected = 1;
@@ -958,8 +980,12 @@ struct Engine {
     LDO_HDN bool move_met_staple_regrowth() {
         SysState<K>* s = sys.S();
         W()->delta_e = 0;
-        if (s->num_staples == 0) return false;
+        if (s->num_staples == 0) {
+            W()->trk_b = 1; // m_tracker.no_staples = true, never reset by this movetype (met_movetypes.cpp:474-477)
+            return false;
+        }
         int c = s->order[uniform_int(1, s->num_staples)];
+        W()->trk_a = s->chain_type[c];
         if (staple_is_connector(c)) return false;
         int n_bd = count_bound_to_other_chains(c);
         if (n_bd == 0) {
@@ -1105,8 +1131,13 @@ struct Engine {
     }
     LDO_HDN bool move_cb_staple_regrowth() {
         SysState<K>* s = sys.S();
-        if (s->num_staples == 0) return false;
+        if (s->num_staples == 0) {
+            W()->trk_b = 1;
+            return false;
+        }
+        W()->trk_b = 0; // (cb_movetypes.cpp:296-303)
         int c = s->order[uniform_int(1, s->num_staples)];
+        W()->trk_a = s->chain_type[c];
         if (staple_is_connector(c)) return false;
         DD bias = dd_from(1.0);
         int n_bd = count_bound_to_other_chains(c);
@@ -2621,6 +2652,7 @@ struct Engine {
         rg_reset(md);
         ct_select_indices(md);
         if (sys.S()->status != LDO_OK) return false;
+        W()->trk_a = C()->n_sel;
         // setup_constraints (rg:134-145)
 #pragma unroll 1
         for (int k = 0; k < C()->n_sel; k++) C()->in_sel[C()->sel_scaf[k]] = 1;
@@ -2682,6 +2714,7 @@ struct Engine {
         int n_stems = 0;
         int n_segs = ct_select_noncontig_segs(md, n_stems);
         if (s->status != LDO_OK) return false;
+        W()->trk_a = 0;
         rg_register_jump_constraints(n_segs, n_stems);
         int first = C()->seg_dom[0];
         cp_remove_active_endpoint(first);
@@ -2874,6 +2907,10 @@ struct Engine {
         cp_save_initial();
         bool whole = sys.SC().cyclic != 0 && C()->n_sel == sys.S()->chain_len[0];
         if (!whole) cp_remove_active_endpoint(C()->sel_scaf[0]);
+        if (TRK()) {
+            W()->trk_a = C()->n_sel;
+            W()->trk_b = num_regrowth_staples();
+        }
         DD bias = dd_from(1.0), new_bias = dd_from(1.0);
         for (int pass = 0; pass < 2; pass++) {
             bool regrow_old = pass == 1;
@@ -2907,6 +2944,10 @@ struct Engine {
         rg_register_jump_constraints(n_segs, n_stems);
         int first = C()->seg_dom[0];
         cp_remove_active_endpoint(first);
+        if (TRK()) {
+            W()->trk_a = 0;
+            W()->trk_b = num_regrowth_staples();
+        }
         DD bias = dd_from(1.0), new_bias = dd_from(1.0);
         for (int pass = 0; pass < 2; pass++) {
             bool regrow_old = pass == 1;
@@ -3530,6 +3571,10 @@ struct Engine {
         const MoveDef& md = MS().mt[i];
         reset_internal();
         STATS()->attempts[i]++;
+        if (TRK()) {
+            W()->trk_a = TRK()->sticky_a[i];
+            W()->trk_b = TRK()->sticky_b[i];
+        }
         bool accepted = false;
         switch (md.type) {
         case MT_ORIENTATION_ROTATION: accepted = move_orientation_rotation(); break;
@@ -3547,7 +3592,56 @@ struct Engine {
         }
         if (sys.S()->status != LDO_OK) return false;
         STATS()->accepts[i] += accepted ? 1 : 0;
+        if (TRK()) track(i, md.type, accepted);
         return accepted;
+    }
+    // add_tracker (movetypes.hpp:327-339) with the fields the move left in Work::trk_a / trk_b
+    LDO_HDN void track(int i, int type, bool accepted) {
+        TrackStats* t = TRK();
+        int a = W()->trk_a, b = W()->trk_b;
+        int fa = -1, fb = -1, va = 0, vb = 0;
+        switch (type) {
+        case MT_MET_STAPLE_EXCHANGE: // a = staple type, b = 1 for a deletion
+        case MT_MET_STAPLE_REGROWTH: // a = staple type, b = no_staples
+        case MT_CB_STAPLE_REGROWTH:
+            fa = b ? 1 : 0;
+            va = a;
+            break;
+        case MT_CTRG_SCAFFOLD_REGROWTH:
+        case MT_CTRG_JUMP_SCAFFOLD_REGROWTH: // a = number of scaffold domains
+            fa = 0;
+            va = a;
+            break;
+        case MT_CTCB_SCAFFOLD_REGROWTH:
+        case MT_CTCB_JUMP_SCAFFOLD_REGROWTH: // a = number of scaffold domains, b = number of staples
+            fa = 0;
+            va = a;
+            fb = 1;
+            vb = b;
+            break;
+        default: break;
+        }
+        if (LDO_LANE == 0) {
+            t->sticky_a[i] = a;
+            t->sticky_b[i] = b;
+            if (fa >= 0) {
+                va = va < 0 ? 0 : (va >= LDO_TRK_BINS ? LDO_TRK_BINS - 1 : va);
+                t->cnt[i][fa][va][0] += 1;
+                t->cnt[i][fa][va][1] += accepted ? 1 : 0;
+            }
+            if (fb >= 0) {
+                vb = vb < 0 ? 0 : (vb >= LDO_TRK_BINS ? LDO_TRK_BINS - 1 : vb);
+                t->cnt[i][fb][vb][0] += 1;
+                t->cnt[i][fb][vb][1] += accepted ? 1 : 0;
+            }
+        }
+        LDO_SYNCWARP();
+    }
+    LDO_HDN int num_regrowth_staples() const {
+        int n = 0;
+#pragma unroll 1
+        for (int c = 1; c < K::C; c++) n += C()->regrow_chain[c] ? 1 : 0;
+        return n;
     }
     LDO_HD bool mc_step() {
         int i = select_movetype();

@@ -364,19 +364,86 @@ bool simulate(ldo_sim& s, long long steps) {
 }
 
 // write_log_summary (simulation.cpp:706-718, movetypes.cpp:87-96)
+// GCMCSimulation::write_log_summary (simulation.cpp:706-718): <filebase>.moves holds, for every movetype but the
+// orientation rotation (whose write_log_summary is empty, orientation_movetype.cpp:28), the header of
+// movetypes.cpp:88-96 and the movetype's own breakdown from its trackers (met_movetypes.cpp:145-190, 442-468;
+// cb_movetypes.cpp:264-290, 626-675, 816-870; rg_movetypes.cpp:593-627, 754-786). The transform / linker movetypes get
+// the header only (their seven-field trackers are not kept on the device).
 void write_move_summary(ldo_sim& s) {
     if (s.params.m_output_filebase.empty()) return;
     size_t n {s.movetypes.size()};
     std::vector<long long> att(n * s.R), acc(n * s.R);
     s.check(ldo_get_move_stats(s.eng, att.data(), acc.data()));
+    int nst {static_cast<int>(s.sysfile->identities.size()) - 1};
+    std::vector<int> sticky(2 * n);
+    std::vector<unsigned int> counts(n * 2 * LDO_TRACKER_BINS * 2);
+    std::vector<double> mults(static_cast<size_t>(s.R) * std::max(nst, 1));
     for (int r {0}; r != s.R; r++) {
         std::ofstream o {replica_filebase(s, r) + ".moves"};
+        bool typed {ldo_get_move_trackers(s.eng, r, sticky.data(), counts.data()) == 0};
+        auto cnt = [&](size_t i, int field, int value, int what) {
+            return static_cast<int>(counts[((i * 2 + field) * LDO_TRACKER_BINS + value) * 2 + what]);
+        };
+        auto block = [&](std::string const& title, int value, int ats, int acs) {
+            double freq {static_cast<double>(acs) / ats};
+            o << "    " << title << ": " << value << "\n";
+            o << "        Attempts: " << ats << "\n";
+            o << "        Accepts: " << acs << "\n";
+            o << "        Frequency: " << freq << "\n";
+        };
         for (size_t i {0}; i != n; i++) {
+            int type {s.movetypes[i].desc.type};
+            if (type == LDO_MT_ORIENTATION_ROTATION) continue;
             long long a {att[static_cast<size_t>(r) * n + i]}, c {acc[static_cast<size_t>(r) * n + i]};
             o << "Movetype: " << s.movetypes[i].label << "\n";
             o << "    Attempts: " << a << "\n";
             o << "    Accepts: " << c << "\n";
             o << "    Frequency: " << static_cast<double>(c) / a << "\n";
+            if (!typed) continue;
+            if (type == LDO_MT_MET_STAPLE_EXCHANGE) {
+                std::set<int> types;
+                for (int f {0}; f != 2; f++)
+                    for (int v {0}; v != LDO_TRACKER_BINS; v++)
+                        if (cnt(i, f, v, 0) != 0) types.insert(v);
+                s.check(ldo_get_exchange_mults(s.eng, static_cast<int>(i), mults.data()));
+                o << "       Exchange multipliers\n        ";
+                for (size_t k {0}; k != types.size(); k++) o << mults[static_cast<size_t>(r) * nst + k] << ", ";
+                o << "\n";
+                for (int st: types) {
+                    o << "    Staple type: " << st << "\n";
+                    int iats {cnt(i, 0, st, 0)}, iacs {cnt(i, 0, st, 1)};
+                    float ifreq {static_cast<float>(iacs) / iats};
+                    o << "        Insertion attempts: " << iats << "\n";
+                    o << "        Insertion accepts: " << iacs << "\n";
+                    o << "        Insertion frequency: " << ifreq << "\n";
+                    int dats {cnt(i, 1, st, 0)}, dacs {cnt(i, 1, st, 1)};
+                    float dfreq {static_cast<float>(dacs) / dats};
+                    o << "        Deletion attempts: " << dats << "\n";
+                    o << "        Deletion accepts: " << dacs << "\n";
+                    o << "        Deletion frequency: " << dfreq << "\n";
+                }
+            }
+            else if (type == LDO_MT_MET_STAPLE_REGROWTH || type == LDO_MT_CB_STAPLE_REGROWTH) {
+                // Met: every tracker's staple type is listed, counted only when staples were present (:449-457);
+                // CB: only the trackers with staples present are listed, after an empty line (:271-280)
+                bool met {type == LDO_MT_MET_STAPLE_REGROWTH};
+                std::set<int> types;
+                for (int f {0}; f != (met ? 2 : 1); f++)
+                    for (int v {0}; v != LDO_TRACKER_BINS; v++)
+                        if (cnt(i, f, v, 0) != 0) types.insert(v);
+                if (!met) o << "\n";
+                for (int st: types) block("Staple type", st, cnt(i, 0, st, 0), cnt(i, 0, st, 1));
+            }
+            else if (type == LDO_MT_CTRG_SCAFFOLD_REGROWTH || type == LDO_MT_CTRG_JUMP_SCAFFOLD_REGROWTH ||
+                     type == LDO_MT_CTCB_SCAFFOLD_REGROWTH || type == LDO_MT_CTCB_JUMP_SCAFFOLD_REGROWTH) {
+                for (int v {0}; v != LDO_TRACKER_BINS; v++)
+                    if (cnt(i, 0, v, 0) != 0) block("Number of scaffold domains", v, cnt(i, 0, v, 0), cnt(i, 0, v, 1));
+                o << "\n";
+                if (type == LDO_MT_CTCB_SCAFFOLD_REGROWTH || type == LDO_MT_CTCB_JUMP_SCAFFOLD_REGROWTH) {
+                    for (int v {0}; v != LDO_TRACKER_BINS; v++)
+                        if (cnt(i, 1, v, 0) != 0) block("Number of staples", v, cnt(i, 1, v, 0), cnt(i, 1, v, 1));
+                }
+            }
         }
     }
 }
@@ -1297,6 +1364,8 @@ ldo_sim* ldo_sim_create(const char* inp_path, int n_replicas, int device, int ra
             std::vector<ldo_movetype_desc> md;
             for (auto const& m: s->movetypes) md.push_back(m.desc);
             s->check(ldo_set_moveset(s->eng, static_cast<int>(md.size()), md.data(), p.m_allow_nonsensical_ps ? 1 : 0));
+            // the breakdowns of the .moves summary (write_move_summary) need the typed trackers
+            if (!p.m_output_filebase.empty() && !s->is_enum) s->check(ldo_enable_move_trackers(s->eng, 1));
         }
 
         // order parameters and biases
