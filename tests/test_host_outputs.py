@@ -4,7 +4,8 @@ assembled snodin system at 300 K with a moveset of staple exchanges only and `ma
 12 staples present — insertions are refused (met_movetypes.cpp:311-318) and a deletion would cost ~40 kT —
 so both programs write the same configurations, counts, energies and order parameters at every output step.
 Covers .trj .vsf .vcf .states .ores .counts .staples .staplestates .ene .ops (files.cpp:519-793) and the
-general part of .moves (movetypes.cpp:87-96; the typed per-move trackers are waived)."""
+general part of .moves (movetypes.cpp:87-96; the movetypes' own breakdowns are compared on evolving runs in
+test_restart_and_outputs.py)."""
 import json
 import os
 import subprocess
