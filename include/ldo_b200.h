@@ -405,6 +405,9 @@ typedef struct ldo_enum_job {
     int n_out_ops;
     const int* out_ops;          /* [n_out_ops <= 6] indices of the order parameters that label a state (ops_to_output) */
     int split_depth;             /* levels of the recursion dealt out as prefixes; <= 0: chosen by the engine */
+    int staples_only;            /* StapleConformationalEnumerator (enumerate.cpp:666-811): the scaffold keeps the configuration */
+    const int* scaffold_pos;     /* below ([n_scaffold][3] positions and orientation vectors), the stack holds staple domains only */
+    const int* scaffold_ore;
 } ldo_enum_job;
 int ldo_enumerate_conformations(ldo_engine* e, const ldo_enum_job* job, int max_keys, int* n_keys, int* keys /* [max_keys][n_out_ops] */,
                                 double* weights /* [max_keys] */, double* sums /* [4] */, long long* n_leaves /* may be NULL */);

@@ -2809,7 +2809,8 @@ int ldo_exchange_buffers(ldo_engine* e, int n_global, void** send_dev, void** re
 int ldo_enumerate_conformations(ldo_engine* e, const ldo_enum_job* j, int max_keys, int* n_keys, int* keys, double* weights, double* sums, long long* n_leaves) {
     EngineBase* b = e->b;
     if (j->n_staples < 0 || j->n_staples > LDO_ENUM_MAX_STAPLES) return b->fail("enumeration: too many staples in the set");
-    if (j->n_stack < 2 || j->n_stack > LDO_ENUM_MAX_DOMAINS) return b->fail("enumeration: between 2 and 32 domains");
+    if (j->n_stack < (j->staples_only ? 0 : 2) || j->n_stack > LDO_ENUM_MAX_DOMAINS) return b->fail("enumeration: between 2 and 32 domains");
+    if (j->staples_only && b->shared.sc.n_scaffold > LDO_ENUM_MAX_DOMAINS) return b->fail("enumeration: scaffold of at most 32 domains");
     if (j->n_growthpoints < 0 || j->n_growthpoints > LDO_ENUM_MAX_STAPLES) return b->fail("enumeration: too many growthpoints");
     if (j->n_out_ops < 1 || j->n_out_ops > LDO_ENUM_MAX_OPS) return b->fail("enumeration: between 1 and 6 order parameters to output");
     if (j->n_ident < 0 || j->n_ident > LDO_ENUM_MAX_IDENT) return b->fail("enumeration: domain identities out of range");
@@ -2841,8 +2842,18 @@ int ldo_enumerate_conformations(ldo_engine* e, const ldo_enum_job* j, int max_ke
         if (j->out_ops[k] < 0 || j->out_ops[k] >= b->shared.ob.n_ops) return b->fail("enumeration: order parameter index out of range");
         job.out_op[k] = j->out_ops[k];
     }
-    // levels of the recursion: one per domain of the stack but the first, a growthpoint pair shares one
-    int levels = j->n_stack - 1 - j->n_growthpoints;
+    job.staples_only = j->staples_only ? 1 : 0;
+    if (job.staples_only) {
+        for (int i = 0; i < b->shared.sc.n_scaffold; i++) {
+            for (int k = 0; k < 3; k++) job.scaf_pos[i][k] = j->scaffold_pos[3 * i + k];
+            int oc = ore_code(v3(j->scaffold_ore[3 * i], j->scaffold_ore[3 * i + 1], j->scaffold_ore[3 * i + 2]));
+            job.scaf_ore[i] = oc == 7 ? ORE_ZERO : oc;
+        }
+    }
+    // levels of the recursion: one per domain of the stack but the first, a growthpoint pair shares one (staples only: the
+    // domains grown off the scaffold take no level)
+    int levels = j->staples_only ? j->n_stack - j->n_growthpoints : j->n_stack - 1 - j->n_growthpoints;
+    if (levels < 0) levels = 0;
     int split = 0;
     if (j->split_depth > 0) {
         split = j->split_depth;

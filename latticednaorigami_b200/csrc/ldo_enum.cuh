@@ -47,6 +47,11 @@ struct EnumJob {
     int split_depth;
     long long n_prefixes; // 36^split_depth
     int n_workers;
+    // StapleConformationalEnumerator (enumerate.cpp:666-811): the scaffold keeps the configuration below, only the staples
+    // attached to it are grown
+    int staples_only;
+    int scaf_pos[LDO_ENUM_MAX_DOMAINS][3];
+    int scaf_ore[LDO_ENUM_MAX_DOMAINS]; // orientation codes
 };
 
 // Per worker: sums over its leaves (weights without the job's prefix factor, which the host applies)
@@ -69,6 +74,7 @@ struct Enumerator {
     short stack[LDO_ENUM_MAX_DOMAINS];
     int n_stack;
     short gp[K::D];
+    short inv_gp[K::D]; // staples-only: staple domain -> the scaffold domain it grows off (m_inverse_growthpoints)
     V3 prev_ps[LDO_ENUM_MAX_DOMAINS];
     int n_prev;
     int id_un[2 * LDO_ENUM_MAX_IDENT + 1];
@@ -135,6 +141,12 @@ struct Enumerator {
             int c = sys().add_chain(job.staple_type[k]);
             if (c != k + 1) sys().fail(LDO_ERR_INTERNAL, 700 + k);
         }
+        if (job.staples_only) {
+            // StapleConformationalEnumerator constructor: the scaffold domains are put back where the input has them
+            for (int i = 0; i < len && ok(); i++) {
+                sys().set_domain_config(i, v3(job.scaf_pos[i][0], job.scaf_pos[i][1], job.scaf_pos[i][2]), job.scaf_ore[i]);
+            }
+        }
         s->energy = 0; // the enumerator keeps its own sum (m_energy)
     }
 
@@ -142,7 +154,12 @@ struct Enumerator {
         n_stack = 0;
         for (int i = job.n_stack - 1; i >= 0; i--) push(flat(job.stack_chain[i], job.stack_d[i])); // popped from the back
         for (int d = 0; d < K::D; d++) gp[d] = -1;
-        for (int g = 0; g < job.n_gp; g++) gp[flat(job.gp_old_chain[g], job.gp_old_d[g])] = (short)flat(job.gp_new_chain[g], job.gp_new_d[g]);
+        for (int d = 0; d < K::D; d++) inv_gp[d] = -1;
+        for (int g = 0; g < job.n_gp; g++) {
+            int od = flat(job.gp_old_chain[g], job.gp_old_d[g]), nd = flat(job.gp_new_chain[g], job.gp_new_d[g]);
+            gp[od] = (short)nd;
+            if (job.staples_only && job.gp_old_chain[g] == 0) inv_gp[nd] = (short)od; // create_domains_stack, :799-807
+        }
         for (int i = 0; i < 2 * LDO_ENUM_MAX_IDENT + 1; i++) id_un[i] = job.ident_unassigned[i];
         start_prefix();
     }
@@ -321,6 +338,15 @@ struct Enumerator {
         mult /= pos_multiplier;
     }
     LDO_HDN void set_unbound_domain(int domain, V3 p_new, int depth) {
+        if (job.staples_only) {
+            // StapleConformationalEnumerator::set_unbound_domain (:781-791): one orientation-free placement
+            if (above_cut(depth) && dig_o[depth] != 0) return;
+            energy += sys().set_domain_config(domain, p_new, ORE_ZERO);
+            mult *= 6;
+            grow_next_domain(domain, p_new, depth);
+            mult /= 6;
+            return;
+        }
         // all orientations only when a twist constraint is possible (enumerate.cpp:525-549)
         if (unassigned_of(-sys().ident(domain)) == 0) {
             if (above_cut(depth) && dig_o[depth] != 0) return;
@@ -344,7 +370,45 @@ struct Enumerator {
             }
         }
     }
+    // a leaf above the cut belongs to the prefix whose remaining digits are zero
+    LDO_HD bool leaf_is_mine(int depth) const {
+        bool mine = true;
+        for (int l = depth + 1; l < job.split_depth; l++) mine = mine && dig_p[l] == 0 && dig_o[l] == 0;
+        return mine;
+    }
+    // StapleConformationalEnumerator::grow_off_scaffold (:754-779): the staple domain bound to its scaffold domain
+    LDO_HDN void grow_off_scaffold(int next_domain, int depth) {
+        int sd = inv_gp[next_domain];
+        V3 p_new = sys().pos(sd);
+        int oc = sys().orc(sd);
+        energy += sys().set_domain_config(next_domain, p_new, oc < ORE_ZERO ? (oc ^ 1) : oc);
+        if (take_violation()) {
+            push(next_domain);
+            return;
+        }
+        if (n_stack > 0) {
+            int nn = pop();
+            if (inv_gp[nn] >= 0) grow_off_scaffold(nn, depth);
+            else enumerate_domain(nn, p_new, depth + 1);
+            push(next_domain);
+        }
+        // (a set that ends here is not counted: the reference saves no weight on this path)
+        energy += sys().unassign_domain(next_domain);
+    }
     LDO_HDN void grow_next_domain(int domain, V3 p_new, int depth) {
+        if (job.staples_only) {
+            // StapleConformationalEnumerator::grow_next_domain (:729-752)
+            if (n_stack > 0) {
+                int next = pop();
+                if (inv_gp[next] >= 0) grow_off_scaffold(next, depth);
+                else enumerate_domain(next, p_new, depth + 1);
+            }
+            else if (leaf_is_mine(depth)) {
+                save_weights();
+            }
+            energy += sys().unassign_domain(domain);
+            return;
+        }
         if (n_stack > 0) {
             int next = pop();
             V3 new_p_prev;
@@ -355,10 +419,7 @@ struct Enumerator {
             if (terminal) prev_ps[n_prev++] = new_p_prev;
         }
         else {
-            // a leaf above the cut belongs to the prefix whose remaining digits are zero
-            bool mine = true;
-            for (int l = depth + 1; l < job.split_depth; l++) mine = mine && dig_p[l] == 0 && dig_o[l] == 0;
-            if (mine) {
+            if (leaf_is_mine(depth)) {
                 if (sys().SC().cyclic) {
                     int last = sys().S()->chain_len[0] - 1;
                     if (abssum(sys().pos(0) - sys().pos(last)) == 1) save_weights();
@@ -384,6 +445,10 @@ struct Enumerator {
             dig_o[l] = digit % 6;
         }
         start_prefix();
+        if (job.staples_only) {
+            enumerate_staples_prefix();
+            return;
+        }
         int starting = pop();
         V3 p_new = v3(0, 0, 0);
         unassigned_of(sys().ident(starting)) -= 1;
@@ -407,6 +472,31 @@ struct Enumerator {
         unassigned_of(sys().ident(starting)) += 1;
         sys().unassign_domain(starting);
         push(starting);
+    }
+
+    // StapleConformationalEnumerator::enumerate (:687-717)
+    LDO_HDN void enumerate_staples_prefix() {
+        int n0 = n_stack;
+        if (n_stack == 0) {
+            if (leaf_is_mine(-1)) save_weights();
+            return;
+        }
+        int starting = pop();
+        int sd = inv_gp[starting];
+        V3 p_new = sys().pos(sd);
+        int oc = sys().orc(sd);
+        energy += sys().set_domain_config(starting, p_new, oc < ORE_ZERO ? (oc ^ 1) : oc);
+        if (n_stack > 0) {
+            int next = pop();
+            if (inv_gp[next] >= 0) grow_off_scaffold(next, -1);
+            else enumerate_domain(next, p_new, 0);
+        }
+        else if (leaf_is_mine(-1)) {
+            save_weights();
+        }
+        energy += sys().unassign_domain(starting);
+        // the reference rebuilds its stack for every call; here it is put back as it was
+        n_stack = n0;
     }
 
     LDO_HDN void run(int worker) {

@@ -859,9 +859,6 @@ struct HostEnumerator {
 
     explicit HostEnumerator(ldo_sim& sim):
             s {sim}, p {sim.params}, identities {sim.sysfile->identities}, quiet {std::getenv("LDO_QUIET") != nullptr} {
-        if (p.m_enumerate_staples_only) {
-            throw NotImplemented {"enumerate_staples_only is not available on the device path (scaffold conformations are enumerated)"};
-        }
         if (p.m_max_staple_size != 2 && p.m_misbinding_pot != "Disallowed") throw NotImplemented {"No enumerator available for system"}; // :26-34
         misbinding = p.m_misbinding_pot != "Disallowed";
         for (int d_ident: identities[0]) ident_unassigned[d_ident] = 1; // :204-206
@@ -954,9 +951,11 @@ struct HostEnumerator {
 
     // ConformationalEnumerator::enumerate (:218-258) - on the device
     void enumerate_conformations() {
+        // create_domains_stack: the scaffold's domains with the staples that grow off them (:591-608), or - staples only -
+        // those staples alone (:793-811)
         std::vector<Dom> order;
         for (int d {0}; d != static_cast<int>(identities[0].size()); d++) {
-            order.push_back({0, d});
+            if (!p.m_enumerate_staples_only) order.push_back({0, d});
             if (conf_growthpoints.count({0, d})) staple_stack(conf_growthpoints[{0, d}], order);
         }
         std::vector<int> staple_type, stack_chain, stack_d, go_c, go_d, gn_c, gn_d;
@@ -993,6 +992,9 @@ struct HostEnumerator {
         job.n_out_ops = static_cast<int>(s.ops_out_idx.size());
         job.out_ops = s.ops_out_idx.data();
         job.split_depth = 0;
+        job.staples_only = p.m_enumerate_staples_only ? 1 : 0;
+        job.scaffold_pos = s.sysfile->chains[0].positions.data();
+        job.scaffold_ore = s.sysfile->chains[0].orientations.data();
         const int max_keys {4096};
         std::vector<int> keys(static_cast<size_t>(max_keys) * job.n_out_ops);
         std::vector<double> weights(max_keys);

@@ -10,7 +10,7 @@ import subprocess
 import pytest
 
 from conftest import GOLDEN, INPUTS, make_options, write_inp
-from latticednaorigami_b200.binding import LdoError, Simulation
+from latticednaorigami_b200.binding import Simulation
 
 OPS = "numfulldomains nummisdomains numstackedpairs numstaples"
 PRINT_TOL = 2e-5  # half a unit in the sixth significant digit, both sides rounded
@@ -62,6 +62,11 @@ VARIANTS = {
     "two_order_parameters": dict(temp=350, ops_to_output="numstaples numfulldomains"),
     "two_staples_disallowed": dict(temp=340, max_total_staples=2, misbinding_pot="Disallowed"),
     "excluded_staple": dict(temp=338, excluded_staples="2"),
+    # StapleConformationalEnumerator (enumerate.cpp:666-811): the scaffold keeps the input's configuration
+    "staples_only": dict(temp=340, enumerate_staples_only=True, max_total_staples=2),
+    "staples_only_disallowed": dict(temp=330, enumerate_staples_only=True, max_total_staples=2, misbinding_pot="Disallowed"),
+    "staples_only_on_assembled_snodin": dict(system="snodin_assembled.json", temp=335, enumerate_staples_only=True, max_total_staples=1,
+                                             max_type_staples=1),
 }
 
 
@@ -103,12 +108,6 @@ def test_prefixes_partition_the_tree(hostsim_lib, tmp_path):
     assert len(leaves) == 1, leaves
 
 
-def test_staples_only_enumeration_is_refused(hostsim_lib, tmp_path):
-    sim = Simulation(options(tmp_path, "so", temp=340, enumerate_staples_only=True), 1, 0, lib=hostsim_lib)
-    with pytest.raises(LdoError, match="enumerate_staples_only"):
-        sim.run()
-
-
 def fixture_case(temp):
     with open(os.path.join(GOLDEN, "enum_four_unbound.json")) as f:
         fx = json.load(f)[str(temp)]
@@ -139,7 +138,7 @@ def test_full_enumeration_matches_fixture_on_gpu(tmp_path, temp):
 def test_gpu_enumeration_matches_reference_cli_variants(tmp_path):
     """GPU against the host emulation on the variants of the CPU test (same code, 4144 workers, deeper cut)."""
     from conftest import load_hostsim
-    for name in ("mean_field", "two_staples_disallowed", "three_quarter_turn"):
+    for name in ("mean_field", "two_staples_disallowed", "three_quarter_turn", "staples_only", "staples_only_on_assembled_snodin"):
         kw = VARIANTS[name]
         host = Simulation(options(tmp_path, "h_" + name, **kw), 1, 0, lib=load_hostsim())
         host.run()
