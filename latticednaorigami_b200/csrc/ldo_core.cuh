@@ -1030,18 +1030,19 @@ struct System {
     }
 
     // origami_potential.cpp:587-652
-    LDO_HDN void central_triplet_combos(DeltaConfig& dc, int di, int dj) const {
-        int h1 = step(di, -1);
+    // di_prev .. dj_forw: the chain neighbours of the pair (computed once per evaluation, see stacking_and_steric_terms)
+    LDO_HDN void central_triplet_combos(DeltaConfig& dc, int di, int dj, int di_prev, int di_forw, int dj_prev, int dj_forw) const {
+        int h1 = di_prev;
         int h2 = di;
-        int h3 = step(dj, 1);
-        int h2_next = step(di, 1);
+        int h3 = dj_forw;
+        int h2_next = di_forw;
         if (exists_bound(h1) && exists_bound(h3) && bound(h3) != h2_next && !doubly_contiguous(h1, h2)) {
             if (pair_stacked(dj, h3)) {
                 if (pair_stacked(h1, h2)) triplet_double_stacking(dc, h1, h2, h3);
                 else triplet_single_stacking(dc, h1, h2, h3);
             }
         }
-        h3 = step(dj, -1);
+        h3 = dj_prev;
         if (exists_bound(h1) && exists_bound(h3) && bound(h3) != h1 && !doubly_contiguous(h1, h2)) {
             if (pair_stacked(h1, h2)) {
                 if (pair_stacked(h3, dj)) triplet_double_stacking(dc, h1, h2, h3);
@@ -1052,13 +1053,13 @@ struct System {
             }
         }
         h2 = di;
-        h3 = step(di, 1);
-        h1 = step(dj, 1);
-        int h2_prev = step(di, -1);
+        h3 = di_forw;
+        h1 = dj_forw;
+        int h2_prev = di_prev;
         if (exists_bound(h1) && exists_bound(h3) && bound(h1) != h3 && !doubly_contiguous(h2, h3)) {
             if (pair_stacked(dj, h1) && pair_stacked(h2, h3)) triplet_double_stacking(dc, h1, h2, h3);
         }
-        h1 = step(dj, -1);
+        h1 = dj_prev;
         if (exists_bound(h1) && exists_bound(h3) && bound(h1) != h2_prev && !doubly_contiguous(h2, h3)) {
             if (pair_stacked(h2, h3)) {
                 if (pair_stacked(h1, dj)) triplet_double_stacking(dc, h1, h2, h3);
@@ -1145,9 +1146,9 @@ struct System {
 
     // origami_potential.cpp:231-286, in its three independent parts: the pair (cd + i, cd + i + 1) for i = -1, 0 and the
     // triplet centred on cd
-    LDO_HDN void check_constraints_pair(DeltaConfig& dc, int cd, int i, int j) const {
-        int d1 = step(cd, i);
-        int d2 = step(cd, i + 1);
+    LDO_HDN void check_constraints_pair(DeltaConfig& dc, int cd, int i, int j, int prev, int forw) const {
+        int d1 = i == -1 ? prev : cd;
+        int d2 = i == -1 ? cd : forw;
         if (!(exists_bound(d1) && exists_bound(d2))) return;
         int b1 = bound(d1), b2 = bound(d2);
         if (chain(b1) == chain(b2)) {
@@ -1159,9 +1160,7 @@ struct System {
             regular_pair_constraints(dc, d1, d2, i);
         }
     }
-    LDO_HDN void check_constraints_middle(DeltaConfig& dc, int cd) const {
-        int prev = step(cd, -1);
-        int forw = step(cd, 1);
+    LDO_HDN void check_constraints_middle(DeltaConfig& dc, int cd, int prev, int forw) const {
         if (exists_bound(prev) && exists_bound(forw)) {
             if (pair_stacked(cd, forw)) {
                 if (pair_stacked(prev, cd)) {
@@ -1185,25 +1184,28 @@ struct System {
     // reduced across the warp (every term of the potential is a whole number of stacked pairs: the energy follows as
     // stacked x stacking energy). Called warp-uniformly. The reference stops at the first violation; a violation
     // anywhere gives the same outcome.
-    LDO_HDN void stacking_task(DeltaConfig& dc, int task, int di, int dj) const {
+    LDO_HDN void stacking_task(DeltaConfig& dc, int task, int di, int dj, int di_prev, int di_forw, int dj_prev, int dj_forw) const {
         if (task == 6) {
-            central_triplet_combos(dc, di, dj);
+            central_triplet_combos(dc, di, dj, di_prev, di_forw, dj_prev, dj_forw);
             return;
         }
         int cd = task < 3 ? di : dj, j = task < 3 ? 0 : 1, t = task < 3 ? task : task - 3;
-        if (t < 2) check_constraints_pair(dc, cd, t - 1, j);
-        else check_constraints_middle(dc, cd);
+        int prev = task < 3 ? di_prev : dj_prev, forw = task < 3 ? di_forw : dj_forw;
+        if (t < 2) check_constraints_pair(dc, cd, t - 1, j, prev, forw);
+        else check_constraints_middle(dc, cd, prev, forw);
     }
     LDO_HDN void stacking_and_steric_terms(DeltaConfig& dc, int di, int dj) const {
         int stacked = 0;
         bool violated = false;
+        // the four chain neighbours every part looks at, once (they were 20 calls of step per evaluation)
+        int di_prev = step(di, -1), di_forw = step(di, 1), dj_prev = step(dj, -1), dj_forw = step(dj, 1);
 #if defined(__CUDA_ARCH__) && !defined(LDO_SERIAL_POTENTIAL)
         DeltaConfig part;
         part.e = 0;
         part.stacked = 0;
         part.violated = false;
         int lane = LDO_LANE;
-        if (lane < 7) stacking_task(part, lane, di, dj);
+        if (lane < 7) stacking_task(part, lane, di, dj, di_prev, di_forw, dj_prev, dj_forw);
         violated = __any_sync(0xffffffffu, part.violated);
         stacked = __reduce_add_sync(0xffffffffu, part.stacked);
 #else
@@ -1213,7 +1215,7 @@ struct System {
             part.e = 0;
             part.stacked = 0;
             part.violated = false;
-            stacking_task(part, task, di, dj);
+            stacking_task(part, task, di, dj, di_prev, di_forw, dj_prev, dj_forw);
             stacked += part.stacked;
             violated = violated || part.violated;
         }
