@@ -1198,7 +1198,7 @@ struct System {
         int stacked = 0;
         bool violated = false;
         // the four chain neighbours every part looks at, once (they were 20 calls of step per evaluation)
-        int di_prev = step(di, -1), di_forw = step(di, 1), dj_prev = step(dj, -1), dj_forw = step(dj, 1);
+        int di_prev = bac(di), di_forw = fwd(di), dj_prev = bac(dj), dj_forw = fwd(dj);
 #if defined(__CUDA_ARCH__) && !defined(LDO_SERIAL_POTENTIAL)
         DeltaConfig part;
         part.e = 0;
