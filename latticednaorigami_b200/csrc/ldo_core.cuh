@@ -37,10 +37,18 @@
 #else
 #define LDO_HDC __host__ __device__ __noinline__
 #endif
+// Functions with a single call site on the hot path: merged into their caller (no code growth, one call / return and two
+// instruction-line jumps fewer per use) unless LDO_SPLIT_SINGLE_SITE (A/B twin, profiles/ab_r2.txt)
+#ifdef LDO_SPLIT_SINGLE_SITE
+#define LDO_HDS __host__ __device__ __noinline__
+#else
+#define LDO_HDS __host__ __device__ __forceinline__
+#endif
 #else
 #define LDO_HD
 #define LDO_HDN
 #define LDO_HDC
+#define LDO_HDS
 #endif
 
 // Warps (= replicas) per block of the staged kernel (the in-place kernel uses 4-warp blocks)
@@ -622,7 +630,7 @@ struct System {
         fail(LDO_ERR_TABLE_FULL, d);
     }
     // Linear-probing erase with backward shift (no tombstones: erases are as frequent as inserts)
-    LDO_HDN void table_erase(V3 p) {
+    LDO_HDS void table_erase(V3 p) {
         LDO_COUNT(2);
         uint32_t key = pack_pos(p);
         uint32_t i = hash_slot<K>(key);
@@ -664,7 +672,7 @@ struct System {
         }
         return rotate_turns(ore(d1), ndr, -1) == ore(d2);
     }
-    LDO_HDN bool check_kink(int d1, V3 ndr, int d2) const {
+    LDO_HDS bool check_kink(int d1, V3 ndr, int d2) const {
         V3 o1 = ore(d1), o2 = ore(d2);
         if (ndr == -o1) return false;
         if (ndr == o1) {
@@ -679,7 +687,7 @@ struct System {
         if (ndr == o2 || ndr == -o2) return false;
         return true;
     }
-    LDO_HDN bool check_junction_constraint(int j1, int j2, int k1, int k2) const {
+    LDO_HDS bool check_junction_constraint(int j1, int j2, int k1, int k2) const {
         if (SC().domain_type == DOMAIN_HALFTURN) return true;
         V3 ndr_k1 = pos(k2) - pos(k1);
         if (ndr_k1 == ore(k1)) {
@@ -709,7 +717,7 @@ struct System {
         if (ndr != o1 && ndr != -o1) return check_twist(d1, ndr, d2);
         return false;
     }
-    LDO_HDN int junction_stacking_penalty(int j1, int j2, int j3, int j4, int k1, int k2) const {
+    LDO_HDS int junction_stacking_penalty(int j1, int j2, int j3, int j4, int k1, int k2) const {
         int penalty = 0;
         V3 ndr_k1 = pos(k2) - pos(k1);
         if (ndr_k1 == ore(k1)) {
@@ -914,7 +922,7 @@ struct System {
     }
 
     // origami_potential.cpp:846-934 (passed domains are the kink pair)
-    LDO_HDN void central_single_junction(DeltaConfig& dc, int d1, int d2) const {
+    LDO_HDS void central_single_junction(DeltaConfig& dc, int d1, int d2) const {
         int k1 = d1, k2 = d2;
         int k1b = bound(k1), k2b = bound(k2);
         if (chain(k1b) == chain(k2b) && abs(dindex(k1b) - dindex(k2b)) == 1) return;
@@ -1031,7 +1039,7 @@ struct System {
 
     // origami_potential.cpp:587-652
     // di_prev .. dj_forw: the chain neighbours of the pair (computed once per evaluation, see stacking_and_steric_terms)
-    LDO_HDN void central_triplet_combos(DeltaConfig& dc, int di, int dj, int di_prev, int di_forw, int dj_prev, int dj_forw) const {
+    LDO_HDS void central_triplet_combos(DeltaConfig& dc, int di, int dj, int di_prev, int di_forw, int dj_prev, int dj_forw) const {
         int h1 = di_prev;
         int h2 = di;
         int h3 = dj_forw;
@@ -1088,7 +1096,7 @@ struct System {
     }
 
     // origami_potential.cpp:322-357
-    LDO_HDN void doubly_contig_helix_pair(DeltaConfig& dc, int d1, int d2, int i, int j) const {
+    LDO_HDS void doubly_contig_helix_pair(DeltaConfig& dc, int d1, int d2, int i, int j) const {
         if (j == 1) return;
         V3 ndr = pos(d2) - pos(d1);
         V3 o1 = ore(d1);
@@ -1114,7 +1122,7 @@ struct System {
     }
 
     // origami_potential.cpp:359-417
-    LDO_HDN void doubly_contig_junction_pair(DeltaConfig& dc, int d1, int d2, int j) const {
+    LDO_HDS void doubly_contig_junction_pair(DeltaConfig& dc, int d1, int d2, int j) const {
         int k1 = d1, k2 = d2;
         V3 ndr = pos(k2) - pos(k1);
         if (ore(k1) != ndr) {
@@ -1146,7 +1154,7 @@ struct System {
 
     // origami_potential.cpp:231-286, in its three independent parts: the pair (cd + i, cd + i + 1) for i = -1, 0 and the
     // triplet centred on cd
-    LDO_HDN void check_constraints_pair(DeltaConfig& dc, int cd, int i, int j, int prev, int forw) const {
+    LDO_HDS void check_constraints_pair(DeltaConfig& dc, int cd, int i, int j, int prev, int forw) const {
         int d1 = i == -1 ? prev : cd;
         int d2 = i == -1 ? cd : forw;
         if (!(exists_bound(d1) && exists_bound(d2))) return;
@@ -1160,7 +1168,7 @@ struct System {
             regular_pair_constraints(dc, d1, d2, i);
         }
     }
-    LDO_HDN void check_constraints_middle(DeltaConfig& dc, int cd, int prev, int forw) const {
+    LDO_HDS void check_constraints_middle(DeltaConfig& dc, int cd, int prev, int forw) const {
         if (exists_bound(prev) && exists_bound(forw)) {
             if (pair_stacked(cd, forw)) {
                 if (pair_stacked(prev, cd)) {
@@ -1184,7 +1192,7 @@ struct System {
     // reduced across the warp (every term of the potential is a whole number of stacked pairs: the energy follows as
     // stacked x stacking energy). Called warp-uniformly. The reference stops at the first violation; a violation
     // anywhere gives the same outcome.
-    LDO_HDN void stacking_task(DeltaConfig& dc, int task, int di, int dj, int di_prev, int di_forw, int dj_prev, int dj_forw) const {
+    LDO_HDS void stacking_task(DeltaConfig& dc, int task, int di, int dj, int di_prev, int di_forw, int dj_prev, int dj_forw) const {
         if (task == 6) {
             central_triplet_combos(dc, di, dj, di_prev, di_forw, dj_prev, dj_forw);
             return;
@@ -1470,7 +1478,7 @@ struct System {
     }
 
     // OrigamiSystem::set_checked_domain_config (origami_system.cpp:478-515)
-    LDO_HDN double set_checked_domain_config_base(int d, V3 p, int o) {
+    LDO_HDS double set_checked_domain_config_base(int d, V3 p, int o) {
         commit_place(d, p, o);
         if (S()->weight_pass) {
             S()->num_unassigned--;
@@ -1497,7 +1505,7 @@ struct System {
     }
 
     // internal_unassign_domain + unassign_domain (origami_system.cpp:375-385, 695-760)
-    LDO_HDN double unassign_domain_base(int d) {
+    LDO_HDS double unassign_domain_base(int d) {
         int st = S()->dom[d].state;
         double e = 0;
         int stacked = 0;

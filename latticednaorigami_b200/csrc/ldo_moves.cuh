@@ -549,7 +549,7 @@ struct Engine {
     }
 
     // ---- order parameters and biases ----
-    LDO_HDN int calc_op(int i) const {
+    LDO_HDS int calc_op(int i) const {
         const OpDef& o = OB().ops[i];
         const SysState<K>* s = sys.S();
         switch (o.type) {
@@ -1293,7 +1293,7 @@ struct Engine {
         }
     }
     // remove_activated_endpoint (:322-338)
-    LDO_HDN void cp_remove_activated_endpoint(int dd) {
+    LDO_HDS void cp_remove_activated_endpoint(int dd) {
         int ed = M()->inactive[dd];
         if (ed < 0) return;
         int c = sys.chain(ed), seg = M()->seg_of[ed], di_ = sys.dindex(ed);
