@@ -1077,7 +1077,7 @@ struct System {
     }
 
     // origami_potential.cpp:288-320
-    LDO_HDN void regular_pair_constraints(DeltaConfig& dc, int d1, int d2, int i) const {
+    LDO_HDS void regular_pair_constraints(DeltaConfig& dc, int d1, int d2, int i) const {
         V3 ndr = pos(d2) - pos(d1);
         if (!check_kink(d1, ndr, d2)) {
             dc.violated = true;
@@ -1159,14 +1159,10 @@ struct System {
         int d2 = i == -1 ? cd : forw;
         if (!(exists_bound(d1) && exists_bound(d2))) return;
         int b1 = bound(d1), b2 = bound(d2);
-        if (chain(b1) == chain(b2)) {
-            if (dindex(b1) == dindex(b2) - 1) doubly_contig_helix_pair(dc, d1, d2, i, j);
-            else if (dindex(b1) == dindex(b2) + 1) doubly_contig_junction_pair(dc, d1, d2, j);
-            else regular_pair_constraints(dc, d1, d2, i);
-        }
-        else {
-            regular_pair_constraints(dc, d1, d2, i);
-        }
+        int rel = chain(b1) == chain(b2) ? (int)dindex(b1) - (int)dindex(b2) : 0;
+        if (rel == -1) doubly_contig_helix_pair(dc, d1, d2, i, j);
+        else if (rel == 1) doubly_contig_junction_pair(dc, d1, d2, j);
+        else regular_pair_constraints(dc, d1, d2, i);
     }
     LDO_HDS void check_constraints_middle(DeltaConfig& dc, int cd, int prev, int forw) const {
         if (exists_bound(prev) && exists_bound(forw)) {

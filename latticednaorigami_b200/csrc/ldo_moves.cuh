@@ -1054,7 +1054,7 @@ struct Engine {
         }
     }
     // select_and_set_config for CBStapleRegrowth (cb_movetypes.cpp:104-160, 363-387)
-    LDO_HDN void cb_select_and_set_config(int dom, int prev_dom, bool regrow_old, DD& bias) {
+    LDO_HDS void cb_select_and_set_config(int dom, int prev_dom, bool regrow_old, DD& bias) {
         V3 p_prev = rec_pos(sys.S()->dom[prev_dom]);
         cb_site_weights(p_prev, dom);
         sys.S()->constraints_violated = 0;
@@ -1871,7 +1871,7 @@ struct Engine {
     // placed; its only effects on the feeler (it is unbound on an empty site) are the endpoint updates
     // carried by an EpOverlay. Fills the memo slots and memo_mask. `fd` / `fref`: feeler domain and its
     // reference domain (the parent itself, or an already placed domain).
-    LDO_HDN void rg_fill_feeler_memo(int fd, int fref) {
+    LDO_HDS void rg_fill_feeler_memo(int fd, int fref) {
         LDO_COUNT(9);
         const RgSlot& own = M()->slots[W()->cur_slot];
         V3 refp = rec_pos(sys.S()->dom[W()->ref_d]);
@@ -2050,7 +2050,7 @@ struct Engine {
     //     the untried set. Same distribution as the serial loop, different stream consumption.
     // When most untried configurations can open the serial loop ends after a draw or two and is kept.
     // Returns whether a configuration opened.
-    LDO_HDN bool rg_select_open_config(V3& p, int& o, double& p_c_open) {
+    LDO_HDS bool rg_select_open_config(V3& p, int& o, double& p_c_open) {
         const RgSlot& sl = M()->slots[W()->cur_slot];
         unsigned long long rem = W()->avail;
         int n_rem = popc36(rem);
@@ -2230,7 +2230,7 @@ struct Engine {
         return de;
     }
     // test_config_avail (rg:422-480)
-    LDO_HDN bool rg_test_config_avail() {
+    LDO_HDS bool rg_test_config_avail() {
         LDO_COUNT(13);
         int feels = 0;
         if (feels == W()->max_recoils || W()->di == M()->n_regrow - 1) return true;
@@ -2404,7 +2404,7 @@ struct Engine {
     // (probability p) and, unless it is the last level, the next domain finds an open configuration
     // among all 36 of its own: probability 1 - prod(1 - p') over the feeler slot, independent of the
     // order in which the reference would have tried them.
-    LDO_HDN int rg_count_avail_parallel(bool last_level) {
+    LDO_HDS int rg_count_avail_parallel(bool last_level) {
         const RgSlot& own = M()->slots[W()->cur_slot];
         // feeler availability probability per parent site (warp-uniform)
         double pav[6];
@@ -2480,7 +2480,7 @@ struct Engine {
     }
     // test_config_avail (rg:422-480) for a single feeler level, replayed on an already computed slot:
     // same draws as the general path, no lattice updates
-    LDO_HDN bool rg_feeler_from_slot(int slot) {
+    LDO_HDS bool rg_feeler_from_slot(int slot) {
         const RgSlot& sl = M()->slots[slot];
         unsigned long long av = all_cis();
 #pragma unroll 1
