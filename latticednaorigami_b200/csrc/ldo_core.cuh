@@ -44,11 +44,19 @@
 #else
 #define LDO_HDS __host__ __device__ __forceinline__
 #endif
+// Small functions called very often from a handful of sites: inlined (a call costs two instruction-line requests, its
+// frame and its convergence barrier; the copies cost a few hundred bytes) unless LDO_NO_HOT_INLINE (A/B twin)
+#ifdef LDO_NO_HOT_INLINE
+#define LDO_HDI __host__ __device__ __noinline__
+#else
+#define LDO_HDI __host__ __device__ __forceinline__
+#endif
 #else
 #define LDO_HD
 #define LDO_HDN
 #define LDO_HDC
 #define LDO_HDS
+#define LDO_HDI
 #endif
 
 // Warps (= replicas) per block of the staged kernel (the in-place kernel uses 4-warp blocks)
@@ -612,7 +620,7 @@ struct System {
         }
         return -1;
     }
-    LDO_HDN void table_put(V3 p, int d) {
+    LDO_HDI void table_put(V3 p, int d) {
         LDO_COUNT(1);
         if (!in_coord_range(p)) fail(LDO_ERR_COORD_RANGE, d);
         uint32_t key = pack_pos(p);
@@ -663,14 +671,15 @@ struct System {
     }
 
     // ---- domain constraint checkers (domain.cpp:33-118) ----
-    LDO_HDN bool check_twist(int d1, V3 ndr, int d2) const {
+    LDO_HDN bool check_twist_three_quarter(int d1, V3 ndr, int d2) const { return rotate_turns(ore(d1), ndr, -1) == ore(d2); }
+    LDO_HDI bool check_twist(int d1, V3 ndr, int d2) const {
         if (SC().domain_type == DOMAIN_HALFTURN) {
             // rotate_half on orientation codes: a unit vector parallel to the axis stays, a perpendicular one flips
             int a = ore_code(ndr), c1 = orc(d1), c2 = orc(d2);
             if (a > 5 || c1 >= ORE_ZERO || (c1 >> 1) == (a >> 1)) return c1 == c2;
             return (c1 ^ 1) == c2;
         }
-        return rotate_turns(ore(d1), ndr, -1) == ore(d2);
+        return check_twist_three_quarter(d1, ndr, d2);
     }
     LDO_HDS bool check_kink(int d1, V3 ndr, int d2) const {
         V3 o1 = ore(d1), o2 = ore(d2);
@@ -1230,7 +1239,7 @@ struct System {
     }
 
     // BindingPotential::check_stacking (origami_potential.cpp:149-156)
-    LDO_HDN DeltaConfig check_stacking(int di, int dj) const {
+    LDO_HDI DeltaConfig check_stacking(int di, int dj) const {
         LDO_COUNT(4);
         DeltaConfig dc;
         dc.e = 0;
@@ -1241,7 +1250,7 @@ struct System {
     }
 
     // OrigamiPotential::bind_domain (origami_potential.cpp:1282-1293) on the (possibly overlaid) pair
-    LDO_HDN DeltaConfig bind_domain(int di) const {
+    LDO_HDS DeltaConfig bind_domain(int di) const {
         int dj = bound(di);
         DeltaConfig dc;
         dc.e = 0;
