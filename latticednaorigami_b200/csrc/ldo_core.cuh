@@ -44,12 +44,17 @@
 #else
 #define LDO_HDS __host__ __device__ __forceinline__
 #endif
-// Small functions called very often from a handful of sites: inlined (a call costs two instruction-line requests, its
-// frame and its convergence barrier; the copies cost a few hundred bytes) unless LDO_NO_HOT_INLINE (A/B twin)
-#ifdef LDO_NO_HOT_INLINE
-#define LDO_HDI __host__ __device__ __noinline__
-#else
+// Small functions called very often from several sites stay out of line: inlining them (LDO_HOT_INLINE, an A/B twin) saved
+// 100 calls per move, grew the kernel by 11 KB and cost 10 % (profiles/ab_r2.txt) - copies cost more than calls.
+#ifdef LDO_HOT_INLINE
 #define LDO_HDI __host__ __device__ __forceinline__
+#else
+#define LDO_HDI __host__ __device__ __noinline__
+#endif
+#ifdef LDO_HOT_INLINE_TWIST
+#define LDO_HDT __host__ __device__ __forceinline__
+#else
+#define LDO_HDT LDO_HDI
 #endif
 #else
 #define LDO_HD
@@ -57,6 +62,7 @@
 #define LDO_HDC
 #define LDO_HDS
 #define LDO_HDI
+#define LDO_HDT
 #endif
 
 // Warps (= replicas) per block of the staged kernel (the in-place kernel uses 4-warp blocks)
@@ -672,7 +678,7 @@ struct System {
 
     // ---- domain constraint checkers (domain.cpp:33-118) ----
     LDO_HDN bool check_twist_three_quarter(int d1, V3 ndr, int d2) const { return rotate_turns(ore(d1), ndr, -1) == ore(d2); }
-    LDO_HDI bool check_twist(int d1, V3 ndr, int d2) const {
+    LDO_HDT bool check_twist(int d1, V3 ndr, int d2) const {
         if (SC().domain_type == DOMAIN_HALFTURN) {
             // rotate_half on orientation codes: a unit vector parallel to the axis stays, a perpendicular one flips
             int a = ore_code(ndr), c1 = orc(d1), c2 = orc(d2);
