@@ -44,25 +44,11 @@
 #else
 #define LDO_HDS __host__ __device__ __forceinline__
 #endif
-// Small functions called very often from several sites stay out of line: inlining them (LDO_HOT_INLINE, an A/B twin) saved
-// 100 calls per move, grew the kernel by 11 KB and cost 10 % (profiles/ab_r2.txt) - copies cost more than calls.
-#ifdef LDO_HOT_INLINE
-#define LDO_HDI __host__ __device__ __forceinline__
-#else
-#define LDO_HDI __host__ __device__ __noinline__
-#endif
-#ifdef LDO_HOT_INLINE_TWIST
-#define LDO_HDT __host__ __device__ __forceinline__
-#else
-#define LDO_HDT LDO_HDI
-#endif
 #else
 #define LDO_HD
 #define LDO_HDN
 #define LDO_HDC
 #define LDO_HDS
-#define LDO_HDI
-#define LDO_HDT
 #endif
 
 // Warps (= replicas) per block of the staged kernel (the in-place kernel uses 4-warp blocks)
@@ -626,7 +612,7 @@ struct System {
         }
         return -1;
     }
-    LDO_HDI void table_put(V3 p, int d) {
+    LDO_HDN void table_put(V3 p, int d) {
         LDO_COUNT(1);
         if (!in_coord_range(p)) fail(LDO_ERR_COORD_RANGE, d);
         uint32_t key = pack_pos(p);
@@ -677,15 +663,14 @@ struct System {
     }
 
     // ---- domain constraint checkers (domain.cpp:33-118) ----
-    LDO_HDN bool check_twist_three_quarter(int d1, V3 ndr, int d2) const { return rotate_turns(ore(d1), ndr, -1) == ore(d2); }
-    LDO_HDT bool check_twist(int d1, V3 ndr, int d2) const {
+    LDO_HDN bool check_twist(int d1, V3 ndr, int d2) const {
         if (SC().domain_type == DOMAIN_HALFTURN) {
             // rotate_half on orientation codes: a unit vector parallel to the axis stays, a perpendicular one flips
             int a = ore_code(ndr), c1 = orc(d1), c2 = orc(d2);
             if (a > 5 || c1 >= ORE_ZERO || (c1 >> 1) == (a >> 1)) return c1 == c2;
             return (c1 ^ 1) == c2;
         }
-        return check_twist_three_quarter(d1, ndr, d2);
+        return rotate_turns(ore(d1), ndr, -1) == ore(d2);
     }
     LDO_HDS bool check_kink(int d1, V3 ndr, int d2) const {
         V3 o1 = ore(d1), o2 = ore(d2);
@@ -1245,7 +1230,7 @@ struct System {
     }
 
     // BindingPotential::check_stacking (origami_potential.cpp:149-156)
-    LDO_HDI DeltaConfig check_stacking(int di, int dj) const {
+    LDO_HDN DeltaConfig check_stacking(int di, int dj) const {
         LDO_COUNT(4);
         DeltaConfig dc;
         dc.e = 0;
@@ -1256,7 +1241,7 @@ struct System {
     }
 
     // OrigamiPotential::bind_domain (origami_potential.cpp:1282-1293) on the (possibly overlaid) pair
-    LDO_HDS DeltaConfig bind_domain(int di) const {
+    LDO_HDN DeltaConfig bind_domain(int di) const {
         int dj = bound(di);
         DeltaConfig dc;
         dc.e = 0;

@@ -1306,7 +1306,7 @@ struct Engine {
         }
     }
     // update_endpoints (:340-349)
-    LDO_HDI void cp_update_endpoints(int dd) {
+    LDO_HDN void cp_update_endpoints(int dd) {
         cp_remove_active_endpoint(dd);
         int ed = M()->inactive[dd];
         if (ed >= 0) cp_add_active_endpoint(ed, rec_pos(sys.S()->dom[dd]));
@@ -1342,7 +1342,7 @@ struct Engine {
         return dr > steps || (steps - dr) % 2 != 0;
     }
     // walks_remain (:397-445)
-    LDO_HDS bool cp_walks_remain_seg(int c, int seg, int dd, V3 p, const EpOverlay* ov) const {
+    LDO_HDN bool cp_walks_remain_seg(int c, int seg, int dd, V3 p, const EpOverlay* ov) const {
         LDO_COUNT(6);
         int dir_ = cp_dir_of(c, seg);
         bool rm = ov && ov->rm_chain == c && ov->rm_seg == seg;
@@ -1363,18 +1363,13 @@ struct Engine {
     }
     LDO_HDN bool cp_walks_remain(int dd, V3 p, const EpOverlay* ov = nullptr) const {
         int c = sys.chain(dd);
-        // a stem domain looks at its two segments, any other at its own (one call site: the segment test is merged in)
-        int seg = M()->seg_of[dd], n_segs = 1;
         if (M()->stem_gp[dd] >= 0) {
-            seg = M()->stem_seg0[dd];
-            if (seg < 0) return true; // m_stemd_to_segs[domain] default-constructs to an empty list
-            n_segs = 2;
+            int s0 = M()->stem_seg0[dd];
+            if (s0 < 0) return true; // m_stemd_to_segs[domain] default-constructs to an empty list
+            if (!cp_walks_remain_seg(c, s0, dd, p, ov)) return false;
+            return cp_walks_remain_seg(c, s0 + 1, dd, p, ov);
         }
-#pragma unroll 1
-        for (int k = 0; k < n_segs; k++) {
-            if (!cp_walks_remain_seg(c, seg + k, dd, p, ov)) return false;
-        }
-        return true;
+        return cp_walks_remain_seg(c, M()->seg_of[dd], dd, p, ov);
     }
 
     // StapleNetwork::scan_network (top_constraint_points.cpp:36-161), iterative.
@@ -1698,7 +1693,7 @@ struct Engine {
     }
 
     // ---- CTRG (rg_movetypes.cpp) ----
-    LDO_HDI void eq_push_erased() {
+    LDO_HDN void eq_push_erased() {
         // m_erased_endpoints_q.push_back(get_erased_endpoints())
         if (M()->eq_depth >= MoveScratch<K>::A || M()->eq_npos + M()->n_erased > MoveScratch<K>::E) {
             sys.fail(LDO_ERR_CAPACITY, 11);
@@ -1712,7 +1707,7 @@ struct Engine {
         }
     }
     // restore_endpoints (rg:288-295)
-    LDO_HDI void rg_restore_endpoints() {
+    LDO_HDN void rg_restore_endpoints() {
         cp_remove_activated_endpoint(W()->d);
         if (M()->eq_depth <= 0) {
             sys.fail(LDO_ERR_INTERNAL, 1);
@@ -2030,7 +2025,7 @@ struct Engine {
         return fmin(1.0, exp(-de));
     }
     // test_config_open (rg:345-361)
-    LDO_HDI bool rg_test_config_open(double p) {
+    LDO_HDC bool rg_test_config_open(double p) {
         p = fmin(1.0, p);
         if (p == 1) return true;
         return p > uniform_real();
