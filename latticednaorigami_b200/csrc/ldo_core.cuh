@@ -1039,26 +1039,24 @@ struct System {
 
     // origami_potential.cpp:587-652
     // di_prev .. dj_forw: the chain neighbours of the pair (computed once per evaluation, see stacking_and_steric_terms)
-    // ps: which of the four chain-adjacent pairs (di - 1, di), (di, di + 1), (dj - 1, dj), (dj, dj + 1) are stacked (bits 0-3)
-    LDO_HDS void central_triplet_combos(DeltaConfig& dc, int di, int dj, int di_prev, int di_forw, int dj_prev, int dj_forw, int ps) const {
-        bool st_ip = ps & 1, st_if = ps & 2, st_jp = ps & 4, st_jf = ps & 8;
+    LDO_HDS void central_triplet_combos(DeltaConfig& dc, int di, int dj, int di_prev, int di_forw, int dj_prev, int dj_forw) const {
         int h1 = di_prev;
         int h2 = di;
         int h3 = dj_forw;
         int h2_next = di_forw;
         if (exists_bound(h1) && exists_bound(h3) && bound(h3) != h2_next && !doubly_contiguous(h1, h2)) {
-            if (st_jf) {
-                if (st_ip) triplet_double_stacking(dc, h1, h2, h3);
+            if (pair_stacked(dj, h3)) {
+                if (pair_stacked(h1, h2)) triplet_double_stacking(dc, h1, h2, h3);
                 else triplet_single_stacking(dc, h1, h2, h3);
             }
         }
         h3 = dj_prev;
         if (exists_bound(h1) && exists_bound(h3) && bound(h3) != h1 && !doubly_contiguous(h1, h2)) {
-            if (st_ip) {
-                if (st_jp) triplet_double_stacking(dc, h1, h2, h3);
+            if (pair_stacked(h1, h2)) {
+                if (pair_stacked(h3, dj)) triplet_double_stacking(dc, h1, h2, h3);
                 else triplet_single_stacking(dc, h3, dj, h1);
             }
-            else if (st_jp) {
+            else if (pair_stacked(h3, dj)) {
                 triplet_single_stacking(dc, h1, h2, h3);
             }
         }
@@ -1067,25 +1065,25 @@ struct System {
         h1 = dj_forw;
         int h2_prev = di_prev;
         if (exists_bound(h1) && exists_bound(h3) && bound(h1) != h3 && !doubly_contiguous(h2, h3)) {
-            if (st_jf && st_if) triplet_double_stacking(dc, h1, h2, h3);
+            if (pair_stacked(dj, h1) && pair_stacked(h2, h3)) triplet_double_stacking(dc, h1, h2, h3);
         }
         h1 = dj_prev;
         if (exists_bound(h1) && exists_bound(h3) && bound(h1) != h2_prev && !doubly_contiguous(h2, h3)) {
-            if (st_if) {
-                if (st_jp) triplet_double_stacking(dc, h1, h2, h3);
+            if (pair_stacked(h2, h3)) {
+                if (pair_stacked(h1, dj)) triplet_double_stacking(dc, h1, h2, h3);
                 else triplet_single_stacking(dc, h1, dj, h3);
             }
         }
     }
 
     // origami_potential.cpp:288-320
-    LDO_HDS void regular_pair_constraints(DeltaConfig& dc, int d1, int d2, int i, bool pair_is_stacked) const {
+    LDO_HDS void regular_pair_constraints(DeltaConfig& dc, int d1, int d2, int i) const {
         V3 ndr = pos(d2) - pos(d1);
         if (!check_kink(d1, ndr, d2)) {
             dc.violated = true;
             return;
         }
-        if (pair_is_stacked) {
+        if (pair_stacked(d1, d2)) {
             dc.stacked += 1;
             if (i == -1) backward_single_junction(dc, d1, d2);
             else forward_single_junction(dc, d1, d2);
@@ -1156,7 +1154,7 @@ struct System {
 
     // origami_potential.cpp:231-286, in its three independent parts: the pair (cd + i, cd + i + 1) for i = -1, 0 and the
     // triplet centred on cd
-    LDO_HDS void check_constraints_pair(DeltaConfig& dc, int cd, int i, int j, int prev, int forw, bool pair_is_stacked) const {
+    LDO_HDS void check_constraints_pair(DeltaConfig& dc, int cd, int i, int j, int prev, int forw) const {
         int d1 = i == -1 ? prev : cd;
         int d2 = i == -1 ? cd : forw;
         if (!(exists_bound(d1) && exists_bound(d2))) return;
@@ -1164,12 +1162,12 @@ struct System {
         int rel = chain(b1) == chain(b2) ? (int)dindex(b1) - (int)dindex(b2) : 0;
         if (rel == -1) doubly_contig_helix_pair(dc, d1, d2, i, j);
         else if (rel == 1) doubly_contig_junction_pair(dc, d1, d2, j);
-        else regular_pair_constraints(dc, d1, d2, i, pair_is_stacked);
+        else regular_pair_constraints(dc, d1, d2, i);
     }
-    LDO_HDS void check_constraints_middle(DeltaConfig& dc, int cd, int prev, int forw, bool st_prev, bool st_forw) const {
+    LDO_HDS void check_constraints_middle(DeltaConfig& dc, int cd, int prev, int forw) const {
         if (exists_bound(prev) && exists_bound(forw)) {
-            if (st_forw) {
-                if (st_prev) {
+            if (pair_stacked(cd, forw)) {
+                if (pair_stacked(prev, cd)) {
                     if (doubly_contiguous(prev, cd) && doubly_contiguous(cd, forw)) {
                         triply_contig_helix(dc, prev, cd, forw);
                         if (dc.violated) return;
@@ -1190,35 +1188,28 @@ struct System {
     // reduced across the warp (every term of the potential is a whole number of stacked pairs: the energy follows as
     // stacked x stacking energy). Called warp-uniformly. The reference stops at the first violation; a violation
     // anywhere gives the same outcome.
-    LDO_HDS void stacking_task(DeltaConfig& dc, int task, int di, int dj, int di_prev, int di_forw, int dj_prev, int dj_forw, int ps) const {
+    LDO_HDS void stacking_task(DeltaConfig& dc, int task, int di, int dj, int di_prev, int di_forw, int dj_prev, int dj_forw) const {
         if (task == 6) {
-            central_triplet_combos(dc, di, dj, di_prev, di_forw, dj_prev, dj_forw, ps);
+            central_triplet_combos(dc, di, dj, di_prev, di_forw, dj_prev, dj_forw);
             return;
         }
         int cd = task < 3 ? di : dj, j = task < 3 ? 0 : 1, t = task < 3 ? task : task - 3;
         int prev = task < 3 ? di_prev : dj_prev, forw = task < 3 ? di_forw : dj_forw;
-        bool st_prev = task < 3 ? (ps & 1) : (ps & 4), st_forw = task < 3 ? (ps & 2) : (ps & 8);
-        if (t < 2) check_constraints_pair(dc, cd, t - 1, j, prev, forw, t == 0 ? st_prev : st_forw);
-        else check_constraints_middle(dc, cd, prev, forw, st_prev, st_forw);
+        if (t < 2) check_constraints_pair(dc, cd, t - 1, j, prev, forw);
+        else check_constraints_middle(dc, cd, prev, forw);
     }
     LDO_HDN void stacking_and_steric_terms(DeltaConfig& dc, int di, int dj) const {
         int stacked = 0;
         bool violated = false;
         // the four chain neighbours every part looks at, once (they were 20 calls of step per evaluation)
         int di_prev = bac(di), di_forw = fwd(di), dj_prev = bac(dj), dj_forw = fwd(dj);
-        // ... and which of the four chain-adjacent pairs are stacked (they were up to 14 calls of pair_stacked)
-        int ps = 0;
-        if (exists_bound(di_prev) && pair_stacked(di_prev, di)) ps |= 1;
-        if (exists_bound(di_forw) && pair_stacked(di, di_forw)) ps |= 2;
-        if (exists_bound(dj_prev) && pair_stacked(dj_prev, dj)) ps |= 4;
-        if (exists_bound(dj_forw) && pair_stacked(dj, dj_forw)) ps |= 8;
 #if defined(__CUDA_ARCH__) && !defined(LDO_SERIAL_POTENTIAL)
         DeltaConfig part;
         part.e = 0;
         part.stacked = 0;
         part.violated = false;
         int lane = LDO_LANE;
-        if (lane < 7) stacking_task(part, lane, di, dj, di_prev, di_forw, dj_prev, dj_forw, ps);
+        if (lane < 7) stacking_task(part, lane, di, dj, di_prev, di_forw, dj_prev, dj_forw);
         violated = __any_sync(0xffffffffu, part.violated);
         stacked = __reduce_add_sync(0xffffffffu, part.stacked);
 #else
@@ -1228,7 +1219,7 @@ struct System {
             part.e = 0;
             part.stacked = 0;
             part.violated = false;
-            stacking_task(part, task, di, dj, di_prev, di_forw, dj_prev, dj_forw, ps);
+            stacking_task(part, task, di, dj, di_prev, di_forw, dj_prev, dj_forw);
             stacked += part.stacked;
             violated = violated || part.violated;
         }
