@@ -1241,7 +1241,12 @@ struct System {
     }
 
     // OrigamiPotential::bind_domain (origami_potential.cpp:1282-1293) on the (possibly overlaid) pair
-    LDO_HDN DeltaConfig bind_domain(int di) const {
+#ifdef LDO_X_BIND_MERGE // experiment twin (profiles/ab_r2.txt)
+    LDO_HDS
+#else
+    LDO_HDN
+#endif
+    DeltaConfig bind_domain(int di) const {
         int dj = bound(di);
         DeltaConfig dc;
         dc.e = 0;

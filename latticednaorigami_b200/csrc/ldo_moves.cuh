@@ -1342,7 +1342,12 @@ struct Engine {
         return dr > steps || (steps - dr) % 2 != 0;
     }
     // walks_remain (:397-445)
-    LDO_HDN bool cp_walks_remain_seg(int c, int seg, int dd, V3 p, const EpOverlay* ov) const {
+#ifdef LDO_X_WALKS_MERGE
+    LDO_HDS
+#else
+    LDO_HDN
+#endif
+    bool cp_walks_remain_seg(int c, int seg, int dd, V3 p, const EpOverlay* ov) const {
         LDO_COUNT(6);
         int dir_ = cp_dir_of(c, seg);
         bool rm = ov && ov->rm_chain == c && ov->rm_seg == seg;
@@ -1363,6 +1368,19 @@ struct Engine {
     }
     LDO_HDN bool cp_walks_remain(int dd, V3 p, const EpOverlay* ov = nullptr) const {
         int c = sys.chain(dd);
+#ifdef LDO_X_WALKS_MERGE // experiment twin (profiles/ab_r2.txt): one call site of the segment test, merged in
+        int seg = M()->seg_of[dd], n_segs = 1;
+        if (M()->stem_gp[dd] >= 0) {
+            seg = M()->stem_seg0[dd];
+            if (seg < 0) return true;
+            n_segs = 2;
+        }
+#pragma unroll 1
+        for (int k = 0; k < n_segs; k++) {
+            if (!cp_walks_remain_seg(c, seg + k, dd, p, ov)) return false;
+        }
+        return true;
+#else
         if (M()->stem_gp[dd] >= 0) {
             int s0 = M()->stem_seg0[dd];
             if (s0 < 0) return true; // m_stemd_to_segs[domain] default-constructs to an empty list
@@ -1370,6 +1388,7 @@ struct Engine {
             return cp_walks_remain_seg(c, s0 + 1, dd, p, ov);
         }
         return cp_walks_remain_seg(c, M()->seg_of[dd], dd, p, ov);
+#endif
     }
 
     // StapleNetwork::scan_network (top_constraint_points.cpp:36-161), iterative.
