@@ -44,3 +44,40 @@ def test_linker_options_out_of_range(hostsim_lib, tmp_path):
         "max_linker_length": 3, "num_transforms": 40})
     with pytest.raises(LdoError, match="linker regrowth options"):
         Simulation(write_inp(str(tmp_path / "c.inp"), opts), 1, 0, lib=hostsim_lib)
+
+
+def test_umbrella_sampling_restart_inputs_that_are_refused(hostsim_lib, tmp_path):
+    """read_biases names a file that must exist (us_simulation.cpp:52-57); restart_us_iter needs Boost archives."""
+    base = dict(temp=334, simulation_type="umbrella_sampling", bias_functions_file=os.path.join(INPUTS, "biases_mwus-numfulldomains.json"),
+                bias_functions_mult=1, us_grid_bias_tag="grid", max_num_iters=1, max_D_bias=1.5, equil_steps=10, max_equil_dur=1000,
+                iter_steps=10, max_iter_dur=1000, output_filebase=str(tmp_path / "us"))
+    sim = Simulation(write_inp(str(tmp_path / "u1.inp"), make_options("snodin_unbound.json", read_biases=True,
+                                                                       biases_file=str(tmp_path / "nothing.biases"), **base)), 1, 0, lib=hostsim_lib)
+    with pytest.raises(LdoError, match="Restart bias file .* does not exist"):
+        sim.run()
+    sim = Simulation(write_inp(str(tmp_path / "u2.inp"), make_options("snodin_unbound.json", restart_us_iter=True,
+                                                                       restart_us_filebase=str(tmp_path / "x"), **base)), 1, 0, lib=hostsim_lib)
+    with pytest.raises(LdoError, match="restart_us_iter"):
+        sim.run()
+
+
+def test_move_trackers_are_optional(hostsim_lib, tmp_path):
+    """Without output files the typed trackers are off (no extra per-replica memory); asking for them then is an error."""
+    sim = Simulation(write_inp(str(tmp_path / "t.inp"), make_options("snodin_unbound.json", temp=340)), 2, 0, lib=hostsim_lib)
+    sim.engine.run(50)
+    with pytest.raises(LdoError, match="not enabled"):
+        sim.engine.move_trackers(0)
+    att0, _ = sim.engine.move_stats()
+    sim.engine.enable_move_trackers(True)
+    sim.engine.run(200)
+    sticky, counts = sim.engine.move_trackers(1)
+    att1, acc1 = sim.engine.move_stats()
+    # every attempt made since the trackers were switched on is in exactly one bin of its movetype (standard moveset:
+    # one field each); the orientation rotation has no tracker
+    assert counts[0].sum() == 0
+    for i in range(1, 5):
+        assert counts[i, :, :, 0].sum() == att1[1][i] - att0[1][i]
+    assert counts[1:, :, :, 0].sum() > 0
+    sim.engine.enable_move_trackers(False)
+    with pytest.raises(LdoError, match="not enabled"):
+        sim.engine.move_trackers(0)
