@@ -194,6 +194,14 @@ int ldo_seed(ldo_engine* e, unsigned long long seed, unsigned int first_subseque
 /* Same with an explicit Philox subsequence per replica ([n_replicas]); used to give a replica the same
  * stream whichever GPU it lives on. */
 int ldo_seed_subsequences(ldo_engine* e, unsigned long long seed, const unsigned int* subsequences);
+/* Replaces: RandomEngineStateOutputFile::write / RandomEngineStateInputFile::read_state + the stream extraction of
+ * simulation.cpp:204-212 (files.cpp:220-246, 781-793), which carry the mt19937_64 state as decimal text. Here the state
+ * of a replica's Philox stream is ldo_rng_state_words() numbers: key (2 words), subsequence, stream, 64-bit draw counter,
+ * number of buffered words, buffered words. words is [count][ldo_rng_state_words()]. Setting the state of replica 0 also
+ * re-keys the engine's exchange stream with that state's key. */
+int ldo_rng_state_words(void);
+int ldo_get_rng_state(ldo_engine* e, int first, int count, unsigned long long* words);
+int ldo_set_rng_state(ldo_engine* e, int first, int count, const unsigned long long* words);
 /* Replay mode: serve the replica's draws from a tape (n = 0 detaches). */
 int ldo_attach_tape(ldo_engine* e, int replica, const ldo_tape_draw* draws, long long n);
 int ldo_tape_position(ldo_engine* e, int replica, long long* pos);

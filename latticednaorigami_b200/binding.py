@@ -14,7 +14,7 @@ ENGINE_SYMBOLS = [
     "ldo_engine_create", "ldo_engine_destroy", "ldo_last_error", "ldo_num_replicas",
     "ldo_set_temperature_tables", "ldo_set_moveset", "ldo_set_domain_update_biases", "ldo_set_order_params", "ldo_set_biases",
     "ldo_set_window", "ldo_set_grid_bias", "ldo_get_grid_visits", "ldo_set_control", "ldo_get_control",
-    "ldo_seed", "ldo_seed_subsequences", "ldo_attach_tape", "ldo_tape_position", "ldo_set_state", "ldo_state_capacity",
+    "ldo_seed", "ldo_seed_subsequences", "ldo_rng_state_words", "ldo_get_rng_state", "ldo_set_rng_state", "ldo_attach_tape", "ldo_tape_position", "ldo_set_state", "ldo_state_capacity",
     "ldo_get_state", "ldo_run", "ldo_get_status", "ldo_run_async", "ldo_synchronize", "ldo_stream",
     "ldo_get_energies", "ldo_get_counters", "ldo_get_staple_counts", "ldo_get_order_params",
     "ldo_get_move_stats", "ldo_get_run_timing", "ldo_recompute_energies", "ldo_check_all_constraints", "ldo_center",
@@ -87,6 +87,9 @@ def bind(L):
         "ldo_get_control": (i, [vp, i, i, vp, vp, vp, vp]),
         "ldo_seed": (i, [vp, C.c_ulonglong, C.c_uint]),
         "ldo_seed_subsequences": (i, [vp, C.c_ulonglong, vp]),
+        "ldo_rng_state_words": (i, []),
+        "ldo_get_rng_state": (i, [vp, i, i, vp]),
+        "ldo_set_rng_state": (i, [vp, i, i, vp]),
         "ldo_attach_tape": (i, [vp, i, vp, ll]),
         "ldo_tape_position": (i, [vp, i, vp]),
         "ldo_set_state": (i, [vp, i, i, vp, vp, vp, vp, vp]),
@@ -222,6 +225,16 @@ class Engine:
         sub = np.ascontiguousarray(subsequences, dtype=np.uint32)
         assert len(sub) == self.R
         self._check(self.L.ldo_seed_subsequences(self.h, int(seed), _ptr(sub)))
+
+    def rng_state(self, first=0, count=None):
+        count = self.R - first if count is None else count
+        w = np.zeros((count, self.L.ldo_rng_state_words()), dtype=np.uint64)
+        self._check(self.L.ldo_get_rng_state(self.h, first, count, _ptr(w)))
+        return w
+
+    def set_rng_state(self, words, first=0):
+        w = np.ascontiguousarray(words, dtype=np.uint64).reshape(-1, self.L.ldo_rng_state_words())
+        self._check(self.L.ldo_set_rng_state(self.h, first, len(w), _ptr(w)))
 
     def attach_tape(self, replica, tape):
         tape = np.ascontiguousarray(tape, dtype=DRAW_DTYPE)

@@ -2427,6 +2427,61 @@ int ldo_seed_subsequences(ldo_engine* e, unsigned long long seed, const unsigned
     return b->put_aux(0, b->R, aux.data());
 }
 
+// Philox state of a replica as LDO_RNG_STATE_WORDS numbers: key0, key1, subsequence, stream, counter, number of buffered
+// words, the buffered words. What RandomEngineStateOutputFile / RandomEngineStateInputFile carry for the reference's
+// mt19937_64 (files.cpp:220-246, 781-793; simulation.cpp:204-212).
+int ldo_rng_state_words(void) { return 6 + 4 * LDO_PHILOX_BLOCKS; }
+
+int ldo_get_rng_state(ldo_engine* e, int first, int count, unsigned long long* words) {
+    EngineBase* b = e->b;
+    if (first < 0 || count < 0 || first + count > b->R) return b->fail("bad replica range");
+    std::vector<RepAux> aux(count);
+    if (count && b->get_aux(first, count, aux.data())) return -1;
+    const int W = ldo_rng_state_words();
+    for (int r = 0; r < count; r++) {
+        const Rng& g = aux[r].rng;
+        unsigned long long* w = words + (size_t)r * W;
+        w[0] = g.key0;
+        w[1] = g.key1;
+        w[2] = g.subseq;
+        w[3] = g.stream;
+        w[4] = g.counter;
+        w[5] = (unsigned long long)g.buf_n;
+        for (int k = 0; k < 4 * LDO_PHILOX_BLOCKS; k++) w[6 + k] = g.buf[k];
+    }
+    return 0;
+}
+
+int ldo_set_rng_state(ldo_engine* e, int first, int count, const unsigned long long* words) {
+    EngineBase* b = e->b;
+    if (first < 0 || count < 0 || first + count > b->R) return b->fail("bad replica range");
+    const int W = ldo_rng_state_words();
+    for (int r = 0; r < count; r++) {
+        const unsigned long long* w = words + (size_t)r * W;
+        if (w[0] > 0xffffffffull || w[1] > 0xffffffffull || w[2] > 0xffffffffull || w[3] > 0xffffffffull ||
+            w[5] > (unsigned long long)(4 * LDO_PHILOX_BLOCKS))
+            return b->fail("not a Philox state");
+        for (int k = 0; k < 4 * LDO_PHILOX_BLOCKS; k++)
+            if (w[6 + k] > 0xffffffffull) return b->fail("not a Philox state");
+    }
+    std::vector<RepAux> aux(count);
+    if (count && b->get_aux(first, count, aux.data())) return -1;
+    for (int r = 0; r < count; r++) {
+        Rng& g = aux[r].rng;
+        const unsigned long long* w = words + (size_t)r * W;
+        g.key0 = (uint32_t)w[0];
+        g.key1 = (uint32_t)w[1];
+        g.subseq = (uint32_t)w[2];
+        g.stream = (uint32_t)w[3];
+        g.counter = w[4];
+        g.buf_n = (int)w[5];
+        for (int k = 0; k < 4 * LDO_PHILOX_BLOCKS; k++) g.buf[k] = (uint32_t)w[6 + k];
+    }
+    // the exchange stream is keyed by the engine's seed: it follows the key of the restored states
+    if (count && first == 0) e->seed = (unsigned long long)aux[0].rng.key0 | ((unsigned long long)aux[0].rng.key1 << 32);
+    return count ? b->put_aux(first, count, aux.data()) : 0;
+}
+
 int ldo_attach_tape(ldo_engine* e, int replica, const ldo_tape_draw* draws, long long n) {
     if (replica < 0 || replica >= e->b->R) return e->b->fail("bad replica index");
     return e->b->attach_tape(replica, draws, n);

@@ -30,7 +30,7 @@ namespace {
 thread_local std::string g_host_error;
 
 struct ReplicaFiles {
-    std::unique_ptr<std::ofstream> trj, counts, staples, staplestates, times, ene, ops;
+    std::unique_ptr<std::ofstream> trj, counts, staples, staplestates, times, ene, ops, randstate;
     std::unique_ptr<std::ofstream> vcf, states, ores; // setup_config_files (simulation.cpp:150-180)
 };
 } // namespace
@@ -172,6 +172,9 @@ void open_output_files(ldo_sim& s) {
             for (auto const& tag: p.m_ops_to_output) *f.ops << tag << ", "; // header quirk (App. A14)
             *f.ops << "\n";
         }
+        // RandomEngineStateOutputFile (simulation.cpp:137-144, files.cpp:781-793): one line per write, the state of the
+        // replica's generator as decimal numbers - here the Philox state of ldo_get_rng_state
+        if (p.m_rand_engine_state_output_freq != 0) f.randstate.reset(new std::ofstream {base + ".randstate"});
     }
     s.ops_out_idx.clear();
     for (auto const& tag: p.m_ops_to_output) {
@@ -183,6 +186,39 @@ void open_output_files(ldo_sim& s) {
     }
 }
 
+// GCMCSimulation constructor (simulation.cpp:204-212) + RandomEngineStateInputFile::read_state (files.cpp:232-246): with no
+// seed specified and read_rand_engine_state set, the generator continues from line restart_step (counted from 0) of
+// rand_engine_state_file. A batch of replicas reads "<file without .randstate>-<replica>.randstate", the names
+// open_output_files gives a batch.
+void restore_rng_states(ldo_sim& s) {
+    InputParameters const& p = s.params;
+    std::cout << "Loading random engine state\n";
+    int const W {ldo_rng_state_words()};
+    std::vector<unsigned long long> words(static_cast<size_t>(s.R) * W);
+    for (int r {0}; r != s.R; r++) {
+        std::string name {p.m_rand_engine_state_file};
+        if (s.R * s.n_ranks != 1) {
+            std::string const ext {".randstate"};
+            std::string stem {name};
+            if (stem.size() >= ext.size() && stem.compare(stem.size() - ext.size(), ext.size(), ext) == 0) stem.resize(stem.size() - ext.size());
+            name = stem + "-" + std::to_string(s.rank * s.R + r) + ext;
+        }
+        std::ifstream in {name};
+        if (!in) throw FileError {"Random engine state input file " + name + " does not exist"};
+        std::string line;
+        for (int i {0}; i <= p.m_restart_step; i++) {
+            if (!std::getline(in, line)) {
+                throw FileError {"Step " + std::to_string(p.m_restart_step) + " not found in trajectory input file" + name};
+            }
+        }
+        std::istringstream is {line};
+        for (int k {0}; k != W; k++) {
+            if (!(is >> words[static_cast<size_t>(r) * W + k])) throw FileError {"Random engine state in " + name + " is not a Philox state of this engine"};
+        }
+    }
+    s.check(ldo_set_rng_state(s.eng, 0, s.R, words.data()));
+}
+
 bool due(int freq, long long step) { return freq != 0 && step % freq == 0; }
 
 // Output at `step` for every replica (simulation.cpp:641-646 and the writers of files.cpp:529-778)
@@ -192,6 +228,19 @@ void write_outputs(ldo_sim& s, long long step) {
     bool w_trj {due(p.m_configs_output_freq, step)}, w_counts {due(p.m_counts_output_freq, step)};
     bool w_times {due(p.m_times_output_freq, step)}, w_ene {due(p.m_energies_output_freq, step)};
     bool w_ops {due(p.m_order_params_output_freq, step)}, w_vtf {due(p.m_vtf_output_freq, step)};
+    bool w_rand {due(p.m_rand_engine_state_output_freq, step)};
+    if (w_rand) {
+        int const W {ldo_rng_state_words()};
+        std::vector<unsigned long long> words(static_cast<size_t>(s.R) * W);
+        s.check(ldo_get_rng_state(s.eng, 0, s.R, words.data()));
+        for (int r {0}; r != s.R; r++) {
+            std::ofstream* f {s.files[r].randstate.get()};
+            if (!f) continue;
+            for (int k {0}; k != W; k++) *f << (k ? " " : "") << words[static_cast<size_t>(r) * W + k];
+            *f << "\n";
+            f->flush();
+        }
+    }
     if (!(w_trj || w_counts || w_times || w_ene || w_ops || w_vtf)) return;
     int nst {static_cast<int>(s.sysfile->identities.size()) - 1};
     std::vector<double> ene;
@@ -325,7 +374,7 @@ long long next_output_step(ldo_sim& s, long long cur, long long end) {
     if (s.files.empty()) return end;
     long long next {end};
     int freqs[] {p.m_configs_output_freq, p.m_counts_output_freq, p.m_times_output_freq, p.m_energies_output_freq, p.m_order_params_output_freq,
-                 p.m_vtf_output_freq};
+                 p.m_vtf_output_freq, p.m_rand_engine_state_output_freq};
     for (int f: freqs) {
         if (f == 0) continue;
         long long n {(cur / f + 1) * f};
@@ -1573,6 +1622,7 @@ ldo_sim* ldo_sim_create(const char* inp_path, int n_replicas, int device, int ra
         else {
             s->check(ldo_seed(s->eng, seed, static_cast<unsigned int>(s->rank * n_replicas)));
         }
+        if (p.m_random_seed == -1 && p.m_read_rand_engine_state) restore_rng_states(*s);
         s->start = std::chrono::steady_clock::now();
     } catch (std::exception const& e) {
         g_host_error = e.what();

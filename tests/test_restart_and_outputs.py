@@ -7,6 +7,9 @@
   reference is read back by both codes, which then continue identically under a replayed tape.
 * Replica-exchange restart (ptmc_simulation.cpp:38-83): per-replica restart_traj_filebase-<rank><postfix> and the last
   row of restart_swap_file.
+* rand_engine_state_output_freq / read_rand_engine_state (files.cpp:220-246, 781-793; simulation.cpp:204-212): the state
+  of the generator written next to the trajectory; a run restarted from frame k of both continues as the uninterrupted
+  run did (production draws, Philox state instead of the reference's mt19937_64 text).
 CPU: host emulation of the device sources; GPU: the CUDA library."""
 import numpy as np
 import pytest
@@ -129,6 +132,69 @@ def trj_restart(lib, oracle, tmp_path):
                                                                      restart_step=9)), 1, 0, lib=lib)
 
 
+def randstate_restart(lib, tmp_path):
+    """An interrupted run = the uninterrupted one: restart from frame 2 of .trj and line 2 of .randstate (production mode).
+    The key, the subsequence, the draw counter and the buffered words all come from the file: no seed is given."""
+    kw = dict(temp=338, configs_output_freq=100, rand_engine_state_output_freq=100)
+    a = Simulation(write_inp(str(tmp_path / "a.inp"), make_options("snodin_unbound.json", random_seed=77, ct_steps=600,
+                                                                    output_filebase=str(tmp_path / "a"), **kw)), 1, 0, lib=lib)
+    a.run()
+    a.engine.assert_ok()
+    lines = (tmp_path / "a.randstate").read_text().splitlines()
+    W = a.engine.rng_state().shape[1]
+    assert len(lines) == 6 and all(len(l.split()) == W for l in lines)
+    assert [int(x) for x in lines[-1].split()] == a.engine.rng_state()[0].tolist()
+    assert int(lines[0].split()[0]) == 77 and len({l.split()[4] for l in lines}) == 6  # key = seed; the counter advances
+    b = Simulation(write_inp(str(tmp_path / "b.inp"), make_options(
+        "snodin_unbound.json", ct_steps=300, restart_traj_file=str(tmp_path / "a.trj"), restart_step=2, read_rand_engine_state=True,
+        rand_engine_state_file=str(tmp_path / "a.randstate"), output_filebase=str(tmp_path / "b"), **kw)), 1, 0, lib=lib)
+    assert [int(x) for x in lines[2].split()] == b.engine.rng_state()[0].tolist()
+    b.run()
+    b.engine.assert_ok()
+    # (unique chain indices restart at the largest one of the frame, origami_system.cpp:1000-1003: everything else is equal)
+    def without_uids(st):  # bound partners name their chain by its unique index: renamed to the chain's position
+        st = dict(st)
+        rank = {int(u): k for k, u in enumerate(st["chain_index"])}
+        bound = st["bound"].copy()
+        for row in bound:
+            if row[0] >= 0:
+                row[0] = rank[int(row[0])]
+        st["bound"] = bound
+        st["chain_index"] = np.arange(len(st["chain_index"]), dtype=st["chain_index"].dtype)
+        return st
+    assert_state_equal(without_uids(b.engine.state(0)), without_uids(a.engine.state(0)), "restarted run")
+    assert np.array_equal(b.engine.rng_state(), a.engine.rng_state())
+
+    def frames(name):  # chain lines without the unique index
+        out = []
+        for f in (tmp_path / name).read_text().split("\n\n"):
+            if f.strip():
+                rows = f.strip().split("\n")[1:]
+                out.append(tuple(r.split()[1] if k % 3 == 0 else r for k, r in enumerate(rows)))
+        return out
+    fa, fb = frames("a.trj"), frames("b.trj")
+    assert fa[3:] == fb and len(set(fa)) == 6  # the same frames after the restart point, on an evolving trajectory
+    assert (tmp_path / "b.randstate").read_text().splitlines() == lines[3:]
+    # a specified seed wins over the file (simulation.cpp:200-204); a missing line or file is a FileError
+    c = Simulation(write_inp(str(tmp_path / "c.inp"), make_options(
+        "snodin_unbound.json", random_seed=5, read_rand_engine_state=True, rand_engine_state_file=str(tmp_path / "a.randstate"), **kw)), 1, 0, lib=lib)
+    assert c.engine.rng_state()[0, 0] == 5 and c.engine.rng_state()[0, 4] == 0
+    for bad in (dict(restart_step=9, rand_engine_state_file=str(tmp_path / "a.randstate")), dict(rand_engine_state_file=str(tmp_path / "none.randstate"))):
+        with pytest.raises(Exception, match="not found|does not exist"):
+            Simulation(write_inp(str(tmp_path / "bad.inp"), make_options("snodin_unbound.json", read_rand_engine_state=True, **bad)), 1, 0, lib=lib)
+    # a batch of replicas writes and reads <filebase>-<replica>.randstate
+    d = Simulation(write_inp(str(tmp_path / "d.inp"), make_options("snodin_unbound.json", random_seed=9, ct_steps=200,
+                                                                    output_filebase=str(tmp_path / "d"), **kw)), 2, 0, lib=lib)
+    d.run()
+    e = Simulation(write_inp(str(tmp_path / "e.inp"), make_options(
+        "snodin_unbound.json", restart_step=1, read_rand_engine_state=True, rand_engine_state_file=str(tmp_path / "d.randstate"))), 2, 0, lib=lib)
+    assert np.array_equal(e.engine.rng_state(), d.engine.rng_state()) and e.engine.rng_state()[1, 2] == 1
+
+
+def test_randstate_restart(hostsim_lib, tmp_path):
+    randstate_restart(hostsim_lib, tmp_path)
+
+
 def test_output_files_on_an_evolving_trajectory(hostsim_lib, oracle, tmp_path):
     evolving_outputs(hostsim_lib, oracle, tmp_path)
 
@@ -150,4 +216,6 @@ def test_outputs_and_restart_gpu(oracle, tmp_path):
     (tmp_path / "p").mkdir()
     evolving_outputs(None, oracle, tmp_path / "o")
     trj_restart(None, oracle, tmp_path / "r")
+    (tmp_path / "s").mkdir()
+    randstate_restart(None, tmp_path / "s")
     exchange_against_oracle(oracle, tmp_path / "p", None, "ut", swaps=8, restart=True)
