@@ -287,7 +287,7 @@ int ldo_get_move_stats(ldo_engine* e, long long* attempts, long long* accepts);
 /* Typed move trackers (movetypes.hpp:327-339, utility.hpp:100-147): the breakdown the reference's .moves summary gives
  * for each movetype - staple moves by staple type (exchange: insertions and deletions apart; regrowth: attempts with and
  * without staples in the system apart), scaffold regrowth by the number of scaffold domains (CTCB: and of staples).
- * Off by default (12 KB per replica, one extra store per move); ldo_sim_run enables them when it writes output files.
+ * Off by default (25 KB per replica, one extra store per move); ldo_sim_run enables them when it writes output files.
  * counts[n_movetypes][2 fields][LDO_TRACKER_BINS values][attempts, accepts]; field / value per movetype type:
  *   MetStapleExchange   field 0 insertions, 1 deletions; value = staple type
  *   Met/CBStapleRegrowth field 0 staples present, 1 no staples in the system; value = staple type (as last set)
@@ -297,6 +297,14 @@ int ldo_get_move_stats(ldo_engine* e, long long* attempts, long long* accepts);
 #define LDO_TRACKER_BINS 64
 int ldo_enable_move_trackers(ldo_engine* e, int on);
 int ldo_get_move_trackers(ldo_engine* e, int replica, int* sticky, unsigned int* counts);
+/* Replaces: LinkerRegrowthMCMovetype::m_tracker / m_tracking (transform_movetypes.hpp:104-105, utility.hpp:136-144) and
+ * the three tables of its write_log_summary (transform_movetypes.cpp:64-139). sticky[n_movetypes][6]: linker domains,
+ * linker staples, central domains, central staples, sum of the displacement, turns, as the last move of each type left
+ * them. entries[n_entries][6] (room for LDO_LINKER_TRACKER_CAP): movetype, table (0 = linker / central domains,
+ * 1 = linker / central staples, 2 = displacement sum / turns), the pair of values, attempts, accepts. dropped: updates
+ * lost because the list was full. */
+#define LDO_LINKER_TRACKER_CAP 1024
+int ldo_get_linker_trackers(ldo_engine* e, int replica, int* sticky, int* n_entries, int* entries, int* dropped);
 
 /* Diagnostics (no reference counterpart): [n_replicas][3] = start ns, end ns (device global timer) and SM id
  * of every replica's warp in the last ldo_run launch; used by profiles/ to measure load imbalance. */

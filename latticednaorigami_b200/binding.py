@@ -20,7 +20,7 @@ ENGINE_SYMBOLS = [
     "ldo_get_move_stats", "ldo_get_run_timing", "ldo_recompute_energies", "ldo_check_all_constraints", "ldo_center",
     "ldo_set_exchange_ladder", "ldo_exchange_collect", "ldo_exchange_pt", "ldo_exchange_pt_2d", "ldo_exchange_acceptance_p", "ldo_get_reduced_staple_u", "ldo_set_step", "ldo_exchange_buffers",
     "ldo_exchange_windows", "ldo_exchange_collect_async", "ldo_exchange_state_set", "ldo_exchange_state_get", "ldo_exchange_pt_async", "ldo_set_exchange_tape", "ldo_exchange_tape_status", "ldo_set_reference_draw_order", "ldo_build_info", "ldo_launch_count", "ldo_state_bytes", "ldo_checkpoint_size", "ldo_checkpoint_save", "ldo_checkpoint_load",
-    "ldo_enumerate_conformations", "ldo_get_exchange_mults", "ldo_replace_config", "ldo_enable_move_trackers", "ldo_get_move_trackers",
+    "ldo_enumerate_conformations", "ldo_get_exchange_mults", "ldo_replace_config", "ldo_enable_move_trackers", "ldo_get_move_trackers", "ldo_get_linker_trackers",
 ]
 HOST_SYMBOLS = [
     "ldo_host_last_error", "ldo_comm_unique_id", "ldo_sim_comm_init", "ldo_sim_exchange_round", "ldo_sim_create", "ldo_sim_destroy", "ldo_sim_engine", "ldo_sim_run",
@@ -136,6 +136,7 @@ def bind(L):
         "ldo_replace_config": (i, [vp, i, i, vp, vp, vp, vp, vp]),
         "ldo_enable_move_trackers": (i, [vp, i]),
         "ldo_get_move_trackers": (i, [vp, i, vp, vp]),
+        "ldo_get_linker_trackers": (i, [vp, i, vp, vp, vp, vp]),
         "ldo_sim_enumeration_summary": (i, [vp, vp]),
         "ldo_host_last_error": (C.c_char_p, []),
         "ldo_sim_create": (vp, [C.c_char_p, i, i, i, i]),
@@ -334,6 +335,14 @@ class Engine:
         counts = np.zeros((self.n_movetypes, 2, 64, 2), dtype=np.uint32)
         self._check(self.L.ldo_get_move_trackers(self.h, int(replica), _ptr(sticky), _ptr(counts)))
         return sticky, counts
+
+    def linker_trackers(self, replica):
+        """(sticky[n_movetypes, 6], entries[n, (movetype, table, value a, value b, attempts, accepts)], dropped)"""
+        sticky = np.zeros((self.n_movetypes, 6), dtype=np.int32)
+        entries = np.zeros((1024, 6), dtype=np.int32)
+        n, dropped = C.c_int(0), C.c_int(0)
+        self._check(self.L.ldo_get_linker_trackers(self.h, int(replica), _ptr(sticky), C.byref(n), _ptr(entries), C.byref(dropped)))
+        return sticky, entries[:n.value].copy(), dropped.value
 
     def recompute_energies(self):
         e = np.zeros(self.R)

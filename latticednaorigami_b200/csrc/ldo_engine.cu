@@ -2648,6 +2648,30 @@ int ldo_get_move_trackers(ldo_engine* e, int replica, int* sticky, unsigned int*
     return 0;
 }
 
+static_assert(LDO_TRK_LK_CAP == LDO_LINKER_TRACKER_CAP, "linker tracker capacity of the ABI and of the device code differ");
+int ldo_get_linker_trackers(ldo_engine* e, int replica, int* sticky, int* n_entries, int* entries, int* dropped) {
+    EngineBase* b = e->b;
+    if (replica < 0 || replica >= b->R) return b->fail("bad replica index");
+    TrackStats t;
+    if (b->get_trackers(replica, &t)) return -1;
+    int n = b->shared.ms.n;
+    for (int i = 0; i < n; i++)
+        for (int k = 0; k < 6; k++) sticky[6 * i + k] = t.lk_sticky[i][k];
+    *n_entries = t.lk_n;
+    *dropped = t.lk_dropped;
+    for (int k = 0; k < t.lk_n; k++) {
+        unsigned key = t.lk_key[k];
+        int* o = entries + 6 * k;
+        o[0] = (int)(key >> 28);
+        o[1] = (int)(key >> 26 & 3);
+        o[2] = (int)(key << 6) >> 19; // two signed 13-bit values
+        o[3] = (int)(key << 19) >> 19;
+        o[4] = (int)t.lk_cnt[k][0];
+        o[5] = (int)t.lk_cnt[k][1];
+    }
+    return 0;
+}
+
 int ldo_get_run_timing(ldo_engine* e, long long* out) {
     EngineBase* b = e->b;
     if (dev_d2h(out, b->run_timing_ptr(), sizeof(long long) * 3 * b->R, b->stream)) return b->fail(dev_err());

@@ -404,11 +404,25 @@ struct MoveStats {
 // number of scaffold domains (and of staples) for the scaffold regrowth moves. Optional (ldo_enable_move_trackers): kept
 // outside RepAux so that checkpoints and the run kernel's staged state do not grow. The tracker fields of a movetype
 // object persist between its moves in the reference (a field a move does not set keeps its last value): sticky_a/_b.
+// The transform / linker movetypes track six numbers (CTCBLinkerRegrowthTracking, utility.hpp:136-144: linker domains,
+// linker staples, central domains, central staples, sum of the displacement, turns; central_domains_connected is never
+// set) and summarise them as three tables keyed by pairs (transform_movetypes.cpp:64-139): the pairs met so far are kept in
+// a list (lk_key = movetype, table, two 13-bit values), the fields of the move under way in lk_now / lk_set.
 #define LDO_TRK_BINS 64
+#define LDO_TRK_LK_CAP 1024
 struct TrackStats {
     int sticky_a[LDO_MAX_MOVETYPES], sticky_b[LDO_MAX_MOVETYPES];
     unsigned cnt[LDO_MAX_MOVETYPES][2][LDO_TRK_BINS][2]; // [movetype][field][value][attempts, accepts]
+    int lk_sticky[LDO_MAX_MOVETYPES][6];
+    int lk_now[6];
+    unsigned lk_set;
+    int lk_n, lk_dropped;
+    unsigned lk_key[LDO_TRK_LK_CAP];
+    unsigned lk_cnt[LDO_TRK_LK_CAP][2];
 };
+LDO_HD inline unsigned trk_lk_key(int movetype, int table, int a, int b) {
+    return ((unsigned)movetype << 28) | ((unsigned)table << 26) | (((unsigned)a & 0x1fffu) << 13) | ((unsigned)b & 0x1fffu);
+}
 
 // ---------------------------------------------------------------------------------------------
 // The per-replica engine
@@ -3461,6 +3475,9 @@ struct Engine {
             center.k = C()->tf_center[sel];
             disp.k = C()->tf_disp[sel];
             lk_apply_transformation(disp, center, C()->tf_axis[sel], C()->tf_turns[sel]);
+#ifndef LDO_NO_LINKER_TRACKERS
+            if (TRK()) trk_lk(4, vx(disp) + vy(disp) + vz(disp), C()->tf_turns[sel]);
+#endif
         }
         return bias;
     }
@@ -3493,6 +3510,7 @@ struct Engine {
         else lk_select_and_setup(md);
         if (M()->rejected || sys.S()->status != LDO_OK) return false;
         lk_find_central_domains();
+        trk_lk_segments();
         DD bias = dd_from(1.0), new_bias = dd_from(1.0);
 #pragma unroll 1
         for (int pass = 0; pass < 2; pass++) {
@@ -3522,6 +3540,7 @@ struct Engine {
         lk_select_and_setup(md);
         if (M()->rejected || sys.S()->status != LDO_OK) return false;
         lk_find_central_domains();
+        trk_lk_segments();
         if (M()->n_regrow < 2) {
             // both linkers empty: the reference indexes m_regrow_ds[1] past its end here
             sys.fail(LDO_ERR_INTERNAL, 3);
@@ -3638,6 +3657,37 @@ struct Engine {
             fb = 1;
             vb = b;
             break;
+#ifndef LDO_NO_LINKER_TRACKERS // A/B knob (profiles/ab_r2.txt): the linker movetypes' trackers compiled out
+        case MT_CTCB_LINKER_REGROWTH:
+        case MT_CTCB_CLUSTERED_LINKER_REGROWTH:
+        case MT_CTRG_LINKER_REGROWTH: // the six fields the move set (trk_lk), the others as its last move left them
+            if (LDO_LANE == 0) {
+                int* f = t->lk_sticky[i];
+#pragma unroll 1
+                for (int k = 0; k < 6; k++)
+                    if (t->lk_set >> k & 1) f[k] = t->lk_now[k];
+                t->lk_set = 0;
+#pragma unroll 1
+                for (int tb = 0; tb < 3; tb++) {
+                    unsigned key = tb == 0 ? trk_lk_key(i, 0, f[0], f[2]) : (tb == 1 ? trk_lk_key(i, 1, f[1], f[3]) : trk_lk_key(i, 2, f[4], f[5]));
+                    int e = 0;
+#pragma unroll 1
+                    while (e < t->lk_n && t->lk_key[e] != key) e++;
+                    if (e == t->lk_n) {
+                        if (e == LDO_TRK_LK_CAP) {
+                            t->lk_dropped++;
+                            continue;
+                        }
+                        t->lk_key[e] = key;
+                        t->lk_cnt[e][0] = t->lk_cnt[e][1] = 0;
+                        t->lk_n = e + 1;
+                    }
+                    t->lk_cnt[e][0] += 1;
+                    t->lk_cnt[e][1] += accepted ? 1 : 0;
+                }
+            }
+            break;
+#endif
         default: break;
         }
         if (LDO_LANE == 0) {
@@ -3656,6 +3706,30 @@ struct Engine {
         }
         LDO_SYNCWARP();
     }
+    // m_tracker fields of the linker movetypes (transform_movetypes.cpp:393-394, 879-882, 1155-1158)
+#ifdef LDO_NO_LINKER_TRACKERS
+    LDO_HD void trk_lk(int, int, int) {}
+    LDO_HD void trk_lk_segments() {}
+#else
+    LDO_HDN void trk_lk(int field, int a, int b) {
+        TrackStats* t = TRK();
+        if (t && LDO_LANE == 0) {
+            t->lk_now[field] = a;
+            t->lk_now[field + 1] = b;
+            t->lk_set |= 3u << field;
+        }
+    }
+#endif
+#ifndef LDO_NO_LINKER_TRACKERS
+    LDO_HDN void trk_lk_segments() {
+        if (!TRK()) return;
+        int cs = 0;
+#pragma unroll 1
+        for (int c = 1; c < K::C; c++) cs += C()->cen_chain[c] ? 1 : 0;
+        trk_lk(0, C()->n_lnk[0] + C()->n_lnk[1], num_regrowth_staples());
+        trk_lk(2, C()->n_sel, cs);
+    }
+#endif
     LDO_HDN int num_regrowth_staples() const {
         int n = 0;
 #pragma unroll 1

@@ -416,8 +416,7 @@ bool simulate(ldo_sim& s, long long steps) {
 // GCMCSimulation::write_log_summary (simulation.cpp:706-718): <filebase>.moves holds, for every movetype but the
 // orientation rotation (whose write_log_summary is empty, orientation_movetype.cpp:28), the header of
 // movetypes.cpp:88-96 and the movetype's own breakdown from its trackers (met_movetypes.cpp:145-190, 442-468;
-// cb_movetypes.cpp:264-290, 626-675, 816-870; rg_movetypes.cpp:593-627, 754-786). The transform / linker movetypes get
-// the header only (their seven-field trackers are not kept on the device).
+// cb_movetypes.cpp:264-290, 626-675, 816-870; rg_movetypes.cpp:593-627, 754-786; transform_movetypes.cpp:64-139).
 void write_move_summary(ldo_sim& s) {
     if (s.params.m_output_filebase.empty()) return;
     size_t n {s.movetypes.size()};
@@ -426,10 +425,14 @@ void write_move_summary(ldo_sim& s) {
     int nst {static_cast<int>(s.sysfile->identities.size()) - 1};
     std::vector<int> sticky(2 * n);
     std::vector<unsigned int> counts(n * 2 * LDO_TRACKER_BINS * 2);
+    std::vector<int> lk_sticky(6 * n), lk_entries(6 * LDO_LINKER_TRACKER_CAP);
     std::vector<double> mults(static_cast<size_t>(s.R) * std::max(nst, 1));
     for (int r {0}; r != s.R; r++) {
         std::ofstream o {replica_filebase(s, r) + ".moves"};
         bool typed {ldo_get_move_trackers(s.eng, r, sticky.data(), counts.data()) == 0};
+        int lk_n {0}, lk_dropped {0};
+        if (typed) s.check(ldo_get_linker_trackers(s.eng, r, lk_sticky.data(), &lk_n, lk_entries.data(), &lk_dropped));
+        if (lk_dropped != 0) std::cerr << "warning: " << lk_dropped << " linker tracker updates of replica " << r << " were dropped (list full)\n";
         auto cnt = [&](size_t i, int field, int value, int what) {
             return static_cast<int>(counts[((i * 2 + field) * LDO_TRACKER_BINS + value) * 2 + what]);
         };
@@ -491,6 +494,26 @@ void write_move_summary(ldo_sim& s) {
                 if (type == LDO_MT_CTCB_SCAFFOLD_REGROWTH || type == LDO_MT_CTCB_JUMP_SCAFFOLD_REGROWTH) {
                     for (int v {0}; v != LDO_TRACKER_BINS; v++)
                         if (cnt(i, 1, v, 0) != 0) block("Number of staples", v, cnt(i, 1, v, 0), cnt(i, 1, v, 1));
+                }
+            }
+            else if (type == LDO_MT_CTCB_LINKER_REGROWTH || type == LDO_MT_CTCB_CLUSTERED_LINKER_REGROWTH || type == LDO_MT_CTRG_LINKER_REGROWTH) {
+                // LinkerRegrowthMCMovetype::write_log_summary (transform_movetypes.cpp:64-139): three tables keyed by pairs,
+                // each in ascending order of the pair, an empty line between them
+                char const* titles[] {"Number of linker/central domains", "Number of linker/central staples", "Sum/number of displacement/turns"};
+                for (int table {0}; table != 3; table++) {
+                    std::map<std::pair<int, int>, std::pair<int, int>> rows;
+                    for (int k {0}; k != lk_n; k++) {
+                        int const* en {&lk_entries[6 * static_cast<size_t>(k)]};
+                        if (en[0] == static_cast<int>(i) && en[1] == table) rows[{en[2], en[3]}] = {en[4], en[5]};
+                    }
+                    if (table != 0) o << "\n";
+                    for (auto const& row: rows) {
+                        double freq {static_cast<double>(row.second.second) / row.second.first};
+                        o << "    " << titles[table] << ": " << row.first.first << "/" << row.first.second << "\n";
+                        o << "        Attempts: " << row.second.first << "\n";
+                        o << "        Accepts: " << row.second.second << "\n";
+                        o << "        Frequency: " << freq << "\n";
+                    }
                 }
             }
         }

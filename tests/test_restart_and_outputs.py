@@ -87,7 +87,11 @@ def test_moves_summary_matches_reference_cli(hostsim_lib, oracle, tmp_path):
     for k, (system, moveset, temp, steps, seed, needles) in enumerate([
             ("snodin_assembled.json", "moveset_standard.json", 338, 3000, 5, ["Insertion attempts", "Number of scaffold domains: 12", "Staple type: 12"]),
             ("snodin_unbound.json", "moveset_ctcb.json", 334, 2500, 6, ["Number of staples: 0", "Number of scaffold domains"]),
-            ("four_unbound.json", "moveset_four.json", 350, 2000, 7, ["Staple type"])]):
+            ("four_unbound.json", "moveset_four.json", 350, 2000, 7, ["Staple type"]),
+            # the transform / linker movetypes: three tables keyed by pairs (transform_movetypes.cpp:64-139)
+            ("snodin_assembled.json", "moveset_linker.json", 340, 2500, 8, ["Number of linker/central domains", "Number of linker/central staples",
+                                                                            "Sum/number of displacement/turns"]),
+            ("snodin_unbound.json", "moveset_linker_heavy.json", 336, 2000, 9, ["Sum/number of displacement/turns: -"])]):
         d = tmp_path / str(k)
         d.mkdir()
         text = moves_summary(hostsim_lib, oracle, d, system, moveset, temp, steps, seed)
@@ -97,7 +101,11 @@ def test_moves_summary_matches_reference_cli(hostsim_lib, oracle, tmp_path):
 
 @pytest.mark.gpu
 def test_moves_summary_matches_reference_cli_gpu(oracle, tmp_path):
-    moves_summary(None, oracle, tmp_path, "snodin_assembled.json", "moveset_standard.json", 338, 3000, 5)
+    (tmp_path / "a").mkdir()
+    (tmp_path / "b").mkdir()
+    moves_summary(None, oracle, tmp_path / "a", "snodin_assembled.json", "moveset_standard.json", 338, 3000, 5)
+    text = moves_summary(None, oracle, tmp_path / "b", "snodin_assembled.json", "moveset_linker.json", 340, 2500, 8)
+    assert "Sum/number of displacement/turns" in text
 
 
 def trj_restart(lib, oracle, tmp_path):
