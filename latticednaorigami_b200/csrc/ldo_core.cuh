@@ -362,6 +362,14 @@ struct Caps {
     static const int T = T_; // chain identities (scaffold + staple types)
     static const int HBITS = HBITS_;
     static const int H = 1 << HBITS_; // occupancy table slots
+    static const bool TRACK = false; // typed move trackers compiled in (Tracked<K>)
+};
+// The same capacities with the typed move trackers (TrackStats, ldo_moves.cuh) compiled in: a second instantiation of
+// the kernels, launched only while ldo_enable_move_trackers is on, so that the run kernel of a production launch carries
+// neither the tracker hooks nor their code. Every structure templated on the capacities has the same layout in both.
+template <class K0>
+struct Tracked : K0 {
+    static const bool TRACK = true;
 };
 
 #define LDO_HEMPTY 0x80000000u // z = -512: outside the coordinate range

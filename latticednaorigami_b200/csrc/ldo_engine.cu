@@ -184,6 +184,17 @@ struct DevPtrs {
     TrackStats* track; // [R] typed move trackers, null unless enabled (ldo_enable_move_trackers)
 };
 
+// The device pointers seen by the Tracked<K> instantiation of the kernels (same layout, ldo_core.cuh)
+template <class K>
+inline DevPtrs<Tracked<K>> tracked_ptrs(const DevPtrs<K>& p) {
+    static_assert(sizeof(DevPtrs<Tracked<K>>) == sizeof(DevPtrs<K>) && sizeof(SysState<Tracked<K>>) == sizeof(SysState<K>) &&
+                  sizeof(MoveScratch<Tracked<K>>) == sizeof(MoveScratch<K>) && sizeof(ColdScratch<Tracked<K>>) == sizeof(ColdScratch<K>) &&
+                  sizeof(Engine<Tracked<K>>) == sizeof(Engine<K>), "Tracked<K> must not change any layout");
+    DevPtrs<Tracked<K>> q;
+    memcpy(&q, &p, sizeof(q));
+    return q;
+}
+
 // ---------------------------------------------------------------------------------------------
 // Per-replica operations (host+device; executed warp-uniformly)
 // ---------------------------------------------------------------------------------------------
@@ -1412,8 +1423,15 @@ struct EngineImpl: EngineBase {
                 memcpy(tmp, st, sizeof(SysState<K>));
                 st = tmp;
             }
-            Engine<K> eng;
-            rep_execute<K>(&eng, st, ms, &P.aux[r], P, a, r);
+            if (tracked_kernels()) {
+                typedef Tracked<K> KT;
+                Engine<KT> eng;
+                rep_execute<KT>(&eng, reinterpret_cast<SysState<KT>*>(st), reinterpret_cast<MoveScratch<KT>*>(ms), &P.aux[r], tracked_ptrs(P), a, r);
+            }
+            else {
+                Engine<K> eng;
+                rep_execute<K>(&eng, st, ms, &P.aux[r], P, a, r);
+            }
         }
         (void)sync;
         return 0;
@@ -1433,10 +1451,14 @@ struct EngineImpl: EngineBase {
             else if (chk(cudaMemsetAsync(P.queue, 0, sizeof(int) * LDO_MAX_LISTS, stream))) return fail(dev_err());
             blocks = (n_items + wpb - 1) / wpb;
             if (blocks > resident_blocks) blocks = resident_blocks;
-            k_exec_staged<K><<<blocks, wpb * 32, smem, stream>>>(P, a, n_items, n_lists, grouped);
+            if (tracked_kernels()) k_exec_staged<Tracked<K>><<<blocks, wpb * 32, smem, stream>>>(tracked_ptrs(P), a, n_items, n_lists, grouped);
+            else k_exec_staged<K><<<blocks, wpb * 32, smem, stream>>>(P, a, n_items, n_lists, grouped);
         }
         else {
-            k_exec_inplace<K><<<blocks, wpb * 32, 0, stream>>>(P, a, wpb, d_recompute_tmp);
+            if (tracked_kernels()) {
+                k_exec_inplace<Tracked<K>><<<blocks, wpb * 32, 0, stream>>>(tracked_ptrs(P), a, wpb, reinterpret_cast<SysState<Tracked<K>>*>(d_recompute_tmp));
+            }
+            else k_exec_inplace<K><<<blocks, wpb * 32, 0, stream>>>(P, a, wpb, d_recompute_tmp);
         }
         if (chk(cudaGetLastError())) return fail(dev_err());
         launches++;
@@ -1445,6 +1467,14 @@ struct EngineImpl: EngineBase {
 #endif
     }
 
+    // the Tracked<K> instantiation runs while the trackers are on (with LDO_ONE_KERNEL / LDO_NO_TRACKERS: never)
+    bool tracked_kernels() const {
+#if defined(LDO_ONE_KERNEL) || defined(LDO_NO_TRACKERS)
+        return false;
+#else
+        return P.track != nullptr;
+#endif
+    }
     int enable_trackers(bool on) override {
         if (on && !P.track) {
             if (dev_malloc((void**)&P.track, sizeof(TrackStats) * R)) return fail(dev_err());
@@ -1567,6 +1597,12 @@ struct EngineImpl: EngineBase {
             if (chk(cudaFuncSetAttribute(k_exec_staged<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(per_warp * wpb)))) {
                 return fail(dev_err());
             }
+#if !defined(LDO_ONE_KERNEL) && !defined(LDO_NO_TRACKERS)
+            static_assert(sizeof(WarpSmem<Tracked<K>>) == sizeof(WarpSmem<K>), "Tracked<K> must not change the shared-memory layout");
+            if (chk(cudaFuncSetAttribute(k_exec_staged<Tracked<K>>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(per_warp * wpb)))) {
+                return fail(dev_err());
+            }
+#endif
 #ifdef LDO_SMEM_WINDOW_BASE
             {
                 unsigned* d_base = nullptr;
@@ -1581,6 +1617,13 @@ struct EngineImpl: EngineBase {
 #endif
             int per_sm = 0;
             if (chk(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_exec_staged<K>, wpb * 32, per_warp * wpb))) return fail(dev_err());
+#if !defined(LDO_ONE_KERNEL) && !defined(LDO_NO_TRACKERS)
+            {
+                int per_sm_t = 0;
+                if (chk(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm_t, k_exec_staged<Tracked<K>>, wpb * 32, per_warp * wpb))) return fail(dev_err());
+                if (per_sm_t < per_sm) per_sm = per_sm_t; // one persistent grid size for both instantiations
+            }
+#endif
             cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, device);
             if (const char* om = getenv("LDO_ORDER_MODE")) order_grouped = strcmp(om, "grouped") == 0;
             // profiling knob (profiles/sweep_occupancy.py): fewer resident blocks per SM than fit

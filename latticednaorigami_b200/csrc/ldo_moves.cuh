@@ -476,8 +476,13 @@ struct Engine {
     LDO_HD MoveStats* STATS() const { return LDO_ENG_FIELD(MoveStats*, stats); } // global memory: touched twice per move
 #ifdef LDO_NO_TRACKERS // A/B knob (profiles/ab_r2.txt): the tracker hooks compiled out
     LDO_HD TrackStats* TRK() const { return nullptr; }
-#else
+#elif defined(LDO_ONE_KERNEL) // A/B knob: one kernel with the hooks tested at run time (as before Tracked<K>)
     LDO_HD TrackStats* TRK() const { return LDO_ENG_FIELD(TrackStats*, trk); }
+#else
+    LDO_HD TrackStats* TRK() const {
+        if (!K::TRACK) return nullptr; // compile-time: the hooks exist in the Tracked<K> instantiation only
+        return LDO_ENG_FIELD(TrackStats*, trk);
+    }
 #endif
     LDO_HD const MoveSet& MS() const {
 #if defined(__CUDA_ARCH__)
