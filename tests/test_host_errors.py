@@ -81,3 +81,30 @@ def test_move_trackers_are_optional(hostsim_lib, tmp_path):
     sim.engine.enable_move_trackers(False)
     with pytest.raises(LdoError, match="not enabled"):
         sim.engine.move_trackers(0)
+
+
+def test_wall_clock_limits_stop_the_drivers(hostsim_lib, tmp_path, capfd):
+    """max_duration (simulation.cpp:574-578: checked after every step, "Maximum time allowed reached") and max_pt_dur
+    (ptmc_simulation.cpp:116-128) end a run early and cleanly: the files written so far are complete and the summary is
+    written."""
+    import time
+    opts = make_options("snodin_unbound.json", temp=340, random_seed=3, ct_steps=10 ** 9, max_duration=0.2, configs_output_freq=50,
+                        output_filebase=str(tmp_path / "ct"))
+    sim = Simulation(write_inp(str(tmp_path / "ct.inp"), opts), 1, 0, lib=hostsim_lib)
+    t0 = time.time()
+    sim.run()
+    assert time.time() - t0 < 20 and 0 < sim.step < 10 ** 9 and sim.step % 50 == 0
+    frames = [f for f in (tmp_path / "ct.trj").read_text().split("\n\n") if f.strip()]
+    assert len(frames) == sim.step // 50 and (tmp_path / "ct.moves").exists()
+    assert "Maximum time allowed reached" in capfd.readouterr().out
+
+    opts = make_options("snodin_unbound.json", simulation_type="ut_parallel_tempering", random_seed=3, temps=[330, 335, 340], num_reps=3,
+                        chem_pot_mults=[1, 1, 1], bias_mults=[1, 1, 1], stacking_mults=[1, 1, 1], exchange_interval=20, swaps=10 ** 8,
+                        max_pt_dur=0.2, configs_output_freq=20, output_filebase=str(tmp_path / "pt"))
+    sim = Simulation(write_inp(str(tmp_path / "pt.inp"), opts), 3, 0, lib=hostsim_lib)
+    t0 = time.time()
+    sim.run()
+    assert time.time() - t0 < 20 and 0 < sim.step < 20 * 10 ** 8 and sim.step % 20 == 0
+    swp = (tmp_path / "pt.swp").read_text().strip().splitlines()
+    assert len(swp) >= 2 and all(sorted(int(x) for x in row.split()) == [0, 1, 2] for row in swp[1:])
+    assert "Maximum time allowed reached" in capfd.readouterr().out
