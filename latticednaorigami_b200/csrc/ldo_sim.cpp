@@ -117,19 +117,21 @@ int bias_type_code(std::string const& t) {
 // order (ldo_exchange_pt, ldo_b200.h), which balances the temperature-dependent cost of a move across GPUs
 int ladder_slot_of(ldo_sim const& s, int b) { return b * s.n_ranks + ((b & 1) ? s.n_ranks - 1 - s.rank : s.rank); }
 
-std::string replica_filebase(ldo_sim& s, int r) {
+// File base of replica r for a run whose file base is `filebase` (the output files; the .randstate files read back)
+std::string replica_filebase_of(ldo_sim& s, std::string const& filebase, int r) {
     if (s.is_us) {
         // MWUSGCMCSimulation::setup_window_variables (us_simulation.cpp:486-501) + "_iter-n" (:107,131)
         int ladder {r / s.n_windows}, w {r % s.n_windows};
-        std::string base {s.params.m_output_filebase};
+        std::string base {filebase};
         if (s.is_mwus) base += s.window_postfix[w];
         if (s.R / s.n_windows > 1) base += "_rep-" + std::to_string(s.rank * (s.R / s.n_windows) + ladder);
         return base + s.filebase_postfix;
     }
     // PTGCMCSimulation appends "-<rank>" (ptmc_simulation.cpp:48); batches of independent replicas do the same
-    if (s.R * s.n_ranks == 1) return s.params.m_output_filebase;
-    return s.params.m_output_filebase + "-" + std::to_string(s.rank * s.R + r);
+    if (s.R * s.n_ranks == 1) return filebase;
+    return filebase + "-" + std::to_string(s.rank * s.R + r);
 }
+std::string replica_filebase(ldo_sim& s, int r) { return replica_filebase_of(s, s.params.m_output_filebase, r); }
 
 void open_output_files(ldo_sim& s) {
     InputParameters const& p = s.params;
@@ -188,8 +190,8 @@ void open_output_files(ldo_sim& s) {
 
 // GCMCSimulation constructor (simulation.cpp:204-212) + RandomEngineStateInputFile::read_state (files.cpp:232-246): with no
 // seed specified and read_rand_engine_state set, the generator continues from line restart_step (counted from 0) of
-// rand_engine_state_file. A batch of replicas reads "<file without .randstate>-<replica>.randstate", the names
-// open_output_files gives a batch.
+// rand_engine_state_file. A batch of replicas reads the names open_output_files gives a batch with the file's base
+// ("<base>-<replica>.randstate", window postfixes for the umbrella-sampling drivers).
 void restore_rng_states(ldo_sim& s) {
     InputParameters const& p = s.params;
     std::cout << "Loading random engine state\n";
@@ -197,11 +199,12 @@ void restore_rng_states(ldo_sim& s) {
     std::vector<unsigned long long> words(static_cast<size_t>(s.R) * W);
     for (int r {0}; r != s.R; r++) {
         std::string name {p.m_rand_engine_state_file};
-        if (s.R * s.n_ranks != 1) {
-            std::string const ext {".randstate"};
-            std::string stem {name};
-            if (stem.size() >= ext.size() && stem.compare(stem.size() - ext.size(), ext.size(), ext) == 0) stem.resize(stem.size() - ext.size());
-            name = stem + "-" + std::to_string(s.rank * s.R + r) + ext;
+        std::string const ext {".randstate"};
+        if (name.size() >= ext.size() && name.compare(name.size() - ext.size(), ext.size(), ext) == 0) {
+            name = replica_filebase_of(s, name.substr(0, name.size() - ext.size()), r) + ext;
+        }
+        else if (s.R * s.n_ranks != 1) {
+            throw FileError {"rand_engine_state_file of a batch of replicas must end in .randstate (read as <filebase>-<replica>.randstate)"};
         }
         std::ifstream in {name};
         if (!in) throw FileError {"Random engine state input file " + name + " does not exist"};
