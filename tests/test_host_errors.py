@@ -108,3 +108,36 @@ def test_wall_clock_limits_stop_the_drivers(hostsim_lib, tmp_path, capfd):
     swp = (tmp_path / "pt.swp").read_text().strip().splitlines()
     assert len(swp) >= 2 and all(sorted(int(x) for x in row.split()) == [0, 1, 2] for row in swp[1:])
     assert "Maximum time allowed reached" in capfd.readouterr().out
+
+
+def tracked_kernels_same_trajectory(lib, tmp_path, replicas):
+    """The Tracked<K> instantiation of the kernels (launched while the typed trackers are on) and the production one are
+    the same move code: a run that switches between them is the run that never does (Philox draws, same seed)."""
+    import numpy as np
+    from conftest import assert_state_equal
+    inp = write_inp(str(tmp_path / "k.inp"), make_options("snodin_assembled.json", "moveset_linker.json", temp=338, random_seed=17))
+    a = Simulation(inp, replicas, 0, lib=lib)
+    b = Simulation(inp, replicas, 0, lib=lib)
+    a.engine.run(600)
+    b.engine.run(150)
+    b.engine.enable_move_trackers(True)
+    b.engine.run(300)
+    b.engine.enable_move_trackers(False)
+    b.engine.run(150)
+    a.engine.assert_ok()
+    b.engine.assert_ok()
+    for r in range(replicas):
+        assert_state_equal(b.engine.state(r), a.engine.state(r), f"replica {r}")
+    ea, eb = a.engine.energies(), b.engine.energies()
+    assert np.all(np.abs(ea - eb) <= 1e-12 * np.maximum(1.0, np.abs(ea)))
+    assert np.array_equal(a.engine.rng_state(), b.engine.rng_state())
+    assert all(np.array_equal(x, y) for x, y in zip(a.engine.move_stats(), b.engine.move_stats()))
+
+
+def test_tracked_kernels_same_trajectory(hostsim_lib, tmp_path):
+    tracked_kernels_same_trajectory(hostsim_lib, tmp_path, 2)
+
+
+@pytest.mark.gpu
+def test_tracked_kernels_same_trajectory_gpu(tmp_path):
+    tracked_kernels_same_trajectory(None, tmp_path, 64)
