@@ -110,12 +110,19 @@ def test_wall_clock_limits_stop_the_drivers(hostsim_lib, tmp_path, capfd):
     assert "Maximum time allowed reached" in capfd.readouterr().out
 
 
-def tracked_kernels_same_trajectory(lib, tmp_path, replicas):
+def tracked_kernels_same_trajectory(lib, tmp_path, replicas, large=False):
     """The Tracked<K> instantiation of the kernels (launched while the typed trackers are on) and the production one are
-    the same move code: a run that switches between them is the run that never does (Philox draws, same seed)."""
+    the same move code: a run that switches between them is the run that never does (Philox draws, same seed). `large`:
+    the 168-domain raster, i.e. the in-place kernel."""
     import numpy as np
     from conftest import assert_state_equal
-    inp = write_inp(str(tmp_path / "k.inp"), make_options("snodin_assembled.json", "moveset_linker.json", temp=338, random_seed=17))
+    opts = make_options("snodin_assembled.json", "moveset_linker.json", temp=338, random_seed=17)
+    if large:
+        from synthetic import UNIFORM_OPTIONS, write_raster_system
+        # cold and concentrated enough that staples bind within the run
+        opts = make_options(temp=270, max_total_staples=168, max_type_staples=2, staple_M=1.0, random_seed=17, **UNIFORM_OPTIONS)
+        opts["origami_input_filename"] = write_raster_system(str(tmp_path / "raster.json"), 12, 14, False)
+    inp = write_inp(str(tmp_path / "k.inp"), opts)
     a = Simulation(inp, replicas, 0, lib=lib)
     b = Simulation(inp, replicas, 0, lib=lib)
     a.engine.run(600)
@@ -132,12 +139,19 @@ def tracked_kernels_same_trajectory(lib, tmp_path, replicas):
     assert np.all(np.abs(ea - eb) <= 1e-12 * np.maximum(1.0, np.abs(ea)))
     assert np.array_equal(a.engine.rng_state(), b.engine.rng_state())
     assert all(np.array_equal(x, y) for x, y in zip(a.engine.move_stats(), b.engine.move_stats()))
+    assert len(a.engine.state(0)["chain_len"]) > 1  # staples are bound: the run is not a free scaffold only
 
 
 def test_tracked_kernels_same_trajectory(hostsim_lib, tmp_path):
     tracked_kernels_same_trajectory(hostsim_lib, tmp_path, 2)
 
 
+def test_tracked_kernels_same_trajectory_in_place(hostsim_lib, tmp_path):
+    tracked_kernels_same_trajectory(hostsim_lib, tmp_path, 1, large=True)
+
+
 @pytest.mark.gpu
 def test_tracked_kernels_same_trajectory_gpu(tmp_path):
     tracked_kernels_same_trajectory(None, tmp_path, 64)
+    (tmp_path / "large").mkdir()
+    tracked_kernels_same_trajectory(None, tmp_path / "large", 16, large=True)
