@@ -190,6 +190,11 @@ def randstate_restart(lib, tmp_path):
     for bad in (dict(restart_step=9, rand_engine_state_file=str(tmp_path / "a.randstate")), dict(rand_engine_state_file=str(tmp_path / "none.randstate"))):
         with pytest.raises(Exception, match="not found|does not exist"):
             Simulation(write_inp(str(tmp_path / "bad.inp"), make_options("snodin_unbound.json", read_rand_engine_state=True, **bad)), 1, 0, lib=lib)
+    # a line that is not a Philox state of this engine (here: the text form of another generator) is refused
+    (tmp_path / "mt.randstate").write_text(" ".join(str(2 ** 40 + k) for k in range(313)) + "\n")
+    with pytest.raises(Exception, match="not a Philox state"):
+        Simulation(write_inp(str(tmp_path / "bad.inp"), make_options("snodin_unbound.json", read_rand_engine_state=True,
+                                                                      rand_engine_state_file=str(tmp_path / "mt.randstate"))), 1, 0, lib=lib)
     # a batch of replicas writes and reads <filebase>-<replica>.randstate
     d = Simulation(write_inp(str(tmp_path / "d.inp"), make_options("snodin_unbound.json", random_seed=9, ct_steps=200,
                                                                     output_filebase=str(tmp_path / "d"), **kw)), 2, 0, lib=lib)
