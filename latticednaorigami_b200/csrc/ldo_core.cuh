@@ -502,7 +502,11 @@ struct System {
     TempTables tt;
     BiasState* bsp; // per-domain order parameters (the hooks below)
     const OpsBiasConst* obp;
+    // != 0: the FourBody terms are evaluated one after the other in the reference's order and their energies added
+    // term by term (stacking_and_steric_terms); set for replicas that replay a tape or follow the reference's draw order
+    int serial_terms;
 
+    LDO_HD int SERIAL_TERMS() const { return *LDO_SMEM_AT(K, const int, SmemLayout<K>::engine + offsetof(System<K>, serial_terms), &serial_terms); }
     LDO_HD BiasState* BSP() const { return LDO_SMEM_PTR(K, BiasState, bias, bsp); }
     LDO_HD const OpsBiasConst& OBC() const {
 #if defined(__CUDA_ARCH__)
@@ -531,6 +535,7 @@ struct System {
         tt = tt_;
         bsp = nullptr;
         obp = nullptr;
+        serial_terms = 0;
     }
 
     LDO_HDN void fail(int code, int detail = 0) {
@@ -746,6 +751,7 @@ struct System {
         if (ndr_1 == ore(h1)) return;
         V3 ndr_2 = pos(h3) - pos(h2);
         if (ndr_1 != ndr_2) {
+            dc.e -= stack_energy();
             dc.stacked -= 1;
         }
     }
@@ -753,6 +759,8 @@ struct System {
         V3 ndr_1 = pos(h2) - pos(h1);
         V3 ndr_2 = pos(h3) - pos(h2);
         if (ndr_1 != ndr_2) {
+            dc.e -= stack_energy() / 2;
+            dc.e -= stack_energy() / 2;
             dc.stacked -= 1;
         }
     }
@@ -782,9 +790,13 @@ struct System {
         }
         int penalty = junction_stacking_penalty(j1, j2, j3, j4, k1, k2);
         if (penalty == 1) {
+            dc.e -= stack_energy() / 2;
+            dc.e -= stack_energy() / 2;
             dc.stacked -= 1;
         }
         else if (penalty == 2) {
+            dc.e -= stack_energy();
+            dc.e -= stack_energy();
             dc.stacked -= 2;
         }
     }
@@ -1092,6 +1104,7 @@ struct System {
             return;
         }
         if (pair_stacked(d1, d2)) {
+            dc.e += stack_energy();
             dc.stacked += 1;
             if (i == -1) backward_single_junction(dc, d1, d2);
             else forward_single_junction(dc, d1, d2);
@@ -1113,6 +1126,7 @@ struct System {
             return;
         }
         if (check_twist(d1, ndr, d2)) {
+            dc.e += stack_energy();
             dc.stacked += 1;
         }
         else {
@@ -1194,8 +1208,15 @@ struct System {
     // parts - two pairs and the middle triplet for each of the two domains, and the central triplet combinations - read
     // the domain records only and add independent terms, so each is evaluated by one lane and the contributions are
     // reduced across the warp (every term of the potential is a whole number of stacked pairs: the energy follows as
-    // stacked x stacking energy). Called warp-uniformly. The reference stops at the first violation; a violation
-    // anywhere gives the same outcome.
+    // stacked x stacking energy). Called warp-uniformly. The reference evaluates the parts in this order and stops at the
+    // first violation (origami_potential.cpp:218-223, 256-258): check_stacking hands the terms counted up to there to
+    // unassign_domain / set_checked_domain_config, which apply them whatever the flag says, so only the parts up to and
+    // including the first violated one are added (trajectories of the reference pass through configurations its own
+    // full constraint check refuses). It also adds the energies term by term (+s, -s/2 -s/2, ...: its running sum
+    // passes through 1.5 s, 2.5 s, 3 s, which round), and a move whose terms cancel leaves a residue of an ulp that
+    // decides whether p == 1 consumes a draw: replicas that replay a tape (serial_terms) therefore evaluate the parts
+    // one after the other with one running sum - bit for bit the reference's arithmetic; production replicas use
+    // the lanes and stacked x s. Both found by the replay campaign (tests/stress_replay.py).
     LDO_HDS void stacking_task(DeltaConfig& dc, int task, int di, int dj, int di_prev, int di_forw, int dj_prev, int dj_forw) const {
         if (task == 6) {
             central_triplet_combos(dc, di, dj, di_prev, di_forw, dj_prev, dj_forw);
@@ -1207,34 +1228,45 @@ struct System {
         else check_constraints_middle(dc, cd, prev, forw);
     }
     LDO_HDN void stacking_and_steric_terms(DeltaConfig& dc, int di, int dj) const {
-        int stacked = 0;
-        bool violated = false;
         // the four chain neighbours every part looks at, once (they were 20 calls of step per evaluation)
         int di_prev = bac(di), di_forw = fwd(di), dj_prev = bac(dj), dj_forw = fwd(dj);
-#if defined(__CUDA_ARCH__) && !defined(LDO_SERIAL_POTENTIAL)
         DeltaConfig part;
         part.e = 0;
         part.stacked = 0;
         part.violated = false;
-        int lane = LDO_LANE;
-        if (lane < 7) stacking_task(part, lane, di, dj, di_prev, di_forw, dj_prev, dj_forw);
-        violated = __any_sync(0xffffffffu, part.violated);
-        stacked = __reduce_add_sync(0xffffffffu, part.stacked);
+#if defined(__CUDA_ARCH__) && !defined(LDO_SERIAL_POTENTIAL)
+        // one pass with a part per lane, or (serial_terms) seven passes with the whole warp on one part after the other:
+        // one call site for both (the mode is re-read from shared memory rather than kept in a register across the parts)
+#define LDO_SERIAL_TERMS_NOW() (SERIAL_TERMS() != 0)
+#define LDO_TERMS_LANE() LDO_LANE
 #else
+#define LDO_SERIAL_TERMS_NOW() true
+#define LDO_TERMS_LANE() 0
+#endif
+        int pass = 0;
 #pragma unroll 1
-        for (int task = 0; task < 7; task++) {
-            DeltaConfig part;
-            part.e = 0;
-            part.stacked = 0;
-            part.violated = false;
-            stacking_task(part, task, di, dj, di_prev, di_forw, dj_prev, dj_forw);
-            stacked += part.stacked;
-            violated = violated || part.violated;
+        for (;;) {
+            int task = LDO_SERIAL_TERMS_NOW() ? pass : LDO_TERMS_LANE();
+            if (task < 7) stacking_task(part, task, di, dj, di_prev, di_forw, dj_prev, dj_forw);
+            // serial: stop at the first violation (origami_potential.cpp:218-223, 256-258)
+            if (!LDO_SERIAL_TERMS_NOW() || part.violated || ++pass == 7) break;
+        }
+#if defined(__CUDA_ARCH__) && !defined(LDO_SERIAL_POTENTIAL)
+        if (!LDO_SERIAL_TERMS_NOW()) {
+            // the parts after the first violated one are not evaluated by the reference: they do not count
+            const int lane = LDO_LANE;
+            unsigned vmask = __ballot_sync(0xffffffffu, part.violated);
+            int stacked = __reduce_add_sync(0xffffffffu, (lane < 7 && (vmask & ((1u << lane) - 1u)) == 0u) ? part.stacked : 0);
+            part.violated = vmask != 0u;
+            part.stacked = stacked;
+            part.e = stacked * stack_energy();
         }
 #endif
-        dc.violated = dc.violated || violated;
-        dc.stacked += stacked;
-        dc.e += stacked * stack_energy();
+#undef LDO_SERIAL_TERMS_NOW
+#undef LDO_TERMS_LANE
+        dc.violated = dc.violated || part.violated;
+        dc.stacked += part.stacked;
+        dc.e += part.e;
     }
 
     // BindingPotential::check_stacking (origami_potential.cpp:149-156)

@@ -203,6 +203,7 @@ template <class K>
 LDO_HD void rep_init_engine(Engine<K>& eng, SysState<K>* st, MoveScratch<K>* ms, RepAux* aux, const DevPtrs<K>& P, int r) {
     const Shared* sh = P.shared;
     eng.sys.init(st, &sh->sc, P.tables[aux->ctl.temp_idx]);
+    eng.sys.serial_terms = (aux->rng.tape != nullptr || sh->ms.reference_draw_order != 0) ? 1 : 0;
     if (aux->init_temp_idx >= 0 && aux->init_temp_idx != aux->ctl.temp_idx) {
         const TempTables& it = P.tables[aux->init_temp_idx];
         eng.sys.tt.init_energy = it.init_energy;

@@ -38,6 +38,28 @@ def _replay(oracle, opts, tmp_path, lib_path, seed, steps, chunks=4):
     return r, sim
 
 
+def _campaign_cases(oracle, tmp_path, lib):
+    """Runs of the replay campaign (tests/stress_replay.py) that a change of the FourBody evaluation once broke: the
+    reference's trajectory passes through configurations in which a stacking / steric constraint is violated (its
+    unchecked placements apply the terms counted up to the violation), and through moves whose stacking terms cancel up
+    to the rounding of its term-by-term sum (which decides whether the acceptance test consumes a draw)."""
+    for cyc, moveset, seed in ((False, "moveset_linker.json", 8029), (True, "moveset_linker_heavy.json", 9400)):
+        opts = _options(tmp_path, 3, 4, temp=302, max_total=8, cyclic=cyc)
+        opts["movetype_file"] = os.path.join(INPUTS, moveset)
+        _replay(oracle, opts, tmp_path, lib, seed=seed, steps=600, chunks=6)
+    for moveset, temp, seed in (("moveset_standard.json", 348, 3048), ("moveset_linker.json", 342, 4907), ("moveset_linker_heavy.json", 330, 9915)):
+        _replay(oracle, make_options("snodin_assembled.json", moveset, temp=temp), tmp_path, lib, seed=seed, steps=300, chunks=6)
+
+
+def test_campaign_cases_hostsim(hostsim_lib, oracle, tmp_path):
+    _campaign_cases(oracle, tmp_path, hostsim_lib)
+
+
+@pytest.mark.gpu
+def test_campaign_cases_gpu(oracle, tmp_path):
+    _campaign_cases(oracle, tmp_path, None)
+
+
 def test_three_quarter_turn_small_hostsim(hostsim_lib, oracle, tmp_path):
     """12-domain ThreeQuarterTurn raster (shared-memory staged path), cold enough that staples bind."""
     opts = _options(tmp_path, 3, 4, temp=300, max_total=8)
