@@ -31,6 +31,7 @@ thread_local std::string g_host_error;
 
 struct ReplicaFiles {
     std::unique_ptr<std::ofstream> trj, counts, staples, staplestates, times, ene, ops, randstate;
+    std::unique_ptr<std::ofstream> log; // m_logging_stream of the PT drivers: <filebase>-<rank>.out (ptmc_simulation.cpp:56)
     std::unique_ptr<std::ofstream> vcf, states, ores; // setup_config_files (simulation.cpp:150-180)
 };
 } // namespace
@@ -174,6 +175,9 @@ void open_output_files(ldo_sim& s) {
             for (auto const& tag: p.m_ops_to_output) *f.ops << tag << ", "; // header quirk (App. A14)
             *f.ops << "\n";
         }
+        // the log of a replica-exchange replica goes to <filebase>-<rank>.out (opened whatever logging_freq says,
+        // ptmc_simulation.cpp:56); batches of independent replicas log the same way, a single replica logs to stdout
+        if (s.is_pt || (!s.is_us && p.m_logging_freq != 0 && s.R * s.n_ranks != 1)) f.log.reset(new std::ofstream {base + ".out"});
         // RandomEngineStateOutputFile (simulation.cpp:137-144, files.cpp:781-793): one line per write, the state of the
         // replica's generator as decimal numbers - here the Philox state of ldo_get_rng_state
         if (p.m_rand_engine_state_output_freq != 0) f.randstate.reset(new std::ofstream {base + ".randstate"});
@@ -372,12 +376,61 @@ void write_outputs(ldo_sim& s, long long step) {
     }
 }
 
+// GCMCSimulation::write_log_entry (simulation.cpp:667-705) for every replica, to stdout (one replica) or the replica's
+// .out file. att0 / acc0: the move counters before the step that is reported.
+void write_log_entries(ldo_sim& s, long long step, std::vector<long long> const& att0, std::vector<long long> const& acc0) {
+    size_t n {s.movetypes.size()};
+    int nst {static_cast<int>(s.sysfile->identities.size()) - 1};
+    std::vector<long long> att(n * s.R), acc(n * s.R);
+    s.check(ldo_get_move_stats(s.eng, att.data(), acc.data()));
+    std::vector<int> counters(9 * static_cast<size_t>(s.R)), staple_counts(static_cast<size_t>(s.R) * std::max(nst, 1)), temp_idx(s.R);
+    std::vector<double> ene(5 * static_cast<size_t>(s.R)), um(s.R), bm(s.R), sm(s.R);
+    s.check(ldo_get_counters(s.eng, counters.data()));
+    s.check(ldo_get_staple_counts(s.eng, staple_counts.data()));
+    s.check(ldo_get_energies(s.eng, ene.data()));
+    s.check(ldo_get_control(s.eng, 0, s.R, temp_idx.data(), um.data(), bm.data(), sm.data()));
+    for (int r {0}; r != s.R; r++) {
+        std::ostream* o {&std::cout};
+        if (!s.files.empty() && s.files[r].log) o = s.files[r].log.get();
+        else if (s.R * s.n_ranks != 1) continue; // a batch without output files has nowhere to log to
+        int const* c {&counters[9 * static_cast<size_t>(r)]};
+        int unique {0};
+        for (int t {0}; t != nst; t++) unique += staple_counts[static_cast<size_t>(r) * nst + t] > 0 ? 1 : 0;
+        int moved {-1};
+        for (size_t i {0}; i != n; i++)
+            if (att[r * n + i] != att0[r * n + i]) moved = static_cast<int>(i);
+        bool accepted {moved >= 0 && acc[r * n + moved] != acc0[r * n + moved]};
+        *o << "Step: " << step << "\n";
+        *o << "Temperature: " << s.temps[temp_idx[r]] << "\n";
+        *o << "Bound staples: " << c[0] << "\n";
+        *o << "Unique bound staples: " << unique << "\n";
+        *o << "Fully bound domain pairs: " << c[3] << "\n";
+        *o << "Misbound domain pairs: " << c[5] << "\n";
+        *o << "Stacked domain pairs: " << c[6] << "\n";
+        // (never updated by the reference, App. A5)
+        *o << "Linear helix triplets: " << 0 << "\n";
+        *o << "Stacked junction quadruplets: " << 0 << "\n";
+        *o << "Staple counts: ";
+        for (int t {0}; t != nst; t++) *o << staple_counts[static_cast<size_t>(r) * nst + t] << " ";
+        *o << "\n";
+        *o << "System energy: " << ene[5 * static_cast<size_t>(r)] << "\n";
+        // every bias is of the move-update kind (no bias can be registered as per-domain)
+        *o << "Total external bias: " << ene[5 * static_cast<size_t>(r) + 4] << "\n";
+        *o << "Domain update external bias: " << 0 << "\n";
+        *o << "Move update external bias: " << ene[5 * static_cast<size_t>(r) + 4] << "\n";
+        *o << "Movetype: " << (moved >= 0 ? s.movetypes[moved].label : std::string {}) << "\n";
+        *o << "Accepted: " << std::boolalpha << accepted << std::noboolalpha << "\n";
+        *o << "\n";
+        o->flush();
+    }
+}
+
 long long next_output_step(ldo_sim& s, long long cur, long long end) {
     InputParameters const& p = s.params;
     if (s.files.empty()) return end;
     long long next {end};
     int freqs[] {p.m_configs_output_freq, p.m_counts_output_freq, p.m_times_output_freq, p.m_energies_output_freq, p.m_order_params_output_freq,
-                 p.m_vtf_output_freq, p.m_rand_engine_state_output_freq};
+                 p.m_vtf_output_freq, p.m_rand_engine_state_output_freq, s.is_us ? 0 : p.m_logging_freq};
     for (int f: freqs) {
         if (f == 0) continue;
         long long n {(cur / f + 1) * f};
@@ -394,7 +447,20 @@ bool simulate(ldo_sim& s, long long steps) {
         long long stop {next_output_step(s, s.step, end)};
         // chunks are bounded so that the wall-clock limit is honoured with useful granularity
         long long chunk {std::min<long long>(stop - s.step, 100000)};
-        s.check(ldo_run(s.eng, chunk, p.m_centering_freq, p.m_centering_domain, p.m_constraint_check_freq));
+        // write_log_entry names the movetype of the step it reports and whether it was accepted (simulation.cpp:628-630,
+        // 701-702): the move that lands on a logging step runs in a launch of its own, between two reads of the counters
+        bool log_here {!s.is_us && due(p.m_logging_freq, s.step + chunk) && s.step + chunk == stop};
+        std::vector<long long> att0, acc0;
+        if (log_here) {
+            if (chunk > 1) s.check(ldo_run(s.eng, chunk - 1, p.m_centering_freq, p.m_centering_domain, p.m_constraint_check_freq));
+            att0.resize(s.movetypes.size() * s.R);
+            acc0.resize(att0.size());
+            s.check(ldo_get_move_stats(s.eng, att0.data(), acc0.data()));
+            s.check(ldo_run(s.eng, 1, p.m_centering_freq, p.m_centering_domain, p.m_constraint_check_freq));
+        }
+        else {
+            s.check(ldo_run(s.eng, chunk, p.m_centering_freq, p.m_centering_domain, p.m_constraint_check_freq));
+        }
         s.step += chunk;
         std::vector<int> status(s.R), detail(s.R);
         s.check(ldo_get_status(s.eng, status.data(), detail.data()));
@@ -405,12 +471,14 @@ bool simulate(ldo_sim& s, long long steps) {
                         std::to_string(status[r]) + " (detail " + std::to_string(detail[r]) + ")"};
             }
         }
-        write_outputs(s, s.step);
         double dt {std::chrono::duration<double>(std::chrono::steady_clock::now() - s.start).count()};
         if (dt > p.m_max_duration) {
+            // (simulation.cpp:621-625: the limit is tested before the step's log entry and output)
             std::cout << "Maximum time allowed reached" << std::endl;
             return false;
         }
+        if (log_here) write_log_entries(s, s.step, att0, acc0);
+        write_outputs(s, s.step);
     }
     return true;
 }
@@ -1268,8 +1336,9 @@ NcclApi& nccl_or_throw() {
 bool exchange_round(ldo_sim& s, long long swap_i) {
     InputParameters const& p = s.params;
     long long end {s.step + p.m_exchange_interval};
-    if (next_output_step(s, s.step, end) < end) {
-        // an output step falls inside the interval: the blocking path writes it where the reference does
+    if (next_output_step(s, s.step, end) < end || due(p.m_logging_freq, end)) {
+        // an output step falls inside the interval, or the last step of the round is logged (its move runs in a launch
+        // of its own): the blocking path writes them where the reference does
         if (!simulate(s, p.m_exchange_interval)) return false;
     }
     else {

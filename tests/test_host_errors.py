@@ -95,7 +95,8 @@ def test_wall_clock_limits_stop_the_drivers(hostsim_lib, tmp_path, capfd):
     sim.run()
     assert time.time() - t0 < 20 and 0 < sim.step < 10 ** 9 and sim.step % 50 == 0
     frames = [f for f in (tmp_path / "ct.trj").read_text().split("\n\n") if f.strip()]
-    assert len(frames) == sim.step // 50 and (tmp_path / "ct.moves").exists()
+    # the limit is tested before the outputs of the step it stops at (simulation.cpp:621-625, 640-646)
+    assert len(frames) == sim.step // 50 - 1 and (tmp_path / "ct.moves").exists()
     assert "Maximum time allowed reached" in capfd.readouterr().out
 
     opts = make_options("snodin_unbound.json", simulation_type="ut_parallel_tempering", random_seed=3, temps=[330, 335, 340], num_reps=3,

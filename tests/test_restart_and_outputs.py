@@ -232,3 +232,59 @@ def test_outputs_and_restart_gpu(oracle, tmp_path):
     (tmp_path / "s").mkdir()
     randstate_restart(None, tmp_path / "s")
     exchange_against_oracle(oracle, tmp_path / "p", None, "ut", swaps=8, restart=True)
+
+
+def _log_blocks(text):
+    out, cur = [], None
+    for line in text.splitlines():
+        if line.startswith("Step: "):
+            cur = [line]
+        elif cur is not None:
+            if line == "":
+                out.append("\n".join(cur))
+                cur = None
+            else:
+                cur.append(line)
+    return out
+
+
+def test_log_entries_match_reference_cli(hostsim_lib, oracle, tmp_path, capfd):
+    """logging_freq (simulation.cpp:628-630, 667-705): the entries a constant-temperature run prints to stdout - counters,
+    staple counts, energy, biases, the movetype of the reported step and whether it was accepted - byte for byte against the
+    reference CLI on the same (replayed) run."""
+    import subprocess
+    kw = dict(temp=338, ct_steps=700, logging_freq=100, configs_output_freq=350)
+    ref_inp = write_inp(str(tmp_path / "ref.inp"), make_options("snodin_assembled.json", random_seed=5, output_filebase=str(tmp_path / "ref"), **kw))
+    ref_out = subprocess.run([oracle.CLI_PATH, "-i", ref_inp], check=True, capture_output=True, text=True).stdout
+    r = oracle.RefSystem(make_options("snodin_assembled.json", **kw))
+    r.seed(5)
+    r.simulate(700)
+    sim = Simulation(write_inp(str(tmp_path / "our.inp"), make_options("snodin_assembled.json", random_seed=1, output_filebase=str(tmp_path / "our"), **kw)),
+                     1, 0, lib=hostsim_lib)
+    sim.engine.attach_tape(0, r.tape())
+    capfd.readouterr()
+    sim.run()
+    ours = capfd.readouterr().out
+    assert (tmp_path / "our.trj").read_text() == (tmp_path / "ref.trj").read_text()  # the same run
+    a, b = _log_blocks(ref_out), _log_blocks(ours)
+    assert len(a) == 7 and a == b
+    assert len({blk.split("Movetype: ")[1] for blk in a}) > 2  # several movetypes and both outcomes are reported
+
+
+def test_replica_exchange_logs_to_out_files(hostsim_lib, tmp_path):
+    """The replica-exchange drivers log to <filebase>-<rank>.out (ptmc_simulation.cpp:56): one entry per logging_freq
+    steps and replica, with the temperature the replica holds at that step."""
+    opts = make_options("snodin_unbound.json", simulation_type="ut_parallel_tempering", random_seed=3, temps=[330, 335, 340], num_reps=3,
+                        chem_pot_mults=[1, 1, 1], bias_mults=[1, 1, 1], stacking_mults=[1, 1, 1], exchange_interval=50, swaps=6,
+                        max_pt_dur=1e9, logging_freq=50, output_filebase=str(tmp_path / "pt"))
+    sim = Simulation(write_inp(str(tmp_path / "pt.inp"), opts), 3, 0, lib=hostsim_lib)
+    sim.run()
+    temps_seen = []
+    for k in range(3):
+        blocks = _log_blocks((tmp_path / f"pt-{k}.out").read_text())
+        assert [b.splitlines()[0] for b in blocks] == [f"Step: {50 * (i + 1)}" for i in range(6)]
+        assert all(len(b.splitlines()) == 16 for b in blocks)
+        temps_seen.append([b.splitlines()[1] for b in blocks])
+    # at every logged step the three replicas hold the three temperatures of the ladder
+    for i in range(6):
+        assert sorted(t[i] for t in temps_seen) == ["Temperature: 330", "Temperature: 335", "Temperature: 340"]
