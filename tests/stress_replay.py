@@ -15,6 +15,7 @@ t_end = time.time() + float(sys.argv[1])
 def run(name, opts, seed, chunks, steps):
     r = o.RefSystem(opts); r.seed(seed)
     sim = Simulation(conftest.write_inp(os.path.join(tmp, f"{seed}.inp"), opts), 1, 0, lib=conftest.load_hostsim())
+    if os.environ.get("LDO_STRESS_TRACKERS"): sim.engine.enable_move_trackers(True)  # the Tracked<K> instantiation
     for k in range(chunks):
         r.tape(clear=True); r.simulate(steps); tape = r.tape(clear=True)
         sim.engine.attach_tape(0, tape); sim.engine.run(steps, 0, 0, 0)
