@@ -390,9 +390,13 @@ void write_log_entries(ldo_sim& s, long long step, std::vector<long long> const&
     s.check(ldo_get_energies(s.eng, ene.data()));
     s.check(ldo_get_control(s.eng, 0, s.R, temp_idx.data(), um.data(), bm.data(), sm.data()));
     for (int r {0}; r != s.R; r++) {
-        std::ostream* o {&std::cout};
-        if (!s.files.empty() && s.files[r].log) o = s.files[r].log.get();
+        std::ostream* sink {&std::cout};
+        if (!s.files.empty() && s.files[r].log) sink = s.files[r].log.get();
         else if (s.R * s.n_ranks != 1) continue; // a batch without output files has nowhere to log to
+        // formatted in a stream of its own: the entry must not inherit whatever precision / flags the process has left
+        // on std::cout (the umbrella-sampling summaries set some)
+        std::ostringstream entry;
+        std::ostream* o {&entry};
         int const* c {&counters[9 * static_cast<size_t>(r)]};
         int unique {0};
         for (int t {0}; t != nst; t++) unique += staple_counts[static_cast<size_t>(r) * nst + t] > 0 ? 1 : 0;
@@ -421,7 +425,8 @@ void write_log_entries(ldo_sim& s, long long step, std::vector<long long> const&
         *o << "Movetype: " << (moved >= 0 ? s.movetypes[moved].label : std::string {}) << "\n";
         *o << "Accepted: " << std::boolalpha << accepted << std::noboolalpha << "\n";
         *o << "\n";
-        o->flush();
+        *sink << entry.str();
+        sink->flush();
     }
 }
 
